@@ -1,0 +1,152 @@
+"""TEST INFRASTRUCTURE ONLY.  Mints tests/golden/*.npz from the LIVE reference (/root/reference imported
+through oracle/compat.py).  Run in the build container:  python -m oracle.gen_golden
+The fixtures pin (a) oracle/tokenizer_ref.py + the CUDA tokenizer, (b) oracle/model_ref.py + the CUDA path
+on the TINY config with `synth_state_dict(TINY, seed=0)` weights (regenerated bit-identically at test time).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import compat  # noqa: E402
+from spatialvla_b200.configs import get_config_dict, default_intrinsic_224  # noqa: E402
+from spatialvla_b200.weights import synth_state_dict  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+BEGIN = 257153
+
+
+class FakeHFTokenizer:
+    """Minimal stand-in for the Gemma tokenizer surface the reference tokenizer touches
+    (add_tokens / convert_tokens_to_ids / vocab_size / __len__): base vocab 257 153."""
+
+    def __init__(self, base=BEGIN):
+        self.base = base
+        self.added = {}
+
+    @property
+    def vocab_size(self):
+        return self.base
+
+    def __len__(self):
+        return self.base + len(self.added)
+
+    def add_tokens(self, toks, special_tokens=False):
+        n = 0
+        for t in toks:
+            if t not in self.added:
+                self.added[t] = self.base + len(self.added)
+                n += 1
+        return n
+
+    def convert_tokens_to_ids(self, tok):
+        if isinstance(tok, (list, tuple, np.ndarray)):
+            return [self.added[str(t)] for t in tok]
+        return self.added[str(tok)]
+
+
+def edge_case_actions(pol):
+    rows = [np.zeros(7), np.ones(7), -np.ones(7), np.array([1, -1, 1, -1, 1, -1, 0.5]),
+            np.array([0, 0, 1, 0, 0, 0, 0.49999]), np.array([0, 0, -1, 0.3, 0.3, 0.3, 1.0]),
+            np.array([1e-300, 0, 0, 0, 0, 0, 0]), np.array([2.5, -3.0, 0.1, 1.5, -1.5, 0.0, 7.0])]
+    for key in ("roll_bins", "pitch_bins", "yaw_bins"):
+        for e in pol["rotation"][key]:
+            for d in (0.0, 1e-12, -1e-12):
+                r = np.zeros(7)
+                r[3:6] = e + d
+                rows.append(r)
+    # points whose radius / polar angle sit exactly on translation edges
+    for e in pol["translation"]["r_bins"]:
+        rows.append(np.array([min(e, 1.0), 0, 0, 0, 0, 0, 0]))
+        rows.append(np.array([0, 0, min(e, 1.0), 0, 0, 0, 0]))
+    for e in pol["translation"]["theta_bins"]:
+        rows.append(np.array([0.5 * np.sin(e), 0, 0.5 * np.cos(e), 0, 0, 0, 0]))
+    for e in pol["translation"]["phi_bins"]:
+        rows.append(np.array([0.5 * np.cos(e), 0.5 * np.sin(e), 0.1, 0, 0, 0, 1]))
+    return np.stack(rows).astype(np.float64)
+
+
+def gen_tokenizer():
+    _, tok_mod, _, _ = compat.import_reference()
+    action_cfg = json.load(open(os.path.join(compat.REFERENCE_ROOT, "scripts", "action_config.json")))
+    gs = json.load(open(os.path.join(compat.REFERENCE_ROOT, "scripts", "gs_spatialvla_plus.json")))
+    for name, gs_params, min_sigma in (("gauss", gs, 0.5), ("uniform", None, 0.0)):
+        tk = tok_mod.SpatialActionTokenizer(FakeHFTokenizer(), num_bins=action_cfg["num_bins"], gs_params=gs_params,
+                                            use_spherical=True, min_sigma=min_sigma)
+        pol = tk.bin_policy
+        assert tk.action_token_begin_idx == BEGIN and tk.vocab_size == 8194
+        rng = np.random.default_rng(0)
+        acts = rng.uniform(-1, 1, size=(20000, 7))
+        acts[:, 6] = rng.integers(0, 2, size=20000)
+        acts = np.concatenate([acts, edge_case_actions(pol)], 0)
+        toks = tk(acts)
+        ids = np.vectorize(lambda s: int(s[7:12]))(toks).astype(np.int32)       # '<ACTION%05d>' -> local id
+        all_ids = np.stack([np.arange(4096) , np.arange(4096) + 4096,
+                            8192 + (np.arange(4096) % 2)], 1) + BEGIN
+        dec_all = tk.decode_token_ids_to_actions(all_ids)
+        oob = np.array([[BEGIN - 5, BEGIN + 100, BEGIN + 9000], [BEGIN + 5000, BEGIN + 10, 0],
+                        [0, 0, 0], [BEGIN + 8193, BEGIN + 8193, BEGIN + 8193]])
+        dec_oob = tk.decode_token_ids_to_actions(oob)
+        edges = {f"edge_{k}": np.asarray(v, dtype=np.float64) for bt in pol.values() for k, v in bt.items()}
+        np.savez_compressed(os.path.join(GOLD, f"tokenizer_{name}.npz"), actions=acts, local_ids=ids,
+                            decode_ids=all_ids.astype(np.int64), decode_actions=dec_all, oob_ids=oob.astype(np.int64),
+                            oob_actions=dec_oob, begin=np.int64(BEGIN), min_sigma=np.float64(min_sigma), **edges)
+        print(f"tokenizer_{name}: {acts.shape[0]} actions, ids range {ids.min()}..{ids.max()}")
+
+
+def tiny_inputs(B=2, T=6, seed=0):
+    cfg = get_config_dict("tiny")
+    g = torch.Generator().manual_seed(seed)
+    px_u8 = torch.randint(0, 256, (B, 3, 224, 224), generator=g, dtype=torch.uint8)
+    # smooth the noise a little so that resampling paths see structure, keep exact u8 storage
+    px_u8 = (torch.nn.functional.avg_pool2d(px_u8.float(), 5, 1, 2)).round().clamp(0, 255).to(torch.uint8)
+    ids = torch.cat([torch.full((B, 256), cfg["image_token_index"]), torch.full((B, 1), 2),
+                     torch.randint(3, 1000, (B, T), generator=g), torch.full((B, 1), 108)], 1)
+    K = torch.tensor(default_intrinsic_224(), dtype=torch.float32)
+    return cfg, px_u8, ids, K
+
+
+def gen_model(n_new=6):
+    cfg, px_u8, ids, K = tiny_inputs()
+    px = px_u8.float() / 255.0
+    model = compat.build_reference_model(cfg)
+    sd = synth_state_dict(cfg, seed=0)
+    model.load_state_dict(sd, strict=True)
+    lo, hi = cfg["action_token_begin_idx"], cfg["action_token_begin_idx"] + cfg["spatial_token_num"]
+    from oracle.model_ref import process_zoe
+    with torch.no_grad():
+        sig = model.vision_tower((px - 0.5) / 0.5).last_hidden_state
+        zo = model.vision_zoe_model(pixel_values=process_zoe(px), output_hidden_states=False)
+        depth384 = zo.predicted_depth
+        depth224 = torch.nn.functional.interpolate(depth384.unsqueeze(1), size=(286, 286), mode="bicubic",
+                                                   align_corners=True)[..., 31:-31, 31:-31]
+        xyz = model.backproject_patch(K, depth224, patch_size=14, reso=cfg["ego3d_patch_reso"])
+        pos3d = model.position_embedding_3d(xyz)
+        feats = model.get_image_features(px, K)
+    toks, logits = compat.reference_greedy(model, ids, px, K, n_new, lo, hi)
+    # teacher-forced second pass on a fixed token stream (tests feed the same stream to both sides)
+    forced = toks.clone()
+    toks_f, logits_f = compat.reference_greedy(model, ids, px, K, n_new, lo, hi, forced_tokens=forced)
+    assert torch.equal(toks, toks_f)
+    np.savez_compressed(
+        os.path.join(GOLD, "tiny_model.npz"),
+        pixel_u8=px_u8.numpy(), input_ids=ids.numpy(), intrinsic=K.numpy(),
+        siglip=sig[:, ::4].numpy(), depth384_s4=depth384[:, ::4, ::4].numpy(),
+        depth384_mean=depth384.mean((1, 2)).numpy(), depth384_std=depth384.std((1, 2)).numpy(),
+        domain_logits=zo.domain_logits.numpy(), xyz=xyz.numpy(), pos3d=pos3d[:, ::4].numpy(),
+        image_features=feats[:, ::4].numpy(), tokens=toks.numpy(), logits=logits.numpy().astype(np.float32),
+        n_new=np.int64(n_new))
+    print("tiny_model: tokens", toks.tolist(), "domain_logits", zo.domain_logits.tolist())
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    gen_tokenizer()
+    gen_model()

@@ -1,0 +1,212 @@
+/*
+ * spatialvla_b200 -- C ABI of the B200 (sm_100a) kernels behind the SpatialVLA `predict_action` path.
+ *
+ * The reference (tomputer-g/SpatialVLA) is pure Python on top of torch/ATen; it has no FFI of its own.  The
+ * drop-in boundary is therefore its HuggingFace-facing Python API (SpatialVLAProcessor,
+ * SpatialVLAForConditionalGeneration.predict_action, SpatialActionTokenizer), mirrored in
+ * spatialvla_b200/*.py, and THIS header is the thin C ABI those classes call through ctypes: every entry
+ * point replaces the torch op sequence of the reference lines cited next to it.
+ *
+ * Conventions: all pointers are DEVICE pointers owned by the caller unless the name ends in `_host`;
+ * every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host
+ * synchronisation and returns 0 on success or a negative code (`svla_last_error()` gives the text).
+ * bf16 = raw uint16 storage.  Row-major everywhere; images/feature maps are NHWC.
+ */
+#ifndef SPATIALVLA_B200_H
+#define SPATIALVLA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVLA_ABI_VERSION 1
+
+const char* svla_last_error(void);
+int svla_abi_version(void);
+/* Number of kernels launched by this library since load (bench.py's `gpu_launches`). */
+long long svla_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * G1: D = epilogue(A[M,K] * W[N,K]^T)  -- tcgen05.mma (cta_group::1, 128xBNx16, fp32 accumulators in TMEM),
+ * operands staged by TMA (SWIZZLE_128B), warp-specialised persistent kernel.
+ * Replaces every nn.Linear / 1x1 conv / patch-embed conv / 3x3 conv of the path:
+ *   model/modeling_gemma2.py:80-92,351-354,993 ; HF siglip/modeling_siglip.py:124-130,252-327 ;
+ *   HF beit/modeling_beit.py:209,225-306,400-440 ; HF zoedepth/modeling_zoedepth.py:129-149,199-216,301-303,
+ *   349-352 ; model/modeling_spatialvla.py:59-64,121-128.
+ * value = act(alpha * acc + bias[n]) * colscale[n] + res_bf16[m,n] + res2_bf16[m,n] + res_f32[res_mod ? m % res_mod : m, n]
+ * --------------------------------------------------------------------------------------------------- */
+enum {
+  SVLA_ACT_NONE = 0, SVLA_ACT_GELU_TANH = 1, SVLA_ACT_GELU_ERF = 2, SVLA_ACT_RELU = 3,
+  SVLA_ACT_SOFTCAP = 4, /* act_param * tanh(x / act_param) */
+  SVLA_ACT_SOFTPLUS = 5
+};
+enum {
+  SVLA_GEMM_GEGLU = 1,       /* out[m, n/2] = gelu_tanh(v[m,2j]) * v[m,2j+1] (gate/up rows interleaved in W) */
+  SVLA_GEMM_ACCUM_F32 = 2,   /* out_f32[m,n] += value (fp32 residual stream read-modify-write)            */
+  SVLA_GEMM_CONV3X3 = 4      /* A is an NHWC tensor, implicit 3x3/pad 1/stride 1 convolution               */
+};
+
+typedef struct SvlaGemmArgs {
+  const void* a;          /* bf16 [M, lda] (or NHWC [nb, h, w, c] in conv mode) */
+  const void* w;          /* bf16 [N, ldw]; conv mode: [N][9][cpad] with cpad = roundup(c, 64) */
+  const float* bias;      /* fp32 [N] or NULL */
+  const float* colscale;  /* fp32 [N] or NULL */
+  const void* res_bf16;   /* bf16 [M, ldo] residual or NULL */
+  const void* res2_bf16;  /* second bf16 [M, ldo] residual or NULL */
+  const float* res_f32;   /* fp32 [M or res_mod, ldo] residual or NULL */
+  int64_t res_mod;        /* > 0: res_f32 row = m % res_mod (learned position embeddings broadcast over the batch) */
+  void* out_bf16;         /* bf16 [M, ldo] or NULL */
+  float* out_f32;         /* fp32 [M, ldo] or NULL */
+  void* out_relu_bf16;    /* bf16 [M, ldo]: relu(value) or NULL */
+  int64_t m, n, k;
+  int64_t lda, ldw, ldo;  /* in elements */
+  int32_t nb, h, wd, c;   /* conv mode geometry */
+  float alpha;
+  float act_param;
+  int32_t act;
+  int32_t flags;
+  int32_t block_n;        /* 0 = auto; else 32 | 64 | 128 | 256 */
+  int32_t impl;           /* 0 = tcgen05 (product path); 1 = SIMT debugging kernel (tests only) */
+} SvlaGemmArgs;
+
+int svla_gemm(const SvlaGemmArgs* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * G2: softmax(scale * Q K^T [softcap] [+ relpos bias] [mask]) V, flash style, fp32 softmax.
+ *   model/modeling_gemma2.py:169-195 (GQA, tanh soft-capping; bidirectional prefill per
+ *   model/modeling_spatialvla.py:291-297) ; HF siglip/modeling_siglip.py:252-312 ;
+ *   HF beit/modeling_beit.py:225-306,511-590 (relative position bias looked up from the table on the fly) ;
+ *   HF zoedepth/modeling_zoedepth.py:783-845.
+ * q: element (b, s, h, d) at q + b*q_bs + s*q_ss + h*D + d   (strides in elements), same for k/v/out.
+ * --------------------------------------------------------------------------------------------------- */
+typedef struct SvlaAttnArgs {
+  const void* q; const void* k; const void* v; void* out;       /* bf16 */
+  int64_t q_bs, q_ss, k_bs, k_ss, v_bs, v_ss, o_bs, o_ss;
+  int32_t batch, hq, hkv, sq, sk, d;
+  float scale;            /* applied before softcap */
+  float softcap;          /* 0 = none */
+  int32_t causal;         /* 1: key j visible to query i iff j <= i + (sk - sq) */
+  const float* relpos_table; /* fp32 [(2*win-1)^2+3, hq] or NULL (BEiT) */
+  int32_t relpos_win;
+} SvlaAttnArgs;
+
+int svla_attention(const SvlaAttnArgs* args, void* stream);
+
+/* G3: single-query decode attention over the KV cache (model/modeling_gemma2.py:387-395,169-195).
+ * q bf16 [B, hq*D]; kcache/vcache bf16 [B, smax, hkv, D]; attends to positions [0, ctx). out bf16 [B, hq*D] */
+int svla_decode_attention(const void* q, const void* kcache, const void* vcache, void* out, int batch, int hq,
+                          int hkv, int d, int smax, int ctx, float scale, float softcap, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Memory-bound fused kernels
+ * --------------------------------------------------------------------------------------------------- */
+/* M1 LayerNorm over fp32 rows (HF siglip :330-362, beit :448-508, zoedepth :843-877, spatialvla :59-64).
+ * out_bf16 / out_f32 may each be NULL; relu applies to both outputs. */
+int svla_layernorm(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int cols,
+                   void* out_bf16, float* out_f32, int relu, void* stream);
+
+/* M2 Gemma2 sandwich norm (model/modeling_gemma2.py:60-77,475-496):
+ *   if branch:  x += rms(branch) * (1 + w_post)        (x fp32 residual, updated in place)
+ *   if w_pre:   out_bf16 = rms(x) * (1 + w_pre)                                                     */
+int svla_rmsnorm_residual(float* x, const float* branch, const float* w_post, const float* w_pre, float eps,
+                          int64_t rows, int cols, void* out_bf16, void* stream);
+
+/* M3 RoPE + KV-cache write (model/modeling_gemma2.py:95-154,376-395; positions 1-indexed per
+ * model/modeling_spatialvla.py:371-372). qkv bf16 [B*S, (hq+2hkv)*D] -> q_out bf16 [B*S, hq*D] (rotated),
+ * kcache/vcache bf16 [B, smax, hkv, D] rows [pos0, pos0+S). */
+int svla_rope_kv(const void* qkv, void* q_out, void* kcache, void* vcache, int batch, int s, int hq, int hkv,
+                 int d, int smax, int pos0, float theta, void* stream);
+
+/* M6 embedding gather (model/modeling_spatialvla.py:361-387, model/modeling_gemma2.py:741-742):
+ * text ids -> embed (bf16 [V,H]); ids in [act_lo, act_lo+n_act) -> spatial_embed (bf16 [n_act,H]);
+ * the k-th image token of row b -> image_feats fp32 [B, n_img, H] row k; everything * sqrt(H) -> x fp32 */
+int svla_embed_tokens(const int64_t* ids, const void* embed, const void* spatial_embed, const float* image_feats,
+                      float* x, int batch, int s, int hdim, int64_t vocab, int64_t image_token, int64_t act_lo,
+                      int64_t n_act, int n_img, float normalizer, int* status_flag, void* stream);
+
+/* M7 argmax over fp32 logits rows (greedy step of HF generate, restricted to the action slice):
+ * out_ids[b*out_stride] = argmax_j logits[b, j] + id_offset (first max wins, like torch.argmax) */
+int svla_argmax_rows(const float* logits, int64_t rows, int64_t cols, int64_t ld, int64_t id_offset,
+                     int64_t* out_ids, int64_t out_stride, void* stream);
+
+/* M9 image preprocessing.
+ * siglip: (x-0.5)/0.5 + im2col for the 14x14/14 patch conv (model/modeling_spatialvla.py:309;
+ *         HF siglip :124-130,176-187): px fp32 [B,3,224,224] -> a bf16 [B*256, kpad] (kpad >= 588, zero padded)
+ * zoe   : reflect-pad 31 -> bicubic(align_corners) 286->384 -> (x-0.5)/0.5 -> im2col 16x16/16
+ *         (model/modeling_spatialvla.py:99-110; HF beit :209): -> a bf16 [B*576, 768] */
+int svla_siglip_patchify(const float* px, void* a, int batch, int kpad, void* stream);
+int svla_zoe_patchify(const float* px, void* a, int batch, void* stream);
+
+/* BEiT token assembly: x[b,0,:] = cls, x[b,1+i,:] = patches[b*n+i,:] (HF beit :190-222). fp32 */
+int svla_beit_assemble(const float* patches, const float* cls, float* x, int batch, int n, int c, void* stream);
+
+/* ZoeDepth reassemble read-out 'project' input (HF zoedepth :55-110): a bf16 [B*n, 2c] = [tok_i | cls] */
+int svla_readout_concat(const float* hs, void* a, int batch, int n, int c, void* stream);
+
+/* ConvTranspose2d with kernel == stride == f as GEMM + this scatter (HF zoedepth :129-149):
+ * g bf16 [B*h*w, f*f*c] (col = (i*f+j)*c + co) -> out bf16 NHWC [B, h*f, w*f, c] */
+int svla_pixel_shuffle(const void* g, void* out, int batch, int h, int w, int c, int f, void* stream);
+
+/* im2col for the single 3x3 stride-2 pad-1 conv of the neck (HF zoedepth :129-149):
+ * x bf16 NHWC [B,h,w,c] -> a bf16 [B*(h/2)*(w/2), 9*c] (col = tap*c + ci) */
+int svla_im2col3x3_s2(const void* x, void* a, int batch, int h, int w, int c, void* stream);
+
+/* Bilinear resize of NHWC bf16 maps, align_corners=True (HF zoedepth :264-272,350,716-728,1094-1095):
+ * out = resize(x) [+ add (same shape as out)], optional relu copy. */
+int svla_bilinear_nhwc(const void* x, const void* add, void* out, void* out_relu, int batch, int h, int w, int c,
+                       int oh, int ow, void* stream);
+
+/* elementwise relu(x) -> out (bf16), n elements (pre-activation residual units, HF zoedepth :182-238) */
+int svla_relu_bf16(const void* x, void* out, int64_t n, void* stream);
+
+/* ZoeDepth patch-transformer input (HF zoedepth :905-963): e fp32 [B, 1+n, c]: row 0 = PE[0] (zero CLS),
+ * row 1+i = conv[b*n+i] + PE[1+i] with the 1-D sinusoidal encoding. conv fp32 [B*n, c]; e_bf16 = bf16 copy */
+int svla_zoe_router_embed(const float* conv, float* e, void* e_bf16, int batch, int n, int c, void* stream);
+
+/* ZoeDepth metric-bins tail (HF zoedepth :551-570,665-746): softplus attractors, bilinear(align_corners)
+ * upsampling of the previous bin centres, inverse-attractor update with alpha=300, gamma=2, mean over na.
+ * attr bf16 [B*oh*ow, na] (pre-softplus), prev fp32 NHWC [B, h, w, nbins] -> out fp32 NHWC [B, oh, ow, nbins] */
+int svla_zoe_attractor(const void* attr, const float* prev, float* out, int batch, int h, int w, int oh, int ow,
+                       int na, int nbins, void* stream);
+
+/* softplus(x) bf16 -> fp32 (seed bin regressor, HF zoedepth :494-547) */
+int svla_softplus_f32(const void* x, float* out, int64_t n, void* stream);
+
+/* ZoeDepth conditional log-binomial + expectation (HF zoedepth :383-491,1094-1101) at full resolution:
+ * t bf16 [B*oh*ow, nh] = W_a*last (no bias); e bf16 NHWC [B, h, w, nh] = W_b*bin_embedding (half res);
+ * b1 fp32 [nh]; w2 fp32 [4, nh]; b2 fp32 [4]; bins fp32 NHWC [B, h, w, nbins]
+ * -> depth fp32 [B, oh, ow] = sum_k softmax_k(logbinom(p)/T) * bilinear(bins)_k */
+int svla_zoe_depth_tail(const void* t, const void* e, const float* b1, const float* w2, const float* b2,
+                        const float* bins, float* depth, int batch, int h, int w, int oh, int ow, int nh,
+                        int nbins, float min_temp, float max_temp, void* stream);
+
+/* M5 Ego3D (model/modeling_spatialvla.py:41-97,181-223,318-323): depth384 fp32 [B,384,384] ->
+ * bicubic(align_corners) 384->286, crop 31 -> 7x7 area mean -> inv(K) uv d -> xyz fp32 [B,256,12]
+ * -> [(x-c)/2, sin(2^k .), cos(2^k .)] -> enc bf16 [B*256, kpad] (kpad >= 204, zero padded).
+ * intrinsic fp32 [3,3] (k_stride = 0) or [B,3,3] (k_stride = 9). */
+int svla_ego3d_encode(const float* depth384, const float* intrinsic, int k_stride, float* xyz, void* enc, int batch,
+                      int kpad, int n_freqs, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * M8 SpatialActionTokenizer grid lookup and inverse (model/action_tokenizer.py:105-137,177-202,227-243,
+ * 305-333), float64 arithmetic, bit-exact ids.
+ * edges: 6 fp64 arrays concatenated [theta(nt+1) | phi(np+1) | r(nr+1) | roll | pitch | yaw];
+ * nbins int32[7] = {theta, phi, r, roll, pitch, yaw, gripper}.
+ * encode: actions fp64 [n,7] -> ids int32 [n,3] LOCAL ids (0..vocab-1); decode: ids int64 [n,3]
+ * (global ids, `begin` subtracted inside like the reference) -> actions fp64 [n,7].
+ * The `_host` variants take HOST buffers and do the H2D/D2H copies themselves (the e2e call). */
+int svla_tok_encode(const double* actions, const double* edges, const int32_t* nbins, int32_t* ids, int64_t n,
+                    double min_action, double max_action, void* stream);
+int svla_tok_decode(const int64_t* ids, const double* edges, const int32_t* nbins, int64_t begin, double* actions,
+                    int64_t n, void* stream);
+int svla_tok_encode_host(const double* actions_host, const double* edges_host, const int32_t* nbins_host,
+                         int32_t* ids_host, int64_t n, double min_action, double max_action);
+int svla_tok_decode_host(const int64_t* ids_host, const double* edges_host, const int32_t* nbins_host, int64_t begin,
+                         double* actions_host, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPATIALVLA_B200_H */

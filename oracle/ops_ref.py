@@ -1,0 +1,333 @@
+"""TEST INFRASTRUCTURE ONLY.  Per-op torch (CPU, fp32 arithmetic) re-statement of every C-ABI kernel with the same
+Python signatures as spatialvla_b200.ops.CudaOps.  Two uses, both in tests/:
+  * the per-kernel oracle of the `-m gpu` parity tests (CUDA op vs this, same inputs);
+  * injected as the op backend to run the host orchestration (spatialvla_b200/engine.py) on CPU and compare it
+    with oracle/model_ref.py and the golden vectors -- the product never imports this file.
+Rounding points (bf16 outputs) mirror the kernels so the CPU run predicts the B200 path's numerics.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from spatialvla_b200._lib import (ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_RELU, ACT_SOFTCAP, ACT_SOFTPLUS)
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _act(v, act, p):
+    if act == ACT_GELU_TANH:
+        return F.gelu(v, approximate="tanh")
+    if act == ACT_GELU_ERF:
+        return F.gelu(v)
+    if act == ACT_RELU:
+        return F.relu(v)
+    if act == ACT_SOFTCAP:
+        return p * torch.tanh(v / p)
+    if act == ACT_SOFTPLUS:
+        return F.softplus(v)
+    return v
+
+
+def _rows(t):
+    return t if t.dim() == 2 else t.view(-1, t.shape[-1])
+
+
+class RefOps:
+    name = "ref"
+
+    def __init__(self, device="cpu"):
+        self.device = torch.device(device)
+        self.launches = 0
+
+    def empty(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def launch_count(self):
+        return self.launches
+
+    # ---- G1
+    def gemm(self, a, w, *, n=None, k=None, out_bf16=None, out_f32=None, out_relu=None, bias=None, colscale=None,
+             res_bf16=None, res2_bf16=None, res_f32=None, res_mod=0, act=ACT_NONE, act_param=0.0, alpha=1.0,
+             geglu=False, accumulate=False, conv=None, block_n=0, impl=None):
+        self.launches += 1
+        N = int(n if n is not None else w.shape[0])
+        wf = w[:N].float()
+        if conv is not None:
+            nb, h, wd, c = conv
+            cpad = (c + 63) // 64 * 64
+            x = a.float().view(nb, h, wd, c).permute(0, 3, 1, 2)
+            w4 = wf.view(N, 9, cpad)[:, :, :c].reshape(N, 3, 3, c).permute(0, 3, 1, 2)
+            acc = F.conv2d(x, w4, None, padding=1).permute(0, 2, 3, 1).reshape(nb * h * wd, N)
+        else:
+            K = int(k if k is not None else a.shape[1])
+            acc = a[:, :K].float() @ wf[:, :K].t()
+        v = acc * alpha
+        if bias is not None:
+            v = v + bias[:N]
+        if geglu:
+            g, u = v[:, 0::2], v[:, 1::2]
+            _rows(out_bf16)[:, : N // 2] = (F.gelu(g, approximate="tanh") * u).to(BF16)
+            return
+        v = _act(v, act, act_param)
+        if colscale is not None:
+            v = v * colscale[:N]
+        if res_bf16 is not None:
+            v = v + _rows(res_bf16)[:, :N].float()
+        if res2_bf16 is not None:
+            v = v + _rows(res2_bf16)[:, :N].float()
+        if res_f32 is not None:
+            r = _rows(res_f32)[:, :N]
+            if res_mod:
+                idx = torch.arange(v.shape[0]) % res_mod
+                r = r[idx]
+            v = v + r
+        if out_f32 is not None:
+            o = _rows(out_f32)
+            if accumulate:
+                v = v + o[:, :N]
+            o[:, :N] = v
+        if out_bf16 is not None:
+            _rows(out_bf16)[:, :N] = v.to(BF16)
+        if out_relu is not None:
+            _rows(out_relu)[:, :N] = F.relu(v).to(BF16)
+
+    # ---- G2 / G3
+    @staticmethod
+    def _strided(t, bs, ss, batch, s, heads, d):
+        """(B, S, H, D) view over the tensor's own storage, exactly the addressing the kernel uses."""
+        return t.as_strided((batch, s, heads, d), (bs, ss, d, 1), t.storage_offset())
+
+    def attention(self, q, k, v, out, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
+                  scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0):
+        self.launches += 1
+        Q = self._strided(q, *q_strides, batch, sq, hq, d).float().permute(0, 2, 1, 3)
+        K = self._strided(k, *k_strides, batch, sk, hkv, d).float().permute(0, 2, 1, 3).repeat_interleave(hq // hkv, 1)
+        V = self._strided(v, *v_strides, batch, sk, hkv, d).float().permute(0, 2, 1, 3).repeat_interleave(hq // hkv, 1)
+        s = (Q @ K.transpose(-1, -2)) * scale
+        if softcap:
+            s = softcap * torch.tanh(s / softcap)
+        if relpos_table is not None:
+            from oracle.model_ref import beit_rel_pos_bias
+            s = s + beit_rel_pos_bias(relpos_table, relpos_win)[None]
+        if causal:
+            m = torch.arange(sk)[None, :] > (torch.arange(sq)[:, None] + (sk - sq))
+            s = s.masked_fill(m, float("-inf"))
+        # the kernel rounds the un-normalised probabilities to bf16 and divides by the fp32 row sum
+        mx = s.max(-1, keepdim=True).values
+        e = torch.exp(s - mx)
+        o = (e.to(BF16).float() @ V) / e.sum(-1, keepdim=True)
+        self._strided(out, *o_strides, batch, sq, hq, d).copy_(o.permute(0, 2, 1, 3).to(BF16))
+
+    def decode_attention(self, q, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, scale, softcap=0.0):
+        self.launches += 1
+        Q = q.float().view(batch, hq, 1, d)
+        K = kcache.float().view(batch, smax, hkv, d)[:, :ctx].permute(0, 2, 1, 3).repeat_interleave(hq // hkv, 1)
+        V = vcache.float().view(batch, smax, hkv, d)[:, :ctx].permute(0, 2, 1, 3).repeat_interleave(hq // hkv, 1)
+        s = (Q @ K.transpose(-1, -2)) * scale
+        if softcap:
+            s = softcap * torch.tanh(s / softcap)
+        p = torch.softmax(s, -1).to(BF16).float()
+        out.view(batch, hq, d)[:] = (p @ V).squeeze(2).to(BF16)
+
+    # ---- fused memory-bound ops
+    def layernorm(self, x, gamma, beta, eps, *, out_bf16=None, out_f32=None, relu=False):
+        self.launches += 1
+        y = F.layer_norm(x, (x.shape[-1],), gamma, beta, eps)
+        if relu:
+            y = F.relu(y)
+        if out_f32 is not None:
+            out_f32.copy_(y.view_as(out_f32))
+        if out_bf16 is not None:
+            out_bf16.copy_(y.view_as(out_bf16).to(BF16))
+
+    def rmsnorm_residual(self, x, *, branch=None, w_post=None, w_pre=None, eps=1e-6, out_bf16=None):
+        self.launches += 1
+
+        def rms(t, w):
+            return t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + eps) * (1.0 + w)
+        if branch is not None:
+            x.add_(rms(branch.view_as(x), w_post))
+        if w_pre is not None:
+            out_bf16.copy_(rms(x, w_pre).view_as(out_bf16).to(BF16))
+
+    def rope_kv(self, qkv, q_out, kcache, vcache, *, batch, s, hq, hkv, d, smax, pos0, theta):
+        self.launches += 1
+        t = qkv.float().view(batch, s, hq + 2 * hkv, d)
+        pos = torch.arange(pos0, pos0 + s).float() + 1.0
+        inv = 1.0 / (theta ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))
+        fr = pos[:, None] * inv[None]
+        cos, sin = torch.cat([fr, fr], -1).cos()[None, :, None], torch.cat([fr, fr], -1).sin()[None, :, None]
+        qk = t[:, :, : hq + hkv]
+        x1, x2 = qk[..., : d // 2], qk[..., d // 2:]
+        rot = qk * cos + torch.cat([-x2, x1], -1) * sin
+        q_out.view(batch, s, hq, d).copy_(rot[:, :, :hq].to(BF16))
+        kcache.view(batch, smax, hkv, d)[:, pos0:pos0 + s] = rot[:, :, hq:].to(BF16)
+        vcache.view(batch, smax, hkv, d)[:, pos0:pos0 + s] = t[:, :, hq + hkv:].to(BF16)
+
+    def embed_tokens(self, ids, embed, spatial_embed, image_feats, x, *, image_token, act_lo, n_act, n_img,
+                     normalizer, status):
+        self.launches += 1
+        B, S = ids.shape
+        H = x.shape[-1]
+        out = embed[ids.clamp(0, embed.shape[0] - 1)].float()
+        if spatial_embed is not None:
+            sel = (ids >= act_lo) & (ids < act_lo + n_act)
+            out[sel] = spatial_embed[ids[sel] - act_lo].float()
+        if image_feats is not None:
+            m = ids == image_token
+            rank = torch.cumsum(m.long(), 1) - 1
+            if int(rank.max()) >= n_img:
+                status.fill_(1)
+                return
+            bidx = torch.arange(B)[:, None].expand(B, S)
+            out[m] = image_feats.view(B, n_img, H)[bidx[m], rank[m]]
+        x.view(B, S, H).copy_(out * normalizer)
+
+    def argmax_rows(self, logits, out_ids, *, id_offset=0):
+        self.launches += 1
+        out_ids.copy_(logits.argmax(-1) + id_offset)
+
+    def siglip_patchify(self, px, a):
+        self.launches += 1
+        B = px.shape[0]
+        x = (px - 0.5) / 0.5
+        col = F.unfold(x, kernel_size=14, stride=14).transpose(1, 2).reshape(B * 256, 588)
+        a.zero_()
+        a[:, :588] = col.to(BF16)
+
+    def zoe_patchify(self, px, a):
+        self.launches += 1
+        from oracle.model_ref import process_zoe
+        B = px.shape[0]
+        col = F.unfold(process_zoe(px), kernel_size=16, stride=16).transpose(1, 2).reshape(B * 576, 768)
+        a.copy_(col.to(BF16))
+
+    def beit_assemble(self, patches, cls, x, *, batch, n, c):
+        self.launches += 1
+        xv = x.view(batch, n + 1, c)
+        xv[:, 0] = cls.view(1, c)
+        xv[:, 1:] = patches.view(batch, n, c)
+
+    def readout_concat(self, hs, a, *, batch, n, c):
+        self.launches += 1
+        h = hs.view(batch, n + 1, c)
+        a.view(batch, n, 2 * c)[:, :, :c] = h[:, 1:].to(BF16)
+        a.view(batch, n, 2 * c)[:, :, c:] = h[:, :1].expand(batch, n, c).to(BF16)
+
+    def pixel_shuffle(self, g, out, *, batch, h, w, c, f):
+        self.launches += 1
+        t = g.view(batch, h, w, f, f, c).permute(0, 1, 3, 2, 4, 5).reshape(batch, h * f, w * f, c)
+        out.view(batch, h * f, w * f, c).copy_(t)
+
+    def im2col3x3_s2(self, x, a, *, batch, h, w, c):
+        self.launches += 1
+        xn = x.float().view(batch, h, w, c).permute(0, 3, 1, 2)
+        col = F.unfold(xn, kernel_size=3, stride=2, padding=1)               # (B, c*9, L) ordered (c, tap)
+        L_ = col.shape[-1]
+        col = col.view(batch, c, 9, L_).permute(0, 3, 2, 1).reshape(batch * L_, 9 * c)
+        a.copy_(col.to(BF16))
+
+    def bilinear_nhwc(self, x, out, *, batch, h, w, c, oh, ow, add=None, out_relu=None):
+        self.launches += 1
+        xn = x.float().view(batch, h, w, c).permute(0, 3, 1, 2)
+        y = F.interpolate(xn, size=(oh, ow), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+        if add is not None:
+            y = y + add.float().view(batch, oh, ow, c)
+        if out is not None:
+            out.view(batch, oh, ow, c).copy_(y.to(BF16))
+        if out_relu is not None:
+            out_relu.view(batch, oh, ow, c).copy_(F.relu(y).to(BF16))
+
+    def relu_bf16(self, x, out):
+        self.launches += 1
+        out.copy_(F.relu(x.float()).to(BF16))
+
+    def zoe_router_embed(self, conv, e, e_bf16, *, batch, n, c):
+        self.launches += 1
+        S = n + 1
+        pos = torch.arange(0, S, dtype=F32).unsqueeze(1)
+        idx = torch.arange(0, c, 2, dtype=F32).unsqueeze(0)
+        div = torch.exp(idx * (-torch.log(torch.tensor(10000.0)) / c))
+        pe = torch.cat([torch.sin(pos * div), torch.cos(pos * div)], 1)
+        ev = e.view(batch, S, c)
+        ev[:, 0] = pe[0]
+        ev[:, 1:] = conv.view(batch, n, c) + pe[1:]
+        if e_bf16 is not None:
+            e_bf16.view(batch, S, c).copy_(ev.to(BF16))
+
+    def zoe_attractor(self, attr, prev, out, *, batch, h, w, oh, ow, na, nbins):
+        self.launches += 1
+        A = F.softplus(attr.float().view(batch, oh, ow, na)).permute(0, 3, 1, 2)
+        c = F.interpolate(prev.view(batch, h, w, nbins).permute(0, 3, 1, 2), (oh, ow), mode="bilinear",
+                          align_corners=True)
+        delta = torch.zeros_like(c)
+        for i in range(na):
+            dx = A[:, i:i + 1] - c
+            delta = delta + dx / (1 + 300.0 * dx * dx)
+        out.view(batch, oh, ow, nbins).copy_((c + delta / na).permute(0, 2, 3, 1))
+
+    def softplus_f32(self, x, out):
+        self.launches += 1
+        out.copy_(F.softplus(x.float()).view_as(out))
+
+    def zoe_depth_tail(self, t, e, b1, w2, b2, bins, depth, *, batch, h, w, oh, ow, nh, nbins, min_temp, max_temp):
+        self.launches += 1
+        eu = F.interpolate(e.float().view(batch, h, w, nh).permute(0, 3, 1, 2), (oh, ow), mode="bilinear",
+                           align_corners=True).permute(0, 2, 3, 1)
+        hid = F.gelu(t.float().view(batch, oh, ow, nh) + eu + b1)
+        o4 = F.softplus(hid @ w2.t() + b2)
+        pr = (o4[..., 0] + 1e-4) / (o4[..., 0] + 1e-4 + o4[..., 1] + 1e-4)
+        tm = (o4[..., 2] + 1e-4) / (o4[..., 2] + 1e-4 + o4[..., 3] + 1e-4)
+        tm = (max_temp - min_temp) * tm + min_temp
+        kk = torch.arange(0, nbins, dtype=F32)
+        nn_ = torch.tensor(float(nbins - 1)) + 1e-7
+        k_ = kk + 1e-7
+        lb = nn_ * torch.log(nn_) - k_ * torch.log(k_) - (nn_ - k_) * torch.log(nn_ - k_ + 1e-7)
+        lp = torch.log(pr.clamp(1e-4, 1)).unsqueeze(-1)
+        lq = torch.log((1 - pr).clamp(1e-4, 1)).unsqueeze(-1)
+        y = (lb + kk * lp + (nbins - 1 - kk) * lq) / tm.unsqueeze(-1)
+        p = torch.softmax(y, -1)
+        c = F.interpolate(bins.view(batch, h, w, nbins).permute(0, 3, 1, 2), (oh, ow), mode="bilinear",
+                          align_corners=True).permute(0, 2, 3, 1)
+        depth.view(batch, oh, ow).copy_((p * c).sum(-1))
+
+    def ego3d_encode(self, depth384, intrinsic, xyz, enc, *, n_freqs):
+        self.launches += 1
+        from oracle.model_ref import backproject_patch, depth_to_224, ego3d_encoding
+        p = backproject_patch(intrinsic, depth_to_224(depth384), 14, 2)
+        xyz.copy_(p.view_as(xyz))
+        e = ego3d_encoding(p, n_freqs).reshape(-1, 12 * (2 * n_freqs + 1))
+        enc.zero_()
+        enc[:, : e.shape[1]] = e.to(BF16)
+
+    # ---- tokenizer
+    def tok_encode(self, actions, edges, nbins_host, ids, *, min_action=-1.0, max_action=1.0):
+        self.launches += 1
+        from oracle import tokenizer_ref as T
+        pol, nb = _policy_from_flat(edges.numpy(), nbins_host)
+        ids.copy_(torch.from_numpy(T.encode(actions.numpy(), pol, nb, min_action, max_action)).to(ids.dtype))
+
+    def tok_decode(self, ids, edges, nbins_host, begin, actions):
+        self.launches += 1
+        from oracle import tokenizer_ref as T
+        pol, nb = _policy_from_flat(edges.numpy(), nbins_host)
+        actions.copy_(torch.from_numpy(T.decode(ids.numpy() - begin, pol, nb)))
+
+
+def _policy_from_flat(edges, nbins):
+    names = (("translation", "theta_bins"), ("translation", "phi_bins"), ("translation", "r_bins"),
+             ("rotation", "roll_bins"), ("rotation", "pitch_bins"), ("rotation", "yaw_bins"))
+    pol = {"translation": {}, "rotation": {}}
+    nb = {"translation": {}, "rotation": {}, "gripper": int(nbins[6])}
+    off = 0
+    for (bt, bk), n in zip(names, nbins[:6]):
+        pol[bt][bk] = edges[off:off + n + 1]
+        nb[bt][bk] = int(n)
+        off += n + 1
+    return pol, nb

@@ -1,0 +1,393 @@
+// G2 / G3: attention kernels.
+//
+// G2 (svla_attention): flash-style fused softmax(scale*QK^T [softcap] [+relpos bias] [mask]) V.  One CTA = 64
+// query rows of one (batch, head); 4 warps x 16 rows; K/V tiles of 64 keys double-buffered with cp.async;
+// bf16 mma.sync.m16n8k16 with fp32 accumulation, fp32 online softmax (exp2).  Sequences on this path are
+// short (256 / 577 / 278 / 145 tokens), attention is ~3% of the FLOPs of an observation; the tcgen05 port of
+// this kernel is scheduled after the GEMM (DESIGN.md "next").  BEiT's relative-position bias is looked up on
+// the fly from the per-layer (2w-1)^2+3 table (one head column cached in shared memory) instead of
+// materialising a [heads, 577, 577] tensor.
+//
+// G3 (svla_decode_attention): q_len = 1 over the KV cache, one CTA per (batch, kv head) serving the whole GQA
+// group, HBM-bound (reads each K/V row once, 16-byte loads).
+#include "svla_common.cuh"
+
+namespace {
+
+constexpr int kBQ = 64, kBKV = 64, kAttnThreads = 128;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct AttnP {
+  const __nv_bfloat16 *q, *k, *v;
+  __nv_bfloat16* out;
+  long long q_bs, q_ss, k_bs, k_ss, v_bs, v_ss, o_bs, o_ss;
+  int hq, hkv, sq, sk, d;
+  float scale, softcap;
+  int causal;
+  const float* relpos;
+  int win;
+};
+
+// Loads `rows` x d (bf16) rows [r0, r0+64) of a [s, ...] strided matrix into smem [64][DP+8]; rows >= s are zeroed.
+template <int DP>
+__device__ __forceinline__ void load_tile(__nv_bfloat16* sm, const __nv_bfloat16* g, long long row_stride, int r0, int s, int d) {
+  constexpr int LD = DP + 8;
+  const int chunks = d >> 3;
+  for (int i = threadIdx.x; i < 64 * chunks; i += kAttnThreads) {
+    const int r = i / chunks, c = i - r * chunks;
+    const bool ok = (r0 + r) < s;
+    const __nv_bfloat16* src = g + static_cast<long long>(ok ? (r0 + r) : 0) * row_stride + c * 8;
+    cp_async16(sm + r * LD + c * 8, src, ok);
+  }
+}
+
+template <int DP>
+__global__ void __launch_bounds__(kAttnThreads)
+svla_flash_attn_kernel(const AttnP p) {
+  constexpr int LD = DP + 8;
+  constexpr int KT = DP / 16;     // k-steps of QK^T
+  constexpr int NT = DP / 8;      // n-tiles of the output
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+  __nv_bfloat16* sK = sQ + 64 * LD;            // 2 buffers
+  __nv_bfloat16* sV = sK + 2 * 64 * LD;        // 2 buffers
+  float* sTab = reinterpret_cast<float*>(sV + 2 * 64 * LD);
+
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kBQ;
+  const int hk = h / (p.hq / p.hkv);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+
+  const __nv_bfloat16* qg = p.q + b * p.q_bs + static_cast<long long>(h) * p.d;
+  const __nv_bfloat16* kg = p.k + b * p.k_bs + static_cast<long long>(hk) * p.d;
+  const __nv_bfloat16* vg = p.v + b * p.v_bs + static_cast<long long>(hk) * p.d;
+
+  // zero the padding columns [d, DP) once (cp.async never touches them)
+  if (p.d < DP) {
+    const int padc = DP - p.d;
+    for (int i = threadIdx.x; i < 5 * 64 * padc; i += kAttnThreads) {
+      const int buf = i / (64 * padc), rem = i - buf * 64 * padc;
+      const int r = rem / padc, c = p.d + rem % padc;
+      sQ[(buf * 64 + r) * LD + c] = __float2bfloat16(0.f);
+    }
+  }
+  int nrel = 0;
+  if (p.relpos) {
+    nrel = (2 * p.win - 1) * (2 * p.win - 1) + 3;
+    for (int i = threadIdx.x; i < nrel; i += kAttnThreads) sTab[i] = p.relpos[static_cast<long long>(i) * p.hq + h];
+  }
+
+  const int n_kv_tiles = (p.sk + kBKV - 1) / kBKV;
+  load_tile<DP>(sQ, qg, p.q_ss, q0, p.sq, p.d);
+  load_tile<DP>(sK, kg, p.k_ss, 0, p.sk, p.d);
+  load_tile<DP>(sV, vg, p.v_ss, 0, p.sk, p.d);
+  cp_async_commit();
+
+  float o[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const int qi0 = q0 + warp * 16 + g;      // this thread's rows: qi0 and qi0 + 8
+  const int causal_off = p.sk - p.sq;
+  constexpr float kLog2e = 1.4426950408889634f;
+
+  for (int jt = 0; jt < n_kv_tiles; ++jt) {
+    const int buf = jt & 1;
+    if (jt + 1 < n_kv_tiles) {
+      load_tile<DP>(sK + (buf ^ 1) * 64 * LD, kg, p.k_ss, (jt + 1) * kBKV, p.sk, p.d);
+      load_tile<DP>(sV + (buf ^ 1) * 64 * LD, vg, p.v_ss, (jt + 1) * kBKV, p.sk, p.d);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const __nv_bfloat16* cK = sK + buf * 64 * LD;
+    const __nv_bfloat16* cV = sV + buf * 64 * LD;
+
+    // ---- S = Q K^T  (16 x 64 per warp)
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      uint32_t a[4];
+      ldsm_x4(a, sQ + (warp * 16 + (lane & 15)) * LD + kt * 16 + (lane >> 4) * 8);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {       // pairs of key n-tiles
+        uint32_t bfr[4];
+        const int mi = lane >> 3;
+        ldsm_x4(bfr, cK + (np * 16 + (mi >> 1) * 8 + (lane & 7)) * LD + kt * 16 + (mi & 1) * 8);
+        mma_bf16(s[2 * np], a, bfr[0], bfr[1]);
+        mma_bf16(s[2 * np + 1], a, bfr[2], bfr[3]);
+      }
+    }
+    // ---- scale, softcap, bias, mask, online softmax
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = e >> 1;
+        const int qi = qi0 + r * 8;
+        const int kj = jt * kBKV + nt * 8 + 2 * t + (e & 1);
+        float x = s[nt][e] * p.scale;
+        if (p.softcap > 0.f) x = p.softcap * tanhf(x / p.softcap);
+        if (p.relpos && qi < p.sq && kj < p.sk) {
+          int idx;
+          if (qi == 0) idx = (kj == 0) ? nrel - 1 : nrel - 3;
+          else if (kj == 0) idx = nrel - 2;
+          else {
+            const int qy = (qi - 1) / p.win, qx = (qi - 1) % p.win, ky = (kj - 1) / p.win, kx = (kj - 1) % p.win;
+            idx = (qy - ky + p.win - 1) * (2 * p.win - 1) + (qx - kx + p.win - 1);
+          }
+          x += sTab[idx];
+        }
+        const bool masked = (kj >= p.sk) || (p.causal && kj > qi + causal_off);
+        x = masked ? -INFINITY : x;
+        s[nt][e] = x;
+        mx[r] = fmaxf(mx[r], x);
+      }
+    }
+    float scale_old[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_run[r], mx[r]);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      scale_old[r] = exp2f((m_run[r] - m_use) * kLog2e);    // m_run = -inf -> 0
+      m_run[r] = m_new;
+      mx[r] = m_use;
+      l_run[r] *= scale_old[r];
+    }
+    float ls[2] = {0.f, 0.f};
+    uint32_t pa[8][2];      // P as bf16 pairs: [n-tile][row half]
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f((s[nt][0] - mx[0]) * kLog2e), p1 = exp2f((s[nt][1] - mx[0]) * kLog2e);
+      const float p2 = exp2f((s[nt][2] - mx[1]) * kLog2e), p3 = exp2f((s[nt][3] - mx[1]) * kLog2e);
+      ls[0] += p0 + p1;
+      ls[1] += p2 + p3;
+      pa[nt][0] = pack_bf16x2(p0, p1);
+      pa[nt][1] = pack_bf16x2(p2, p3);
+    }
+    l_run[0] += ls[0];
+    l_run[1] += ls[1];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      o[i][0] *= scale_old[0]; o[i][1] *= scale_old[0];
+      o[i][2] *= scale_old[1]; o[i][3] *= scale_old[1];
+    }
+    // ---- O += P V   (k = 64 keys in 4 steps of 16)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t a[4] = {pa[2 * ks][0], pa[2 * ks][1], pa[2 * ks + 1][0], pa[2 * ks + 1][1]};
+#pragma unroll
+      for (int dp = 0; dp < NT / 2; ++dp) {   // pairs of output d n-tiles
+        uint32_t bfr[4];
+        const int mi = lane >> 3;
+        ldsm_x4_t(bfr, cV + (ks * 16 + (mi & 1) * 8 + (lane & 7)) * LD + dp * 16 + (mi >> 1) * 8);
+        mma_bf16(o[2 * dp], a, bfr[0], bfr[1]);
+        mma_bf16(o[2 * dp + 1], a, bfr[2], bfr[3]);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- finalize: row sums across the quad, normalise, store
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
+  const float inv1 = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
+  __nv_bfloat16* og = p.out + b * p.o_bs + static_cast<long long>(h) * p.d;
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const int dcol = i * 8 + 2 * t;
+    if (dcol < p.d) {
+      if (qi0 < p.sq)
+        *reinterpret_cast<uint32_t*>(og + static_cast<long long>(qi0) * p.o_ss + dcol) = pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0);
+      if (qi0 + 8 < p.sq)
+        *reinterpret_cast<uint32_t*>(og + static_cast<long long>(qi0 + 8) * p.o_ss + dcol) = pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1);
+    }
+  }
+}
+
+template <int DP>
+int launch_attn(const AttnP& p, int batch, cudaStream_t st) {
+  constexpr int LD = DP + 8;
+  int nrel = p.relpos ? (2 * p.win - 1) * (2 * p.win - 1) + 3 : 0;
+  const size_t smem = static_cast<size_t>(5) * 64 * LD * 2 + static_cast<size_t>(nrel) * 4 + 16;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(svla_flash_attn_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) {
+      svla_set_error("svla_attention: smem opt-in %zu failed: %s", smem, cudaGetErrorString(e));
+      return -2;
+    }
+    configured = smem;
+  }
+  dim3 grid((p.sq + kBQ - 1) / kBQ, p.hq, batch);
+  svla_flash_attn_kernel<DP><<<grid, kAttnThreads, smem, st>>>(p);
+  SVLA_LAUNCH_CHECK("svla_flash_attn");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ decode (q_len = 1)
+constexpr int kDecThreads = 256;
+constexpr int kMaxGroup = 4;
+
+template <int D>
+__global__ void __launch_bounds__(kDecThreads)
+svla_decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
+                        const __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out, int hq, int hkv, int smax,
+                        int ctx, float scale, float softcap) {
+  extern __shared__ float sm_dec[];
+  const int grp = hq / hkv;
+  float* sq = sm_dec;                       // [grp][D]
+  float* sc = sq + grp * D;                 // [grp][ctx]
+  float* red = sc + grp * ctx;              // [64]
+  const int b = blockIdx.y, hk = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = kDecThreads / 32;
+  for (int i = threadIdx.x; i < grp * D; i += kDecThreads)
+    sq[i] = __bfloat162float(q[(static_cast<long long>(b) * hq + hk * grp) * D + i]);
+  __syncthreads();
+  const __nv_bfloat16* kb = kc + (static_cast<long long>(b) * smax * hkv + hk) * D;
+  const __nv_bfloat16* vb = vc + (static_cast<long long>(b) * smax * hkv + hk) * D;
+  const long long row_stride = static_cast<long long>(hkv) * D;
+  // scores: one warp per key, each lane covers D/32 contiguous dims
+  constexpr int PER = D / 32;
+  for (int j = warp; j < ctx; j += NW) {
+    float kv[PER];
+    const __nv_bfloat16* kr = kb + j * row_stride + lane * PER;
+#pragma unroll
+    for (int e = 0; e < PER; e += 8) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(kr + e));
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        kv[e + 2 * u] = bf16_bits_to_float(w[u] & 0xFFFFu);
+        kv[e + 2 * u + 1] = bf16_bits_to_float(w[u] >> 16);
+      }
+    }
+    for (int gi = 0; gi < grp; ++gi) {
+      float acc = 0.f;
+#pragma unroll
+      for (int e = 0; e < PER; ++e) acc += kv[e] * sq[gi * D + lane * PER + e];
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        float x = acc * scale;
+        if (softcap > 0.f) x = softcap * tanhf(x / softcap);
+        sc[gi * ctx + j] = x;
+      }
+    }
+  }
+  __syncthreads();
+  // softmax per group row (fp32)
+  for (int gi = 0; gi < grp; ++gi) {
+    float mx = -INFINITY;
+    for (int j = threadIdx.x; j < ctx; j += kDecThreads) mx = fmaxf(mx, sc[gi * ctx + j]);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < NW; ++w) mx = fmaxf(mx, red[w]);
+    float sum = 0.f;
+    for (int j = threadIdx.x; j < ctx; j += kDecThreads) {
+      const float e = expf(sc[gi * ctx + j] - mx);
+      sc[gi * ctx + j] = e;
+      sum += e;
+    }
+    sum = block_sum(sum, red + 16);
+    const float inv = 1.f / sum;
+    for (int j = threadIdx.x; j < ctx; j += kDecThreads) sc[gi * ctx + j] *= inv;
+    __syncthreads();
+  }
+  // out[d] = sum_j p[j] V[j][d] : thread <-> dim (D == kDecThreads), probabilities rounded to bf16 like the prefill path
+  float acc[kMaxGroup];
+#pragma unroll
+  for (int gi = 0; gi < kMaxGroup; ++gi) acc[gi] = 0.f;
+  for (int d0 = threadIdx.x; d0 < D; d0 += kDecThreads) {
+    for (int j = 0; j < ctx; ++j) {
+      const float vv = __bfloat162float(vb[j * row_stride + d0]);
+#pragma unroll
+      for (int gi = 0; gi < kMaxGroup; ++gi)
+        if (gi < grp) acc[gi] += __bfloat162float(__float2bfloat16(sc[gi * ctx + j])) * vv;
+    }
+    for (int gi = 0; gi < grp; ++gi) {
+      out[(static_cast<long long>(b) * hq + hk * grp + gi) * D + d0] = __float2bfloat16(acc[gi]);
+      acc[gi] = 0.f;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int svla_attention(const SvlaAttnArgs* a, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SVLA_REQUIRE(a && a->q && a->k && a->v && a->out, "svla_attention: null pointer");
+  SVLA_REQUIRE(a->d > 0 && (a->d % 8) == 0 && a->d <= 256, "svla_attention: head dim %d unsupported", a->d);
+  SVLA_REQUIRE(a->hkv > 0 && a->hq % a->hkv == 0, "svla_attention: hq %% hkv != 0");
+  SVLA_REQUIRE(a->sq > 0 && a->sk > 0 && a->batch > 0, "svla_attention: empty problem");
+  SVLA_REQUIRE((a->q_ss % 8) == 0 && (a->k_ss % 8) == 0 && (a->v_ss % 8) == 0 && (a->o_ss % 2) == 0,
+               "svla_attention: row strides must keep 16-byte alignment");
+  AttnP p;
+  p.q = static_cast<const __nv_bfloat16*>(a->q); p.k = static_cast<const __nv_bfloat16*>(a->k);
+  p.v = static_cast<const __nv_bfloat16*>(a->v); p.out = static_cast<__nv_bfloat16*>(a->out);
+  p.q_bs = a->q_bs; p.q_ss = a->q_ss; p.k_bs = a->k_bs; p.k_ss = a->k_ss; p.v_bs = a->v_bs; p.v_ss = a->v_ss;
+  p.o_bs = a->o_bs; p.o_ss = a->o_ss;
+  p.hq = a->hq; p.hkv = a->hkv; p.sq = a->sq; p.sk = a->sk; p.d = a->d;
+  p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.relpos = a->relpos_table; p.win = a->relpos_win;
+  if (a->d <= 32) return launch_attn<32>(p, a->batch, st);
+  if (a->d <= 64) return launch_attn<64>(p, a->batch, st);
+  if (a->d <= 80) return launch_attn<80>(p, a->batch, st);
+  if (a->d <= 128) return launch_attn<128>(p, a->batch, st);
+  return launch_attn<256>(p, a->batch, st);
+}
+
+extern "C" int svla_decode_attention(const void* q, const void* kcache, const void* vcache, void* out, int batch, int hq,
+                                     int hkv, int d, int smax, int ctx, float scale, float softcap, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SVLA_REQUIRE(q && kcache && vcache && out, "svla_decode_attention: null pointer");
+  SVLA_REQUIRE(d == 256, "svla_decode_attention: head dim %d unsupported (256 only)", d);
+  SVLA_REQUIRE(hkv > 0 && hq % hkv == 0 && hq / hkv <= kMaxGroup, "svla_decode_attention: bad GQA group");
+  SVLA_REQUIRE(ctx > 0 && ctx <= smax, "svla_decode_attention: ctx %d out of range", ctx);
+  const int grp = hq / hkv;
+  const size_t smem = (static_cast<size_t>(grp) * d + static_cast<size_t>(grp) * ctx + 64) * sizeof(float);
+  SVLA_REQUIRE(smem <= 200 * 1024, "svla_decode_attention: context too long for shared memory");
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    cudaFuncSetAttribute(svla_decode_attn_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured = smem;
+  }
+  dim3 grid(hkv, batch);
+  svla_decode_attn_kernel<256><<<grid, kDecThreads, smem, st>>>(
+      static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(kcache),
+      static_cast<const __nv_bfloat16*>(vcache), static_cast<__nv_bfloat16*>(out), hq, hkv, smax, ctx, scale, softcap);
+  SVLA_LAUNCH_CHECK("svla_decode_attn");
+  return 0;
+}

@@ -1,0 +1,753 @@
+// Memory-bound fused kernels of the predict_action path (M1-M7, M9, ZoeDepth metric-bins tail, Ego3D).
+// All of them stream each operand once with 128-bit accesses where the layout allows, keep statistics in
+// fp32 and use warp-shuffle reductions.  Reference lines replaced: see include/spatialvla_b200.h.
+#include "svla_common.cuh"
+
+namespace {
+
+constexpr int kRowThreads = 256;
+constexpr int kMaxVec = 5;   // float4 per thread: rows up to 256*5*4 = 5120 columns
+
+// ------------------------------------------------------------------------------------------ row loaders
+__device__ __forceinline__ int load_row(const float* __restrict__ x, int cols, float4 (&v)[kMaxVec]) {
+  const int nv = cols >> 2;
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < kMaxVec; ++k) {
+    const int i = threadIdx.x + k * kRowThreads;
+    if (i < nv) { v[k] = reinterpret_cast<const float4*>(x)[i]; cnt = k + 1; }
+    else v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  return cnt;
+}
+
+// ------------------------------------------------------------------------------------------ M1 LayerNorm
+__global__ void __launch_bounds__(kRowThreads)
+svla_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                      int cols, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32, int relu) {
+  __shared__ float sh[33];
+  const long long row = blockIdx.x;
+  const float* xr = x + row * cols;
+  float4 v[kMaxVec];
+  load_row(xr, cols, v);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxVec; ++k) s += v[k].x + v[k].y + v[k].z + v[k].w;
+  const float mean = block_sum(s, sh) / cols;
+  const int nv = cols >> 2;
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxVec; ++k) {
+    if (threadIdx.x + k * kRowThreads < nv) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      ss += a * a + b * b + c * c + d * d;
+    }
+  }
+  const float rstd = rsqrtf(block_sum(ss, sh) / cols + eps);
+#pragma unroll
+  for (int k = 0; k < kMaxVec; ++k) {
+    const int i = threadIdx.x + k * kRowThreads;
+    if (i < nv) {
+      const float4 g = reinterpret_cast<const float4*>(gamma)[i];
+      const float4 b = reinterpret_cast<const float4*>(beta)[i];
+      float4 o;
+      o.x = (v[k].x - mean) * rstd * g.x + b.x;
+      o.y = (v[k].y - mean) * rstd * g.y + b.y;
+      o.z = (v[k].z - mean) * rstd * g.z + b.z;
+      o.w = (v[k].w - mean) * rstd * g.w + b.w;
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      if (out_f32) reinterpret_cast<float4*>(out_f32 + row * cols)[i] = o;
+      if (out_bf16) reinterpret_cast<uint2*>(out_bf16 + row * cols)[i] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ M2 Gemma2 sandwich norm
+__global__ void __launch_bounds__(kRowThreads)
+svla_rmsnorm_residual_kernel(float* __restrict__ x, const float* __restrict__ branch, const float* __restrict__ w_post,
+                             const float* __restrict__ w_pre, float eps, int cols, __nv_bfloat16* __restrict__ out_bf16) {
+  __shared__ float sh[33];
+  const long long row = blockIdx.x;
+  const int nv = cols >> 2;
+  float4 xv[kMaxVec];
+  load_row(x + row * cols, cols, xv);
+  if (branch) {
+    float4 bv[kMaxVec];
+    load_row(branch + row * cols, cols, bv);
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxVec; ++k) ss += bv[k].x * bv[k].x + bv[k].y * bv[k].y + bv[k].z * bv[k].z + bv[k].w * bv[k].w;
+    const float r = rsqrtf(block_sum(ss, sh) / cols + eps);
+#pragma unroll
+    for (int k = 0; k < kMaxVec; ++k) {
+      const int i = threadIdx.x + k * kRowThreads;
+      if (i < nv) {
+        const float4 w = reinterpret_cast<const float4*>(w_post)[i];
+        xv[k].x += bv[k].x * r * (1.f + w.x);
+        xv[k].y += bv[k].y * r * (1.f + w.y);
+        xv[k].z += bv[k].z * r * (1.f + w.z);
+        xv[k].w += bv[k].w * r * (1.f + w.w);
+        reinterpret_cast<float4*>(x + row * cols)[i] = xv[k];
+      }
+    }
+  }
+  if (w_pre) {
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxVec; ++k) ss += xv[k].x * xv[k].x + xv[k].y * xv[k].y + xv[k].z * xv[k].z + xv[k].w * xv[k].w;
+    const float r = rsqrtf(block_sum(ss, sh) / cols + eps);
+#pragma unroll
+    for (int k = 0; k < kMaxVec; ++k) {
+      const int i = threadIdx.x + k * kRowThreads;
+      if (i < nv) {
+        const float4 w = reinterpret_cast<const float4*>(w_pre)[i];
+        reinterpret_cast<uint2*>(out_bf16 + row * cols)[i] =
+            make_uint2(pack_bf16x2(xv[k].x * r * (1.f + w.x), xv[k].y * r * (1.f + w.y)),
+                       pack_bf16x2(xv[k].z * r * (1.f + w.z), xv[k].w * r * (1.f + w.w)));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ M3 RoPE + KV cache write
+// one block per token; thread pairs (d, d + D/2) of every head
+__global__ void svla_rope_kv_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ q_out,
+                                    __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc, int s, int hq, int hkv, int d,
+                                    int smax, int pos0, float theta) {
+  const long long tok = blockIdx.x;
+  const int b = static_cast<int>(tok / s), si = static_cast<int>(tok % s);
+  const int pos = pos0 + si;                       // cache slot
+  const float fpos = static_cast<float>(pos + 1);  // PaliGemma positions are 1-indexed
+  const int half = d >> 1;
+  const long long width = static_cast<long long>(hq + 2 * hkv) * d;
+  const __nv_bfloat16* src = qkv + tok * width;
+  const long long cache_row = (static_cast<long long>(b) * smax + pos) * hkv * d;
+  const int rot_items = (hq + hkv) * half;
+  for (int i = threadIdx.x; i < rot_items; i += blockDim.x) {
+    const int hh = i / half, j = i - hh * half;
+    // inv_freq = 1 / theta^(2j/d) in fp32 exactly like torch: base ** (arange(0,d,2).float()/d)
+    const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * j) / static_cast<float>(d));
+    const float ang = fpos * inv_freq;
+    float sn, cs;
+    sincosf(ang, &sn, &cs);
+    const float x1 = __bfloat162float(src[hh * d + j]);
+    const float x2 = __bfloat162float(src[hh * d + j + half]);
+    const float o1 = x1 * cs - x2 * sn;
+    const float o2 = x2 * cs + x1 * sn;
+    if (hh < hq) {
+      q_out[tok * hq * d + hh * d + j] = __float2bfloat16(o1);
+      q_out[tok * hq * d + hh * d + j + half] = __float2bfloat16(o2);
+    } else {
+      const int kh = hh - hq;
+      kc[cache_row + kh * d + j] = __float2bfloat16(o1);
+      kc[cache_row + kh * d + j + half] = __float2bfloat16(o2);
+    }
+  }
+  const __nv_bfloat16* vsrc = src + static_cast<long long>(hq + hkv) * d;
+  for (int i = threadIdx.x; i < hkv * d; i += blockDim.x) vc[cache_row + i] = vsrc[i];
+}
+
+// ------------------------------------------------------------------------------------------ M6 embedding gather
+__global__ void svla_embed_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ embed,
+                                  const __nv_bfloat16* __restrict__ spatial, const float* __restrict__ img, float* __restrict__ x,
+                                  int s, int hdim, long long vocab, long long image_token, long long act_lo, long long n_act,
+                                  int n_img, float normalizer, int* __restrict__ status) {
+  const long long tok = blockIdx.x;
+  const int b = static_cast<int>(tok / s), si = static_cast<int>(tok % s);
+  const long long id = ids[tok];
+  float* dst = x + tok * hdim;
+  if (id == image_token && img != nullptr) {
+    // rank of this image token inside its row (the processor puts them first, but stay general)
+    __shared__ int rank_sh;
+    if (threadIdx.x == 0) rank_sh = 0;
+    __syncthreads();
+    int cnt = 0;
+    for (int j = threadIdx.x; j < si; j += blockDim.x) cnt += (ids[static_cast<long long>(b) * s + j] == image_token);
+    if (cnt) atomicAdd(&rank_sh, cnt);
+    __syncthreads();
+    const int rank = rank_sh;
+    if (rank >= n_img) {
+      if (threadIdx.x == 0 && status) atomicExch(status, 1);   // image-token / feature count mismatch
+      return;
+    }
+    const float* src = img + (static_cast<long long>(b) * n_img + rank) * hdim;
+    for (int i = threadIdx.x; i < hdim; i += blockDim.x) dst[i] = src[i] * normalizer;
+    return;
+  }
+  const __nv_bfloat16* src;
+  if (spatial != nullptr && id >= act_lo && id < act_lo + n_act) src = spatial + (id - act_lo) * hdim;
+  else {
+    if (id < 0 || id >= vocab) {
+      if (threadIdx.x == 0 && status) atomicExch(status, 2);
+      return;
+    }
+    src = embed + id * hdim;
+  }
+  for (int i = threadIdx.x; i < hdim; i += blockDim.x) dst[i] = __bfloat162float(src[i]) * normalizer;
+}
+
+// ------------------------------------------------------------------------------------------ M7 argmax
+__global__ void __launch_bounds__(256)
+svla_argmax_kernel(const float* __restrict__ logits, long long cols, long long ld, long long id_offset,
+                   long long* __restrict__ out, long long out_stride) {
+  __shared__ float sv[8];
+  __shared__ long long si[8];
+  const long long row = blockIdx.x;
+  const float* r = logits + row * ld;
+  float best = -INFINITY;
+  long long bi = 0x7fffffffffffffffLL;
+  for (long long j = threadIdx.x; j < cols; j += blockDim.x) {
+    const float v = r[j];
+    if (v > best || (v == best && j < bi)) { best = v; bi = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+    out[row * out_stride] = bi + id_offset;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ bicubic helpers (A = -0.75)
+__device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
+  const float A = -0.75f;
+  const float x1 = t, x2 = 1.f - t;
+  w[0] = ((A * (x1 + 1.f) - 5.f * A) * (x1 + 1.f) + 8.f * A) * (x1 + 1.f) - 4.f * A;
+  w[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  w[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  w[3] = ((A * (x2 + 1.f) - 5.f * A) * (x2 + 1.f) + 8.f * A) * (x2 + 1.f) - 4.f * A;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ int reflect224(int p) {   // index into the 286-wide reflect-padded image -> 224 image
+  int i = p - 31;
+  if (i < 0) i = -i;
+  if (i > 223) i = 446 - i;
+  return i;
+}
+
+// ------------------------------------------------------------------------------------------ M9 patchify
+// siglip: a[(b*256 + py*16+px), c*196 + i*14 + j] = (px[b,c,py*14+i,px*14+j] - .5)/.5 ; cols [588,kpad) = 0
+__global__ void svla_siglip_patchify_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ a, int kpad) {
+  const int row = blockIdx.x;            // b*256 + patch
+  const int b = row >> 8, patch = row & 255, py = patch >> 4, pxx = patch & 15;
+  for (int col = threadIdx.x; col < kpad; col += blockDim.x) {
+    float v = 0.f;
+    if (col < 588) {
+      const int c = col / 196, r = col % 196, i = r / 14, j = r % 14;
+      v = (px[((static_cast<long long>(b) * 3 + c) * 224 + py * 14 + i) * 224 + pxx * 14 + j] - 0.5f) / 0.5f;
+    }
+    a[static_cast<long long>(row) * kpad + col] = __float2bfloat16(v);
+  }
+}
+
+// zoe: 224 -(reflect pad 31)-> 286 -(bicubic, align_corners)-> 384 -> normalise -> im2col(16x16):
+// a[(b*576 + py*24+px), c*256 + i*16 + j]
+__global__ void svla_zoe_patchify_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ a) {
+  const int row = blockIdx.x;
+  const int b = row / 576, patch = row % 576, py = patch / 24, pxx = patch % 24;
+  const float scale = 285.0f / 383.0f;
+  for (int col = threadIdx.x; col < 768; col += blockDim.x) {
+    const int c = col >> 8, i = (col >> 4) & 15, j = col & 15;
+    const int oy = py * 16 + i, ox = pxx * 16 + j;
+    const float sy = scale * oy, sx = scale * ox;
+    const int y0 = static_cast<int>(floorf(sy)), x0 = static_cast<int>(floorf(sx));
+    float wy[4], wx[4];
+    cubic_coeffs(sy - y0, wy);
+    cubic_coeffs(sx - x0, wx);
+    const float* img = px + (static_cast<long long>(b) * 3 + c) * 224 * 224;
+    float acc = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int yy = reflect224(clampi(y0 - 1 + u, 0, 285));
+      float racc = 0.f;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int xx = reflect224(clampi(x0 - 1 + v, 0, 285));
+        racc += wx[v] * img[yy * 224 + xx];
+      }
+      acc += wy[u] * racc;
+    }
+    a[static_cast<long long>(row) * 768 + col] = __float2bfloat16((acc - 0.5f) / 0.5f);
+  }
+}
+
+__global__ void svla_beit_assemble_kernel(const float* __restrict__ patches, const float* __restrict__ cls, float* __restrict__ x,
+                                          int n, int c) {
+  const long long row = blockIdx.x;   // b*(n+1) + t
+  const int t = static_cast<int>(row % (n + 1));
+  const long long b = row / (n + 1);
+  const float* src = (t == 0) ? cls : patches + (b * n + (t - 1)) * c;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) x[row * c + i] = src[i];
+}
+
+__global__ void svla_readout_concat_kernel(const float* __restrict__ hs, __nv_bfloat16* __restrict__ a, int n, int c) {
+  const long long row = blockIdx.x;   // b*n + i
+  const long long b = row / n;
+  const int i = static_cast<int>(row % n);
+  const float* tok = hs + (b * (n + 1) + 1 + i) * c;
+  const float* cls = hs + (b * (n + 1)) * c;
+  for (int j = threadIdx.x; j < c; j += blockDim.x) {
+    a[row * 2 * c + j] = __float2bfloat16(tok[j]);
+    a[row * 2 * c + c + j] = __float2bfloat16(cls[j]);
+  }
+}
+
+// g [B*h*w, f*f*c] -> out NHWC [B, h*f, w*f, c]; 8 bf16 (16 bytes) per thread
+__global__ void svla_pixel_shuffle_kernel(const uint4* __restrict__ g, uint4* __restrict__ out, int h, int w, int c8, int f, long long total) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int cc = static_cast<int>(idx % c8);
+  long long r = idx / c8;
+  const int ox = static_cast<int>(r % (w * f)); r /= (w * f);
+  const int oy = static_cast<int>(r % (h * f));
+  const long long b = r / (h * f);
+  const int y = oy / f, i = oy % f, x = ox / f, j = ox % f;
+  out[idx] = g[((b * h + y) * w + x) * (static_cast<long long>(f) * f * c8) + (i * f + j) * c8 + cc];
+}
+
+__global__ void svla_im2col3x3_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ a, int h, int w, int c8, long long total) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int cc = static_cast<int>(idx % c8);
+  long long r = idx / c8;
+  const int tap = static_cast<int>(r % 9); r /= 9;
+  const int oh = h / 2, ow = w / 2;
+  const int ox = static_cast<int>(r % ow); r /= ow;
+  const int oy = static_cast<int>(r % oh);
+  const long long b = r / oh;
+  const int y = oy * 2 + tap / 3 - 1, xx = ox * 2 + tap % 3 - 1;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (y >= 0 && y < h && xx >= 0 && xx < w) v = x[((b * h + y) * w + xx) * c8 + cc];
+  a[idx] = v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { f[2 * u] = bf16_bits_to_float(w[u] & 0xFFFFu); f[2 * u + 1] = bf16_bits_to_float(w[u] >> 16); }
+}
+
+// bilinear, align_corners=True, NHWC bf16, 8 channels per thread
+__global__ void svla_bilinear_nhwc_kernel(const uint4* __restrict__ x, const uint4* __restrict__ add, uint4* __restrict__ out,
+                                          uint4* __restrict__ out_relu, int h, int w, int c8, int oh, int ow, long long total) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int cc = static_cast<int>(idx % c8);
+  long long r = idx / c8;
+  const int ox = static_cast<int>(r % ow); r /= ow;
+  const int oy = static_cast<int>(r % oh);
+  const long long b = r / oh;
+  const float sy = (oh > 1) ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) * oy : 0.f;
+  const float sx = (ow > 1) ? static_cast<float>(w - 1) / static_cast<float>(ow - 1) * ox : 0.f;
+  const int y0 = min(static_cast<int>(sy), h - 1), x0 = min(static_cast<int>(sx), w - 1);
+  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  float f00[8], f01[8], f10[8], f11[8], o[8];
+  unpack8(x[((b * h + y0) * w + x0) * c8 + cc], f00);
+  unpack8(x[((b * h + y0) * w + x1) * c8 + cc], f01);
+  unpack8(x[((b * h + y1) * w + x0) * c8 + cc], f10);
+  unpack8(x[((b * h + y1) * w + x1) * c8 + cc], f11);
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    o[e] = (1.f - ly) * ((1.f - lx) * f00[e] + lx * f01[e]) + ly * ((1.f - lx) * f10[e] + lx * f11[e]);
+  if (add) {
+    float ad[8];
+    unpack8(add[idx], ad);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] += ad[e];
+  }
+  if (out) out[idx] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  if (out_relu)
+    out_relu[idx] = make_uint4(pack_bf16x2(fmaxf(o[0], 0.f), fmaxf(o[1], 0.f)), pack_bf16x2(fmaxf(o[2], 0.f), fmaxf(o[3], 0.f)),
+                               pack_bf16x2(fmaxf(o[4], 0.f), fmaxf(o[5], 0.f)), pack_bf16x2(fmaxf(o[6], 0.f), fmaxf(o[7], 0.f)));
+}
+
+__global__ void svla_relu_bf16_kernel(const __nv_bfloat162* __restrict__ x, __nv_bfloat162* __restrict__ out, long long n2) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= n2) return;
+  const float2 f = __bfloat1622float2(x[idx]);
+  out[idx] = __floats2bfloat162_rn(fmaxf(f.x, 0.f), fmaxf(f.y, 0.f));
+}
+
+__global__ void svla_softplus_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long n) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx < n) out[idx] = softplus_f(__bfloat162float(x[idx]));
+}
+
+// ZoeDepth patch transformer input: PE = cat(sin(pos*div), cos(pos*div)), div_i = exp(2i * (-ln(1e4)/c))
+__global__ void svla_zoe_router_embed_kernel(const float* __restrict__ conv, float* __restrict__ e, __nv_bfloat16* __restrict__ eb, int n, int c) {
+  const long long row = blockIdx.x;   // b*(n+1) + t
+  const int t = static_cast<int>(row % (n + 1));
+  const long long b = row / (n + 1);
+  const int half = c / 2;
+  const float k = -logf(10000.0f) / static_cast<float>(c);
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    const int fi = (i < half) ? i : i - half;
+    const float ang = static_cast<float>(t) * expf(static_cast<float>(2 * fi) * k);
+    const float pe = (i < half) ? sinf(ang) : cosf(ang);
+    const float base = (t == 0) ? 0.f : conv[(b * n + (t - 1)) * c + i];
+    e[row * c + i] = base + pe;
+    if (eb) eb[row * c + i] = __float2bfloat16(base + pe);
+  }
+}
+
+// bilinear (align_corners=True) sample of an fp32 NHWC map: channel ch of pixel (oy, ox) of an oh x ow grid
+struct Bilin {
+  int y0, y1, x0, x1;
+  float ly, lx;
+};
+__device__ __forceinline__ Bilin make_bilin(int oy, int ox, int h, int w, int oh, int ow) {
+  Bilin s;
+  const float sy = (oh > 1) ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) * oy : 0.f;
+  const float sx = (ow > 1) ? static_cast<float>(w - 1) / static_cast<float>(ow - 1) * ox : 0.f;
+  s.y0 = min(static_cast<int>(sy), h - 1); s.x0 = min(static_cast<int>(sx), w - 1);
+  s.y1 = min(s.y0 + 1, h - 1); s.x1 = min(s.x0 + 1, w - 1);
+  s.ly = sy - s.y0; s.lx = sx - s.x0;
+  return s;
+}
+__device__ __forceinline__ float bilin_f32(const float* __restrict__ base, const Bilin& s, int w, int c, int ch) {
+  const float v00 = base[(static_cast<long long>(s.y0) * w + s.x0) * c + ch], v01 = base[(static_cast<long long>(s.y0) * w + s.x1) * c + ch];
+  const float v10 = base[(static_cast<long long>(s.y1) * w + s.x0) * c + ch], v11 = base[(static_cast<long long>(s.y1) * w + s.x1) * c + ch];
+  return (1.f - s.ly) * ((1.f - s.lx) * v00 + s.lx * v01) + s.ly * ((1.f - s.lx) * v10 + s.lx * v11);
+}
+__device__ __forceinline__ float bilin_bf16(const __nv_bfloat16* __restrict__ base, const Bilin& s, int w, int c, int ch) {
+  const float v00 = __bfloat162float(base[(static_cast<long long>(s.y0) * w + s.x0) * c + ch]);
+  const float v01 = __bfloat162float(base[(static_cast<long long>(s.y0) * w + s.x1) * c + ch]);
+  const float v10 = __bfloat162float(base[(static_cast<long long>(s.y1) * w + s.x0) * c + ch]);
+  const float v11 = __bfloat162float(base[(static_cast<long long>(s.y1) * w + s.x1) * c + ch]);
+  return (1.f - s.ly) * ((1.f - s.lx) * v00 + s.lx * v01) + s.ly * ((1.f - s.lx) * v10 + s.lx * v11);
+}
+
+// one warp per output pixel; lane handles bins lane, lane+32, ...
+__global__ void __launch_bounds__(256)
+svla_zoe_attractor_kernel(const __nv_bfloat16* __restrict__ attr, const float* __restrict__ prev, float* __restrict__ out, int h,
+                          int w, int oh, int ow, int na, int nbins, long long npix) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
+  for (long long pix = warp_global; pix < npix; pix += nwarps) {
+    const int ox = static_cast<int>(pix % ow);
+    const int oy = static_cast<int>((pix / ow) % oh);
+    const long long b = pix / (static_cast<long long>(ow) * oh);
+    const float a_l = (lane < na) ? softplus_f(__bfloat162float(attr[pix * na + lane])) : 0.f;
+    const Bilin s = make_bilin(oy, ox, h, w, oh, ow);
+    const float* pb = prev + b * h * w * nbins;
+    for (int k = lane; k < nbins; k += 32) {
+      const float c = bilin_f32(pb, s, w, nbins, k);
+      float delta = 0.f;
+      for (int a = 0; a < na; ++a) {
+        const float dx = __shfl_sync(0xffffffffu, a_l, a) - c;
+        delta += dx / (1.f + 300.f * dx * dx);
+      }
+      out[pix * nbins + k] = c + delta / static_cast<float>(na);
+    }
+  }
+}
+
+// one warp per output pixel (nbins <= 64, nh <= 64)
+__global__ void __launch_bounds__(256)
+svla_zoe_depth_tail_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloat16* __restrict__ e, const float* __restrict__ b1,
+                           const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ bins,
+                           float* __restrict__ depth, int h, int w, int oh, int ow, int nh, int nbins, float min_temp,
+                           float max_temp, long long npix) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
+  for (long long pix = warp_global; pix < npix; pix += nwarps) {
+    const int ox = static_cast<int>(pix % ow);
+    const int oy = static_cast<int>((pix / ow) % oh);
+    const long long b = pix / (static_cast<long long>(ow) * oh);
+    const Bilin s = make_bilin(oy, ox, h, w, oh, ow);
+    // hidden = gelu(W_a*last + up(W_b*emb) + b1), then 4 outputs
+    float o4[4] = {0.f, 0.f, 0.f, 0.f};
+    const __nv_bfloat16* eb = e + b * h * w * nh;
+    for (int ch = lane; ch < nh; ch += 32) {
+      const float hv = gelu_erf_f(__bfloat162float(t[pix * nh + ch]) + bilin_bf16(eb, s, w, nh, ch) + b1[ch]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o4[q] += w2[q * nh + ch] * hv;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o4[q] = softplus_f(warp_sum(o4[q]) + b2[q]);
+    const float p0 = o4[0] + 1e-4f, p1 = o4[1] + 1e-4f, t0 = o4[2] + 1e-4f, t1 = o4[3] + 1e-4f;
+    const float prob = p0 / (p0 + p1);
+    const float temp = (max_temp - min_temp) * (t0 / (t0 + t1)) + min_temp;
+    const float lp = logf(fminf(fmaxf(prob, 1e-4f), 1.f)), lq = logf(fminf(fmaxf(1.f - prob, 1e-4f), 1.f));
+    const float nn = static_cast<float>(nbins - 1) + 1e-7f;
+    // y_k = log C(K-1, k) (Stirling form with the reference's eps) + k log p + (K-1-k) log(1-p)
+    float y[2], c[2];
+    float mx = -INFINITY;
+    const float* bb = bins + b * h * w * nbins;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int k = lane + 32 * r;
+      if (k < nbins) {
+        const float kk = static_cast<float>(k) + 1e-7f;
+        const float lb = nn * logf(nn) - kk * logf(kk) - (nn - kk) * logf(nn - kk + 1e-7f);
+        y[r] = (lb + static_cast<float>(k) * lp + static_cast<float>(nbins - 1 - k) * lq) / temp;
+        c[r] = bilin_f32(bb, s, w, nbins, k);
+        mx = fmaxf(mx, y[r]);
+      } else { y[r] = -INFINITY; c[r] = 0.f; }
+    }
+    mx = warp_max(mx);
+    float se = 0.f, sc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float ex = (y[r] == -INFINITY) ? 0.f : expf(y[r] - mx);
+      se += ex; sc += ex * c[r];
+    }
+    se = warp_sum(se); sc = warp_sum(sc);
+    if (lane == 0) depth[pix] = sc / se;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ M5 Ego3D
+// grid (32 cell rows, B); 256 threads = 32 cells x 8 lanes; each cell = 7x7 mean of the bicubic-resampled depth
+__global__ void __launch_bounds__(256)
+svla_ego3d_kernel(const float* __restrict__ depth384, const float* __restrict__ intr, int k_stride, float* __restrict__ xyz,
+                  __nv_bfloat16* __restrict__ enc, int kpad, int n_freqs) {
+  const int ci = blockIdx.x, b = blockIdx.y;
+  const int cj = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  const float* dm = depth384 + static_cast<long long>(b) * 384 * 384;
+  const float scale = 383.0f / 285.0f;
+  float acc = 0.f;
+  for (int pidx = sub; pidx < 49; pidx += 8) {
+    const int py = ci * 7 + pidx / 7 + 31, px = cj * 7 + pidx % 7 + 31;   // coordinates in the 286 grid
+    const float sy = scale * py, sx = scale * px;
+    const int y0 = static_cast<int>(floorf(sy)), x0 = static_cast<int>(floorf(sx));
+    float wy[4], wx[4];
+    cubic_coeffs(sy - y0, wy);
+    cubic_coeffs(sx - x0, wx);
+    float v = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int yy = clampi(y0 - 1 + u, 0, 383);
+      float racc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) racc += wx[q] * dm[yy * 384 + clampi(x0 - 1 + q, 0, 383)];
+      v += wy[u] * racc;
+    }
+    acc += v;
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (sub >= 3) return;
+  const float d = acc / 49.f;
+  // inverse of the 3x3 intrinsic matrix (adjugate / det) in fp32
+  const float* K = intr + static_cast<long long>(b) * k_stride;
+  const float a00 = K[0], a01 = K[1], a02 = K[2], a10 = K[3], a11 = K[4], a12 = K[5], a20 = K[6], a21 = K[7], a22 = K[8];
+  const float c00 = a11 * a22 - a12 * a21, c01 = a02 * a21 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+  const float c10 = a12 * a20 - a10 * a22, c11 = a00 * a22 - a02 * a20, c12 = a02 * a10 - a00 * a12;
+  const float c20 = a10 * a21 - a11 * a20, c21 = a01 * a20 - a00 * a21, c22 = a00 * a11 - a01 * a10;
+  const float det = a00 * c00 + a01 * c10 + a02 * c20;
+  const float u = cj * 7 + 3.5f, v = ci * 7 + 3.5f;
+  float r;
+  if (sub == 0) r = (c00 * u + c01 * v + c02) / det;
+  else if (sub == 1) r = (c10 * u + c11 * v + c12) / det;
+  else r = (c20 * u + c21 * v + c22) / det;
+  const float val = r * d;
+  const int patch = (ci >> 1) * 16 + (cj >> 1);
+  const int m = ((ci & 1) * 2 + (cj & 1)) * 3 + sub;      // (sub_row, sub_col, xyz)
+  const long long prow = static_cast<long long>(b) * 256 + patch;
+  xyz[prow * 12 + m] = val;
+  const float xn = (val - (sub == 2 ? 2.f : 0.f)) / 2.f;
+  __nv_bfloat16* er = enc + prow * kpad + m * (2 * n_freqs + 1);
+  er[0] = __float2bfloat16(xn);
+  float f = 1.f;
+  for (int k = 0; k < n_freqs; ++k) {
+    er[1 + k] = __float2bfloat16(sinf(xn * f));
+    er[1 + n_freqs + k] = __float2bfloat16(cosf(xn * f));
+    f *= 2.f;
+  }
+  // zero the K padding once per row (the thread that owns m == 0)
+  if (m == 0)
+    for (int col = 12 * (2 * n_freqs + 1); col < kpad; ++col) enc[prow * kpad + col] = __float2bfloat16(0.f);
+}
+
+inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" int svla_layernorm(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int cols,
+                              void* out_bf16, float* out_f32, int relu, void* stream) {
+  SVLA_REQUIRE(x && gamma && beta && (out_bf16 || out_f32), "svla_layernorm: null pointer");
+  SVLA_REQUIRE(rows > 0 && cols > 0 && (cols % 4) == 0 && cols <= kRowThreads * kMaxVec * 4, "svla_layernorm: cols=%d unsupported", cols);
+  svla_layernorm_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, gamma, beta, eps, cols, static_cast<__nv_bfloat16*>(out_bf16), out_f32, relu);
+  SVLA_LAUNCH_CHECK("svla_layernorm");
+  return 0;
+}
+
+extern "C" int svla_rmsnorm_residual(float* x, const float* branch, const float* w_post, const float* w_pre, float eps,
+                                     int64_t rows, int cols, void* out_bf16, void* stream) {
+  SVLA_REQUIRE(x, "svla_rmsnorm_residual: null x");
+  SVLA_REQUIRE((branch == nullptr) == (w_post == nullptr), "svla_rmsnorm_residual: branch and w_post go together");
+  SVLA_REQUIRE((w_pre == nullptr) == (out_bf16 == nullptr), "svla_rmsnorm_residual: w_pre and out_bf16 go together");
+  SVLA_REQUIRE(rows > 0 && cols > 0 && (cols % 4) == 0 && cols <= kRowThreads * kMaxVec * 4, "svla_rmsnorm_residual: cols=%d unsupported", cols);
+  svla_rmsnorm_residual_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, branch, w_post, w_pre, eps, cols, static_cast<__nv_bfloat16*>(out_bf16));
+  SVLA_LAUNCH_CHECK("svla_rmsnorm_residual");
+  return 0;
+}
+
+extern "C" int svla_rope_kv(const void* qkv, void* q_out, void* kcache, void* vcache, int batch, int s, int hq, int hkv, int d,
+                            int smax, int pos0, float theta, void* stream) {
+  SVLA_REQUIRE(qkv && q_out && kcache && vcache, "svla_rope_kv: null pointer");
+  SVLA_REQUIRE(batch > 0 && s > 0 && (d % 2) == 0 && pos0 >= 0 && pos0 + s <= smax, "svla_rope_kv: bad geometry (pos0=%d s=%d smax=%d)", pos0, s, smax);
+  svla_rope_kv_kernel<<<static_cast<unsigned>(batch) * s, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(q_out), static_cast<__nv_bfloat16*>(kcache),
+      static_cast<__nv_bfloat16*>(vcache), s, hq, hkv, d, smax, pos0, theta);
+  SVLA_LAUNCH_CHECK("svla_rope_kv");
+  return 0;
+}
+
+extern "C" int svla_embed_tokens(const int64_t* ids, const void* embed, const void* spatial_embed, const float* image_feats,
+                                 float* x, int batch, int s, int hdim, int64_t vocab, int64_t image_token, int64_t act_lo,
+                                 int64_t n_act, int n_img, float normalizer, int* status_flag, void* stream) {
+  SVLA_REQUIRE(ids && embed && x, "svla_embed_tokens: null pointer");
+  SVLA_REQUIRE(batch > 0 && s > 0 && hdim > 0, "svla_embed_tokens: empty problem");
+  svla_embed_kernel<<<static_cast<unsigned>(batch) * s, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), static_cast<const __nv_bfloat16*>(embed),
+      static_cast<const __nv_bfloat16*>(spatial_embed), image_feats, x, s, hdim, vocab, image_token, act_lo, n_act, n_img,
+      normalizer, status_flag);
+  SVLA_LAUNCH_CHECK("svla_embed_tokens");
+  return 0;
+}
+
+extern "C" int svla_argmax_rows(const float* logits, int64_t rows, int64_t cols, int64_t ld, int64_t id_offset, int64_t* out_ids,
+                                int64_t out_stride, void* stream) {
+  SVLA_REQUIRE(logits && out_ids && rows > 0 && cols > 0, "svla_argmax_rows: bad arguments");
+  svla_argmax_kernel<<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, cols, ld, id_offset, reinterpret_cast<long long*>(out_ids), out_stride);
+  SVLA_LAUNCH_CHECK("svla_argmax_rows");
+  return 0;
+}
+
+extern "C" int svla_siglip_patchify(const float* px, void* a, int batch, int kpad, void* stream) {
+  SVLA_REQUIRE(px && a && batch > 0 && kpad >= 588, "svla_siglip_patchify: bad arguments");
+  svla_siglip_patchify_kernel<<<static_cast<unsigned>(batch) * 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      px, static_cast<__nv_bfloat16*>(a), kpad);
+  SVLA_LAUNCH_CHECK("svla_siglip_patchify");
+  return 0;
+}
+
+extern "C" int svla_zoe_patchify(const float* px, void* a, int batch, void* stream) {
+  SVLA_REQUIRE(px && a && batch > 0, "svla_zoe_patchify: bad arguments");
+  svla_zoe_patchify_kernel<<<static_cast<unsigned>(batch) * 576, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      px, static_cast<__nv_bfloat16*>(a));
+  SVLA_LAUNCH_CHECK("svla_zoe_patchify");
+  return 0;
+}
+
+extern "C" int svla_beit_assemble(const float* patches, const float* cls, float* x, int batch, int n, int c, void* stream) {
+  SVLA_REQUIRE(patches && cls && x && batch > 0 && n > 0 && c > 0, "svla_beit_assemble: bad arguments");
+  svla_beit_assemble_kernel<<<static_cast<unsigned>(batch) * (n + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(patches, cls, x, n, c);
+  SVLA_LAUNCH_CHECK("svla_beit_assemble");
+  return 0;
+}
+
+extern "C" int svla_readout_concat(const float* hs, void* a, int batch, int n, int c, void* stream) {
+  SVLA_REQUIRE(hs && a && batch > 0 && n > 0 && c > 0, "svla_readout_concat: bad arguments");
+  svla_readout_concat_kernel<<<static_cast<unsigned>(batch) * n, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      hs, static_cast<__nv_bfloat16*>(a), n, c);
+  SVLA_LAUNCH_CHECK("svla_readout_concat");
+  return 0;
+}
+
+extern "C" int svla_pixel_shuffle(const void* g, void* out, int batch, int h, int w, int c, int f, void* stream) {
+  SVLA_REQUIRE(g && out && batch > 0 && (c % 8) == 0 && f > 0, "svla_pixel_shuffle: bad arguments");
+  const long long total = static_cast<long long>(batch) * h * f * w * f * (c / 8);
+  svla_pixel_shuffle_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(g), static_cast<uint4*>(out), h, w, c / 8, f, total);
+  SVLA_LAUNCH_CHECK("svla_pixel_shuffle");
+  return 0;
+}
+
+extern "C" int svla_im2col3x3_s2(const void* x, void* a, int batch, int h, int w, int c, void* stream) {
+  SVLA_REQUIRE(x && a && batch > 0 && (c % 8) == 0 && (h % 2) == 0 && (w % 2) == 0, "svla_im2col3x3_s2: bad arguments");
+  const long long total = static_cast<long long>(batch) * (h / 2) * (w / 2) * 9 * (c / 8);
+  svla_im2col3x3_s2_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(a), h, w, c / 8, total);
+  SVLA_LAUNCH_CHECK("svla_im2col3x3_s2");
+  return 0;
+}
+
+extern "C" int svla_bilinear_nhwc(const void* x, const void* add, void* out, void* out_relu, int batch, int h, int w, int c,
+                                  int oh, int ow, void* stream) {
+  SVLA_REQUIRE(x && (out || out_relu) && batch > 0 && (c % 8) == 0, "svla_bilinear_nhwc: bad arguments");
+  const long long total = static_cast<long long>(batch) * oh * ow * (c / 8);
+  svla_bilinear_nhwc_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<const uint4*>(add), static_cast<uint4*>(out), static_cast<uint4*>(out_relu), h, w,
+      c / 8, oh, ow, total);
+  SVLA_LAUNCH_CHECK("svla_bilinear_nhwc");
+  return 0;
+}
+
+extern "C" int svla_relu_bf16(const void* x, void* out, int64_t n, void* stream) {
+  SVLA_REQUIRE(x && out && n > 0 && (n % 2) == 0, "svla_relu_bf16: bad arguments");
+  svla_relu_bf16_kernel<<<blocks_for(n / 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat162*>(x), static_cast<__nv_bfloat162*>(out), n / 2);
+  SVLA_LAUNCH_CHECK("svla_relu_bf16");
+  return 0;
+}
+
+extern "C" int svla_softplus_f32(const void* x, float* out, int64_t n, void* stream) {
+  SVLA_REQUIRE(x && out && n > 0, "svla_softplus_f32: bad arguments");
+  svla_softplus_f32_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), out, n);
+  SVLA_LAUNCH_CHECK("svla_softplus_f32");
+  return 0;
+}
+
+extern "C" int svla_zoe_router_embed(const float* conv, float* e, void* e_bf16, int batch, int n, int c, void* stream) {
+  SVLA_REQUIRE(conv && e && batch > 0 && n > 0 && (c % 2) == 0, "svla_zoe_router_embed: bad arguments");
+  svla_zoe_router_embed_kernel<<<static_cast<unsigned>(batch) * (n + 1), 128, 0, static_cast<cudaStream_t>(stream)>>>(conv, e, static_cast<__nv_bfloat16*>(e_bf16), n, c);
+  SVLA_LAUNCH_CHECK("svla_zoe_router_embed");
+  return 0;
+}
+
+extern "C" int svla_zoe_attractor(const void* attr, const float* prev, float* out, int batch, int h, int w, int oh, int ow, int na,
+                                  int nbins, void* stream) {
+  SVLA_REQUIRE(attr && prev && out && batch > 0 && na > 0 && na <= 32 && nbins > 0, "svla_zoe_attractor: bad arguments");
+  const long long npix = static_cast<long long>(batch) * oh * ow;
+  const long long want = (npix + 7) / 8;
+  const unsigned blocks = static_cast<unsigned>(want < 148LL * 32 ? want : 148LL * 32);
+  svla_zoe_attractor_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(attr), prev, out, h, w, oh, ow, na, nbins, npix);
+  SVLA_LAUNCH_CHECK("svla_zoe_attractor");
+  return 0;
+}
+
+extern "C" int svla_zoe_depth_tail(const void* t, const void* e, const float* b1, const float* w2, const float* b2,
+                                   const float* bins, float* depth, int batch, int h, int w, int oh, int ow, int nh, int nbins,
+                                   float min_temp, float max_temp, void* stream) {
+  SVLA_REQUIRE(t && e && b1 && w2 && b2 && bins && depth, "svla_zoe_depth_tail: null pointer");
+  SVLA_REQUIRE(batch > 0 && nbins > 0 && nbins <= 64 && nh > 0, "svla_zoe_depth_tail: bad geometry");
+  const long long npix = static_cast<long long>(batch) * oh * ow;
+  const long long want = (npix + 7) / 8;
+  const unsigned blocks = static_cast<unsigned>(want < 148LL * 32 ? want : 148LL * 32);
+  svla_zoe_depth_tail_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(t), static_cast<const __nv_bfloat16*>(e), b1, w2, b2, bins, depth, h, w, oh, ow, nh, nbins,
+      min_temp, max_temp, npix);
+  SVLA_LAUNCH_CHECK("svla_zoe_depth_tail");
+  return 0;
+}
+
+extern "C" int svla_ego3d_encode(const float* depth384, const float* intrinsic, int k_stride, float* xyz, void* enc, int batch,
+                                 int kpad, int n_freqs, void* stream) {
+  SVLA_REQUIRE(depth384 && intrinsic && xyz && enc && batch > 0, "svla_ego3d_encode: bad arguments");
+  SVLA_REQUIRE(kpad >= 12 * (2 * n_freqs + 1) && (k_stride == 0 || k_stride == 9), "svla_ego3d_encode: bad kpad / k_stride");
+  dim3 grid(32, batch);
+  svla_ego3d_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(depth384, intrinsic, k_stride, xyz,
+                                                                        static_cast<__nv_bfloat16*>(enc), kpad, n_freqs);
+  SVLA_LAUNCH_CHECK("svla_ego3d_encode");
+  return 0;
+}

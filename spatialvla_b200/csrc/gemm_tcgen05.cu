@@ -1,0 +1,637 @@
+// G1: bf16 GEMM  D = epilogue(A[M,K] * W[N,K]^T)  on Blackwell 5th-gen tensor cores.
+//
+//   * tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x BN x 16, fp32 accumulators in TMEM (double buffered:
+//     2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * A and W tiles (128x64 / BNx64 bf16, K-major) staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) through an
+//     mbarrier ring of kStages stages; TMA zero-fills every M/N/K tail, so ragged shapes need no host padding;
+//   * warp-specialised persistent CTA (192 threads): warp0 = TMA producer, warp1 = TMEM allocator + MMA issuer,
+//     warps2-5 = epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> 128-bit global stores);
+//   * implicit 3x3 convolution mode: the A tile of a tap is a 4-D TMA box {64 ch, 16 w, 8 h, 1 n} of the NHWC
+//     activation shifted by the tap offset -- the TMA out-of-bounds zero fill *is* the conv padding, there is
+//     no im2col buffer.  The K loop runs over 9 taps x (C/64) channel chunks.
+//
+// Reference ops replaced: see include/spatialvla_b200.h (svla_gemm).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include "svla_common.cuh"
+
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;             // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 192;
+constexpr int kConvTileW = 16, kConvTileH = 8;
+constexpr uint32_t kSpinLimit = 1u << 28;
+
+template <int BN> struct Cfg {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct EpiParams {
+  const float* bias;
+  const float* colscale;
+  const __nv_bfloat16* res_bf16;
+  const __nv_bfloat16* res2_bf16;
+  const float* res_f32;
+  long long res_mod;
+  __nv_bfloat16* out_bf16;
+  float* out_f32;
+  __nv_bfloat16* out_relu;
+  long long m, n, ldo;
+  float alpha, act_param;
+  int act, flags;
+  // conv geometry
+  int nb, h, wd, tiles_h, tiles_w;
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < kSpinLimit; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  // A pipeline bug must surface as a launch failure, never as a hung GPU box.
+  printf("svla_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  __trap();
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS> __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+template <int COLS> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS));
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (ignored for swizzled K-major, canonical value 1) | [32,46) SBO>>4 = 1024B>>4
+//   [46,48) version = 1 (sm100) | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------ fused epilogue
+__device__ __forceinline__ float apply_act(float v, int act, float p) {
+  switch (act) {
+    case SVLA_ACT_GELU_TANH: return gelu_tanh_f(v);
+    case SVLA_ACT_GELU_ERF: return gelu_erf_f(v);
+    case SVLA_ACT_RELU: return fmaxf(v, 0.f);
+    case SVLA_ACT_SOFTCAP: return p * tanhf(v / p);
+    case SVLA_ACT_SOFTPLUS: return softplus_f(v);
+    default: return v;
+  }
+}
+
+// One output row, 32 consecutive accumulator columns starting at n0 (global column). `grow` = global output row.
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, const float (&acc)[32], long long grow, long long n0) {
+  const bool geglu = (ep.flags & SVLA_GEMM_GEGLU) != 0;
+  const bool accum = (ep.flags & SVLA_GEMM_ACCUM_F32) != 0;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const long long n = n0 + j;
+    float x = acc[j] * ep.alpha;
+    if (n < ep.n) {
+      if (ep.bias) x += __ldg(ep.bias + n);
+      if (!geglu) x = apply_act(x, ep.act, ep.act_param);
+      if (ep.colscale) x *= __ldg(ep.colscale + n);
+    }
+    v[j] = x;
+  }
+  if (geglu) {
+    // columns (2j, 2j+1) = (gate_j, up_j): out[:, n0/2 + j] = gelu_tanh(gate) * up
+    const long long o0 = n0 >> 1;
+    const long long on = ep.n >> 1;
+    __nv_bfloat16* dst = ep.out_bf16 + grow * ep.ldo + o0;
+    if (o0 + 16 <= on && (ep.ldo & 7) == 0) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        pk[j] = pack_bf16x2(gelu_tanh_f(v[4 * j]) * v[4 * j + 1], gelu_tanh_f(v[4 * j + 2]) * v[4 * j + 3]);
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+      d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    } else {
+      for (int j = 0; j < 16; ++j)
+        if (o0 + j < on) dst[j] = __float2bfloat16(gelu_tanh_f(v[2 * j]) * v[2 * j + 1]);
+    }
+    return;
+  }
+  const long long off = grow * ep.ldo + n0;
+  const long long off_r32 = (ep.res_mod > 0 ? grow % ep.res_mod : grow) * ep.ldo + n0;
+  const bool full = (n0 + 32 <= ep.n) && ((ep.ldo & 7) == 0);
+  if (full) {
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const __nv_bfloat16* rp = which == 0 ? ep.res_bf16 : ep.res2_bf16;
+      if (rp == nullptr) continue;
+      const uint4* r4 = reinterpret_cast<const uint4*>(rp + off);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 t = __ldg(r4 + q);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[q * 8 + 2 * e] += bf16_bits_to_float(w[e] & 0xFFFFu);
+          v[q * 8 + 2 * e + 1] += bf16_bits_to_float(w[e] >> 16);
+        }
+      }
+    }
+    if (ep.res_f32) {
+      const float4* r4 = reinterpret_cast<const float4*>(ep.res_f32 + off_r32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = __ldg(r4 + q);
+        v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+      }
+    }
+    if (ep.out_f32) {
+      float4* o4 = reinterpret_cast<float4*>(ep.out_f32 + off);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (accum) {
+          const float4 t = o4[q];
+          v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+        }
+        o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    }
+    if (ep.out_bf16) {
+      uint4* o4 = reinterpret_cast<uint4*>(ep.out_bf16 + off);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        o4[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                           pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+    }
+    if (ep.out_relu) {
+      uint4* o4 = reinterpret_cast<uint4*>(ep.out_relu + off);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        o4[q] = make_uint4(pack_bf16x2(fmaxf(v[8 * q], 0.f), fmaxf(v[8 * q + 1], 0.f)),
+                           pack_bf16x2(fmaxf(v[8 * q + 2], 0.f), fmaxf(v[8 * q + 3], 0.f)),
+                           pack_bf16x2(fmaxf(v[8 * q + 4], 0.f), fmaxf(v[8 * q + 5], 0.f)),
+                           pack_bf16x2(fmaxf(v[8 * q + 6], 0.f), fmaxf(v[8 * q + 7], 0.f)));
+    }
+  } else {
+    for (int j = 0; j < 32; ++j) {
+      const long long n = n0 + j;
+      if (n >= ep.n) break;
+      float x = v[j];
+      if (ep.res_bf16) x += __bfloat162float(ep.res_bf16[off + j]);
+      if (ep.res2_bf16) x += __bfloat162float(ep.res2_bf16[off + j]);
+      if (ep.res_f32) x += ep.res_f32[off_r32 + j];
+      if (ep.out_f32) {
+        if (accum) x += ep.out_f32[off + j];
+        ep.out_f32[off + j] = x;
+      }
+      if (ep.out_bf16) ep.out_bf16[off + j] = __float2bfloat16(x);
+      if (ep.out_relu) ep.out_relu[off + j] = __float2bfloat16(fmaxf(x, 0.f));
+    }
+  }
+}
+
+// Global output row of tile row r (and validity) in linear / conv mode.
+__device__ __forceinline__ bool tile_row_to_global(const EpiParams& ep, bool conv, long long m_tile, int r, long long& grow) {
+  if (!conv) {
+    grow = m_tile * kBM + r;
+    return grow < ep.m;
+  }
+  const int tiles_per_img = ep.tiles_h * ep.tiles_w;
+  const int img = static_cast<int>(m_tile / tiles_per_img);
+  const int rem = static_cast<int>(m_tile % tiles_per_img);
+  const int hh = (rem / ep.tiles_w) * kConvTileH + r / kConvTileW;
+  const int ww = (rem % ep.tiles_w) * kConvTileW + r % kConvTileW;
+  grow = (static_cast<long long>(img) * ep.h + hh) * ep.wd + ww;
+  return hh < ep.h && ww < ep.wd && img < ep.nb;
+}
+
+// ------------------------------------------------------------------------------------------ the kernel
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                         const EpiParams ep, const long long num_m_tiles, const long long num_n_tiles,
+                         const int num_k_blocks, const int conv, const int c_chunks) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned stage bases
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kStages * C::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tmem_full = bars + 2 * C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+#pragma unroll 1
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 4);
+    mbar_init(&tmem_empty[1], 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const long long num_tiles = num_m_tiles * num_n_tiles;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (one lane)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long m_tile = tile % num_m_tiles;
+        const long long n_tile = tile / num_m_tiles;
+        int img = 0, h0 = 0, w0 = 0;
+        if (conv) {
+          const int tiles_per_img = ep.tiles_h * ep.tiles_w;
+          img = static_cast<int>(m_tile / tiles_per_img);
+          const int rem = static_cast<int>(m_tile % tiles_per_img);
+          h0 = (rem / ep.tiles_w) * kConvTileH;
+          w0 = (rem % ep.tiles_w) * kConvTileW;
+        }
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          if (conv) {
+            const int tap = kb / c_chunks, cc = kb - tap * c_chunks;
+            tma_load_4d(smem_a + stage * C::kABytes, &tm_a, &full_bar[stage], cc * kBK, w0 + (tap % 3) - 1,
+                        h0 + (tap / 3) - 1, img);
+          } else {
+            tma_load_2d(smem_a + stage * C::kABytes, &tm_a, &full_bar[stage], kb * kBK, static_cast<int>(m_tile * kBM));
+          }
+          tma_load_2d(smem_b + stage * C::kBBytes, &tm_b, &full_bar[stage], kb * kBK, static_cast<int>(n_tile * BN));
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (one lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+        mbar_wait(&tmem_empty[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + stage * C::kABytes));
+          const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + stage * C::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                      static_cast<uint32_t>((kb | k) != 0));
+          }
+          umma_commit(&empty_bar[stage]);      // frees the smem stage once these MMAs have read it
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tmem_full[as]);           // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps 2..5 (TMEM lane group = warp % 4)
+    const int q = warp & 3;
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const long long m_tile = tile % num_m_tiles;
+      const long long n_tile = tile / num_m_tiles;
+      const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      long long grow;
+      const bool row_ok = tile_row_to_global(ep, conv != 0, m_tile, q * 32 + lane, grow);
+      const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const long long n0 = n_tile * BN + c0;
+        if (n0 >= ep.n) break;                 // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        if (row_ok) {
+          float acc[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+          epilogue_chunk(ep, acc, grow, n0);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ SIMT debug kernel
+// Straightforward one-thread-per-output kernel with the same epilogue; used by tests only (args->impl == 1) so
+// that the rest of the path can be validated independently of the tcgen05 kernel.
+__global__ void svla_gemm_simt_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ w,
+                                      EpiParams ep, long long k, long long lda, long long ldw, int conv, int c, int cpad) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const bool geglu = (ep.flags & SVLA_GEMM_GEGLU) != 0;
+  const long long ncols = geglu ? (ep.n >> 1) : ep.n;
+  if (idx >= ep.m * ncols) return;
+  const long long row = idx / ncols, col = idx % ncols;
+  auto dot = [&](long long n) {
+    float acc = 0.f;
+    if (!conv) {
+      for (long long kk = 0; kk < k; ++kk) acc += __bfloat162float(a[row * lda + kk]) * __bfloat162float(w[n * ldw + kk]);
+    } else {
+      const int ww = static_cast<int>(row % ep.wd), hh = static_cast<int>((row / ep.wd) % ep.h);
+      const long long img = row / (static_cast<long long>(ep.wd) * ep.h);
+      for (int tap = 0; tap < 9; ++tap) {
+        const int y = hh + tap / 3 - 1, x = ww + tap % 3 - 1;
+        if (y < 0 || y >= ep.h || x < 0 || x >= ep.wd) continue;
+        const __nv_bfloat16* ap = a + ((img * ep.h + y) * ep.wd + x) * c;
+        const __nv_bfloat16* wp = w + n * ldw + tap * cpad;
+        for (int ci = 0; ci < c; ++ci) acc += __bfloat162float(ap[ci]) * __bfloat162float(wp[ci]);
+      }
+    }
+    return acc;
+  };
+  auto pre = [&](float x, long long n) {
+    x *= ep.alpha;
+    if (ep.bias) x += ep.bias[n];
+    if (!geglu) x = apply_act(x, ep.act, ep.act_param);
+    if (ep.colscale) x *= ep.colscale[n];
+    return x;
+  };
+  if (geglu) {
+    const float g = pre(dot(2 * col), 2 * col), u = pre(dot(2 * col + 1), 2 * col + 1);
+    ep.out_bf16[row * ep.ldo + col] = __float2bfloat16(gelu_tanh_f(g) * u);
+    return;
+  }
+  float x = pre(dot(col), col);
+  const long long off = row * ep.ldo + col;
+  if (ep.res_bf16) x += __bfloat162float(ep.res_bf16[off]);
+  if (ep.res2_bf16) x += __bfloat162float(ep.res2_bf16[off]);
+  if (ep.res_f32) x += ep.res_f32[(ep.res_mod > 0 ? row % ep.res_mod : row) * ep.ldo + col];
+  if (ep.out_f32) {
+    if (ep.flags & SVLA_GEMM_ACCUM_F32) x += ep.out_f32[off];
+    ep.out_f32[off] = x;
+  }
+  if (ep.out_bf16) ep.out_bf16[off] = __float2bfloat16(x);
+  if (ep.out_relu) ep.out_relu[off] = __float2bfloat16(fmaxf(x, 0.f));
+}
+
+// ------------------------------------------------------------------------------------------ host side
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems, uint32_t box_inner,
+              uint32_t box_outer) {
+  auto fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 100;
+}
+
+int encode_nhwc(CUtensorMap* tm, const void* base, int nb, int h, int w, int c) {
+  auto fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
+                        static_cast<cuuint64_t>(nb)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w) * c * 2,
+                           static_cast<cuuint64_t>(h) * w * c * 2};
+  cuuint32_t box[4] = {kBK, kConvTileW, kConvTileH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 100;
+}
+
+template <int BN>
+int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& ep, long long mt, long long nt, int kb,
+              int conv, int c_chunks, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(svla_gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::kSmemBytes);
+    if (e != cudaSuccess) {
+      svla_set_error("svla_gemm: cudaFuncSetAttribute(%d bytes) failed: %s", C::kSmemBytes, cudaGetErrorString(e));
+      return -2;
+    }
+    configured = true;
+  }
+  const long long tiles = mt * nt;
+  const int grid = static_cast<int>(tiles < svla_num_sms() ? tiles : svla_num_sms());
+  svla_gemm_tcgen05_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, ep, mt, nt, kb, conv, c_chunks);
+  SVLA_LAUNCH_CHECK("svla_gemm_tcgen05");
+  return 0;
+}
+
+int pick_block_n(long long m_tiles, long long n) {
+  if (n <= 32) return 32;
+  if (n <= 64) return 64;
+  const int sms = svla_num_sms();
+  long long best_cost = -1;
+  int best = 128;
+  for (int bn : {256, 128}) {
+    const long long tiles = m_tiles * ((n + bn - 1) / bn);
+    const long long cost = ((tiles + sms - 1) / sms) * bn;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+}  // namespace
+
+extern "C" int svla_gemm(const SvlaGemmArgs* g, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SVLA_REQUIRE(g && g->a && g->w, "svla_gemm: null operand");
+  SVLA_REQUIRE(g->m > 0 && g->n > 0 && g->k > 0, "svla_gemm: empty problem m=%lld n=%lld k=%lld", (long long)g->m,
+               (long long)g->n, (long long)g->k);
+  const bool conv = (g->flags & SVLA_GEMM_CONV3X3) != 0;
+  const bool geglu = (g->flags & SVLA_GEMM_GEGLU) != 0;
+  SVLA_REQUIRE(!geglu || (g->out_bf16 && !g->out_f32 && !g->out_relu_bf16 && !g->res_bf16 && !g->res2_bf16 && !g->res_f32 && (g->n % 2) == 0),
+               "svla_gemm: GEGLU mode needs out_bf16 only and even n");
+  SVLA_REQUIRE(g->out_bf16 || g->out_f32 || g->out_relu_bf16, "svla_gemm: no output");
+  SVLA_REQUIRE(!(g->flags & SVLA_GEMM_ACCUM_F32) || g->out_f32, "svla_gemm: ACCUM_F32 needs out_f32");
+
+  EpiParams ep{};
+  ep.bias = g->bias; ep.colscale = g->colscale;
+  ep.res_bf16 = static_cast<const __nv_bfloat16*>(g->res_bf16); ep.res_f32 = g->res_f32;
+  ep.res2_bf16 = static_cast<const __nv_bfloat16*>(g->res2_bf16); ep.res_mod = g->res_mod;
+  ep.out_bf16 = static_cast<__nv_bfloat16*>(g->out_bf16); ep.out_f32 = g->out_f32;
+  ep.out_relu = static_cast<__nv_bfloat16*>(g->out_relu_bf16);
+  ep.m = g->m; ep.n = g->n; ep.ldo = g->ldo;
+  ep.alpha = g->alpha; ep.act_param = g->act_param; ep.act = g->act; ep.flags = g->flags;
+  int cpad = 0, c_chunks = 1;
+  if (conv) {
+    SVLA_REQUIRE(g->nb > 0 && g->h > 0 && g->wd > 0 && g->c > 0 && (g->c % 8) == 0, "svla_gemm: bad conv geometry");
+    SVLA_REQUIRE(g->m == static_cast<int64_t>(g->nb) * g->h * g->wd, "svla_gemm: conv m != nb*h*w");
+    cpad = (g->c + kBK - 1) / kBK * kBK;
+    c_chunks = cpad / kBK;
+    SVLA_REQUIRE(g->k == 9LL * cpad && g->ldw >= g->k, "svla_gemm: conv weight must be [n][9][%d]", cpad);
+    ep.nb = g->nb; ep.h = g->h; ep.wd = g->wd;
+    ep.tiles_h = (g->h + kConvTileH - 1) / kConvTileH;
+    ep.tiles_w = (g->wd + kConvTileW - 1) / kConvTileW;
+  } else {
+    SVLA_REQUIRE(g->lda >= g->k && (g->lda % 8) == 0, "svla_gemm: lda=%lld must be >= k and a multiple of 8", (long long)g->lda);
+  }
+  SVLA_REQUIRE(g->ldw >= g->k && (g->ldw % 8) == 0, "svla_gemm: ldw=%lld must be >= k and a multiple of 8", (long long)g->ldw);
+  SVLA_REQUIRE((reinterpret_cast<uintptr_t>(g->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g->w) & 15) == 0,
+               "svla_gemm: operands must be 16-byte aligned");
+
+  if (g->impl == 1) {
+    const long long ncols = geglu ? g->n / 2 : g->n;
+    const long long total = g->m * ncols;
+    const int threads = 128;
+    const long long blocks = (total + threads - 1) / threads;
+    svla_gemm_simt_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(g->a), static_cast<const __nv_bfloat16*>(g->w), ep, g->k, g->lda, g->ldw,
+        conv ? 1 : 0, g->c, cpad);
+    SVLA_LAUNCH_CHECK("svla_gemm_simt");
+    return 0;
+  }
+
+  const long long m_tiles = conv ? static_cast<long long>(g->nb) * ep.tiles_h * ep.tiles_w : (g->m + kBM - 1) / kBM;
+  int bn = g->block_n ? g->block_n : pick_block_n(m_tiles, g->n);
+  SVLA_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "svla_gemm: block_n=%d unsupported", bn);
+  const long long n_tiles = (g->n + bn - 1) / bn;
+  const int kblocks = conv ? 9 * c_chunks : static_cast<int>((g->k + kBK - 1) / kBK);
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (conv) rc = encode_nhwc(&ta, g->a, g->nb, g->h, g->wd, g->c);
+  else rc = encode_2d(&ta, g->a, static_cast<uint64_t>(g->k), static_cast<uint64_t>(g->m), static_cast<uint64_t>(g->lda), kBK, kBM);
+  SVLA_REQUIRE(rc == 0, "svla_gemm: cuTensorMapEncodeTiled(A) failed (%d)", rc);
+  rc = encode_2d(&tb, g->w, static_cast<uint64_t>(g->k), static_cast<uint64_t>(g->n), static_cast<uint64_t>(g->ldw), kBK,
+                 static_cast<uint32_t>(bn));
+  SVLA_REQUIRE(rc == 0, "svla_gemm: cuTensorMapEncodeTiled(W) failed (%d)", rc);
+
+  switch (bn) {
+    case 32: return launch_tc<32>(ta, tb, ep, m_tiles, n_tiles, kblocks, conv ? 1 : 0, c_chunks, st);
+    case 64: return launch_tc<64>(ta, tb, ep, m_tiles, n_tiles, kblocks, conv ? 1 : 0, c_chunks, st);
+    case 128: return launch_tc<128>(ta, tb, ep, m_tiles, n_tiles, kblocks, conv ? 1 : 0, c_chunks, st);
+    default: return launch_tc<256>(ta, tb, ep, m_tiles, n_tiles, kblocks, conv ? 1 : 0, c_chunks, st);
+  }
+}

@@ -1,0 +1,77 @@
+// Shared helpers for the spatialvla_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/spatialvla_b200.h"
+
+void svla_set_error(const char* fmt, ...);
+void svla_count_launch(int n = 1);
+
+// Every launch goes through this: records the launch (gpu_launches claim) and maps CUDA errors to the ABI.
+#define SVLA_LAUNCH_CHECK(name)                                                          \
+  do {                                                                                   \
+    svla_count_launch();                                                                 \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      svla_set_error("%s: launch failed: %s", name, cudaGetErrorString(_e));             \
+      return -2;                                                                         \
+    }                                                                                    \
+  } while (0)
+
+#define SVLA_REQUIRE(cond, ...)                                                          \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      svla_set_error(__VA_ARGS__);                                                       \
+      return -1;                                                                         \
+    }                                                                                    \
+  } while (0)
+
+static inline int svla_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t bits16) { return __uint_as_float(bits16 << 16); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32). `sh` needs 33 floats.
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  float t = (lane < nw) ? sh[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * x * (1.f + tanhf(k0 * (x + k1 * x * x * x)));
+}
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }

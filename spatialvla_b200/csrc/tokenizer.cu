@@ -1,0 +1,205 @@
+// M8: SpatialActionTokenizer adaptive-grid lookup and inverse in FP64.
+// Reference: model/action_tokenizer.py:105-137 (translation, spherical), :177-202 (rotation), :227-243 (gripper),
+// :305-333 (SpatialActionTokenizer.__call__ / decode_token_ids_to_actions).
+// HBM-bound: encode reads 56 B and writes 12 B per action, decode reads 24 B and writes 56 B.
+// IEEE add/mul/sqrt are issued through the _rn intrinsics so nvcc cannot contract them into FMAs: the sums of
+// squares are then bit-identical to numpy's; only atan2 / sin / cos can differ from glibc in the last ulp.
+#include "svla_common.cuh"
+
+namespace {
+
+constexpr int kMaxEdges = 6 * 65;
+
+struct TokGrid {
+  int nb[7];
+  int off[6];
+};
+
+__device__ __forceinline__ int digitize_right_open(double v, const double* __restrict__ e, int n) {
+  // number of edges e[0..n) that are <= v  (== np.digitize(v, e) for increasing e; NaN -> n like numpy's searchsorted)
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (e[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return (v != v) ? n : lo;
+}
+
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
+__global__ void __launch_bounds__(256)
+svla_tok_encode_kernel(const double* __restrict__ actions, const double* __restrict__ edges, TokGrid g, int* __restrict__ ids,
+                       long long n, double amin, double amax) {
+  __shared__ double se[kMaxEdges];
+  int total = g.off[5] + g.nb[5] + 1;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) se[i] = edges[i];
+  __syncthreads();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    const double* a = actions + i * 7;
+    const double x = clampd(a[0], amin, amax), y = clampd(a[1], amin, amax), z = clampd(a[2], amin, amax);
+    const double xx = __dmul_rn(x, x), yy = __dmul_rn(y, y), zz = __dmul_rn(z, z);
+    const double sxy = __dadd_rn(xx, yy);
+    const double theta = atan2(sqrt(sxy), z);
+    const double phi = atan2(y, x);
+    const double r = sqrt(__dadd_rn(sxy, zz));
+    // translation uses the interior edges e[1:-1]
+    const int dt = digitize_right_open(theta, se + g.off[0] + 1, g.nb[0] - 1);
+    const int dp = digitize_right_open(phi, se + g.off[1] + 1, g.nb[1] - 1);
+    const int dr = digitize_right_open(r, se + g.off[2] + 1, g.nb[2] - 1);
+    const int tid = dt * (g.nb[1] * g.nb[2]) + dp * g.nb[2] + dr;
+    int d3[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double v = clampd(a[3 + c], amin, amax);
+      int d = digitize_right_open(v, se + g.off[3 + c], g.nb[3 + c] + 1) - 1;
+      d3[c] = min(max(d, 0), g.nb[3 + c] - 1);
+    }
+    const int n_trans = g.nb[0] * g.nb[1] * g.nb[2];
+    const int n_rot = g.nb[3] * g.nb[4] * g.nb[5];
+    const int rid = d3[0] * (g.nb[4] * g.nb[5]) + d3[1] * g.nb[5] + d3[2] + n_trans;
+    const int gid = (clampd(a[6], amin, amax) >= 0.5 ? 1 : 0) + n_trans + n_rot;
+    ids[i * 3 + 0] = tid;
+    ids[i * 3 + 1] = rid;
+    ids[i * 3 + 2] = gid;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+svla_tok_decode_kernel(const long long* __restrict__ ids, const double* __restrict__ edges, TokGrid g, long long begin,
+                       double* __restrict__ actions, long long n) {
+  __shared__ double se[kMaxEdges];
+  int total = g.off[5] + g.nb[5] + 1;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) se[i] = edges[i];
+  __syncthreads();
+  const long long n_trans = static_cast<long long>(g.nb[0]) * g.nb[1] * g.nb[2];
+  const long long n_rot = static_cast<long long>(g.nb[3]) * g.nb[4] * g.nb[5];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    // clip each id into its sub-range first (model/action_tokenizer.py:126,195,240)
+    long long t = ids[i * 3 + 0] - begin;
+    t = t < 0 ? 0 : (t > n_trans - 1 ? n_trans - 1 : t);
+    const int np_ = g.nb[1] * g.nb[2];
+    const int a = static_cast<int>(t / np_), b = static_cast<int>((t % np_) / g.nb[2]), c = static_cast<int>(t % g.nb[2]);
+    const double th = 0.5 * __dadd_rn(se[g.off[0] + a], se[g.off[0] + a + 1]);
+    const double ph = 0.5 * __dadd_rn(se[g.off[1] + b], se[g.off[1] + b + 1]);
+    const double rr = 0.5 * __dadd_rn(se[g.off[2] + c], se[g.off[2] + c + 1]);
+    const double st = sin(th), ct = cos(th), sp = sin(ph), cp = cos(ph);
+    double x = __dmul_rn(__dmul_rn(rr, st), cp);
+    double y = __dmul_rn(__dmul_rn(rr, st), sp);
+    double z = __dmul_rn(rr, ct);
+    double* o = actions + i * 7;
+    o[0] = clampd(x, -1.0, 1.0);
+    o[1] = clampd(y, -1.0, 1.0);
+    o[2] = clampd(z, -1.0, 1.0);
+    long long r = ids[i * 3 + 1] - begin;
+    r = r < n_trans ? n_trans : (r > n_trans + n_rot - 1 ? n_trans + n_rot - 1 : r);
+    r -= n_trans;
+    const int nq = g.nb[4] * g.nb[5];
+    const int r0 = static_cast<int>(r / nq), r1 = static_cast<int>((r % nq) / g.nb[5]), r2 = static_cast<int>(r % g.nb[5]);
+    o[3] = 0.5 * __dadd_rn(se[g.off[3] + r0], se[g.off[3] + r0 + 1]);
+    o[4] = 0.5 * __dadd_rn(se[g.off[4] + r1], se[g.off[4] + r1 + 1]);
+    o[5] = 0.5 * __dadd_rn(se[g.off[5] + r2], se[g.off[5] + r2 + 1]);
+    long long gi = ids[i * 3 + 2] - begin;
+    const long long glo = n_trans + n_rot, ghi = n_trans + n_rot + g.nb[6] - 1;
+    gi = gi < glo ? glo : (gi > ghi ? ghi : gi);
+    o[6] = (gi - glo == 0) ? 0.0 : 1.0;
+  }
+}
+
+int make_grid(const int32_t* nbins_host, TokGrid& g) {
+  int off = 0;
+  for (int i = 0; i < 7; ++i) g.nb[i] = nbins_host[i];
+  for (int i = 0; i < 6; ++i) {
+    if (g.nb[i] < 1 || g.nb[i] > 64) return -1;
+    g.off[i] = off;
+    off += g.nb[i] + 1;
+  }
+  return off;
+}
+
+unsigned grid_for(long long n) {
+  long long b = (n + 255) / 256;
+  const long long cap = 148LL * 8;
+  return static_cast<unsigned>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+// nbins is read on the HOST in every variant (it is 7 ints of configuration, never per-sample data).
+extern "C" int svla_tok_encode(const double* actions, const double* edges, const int32_t* nbins, int32_t* ids, int64_t n,
+                               double min_action, double max_action, void* stream) {
+  SVLA_REQUIRE(edges && nbins && (n == 0 || (actions && ids)), "svla_tok_encode: null pointer");
+  SVLA_REQUIRE(n >= 0, "svla_tok_encode: negative n");
+  if (n == 0) return 0;
+  TokGrid g;
+  SVLA_REQUIRE(make_grid(nbins, g) > 0, "svla_tok_encode: bins per axis must be in [1, 64]");
+  svla_tok_encode_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(actions, edges, g, ids, n, min_action, max_action);
+  SVLA_LAUNCH_CHECK("svla_tok_encode");
+  return 0;
+}
+
+extern "C" int svla_tok_decode(const int64_t* ids, const double* edges, const int32_t* nbins, int64_t begin, double* actions,
+                               int64_t n, void* stream) {
+  SVLA_REQUIRE(edges && nbins && (n == 0 || (actions && ids)), "svla_tok_decode: null pointer");
+  SVLA_REQUIRE(n >= 0, "svla_tok_decode: negative n");
+  if (n == 0) return 0;
+  TokGrid g;
+  SVLA_REQUIRE(make_grid(nbins, g) > 0, "svla_tok_decode: bins per axis must be in [1, 64]");
+  svla_tok_decode_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), edges, g, begin, actions, n);
+  SVLA_LAUNCH_CHECK("svla_tok_decode");
+  return 0;
+}
+
+#define SVLA_CUDA_OK(call)                                                        \
+  do {                                                                            \
+    cudaError_t _e = (call);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      svla_set_error("%s failed: %s", #call, cudaGetErrorString(_e));             \
+      rc = -2;                                                                    \
+      goto done;                                                                  \
+    }                                                                             \
+  } while (0)
+
+extern "C" int svla_tok_encode_host(const double* actions_host, const double* edges_host, const int32_t* nbins_host,
+                                    int32_t* ids_host, int64_t n, double min_action, double max_action) {
+  if (n == 0) return 0;
+  TokGrid g;
+  const int ne = make_grid(nbins_host, g);
+  SVLA_REQUIRE(ne > 0, "svla_tok_encode_host: bins per axis must be in [1, 64]");
+  int rc = 0;
+  double *d_a = nullptr, *d_e = nullptr;
+  int32_t* d_i = nullptr;
+  SVLA_CUDA_OK(cudaMalloc(&d_a, sizeof(double) * 7 * n));
+  SVLA_CUDA_OK(cudaMalloc(&d_e, sizeof(double) * ne));
+  SVLA_CUDA_OK(cudaMalloc(&d_i, sizeof(int32_t) * 3 * n));
+  SVLA_CUDA_OK(cudaMemcpy(d_a, actions_host, sizeof(double) * 7 * n, cudaMemcpyHostToDevice));
+  SVLA_CUDA_OK(cudaMemcpy(d_e, edges_host, sizeof(double) * ne, cudaMemcpyHostToDevice));
+  rc = svla_tok_encode(d_a, d_e, nbins_host, d_i, n, min_action, max_action, nullptr);
+  if (rc == 0) SVLA_CUDA_OK(cudaMemcpy(ids_host, d_i, sizeof(int32_t) * 3 * n, cudaMemcpyDeviceToHost));
+done:
+  cudaFree(d_a); cudaFree(d_e); cudaFree(d_i);
+  return rc;
+}
+
+extern "C" int svla_tok_decode_host(const int64_t* ids_host, const double* edges_host, const int32_t* nbins_host, int64_t begin,
+                                    double* actions_host, int64_t n) {
+  if (n == 0) return 0;
+  TokGrid g;
+  const int ne = make_grid(nbins_host, g);
+  SVLA_REQUIRE(ne > 0, "svla_tok_decode_host: bins per axis must be in [1, 64]");
+  int rc = 0;
+  double *d_a = nullptr, *d_e = nullptr;
+  int64_t* d_i = nullptr;
+  SVLA_CUDA_OK(cudaMalloc(&d_a, sizeof(double) * 7 * n));
+  SVLA_CUDA_OK(cudaMalloc(&d_e, sizeof(double) * ne));
+  SVLA_CUDA_OK(cudaMalloc(&d_i, sizeof(int64_t) * 3 * n));
+  SVLA_CUDA_OK(cudaMemcpy(d_i, ids_host, sizeof(int64_t) * 3 * n, cudaMemcpyHostToDevice));
+  SVLA_CUDA_OK(cudaMemcpy(d_e, edges_host, sizeof(double) * ne, cudaMemcpyHostToDevice));
+  rc = svla_tok_decode(d_i, d_e, nbins_host, begin, d_a, n, nullptr);
+  if (rc == 0) SVLA_CUDA_OK(cudaMemcpy(actions_host, d_a, sizeof(double) * 7 * n, cudaMemcpyDeviceToHost));
+done:
+  cudaFree(d_a); cudaFree(d_e); cudaFree(d_i);
+  return rc;
+}

@@ -1,0 +1,549 @@
+"""Host-side orchestration of the predict_action forward path over the C-ABI kernels.
+
+`SpatialVLAEngine` owns the repacked weights (HF state_dict -> kernel layouts, done once) and issues the kernel
+sequence of SURVEY.md §3.1 through an `ops` backend (spatialvla_b200.ops.CudaOps in production):
+
+  pixel_values --siglip_patchify--> GEMM(+pos-emb) -> 27 x [LN, QKV GEMM, attention, out GEMM(+=), LN, fc1 GEMM(gelu),
+                                    fc2 GEMM(+=)] -> LN                                   (SigLIP, a5)
+  pixel_values --zoe_patchify----> BEiT-L (24 blocks, rel-pos attention, layer scale) -> DPT neck (reassemble,
+                                    3x3 implicit-GEMM convs, fusion) -> relative head -> metric bins head  (a6-a8)
+  depth --ego3d_encode--> GEMM -> LN+ReLU -> GEMM (+= SigLIP tokens) -> projector GEMM (x 1/sqrt(H))      (a9-a11)
+  ids --embed_tokens--> 26 x Gemma2 layer (prefill, bidirectional) -> lm_head(action slice)+softcap -> argmax,
+  then n_new-1 decode steps over the static KV cache.                                                   (a12-a18)
+
+Numerics: bf16 GEMM/attention operands, fp32 accumulation, fp32 residual streams / norm statistics / softmax.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from ._lib import ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_RELU, ACT_SOFTCAP, ACT_SOFTPLUS
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _pad_cols(w, kpad):
+    if w.shape[1] == kpad:
+        return w
+    out = torch.zeros(w.shape[0], kpad, dtype=w.dtype, device=w.device)
+    out[:, : w.shape[1]] = w
+    return out
+
+
+def pack_conv3x3(w):
+    """(Cout, Cin, 3, 3) -> [Cout, 9 * cpad] with K index = tap * cpad + ci, tap = ky * 3 + kx, cpad = roundup(Cin, 64)"""
+    co, ci = w.shape[0], w.shape[1]
+    cpad = (ci + 63) // 64 * 64
+    out = torch.zeros(co, 9, cpad, dtype=w.dtype, device=w.device)
+    out[:, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, 9, ci)
+    return out.reshape(co, 9 * cpad)
+
+
+def pack_conv3x3_im2col(w):
+    """(Cout, Cin, 3, 3) -> [Cout, 9 * Cin] matching svla_im2col3x3_s2 (col = tap * Cin + ci)"""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+
+def pack_deconv(w, b):
+    """ConvTranspose2d (Cin, Cout, f, f), stride f -> GEMM weight [(i*f+j)*Cout + co, ci] and tiled bias"""
+    ci, co, f, _ = w.shape
+    wg = w.permute(2, 3, 1, 0).reshape(f * f * co, ci)
+    return wg, b.repeat(f * f)
+
+
+class SpatialVLAEngine:
+    def __init__(self, cfg: dict, state_dict, ops, max_batch: int = 64):
+        self.cfg = cfg
+        self.ops = ops
+        self.dev = ops.device
+        self.v, self.t = cfg["vision_config"], cfg["text_config"]
+        self.use_zoe = cfg.get("use_vision_zoe", True)
+        self.z = cfg["vision_zoe_config"] if self.use_zoe else None
+        self.act_lo = cfg["action_token_begin_idx"]
+        self.n_act = cfg["spatial_token_num"]
+        self.last_router_head = None
+        self.force_head = None
+        self._pack(state_dict)
+
+    # ------------------------------------------------------------------------------------------ weight repack
+    def _w(self, t, dtype):
+        return t.detach().to(device=self.dev, dtype=dtype).contiguous()
+
+    def _pack(self, sd):
+        W = lambda k: self._w(sd[k], BF16)      # noqa: E731  GEMM operand
+        Fp = lambda k: self._w(sd[k], F32)      # noqa: E731  epilogue / norm vector
+        v, t = self.v, self.t
+        # ---- SigLIP
+        p = "vision_tower.vision_model."
+        D = v["hidden_size"]
+        self.sig_kpad = 640
+        s = {"patch_w": self._w(_pad_cols(sd[p + "embeddings.patch_embedding.weight"].reshape(D, -1).float(), self.sig_kpad), BF16),
+             "patch_b": Fp(p + "embeddings.patch_embedding.bias"), "pos": Fp(p + "embeddings.position_embedding.weight"),
+             "post_g": Fp(p + "post_layernorm.weight"), "post_b": Fp(p + "post_layernorm.bias"), "layers": []}
+        for i in range(v["num_hidden_layers"]):
+            q = f"{p}encoder.layers.{i}."
+            s["layers"].append({
+                "ln1_g": Fp(q + "layer_norm1.weight"), "ln1_b": Fp(q + "layer_norm1.bias"),
+                "ln2_g": Fp(q + "layer_norm2.weight"), "ln2_b": Fp(q + "layer_norm2.bias"),
+                "wqkv": self._w(torch.cat([sd[q + f"self_attn.{n}_proj.weight"] for n in "qkv"], 0), BF16),
+                "bqkv": self._w(torch.cat([sd[q + f"self_attn.{n}_proj.bias"] for n in "qkv"], 0), F32),
+                "wo": W(q + "self_attn.out_proj.weight"), "bo": Fp(q + "self_attn.out_proj.bias"),
+                "w1": W(q + "mlp.fc1.weight"), "b1": Fp(q + "mlp.fc1.bias"),
+                "w2": W(q + "mlp.fc2.weight"), "b2": Fp(q + "mlp.fc2.bias")})
+        self.sig = s
+        # ---- projector
+        H = t["hidden_size"]
+        self.proj_w, self.proj_b = W("multi_modal_projector.linear.weight"), Fp("multi_modal_projector.linear.bias")
+        self.proj_scale = torch.full((H,), 1.0 / (H ** 0.5), dtype=F32, device=self.dev)
+        # ---- Gemma2
+        p = "language_model.model."
+        g = {"embed": W(p + "embed_tokens.weight"), "final": Fp(p + "norm.weight"),
+             "head_act": self._w(sd["language_model.lm_head.weight"][self.act_lo:self.act_lo + self.n_act], BF16),
+             "layers": []}
+        self._lm_head_full_src = sd["language_model.lm_head.weight"]
+        self._lm_head_full = None
+        g["spatial"] = W("spatial_embed_tokens.weight") if self.cfg.get("use_spatial_token", True) else None
+        for i in range(t["num_hidden_layers"]):
+            q = f"{p}layers.{i}."
+            gate, up = sd[q + "mlp.gate_proj.weight"], sd[q + "mlp.up_proj.weight"]
+            gu = torch.stack([gate, up], 1).reshape(2 * gate.shape[0], gate.shape[1])   # rows 2j = gate_j, 2j+1 = up_j
+            g["layers"].append({
+                "wqkv": self._w(torch.cat([sd[q + f"self_attn.{n}_proj.weight"] for n in "qkv"], 0), BF16),
+                "wo": W(q + "self_attn.o_proj.weight"), "wgu": self._w(gu, BF16), "wd": W(q + "mlp.down_proj.weight"),
+                "ln_in": Fp(q + "input_layernorm.weight"), "ln_post_attn": Fp(q + "post_attention_layernorm.weight"),
+                "ln_pre_ff": Fp(q + "pre_feedforward_layernorm.weight"), "ln_post_ff": Fp(q + "post_feedforward_layernorm.weight")})
+        self.gem = g
+        if not self.use_zoe:
+            return
+        # ---- Ego3D
+        p = "position_embedding_3d.position_embedding_head."
+        self.ego_kpad = (12 * (2 * self.cfg["n_freqs"] + 1) + 7) // 8 * 8
+        self.ego = {"w0": self._w(_pad_cols(sd[p + "0.weight"].float(), self.ego_kpad), BF16), "b0": Fp(p + "0.bias"),
+                    "ln_g": Fp(p + "1.weight"), "ln_b": Fp(p + "1.bias"), "w3": W(p + "3.weight"), "b3": Fp(p + "3.bias")}
+        # ---- ZoeDepth: BEiT backbone
+        z = self.z
+        b = z["backbone_config"]
+        p = "vision_zoe_model.backbone."
+        C_ = b["hidden_size"]
+        bt = {"patch_w": self._w(sd[p + "embeddings.patch_embeddings.projection.weight"].reshape(C_, -1), BF16),
+              "patch_b": Fp(p + "embeddings.patch_embeddings.projection.bias"),
+              "cls": self._w(sd[p + "embeddings.cls_token"].reshape(C_), F32), "layers": []}
+        for i in range(b["num_hidden_layers"]):
+            q = f"{p}encoder.layer.{i}."
+            qb, vb = sd[q + "attention.attention.query.bias"], sd[q + "attention.attention.value.bias"]
+            bt["layers"].append({
+                "lnb_g": Fp(q + "layernorm_before.weight"), "lnb_b": Fp(q + "layernorm_before.bias"),
+                "lna_g": Fp(q + "layernorm_after.weight"), "lna_b": Fp(q + "layernorm_after.bias"),
+                "wqkv": self._w(torch.cat([sd[q + "attention.attention.query.weight"], sd[q + "attention.attention.key.weight"],
+                                           sd[q + "attention.attention.value.weight"]], 0), BF16),
+                "bqkv": self._w(torch.cat([qb, torch.zeros_like(qb), vb], 0), F32),
+                "relpos": Fp(q + "attention.attention.relative_position_bias.relative_position_bias_table"),
+                "wo": W(q + "attention.output.dense.weight"), "bo": Fp(q + "attention.output.dense.bias"),
+                "l1": Fp(q + "lambda_1"), "l2": Fp(q + "lambda_2"),
+                "wi": W(q + "intermediate.dense.weight"), "bi": Fp(q + "intermediate.dense.bias"),
+                "wo2": W(q + "output.dense.weight"), "bo2": Fp(q + "output.dense.bias")})
+        self.beit_w = bt
+        # ---- neck
+        p = "vision_zoe_model.neck."
+        nk = {"stages": [], "convs": [], "fusion": []}
+        for s_, fac in enumerate(z["reassemble_factors"]):
+            q = f"{p}reassemble_stage.layers.{s_}."
+            st = {"ro_w": W(f"{p}reassemble_stage.readout_projects.{s_}.0.weight"),
+                  "ro_b": Fp(f"{p}reassemble_stage.readout_projects.{s_}.0.bias"),
+                  "proj_w": self._w(sd[q + "projection.weight"].flatten(1), BF16), "proj_b": Fp(q + "projection.bias"),
+                  "factor": fac}
+            if fac > 1:
+                wg, bg = pack_deconv(sd[q + "resize.weight"], sd[q + "resize.bias"])
+                st["rs_w"], st["rs_b"] = self._w(wg, BF16), self._w(bg, F32)
+            elif fac < 1:
+                st["rs_w"], st["rs_b"] = self._w(pack_conv3x3_im2col(sd[q + "resize.weight"]), BF16), Fp(q + "resize.bias")
+            nk["stages"].append(st)
+            nk["convs"].append(self._w(pack_conv3x3(sd[f"{p}convs.{s_}.weight"]), BF16))
+        for li in range(len(z["neck_hidden_sizes"])):
+            q = f"{p}fusion_stage.layers.{li}."
+            fu = {"proj_w": self._w(sd[q + "projection.weight"].flatten(1), BF16), "proj_b": Fp(q + "projection.bias")}
+            for r in ("residual_layer1", "residual_layer2"):
+                for c in ("convolution1", "convolution2"):
+                    fu[f"{r}.{c}.w"] = self._w(pack_conv3x3(sd[q + f"{r}.{c}.weight"]), BF16)
+                    fu[f"{r}.{c}.b"] = Fp(q + f"{r}.{c}.bias")
+            nk["fusion"].append(fu)
+        self.neck = nk
+        p = "vision_zoe_model.relative_head."
+        self.rel = {"w1": self._w(pack_conv3x3(sd[p + "conv1.weight"]), BF16), "b1": Fp(p + "conv1.bias"),
+                    "w2": self._w(pack_conv3x3(sd[p + "conv2.weight"]), BF16), "b2": Fp(p + "conv2.bias")}
+        # ---- metric head
+        p = "vision_zoe_model.metric_head."
+        c1 = lambda k: self._w(sd[k].flatten(1), BF16)     # noqa: E731  1x1 conv -> [Cout, Cin]
+        R = z["num_relative_features"]
+        mh = {"conv2_w": c1(p + "conv2.weight"), "conv2_b": Fp(p + "conv2.bias"),
+              "emb_w": c1(p + "patch_transformer.embedding_convPxP.weight"), "emb_b": Fp(p + "patch_transformer.embedding_convPxP.bias"),
+              "cls1_w": W(p + "mlp_classifier.linear1.weight"), "cls1_b": Fp(p + "mlp_classifier.linear1.bias"),
+              "cls2_w": W(p + "mlp_classifier.linear2.weight"), "cls2_b": Fp(p + "mlp_classifier.linear2.bias"),
+              "sp1_w": c1(p + "seed_projector.conv1.weight"), "sp1_b": Fp(p + "seed_projector.conv1.bias"),
+              "sp2_w": c1(p + "seed_projector.conv2.weight"), "sp2_b": Fp(p + "seed_projector.conv2.bias"),
+              "tr": [], "proj": [], "heads": []}
+        for i in range(z["num_patch_transformer_layers"]):
+            q = f"{p}patch_transformer.transformer_encoder.{i}."
+            mh["tr"].append({
+                "wqkv": self._w(torch.cat([sd[q + f"self_attn.{n}.weight"] for n in ("query", "key", "value")], 0), BF16),
+                "bqkv": self._w(torch.cat([sd[q + f"self_attn.{n}.bias"] for n in ("query", "key", "value")], 0), F32),
+                "wo": W(q + "self_attn.out_proj.weight"), "bo": Fp(q + "self_attn.out_proj.bias"),
+                "w1": W(q + "linear1.weight"), "b1": Fp(q + "linear1.bias"), "w2": W(q + "linear2.weight"), "b2": Fp(q + "linear2.bias"),
+                "n1_g": Fp(q + "norm1.weight"), "n1_b": Fp(q + "norm1.bias"), "n2_g": Fp(q + "norm2.weight"), "n2_b": Fp(q + "norm2.bias")})
+        for s_ in range(4):
+            q = f"{p}projectors.{s_}."
+            mh["proj"].append({"w1": c1(q + "conv1.weight"), "b1": Fp(q + "conv1.bias"), "w2": c1(q + "conv2.weight"), "b2": Fp(q + "conv2.bias")})
+        for conf in z["bin_configurations"]:
+            nm = conf["name"]
+            hd = {"conf": conf,
+                  "sr1_w": c1(f"{p}seed_bin_regressors.{nm}.conv1.weight"), "sr1_b": Fp(f"{p}seed_bin_regressors.{nm}.conv1.bias"),
+                  "sr2_w": c1(f"{p}seed_bin_regressors.{nm}.conv2.weight"), "sr2_b": Fp(f"{p}seed_bin_regressors.{nm}.conv2.bias"),
+                  "att": []}
+            for s_ in range(len(z["num_attractors"])):
+                q = f"{p}attractors.{nm}.{s_}."
+                hd["att"].append({"w1": c1(q + "conv1.weight"), "b1": Fp(q + "conv1.bias"), "w2": c1(q + "conv2.weight"), "b2": Fp(q + "conv2.bias")})
+            q = f"{p}conditional_log_binomial.{nm}.mlp."
+            w0 = sd[q + "0.weight"].flatten(1)
+            hd["clb_wa"] = self._w(w0[:, :R], BF16)           # acts on the relative-head features (full res)
+            hd["clb_wb"] = self._w(w0[:, R:], BF16)           # acts on the bin embedding (half res; bilinear commutes with 1x1)
+            hd["clb_b1"] = Fp(q + "0.bias")
+            hd["clb_w2"] = self._w(sd[q + "2.weight"].flatten(1), F32)
+            hd["clb_b2"] = Fp(q + "2.bias")
+            mh["heads"].append(hd)
+        self.mh = mh
+
+    def lm_head_full(self):
+        if self._lm_head_full is None:
+            self._lm_head_full = self._w(self._lm_head_full_src, BF16)
+        return self._lm_head_full
+
+    # ------------------------------------------------------------------------------------------ small helpers
+    def _lin(self, a, w, rows, dtype=BF16, **kw):
+        out = self.ops.empty((rows, w.shape[0] // (2 if kw.get("geglu") else 1)), dtype)
+        if dtype == BF16:
+            self.ops.gemm(a, w, out_bf16=out, **kw)
+        else:
+            self.ops.gemm(a, w, out_f32=out, **kw)
+        return out
+
+    def _mha(self, qkv, B, S, nh, hd, scale, **kw):
+        D = nh * hd
+        ctx = self.ops.empty((B * S, D), BF16)
+        st = (S * 3 * D, 3 * D)
+        self.ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], ctx, batch=B, hq=nh, hkv=nh, sq=S, sk=S, d=hd,
+                           q_strides=st, k_strides=st, v_strides=st, o_strides=(S * D, D), scale=scale, **kw)
+        return ctx
+
+    # ------------------------------------------------------------------------------------------ SigLIP (a5)
+    def siglip(self, px):
+        """px fp32 [B,3,224,224] in [0,1] -> last_hidden_state fp32 [B*256, D] (post_layernorm applied)"""
+        ops, s, v = self.ops, self.sig, self.v
+        B = px.shape[0]
+        D, nh = v["hidden_size"], v["num_attention_heads"]
+        S, M = 256, B * 256
+        eps = v.get("layer_norm_eps", 1e-6)
+        a = ops.empty((M, self.sig_kpad), BF16)
+        ops.siglip_patchify(px, a)
+        x = ops.empty((M, D), F32)
+        ops.gemm(a, s["patch_w"], bias=s["patch_b"], res_f32=s["pos"], res_mod=S, out_f32=x)
+        h = ops.empty((M, D), BF16)
+        for L_ in s["layers"]:
+            ops.layernorm(x, L_["ln1_g"], L_["ln1_b"], eps, out_bf16=h)
+            qkv = self._lin(h, L_["wqkv"], M, bias=L_["bqkv"])
+            ctx = self._mha(qkv, B, S, nh, D // nh, (D // nh) ** -0.5)
+            ops.gemm(ctx, L_["wo"], bias=L_["bo"], out_f32=x, accumulate=True)
+            ops.layernorm(x, L_["ln2_g"], L_["ln2_b"], eps, out_bf16=h)
+            f = self._lin(h, L_["w1"], M, bias=L_["b1"], act=ACT_GELU_TANH)
+            ops.gemm(f, L_["w2"], bias=L_["b2"], out_f32=x, accumulate=True)
+        out = ops.empty((M, D), F32)
+        out_b = ops.empty((M, D), BF16)
+        ops.layernorm(x, s["post_g"], s["post_b"], eps, out_f32=out, out_bf16=out_b)
+        return out, out_b
+
+    # ------------------------------------------------------------------------------------------ ZoeDepth (a6-a8)
+    def beit(self, px):
+        ops, bt = self.ops, self.beit_w
+        b = self.z["backbone_config"]
+        B = px.shape[0]
+        C_, nh = b["hidden_size"], b["num_attention_heads"]
+        win = b["image_size"] // b["patch_size"]
+        n = win * win
+        S = n + 1
+        eps = b.get("layer_norm_eps", 1e-12)
+        a = ops.empty((B * n, 768), BF16)
+        ops.zoe_patchify(px, a)
+        patches = self._lin(a, bt["patch_w"], B * n, F32, bias=bt["patch_b"])
+        x = ops.empty((B * S, C_), F32)
+        ops.beit_assemble(patches, bt["cls"], x, batch=B, n=n, c=C_)
+        taps = [int(s.replace("stage", "")) for s in b["out_features"]]
+        hs = []
+        h = ops.empty((B * S, C_), BF16)
+        for i, L_ in enumerate(bt["layers"]):
+            ops.layernorm(x, L_["lnb_g"], L_["lnb_b"], eps, out_bf16=h)
+            qkv = self._lin(h, L_["wqkv"], B * S, bias=L_["bqkv"])
+            ctx = self._mha(qkv, B, S, nh, C_ // nh, 1.0 / math.sqrt(C_ // nh), relpos_table=L_["relpos"], relpos_win=win)
+            ops.gemm(ctx, L_["wo"], bias=L_["bo"], colscale=L_["l1"], out_f32=x, accumulate=True)
+            ops.layernorm(x, L_["lna_g"], L_["lna_b"], eps, out_bf16=h)
+            f = self._lin(h, L_["wi"], B * S, bias=L_["bi"], act=ACT_GELU_ERF)
+            ops.gemm(f, L_["wo2"], bias=L_["bo2"], colscale=L_["l2"], out_f32=x, accumulate=True)
+            if (i + 1) in taps:
+                hs.append(x.clone())
+        return hs, win
+
+    def _conv3(self, x, w, shape, **kw):
+        """3x3 / pad 1 implicit-GEMM conv on an NHWC bf16 map. Returns (out, relu_copy-or-None)."""
+        nb, hh, ww, c = shape
+        co = w.shape[0]
+        want_relu = kw.pop("want_relu", False)
+        want_out = kw.pop("want_out", True)
+        out = self.ops.empty((nb * hh * ww, co), BF16) if want_out else None
+        outr = self.ops.empty((nb * hh * ww, co), BF16) if want_relu else None
+        self.ops.gemm(x, w, conv=shape, out_bf16=out, out_relu=outr, **kw)
+        return out, outr
+
+    def zoe_neck(self, hs, win, B):
+        ops, nk, z = self.ops, self.neck, self.z
+        C_ = z["backbone_config"]["hidden_size"]
+        n = win * win
+        Fh = z["fusion_hidden_size"]
+        feats, feats_relu, res_ = [], [], []
+        for s_, (st, ch) in enumerate(zip(nk["stages"], z["neck_hidden_sizes"])):
+            a = ops.empty((B * n, 2 * C_), BF16)
+            ops.readout_concat(hs[s_], a, batch=B, n=n, c=C_)
+            r = self._lin(a, st["ro_w"], B * n, bias=st["ro_b"], act=ACT_GELU_ERF)
+            pj = self._lin(r, st["proj_w"], B * n, bias=st["proj_b"])
+            fac = st["factor"]
+            if fac > 1:
+                f = int(fac)
+                g = self._lin(pj, st["rs_w"], B * n, bias=st["rs_b"])
+                m = ops.empty((B * win * f * win * f, ch), BF16)
+                ops.pixel_shuffle(g, m, batch=B, h=win, w=win, c=ch, f=f)
+                r_ = win * f
+            elif fac < 1:
+                col = ops.empty((B * (win // 2) * (win // 2), 9 * ch), BF16)
+                ops.im2col3x3_s2(pj, col, batch=B, h=win, w=win, c=ch)
+                m = self._lin(col, st["rs_w"], B * (win // 2) * (win // 2), bias=st["rs_b"])
+                r_ = win // 2
+            else:
+                m, r_ = pj, win
+            o, orl = self._conv3(m, nk["convs"][s_], (B, r_, r_, ch), want_relu=True)
+            feats.append(o)
+            feats_relu.append(orl)
+            res_.append(r_)
+        fused_list, fused, fr = [], None, None
+        for li in range(len(feats)):
+            fu = nk["fusion"][li]
+            src = len(feats) - 1 - li
+            r_ = res_[src]
+            shp = (B, r_, r_, Fh)
+            if fused is None:
+                hcur, hrelu = feats[src], feats_relu[src]
+            else:
+                assert fr == r_, "fusion: feature / fused resolution mismatch"
+                c1, _ = self._conv3(feats_relu[src], fu["residual_layer1.convolution1.w"], shp,
+                                    bias=fu["residual_layer1.convolution1.b"], act=ACT_RELU)
+                hcur, hrelu = self._conv3(c1, fu["residual_layer1.convolution2.w"], shp, bias=fu["residual_layer1.convolution2.b"],
+                                          res_bf16=feats[src], res2_bf16=fused, want_relu=True)
+            c1, _ = self._conv3(hrelu, fu["residual_layer2.convolution1.w"], shp, bias=fu["residual_layer2.convolution1.b"], act=ACT_RELU)
+            h2, _ = self._conv3(c1, fu["residual_layer2.convolution2.w"], shp, bias=fu["residual_layer2.convolution2.b"], res_bf16=hcur)
+            up = ops.empty((B * 2 * r_ * 2 * r_, Fh), BF16)
+            ops.bilinear_nhwc(h2, up, batch=B, h=r_, w=r_, c=Fh, oh=2 * r_, ow=2 * r_)
+            fused = self._lin(up, fu["proj_w"], B * 4 * r_ * r_, bias=fu["proj_b"])
+            fr = 2 * r_
+            fused_list.append((fused, fr))
+        return fused_list, (feats[-1], res_[-1])
+
+    def zoe_relative_head(self, fused_last, B):
+        ops, z = self.ops, self.z
+        x, r_ = fused_last
+        Fh = z["fusion_hidden_size"]
+        c1, _ = self._conv3(x, self.rel["w1"], (B, r_, r_, Fh), bias=self.rel["b1"])
+        up = ops.empty((B * 4 * r_ * r_, Fh // 2), BF16)
+        ops.bilinear_nhwc(c1, up, batch=B, h=r_, w=r_, c=Fh // 2, oh=2 * r_, ow=2 * r_)
+        out, _ = self._conv3(up, self.rel["w2"], (B, 2 * r_, 2 * r_, Fh // 2), bias=self.rel["b2"], act=ACT_RELU)
+        return out, 2 * r_
+
+    def zoe_router(self, xb, B, n):
+        """HF zoedepth :905-963,1056-1067 -> domain logits fp32 [B, 2]"""
+        ops, mh, z = self.ops, self.mh, self.z
+        E, nh = z["patch_transformer_hidden_size"], z["patch_transformer_num_attention_heads"]
+        S = n + 1
+        e0 = self._lin(xb, mh["emb_w"], B * n, F32, bias=mh["emb_b"])
+        e = ops.empty((B * S, E), F32)
+        eb = ops.empty((B * S, E), BF16)
+        ops.zoe_router_embed(e0, e, eb, batch=B, n=n, c=E)
+        for L_ in mh["tr"]:
+            qkv = self._lin(eb, L_["wqkv"], B * S, bias=L_["bqkv"])
+            ctx = self._mha(qkv, B, S, nh, E // nh, 1.0 / math.sqrt(E // nh))
+            ops.gemm(ctx, L_["wo"], bias=L_["bo"], out_f32=e, accumulate=True)
+            ops.layernorm(e, L_["n1_g"], L_["n1_b"], 1e-5, out_f32=e, out_bf16=eb)
+            f = self._lin(eb, L_["w1"], B * S, bias=L_["b1"], act=ACT_RELU)
+            ops.gemm(f, L_["w2"], bias=L_["b2"], out_f32=e, accumulate=True)
+            ops.layernorm(e, L_["n2_g"], L_["n2_b"], 1e-5, out_f32=e, out_bf16=eb)
+        cls = eb.view(B, S * E)[:, :E]                     # CLS rows, row stride S*E
+        c1 = self._lin(cls, mh["cls1_w"], B, bias=mh["cls1_b"], act=ACT_RELU)
+        return self._lin(c1, mh["cls2_w"], B, F32, bias=mh["cls2_b"])
+
+    def zoe_metric_head(self, outconv, bottleneck, fused_list, B):
+        ops, mh, z = self.ops, self.mh, self.z
+        bneck, rb = bottleneck
+        n = rb * rb
+        E = z["bin_embedding_dim"]
+        xb = self._lin(bneck, mh["conv2_w"], B * n, bias=mh["conv2_b"])
+        dlog = self.zoe_router(xb, B, n)
+        self.last_domain_logits = dlog
+        if self.force_head is not None:
+            head = int(self.force_head)
+        else:
+            # batch-level vote exactly as HF (:1059-1067); one tiny D2H sync like the reference's `.item()`
+            head = int(torch.argmax(dlog.sum(0)).item())
+        self.last_router_head = head
+        hd = mh["heads"][head]
+        nbins = hd["conf"]["n_bins"]
+        s1 = self._lin(xb, hd["sr1_w"], B * n, bias=hd["sr1_b"], act=ACT_RELU)
+        prev_bin = self._lin(s1, hd["sr2_w"], B * n, F32, bias=hd["sr2_b"], act=ACT_SOFTPLUS)
+        p1 = self._lin(xb, mh["sp1_w"], B * n, bias=mh["sp1_b"], act=ACT_RELU)
+        prev_emb = self._lin(p1, mh["sp2_w"], B * n, bias=mh["sp2_b"])
+        pr = rb
+        for s_, (feat, r_) in enumerate(fused_list):
+            pj, at = mh["proj"][s_], hd["att"][s_]
+            M = B * r_ * r_
+            q1 = self._lin(feat, pj["w1"], M, bias=pj["b1"], act=ACT_RELU)
+            emb = self._lin(q1, pj["w2"], M, bias=pj["b2"])
+            hh = ops.empty((M, E), BF16)
+            ops.bilinear_nhwc(prev_emb, hh, batch=B, h=pr, w=pr, c=E, oh=r_, ow=r_, add=emb)
+            a1 = self._lin(hh, at["w1"], M, bias=at["b1"], act=ACT_RELU)
+            attr = self._lin(a1, at["w2"], M, bias=at["b2"])
+            bins = ops.empty((M, nbins), F32)
+            ops.zoe_attractor(attr, prev_bin, bins, batch=B, h=pr, w=pr, oh=r_, ow=r_, na=attr.shape[1], nbins=nbins)
+            prev_bin, prev_emb, pr = bins, emb, r_
+        oc, ro = outconv
+        Mo = B * ro * ro
+        t = self._lin(oc, hd["clb_wa"], Mo)
+        e40 = self._lin(prev_emb, hd["clb_wb"], B * pr * pr)
+        depth = ops.empty((B, ro, ro), F32)
+        ops.zoe_depth_tail(t, e40, hd["clb_b1"], hd["clb_w2"], hd["clb_b2"], prev_bin, depth, batch=B, h=pr, w=pr, oh=ro, ow=ro,
+                           nh=t.shape[1], nbins=nbins, min_temp=z["min_temp"], max_temp=z["max_temp"])
+        return depth
+
+    def zoedepth(self, px):
+        """px fp32 [B,3,224,224] in [0,1] -> metric depth fp32 [B,384,384] (process_zoe fused into the patchify)"""
+        B = px.shape[0]
+        hs, win = self.beit(px)
+        fused_list, bottleneck = self.zoe_neck(hs, win, B)
+        outconv = self.zoe_relative_head(fused_list[-1], B)
+        return self.zoe_metric_head(outconv, bottleneck, fused_list, B)
+
+    # ------------------------------------------------------------------------------------------ image features (a4)
+    def image_features(self, px, intrinsic, return_aux=False):
+        """-> fp32 [B, 256, H_text] (already divided by sqrt(H), model/modeling_spatialvla.py:331-332)"""
+        ops = self.ops
+        B = px.shape[0]
+        D, H = self.v["hidden_size"], self.t["hidden_size"]
+        px = px.to(device=self.dev, dtype=F32).contiguous()
+        sig, sig_b = self.siglip(px)
+        aux = {"siglip": sig.clone() if return_aux else None}
+        src = sig_b
+        if self.use_zoe:
+            depth = self.zoedepth(px)
+            K = intrinsic.to(device=self.dev, dtype=F32).contiguous()
+            xyz = ops.empty((B * 256, 12), F32)
+            enc = ops.empty((B * 256, self.ego_kpad), BF16)
+            ops.ego3d_encode(depth, K, xyz, enc, n_freqs=self.cfg["n_freqs"])
+            h0 = self._lin(enc, self.ego["w0"], B * 256, F32, bias=self.ego["b0"])
+            hb = ops.empty((B * 256, D), BF16)
+            ops.layernorm(h0, self.ego["ln_g"], self.ego["ln_b"], 1e-5, out_bf16=hb, relu=True)
+            src = ops.empty((B * 256, D), BF16)
+            ops.gemm(hb, self.ego["w3"], bias=self.ego["b3"], res_f32=sig, out_bf16=src)
+            aux.update({"depth384": depth, "xyz": xyz.view(B, 256, 12)})
+        feats = self._lin(src, self.proj_w, B * 256, F32, bias=self.proj_b, colscale=self.proj_scale)
+        feats = feats.view(B, 256, H)
+        return (feats, aux) if return_aux else feats
+
+    # ------------------------------------------------------------------------------------------ Gemma2 (a12-a18)
+    def new_cache(self, B, smax):
+        t = self.t
+        L_, hkv, hd = t["num_hidden_layers"], t["num_key_value_heads"], t["head_dim"]
+        return {"k": self.ops.zeros((L_, B, smax, hkv, hd), BF16), "v": self.ops.zeros((L_, B, smax, hkv, hd), BF16),
+                "smax": smax, "len": 0}
+
+    def gemma_forward(self, x, B, S, cache, bidirectional):
+        """x fp32 [B*S, H] (already scaled by sqrt(H)) -> final-normed hidden bf16 [B*S, H]; appends to the cache."""
+        ops, g, t = self.ops, self.gem, self.t
+        H, nh, nkv, hd, FF = t["hidden_size"], t["num_attention_heads"], t["num_key_value_heads"], t["head_dim"], t["intermediate_size"]
+        eps, theta = t["rms_norm_eps"], float(t.get("rope_theta", 10000.0))
+        scale, cap = t["query_pre_attn_scalar"] ** -0.5, t["attn_logit_softcapping"] or 0.0
+        M, pos0, smax = B * S, cache["len"], cache["smax"]
+        assert pos0 + S <= smax, "KV cache overflow"
+        h = ops.empty((M, H), BF16)
+        ops.rmsnorm_residual(x, w_pre=g["layers"][0]["ln_in"], eps=eps, out_bf16=h)
+        q = ops.empty((M, nh * hd), BF16)
+        ctx = ops.empty((M, nh * hd), BF16)
+        for li, L_ in enumerate(g["layers"]):
+            qkv = self._lin(h, L_["wqkv"], M)
+            kc, vc = cache["k"][li], cache["v"][li]
+            ops.rope_kv(qkv, q, kc, vc, batch=B, s=S, hq=nh, hkv=nkv, d=hd, smax=smax, pos0=pos0, theta=theta)
+            if S == 1:
+                ops.decode_attention(q, kc, vc, ctx, batch=B, hq=nh, hkv=nkv, d=hd, smax=smax, ctx=pos0 + 1, scale=scale, softcap=cap)
+            else:
+                kvs = (smax * nkv * hd, nkv * hd)
+                ops.attention(q, kc, vc, ctx, batch=B, hq=nh, hkv=nkv, sq=S, sk=pos0 + S, d=hd, q_strides=(S * nh * hd, nh * hd),
+                              k_strides=kvs, v_strides=kvs, o_strides=(S * nh * hd, nh * hd), scale=scale, softcap=cap,
+                              causal=not bidirectional)
+            br = self._lin(ctx, L_["wo"], M, F32)
+            ops.rmsnorm_residual(x, branch=br, w_post=L_["ln_post_attn"], w_pre=L_["ln_pre_ff"], eps=eps, out_bf16=h)
+            act = self._lin(h, L_["wgu"], M, geglu=True)
+            br = self._lin(act, L_["wd"], M, F32)
+            nxt = g["layers"][li + 1]["ln_in"] if li + 1 < len(g["layers"]) else g["final"]
+            ops.rmsnorm_residual(x, branch=br, w_post=L_["ln_post_ff"], w_pre=nxt, eps=eps, out_bf16=h)
+        cache["len"] = pos0 + S
+        return h
+
+    def embed(self, ids, image_feats=None):
+        ops, g, t = self.ops, self.gem, self.t
+        B, S = ids.shape
+        H = t["hidden_size"]
+        x = ops.empty((B * S, H), F32)
+        status = ops.zeros((1,), torch.int32)
+        n_img = 0 if image_feats is None else image_feats.shape[1]
+        ops.embed_tokens(ids.contiguous(), g["embed"], g["spatial"], image_feats, x, image_token=self.cfg["image_token_index"],
+                         act_lo=self.act_lo, n_act=self.n_act if g["spatial"] is not None else 0, n_img=n_img,
+                         normalizer=float(torch.tensor(H ** 0.5, dtype=F32)), status=status)
+        return x, status
+
+    def action_logits(self, h_rows, B):
+        """h_rows: bf16 [B, H] view (any row stride) -> post-softcap fp32 logits over the action slice [B, n_act]"""
+        cap = self.t["final_logit_softcapping"]
+        lg = self.ops.empty((B, self.n_act), F32)
+        self.ops.gemm(h_rows, self.gem["head_act"], out_f32=lg, act=ACT_SOFTCAP if cap else ACT_NONE, act_param=cap or 0.0)
+        return lg
+
+    def generate_actions(self, ids, px, intrinsic, n_new, forced_tokens=None, return_logits=False):
+        """Greedy decode of n_new action tokens (argmax restricted to the action slice). ids int64 [B,P] on device.
+        Returns tokens int64 [B, n_new] (+ fp32 logits [B, n_new, n_act])."""
+        ops = self.ops
+        B, P = ids.shape
+        H = self.t["hidden_size"]
+        feats = self.image_features(px, intrinsic) if px is not None else None
+        x, status = self.embed(ids, feats)
+        cache = self.new_cache(B, P + n_new)
+        h = self.gemma_forward(x, B, P, cache, bidirectional=True)
+        toks = ops.zeros((B, n_new), torch.int64)
+        logs = []
+        rows = h.view(B, P * H)[:, (P - 1) * H:]
+        for step in range(n_new):
+            lg = self.action_logits(rows, B)
+            if return_logits:
+                logs.append(lg)
+            ops.argmax_rows(lg, toks[:, step], id_offset=self.act_lo)
+            if step == n_new - 1:
+                break
+            feed = toks[:, step:step + 1] if forced_tokens is None else forced_tokens[:, step:step + 1]
+            x, _ = self.embed(feed.contiguous())
+            rows = self.gemma_forward(x, B, 1, cache, bidirectional=False)
+        self.last_status = status
+        if return_logits:
+            return toks, torch.stack(logs, 1)
+        return toks

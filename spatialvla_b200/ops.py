@@ -1,0 +1,224 @@
+"""Thin torch-tensor front end of the C ABI: validates shapes/dtypes, passes raw device pointers + the current
+CUDA stream.  PyTorch is plumbing only (device memory, streams); every op below runs a hand-written sm_100a
+kernel from libspatialvla_b200.so.  There is no CPU path here -- tests inject `oracle.ops_ref.RefOps`, a torch
+re-statement with the same method signatures, to validate the host orchestration without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._lib import (ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_RELU, ACT_SOFTCAP, ACT_SOFTPLUS,  # noqa: F401
+                   GEMM_GEGLU, GEMM_ACCUM_F32, GEMM_CONV3X3)
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _req(cond, msg):
+    if not cond:
+        raise ValueError(msg)
+
+
+class CudaOps:
+    """All methods are asynchronous on torch's current stream."""
+
+    name = "cuda"
+
+    def __init__(self, device="cuda:0", gemm_impl: int = 0):
+        if not torch.cuda.is_available():
+            raise L.SvlaError("spatialvla_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = L.load_library()
+        self.device = torch.device(device)
+        self.gemm_impl = gemm_impl    # 0 = tcgen05 (product); 1 = SIMT debugging kernel (tests only)
+
+    # ---- helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def launch_count(self) -> int:
+        return int(self.lib.svla_launch_count())
+
+    # ---- G1
+    def gemm(self, a, w, *, n=None, k=None, out_bf16=None, out_f32=None, out_relu=None, bias=None, colscale=None,
+             res_bf16=None, res2_bf16=None, res_f32=None, res_mod=0, act=ACT_NONE, act_param=0.0, alpha=1.0,
+             geglu=False, accumulate=False, conv=None, block_n=0, impl=None):
+        """value = act(alpha * a @ w.T + bias) * colscale + residuals; see include/spatialvla_b200.h (svla_gemm).
+        a: bf16 [M, K] (row stride = lda) or, with conv=(nb,h,w,c), a contiguous NHWC bf16 tensor.
+        w: bf16 [N, ldw]. Outputs are caller-allocated [M, >=N] row-major tensors sharing one row stride."""
+        g = L.SvlaGemmArgs()
+        _req(a.dtype == BF16 and w.dtype == BF16, "gemm: operands must be bf16")
+        _req(w.dim() == 2 and w.stride(1) == 1, "gemm: w must be [N, ldw] row-major")
+        N = int(n if n is not None else w.shape[0])
+        flags = 0
+        if conv is not None:
+            nb, h, wd, c = conv
+            _req(a.is_contiguous() and a.numel() == nb * h * wd * c, "gemm(conv): a must be contiguous NHWC")
+            M, K, lda = nb * h * wd, int(w.shape[1]), c
+            g.nb, g.h, g.wd, g.c = nb, h, wd, c
+            flags |= GEMM_CONV3X3
+        else:
+            _req(a.dim() == 2 and a.stride(1) == 1, "gemm: a must be [M, lda] row-major")
+            M, K, lda = int(a.shape[0]), int(k if k is not None else a.shape[1]), int(a.stride(0))
+        if geglu:
+            flags |= GEMM_GEGLU
+        if accumulate:
+            flags |= GEMM_ACCUM_F32
+        outs = [t for t in (out_bf16, out_f32, out_relu, res_bf16, res2_bf16, res_f32) if t is not None]
+        _req(len(outs) > 0, "gemm: no output")
+        ldo = None
+        for t in outs:
+            _req(t.dim() >= 2 and t.stride(-1) == 1, "gemm: outputs/residuals must be row-major")
+            t2 = t if t.dim() == 2 else t.view(-1, t.shape[-1])
+            ld = int(t2.stride(0))
+            ldo = ld if ldo is None else ldo
+            _req(ld == ldo, "gemm: outputs/residuals must share one row stride")
+        for t, dt in ((out_bf16, BF16), (out_relu, BF16), (res_bf16, BF16), (res2_bf16, BF16), (out_f32, F32),
+                      (res_f32, F32), (bias, F32), (colscale, F32)):
+            _req(t is None or t.dtype == dt, "gemm: dtype mismatch in epilogue tensors")
+        g.a, g.w = _ptr(a), _ptr(w)
+        g.bias, g.colscale = _ptr(bias), _ptr(colscale)
+        g.res_bf16, g.res2_bf16, g.res_f32, g.res_mod = _ptr(res_bf16), _ptr(res2_bf16), _ptr(res_f32), int(res_mod)
+        g.out_bf16, g.out_f32, g.out_relu_bf16 = _ptr(out_bf16), _ptr(out_f32), _ptr(out_relu)
+        g.m, g.n, g.k = M, N, K
+        g.lda, g.ldw, g.ldo = lda, int(w.stride(0)), ldo
+        g.alpha, g.act_param, g.act, g.flags = float(alpha), float(act_param), int(act), flags
+        g.block_n = int(block_n)
+        g.impl = int(self.gemm_impl if impl is None else impl)
+        L.check(self.lib.svla_gemm(C.byref(g), self._stream()), "svla_gemm")
+
+    # ---- G2 / G3
+    def attention(self, q, k, v, out, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
+                  scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0):
+        """strides = (batch stride, token stride) in elements; head h lives at column offset h*d."""
+        a = L.SvlaAttnArgs()
+        for t in (q, k, v, out):
+            _req(t.dtype == BF16, "attention: bf16 only")
+        a.q, a.k, a.v, a.out = _ptr(q), _ptr(k), _ptr(v), _ptr(out)
+        a.q_bs, a.q_ss = q_strides
+        a.k_bs, a.k_ss = k_strides
+        a.v_bs, a.v_ss = v_strides
+        a.o_bs, a.o_ss = o_strides
+        a.batch, a.hq, a.hkv, a.sq, a.sk, a.d = batch, hq, hkv, sq, sk, d
+        a.scale, a.softcap, a.causal = float(scale), float(softcap or 0.0), int(bool(causal))
+        _req(relpos_table is None or relpos_table.dtype == F32, "attention: relpos table must be fp32")
+        a.relpos_table, a.relpos_win = _ptr(relpos_table), int(relpos_win)
+        L.check(self.lib.svla_attention(C.byref(a), self._stream()), "svla_attention")
+
+    def decode_attention(self, q, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, scale, softcap=0.0):
+        L.check(self.lib.svla_decode_attention(_ptr(q), _ptr(kcache), _ptr(vcache), _ptr(out), batch, hq, hkv, d,
+                                               smax, ctx, float(scale), float(softcap or 0.0), self._stream()),
+                "svla_decode_attention")
+
+    # ---- memory-bound fused ops
+    def layernorm(self, x, gamma, beta, eps, *, out_bf16=None, out_f32=None, relu=False):
+        _req(x.dtype == F32 and x.is_contiguous(), "layernorm: x must be contiguous fp32")
+        rows, cols = x.numel() // x.shape[-1], x.shape[-1]
+        L.check(self.lib.svla_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), rows, cols, _ptr(out_bf16),
+                                        _ptr(out_f32), int(relu), self._stream()), "svla_layernorm")
+
+    def rmsnorm_residual(self, x, *, branch=None, w_post=None, w_pre=None, eps=1e-6, out_bf16=None):
+        _req(x.dtype == F32 and x.is_contiguous(), "rmsnorm_residual: x must be contiguous fp32")
+        rows, cols = x.numel() // x.shape[-1], x.shape[-1]
+        L.check(self.lib.svla_rmsnorm_residual(_ptr(x), _ptr(branch), _ptr(w_post), _ptr(w_pre), float(eps), rows,
+                                               cols, _ptr(out_bf16), self._stream()), "svla_rmsnorm_residual")
+
+    def rope_kv(self, qkv, q_out, kcache, vcache, *, batch, s, hq, hkv, d, smax, pos0, theta):
+        L.check(self.lib.svla_rope_kv(_ptr(qkv), _ptr(q_out), _ptr(kcache), _ptr(vcache), batch, s, hq, hkv, d, smax,
+                                      pos0, float(theta), self._stream()), "svla_rope_kv")
+
+    def embed_tokens(self, ids, embed, spatial_embed, image_feats, x, *, image_token, act_lo, n_act, n_img,
+                     normalizer, status):
+        _req(ids.dtype == torch.int64 and ids.is_contiguous(), "embed_tokens: ids must be contiguous int64")
+        B, S = ids.shape
+        L.check(self.lib.svla_embed_tokens(_ptr(ids), _ptr(embed), _ptr(spatial_embed), _ptr(image_feats), _ptr(x), B,
+                                           S, x.shape[-1], embed.shape[0], int(image_token), int(act_lo), int(n_act),
+                                           int(n_img), float(normalizer), _ptr(status), self._stream()),
+                "svla_embed_tokens")
+
+    def argmax_rows(self, logits, out_ids, *, id_offset=0):
+        """out_ids: int64 view with one element per row (any stride)."""
+        _req(logits.dtype == F32 and logits.dim() == 2 and logits.stride(1) == 1, "argmax_rows: bad logits")
+        _req(out_ids.dtype == torch.int64 and out_ids.dim() == 1, "argmax_rows: out_ids must be 1-D int64")
+        L.check(self.lib.svla_argmax_rows(_ptr(logits), logits.shape[0], logits.shape[1], logits.stride(0),
+                                          int(id_offset), _ptr(out_ids), out_ids.stride(0), self._stream()),
+                "svla_argmax_rows")
+
+    def siglip_patchify(self, px, a):
+        _req(px.dtype == F32 and px.is_contiguous() and tuple(px.shape[1:]) == (3, 224, 224), "siglip_patchify: px")
+        L.check(self.lib.svla_siglip_patchify(_ptr(px), _ptr(a), px.shape[0], a.shape[1], self._stream()),
+                "svla_siglip_patchify")
+
+    def zoe_patchify(self, px, a):
+        _req(px.dtype == F32 and px.is_contiguous() and tuple(px.shape[1:]) == (3, 224, 224), "zoe_patchify: px")
+        L.check(self.lib.svla_zoe_patchify(_ptr(px), _ptr(a), px.shape[0], self._stream()), "svla_zoe_patchify")
+
+    def beit_assemble(self, patches, cls, x, *, batch, n, c):
+        L.check(self.lib.svla_beit_assemble(_ptr(patches), _ptr(cls), _ptr(x), batch, n, c, self._stream()),
+                "svla_beit_assemble")
+
+    def readout_concat(self, hs, a, *, batch, n, c):
+        L.check(self.lib.svla_readout_concat(_ptr(hs), _ptr(a), batch, n, c, self._stream()), "svla_readout_concat")
+
+    def pixel_shuffle(self, g, out, *, batch, h, w, c, f):
+        L.check(self.lib.svla_pixel_shuffle(_ptr(g), _ptr(out), batch, h, w, c, f, self._stream()),
+                "svla_pixel_shuffle")
+
+    def im2col3x3_s2(self, x, a, *, batch, h, w, c):
+        L.check(self.lib.svla_im2col3x3_s2(_ptr(x), _ptr(a), batch, h, w, c, self._stream()), "svla_im2col3x3_s2")
+
+    def bilinear_nhwc(self, x, out, *, batch, h, w, c, oh, ow, add=None, out_relu=None):
+        L.check(self.lib.svla_bilinear_nhwc(_ptr(x), _ptr(add), _ptr(out), _ptr(out_relu), batch, h, w, c, oh, ow,
+                                            self._stream()), "svla_bilinear_nhwc")
+
+    def relu_bf16(self, x, out):
+        L.check(self.lib.svla_relu_bf16(_ptr(x), _ptr(out), x.numel(), self._stream()), "svla_relu_bf16")
+
+    def zoe_router_embed(self, conv, e, e_bf16, *, batch, n, c):
+        L.check(self.lib.svla_zoe_router_embed(_ptr(conv), _ptr(e), _ptr(e_bf16), batch, n, c, self._stream()),
+                "svla_zoe_router_embed")
+
+    def zoe_attractor(self, attr, prev, out, *, batch, h, w, oh, ow, na, nbins):
+        L.check(self.lib.svla_zoe_attractor(_ptr(attr), _ptr(prev), _ptr(out), batch, h, w, oh, ow, na, nbins,
+                                            self._stream()), "svla_zoe_attractor")
+
+    def softplus_f32(self, x, out):
+        L.check(self.lib.svla_softplus_f32(_ptr(x), _ptr(out), x.numel(), self._stream()), "svla_softplus_f32")
+
+    def zoe_depth_tail(self, t, e, b1, w2, b2, bins, depth, *, batch, h, w, oh, ow, nh, nbins, min_temp, max_temp):
+        L.check(self.lib.svla_zoe_depth_tail(_ptr(t), _ptr(e), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(bins), _ptr(depth),
+                                             batch, h, w, oh, ow, nh, nbins, float(min_temp), float(max_temp),
+                                             self._stream()), "svla_zoe_depth_tail")
+
+    def ego3d_encode(self, depth384, intrinsic, xyz, enc, *, n_freqs):
+        _req(depth384.dtype == F32 and depth384.is_contiguous() and tuple(depth384.shape[1:]) == (384, 384),
+             "ego3d_encode: depth must be fp32 [B,384,384]")
+        _req(intrinsic.dtype == F32 and intrinsic.is_contiguous(), "ego3d_encode: intrinsic must be fp32")
+        k_stride = 9 if intrinsic.dim() == 3 else 0
+        _req(k_stride == 0 or intrinsic.shape[0] == depth384.shape[0], "ego3d_encode: per-sample K batch mismatch")
+        L.check(self.lib.svla_ego3d_encode(_ptr(depth384), _ptr(intrinsic), k_stride, _ptr(xyz), _ptr(enc),
+                                           depth384.shape[0], enc.shape[1], n_freqs, self._stream()),
+                "svla_ego3d_encode")
+
+    # ---- M8 tokenizer (device buffers)
+    def tok_encode(self, actions, edges, nbins_host, ids, *, min_action=-1.0, max_action=1.0):
+        nb = (C.c_int32 * 7)(*nbins_host)
+        L.check(self.lib.svla_tok_encode(_ptr(actions), _ptr(edges), C.cast(nb, C.c_void_p), _ptr(ids),
+                                         actions.shape[0], float(min_action), float(max_action), self._stream()),
+                "svla_tok_encode")
+
+    def tok_decode(self, ids, edges, nbins_host, begin, actions):
+        nb = (C.c_int32 * 7)(*nbins_host)
+        L.check(self.lib.svla_tok_decode(_ptr(ids), _ptr(edges), C.cast(nb, C.c_void_p), int(begin), _ptr(actions),
+                                         ids.shape[0], self._stream()), "svla_tok_decode")

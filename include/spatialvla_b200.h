@@ -196,15 +196,17 @@ int svla_ego3d_encode(const float* depth384, const float* intrinsic, int k_strid
  * nbins int32[7] = {theta, phi, r, roll, pitch, yaw, gripper}.
  * encode: actions fp64 [n,7] -> ids int32 [n,3] LOCAL ids (0..vocab-1); decode: ids int64 [n,3]
  * (global ids, `begin` subtracted inside like the reference) -> actions fp64 [n,7].
+ * use_spherical = 0 bins the Cartesian translation directly (model/action_tokenizer.py:110-113,135).
+ * nbins is always read on the HOST (7 ints of configuration).
  * The `_host` variants take HOST buffers and do the H2D/D2H copies themselves (the e2e call). */
 int svla_tok_encode(const double* actions, const double* edges, const int32_t* nbins, int32_t* ids, int64_t n,
-                    double min_action, double max_action, void* stream);
+                    double min_action, double max_action, int use_spherical, void* stream);
 int svla_tok_decode(const int64_t* ids, const double* edges, const int32_t* nbins, int64_t begin, double* actions,
-                    int64_t n, void* stream);
+                    int64_t n, int use_spherical, void* stream);
 int svla_tok_encode_host(const double* actions_host, const double* edges_host, const int32_t* nbins_host,
-                         int32_t* ids_host, int64_t n, double min_action, double max_action);
+                         int32_t* ids_host, int64_t n, double min_action, double max_action, int use_spherical);
 int svla_tok_decode_host(const int64_t* ids_host, const double* edges_host, const int32_t* nbins_host, int64_t begin,
-                         double* actions_host, int64_t n);
+                         double* actions_host, int64_t n, int use_spherical);
 
 #ifdef __cplusplus
 }

@@ -307,13 +307,13 @@ class RefOps:
         enc[:, : e.shape[1]] = e.to(BF16)
 
     # ---- tokenizer
-    def tok_encode(self, actions, edges, nbins_host, ids, *, min_action=-1.0, max_action=1.0):
+    def tok_encode(self, actions, edges, nbins_host, ids, *, min_action=-1.0, max_action=1.0, use_spherical=True):
         self.launches += 1
         from oracle import tokenizer_ref as T
         pol, nb = _policy_from_flat(edges.numpy(), nbins_host)
         ids.copy_(torch.from_numpy(T.encode(actions.numpy(), pol, nb, min_action, max_action)).to(ids.dtype))
 
-    def tok_decode(self, ids, edges, nbins_host, begin, actions):
+    def tok_decode(self, ids, edges, nbins_host, begin, actions, *, use_spherical=True):
         self.launches += 1
         from oracle import tokenizer_ref as T
         pol, nb = _policy_from_flat(edges.numpy(), nbins_host)

@@ -1,0 +1,206 @@
+"""`SpatialActionTokenizer` with the reference's interface (model/action_tokenizer.py:249-430); the grid lookup and
+its inverse run in the FP64 CUDA kernels behind `svla_tok_encode_host` / `svla_tok_decode_host` (HOST buffers in,
+HOST buffers out -- the call a dataset / processor makes) or, for device-resident batches, `encode_ids` /
+`decode_ids` on torch CUDA tensors.  Token strings `<ACTION%05d>` only appear at the API edge.
+
+Bin edges are configuration (6 small float64 arrays), computed on the host exactly like the reference's
+`get_bin_policy` (scipy.stats.norm cdf/ppf, model/action_tokenizer.py:343-370)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib as L
+
+ACTION_TOKEN = "<ACTION{:05d}>"
+_TRANS_KEYS = ("theta_bins", "phi_bins", "r_bins")
+_ROT_KEYS = ("roll_bins", "pitch_bins", "yaw_bins")
+
+
+class _SubTokenizer:
+    """Attribute surface of the reference's Translation/Rotation/Gripper tokenizers that other code reads
+    (train/monkey_patch.py:273-297): token_start_idx, token_end_idx, vocab_size, token_array."""
+
+    def __init__(self, tokenizer, n, array_begin_idx):
+        self.tokenizer = tokenizer
+        self.array_begin_idx = array_begin_idx
+        self._vocab_size = n
+        self.token_array = np.array([ACTION_TOKEN.format(i + array_begin_idx) for i in range(n)])
+        self.tokenizer.add_tokens(list(self.token_array), special_tokens=True)
+        self.token_start_idx = self.tokenizer.convert_tokens_to_ids(self.token_array[0])
+        self.token_end_idx = self.tokenizer.convert_tokens_to_ids(self.token_array[-1])
+
+    @property
+    def vocab_size(self):
+        return self._vocab_size
+
+
+class SpatialActionTokenizer:
+    range_bins = {
+        "translation": {"theta_bins": (0.0, np.pi), "phi_bins": (-np.pi, np.pi), "r_bins": (0.0, np.sqrt(3))},
+        "rotation": {"roll_bins": (-1.0, 1.0), "pitch_bins": (-1.0, 1.0), "yaw_bins": (-1.0, 1.0)},
+    }
+
+    def __init__(self, tokenizer, num_bins: Dict, gs_params: Dict = None, bin_policy: Dict = None,
+                 use_spherical: bool = True, min_sigma: float = 0.0, min_action: float = -1.0, max_action: float = 1.0):
+        self.tokenizer = tokenizer
+        self.min_action, self.max_action = min_action, max_action
+        self.num_bins = num_bins
+        self.min_sigma = min_sigma
+        self.use_spherical = use_spherical
+        self.bin_policy = bin_policy if bin_policy else self.get_bin_policy(gs_params, self.min_sigma)
+        nt, nr = num_bins["translation"], num_bins["rotation"]
+        n_trans = nt["theta_bins"] * nt["phi_bins"] * nt["r_bins"]
+        n_rot = nr["roll_bins"] * nr["pitch_bins"] * nr["yaw_bins"]
+        self.translation_tokenizer = _SubTokenizer(tokenizer, n_trans, 0)
+        self.rotation_tokenizer = _SubTokenizer(tokenizer, n_rot, n_trans)
+        self.gripper_tokenizer = _SubTokenizer(tokenizer, num_bins["gripper"], n_trans + n_rot)
+        self._vocab_size = n_trans + n_rot + num_bins["gripper"]
+        self.token_array = np.concatenate([self.translation_tokenizer.token_array, self.rotation_tokenizer.token_array,
+                                           self.gripper_tokenizer.token_array])
+        self._refresh_edges()
+
+    # ---- configuration
+    def _refresh_edges(self):
+        pol = self.bin_policy
+        arrs = [np.asarray(pol["translation"][k], dtype=np.float64) for k in _TRANS_KEYS] + \
+               [np.asarray(pol["rotation"][k], dtype=np.float64) for k in _ROT_KEYS]
+        nb = [self.num_bins["translation"][k] for k in _TRANS_KEYS] + [self.num_bins["rotation"][k] for k in _ROT_KEYS]
+        for a, n in zip(arrs, nb):
+            if a.shape[0] != n + 1:
+                raise ValueError(f"bin policy has {a.shape[0]} edges for {n} bins")
+        self._edges = np.ascontiguousarray(np.concatenate(arrs))
+        self._nbins = (C.c_int32 * 7)(*nb, int(self.num_bins["gripper"]))
+        self._nbins_list = nb + [int(self.num_bins["gripper"])]
+        self._dev_edges = {}
+
+    @property
+    def vocab_size(self) -> int:
+        return self._vocab_size
+
+    @property
+    def action_token_begin_idx(self) -> int:
+        return self.translation_tokenizer.token_start_idx
+
+    def get_bin_policy(self, gs_params=None, min_sigma=0.0):
+        """model/action_tokenizer.py:343-370: Gaussian-quantile edges clipped to the axis range, or uniform."""
+        from scipy.stats import norm
+        pol = {"translation": {}, "rotation": {}}
+        for bt, axes in self.range_bins.items():
+            for bk, (lo, hi) in axes.items():
+                n = self.num_bins[bt][bk]
+                if gs_params is None:
+                    pol[bt][bk] = np.linspace(lo, hi, n + 1)
+                else:
+                    g = gs_params[bk.split("_")[0].lower()]
+                    mu, sigma = g["mu"], max(g["sigma"], min_sigma)
+                    prob = np.linspace(norm.cdf(lo, loc=mu, scale=sigma), norm.cdf(hi, loc=mu, scale=sigma), n + 1)
+                    pol[bt][bk] = np.clip(norm.ppf(prob, loc=mu, scale=sigma), lo, hi).tolist()
+        return pol
+
+    # ---- host-buffer API (reference signatures)
+    def encode_local_ids(self, action: np.ndarray) -> np.ndarray:
+        """(n,7)|(7,) float -> (n,3) int32 local ids in [0, vocab). Runs svla_tok_encode_host."""
+        action = np.asarray(action)
+        if action.ndim == 1:
+            assert action.shape[0] == 7, f"action dim mismatch, got action shape: {action.shape}"
+            action = action.reshape(1, 7)
+        assert action.shape[1] == 7, f"action dim mismatch, got action shape: {action.shape}"
+        a = np.ascontiguousarray(action, dtype=np.float64)
+        ids = np.empty((a.shape[0], 3), dtype=np.int32)
+        lib = L.load_library()
+        L.check(lib.svla_tok_encode_host(a.ctypes.data, self._edges.ctypes.data, C.cast(self._nbins, C.c_void_p),
+                                         ids.ctypes.data, a.shape[0], float(self.min_action), float(self.max_action),
+                                         int(self.use_spherical)), "svla_tok_encode_host")
+        return ids
+
+    def __call__(self, action: np.ndarray) -> np.ndarray:
+        """Discretize continuous actions (n,7) to token strings (n,3) (model/action_tokenizer.py:305-319)."""
+        return self.token_array[self.encode_local_ids(action)]
+
+    def decode_token_ids_to_actions(self, action_token_ids: np.ndarray) -> np.ndarray:
+        """(n,3)|(3,) global token ids -> (n,7) float64 actions (model/action_tokenizer.py:321-333)."""
+        ids = np.asarray(action_token_ids)
+        if ids.ndim == 1:
+            assert ids.shape[0] == 3, f"action token id numbers mismatich, need 3 got {ids.shape[0]}"
+            ids = ids.reshape(1, 3)
+        assert ids.shape[1] == 3, f"token id numbers mismatich, need 3 got {ids.shape[1]}"
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        out = np.empty((ids.shape[0], 7), dtype=np.float64)
+        lib = L.load_library()
+        L.check(lib.svla_tok_decode_host(ids.ctypes.data, self._edges.ctypes.data, C.cast(self._nbins, C.c_void_p),
+                                         int(self.action_token_begin_idx), out.ctypes.data, ids.shape[0],
+                                         int(self.use_spherical)), "svla_tok_decode_host")
+        return out
+
+    # ---- device-resident API (batched serving / training data path)
+    def _edges_on(self, device):
+        import torch
+        key = str(device)
+        if key not in self._dev_edges:
+            self._dev_edges[key] = torch.from_numpy(self._edges).to(device)
+        return self._dev_edges[key]
+
+    def encode_ids(self, actions):
+        """torch float64 CUDA tensor (n,7) -> int64 (n,3) GLOBAL token ids, asynchronous on the current stream."""
+        import torch
+        from .ops import CudaOps
+        ops = CudaOps(actions.device)
+        a = actions.to(torch.float64).contiguous()
+        ids = torch.empty((a.shape[0], 3), dtype=torch.int32, device=a.device)
+        ops.tok_encode(a, self._edges_on(a.device), self._nbins_list, ids, min_action=self.min_action,
+                       max_action=self.max_action, use_spherical=self.use_spherical)
+        return ids.to(torch.int64) + self.action_token_begin_idx
+
+    def decode_ids(self, ids):
+        """torch int64 CUDA tensor (n,3) of global ids -> float64 (n,7)"""
+        import torch
+        from .ops import CudaOps
+        ops = CudaOps(ids.device)
+        i = ids.to(torch.int64).contiguous()
+        out = torch.empty((i.shape[0], 7), dtype=torch.float64, device=i.device)
+        ops.tok_decode(i, self._edges_on(i.device), self._nbins_list, self.action_token_begin_idx, out,
+                       use_spherical=self.use_spherical)
+        return out
+
+    # ---- fine-tune-time re-gridding (host-side one-off, mirrors :372-430)
+    def get_norm_meshgrid(self, bin_policy):
+        grids = []
+        policy = {k1: {k2: np.array(v2) for k2, v2 in v1.items()} for k1, v1 in bin_policy.items()}
+        for bin_type in self.range_bins.keys():
+            bounds = []
+            for bin_key in self.range_bins[bin_type].keys():
+                minb, maxb = self.range_bins[bin_type][bin_key]
+                edges = policy[bin_type][bin_key]
+                centre = np.concatenate([np.array([minb]), (edges[:-1] + edges[1:]) / 2, np.array([maxb])])
+                bounds.append((centre - minb) / (maxb - minb))
+            gx, gy, gz = np.meshgrid(*bounds)
+            grids += [np.stack([gx, gy, gz], -1).reshape(-1, 3)]
+        return grids[0], grids[1]
+
+    def spatial_embedding_adaption(self, gs_params, embeddings, min_sigma=0.0, adpt_feature=False):
+        """Re-grid the tokenizer to new Gaussians and (optionally) re-sample the spatial embeddings by scattered
+        linear interpolation, as model/action_tokenizer.py:390-430 does (scipy.interpolate.griddata, host)."""
+        import torch
+        from scipy.interpolate import griddata
+        new_policy = self.get_bin_policy(gs_params, min_sigma=min_sigma)
+        g0t, g0r = self.get_norm_meshgrid(self.bin_policy)
+        g1t, g1r = self.get_norm_meshgrid(new_policy)
+        self.bin_policy, self.min_sigma = new_policy, min_sigma
+        self._refresh_edges()
+        if not adpt_feature:
+            return
+        emb = embeddings.weight.data
+        E = emb.shape[1]
+        off = 0
+        for (grid0, grid1, keys, bt) in ((g0t, g1t, _TRANS_KEYS, "translation"), (g0r, g1r, _ROT_KEYS, "rotation")):
+            m, n, k = (self.num_bins[bt][kk] for kk in keys)
+            N = m * n * k
+            blk = emb[off:off + N].reshape(m, n, k, -1).permute(3, 0, 1, 2)
+            pad = torch.nn.functional.pad(blk, (1, 1, 1, 1, 1, 1), "replicate").permute(1, 2, 3, 0).reshape(-1, E)
+            ad = griddata(grid0, pad.float().cpu().numpy(), grid1, method="linear")
+            ad = ad.reshape(m + 2, n + 2, k + 2, E)[1:-1, 1:-1, 1:-1]
+            emb[off:off + N] = torch.from_numpy(ad.reshape(-1, E)).to(emb.dtype).to(emb.device)
+            off += N

@@ -29,7 +29,7 @@ __device__ __forceinline__ double clampd(double v, double lo, double hi) { retur
 
 __global__ void __launch_bounds__(256)
 svla_tok_encode_kernel(const double* __restrict__ actions, const double* __restrict__ edges, TokGrid g, int* __restrict__ ids,
-                       long long n, double amin, double amax) {
+                       long long n, double amin, double amax, int spherical) {
   __shared__ double se[kMaxEdges];
   int total = g.off[5] + g.nb[5] + 1;
   for (int i = threadIdx.x; i < total; i += blockDim.x) se[i] = edges[i];
@@ -40,9 +40,10 @@ svla_tok_encode_kernel(const double* __restrict__ actions, const double* __restr
     const double x = clampd(a[0], amin, amax), y = clampd(a[1], amin, amax), z = clampd(a[2], amin, amax);
     const double xx = __dmul_rn(x, x), yy = __dmul_rn(y, y), zz = __dmul_rn(z, z);
     const double sxy = __dadd_rn(xx, yy);
-    const double theta = atan2(sqrt(sxy), z);
-    const double phi = atan2(y, x);
-    const double r = sqrt(__dadd_rn(sxy, zz));
+    // use_spherical=False (model/action_tokenizer.py:112-113) bins the clipped Cartesian components directly
+    const double theta = spherical ? atan2(sqrt(sxy), z) : x;
+    const double phi = spherical ? atan2(y, x) : y;
+    const double r = spherical ? sqrt(__dadd_rn(sxy, zz)) : z;
     // translation uses the interior edges e[1:-1]
     const int dt = digitize_right_open(theta, se + g.off[0] + 1, g.nb[0] - 1);
     const int dp = digitize_right_open(phi, se + g.off[1] + 1, g.nb[1] - 1);
@@ -67,7 +68,7 @@ svla_tok_encode_kernel(const double* __restrict__ actions, const double* __restr
 
 __global__ void __launch_bounds__(256)
 svla_tok_decode_kernel(const long long* __restrict__ ids, const double* __restrict__ edges, TokGrid g, long long begin,
-                       double* __restrict__ actions, long long n) {
+                       double* __restrict__ actions, long long n, int spherical) {
   __shared__ double se[kMaxEdges];
   int total = g.off[5] + g.nb[5] + 1;
   for (int i = threadIdx.x; i < total; i += blockDim.x) se[i] = edges[i];
@@ -84,10 +85,13 @@ svla_tok_decode_kernel(const long long* __restrict__ ids, const double* __restri
     const double th = 0.5 * __dadd_rn(se[g.off[0] + a], se[g.off[0] + a + 1]);
     const double ph = 0.5 * __dadd_rn(se[g.off[1] + b], se[g.off[1] + b + 1]);
     const double rr = 0.5 * __dadd_rn(se[g.off[2] + c], se[g.off[2] + c + 1]);
-    const double st = sin(th), ct = cos(th), sp = sin(ph), cp = cos(ph);
-    double x = __dmul_rn(__dmul_rn(rr, st), cp);
-    double y = __dmul_rn(__dmul_rn(rr, st), sp);
-    double z = __dmul_rn(rr, ct);
+    double x = th, y = ph, z = rr;
+    if (spherical) {
+      const double st = sin(th), ct = cos(th), sp = sin(ph), cp = cos(ph);
+      x = __dmul_rn(__dmul_rn(rr, st), cp);
+      y = __dmul_rn(__dmul_rn(rr, st), sp);
+      z = __dmul_rn(rr, ct);
+    }
     double* o = actions + i * 7;
     o[0] = clampd(x, -1.0, 1.0);
     o[1] = clampd(y, -1.0, 1.0);
@@ -128,26 +132,26 @@ unsigned grid_for(long long n) {
 
 // nbins is read on the HOST in every variant (it is 7 ints of configuration, never per-sample data).
 extern "C" int svla_tok_encode(const double* actions, const double* edges, const int32_t* nbins, int32_t* ids, int64_t n,
-                               double min_action, double max_action, void* stream) {
+                               double min_action, double max_action, int use_spherical, void* stream) {
   SVLA_REQUIRE(edges && nbins && (n == 0 || (actions && ids)), "svla_tok_encode: null pointer");
   SVLA_REQUIRE(n >= 0, "svla_tok_encode: negative n");
   if (n == 0) return 0;
   TokGrid g;
   SVLA_REQUIRE(make_grid(nbins, g) > 0, "svla_tok_encode: bins per axis must be in [1, 64]");
-  svla_tok_encode_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(actions, edges, g, ids, n, min_action, max_action);
+  svla_tok_encode_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(actions, edges, g, ids, n, min_action, max_action, use_spherical);
   SVLA_LAUNCH_CHECK("svla_tok_encode");
   return 0;
 }
 
 extern "C" int svla_tok_decode(const int64_t* ids, const double* edges, const int32_t* nbins, int64_t begin, double* actions,
-                               int64_t n, void* stream) {
+                               int64_t n, int use_spherical, void* stream) {
   SVLA_REQUIRE(edges && nbins && (n == 0 || (actions && ids)), "svla_tok_decode: null pointer");
   SVLA_REQUIRE(n >= 0, "svla_tok_decode: negative n");
   if (n == 0) return 0;
   TokGrid g;
   SVLA_REQUIRE(make_grid(nbins, g) > 0, "svla_tok_decode: bins per axis must be in [1, 64]");
   svla_tok_decode_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const long long*>(ids), edges, g, begin, actions, n);
+      reinterpret_cast<const long long*>(ids), edges, g, begin, actions, n, use_spherical);
   SVLA_LAUNCH_CHECK("svla_tok_decode");
   return 0;
 }
@@ -163,7 +167,8 @@ extern "C" int svla_tok_decode(const int64_t* ids, const double* edges, const in
   } while (0)
 
 extern "C" int svla_tok_encode_host(const double* actions_host, const double* edges_host, const int32_t* nbins_host,
-                                    int32_t* ids_host, int64_t n, double min_action, double max_action) {
+                                    int32_t* ids_host, int64_t n, double min_action, double max_action,
+                                    int use_spherical) {
   if (n == 0) return 0;
   TokGrid g;
   const int ne = make_grid(nbins_host, g);
@@ -176,7 +181,7 @@ extern "C" int svla_tok_encode_host(const double* actions_host, const double* ed
   SVLA_CUDA_OK(cudaMalloc(&d_i, sizeof(int32_t) * 3 * n));
   SVLA_CUDA_OK(cudaMemcpy(d_a, actions_host, sizeof(double) * 7 * n, cudaMemcpyHostToDevice));
   SVLA_CUDA_OK(cudaMemcpy(d_e, edges_host, sizeof(double) * ne, cudaMemcpyHostToDevice));
-  rc = svla_tok_encode(d_a, d_e, nbins_host, d_i, n, min_action, max_action, nullptr);
+  rc = svla_tok_encode(d_a, d_e, nbins_host, d_i, n, min_action, max_action, use_spherical, nullptr);
   if (rc == 0) SVLA_CUDA_OK(cudaMemcpy(ids_host, d_i, sizeof(int32_t) * 3 * n, cudaMemcpyDeviceToHost));
 done:
   cudaFree(d_a); cudaFree(d_e); cudaFree(d_i);
@@ -184,7 +189,7 @@ done:
 }
 
 extern "C" int svla_tok_decode_host(const int64_t* ids_host, const double* edges_host, const int32_t* nbins_host, int64_t begin,
-                                    double* actions_host, int64_t n) {
+                                    double* actions_host, int64_t n, int use_spherical) {
   if (n == 0) return 0;
   TokGrid g;
   const int ne = make_grid(nbins_host, g);
@@ -197,7 +202,7 @@ extern "C" int svla_tok_decode_host(const int64_t* ids_host, const double* edges
   SVLA_CUDA_OK(cudaMalloc(&d_i, sizeof(int64_t) * 3 * n));
   SVLA_CUDA_OK(cudaMemcpy(d_i, ids_host, sizeof(int64_t) * 3 * n, cudaMemcpyHostToDevice));
   SVLA_CUDA_OK(cudaMemcpy(d_e, edges_host, sizeof(double) * ne, cudaMemcpyHostToDevice));
-  rc = svla_tok_decode(d_i, d_e, nbins_host, begin, d_a, n, nullptr);
+  rc = svla_tok_decode(d_i, d_e, nbins_host, begin, d_a, n, use_spherical, nullptr);
   if (rc == 0) SVLA_CUDA_OK(cudaMemcpy(actions_host, d_a, sizeof(double) * 7 * n, cudaMemcpyDeviceToHost));
 done:
   cudaFree(d_a); cudaFree(d_e); cudaFree(d_i);

@@ -1,0 +1,179 @@
+"""`SpatialVLAForConditionalGeneration` -- the reference's model-side API (model/modeling_spatialvla.py:162-526)
+over the B200 engine: `predict_action`, `forward` (logits), `get_image_features`, `backproject_patch`,
+`from_pretrained`.  There is no torch.nn module tree and no CPU path: weights are repacked once into kernel layouts
+(spatialvla_b200/engine.py) and every FLOP runs in libspatialvla_b200.so.
+
+Differences from the reference, all deliberate and documented in DESIGN.md:
+  * `predict_action` decodes a fixed number of action tokens (3 per action x action_chunk_size, default 12) with the
+    argmax restricted to the spatial-action slice of the vocabulary instead of HF `generate(max_new_tokens=256)` +
+    EOS stop (north_star: "argmax restricted to the action vocabulary"); `max_new_tokens` can be passed.
+  * inputs stay fp32 (the reference rounds pixel_values *and* the intrinsic matrix to bf16 at :489).
+  * padded batches (attention_mask with zeros) and the training-time prefix-LM mask / loss are not part of this
+    path yet and raise NotImplementedError instead of silently mis-computing.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from .configuration_spatialvla import SpatialVLAConfig
+from .engine import SpatialVLAEngine
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+@dataclass
+class SpatialVLACausalLMOutputWithPast:
+    loss: Optional[torch.Tensor] = None
+    logits: torch.Tensor = None
+    past_key_values: Optional[dict] = None
+    hidden_states: Optional[tuple] = None
+    attentions: Optional[tuple] = None
+    image_hidden_states: Optional[torch.Tensor] = None
+
+
+class SpatialVLAForConditionalGeneration:
+    config_class = SpatialVLAConfig
+
+    def __init__(self, config, state_dict=None, device="cuda:0", ops=None, action_chunk_size: int = 4):
+        """config: SpatialVLAConfig or plain engine dict. state_dict: HF-keyed tensors (any float dtype); when None,
+        deterministic synthetic weights are generated (tests / bench: there is no network for checkpoints)."""
+        if isinstance(config, SpatialVLAConfig):
+            self.config, cfg = config, config.to_engine_dict()
+        else:
+            self.config, cfg = None, dict(config)
+        self.engine_config = cfg
+        if ops is None:
+            from .ops import CudaOps          # raises when the CUDA extension / device is missing -- no fallback
+            ops = CudaOps(device)
+        self.ops = ops
+        self.device = ops.device
+        self.dtype = BF16
+        if state_dict is None:
+            from .weights import synth_state_dict
+            state_dict = synth_state_dict(cfg, seed=0)
+        self.engine = SpatialVLAEngine(cfg, state_dict, ops)
+        self.action_chunk_size = action_chunk_size
+        self.vocab_size = cfg["text_config"]["vocab_size"]
+
+    # ------------------------------------------------------------------------------------------ construction
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, *model_args, config=None, device="cuda:0", **kwargs):
+        """Loads `config.json` + `*.safetensors` from a local directory written by the reference
+        (model/modeling_spatialvla.py:494-526).  Like the reference, the last `spatial_token_num` rows of
+        `embed_tokens` are overwritten with `spatial_embed_tokens` (:524-525)."""
+        path = str(pretrained_model_name_or_path)
+        if not os.path.isdir(path):
+            raise OSError(f"{path} is not a local directory (this build has no hub access)")
+        if config is None:
+            config = SpatialVLAConfig.from_pretrained(path)
+        from safetensors.torch import load_file
+        sd = {}
+        for fn in sorted(os.listdir(path)):
+            if fn.endswith(".safetensors"):
+                sd.update(load_file(os.path.join(path, fn)))
+        if not sd:
+            raise OSError(f"no *.safetensors under {path}")
+        if config.use_spatial_token:
+            n = config.spatial_token_num
+            sd["language_model.model.embed_tokens.weight"][-n:] = sd["spatial_embed_tokens.weight"]
+        return cls(config, sd, device=device, **kwargs)
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def cuda(self):
+        return self
+
+    # ------------------------------------------------------------------------------------------ hot path
+    def _prepare(self, model_inputs):
+        ids = model_inputs["input_ids"]
+        px = model_inputs.get("pixel_values") if hasattr(model_inputs, "get") else model_inputs["pixel_values"]
+        K = model_inputs.get("intrinsic") if hasattr(model_inputs, "get") else model_inputs["intrinsic"]
+        am = model_inputs.get("attention_mask") if hasattr(model_inputs, "get") else None
+        if am is not None and am.dim() == 2 and bool((am == 0).any()):
+            raise NotImplementedError("padded batches (attention_mask with zeros) are not supported on this path yet")
+        ids = ids.to(self.device, torch.int64).contiguous()
+        if px is not None:
+            px = px.to(self.device, F32).contiguous()
+            n_img = int((ids[0] == self.engine_config["image_token_index"]).sum())
+            if n_img * ids.shape[0] != px.shape[0] * 256:
+                raise ValueError(
+                    "Number of images does not match number of special image tokens in the input text. "
+                    f"Got {n_img * ids.shape[0]} image tokens in the text but {px.shape[0] * 256} tokens from image embeddings.")
+        if K is not None:
+            K = K.to(self.device, F32).contiguous()
+        return ids, px, K
+
+    @torch.no_grad()
+    def predict_action(self, model_inputs, max_new_tokens: Optional[int] = None, return_logits: bool = False):
+        """model_inputs: dict-like with input_ids (B,P), pixel_values (B,3,224,224) in [0,1], intrinsic (3,3)|(B,3,3)
+        -> LongTensor (B, n_new) of generated action-token ids on the model device (prompt stripped, :492)."""
+        ids, px, K = self._prepare(model_inputs)
+        n_new = int(max_new_tokens) if max_new_tokens is not None else 3 * self.action_chunk_size
+        out = self.engine.generate_actions(ids, px, K, n_new, return_logits=return_logits)
+        return out
+
+    @torch.no_grad()
+    def get_image_features(self, pixel_values: torch.Tensor, intrinsic: torch.Tensor):
+        """(B,3,224,224) in [0,1], K -> (B, 256, H_text) fp32, already / sqrt(H) (model/modeling_spatialvla.py:308-333)"""
+        return self.engine.image_features(pixel_values.to(self.device, F32).contiguous(), intrinsic.to(self.device, F32))
+
+    @torch.no_grad()
+    def predict_depth(self, pixel_values: torch.Tensor):
+        """ZoeDepth metric depth at 384x384 for [0,1] 224x224 images (the tensor :317 produces)."""
+        return self.engine.zoedepth(pixel_values.to(self.device, F32).contiguous())
+
+    @torch.no_grad()
+    def backproject_patch(self, K: torch.Tensor, depth384: torch.Tensor, patch_size=14, reso=2) -> torch.Tensor:
+        """Fused kernel for model/modeling_spatialvla.py:318-323 + :195-223: takes the 384x384 ZoeDepth output
+        (B,384,384), resamples/crops to 224, area-pools and back-projects -> (B, 256, 12) fp32."""
+        if patch_size != 14 or reso != 2:
+            raise NotImplementedError("the fused Ego3D kernel is specialised for patch 14 / reso 2 (4B-224 config)")
+        B = depth384.shape[0]
+        xyz = self.ops.empty((B * 256, 12), F32)
+        enc = self.ops.empty((B * 256, self.engine.ego_kpad), BF16)
+        self.ops.ego3d_encode(depth384.to(self.device, F32).contiguous(), K.to(self.device, F32).contiguous(), xyz, enc,
+                              n_freqs=self.engine_config["n_freqs"])
+        return xyz.view(B, 256, 12)
+
+    @torch.no_grad()
+    def forward(self, input_ids=None, pixel_values=None, actions=None, intrinsic=None, attention_mask=None,
+                position_ids=None, past_key_values=None, token_type_ids=None, cache_position=None, inputs_embeds=None,
+                labels=None, use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None,
+                num_logits_to_keep: int = 0):
+        """Inference forward (model/modeling_spatialvla.py:335-442): full-vocabulary post-softcap logits (fp32) for the
+        last `num_logits_to_keep` positions (0 = all). `past_key_values` is this engine's cache dict."""
+        if labels is not None or token_type_ids is not None:
+            raise NotImplementedError("training forward (labels / prefix-LM mask) is not part of this path yet")
+        if inputs_embeds is not None or position_ids is not None or output_attentions or output_hidden_states:
+            raise NotImplementedError("inputs_embeds / position_ids / output_attentions / output_hidden_states")
+        eng = self.engine
+        ids, px, K = self._prepare({"input_ids": input_ids, "pixel_values": pixel_values, "intrinsic": intrinsic,
+                                    "attention_mask": attention_mask if (attention_mask is not None and attention_mask.dim() == 2) else None})
+        B, S = ids.shape
+        feats = eng.image_features(px, K) if px is not None else None
+        x, status = eng.embed(ids, feats)
+        cache = past_key_values if past_key_values is not None else eng.new_cache(B, S + 256)
+        prefill = cache["len"] == 0
+        h = eng.gemma_forward(x, B, S, cache, bidirectional=prefill)
+        H = h.shape[-1]
+        keep = S if num_logits_to_keep in (0, None) else int(num_logits_to_keep)
+        rows = h.view(B, S, H)[:, S - keep:].reshape(B * keep, H)
+        V = self.vocab_size
+        cap = eng.t["final_logit_softcapping"]
+        logits = self.ops.empty((B * keep, V), F32)
+        from ._lib import ACT_NONE, ACT_SOFTCAP
+        self.ops.gemm(rows, eng.lm_head_full(), out_f32=logits, act=ACT_SOFTCAP if cap else ACT_NONE, act_param=cap or 0.0)
+        if int(status.item()) == 1:
+            raise ValueError("Number of images does not match number of special image tokens in the input text.")
+        return SpatialVLACausalLMOutputWithPast(logits=logits.view(B, keep, V), past_key_values=cache,
+                                                image_hidden_states=feats)
+
+    __call__ = forward

@@ -212,13 +212,13 @@ class CudaOps:
                 "svla_ego3d_encode")
 
     # ---- M8 tokenizer (device buffers)
-    def tok_encode(self, actions, edges, nbins_host, ids, *, min_action=-1.0, max_action=1.0):
+    def tok_encode(self, actions, edges, nbins_host, ids, *, min_action=-1.0, max_action=1.0, use_spherical=True):
         nb = (C.c_int32 * 7)(*nbins_host)
         L.check(self.lib.svla_tok_encode(_ptr(actions), _ptr(edges), C.cast(nb, C.c_void_p), _ptr(ids),
-                                         actions.shape[0], float(min_action), float(max_action), self._stream()),
-                "svla_tok_encode")
+                                         actions.shape[0], float(min_action), float(max_action), int(use_spherical),
+                                         self._stream()), "svla_tok_encode")
 
-    def tok_decode(self, ids, edges, nbins_host, begin, actions):
+    def tok_decode(self, ids, edges, nbins_host, begin, actions, *, use_spherical=True):
         nb = (C.c_int32 * 7)(*nbins_host)
         L.check(self.lib.svla_tok_decode(_ptr(ids), _ptr(edges), C.cast(nb, C.c_void_p), int(begin), _ptr(actions),
-                                         ids.shape[0], self._stream()), "svla_tok_decode")
+                                         ids.shape[0], int(use_spherical), self._stream()), "svla_tok_decode")

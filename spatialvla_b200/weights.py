@@ -209,17 +209,20 @@ def _is_norm_weight(key: str) -> bool:
     return any(key.endswith(n) for n in names) or leaf in names
 
 
-def synth_tensor(key: str, shape: tuple, seed: int = 0, device="cpu") -> torch.Tensor:
+def synth_tensor(key: str, shape: tuple, seed: int = 0, device="cpu", on_device_rng: bool = False) -> torch.Tensor:
     """One synthetic fp32 parameter. Fan-in scaled normals keep activations O(1) through every sub-model so
-    that parity tests are sensitive (a sigma=0.02 init makes ZoeDepth's output nearly constant)."""
-    g = torch.Generator(device="cpu")
+    that parity tests are sensitive (a sigma=0.02 init makes ZoeDepth's output nearly constant).
+    `on_device_rng` draws with the device generator (fast for the 4 B-parameter bench model; values then differ
+    from the CPU stream, so parity tests never use it)."""
+    gdev = device if on_device_rng else "cpu"
+    g = torch.Generator(device=gdev)
     g.manual_seed((zlib.crc32(key.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
     n = 1
     for s in shape:
         n *= s
 
     def randn(std=1.0):
-        return torch.randn(n, generator=g, dtype=torch.float32).reshape(shape) * std
+        return torch.randn(n, generator=g, dtype=torch.float32, device=gdev).reshape(shape) * std
 
     if key.startswith("language_model.model.layers") and key.endswith("layernorm.weight") \
             or key == "language_model.model.norm.weight":
@@ -238,7 +241,7 @@ def synth_tensor(key: str, shape: tuple, seed: int = 0, device="cpu") -> torch.T
         out = randn(0.02)
     elif "conditional_log_binomial" in key and key.endswith("mlp.2.bias"):
         # low temperature -> peaked bin distribution -> depth varies strongly per pixel (sensitive parity tests)
-        out = torch.tensor([0.0, 0.0, -4.0, 3.0]) + randn(0.05)
+        out = torch.tensor([0.0, 0.0, -4.0, 3.0], device=gdev) + randn(0.05)
     elif key.endswith(".bias"):
         out = randn(0.05)
     elif len(shape) >= 2:
@@ -253,7 +256,8 @@ def synth_tensor(key: str, shape: tuple, seed: int = 0, device="cpu") -> torch.T
     return out.to(device)
 
 
-def synth_state_dict(cfg: dict, seed: int = 0, prefix_filter=None, device="cpu", bf16_round: bool = True):
+def synth_state_dict(cfg: dict, seed: int = 0, prefix_filter=None, device="cpu", bf16_round: bool = True,
+                     on_device_rng: bool = False, dtype=torch.float32):
     """All (or a prefix-filtered subset of) parameters. With `bf16_round` every GEMM operand matrix is rounded
     to bf16 and stored back as fp32, so the fp32 oracle and the bf16 B200 path share identical weights
     (weight quantisation is common-mode; SURVEY.md §7 'bf16-vs-fp32 flips')."""
@@ -261,8 +265,9 @@ def synth_state_dict(cfg: dict, seed: int = 0, prefix_filter=None, device="cpu",
     for key, shape in state_dict_spec(cfg).items():
         if prefix_filter is not None and not any(key.startswith(p) for p in prefix_filter):
             continue
-        t = synth_tensor(key, shape, seed)
+        t = synth_tensor(key, shape, seed, device=device, on_device_rng=on_device_rng)
         if bf16_round and t.dim() >= 2:
-            t = t.to(torch.bfloat16).to(torch.float32)
+            t = t.to(torch.bfloat16)
+            t = t if dtype == torch.bfloat16 else t.to(torch.float32)
         sd[key] = t.to(device)
     return sd

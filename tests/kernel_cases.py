@@ -1,0 +1,475 @@
+"""Per-kernel parity cases: every C-ABI op (CUDA, through spatialvla_b200.ops.CudaOps) against its torch oracle
+(oracle.ops_ref.RefOps) on the same seeded inputs.  Used by tests/test_kernels_gpu.py (pytest -m gpu) and by
+tools/gpu_selftest.py (one subprocess per case, so one faulting kernel cannot hide the others).
+
+Tolerances (written here, used by both): bf16 outputs: max|err| <= 1e-2 * max|ref| (one bf16 ulp is 2^-8 relative,
+plus fp32 accumulation-order noise); fp32 outputs: 1e-3 * max|ref| unless stated; integer outputs: exact.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle.ops_ref import RefOps  # noqa: E402
+from spatialvla_b200._lib import (ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_RELU, ACT_SOFTCAP, ACT_SOFTPLUS)  # noqa: E402
+
+BF16, F32 = torch.bfloat16, torch.float32
+TOL_BF16, TOL_F32 = 1e-2, 1e-3
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _randn(g, *shape, dtype=F32, scale=1.0):
+    return (torch.randn(*shape, generator=g) * scale).to(dtype)
+
+
+def _err(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    denom = max(float(ref.abs().max()), 1e-20)
+    return float((got - ref).abs().max()) / denom
+
+
+class Result:
+    def __init__(self, name):
+        self.name, self.items = name, []
+
+    def add(self, what, err, tol):
+        self.items.append((what, float(err), float(tol)))
+
+    @property
+    def ok(self):
+        return all(e <= t and e == e for _, e, t in self.items)
+
+    def __str__(self):
+        return f"{self.name}: " + ", ".join(f"{w} err={e:.3e} (tol {t:.0e}){'' if e <= t else ' FAIL'}" for w, e, t in self.items)
+
+
+def _both(fn, dev):
+    """Run `fn(ops, to)` with the CUDA ops and the reference ops; `to` moves inputs to the op device."""
+    from spatialvla_b200.ops import CudaOps
+    cu = CudaOps(dev)
+    rf = RefOps()
+    out_c = fn(cu, lambda t: None if t is None else t.to(dev))
+    torch.cuda.synchronize()
+    out_r = fn(rf, lambda t: None if t is None else t.clone())
+    return out_c, out_r
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+def gemm_case(name, M, N, K, *, lda=None, bias=False, act=ACT_NONE, act_param=0.0, colscale=False, res_bf16=False,
+              res2=False, res_f32=False, res_mod=0, out=("bf16",), accumulate=False, geglu=False, alpha=1.0,
+              block_n=0, conv=None, seed=0, impl=None):
+    def case(dev="cuda:0"):
+        g = _gen(seed)
+        if conv is not None:
+            nb, h, w, c = conv
+            cpad = (c + 63) // 64 * 64
+            a = _randn(g, nb, h, w, c, dtype=BF16)
+            wt = torch.zeros(N, 9, cpad)
+            wt[:, :, :c] = torch.randn(N, 9, c, generator=g) / (9 * c) ** 0.5
+            wt = wt.reshape(N, 9 * cpad).to(BF16)
+            m = nb * h * w
+        else:
+            ld = lda or K
+            a = _randn(g, M, ld, dtype=BF16)          # sliced to [:, :K] after the move so the row stride survives
+            wt = (_randn(g, N, K) / K ** 0.5).to(BF16)
+            m = M
+        ncol = N // 2 if geglu else N
+        ldo = (ncol + 7) // 8 * 8 if ncol % 8 else ncol
+        t = {"bias": _randn(g, N) if bias else None, "colscale": (_randn(g, N) * 0.5 + 1.0) if colscale else None,
+             "res_bf16": _randn(g, m, ldo, dtype=BF16) if res_bf16 else None,
+             "res2_bf16": _randn(g, m, ldo, dtype=BF16) if res2 else None,
+             "res_f32": _randn(g, res_mod or m, ldo) if res_f32 else None,
+             "init_f32": _randn(g, m, ldo) if accumulate else None}
+
+        def run(ops, to):
+            A, W = to(a), to(wt)
+            if conv is None and A.shape[1] != K:
+                A = A[:, :K]
+            o_b = ops.zeros((m, ldo), BF16) if "bf16" in out else None
+            o_f = (to(t["init_f32"]) if accumulate else ops.zeros((m, ldo), F32)) if "f32" in out else None
+            o_r = ops.zeros((m, ldo), BF16) if "relu" in out else None
+            ops.gemm(A, W, out_bf16=o_b, out_f32=o_f, out_relu=o_r, bias=to(t["bias"]), colscale=to(t["colscale"]),
+                     res_bf16=to(t["res_bf16"]), res2_bf16=to(t["res2_bf16"]), res_f32=to(t["res_f32"]), res_mod=res_mod,
+                     act=act, act_param=act_param, alpha=alpha, geglu=geglu, accumulate=accumulate, conv=conv,
+                     block_n=block_n, impl=impl)
+            return o_b, o_f, o_r
+        (cb, cf, cr), (rb, rf_, rr) = _both(run, dev)
+        res = Result(name)
+        if cb is not None:
+            res.add("bf16", _err(cb, rb), TOL_BF16)
+        if cf is not None:
+            res.add("f32", _err(cf, rf_), TOL_F32)
+        if cr is not None:
+            res.add("relu", _err(cr, rr), TOL_BF16)
+        return res
+    case.__name__ = name
+    return case
+
+
+GEMM_CASES = [
+    gemm_case("gemm_basic_256", 256, 256, 128),
+    gemm_case("gemm_bn128", 256, 256, 128, block_n=128),
+    gemm_case("gemm_bn64", 128, 64, 64, block_n=64, out=("bf16", "f32")),
+    gemm_case("gemm_bn32_n2", 64, 2, 128, out=("f32",), bias=True),
+    gemm_case("gemm_n16_n40", 1000, 40, 32, out=("bf16",)),
+    gemm_case("gemm_ragged_bias_gelu", 300, 200, 104, bias=True, act=ACT_GELU_TANH, out=("bf16", "f32")),
+    gemm_case("gemm_gelu_erf_colscale_accum", 577, 128, 256, bias=True, act=ACT_GELU_ERF, colscale=True, out=("f32",), accumulate=True),
+    gemm_case("gemm_posemb_resmod", 1024, 1152, 640, bias=True, res_f32=True, res_mod=256, out=("f32",)),
+    gemm_case("gemm_geglu", 512, 1024, 256, geglu=True),
+    gemm_case("gemm_softcap_tail", 64, 8194, 512, act=ACT_SOFTCAP, act_param=30.0, out=("f32",)),
+    gemm_case("gemm_softplus_f32", 288, 64, 64, bias=True, act=ACT_SOFTPLUS, out=("f32",)),
+    gemm_case("gemm_strided_a", 64, 128, 512, lda=512 * 7),
+    gemm_case("gemm_res_bf16_relu_copy", 384, 256, 256, bias=True, res_bf16=True, res2=True, out=("bf16", "relu")),
+    gemm_case("gemm_long_k", 256, 256, 9216),
+    gemm_case("gemm_multiwave", 4096 + 77, 4304, 1152, bias=True, act=ACT_GELU_TANH),
+    gemm_case("gemm_multiwave_bn128", 20000, 1152, 576, block_n=128, out=("f32",), accumulate=True),
+    gemm_case("conv_24_c64", 0, 64, 0, conv=(2, 24, 24, 64), bias=True, act=ACT_RELU),
+    gemm_case("conv_12_c128_res", 0, 64, 0, conv=(3, 12, 12, 128), bias=True, res_bf16=True, res2=True, out=("bf16", "relu")),
+    gemm_case("conv_48_c32", 0, 32, 0, conv=(1, 48, 48, 32), bias=True),
+    gemm_case("conv_96_c256", 0, 256, 0, conv=(2, 96, 96, 256)),
+    gemm_case("conv_odd_20x28", 0, 128, 0, conv=(2, 20, 28, 64), bias=True),
+]
+SIMT_CASES = [
+    gemm_case("simt_ragged", 300, 200, 104, bias=True, act=ACT_GELU_TANH, out=("bf16", "f32"), impl=1),
+    gemm_case("simt_conv", 0, 64, 0, conv=(2, 24, 24, 64), bias=True, act=ACT_RELU, impl=1),
+    gemm_case("simt_geglu", 128, 256, 64, geglu=True, impl=1),
+]
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def attn_case(name, B, hq, hkv, sq, sk, d, *, scale=None, softcap=0.0, causal=False, relpos_win=0, packed_qkv=False,
+              smax=None, seed=0):
+    def case(dev="cuda:0"):
+        g = _gen(seed)
+        sc = scale if scale is not None else d ** -0.5
+        if packed_qkv:      # [B*S, 3*hq*d] like the ViT towers
+            D = hq * d
+            qkv = _randn(g, B * sq, 3 * D, dtype=BF16)
+            tab = _randn(g, (2 * relpos_win - 1) ** 2 + 3, hq, scale=0.5) if relpos_win else None
+
+            def run(ops, to):
+                t = to(qkv)
+                out = ops.zeros((B * sq, D), BF16)
+                st = (sq * 3 * D, 3 * D)
+                ops.attention(t, t[:, D:], t[:, 2 * D:], out, batch=B, hq=hq, hkv=hkv, sq=sq, sk=sk, d=d, q_strides=st,
+                              k_strides=st, v_strides=st, o_strides=(sq * D, D), scale=sc, softcap=softcap, causal=causal,
+                              relpos_table=to(tab), relpos_win=relpos_win)
+                return out
+        else:               # Gemma2 layout: q [B*sq, hq*d], cache [B, smax, hkv, d]
+            sm = smax or sk
+            q = _randn(g, B * sq, hq * d, dtype=BF16)
+            kc = _randn(g, B, sm, hkv, d, dtype=BF16)
+            vc = _randn(g, B, sm, hkv, d, dtype=BF16)
+
+            def run(ops, to):
+                out = ops.zeros((B * sq, hq * d), BF16)
+                kvs = (sm * hkv * d, hkv * d)
+                ops.attention(to(q), to(kc), to(vc), out, batch=B, hq=hq, hkv=hkv, sq=sq, sk=sk, d=d,
+                              q_strides=(sq * hq * d, hq * d), k_strides=kvs, v_strides=kvs, o_strides=(sq * hq * d, hq * d),
+                              scale=sc, softcap=softcap, causal=causal)
+                return out
+        c, r = _both(run, dev)
+        res = Result(name)
+        res.add("out", _err(c, r), 1.5e-2)
+        return res
+    case.__name__ = name
+    return case
+
+
+def decode_attn_case(dev="cuda:0"):
+    g = _gen(3)
+    B, hq, hkv, d, smax, ctx = 3, 4, 2, 256, 300, 271
+    q, kc, vc = _randn(g, B, hq * d, dtype=BF16), _randn(g, B, smax, hkv, d, dtype=BF16), _randn(g, B, smax, hkv, d, dtype=BF16)
+
+    def run(ops, to):
+        out = ops.zeros((B, hq * d), BF16)
+        ops.decode_attention(to(q), to(kc), to(vc), out, batch=B, hq=hq, hkv=hkv, d=d, smax=smax, ctx=ctx, scale=1 / 16, softcap=50.0)
+        return out
+    c, r = _both(run, dev)
+    res = Result("decode_attention")
+    res.add("out", _err(c, r), 1.5e-2)
+    return res
+
+
+ATTN_CASES = [
+    attn_case("attn_siglip_d72", 2, 2, 2, 256, 256, 72, packed_qkv=True),
+    attn_case("attn_beit_d64_relpos", 1, 2, 2, 577, 577, 64, packed_qkv=True, relpos_win=24),
+    attn_case("attn_router_d32", 2, 4, 4, 145, 145, 32, packed_qkv=True),
+    attn_case("attn_gemma_prefill_d256", 2, 4, 2, 278, 278, 256, scale=1 / 16, softcap=50.0, smax=290),
+    attn_case("attn_gemma_causal_d256", 1, 2, 1, 70, 70, 256, scale=1 / 16, softcap=50.0, causal=True, smax=80),
+    attn_case("attn_d128_generic", 1, 2, 2, 100, 130, 128, causal=False, smax=130),
+    decode_attn_case,
+]
+
+
+# ------------------------------------------------------------------------------------------------ fused ops
+def layernorm_case(dev="cuda:0"):
+    res = Result("layernorm")
+    for cols, rows in ((144, 37), (1152, 300), (4304, 5), (128, 290)):
+        g = _gen(cols)
+        x, ga, be = _randn(g, rows, cols), _randn(g, cols) * 0.1 + 1, _randn(g, cols) * 0.1
+
+        def run(ops, to):
+            ob, of = ops.zeros((rows, cols), BF16), ops.zeros((rows, cols), F32)
+            ops.layernorm(to(x), to(ga), to(be), 1e-6, out_bf16=ob, out_f32=of, relu=(cols == 128))
+            return ob, of
+        (cb, cf), (rb, rf_) = _both(run, dev)
+        res.add(f"bf16[{cols}]", _err(cb, rb), TOL_BF16)
+        res.add(f"f32[{cols}]", _err(cf, rf_), 1e-4)
+    return res
+
+
+def rmsnorm_case(dev="cuda:0"):
+    res = Result("rmsnorm_residual")
+    for cols, rows in ((2304, 70), (512, 9)):
+        g = _gen(cols)
+        x, br = _randn(g, rows, cols), _randn(g, rows, cols, scale=3.0)
+        wp, wq = _randn(g, cols) * 0.1, _randn(g, cols) * 0.1
+
+        def run(ops, to):
+            xx, ob = to(x), ops.zeros((rows, cols), BF16)
+            ops.rmsnorm_residual(xx, branch=to(br), w_post=to(wp), w_pre=to(wq), eps=1e-6, out_bf16=ob)
+            ob2 = ops.zeros((rows, cols), BF16)
+            ops.rmsnorm_residual(xx, w_pre=to(wp), eps=1e-6, out_bf16=ob2)
+            return xx, ob, ob2
+        (cx, cb, cb2), (rx, rb, rb2) = _both(run, dev)
+        res.add(f"x[{cols}]", _err(cx, rx), 1e-5)
+        res.add(f"h[{cols}]", _err(cb, rb), TOL_BF16)
+        res.add(f"h2[{cols}]", _err(cb2, rb2), TOL_BF16)
+    return res
+
+
+def rope_case(dev="cuda:0"):
+    g = _gen(5)
+    B, S, hq, hkv, d, smax, pos0 = 2, 37, 4, 2, 256, 64, 11
+    qkv = _randn(g, B * S, (hq + 2 * hkv) * d, dtype=BF16)
+
+    def run(ops, to):
+        q, kc, vc = ops.zeros((B * S, hq * d), BF16), ops.zeros((B, smax, hkv, d), BF16), ops.zeros((B, smax, hkv, d), BF16)
+        ops.rope_kv(to(qkv), q, kc, vc, batch=B, s=S, hq=hq, hkv=hkv, d=d, smax=smax, pos0=pos0, theta=10000.0)
+        return q, kc, vc
+    c, r = _both(run, dev)
+    res = Result("rope_kv")
+    for nm, a, b in zip(("q", "k", "v"), c, r):
+        res.add(nm, _err(a, b), TOL_BF16 if nm != "v" else 0.0)
+    return res
+
+
+def embed_case(dev="cuda:0"):
+    g = _gen(6)
+    B, S, H, V, n_act, n_img = 3, 40, 512, 9216, 8194, 16
+    act_lo, img_tok = 1022, 1021
+    ids = torch.randint(3, 1000, (B, S), generator=g)
+    ids[:, 2:2 + n_img] = img_tok
+    ids[:, -3:] = torch.randint(act_lo, act_lo + n_act, (B, 3), generator=g)
+    emb, sp, img = _randn(g, V, H, dtype=BF16), _randn(g, n_act, H, dtype=BF16), _randn(g, B, n_img, H)
+
+    def run(ops, to):
+        x, st = ops.zeros((B * S, H), F32), ops.zeros((1,), torch.int32)
+        ops.embed_tokens(to(ids), to(emb), to(sp), to(img), x, image_token=img_tok, act_lo=act_lo, n_act=n_act, n_img=n_img,
+                         normalizer=float(torch.tensor(H ** 0.5)), status=st)
+        return x, st
+    (cx, cs), (rx, rs) = _both(run, dev)
+    res = Result("embed_tokens")
+    res.add("x", _err(cx, rx), 1e-6)
+    res.add("status", abs(int(cs.item()) - int(rs.item())), 0)
+    return res
+
+
+def argmax_case(dev="cuda:0"):
+    g = _gen(7)
+    lg = _randn(g, 64, 8194)
+    lg[3, 100] = lg[3, 7000] = 9.0          # tie -> first index wins (torch.argmax)
+    lg[5, 8193] = 11.0
+
+    def run(ops, to):
+        out = ops.zeros((64, 4), torch.int64)
+        ops.argmax_rows(to(lg), out[:, 2], id_offset=257153)
+        return out
+    c, r = _both(run, dev)
+    res = Result("argmax_rows")
+    res.add("ids", float((c.cpu() != r).sum()), 0)
+    return res
+
+
+def patchify_case(dev="cuda:0"):
+    g = _gen(8)
+    px = torch.rand(2, 3, 224, 224, generator=g)
+    px = torch.nn.functional.avg_pool2d(px, 3, 1, 1)
+
+    def run(ops, to):
+        a, b = ops.zeros((2 * 256, 640), BF16), ops.zeros((2 * 576, 768), BF16)
+        ops.siglip_patchify(to(px), a)
+        ops.zoe_patchify(to(px), b)
+        return a, b
+    (ca, cb), (ra, rb) = _both(run, dev)
+    res = Result("patchify")
+    res.add("siglip", _err(ca, ra), 0.0)
+    res.add("zoe_bicubic", _err(cb, rb), TOL_BF16)
+    return res
+
+
+def assemble_concat_case(dev="cuda:0"):
+    g = _gen(9)
+    B, n, c = 2, 576, 128
+    patches, cls = _randn(g, B * n, c), _randn(g, c)
+
+    def run(ops, to):
+        x = ops.zeros((B * (n + 1), c), F32)
+        ops.beit_assemble(to(patches), to(cls), x, batch=B, n=n, c=c)
+        a = ops.zeros((B * n, 2 * c), BF16)
+        ops.readout_concat(x, a, batch=B, n=n, c=c)
+        return x, a
+    (cx, ca), (rx, ra) = _both(run, dev)
+    res = Result("beit_assemble+readout_concat")
+    res.add("x", _err(cx, rx), 0.0)
+    res.add("concat", _err(ca, ra), 0.0)
+    return res
+
+
+def shuffle_im2col_case(dev="cuda:0"):
+    g = _gen(10)
+    B, h, w, c = 2, 24, 24, 64
+    gt = _randn(g, B * h * w, 16 * c, dtype=BF16)
+    x = _randn(g, B, h, w, c, dtype=BF16)
+
+    def run(ops, to):
+        o4 = ops.zeros((B * h * 4 * w * 4, c), BF16)
+        ops.pixel_shuffle(to(gt), o4, batch=B, h=h, w=w, c=c, f=4)
+        o2 = ops.zeros((B * h * 2 * w * 2, c), BF16)
+        ops.pixel_shuffle(to(gt)[:, : 4 * c].contiguous(), o2, batch=B, h=h, w=w, c=c, f=2)
+        col = ops.zeros((B * (h // 2) * (w // 2), 9 * c), BF16)
+        ops.im2col3x3_s2(to(x), col, batch=B, h=h, w=w, c=c)
+        return o4, o2, col
+    c_, r_ = _both(run, dev)
+    res = Result("pixel_shuffle+im2col_s2")
+    for nm, a, b in zip(("shuffle4", "shuffle2", "im2col"), c_, r_):
+        res.add(nm, _err(a, b), 0.0)
+    return res
+
+
+def bilinear_case(dev="cuda:0"):
+    g = _gen(11)
+    res = Result("bilinear_nhwc")
+    for (h, w, oh, ow, c) in ((12, 12, 24, 24, 128), (24, 24, 48, 48, 64), (7, 9, 21, 20, 8)):
+        x, ad = _randn(g, 2, h, w, c, dtype=BF16), _randn(g, 2, oh, ow, c, dtype=BF16)
+
+        def run(ops, to):
+            o, orl = ops.zeros((2, oh, ow, c), BF16), ops.zeros((2, oh, ow, c), BF16)
+            ops.bilinear_nhwc(to(x), o, batch=2, h=h, w=w, c=c, oh=oh, ow=ow, add=to(ad), out_relu=orl)
+            rl = ops.zeros((2, h, w, c), BF16)
+            ops.relu_bf16(to(x), rl)
+            return o, orl, rl
+        (co, cr, cl), (ro, rr, rl_) = _both(run, dev)
+        res.add(f"out[{h}->{oh}]", _err(co, ro), TOL_BF16)
+        res.add(f"relu[{h}->{oh}]", _err(cr, rr), TOL_BF16)
+        res.add(f"relu_bf16[{h}]", _err(cl, rl_), 0.0)
+    return res
+
+
+def zoe_tail_case(dev="cuda:0"):
+    g = _gen(12)
+    B, h, w, oh, ow, na, nb, nh = 2, 12, 12, 24, 24, 16, 64, 40
+    attr = _randn(g, B * oh * ow, na, dtype=BF16)
+    prev = torch.nn.functional.softplus(_randn(g, B, h, w, nb))
+    conv = _randn(g, B * 144, 128)
+    t, e = _randn(g, B * oh * ow, nh, dtype=BF16), _randn(g, B, h, w, nh, dtype=BF16)
+    b1, w2, b2 = _randn(g, nh) * 0.1, _randn(g, 4, nh) * 0.3, torch.tensor([0.0, 0.0, -4.0, 3.0])
+    sp_in = _randn(g, 1000, dtype=BF16)
+
+    def run(ops, to):
+        bins = ops.zeros((B * oh * ow, nb), F32)
+        ops.zoe_attractor(to(attr), to(prev), bins, batch=B, h=h, w=w, oh=oh, ow=ow, na=na, nbins=nb)
+        e32, eb = ops.zeros((B * 145, 128), F32), ops.zeros((B * 145, 128), BF16)
+        ops.zoe_router_embed(to(conv), e32, eb, batch=B, n=144, c=128)
+        depth = ops.zeros((B, oh, ow), F32)
+        ops.zoe_depth_tail(to(t), to(e), to(b1), to(w2), to(b2), to(prev), depth, batch=B, h=h, w=w, oh=oh, ow=ow, nh=nh,
+                           nbins=nb, min_temp=0.0212, max_temp=50.0)
+        sp = ops.zeros((1000,), F32)
+        ops.softplus_f32(to(sp_in), sp)
+        return bins, e32, eb, depth, sp
+    c_, r_ = _both(run, dev)
+    res = Result("zoe_metric_tail")
+    for nm, a, b, tol in zip(("attractor", "router_embed", "router_embed_bf16", "depth_tail", "softplus"), c_, r_,
+                             (1e-4, 1e-4, TOL_BF16, 2e-3, 1e-5)):
+        res.add(nm, _err(a, b), tol)
+    return res
+
+
+def ego3d_case(dev="cuda:0"):
+    from spatialvla_b200.configs import default_intrinsic_224
+    g = _gen(13)
+    B = 3
+    depth = torch.rand(B, 384, 384, generator=g) * 4.7 + 0.3
+    depth = torch.nn.functional.avg_pool2d(depth[:, None], 9, 1, 4)[:, 0].contiguous()
+    K1 = torch.tensor(default_intrinsic_224())
+    Kb = K1[None].repeat(B, 1, 1) * torch.tensor([1.0, 1.1, 0.9])[:, None, None]
+    Kb[:, 2, 2] = 1.0
+    res = Result("ego3d_encode")
+    for nm, K in (("K3x3", K1), ("Kbatched", Kb.contiguous())):
+        def run(ops, to):
+            xyz, enc = ops.zeros((B * 256, 12), F32), ops.zeros((B * 256, 208), BF16)
+            ops.ego3d_encode(to(depth), to(K), xyz, enc, n_freqs=8)
+            return xyz, enc
+        (cx, ce), (rx, re_) = _both(run, dev)
+        res.add(f"xyz[{nm}]", _err(cx, rx), 1e-5)
+        # sin/cos of 2^7 * x amplify the fp32 xyz difference: compare with an absolute bf16-level tolerance
+        res.add(f"enc[{nm}]", float((ce.float().cpu() - re_.float()).abs().max()), 2e-2)
+    return res
+
+
+def tokenizer_case(dev="cuda:0"):
+    """Bit-exact ids against the golden vectors minted from the live reference; decode within 4 ulp (sin/cos)."""
+    from spatialvla_b200.ops import CudaOps
+    ops = CudaOps(dev)
+    res = Result("tokenizer")
+    for name in ("gauss", "uniform"):
+        gold = np.load(os.path.join(ROOT, "tests", "golden", f"tokenizer_{name}.npz"))
+        keys = ("theta_bins", "phi_bins", "r_bins", "roll_bins", "pitch_bins", "yaw_bins")
+        edges = np.concatenate([gold[f"edge_{k}"] for k in keys])
+        nb = [len(gold[f"edge_{k}"]) - 1 for k in keys] + [2]
+        acts = torch.from_numpy(gold["actions"]).to(dev)
+        ids = torch.zeros(acts.shape[0], 3, dtype=torch.int32, device=dev)
+        ed = torch.from_numpy(edges).to(dev)
+        ops.tok_encode(acts, ed, nb, ids)
+        got = ids.cpu().numpy()
+        mism = got != gold["local_ids"]
+        n_bad = int(mism.any(1).sum())
+        # rows where a transcendental (atan2) lands within 4 ulp of a bin edge are platform-dependent
+        if n_bad:
+            a = np.clip(gold["actions"][mism.any(1)], -1, 1)
+            th = np.arctan2(np.sqrt(a[:, 0] ** 2 + a[:, 1] ** 2), a[:, 2])
+            ph = np.arctan2(a[:, 1], a[:, 0])
+            near = (np.abs(th[:, None] - gold["edge_theta_bins"][None]).min(1) <= 4 * np.spacing(np.abs(th))) | \
+                   (np.abs(ph[:, None] - gold["edge_phi_bins"][None]).min(1) <= 4 * np.spacing(np.abs(ph)))
+            n_bad -= int(near.sum())
+        res.add(f"encode_mismatch[{name}]", n_bad, 0)
+        res.add(f"encode_exact_frac_missing[{name}]", float(mism.any(1).mean()), 5e-4)
+        dids = torch.from_numpy(gold["decode_ids"]).to(dev)
+        out = torch.zeros(dids.shape[0], 7, dtype=torch.float64, device=dev)
+        ops.tok_decode(dids, ed, nb, int(gold["begin"]), out)
+        ref = gold["decode_actions"]
+        ulp = np.abs(out.cpu().numpy() - ref) / np.maximum(np.spacing(np.abs(ref)), 1e-300)
+        res.add(f"decode_ulp_xyz[{name}]", float(ulp[:, :3].max()), 4)
+        res.add(f"decode_ulp_rot_grip[{name}]", float(ulp[:, 3:].max()), 0)
+        oob = torch.from_numpy(gold["oob_ids"]).to(dev)
+        out2 = torch.zeros(oob.shape[0], 7, dtype=torch.float64, device=dev)
+        ops.tok_decode(oob, ed, nb, int(gold["begin"]), out2)
+        res.add(f"decode_oob[{name}]", float(np.abs(out2.cpu().numpy() - gold["oob_actions"]).max()), 1e-15)
+    return res
+
+
+FUSED_CASES = [layernorm_case, rmsnorm_case, rope_case, embed_case, argmax_case, patchify_case, assemble_concat_case,
+               shuffle_im2col_case, bilinear_case, zoe_tail_case, ego3d_case, tokenizer_case]
+
+ALL_CASES = {c.__name__: c for c in (SIMT_CASES + GEMM_CASES + ATTN_CASES + FUSED_CASES)}

@@ -1,0 +1,109 @@
+"""CPU: the host orchestration (weight repack + kernel sequence) run through the torch op re-statements
+(oracle/ops_ref.py) against the fp32 oracle and the golden vectors; config / processor / sharding helpers."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import model_ref as R
+from oracle.gen_golden import tiny_inputs
+from oracle.ops_ref import RefOps
+from spatialvla_b200.engine import SpatialVLAEngine, pack_conv3x3, pack_conv3x3_im2col, pack_deconv
+from spatialvla_b200.weights import synth_state_dict
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    cfg, px_u8, ids, K = tiny_inputs()
+    sd = synth_state_dict(cfg, seed=0)
+    return cfg, px_u8.float() / 255.0, ids, K, sd, SpatialVLAEngine(cfg, sd, RefOps())
+
+
+def test_engine_matches_oracle_and_golden(tiny):
+    cfg, px, ids, K, sd, eng = tiny
+    g = np.load(os.path.join(GOLD, "tiny_model.npz"))
+    with torch.no_grad():
+        feats, aux = eng.image_features(px, K, return_aux=True)
+        toks, logits = eng.generate_actions(ids, px, K, int(g["n_new"]), return_logits=True)
+    assert eng.last_router_head == int(np.argmax(g["domain_logits"].sum(0)))
+    assert np.abs(aux["siglip"].view(2, 256, -1)[:, ::4].numpy() - g["siglip"]).max() < 3e-2 * np.abs(g["siglip"]).max()
+    d = aux["depth384"][:, ::4, ::4].numpy()
+    assert np.abs(d - g["depth384_s4"]).max() < 5e-3            # metric depth, metres; bf16 operands
+    assert np.abs(aux["xyz"].numpy() - g["xyz"]).max() < 5e-3
+    assert np.abs(feats[:, ::4].numpy() - g["image_features"]).max() < 2e-2 * np.abs(g["image_features"]).max()
+    assert np.array_equal(toks.numpy(), g["tokens"])
+    assert np.abs(logits.numpy() - g["logits"]).max() < 6e-2
+
+
+def test_forward_logits_api(tiny):
+    from spatialvla_b200.modeling_spatialvla import SpatialVLAForConditionalGeneration
+    cfg, px, ids, K, sd, eng = tiny
+    m = SpatialVLAForConditionalGeneration(cfg, sd, ops=RefOps())
+    out = m.forward(input_ids=ids, pixel_values=px, intrinsic=K, num_logits_to_keep=1)
+    lo = cfg["action_token_begin_idx"]
+    toks, logits = R.predict_action_ref(sd, cfg, ids, px, K, 1, force_head=m.engine.last_router_head)
+    assert out.logits.shape == (2, 1, cfg["text_config"]["vocab_size"])
+    assert (out.logits[:, 0, lo:lo + cfg["spatial_token_num"]] - logits[:, 0]).abs().max() < 6e-2
+    pa = m.predict_action({"input_ids": ids, "pixel_values": px, "intrinsic": K}, max_new_tokens=3)
+    assert pa.shape == (2, 3) and pa.dtype == torch.int64
+    with pytest.raises(ValueError):
+        m.predict_action({"input_ids": ids[:, 5:], "pixel_values": px, "intrinsic": K})
+    with pytest.raises(NotImplementedError):
+        m.predict_action({"input_ids": ids, "pixel_values": px, "intrinsic": K, "attention_mask": torch.zeros_like(ids)})
+
+
+def test_weight_packing_layouts():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 8, 10, 12, generator=g)            # NCHW
+    w = torch.randn(5, 8, 3, 3, generator=g)
+    ref = F.conv2d(x, w, padding=1)
+    wp = pack_conv3x3(w).view(5, 9, 64)[:, :, :8]
+    xp = F.pad(x, (1, 1, 1, 1))
+    acc = sum(torch.einsum("nchw,oc->nohw", xp[:, :, t // 3:t // 3 + 10, t % 3:t % 3 + 12], wp[:, t]) for t in range(9))
+    assert torch.allclose(acc, ref, atol=1e-4)
+    ops = RefOps()
+    col = torch.zeros(2 * 5 * 6, 9 * 8, dtype=torch.bfloat16)
+    ops.im2col3x3_s2(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), col, batch=2, h=10, w=12, c=8)
+    xb = x.to(torch.bfloat16).float()
+    ref2 = F.conv2d(xb, w, stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, 5)
+    assert torch.allclose(col.float() @ pack_conv3x3_im2col(w).t(), ref2, atol=1e-3)
+    wt, bt = torch.randn(8, 6, 4, 4, generator=g), torch.randn(6, generator=g)
+    wg, bg = pack_deconv(wt, bt)
+    ref3 = F.conv_transpose2d(x, wt, bt, stride=4)
+    gm = (x.permute(0, 2, 3, 1).reshape(-1, 8) @ wg.t() + bg).to(torch.bfloat16)
+    out = torch.zeros(2, 40, 48, 6, dtype=torch.bfloat16)
+    # pixel_shuffle wants c % 8 == 0 on the GPU; the torch re-statement has no such limit
+    ops.pixel_shuffle(gm, out, batch=2, h=10, w=12, c=6, f=4)
+    assert torch.allclose(out.float().permute(0, 3, 1, 2), ref3, atol=5e-2)
+
+
+def test_config_roundtrip():
+    from spatialvla_b200 import SpatialVLAConfig, get_config_dict
+    c = SpatialVLAConfig(**get_config_dict("tiny"))
+    d = c.to_engine_dict()
+    assert d["text_config"]["head_dim"] == 256 and d["vision_zoe_config"]["backbone_config"]["hidden_size"] == 128
+    assert d["text_config"]["rope_theta"] == 10000.0
+    assert c.text_config.num_image_tokens == 256
+    c2 = SpatialVLAConfig(**json.loads(json.dumps({k: v for k, v in c.to_dict().items() if k in
+                                                   ("vision_config", "text_config", "vision_zoe_config", "image_token_index",
+                                                    "action_token_begin_idx", "spatial_token_num", "use_spatial_token",
+                                                    "ego3d_patch_reso", "n_freqs", "use_vision_zoe")})))
+    assert c2.to_engine_dict()["vision_config"]["hidden_size"] == d["vision_config"]["hidden_size"]
+
+
+def test_shard_bounds():
+    from spatialvla_b200.parallel import shard_batch, shard_bounds
+    for n in (1, 7, 64, 65):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+    b = {"input_ids": torch.arange(10).view(5, 2), "pixel_values": torch.zeros(5, 3, 4, 4), "intrinsic": torch.eye(3)}
+    s = shard_batch(b, 1, 2)
+    assert s["input_ids"].shape[0] == 2 and s["intrinsic"].shape == (3, 3)

@@ -1,0 +1,68 @@
+"""CPU: the oracle restatements (oracle/tokenizer_ref.py, oracle/model_ref.py) against the golden vectors minted from
+the live reference (oracle/gen_golden.py)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import model_ref as R
+from oracle import tokenizer_ref as T
+from spatialvla_b200.weights import synth_state_dict
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+NUM_BINS = {"translation": {"theta_bins": 16, "phi_bins": 32, "r_bins": 8},
+            "rotation": {"roll_bins": 16, "pitch_bins": 16, "yaw_bins": 16}, "gripper": 2, "total": 8194}
+
+
+def _policy(g):
+    return {"translation": {k: g[f"edge_{k}"] for k in ("theta_bins", "phi_bins", "r_bins")},
+            "rotation": {k: g[f"edge_{k}"] for k in ("roll_bins", "pitch_bins", "yaw_bins")}}
+
+
+def test_tokenizer_restatement_bit_exact():
+    for name in ("gauss", "uniform"):
+        g = np.load(os.path.join(GOLD, f"tokenizer_{name}.npz"))
+        pol = _policy(g)
+        ids = T.encode(g["actions"], pol, NUM_BINS)
+        assert np.array_equal(ids, g["local_ids"]), name
+        dec = T.decode(g["decode_ids"] - int(g["begin"]), pol, NUM_BINS)
+        assert np.array_equal(dec, g["decode_actions"]), name
+        assert np.array_equal(T.decode(g["oob_ids"] - int(g["begin"]), pol, NUM_BINS), g["oob_actions"])
+
+
+def test_bin_policy_restatement():
+    import json
+    gs = {"x": {"mu": 0.027242150055384978, "sigma": 0.3594921286169892}, "y": {"mu": 0.02508918994616194, "sigma": 0.3583033723406619},
+          "z": {"mu": -0.10367949030112077, "sigma": 0.3891227767239212}, "theta": {"mu": 1.8739714125737532, "sigma": 0.779843323370511},
+          "phi": {"mu": 0.08796911369129973, "sigma": 1.6921243756107702}, "r": {"mu": 0.5480865478719801, "sigma": 0.34749763559260854},
+          "roll": {"mu": -0.016498618557435858, "sigma": 0.3804899850542066}, "pitch": {"mu": 0.028462961721089787, "sigma": 0.29912182728829634},
+          "yaw": {"mu": -0.004913600039079129, "sigma": 0.39022979006490277}}     # scripts/gs_spatialvla_plus.json
+    g = np.load(os.path.join(GOLD, "tokenizer_gauss.npz"))
+    pol = T.get_bin_policy(NUM_BINS, gs, min_sigma=float(g["min_sigma"]))
+    for bt in pol.values():
+        for k, v in bt.items():
+            assert np.array_equal(np.asarray(v), g[f"edge_{k}"]), k
+    u = np.load(os.path.join(GOLD, "tokenizer_uniform.npz"))
+    pol = T.get_bin_policy(NUM_BINS, None)
+    for bt in pol.values():
+        for k, v in bt.items():
+            assert np.array_equal(np.asarray(v), u[f"edge_{k}"]), k
+
+
+def test_model_restatement_matches_reference_golden():
+    from oracle.gen_golden import tiny_inputs
+    g = np.load(os.path.join(GOLD, "tiny_model.npz"))
+    cfg, px_u8, ids, K = tiny_inputs()
+    assert np.array_equal(px_u8.numpy(), g["pixel_u8"]) and np.array_equal(ids.numpy(), g["input_ids"])
+    px = px_u8.float() / 255.0
+    sd = synth_state_dict(cfg, seed=0)
+    n_new = int(g["n_new"])
+    toks, logits, aux = R.predict_action_ref(sd, cfg, ids, px, K, n_new, return_aux=True)
+    assert np.array_equal(toks.numpy(), g["tokens"])
+    assert np.abs(logits.numpy() - g["logits"]).max() < 2e-5
+    assert np.abs(aux["siglip"][:, ::4].numpy() - g["siglip"]).max() < 2e-5
+    assert np.abs(aux["depth384"][:, ::4, ::4].numpy() - g["depth384_s4"]).max() < 2e-5
+    assert np.abs(aux["xyz"].numpy() - g["xyz"]).max() < 2e-5
+    assert np.abs(aux["pos3d"][:, ::4].numpy() - g["pos3d"]).max() < 2e-5
+    assert np.abs(aux["image_features"][:, ::4].numpy() - g["image_features"]).max() < 2e-5
+    assert np.abs(aux["zoe"]["domain_logits"].numpy() - g["domain_logits"]).max() < 2e-5

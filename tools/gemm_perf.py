@@ -1,0 +1,64 @@
+"""GEMM / conv / attention micro-benchmark on the shapes of the 4B-224 path at batch 64 (CUDA events, L2 flushed)."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from spatialvla_b200.ops import CudaOps
+
+dev = "cuda:0"
+ops = CudaOps(dev)
+BF16, F32 = torch.bfloat16, torch.float32
+flush = torch.empty(256 * 2**20, dtype=torch.uint8, device=dev)
+
+def timeit(fn, iters=5):
+    fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    return min(ts)
+
+rows = []
+shapes = [("siglip_qkv", 16384, 3456, 1152), ("siglip_out", 16384, 1152, 1152), ("siglip_fc1", 16384, 4304, 1152), ("siglip_fc2", 16384, 1152, 4304),
+          ("beit_qkv", 36928, 3072, 1024), ("beit_out", 36928, 1024, 1024), ("beit_fc1", 36928, 4096, 1024), ("beit_fc2", 36928, 1024, 4096),
+          ("gemma_qkv", 17792, 4096, 2304), ("gemma_o", 17792, 2304, 2048), ("gemma_gateup", 17792, 18432, 2304), ("gemma_down", 17792, 2304, 9216),
+          ("dec_qkv", 64, 4096, 2304), ("dec_o", 64, 2304, 2048), ("dec_gateup", 64, 18432, 2304), ("dec_down", 64, 2304, 9216), ("dec_head", 64, 8194, 2304),
+          ("cublas_ref_8192", 8192, 8192, 8192)]
+only = sys.argv[1] if len(sys.argv) > 1 else ""
+for name, M, N, K in shapes:
+    if only and only not in name: continue
+    a = torch.randn(M, K, device=dev).to(BF16); w = torch.randn(N, K, device=dev).to(BF16)
+    out = torch.empty(M, N, device=dev, dtype=BF16)
+    for bn in ([0] if M <= 64 else [128, 256]):
+        ms = timeit(lambda: ops.gemm(a, w, out_bf16=out, block_n=bn))
+        tf = 2.0 * M * N * K / ms / 1e9
+        gbs = (M * K + N * K + M * N) * 2 / ms / 1e6
+        rows.append({"name": name, "M": M, "N": N, "K": K, "bn": bn, "ms": round(ms, 4), "tflops": round(tf, 1), "gbs": round(gbs, 1)})
+        print(rows[-1], flush=True)
+    if name.startswith("cublas") or name in ("gemma_gateup", "beit_fc1"):
+        ms = timeit(lambda: torch.matmul(a, w.t()))
+        print({"name": name + "_torch_matmul", "ms": round(ms, 4), "tflops": round(2.0 * M * N * K / ms / 1e9, 1)}, flush=True)
+# conv
+for name, (nb, h, w_, c), N in [("fusion_conv_96", (64, 96, 96, 256), 256), ("fusion_conv_48", (64, 48, 48, 256), 256), ("rel_conv1_192", (64, 192, 192, 256), 128), ("rel_conv2_384", (64, 384, 384, 128), 32)]:
+    if only and only not in name: continue
+    x = torch.randn(nb, h, w_, c, device=dev).to(BF16); wt = torch.randn(N, 9 * c, device=dev).to(BF16)
+    out = torch.empty(nb * h * w_, N, device=dev, dtype=BF16)
+    ms = timeit(lambda: ops.gemm(x, wt, conv=(nb, h, w_, c), out_bf16=out), iters=3)
+    print({"name": name, "ms": round(ms, 3), "tflops": round(2.0 * nb * h * w_ * N * 9 * c / ms / 1e9, 1)}, flush=True)
+# attention
+for name, B, hq, hkv, S, d, kw in [("attn_siglip", 64, 16, 16, 256, 72, {}), ("attn_beit", 64, 16, 16, 577, 64, {"relpos": 24}), ("attn_gemma", 64, 8, 4, 278, 256, {"softcap": 50.0})]:
+    if only and only not in name: continue
+    D = hq * d
+    if hq == hkv:
+        qkv = torch.randn(B * S, 3 * D, device=dev).to(BF16); out = torch.empty(B * S, D, device=dev, dtype=BF16)
+        tab = torch.randn((2 * 24 - 1) ** 2 + 3, hq, device=dev) if "relpos" in kw else None
+        st = (S * 3 * D, 3 * D)
+        fn = lambda: ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], out, batch=B, hq=hq, hkv=hkv, sq=S, sk=S, d=d, q_strides=st, k_strides=st, v_strides=st, o_strides=(S * D, D), scale=d ** -0.5, relpos_table=tab, relpos_win=24 if tab is not None else 0)
+    else:
+        q = torch.randn(B * S, D, device=dev).to(BF16); kc = torch.randn(B, 290, hkv, d, device=dev).to(BF16); vc = torch.randn_like(kc); out = torch.empty_like(q)
+        kvs = (290 * hkv * d, hkv * d)
+        fn = lambda: ops.attention(q, kc, vc, out, batch=B, hq=hq, hkv=hkv, sq=S, sk=S, d=d, q_strides=(S * D, D), k_strides=kvs, v_strides=kvs, o_strides=(S * D, D), scale=1 / 16, softcap=50.0)
+    ms = timeit(fn)
+    print({"name": name, "ms": round(ms, 3), "tflops": round(4.0 * B * hq * S * S * d / ms / 1e9, 1)}, flush=True)

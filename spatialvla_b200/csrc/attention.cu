@@ -14,7 +14,7 @@
 
 namespace {
 
-constexpr int kBQ = 64, kBKV = 64, kAttnThreads = 128;
+constexpr int kBQ = 128, kBKV = 64, kAttnThreads = 256;   // 8 warps x 16 query rows share each K/V tile
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
@@ -38,6 +38,21 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// tanh for soft-capping: |u| is small (scores / 50), so an odd degree-9 Taylor polynomial is exact to fp32
+// rounding below 0.35 and the libm path handles the rare large argument.
+__device__ __forceinline__ float tanh_small(float u) {
+  const float u2 = u * u;
+  if (u2 < 0.1225f) {
+    float p = 62.f / 2835.f;
+    p = fmaf(p, u2, -17.f / 315.f);
+    p = fmaf(p, u2, 2.f / 15.f);
+    p = fmaf(p, u2, -1.f / 3.f);
+    p = fmaf(p, u2, 1.f);
+    return u * p;
+  }
+  return tanhf(u);
+}
+
 struct AttnP {
   const __nv_bfloat16 *q, *k, *v;
   __nv_bfloat16* out;
@@ -49,12 +64,12 @@ struct AttnP {
   int win;
 };
 
-// Loads `rows` x d (bf16) rows [r0, r0+64) of a [s, ...] strided matrix into smem [64][DP+8]; rows >= s are zeroed.
-template <int DP>
+// Loads rows [r0, r0+ROWS) x d (bf16) of a [s, ...] strided matrix into smem [ROWS][DP+8]; rows >= s are zeroed.
+template <int DP, int ROWS>
 __device__ __forceinline__ void load_tile(__nv_bfloat16* sm, const __nv_bfloat16* g, long long row_stride, int r0, int s, int d) {
   constexpr int LD = DP + 8;
   const int chunks = d >> 3;
-  for (int i = threadIdx.x; i < 64 * chunks; i += kAttnThreads) {
+  for (int i = threadIdx.x; i < ROWS * chunks; i += kAttnThreads) {
     const int r = i / chunks, c = i - r * chunks;
     const bool ok = (r0 + r) < s;
     const __nv_bfloat16* src = g + static_cast<long long>(ok ? (r0 + r) : 0) * row_stride + c * 8;
@@ -70,9 +85,10 @@ svla_flash_attn_kernel(const AttnP p) {
   constexpr int NT = DP / 8;      // n-tiles of the output
   extern __shared__ __align__(16) uint8_t smem_attn[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
-  __nv_bfloat16* sK = sQ + 64 * LD;            // 2 buffers
+  __nv_bfloat16* sK = sQ + kBQ * LD;           // 2 buffers
   __nv_bfloat16* sV = sK + 2 * 64 * LD;        // 2 buffers
   float* sTab = reinterpret_cast<float*>(sV + 2 * 64 * LD);
+  int* sKterm = reinterpret_cast<int*>(sTab + (p.relpos ? (2 * p.win - 1) * (2 * p.win - 1) + 3 : 0));   // [64]
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kBQ;
   const int hk = h / (p.hq / p.hkv);
@@ -85,10 +101,9 @@ svla_flash_attn_kernel(const AttnP p) {
   // zero the padding columns [d, DP) once (cp.async never touches them)
   if (p.d < DP) {
     const int padc = DP - p.d;
-    for (int i = threadIdx.x; i < 5 * 64 * padc; i += kAttnThreads) {
-      const int buf = i / (64 * padc), rem = i - buf * 64 * padc;
-      const int r = rem / padc, c = p.d + rem % padc;
-      sQ[(buf * 64 + r) * LD + c] = __float2bfloat16(0.f);
+    for (int i = threadIdx.x; i < (kBQ + 4 * 64) * padc; i += kAttnThreads) {
+      const int r = i / padc, c = p.d + i % padc;
+      sQ[r * LD + c] = __float2bfloat16(0.f);      // sQ, sK[2], sV[2] are contiguous
     }
   }
   int nrel = 0;
@@ -98,9 +113,9 @@ svla_flash_attn_kernel(const AttnP p) {
   }
 
   const int n_kv_tiles = (p.sk + kBKV - 1) / kBKV;
-  load_tile<DP>(sQ, qg, p.q_ss, q0, p.sq, p.d);
-  load_tile<DP>(sK, kg, p.k_ss, 0, p.sk, p.d);
-  load_tile<DP>(sV, vg, p.v_ss, 0, p.sk, p.d);
+  load_tile<DP, kBQ>(sQ, qg, p.q_ss, q0, p.sq, p.d);
+  load_tile<DP, 64>(sK, kg, p.k_ss, 0, p.sk, p.d);
+  load_tile<DP, 64>(sV, vg, p.v_ss, 0, p.sk, p.d);
   cp_async_commit();
 
   float o[NT][4];
@@ -110,16 +125,31 @@ svla_flash_attn_kernel(const AttnP p) {
   const int qi0 = q0 + warp * 16 + g;      // this thread's rows: qi0 and qi0 + 8
   const int causal_off = p.sk - p.sq;
   constexpr float kLog2e = 1.4426950408889634f;
+  // BEiT relative-position index = qbase(query) - kterm(key) for patch tokens; CLS row/column are special-cased
+  int qbase[2] = {0, 0};
+  const int w2 = 2 * p.win - 1;
+  if (p.relpos) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int qi = qi0 + 8 * r;
+      if (qi >= 1) qbase[r] = ((qi - 1) / p.win + p.win - 1) * w2 + (qi - 1) % p.win + p.win - 1;
+    }
+  }
+  const float inv_cap = p.softcap > 0.f ? 1.f / p.softcap : 0.f;
 
   for (int jt = 0; jt < n_kv_tiles; ++jt) {
     const int buf = jt & 1;
     if (jt + 1 < n_kv_tiles) {
-      load_tile<DP>(sK + (buf ^ 1) * 64 * LD, kg, p.k_ss, (jt + 1) * kBKV, p.sk, p.d);
-      load_tile<DP>(sV + (buf ^ 1) * 64 * LD, vg, p.v_ss, (jt + 1) * kBKV, p.sk, p.d);
+      load_tile<DP, 64>(sK + (buf ^ 1) * 64 * LD, kg, p.k_ss, (jt + 1) * kBKV, p.sk, p.d);
+      load_tile<DP, 64>(sV + (buf ^ 1) * 64 * LD, vg, p.v_ss, (jt + 1) * kBKV, p.sk, p.d);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
+    }
+    if (p.relpos && threadIdx.x < 64) {
+      const int kj = jt * kBKV + threadIdx.x;
+      sKterm[threadIdx.x] = kj >= 1 ? ((kj - 1) / p.win) * w2 + (kj - 1) % p.win : 0;
     }
     __syncthreads();
     const __nv_bfloat16* cK = sK + buf * 64 * LD;
@@ -152,15 +182,11 @@ svla_flash_attn_kernel(const AttnP p) {
         const int qi = qi0 + r * 8;
         const int kj = jt * kBKV + nt * 8 + 2 * t + (e & 1);
         float x = s[nt][e] * p.scale;
-        if (p.softcap > 0.f) x = p.softcap * tanhf(x / p.softcap);
+        if (p.softcap > 0.f) x = p.softcap * tanh_small(x * inv_cap);
         if (p.relpos && qi < p.sq && kj < p.sk) {
-          int idx;
+          int idx = qbase[r] - sKterm[nt * 8 + 2 * t + (e & 1)];
+          if (kj == 0) idx = nrel - 2;
           if (qi == 0) idx = (kj == 0) ? nrel - 1 : nrel - 3;
-          else if (kj == 0) idx = nrel - 2;
-          else {
-            const int qy = (qi - 1) / p.win, qx = (qi - 1) % p.win, ky = (kj - 1) / p.win, kx = (kj - 1) % p.win;
-            idx = (qy - ky + p.win - 1) * (2 * p.win - 1) + (qx - kx + p.win - 1);
-          }
           x += sTab[idx];
         }
         const bool masked = (kj >= p.sk) || (p.causal && kj > qi + causal_off);
@@ -240,7 +266,7 @@ template <int DP>
 int launch_attn(const AttnP& p, int batch, cudaStream_t st) {
   constexpr int LD = DP + 8;
   int nrel = p.relpos ? (2 * p.win - 1) * (2 * p.win - 1) + 3 : 0;
-  const size_t smem = static_cast<size_t>(5) * 64 * LD * 2 + static_cast<size_t>(nrel) * 4 + 16;
+  const size_t smem = static_cast<size_t>(kBQ + 4 * 64) * LD * 2 + static_cast<size_t>(nrel) * 4 + 64 * 4 + 16;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(svla_flash_attn_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -327,21 +353,46 @@ svla_decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16
     for (int j = threadIdx.x; j < ctx; j += kDecThreads) sc[gi * ctx + j] *= inv;
     __syncthreads();
   }
-  // out[d] = sum_j p[j] V[j][d] : thread <-> dim (D == kDecThreads), probabilities rounded to bf16 like the prefill path
-  float acc[kMaxGroup];
+  // out[d] = sum_j p[j] V[j][d]: one warp per key (16-byte V loads, lane <-> 8 dims), partial sums reduced over
+  // the 8 warps through shared memory. Probabilities are rounded to bf16 like the prefill path.
+  float acc[kMaxGroup][PER];
 #pragma unroll
-  for (int gi = 0; gi < kMaxGroup; ++gi) acc[gi] = 0.f;
-  for (int d0 = threadIdx.x; d0 < D; d0 += kDecThreads) {
-    for (int j = 0; j < ctx; ++j) {
-      const float vv = __bfloat162float(vb[j * row_stride + d0]);
+  for (int gi = 0; gi < kMaxGroup; ++gi)
 #pragma unroll
-      for (int gi = 0; gi < kMaxGroup; ++gi)
-        if (gi < grp) acc[gi] += __bfloat162float(__float2bfloat16(sc[gi * ctx + j])) * vv;
+    for (int e = 0; e < PER; ++e) acc[gi][e] = 0.f;
+  for (int j = warp; j < ctx; j += NW) {
+    float vv[PER];
+    const __nv_bfloat16* vr = vb + j * row_stride + lane * PER;
+#pragma unroll
+    for (int e = 0; e < PER; e += 8) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(vr + e));
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        vv[e + 2 * u] = bf16_bits_to_float(w[u] & 0xFFFFu);
+        vv[e + 2 * u + 1] = bf16_bits_to_float(w[u] >> 16);
+      }
     }
-    for (int gi = 0; gi < grp; ++gi) {
-      out[(static_cast<long long>(b) * hq + hk * grp + gi) * D + d0] = __float2bfloat16(acc[gi]);
-      acc[gi] = 0.f;
+#pragma unroll
+    for (int gi = 0; gi < kMaxGroup; ++gi) {
+      if (gi < grp) {
+        const float pj = __bfloat162float(__float2bfloat16(sc[gi * ctx + j]));
+#pragma unroll
+        for (int e = 0; e < PER; ++e) acc[gi][e] += pj * vv[e];
+      }
     }
+  }
+  __syncthreads();                 // scores no longer needed: reuse sq/sc region? keep separate partial buffer
+  float* part = red + 64;          // [NW][grp][D]
+  for (int gi = 0; gi < grp; ++gi)
+#pragma unroll
+    for (int e = 0; e < PER; ++e) part[(warp * grp + gi) * D + lane * PER + e] = acc[gi][e];
+  __syncthreads();
+  for (int i = threadIdx.x; i < grp * D; i += kDecThreads) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) t += part[w * grp * D + i];
+    out[(static_cast<long long>(b) * hq + hk * grp) * D + i] = __float2bfloat16(t);
   }
 }
 
@@ -377,7 +428,7 @@ extern "C" int svla_decode_attention(const void* q, const void* kcache, const vo
   SVLA_REQUIRE(hkv > 0 && hq % hkv == 0 && hq / hkv <= kMaxGroup, "svla_decode_attention: bad GQA group");
   SVLA_REQUIRE(ctx > 0 && ctx <= smax, "svla_decode_attention: ctx %d out of range", ctx);
   const int grp = hq / hkv;
-  const size_t smem = (static_cast<size_t>(grp) * d + static_cast<size_t>(grp) * ctx + 64) * sizeof(float);
+  const size_t smem = (static_cast<size_t>(grp) * d + static_cast<size_t>(grp) * ctx + 64 + static_cast<size_t>(kDecThreads / 32) * grp * d) * sizeof(float);
   SVLA_REQUIRE(smem <= 200 * 1024, "svla_decode_attention: context too long for shared memory");
   static size_t configured = 48 * 1024;
   if (smem > configured) {

@@ -30,7 +30,8 @@ template <int BN> struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 4 * 32 * 36 * 4;     // per-epilogue-warp fp32 transpose tile
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes;
 };
 
 struct EpiParams {
@@ -156,7 +157,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // ------------------------------------------------------------------------------------------ fused epilogue
 __device__ __forceinline__ float apply_act(float v, int act, float p) {
   switch (act) {
-    case SVLA_ACT_GELU_TANH: return gelu_tanh_f(v);
+    case SVLA_ACT_GELU_TANH: return gelu_tanh_fast(v);
     case SVLA_ACT_GELU_ERF: return gelu_erf_f(v);
     case SVLA_ACT_RELU: return fmaxf(v, 0.f);
     case SVLA_ACT_SOFTCAP: return p * tanhf(v / p);
@@ -165,112 +166,135 @@ __device__ __forceinline__ float apply_act(float v, int act, float p) {
   }
 }
 
-// One output row, 32 consecutive accumulator columns starting at n0 (global column). `grow` = global output row.
-__device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, const float (&acc)[32], long long grow, long long n0) {
+// Epilogue of one 32-row x 32-column accumulator chunk owned by one warp (lane = tile row q*32 + lane).
+// Phase 1 (row owner): value = act(alpha*acc + bias) * colscale (or the GeGLU pair product) -> per-warp fp32
+// staging tile in shared memory (row stride 36 floats: conflict-free 128-bit accesses).
+// Phase 2 (coalesced): 8 (fp32) / 4 (GeGLU) lanes cover one row's 4-column groups, so every warp-wide global
+// access touches whole 32-byte sectors of 4 / 8 consecutive rows; residual loads, the fp32 read-modify-write and
+// the bf16 / relu stores all happen here.
+constexpr int kStageLd = 36;
+
+template <typename RowFn>
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, const float (&acc)[32], float* stage, int lane,
+                                               long long n0, RowFn row_of) {
   const bool geglu = (ep.flags & SVLA_GEMM_GEGLU) != 0;
   const bool accum = (ep.flags & SVLA_GEMM_ACCUM_F32) != 0;
+  // NOTE: the activation switch is hoisted out of the element loop on purpose -- a per-element switch inlines every
+  // libm body 32 times (~100 KB of SASS) and turns the epilogue into an instruction-cache-miss-bound loop.
   float v[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const long long n = n0 + j;
-    float x = acc[j] * ep.alpha;
-    if (n < ep.n) {
-      if (ep.bias) x += __ldg(ep.bias + n);
-      if (!geglu) x = apply_act(x, ep.act, ep.act_param);
-      if (ep.colscale) x *= __ldg(ep.colscale + n);
-    }
-    v[j] = x;
+  for (int j = 0; j < 32; ++j) v[j] = acc[j] * ep.alpha;
+  if (ep.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n0 + j < ep.n) v[j] += __ldg(ep.bias + n0 + j);
   }
+  if (!geglu) {
+    switch (ep.act) {
+      case SVLA_ACT_GELU_TANH:
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
+        break;
+      case SVLA_ACT_GELU_ERF:
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+        break;
+      case SVLA_ACT_RELU:
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        break;
+      case SVLA_ACT_SOFTCAP: {
+        const float inv = 1.f / ep.act_param;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = ep.act_param * tanhf(v[j] * inv);
+        break;
+      }
+      case SVLA_ACT_SOFTPLUS:
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = softplus_f(v[j]);
+        break;
+      default: break;
+    }
+  }
+  if (ep.colscale) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n0 + j < ep.n) v[j] *= __ldg(ep.colscale + n0 + j);
+  }
+  float4* srow = reinterpret_cast<float4*>(stage + lane * kStageLd);
+  int groups;             // 4-column groups per staged row
+  long long col0, ncols;  // first output column of this chunk / number of valid output columns overall
   if (geglu) {
-    // columns (2j, 2j+1) = (gate_j, up_j): out[:, n0/2 + j] = gelu_tanh(gate) * up
-    const long long o0 = n0 >> 1;
-    const long long on = ep.n >> 1;
-    __nv_bfloat16* dst = ep.out_bf16 + grow * ep.ldo + o0;
-    if (o0 + 16 <= on && (ep.ldo & 7) == 0) {
-      uint32_t pk[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        pk[j] = pack_bf16x2(gelu_tanh_f(v[4 * j]) * v[4 * j + 1], gelu_tanh_f(v[4 * j + 2]) * v[4 * j + 3]);
-      uint4* d4 = reinterpret_cast<uint4*>(dst);
-      d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-    } else {
-      for (int j = 0; j < 16; ++j)
-        if (o0 + j < on) dst[j] = __float2bfloat16(gelu_tanh_f(v[2 * j]) * v[2 * j + 1]);
-    }
-    return;
-  }
-  const long long off = grow * ep.ldo + n0;
-  const long long off_r32 = (ep.res_mod > 0 ? grow % ep.res_mod : grow) * ep.ldo + n0;
-  const bool full = (n0 + 32 <= ep.n) && ((ep.ldo & 7) == 0);
-  if (full) {
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      const __nv_bfloat16* rp = which == 0 ? ep.res_bf16 : ep.res2_bf16;
-      if (rp == nullptr) continue;
-      const uint4* r4 = reinterpret_cast<const uint4*>(rp + off);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint4 t = __ldg(r4 + q);
-        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          v[q * 8 + 2 * e] += bf16_bits_to_float(w[e] & 0xFFFFu);
-          v[q * 8 + 2 * e + 1] += bf16_bits_to_float(w[e] >> 16);
-        }
-      }
-    }
-    if (ep.res_f32) {
-      const float4* r4 = reinterpret_cast<const float4*>(ep.res_f32 + off_r32);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 t = __ldg(r4 + q);
-        v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
-      }
-    }
-    if (ep.out_f32) {
-      float4* o4 = reinterpret_cast<float4*>(ep.out_f32 + off);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (accum) {
-          const float4 t = o4[q];
-          v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
-        }
-        o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      }
-    }
-    if (ep.out_bf16) {
-      uint4* o4 = reinterpret_cast<uint4*>(ep.out_bf16 + off);
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        o4[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                           pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-    }
-    if (ep.out_relu) {
-      uint4* o4 = reinterpret_cast<uint4*>(ep.out_relu + off);
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        o4[q] = make_uint4(pack_bf16x2(fmaxf(v[8 * q], 0.f), fmaxf(v[8 * q + 1], 0.f)),
-                           pack_bf16x2(fmaxf(v[8 * q + 2], 0.f), fmaxf(v[8 * q + 3], 0.f)),
-                           pack_bf16x2(fmaxf(v[8 * q + 4], 0.f), fmaxf(v[8 * q + 5], 0.f)),
-                           pack_bf16x2(fmaxf(v[8 * q + 6], 0.f), fmaxf(v[8 * q + 7], 0.f)));
-    }
+    for (int j = 0; j < 4; ++j)
+      srow[j] = make_float4(gelu_tanh_fast(v[8 * j]) * v[8 * j + 1], gelu_tanh_fast(v[8 * j + 2]) * v[8 * j + 3],
+                            gelu_tanh_fast(v[8 * j + 4]) * v[8 * j + 5], gelu_tanh_fast(v[8 * j + 6]) * v[8 * j + 7]);
+    groups = 4; col0 = n0 >> 1; ncols = ep.n >> 1;
   } else {
-    for (int j = 0; j < 32; ++j) {
-      const long long n = n0 + j;
-      if (n >= ep.n) break;
-      float x = v[j];
-      if (ep.res_bf16) x += __bfloat162float(ep.res_bf16[off + j]);
-      if (ep.res2_bf16) x += __bfloat162float(ep.res2_bf16[off + j]);
-      if (ep.res_f32) x += ep.res_f32[off_r32 + j];
-      if (ep.out_f32) {
-        if (accum) x += ep.out_f32[off + j];
-        ep.out_f32[off + j] = x;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    groups = 8; col0 = n0; ncols = ep.n;
+  }
+  __syncwarp();
+  const int rows_per_pass = 32 / groups;
+  const int cg = lane % groups;
+  const long long col = col0 + 4 * cg;
+  const bool vec_ok = ((ep.ldo & 3) == 0) && (col + 4 <= ncols);
+  if (col < ncols) {
+#pragma unroll 1
+    for (int pass = 0; pass < groups; ++pass) {
+      const int r = pass * rows_per_pass + lane / groups;
+      long long grow;
+      if (!row_of(r, grow)) continue;
+      const float4 sv = *reinterpret_cast<const float4*>(stage + r * kStageLd + 4 * cg);
+      float x[4] = {sv.x, sv.y, sv.z, sv.w};
+      const long long off = grow * ep.ldo + col;
+      const long long off_r32 = (ep.res_mod > 0 ? grow % ep.res_mod : grow) * ep.ldo + col;
+      if (vec_ok) {
+        if (ep.res_bf16) {
+          const uint2 t = __ldg(reinterpret_cast<const uint2*>(ep.res_bf16 + off));
+          x[0] += bf16_bits_to_float(t.x & 0xFFFFu); x[1] += bf16_bits_to_float(t.x >> 16);
+          x[2] += bf16_bits_to_float(t.y & 0xFFFFu); x[3] += bf16_bits_to_float(t.y >> 16);
+        }
+        if (ep.res2_bf16) {
+          const uint2 t = __ldg(reinterpret_cast<const uint2*>(ep.res2_bf16 + off));
+          x[0] += bf16_bits_to_float(t.x & 0xFFFFu); x[1] += bf16_bits_to_float(t.x >> 16);
+          x[2] += bf16_bits_to_float(t.y & 0xFFFFu); x[3] += bf16_bits_to_float(t.y >> 16);
+        }
+        if (ep.res_f32) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(ep.res_f32 + off_r32));
+          x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w;
+        }
+        if (ep.out_f32) {
+          float4* o4 = reinterpret_cast<float4*>(ep.out_f32 + off);
+          if (accum) {
+            const float4 t = *o4;
+            x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w;
+          }
+          *o4 = make_float4(x[0], x[1], x[2], x[3]);
+        }
+        if (ep.out_bf16)
+          *reinterpret_cast<uint2*>(ep.out_bf16 + off) = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
+        if (ep.out_relu)
+          *reinterpret_cast<uint2*>(ep.out_relu + off) =
+              make_uint2(pack_bf16x2(fmaxf(x[0], 0.f), fmaxf(x[1], 0.f)), pack_bf16x2(fmaxf(x[2], 0.f), fmaxf(x[3], 0.f)));
+      } else {
+        for (int e = 0; e < 4 && col + e < ncols; ++e) {
+          float y = x[e];
+          if (ep.res_bf16) y += __bfloat162float(ep.res_bf16[off + e]);
+          if (ep.res2_bf16) y += __bfloat162float(ep.res2_bf16[off + e]);
+          if (ep.res_f32) y += ep.res_f32[off_r32 + e];
+          if (ep.out_f32) {
+            if (accum) y += ep.out_f32[off + e];
+            ep.out_f32[off + e] = y;
+          }
+          if (ep.out_bf16) ep.out_bf16[off + e] = __float2bfloat16(y);
+          if (ep.out_relu) ep.out_relu[off + e] = __float2bfloat16(fmaxf(y, 0.f));
+        }
       }
-      if (ep.out_bf16) ep.out_bf16[off + j] = __float2bfloat16(x);
-      if (ep.out_relu) ep.out_relu[off + j] = __float2bfloat16(fmaxf(x, 0.f));
     }
   }
+  __syncwarp();
 }
 
 // Global output row of tile row r (and validity) in linear / conv mode.
@@ -307,6 +331,7 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   uint64_t* tmem_full = bars + 2 * C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* staging = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -403,8 +428,8 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      long long grow;
-      const bool row_ok = tile_row_to_global(ep, conv != 0, m_tile, q * 32 + lane, grow);
+      float* stage = staging + (warp - 2) * 32 * kStageLd;
+      auto row_of = [&](int r, long long& grow) { return tile_row_to_global(ep, conv != 0, m_tile, q * 32 + r, grow); };
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -412,12 +437,10 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         if (n0 >= ep.n) break;                 // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
-        if (row_ok) {
-          float acc[32];
+        float acc[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
-          epilogue_chunk(ep, acc, grow, n0);
-        }
+        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+        epilogue_chunk(ep, acc, stage, lane, n0, row_of);
       }
       tc_fence_before();
       __syncwarp();
@@ -549,9 +572,22 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& ep,
 }
 
 int pick_block_n(long long m_tiles, long long n) {
+  const int sms = svla_num_sms();
+  if (m_tiles == 1) {
+    // Skinny (decode, M <= 128): weight-streaming, HBM-bound. Spread N over as many SMs as possible; the per-k-block
+    // cost of a CTA is the 16 KB A tile (L2-hot) plus BN*128 B of weights.
+    long long best_cost = -1;
+    int best = 32;
+    for (int bn : {32, 64, 128, 256}) {
+      if (bn > 32 && n <= bn / 2) continue;
+      const long long tiles = (n + bn - 1) / bn;
+      const long long cost = ((tiles + sms - 1) / sms) * (128 + bn);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+    }
+    return best;
+  }
   if (n <= 32) return 32;
   if (n <= 64) return 64;
-  const int sms = svla_num_sms();
   long long best_cost = -1;
   int best = 128;
   for (int bn : {256, 128}) {

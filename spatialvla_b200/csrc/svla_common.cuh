@@ -73,5 +73,15 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   return 0.5f * x * (1.f + tanhf(k0 * (x + k1 * x * x * x)));
 }
+// MUFU tanh (max rel. error 2^-11): below the bf16 rounding of every consumer it is used for
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * x * (1.f + tanh_approx(k0 * (x + k1 * x * x * x)));
+}
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }

@@ -386,20 +386,26 @@ class SpatialVLAEngine:
         c1 = self._lin(cls, mh["cls1_w"], B, bias=mh["cls1_b"], act=ACT_RELU)
         return self._lin(c1, mh["cls2_w"], B, F32, bias=mh["cls2_b"])
 
-    def zoe_metric_head(self, outconv, bottleneck, fused_list, B):
-        ops, mh, z = self.ops, self.mh, self.z
+    def zoe_router_stage(self, bottleneck, B):
+        """bottleneck conv + patch-transformer router -> (xb bf16 [B*n, C], domain logits fp32 [B, 2])"""
         bneck, rb = bottleneck
         n = rb * rb
-        E = z["bin_embedding_dim"]
-        xb = self._lin(bneck, mh["conv2_w"], B * n, bias=mh["conv2_b"])
-        dlog = self.zoe_router(xb, B, n)
+        xb = self._lin(bneck, self.mh["conv2_w"], B * n, bias=self.mh["conv2_b"])
+        return xb, self.zoe_router(xb, B, n)
+
+    def pick_head(self, dlog):
+        """Batch-level vote exactly as HF (:1059-1067); one tiny D2H read like the reference's `.item()`."""
         self.last_domain_logits = dlog
-        if self.force_head is not None:
-            head = int(self.force_head)
-        else:
-            # batch-level vote exactly as HF (:1059-1067); one tiny D2H sync like the reference's `.item()`
-            head = int(torch.argmax(dlog.sum(0)).item())
+        head = int(self.force_head) if self.force_head is not None else int(torch.argmax(dlog.sum(0)).item())
         self.last_router_head = head
+        return head
+
+    def zoe_bins_stage(self, head, xb, outconv, bottleneck, fused_list, B):
+        """Seed bins, 4 attractor stages and the conditional log-binomial tail of the chosen metric head."""
+        ops, mh, z = self.ops, self.mh, self.z
+        rb = bottleneck[1]
+        n = rb * rb
+        E = z["bin_embedding_dim"]
         hd = mh["heads"][head]
         nbins = hd["conf"]["n_bins"]
         s1 = self._lin(xb, hd["sr1_w"], B * n, bias=hd["sr1_b"], act=ACT_RELU)
@@ -428,38 +434,60 @@ class SpatialVLAEngine:
                            nh=t.shape[1], nbins=nbins, min_temp=z["min_temp"], max_temp=z["max_temp"])
         return depth
 
-    def zoedepth(self, px):
-        """px fp32 [B,3,224,224] in [0,1] -> metric depth fp32 [B,384,384] (process_zoe fused into the patchify)"""
+    def zoe_trunk(self, px):
+        """Everything of ZoeDepth up to the router decision (stage A): BEiT, neck, relative head, router logits."""
         B = px.shape[0]
         hs, win = self.beit(px)
         fused_list, bottleneck = self.zoe_neck(hs, win, B)
         outconv = self.zoe_relative_head(fused_list[-1], B)
-        return self.zoe_metric_head(outconv, bottleneck, fused_list, B)
+        xb, dlog = self.zoe_router_stage(bottleneck, B)
+        return {"fused": fused_list, "bottleneck": bottleneck, "outconv": outconv, "xb": xb, "dlog": dlog}
+
+    def zoedepth(self, px):
+        """px fp32 [B,3,224,224] in [0,1] -> metric depth fp32 [B,384,384] (process_zoe fused into the patchify)"""
+        B = px.shape[0]
+        st = self.zoe_trunk(px)
+        head = self.pick_head(st["dlog"])
+        return self.zoe_bins_stage(head, st["xb"], st["outconv"], st["bottleneck"], st["fused"], B)
 
     # ------------------------------------------------------------------------------------------ image features (a4)
-    def image_features(self, px, intrinsic, return_aux=False):
-        """-> fp32 [B, 256, H_text] (already divided by sqrt(H), model/modeling_spatialvla.py:331-332)"""
-        ops = self.ops
-        B = px.shape[0]
-        D, H = self.v["hidden_size"], self.t["hidden_size"]
-        px = px.to(device=self.dev, dtype=F32).contiguous()
+    def vision_stage_a(self, px):
+        """SigLIP tower + ZoeDepth trunk + router logits (no host interaction)."""
         sig, sig_b = self.siglip(px)
-        aux = {"siglip": sig.clone() if return_aux else None}
-        src = sig_b
+        st = {"sig": sig, "sig_b": sig_b}
         if self.use_zoe:
-            depth = self.zoedepth(px)
-            K = intrinsic.to(device=self.dev, dtype=F32).contiguous()
+            st.update(self.zoe_trunk(px))
+        return st
+
+    def vision_stage_b(self, st, head, intrinsic, B, aux=None):
+        """Metric-bins head `head`, Ego3D position embedding, add to SigLIP tokens, projector -> fp32 [B,256,H]."""
+        ops = self.ops
+        D, H = self.v["hidden_size"], self.t["hidden_size"]
+        src = st["sig_b"]
+        if self.use_zoe:
+            depth = self.zoe_bins_stage(head, st["xb"], st["outconv"], st["bottleneck"], st["fused"], B)
             xyz = ops.empty((B * 256, 12), F32)
             enc = ops.empty((B * 256, self.ego_kpad), BF16)
-            ops.ego3d_encode(depth, K, xyz, enc, n_freqs=self.cfg["n_freqs"])
+            ops.ego3d_encode(depth, intrinsic, xyz, enc, n_freqs=self.cfg["n_freqs"])
             h0 = self._lin(enc, self.ego["w0"], B * 256, F32, bias=self.ego["b0"])
             hb = ops.empty((B * 256, D), BF16)
             ops.layernorm(h0, self.ego["ln_g"], self.ego["ln_b"], 1e-5, out_bf16=hb, relu=True)
             src = ops.empty((B * 256, D), BF16)
-            ops.gemm(hb, self.ego["w3"], bias=self.ego["b3"], res_f32=sig, out_bf16=src)
-            aux.update({"depth384": depth, "xyz": xyz.view(B, 256, 12)})
+            ops.gemm(hb, self.ego["w3"], bias=self.ego["b3"], res_f32=st["sig"], out_bf16=src)
+            if aux is not None:
+                aux.update({"depth384": depth, "xyz": xyz.view(B, 256, 12)})
         feats = self._lin(src, self.proj_w, B * 256, F32, bias=self.proj_b, colscale=self.proj_scale)
-        feats = feats.view(B, 256, H)
+        return feats.view(B, 256, H)
+
+    def image_features(self, px, intrinsic, return_aux=False):
+        """-> fp32 [B, 256, H_text] (already divided by sqrt(H), model/modeling_spatialvla.py:331-332)"""
+        B = px.shape[0]
+        px = px.to(device=self.dev, dtype=F32).contiguous()
+        K = intrinsic.to(device=self.dev, dtype=F32).contiguous() if intrinsic is not None else None
+        st = self.vision_stage_a(px)
+        aux = {"siglip": st["sig"].clone()} if return_aux else None
+        head = self.pick_head(st["dlog"]) if self.use_zoe else 0
+        feats = self.vision_stage_b(st, head, K, B, aux)
         return (feats, aux) if return_aux else feats
 
     # ------------------------------------------------------------------------------------------ Gemma2 (a12-a18)
@@ -520,22 +548,19 @@ class SpatialVLAEngine:
         self.ops.gemm(h_rows, self.gem["head_act"], out_f32=lg, act=ACT_SOFTCAP if cap else ACT_NONE, act_param=cap or 0.0)
         return lg
 
-    def generate_actions(self, ids, px, intrinsic, n_new, forced_tokens=None, return_logits=False):
-        """Greedy decode of n_new action tokens (argmax restricted to the action slice). ids int64 [B,P] on device.
-        Returns tokens int64 [B, n_new] (+ fp32 logits [B, n_new, n_act])."""
+    def language_stage(self, ids, feats, n_new, forced_tokens=None, logs=None):
+        """Embed + bidirectional prefill + n_new greedy action tokens (argmax over the action slice) -> int64 [B, n_new]"""
         ops = self.ops
         B, P = ids.shape
         H = self.t["hidden_size"]
-        feats = self.image_features(px, intrinsic) if px is not None else None
         x, status = self.embed(ids, feats)
         cache = self.new_cache(B, P + n_new)
         h = self.gemma_forward(x, B, P, cache, bidirectional=True)
         toks = ops.zeros((B, n_new), torch.int64)
-        logs = []
         rows = h.view(B, P * H)[:, (P - 1) * H:]
         for step in range(n_new):
             lg = self.action_logits(rows, B)
-            if return_logits:
+            if logs is not None:
                 logs.append(lg)
             ops.argmax_rows(lg, toks[:, step], id_offset=self.act_lo)
             if step == n_new - 1:
@@ -544,6 +569,64 @@ class SpatialVLAEngine:
             x, _ = self.embed(feed.contiguous())
             rows = self.gemma_forward(x, B, 1, cache, bidirectional=False)
         self.last_status = status
+        return toks
+
+    def generate_actions(self, ids, px, intrinsic, n_new, forced_tokens=None, return_logits=False):
+        """Greedy decode of n_new action tokens (argmax restricted to the action slice). ids int64 [B,P] on device.
+        Returns tokens int64 [B, n_new] (+ fp32 logits [B, n_new, n_act]).  On a CUDA device the whole step is
+        replayed from two CUDA graphs (before / after the ZoeDepth router's host read) unless logits or teacher
+        forcing are requested."""
+        if (self.use_graphs and px is not None and forced_tokens is None and not return_logits
+                and getattr(self.ops, "name", "") == "cuda"):
+            return self._generate_graphed(ids, px, intrinsic, n_new)
+        feats = self.image_features(px, intrinsic) if px is not None else None
+        logs = [] if return_logits else None
+        toks = self.language_stage(ids, feats, n_new, forced_tokens, logs)
         if return_logits:
             return toks, torch.stack(logs, 1)
         return toks
+
+    # ------------------------------------------------------------------------------------------ CUDA graphs
+    use_graphs = True
+
+    def _generate_graphed(self, ids, px, intrinsic, n_new):
+        """Static-shape replay: graph A = vision stage A (ends with the router logits); one D2H read picks the metric
+        head; graph B[head] = metric-bins tail + Ego3D + projector + Gemma2 prefill + decode loop.  Kernel arguments
+        (TMA descriptors included) are baked at capture; inputs are copied into static buffers before each replay."""
+        B, P = ids.shape
+        Kdim = intrinsic.dim()
+        key = (B, P, n_new, Kdim)
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        g = self._graphs.get(key)
+        px = px.to(device=self.dev, dtype=F32)
+        K = intrinsic.to(device=self.dev, dtype=F32)
+        if g is None:
+            g = {"ids": ids.clone(), "px": px.clone().contiguous(), "K": K.clone().contiguous(), "B": {}, "launches_b": {}}
+            # warm-up outside capture (cudaFuncSetAttribute, lazy module load), then capture stage A
+            feats = self.image_features(g["px"], g["K"])
+            self.language_stage(g["ids"], feats, n_new)
+            torch.cuda.synchronize()
+            n0 = self.ops.launch_count()
+            ga = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                g["st"] = self.vision_stage_a(g["px"])
+            g["A"], g["launches_a"] = ga, self.ops.launch_count() - n0
+            self._graphs[key] = g
+        g["ids"].copy_(ids)
+        g["px"].copy_(px)
+        g["K"].copy_(K)
+        g["A"].replay()
+        head = self.pick_head(g["st"]["dlog"]) if self.use_zoe else 0
+        if head not in g["B"]:
+            n0 = self.ops.launch_count()
+            gb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb):
+                feats = self.vision_stage_b(g["st"], head, g["K"], B)
+                toks = self.language_stage(g["ids"], feats, n_new)
+            g["B"][head] = (gb, toks)
+            g["launches_b"][head] = self.ops.launch_count() - n0
+        gb, toks = g["B"][head]
+        gb.replay()
+        self.graph_replayed_launches = getattr(self, "graph_replayed_launches", 0) + g["launches_a"] + g["launches_b"][head]
+        return toks.clone()

@@ -40,6 +40,15 @@ for name, M, N, K in shapes:
     if name.startswith("cublas") or name in ("gemma_gateup", "beit_fc1"):
         ms = timeit(lambda: torch.matmul(a, w.t()))
         print({"name": name + "_torch_matmul", "ms": round(ms, 4), "tflops": round(2.0 * M * N * K / ms / 1e9, 1)}, flush=True)
+# mainloop probes: one tile per SM (148 tiles) and a single tile, K sweep -> time per 64-wide k-block
+for name, M, N in [("probe_148tiles_bn256", 128 * 148, 256), ("probe_1tile_bn256", 128, 256), ("probe_148tiles_m64_bn128", 64, 128 * 148)]:
+    if only and only not in name: continue
+    for K in (1024, 4096, 16384):
+        a = torch.randn(M, K, device=dev).to(BF16); w = torch.randn(N, K, device=dev).to(BF16)
+        out = torch.empty(M, N, device=dev, dtype=BF16)
+        bn = 128 if "bn128" in name else 256
+        ms = timeit(lambda: ops.gemm(a, w, out_bf16=out, block_n=bn))
+        print({"name": name, "K": K, "ms": round(ms, 4), "us_per_kblock": round(ms * 1e3 / (K / 64), 3), "tflops": round(2.0 * M * N * K / ms / 1e9, 1)}, flush=True)
 # conv
 for name, (nb, h, w_, c), N in [("fusion_conv_96", (64, 96, 96, 256), 256), ("fusion_conv_48", (64, 48, 48, 256), 256), ("rel_conv1_192", (64, 192, 192, 256), 128), ("rel_conv2_384", (64, 384, 384, 128), 32)]:
     if only and only not in name: continue

@@ -16,6 +16,7 @@ Numerics: bf16 GEMM/attention operands, fp32 accumulation, fp32 residual streams
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -587,7 +588,7 @@ class SpatialVLAEngine:
         return toks
 
     # ------------------------------------------------------------------------------------------ CUDA graphs
-    use_graphs = True
+    use_graphs = os.environ.get("SVLA_NO_GRAPHS", "0") != "1"
 
     def _generate_graphed(self, ids, px, intrinsic, n_new):
         """Static-shape replay: graph A = vision stage A (ends with the router logits); one D2H read picks the metric

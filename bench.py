@@ -101,9 +101,23 @@ class TimedOps:
             s.record()
             out = fn(*a, **k)
             e.record()
-            self.records.append((name, self._work(name, a, k), s, e))
+            self.records.append((name, self._work(name, a, k), s, e, self._shape(name, a, k)))
             return out
         return wrapped
+
+    @staticmethod
+    def _shape(name, a, k):
+        if name == "gemm":
+            n = k.get("n") or a[1].shape[0]
+            tags = "".join(t for t, on in (("+bias", k.get("bias") is not None), ("+act%d" % k.get("act", 0), k.get("act", 0)),
+                                           ("+geglu", k.get("geglu")), ("+acc", k.get("accumulate")), ("+f32", k.get("out_f32") is not None),
+                                           ("+res", k.get("res_bf16") is not None or k.get("res_f32") is not None)) if on)
+            if k.get("conv") is not None:
+                return f"conv{k['conv']} N={n}{tags}"
+            return f"M={a[0].shape[0]} N={n} K={k.get('k') or a[0].shape[1]}{tags}"
+        if name == "attention":
+            return f"B={k['batch']} h={k['hq']} S={k['sq']} d={k['d']}"
+        return ""
 
     @staticmethod
     def _work(name, a, k):
@@ -121,11 +135,18 @@ class TimedOps:
     def summary(self):
         torch.cuda.synchronize()
         agg = {}
-        for name, (kind, work), s, e in self.records:
+        self.by_shape = {}
+        for name, (kind, work), s, e, shape in self.records:
+            ms = s.elapsed_time(e)
             d = agg.setdefault(name, {"ms": 0.0, "calls": 0, "flop": 0.0})
-            d["ms"] += s.elapsed_time(e)
+            d["ms"] += ms
             d["calls"] += 1
             d["flop"] += work if kind == "flop" else 0.0
+            if shape:
+                b = self.by_shape.setdefault((name, shape), {"ms": 0.0, "calls": 0, "flop": 0.0})
+                b["ms"] += ms
+                b["calls"] += 1
+                b["flop"] += work if kind == "flop" else 0.0
         return agg
 
 
@@ -232,6 +253,8 @@ def run_ours(args):
     for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
         extra = f" {d['flop'] / d['ms'] / 1e9:8.1f} TFLOP/s" if d["flop"] else ""
         log(f"  {name:22s} {d['calls']:5d} calls {d['ms']:9.2f} ms {100 * d['ms'] / total_ms:5.1f}%{extra}")
+    for (name, shape), d in sorted(timed.by_shape.items(), key=lambda kv: -kv[1]["ms"])[:28]:
+        log(f"    {name:10s} {shape:58s} x{d['calls']:4d} {d['ms']:8.2f} ms  {d['flop'] / max(d['ms'], 1e-9) / 1e9:7.1f} TFLOP/s")
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -73,6 +73,23 @@ typedef struct SvlaGemmArgs {
 
 int svla_gemm(const SvlaGemmArgs* args, void* stream);
 
+/* G1s: skinny GEMM for the decode steps (M <= 128 activation rows): weight-streaming, swap-AB (UMMA M walks the weight
+ * rows), split-K across CTAs so every SM streams weights. out[m,n] = act(alpha * sum_k x[m,k] w[n,k] + bias[n]).
+ * flags: 1 = GEGLU (as svla_gemm), 2 = PARTIAL: raw fp32 partial sums out_f32[split * partial_stride + m*ldo + n] for
+ * `splits` K-slices (the consumers svla_rmsnorm_residual / svla_rope_kv add them). model/modeling_gemma2.py:80-92,351-354,993 */
+typedef struct SvlaSkinnyArgs {
+  const void* x;          /* bf16 [M, ldx] */
+  const void* w;          /* bf16 [N, ldw] */
+  const float* bias;      /* fp32 [N] or NULL */
+  void* out_bf16;         /* bf16 [M, ldo] or NULL */
+  float* out_f32;         /* fp32 [M, ldo] (or [splits][M][ldo] with PARTIAL) or NULL */
+  int64_t m, n, k, ldx, ldw, ldo, partial_stride;
+  float alpha, act_param;
+  int32_t act, flags, splits;
+} SvlaSkinnyArgs;
+int svla_gemm_skinny(const SvlaSkinnyArgs* args, void* stream);
+int svla_gemm_skinny_splits(int64_t n, int64_t k);   /* the split count the library would pick for an [n, k] weight */
+
 /* ---------------------------------------------------------------------------------------------------
  * G2: softmax(scale * Q K^T [softcap] [+ relpos bias] [mask]) V, flash style, fp32 softmax.
  *   model/modeling_gemma2.py:169-195 (GQA, tanh soft-capping; bidirectional prefill per
@@ -111,13 +128,16 @@ int svla_layernorm(const float* x, const float* gamma, const float* beta, float 
  *   if branch:  x += rms(branch) * (1 + w_post)        (x fp32 residual, updated in place)
  *   if w_pre:   out_bf16 = rms(x) * (1 + w_pre)                                                     */
 int svla_rmsnorm_residual(float* x, const float* branch, const float* w_post, const float* w_pre, float eps,
-                          int64_t rows, int cols, void* out_bf16, void* stream);
+                          int64_t rows, int cols, void* out_bf16, int n_partials, int64_t partial_stride, void* stream);
+/* n_partials > 1: branch = sum_s branch[s * partial_stride + ...] (split-K partial sums of svla_gemm_skinny) */
 
 /* M3 RoPE + KV-cache write (model/modeling_gemma2.py:95-154,376-395; positions 1-indexed per
  * model/modeling_spatialvla.py:371-372). qkv bf16 [B*S, (hq+2hkv)*D] -> q_out bf16 [B*S, hq*D] (rotated),
  * kcache/vcache bf16 [B, smax, hkv, D] rows [pos0, pos0+S). */
 int svla_rope_kv(const void* qkv, void* q_out, void* kcache, void* vcache, int batch, int s, int hq, int hkv,
-                 int d, int smax, int pos0, float theta, void* stream);
+                 int d, int smax, int pos0, float theta, const float* qkv_f32, int n_partials, int64_t partial_stride,
+                 void* stream);
+/* qkv_f32 != NULL: read qkv as the sum of n_partials fp32 partial buffers instead of the bf16 `qkv` */
 
 /* M6 embedding gather (model/modeling_spatialvla.py:361-387, model/modeling_gemma2.py:741-742):
  * text ids -> embed (bf16 [V,H]); ids in [act_lo, act_lo+n_act) -> spatial_embed (bf16 [n_act,H]);

@@ -97,6 +97,34 @@ class RefOps:
         if out_relu is not None:
             _rows(out_relu)[:, :N] = F.relu(v).to(BF16)
 
+    # ---- G1s
+    def skinny_splits(self, n, k):
+        return max(1, min(148 // max(1, (n + 127) // 128), max(1, ((k + 63) // 64) // 4)))
+
+    def gemm_skinny(self, x, w, *, out_bf16=None, out_f32=None, bias=None, act=ACT_NONE, act_param=0.0, alpha=1.0,
+                    geglu=False, splits=1):
+        self.launches += 1
+        xf, wf = x.float(), w.float()
+        if out_f32 is not None and out_f32.dim() == 3:
+            S, K = out_f32.shape[0], x.shape[1]
+            kb = (K + 63) // 64
+            per = (kb + S - 1) // S
+            for sidx in range(S):
+                lo, hi = sidx * per * 64, min(K, (sidx + 1) * per * 64)
+                out_f32[sidx, :, : w.shape[0]] = xf[:, lo:hi] @ wf[:, lo:hi].t()
+            return
+        v = (xf @ wf.t()) * alpha
+        if bias is not None:
+            v = v + bias
+        if geglu:
+            out_bf16[:, : w.shape[0] // 2] = (F.gelu(v[:, 0::2], approximate="tanh") * v[:, 1::2]).to(BF16)
+            return
+        v = _act(v, act, act_param)
+        if out_f32 is not None:
+            out_f32[:, : w.shape[0]] = v
+        if out_bf16 is not None:
+            out_bf16[:, : w.shape[0]] = v.to(BF16)
+
     # ---- G2 / G3
     @staticmethod
     def _strided(t, bs, ss, batch, s, heads, d):
@@ -152,12 +180,16 @@ class RefOps:
         def rms(t, w):
             return t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + eps) * (1.0 + w)
         if branch is not None:
-            x.add_(rms(branch.view_as(x), w_post))
+            if branch.dim() == 3:
+                branch = branch.sum(0)
+            x.add_(rms(branch.reshape(x.shape), w_post))
         if w_pre is not None:
             out_bf16.copy_(rms(x, w_pre).view_as(out_bf16).to(BF16))
 
     def rope_kv(self, qkv, q_out, kcache, vcache, *, batch, s, hq, hkv, d, smax, pos0, theta):
         self.launches += 1
+        if qkv.dtype == F32 and qkv.dim() == 3:
+            qkv = qkv.sum(0)
         t = qkv.float().view(batch, s, hq + 2 * hkv, d)
         pos = torch.arange(pos0, pos0 + s).float() + 1.0
         inv = 1.0 / (theta ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))

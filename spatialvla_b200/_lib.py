@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "lib", "libspatialvla_b200.so")
-SOURCES = ["capi.cu", "gemm_tcgen05.cu", "attention.cu", "fused_ops.cu", "tokenizer.cu"]
+SOURCES = ["capi.cu", "gemm_tcgen05.cu", "gemm_skinny.cu", "attention.cu", "fused_ops.cu", "tokenizer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -30,6 +30,15 @@ class SvlaGemmArgs(C.Structure):
         ("nb", C.c_int32), ("h", C.c_int32), ("wd", C.c_int32), ("c", C.c_int32),
         ("alpha", C.c_float), ("act_param", C.c_float), ("act", C.c_int32), ("flags", C.c_int32),
         ("block_n", C.c_int32), ("impl", C.c_int32),
+    ]
+
+
+class SvlaSkinnyArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("out_bf16", C.c_void_p), ("out_f32", C.c_void_p),
+        ("m", C.c_int64), ("n", C.c_int64), ("k", C.c_int64), ("ldx", C.c_int64), ("ldw", C.c_int64), ("ldo", C.c_int64),
+        ("partial_stride", C.c_int64), ("alpha", C.c_float), ("act_param", C.c_float), ("act", C.c_int32),
+        ("flags", C.c_int32), ("splits", C.c_int32),
     ]
 
 
@@ -52,11 +61,13 @@ SIGNATURES = {
     "svla_abi_version": (_I, []),
     "svla_launch_count": (C.c_longlong, []),
     "svla_gemm": (_I, [C.POINTER(SvlaGemmArgs), _P]),
+    "svla_gemm_skinny": (_I, [C.POINTER(SvlaSkinnyArgs), _P]),
+    "svla_gemm_skinny_splits": (_I, [_L, _L]),
     "svla_attention": (_I, [C.POINTER(SvlaAttnArgs), _P]),
     "svla_decode_attention": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "svla_layernorm": (_I, [_P, _P, _P, _F, _L, _I, _P, _P, _I, _P]),
-    "svla_rmsnorm_residual": (_I, [_P, _P, _P, _P, _F, _L, _I, _P, _P]),
-    "svla_rope_kv": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "svla_rmsnorm_residual": (_I, [_P, _P, _P, _P, _F, _L, _I, _P, _I, _L, _P]),
+    "svla_rope_kv": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _I, _L, _P]),
     "svla_embed_tokens": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _L, _I, _F, _P, _P]),
     "svla_argmax_rows": (_I, [_P, _L, _L, _L, _L, _P, _L, _P]),
     "svla_siglip_patchify": (_I, [_P, _P, _I, _I, _P]),
@@ -87,7 +98,7 @@ def build_library(verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into the in-tree shared library (no GPU needed)."""
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "svla_common.cuh"), os.path.join(_HERE, "..", "include", "spatialvla_b200.h")]
+    deps = srcs + [os.path.join(CSRC, "svla_common.cuh"), os.path.join(CSRC, "tc_ptx.cuh"), os.path.join(_HERE, "..", "include", "spatialvla_b200.h")]
     if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -283,6 +283,11 @@ int launch_attn(const AttnP& p, int batch, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------ decode (q_len = 1)
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { f[2 * u] = bf16_bits_to_float(w[u] & 0xFFFFu); f[2 * u + 1] = bf16_bits_to_float(w[u] >> 16); }
+}
 constexpr int kDecThreads = 256;
 constexpr int kMaxGroup = 4;
 
@@ -305,30 +310,30 @@ svla_decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16
   const __nv_bfloat16* kb = kc + (static_cast<long long>(b) * smax * hkv + hk) * D;
   const __nv_bfloat16* vb = vc + (static_cast<long long>(b) * smax * hkv + hk) * D;
   const long long row_stride = static_cast<long long>(hkv) * D;
-  // scores: one warp per key, each lane covers D/32 contiguous dims
+  // scores: one warp per key, each lane covers D/32 contiguous dims; 4 keys in flight per warp (memory-level parallelism)
   constexpr int PER = D / 32;
-  for (int j = warp; j < ctx; j += NW) {
-    float kv[PER];
-    const __nv_bfloat16* kr = kb + j * row_stride + lane * PER;
+  constexpr int KB = 4;
+  static_assert(PER == 8, "one 16-byte load per lane per key");
+  for (int j0 = warp * KB; j0 < ctx; j0 += NW * KB) {
+    uint4 raw[KB];
 #pragma unroll
-    for (int e = 0; e < PER; e += 8) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(kr + e));
-      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    for (int u = 0; u < KB; ++u)
+      raw[u] = (j0 + u < ctx) ? __ldg(reinterpret_cast<const uint4*>(kb + (j0 + u) * row_stride + lane * PER)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        kv[e + 2 * u] = bf16_bits_to_float(w[u] & 0xFFFFu);
-        kv[e + 2 * u + 1] = bf16_bits_to_float(w[u] >> 16);
-      }
-    }
-    for (int gi = 0; gi < grp; ++gi) {
-      float acc = 0.f;
+    for (int u = 0; u < KB; ++u) {
+      if (j0 + u >= ctx) break;
+      float kv[PER];
+      unpack8(raw[u], kv);
+      for (int gi = 0; gi < grp; ++gi) {
+        float acc = 0.f;
 #pragma unroll
-      for (int e = 0; e < PER; ++e) acc += kv[e] * sq[gi * D + lane * PER + e];
-      acc = warp_sum(acc);
-      if (lane == 0) {
-        float x = acc * scale;
-        if (softcap > 0.f) x = softcap * tanhf(x / softcap);
-        sc[gi * ctx + j] = x;
+        for (int e = 0; e < PER; ++e) acc += kv[e] * sq[gi * D + lane * PER + e];
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          float x = acc * scale;
+          if (softcap > 0.f) x = softcap * tanhf(x / softcap);
+          sc[gi * ctx + j0 + u] = x;
+        }
       }
     }
   }
@@ -360,25 +365,23 @@ svla_decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16
   for (int gi = 0; gi < kMaxGroup; ++gi)
 #pragma unroll
     for (int e = 0; e < PER; ++e) acc[gi][e] = 0.f;
-  for (int j = warp; j < ctx; j += NW) {
-    float vv[PER];
-    const __nv_bfloat16* vr = vb + j * row_stride + lane * PER;
+  for (int j0 = warp * KB; j0 < ctx; j0 += NW * KB) {
+    uint4 raw[KB];
 #pragma unroll
-    for (int e = 0; e < PER; e += 8) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(vr + e));
-      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    for (int u = 0; u < KB; ++u)
+      raw[u] = (j0 + u < ctx) ? __ldg(reinterpret_cast<const uint4*>(vb + (j0 + u) * row_stride + lane * PER)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        vv[e + 2 * u] = bf16_bits_to_float(w[u] & 0xFFFFu);
-        vv[e + 2 * u + 1] = bf16_bits_to_float(w[u] >> 16);
-      }
-    }
+    for (int u = 0; u < KB; ++u) {
+      if (j0 + u >= ctx) break;
+      float vv[PER];
+      unpack8(raw[u], vv);
 #pragma unroll
-    for (int gi = 0; gi < kMaxGroup; ++gi) {
-      if (gi < grp) {
-        const float pj = __bfloat162float(__float2bfloat16(sc[gi * ctx + j]));
+      for (int gi = 0; gi < kMaxGroup; ++gi) {
+        if (gi < grp) {
+          const float pj = __bfloat162float(__float2bfloat16(sc[gi * ctx + j0 + u]));
 #pragma unroll
-        for (int e = 0; e < PER; ++e) acc[gi][e] += pj * vv[e];
+          for (int e = 0; e < PER; ++e) acc[gi][e] += pj * vv[e];
+        }
       }
     }
   }

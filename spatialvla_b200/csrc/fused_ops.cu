@@ -65,7 +65,8 @@ svla_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gam
 // ------------------------------------------------------------------------------------------ M2 Gemma2 sandwich norm
 __global__ void __launch_bounds__(kRowThreads)
 svla_rmsnorm_residual_kernel(float* __restrict__ x, const float* __restrict__ branch, const float* __restrict__ w_post,
-                             const float* __restrict__ w_pre, float eps, int cols, __nv_bfloat16* __restrict__ out_bf16) {
+                             const float* __restrict__ w_pre, float eps, int cols, __nv_bfloat16* __restrict__ out_bf16,
+                             int n_partials, long long partial_stride) {
   __shared__ float sh[33];
   const long long row = blockIdx.x;
   const int nv = cols >> 2;
@@ -74,6 +75,12 @@ svla_rmsnorm_residual_kernel(float* __restrict__ x, const float* __restrict__ br
   if (branch) {
     float4 bv[kMaxVec];
     load_row(branch + row * cols, cols, bv);
+    for (int sp = 1; sp < n_partials; ++sp) {           // split-K partial sums, added in a fixed order
+      float4 pv[kMaxVec];
+      load_row(branch + sp * partial_stride + row * cols, cols, pv);
+#pragma unroll
+      for (int k = 0; k < kMaxVec; ++k) { bv[k].x += pv[k].x; bv[k].y += pv[k].y; bv[k].z += pv[k].z; bv[k].w += pv[k].w; }
+    }
     float ss = 0.f;
 #pragma unroll
     for (int k = 0; k < kMaxVec; ++k) ss += bv[k].x * bv[k].x + bv[k].y * bv[k].y + bv[k].z * bv[k].z + bv[k].w * bv[k].w;
@@ -113,7 +120,8 @@ svla_rmsnorm_residual_kernel(float* __restrict__ x, const float* __restrict__ br
 // one block per token; thread pairs (d, d + D/2) of every head
 __global__ void svla_rope_kv_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ q_out,
                                     __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc, int s, int hq, int hkv, int d,
-                                    int smax, int pos0, float theta) {
+                                    int smax, int pos0, float theta, const float* __restrict__ qkv_f32, int n_partials,
+                                    long long partial_stride) {
   const long long tok = blockIdx.x;
   const int b = static_cast<int>(tok / s), si = static_cast<int>(tok % s);
   const int pos = pos0 + si;                       // cache slot
@@ -121,6 +129,12 @@ __global__ void svla_rope_kv_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_
   const int half = d >> 1;
   const long long width = static_cast<long long>(hq + 2 * hkv) * d;
   const __nv_bfloat16* src = qkv + tok * width;
+  auto load = [&](long long col) -> float {
+    if (qkv_f32 == nullptr) return __bfloat162float(src[col]);
+    float acc = 0.f;
+    for (int sp = 0; sp < n_partials; ++sp) acc += qkv_f32[sp * partial_stride + tok * width + col];
+    return acc;
+  };
   const long long cache_row = (static_cast<long long>(b) * smax + pos) * hkv * d;
   const int rot_items = (hq + hkv) * half;
   for (int i = threadIdx.x; i < rot_items; i += blockDim.x) {
@@ -130,8 +144,8 @@ __global__ void svla_rope_kv_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_
     const float ang = fpos * inv_freq;
     float sn, cs;
     sincosf(ang, &sn, &cs);
-    const float x1 = __bfloat162float(src[hh * d + j]);
-    const float x2 = __bfloat162float(src[hh * d + j + half]);
+    const float x1 = load(hh * d + j);
+    const float x2 = load(hh * d + j + half);
     const float o1 = x1 * cs - x2 * sn;
     const float o2 = x2 * cs + x1 * sn;
     if (hh < hq) {
@@ -143,8 +157,8 @@ __global__ void svla_rope_kv_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_
       kc[cache_row + kh * d + j + half] = __float2bfloat16(o2);
     }
   }
-  const __nv_bfloat16* vsrc = src + static_cast<long long>(hq + hkv) * d;
-  for (int i = threadIdx.x; i < hkv * d; i += blockDim.x) vc[cache_row + i] = vsrc[i];
+  const long long voff = static_cast<long long>(hq + hkv) * d;
+  for (int i = threadIdx.x; i < hkv * d; i += blockDim.x) vc[cache_row + i] = __float2bfloat16(load(voff + i));
 }
 
 // ------------------------------------------------------------------------------------------ M6 embedding gather
@@ -458,6 +472,18 @@ svla_zoe_depth_tail_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloa
                            const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ bins,
                            float* __restrict__ depth, int h, int w, int oh, int ow, int nh, int nbins, float min_temp,
                            float max_temp, long long npix) {
+  // per-block tables: log C(K-1, k) in the reference's Stirling form (HF zoedepth log_binom, eps = 1e-7), MLP weights
+  __shared__ float s_lb[64];
+  __shared__ float s_w2[4 * 64];
+  __shared__ float s_b1[64];
+  const float nn = static_cast<float>(nbins - 1) + 1e-7f;
+  for (int k = threadIdx.x; k < nbins; k += blockDim.x) {
+    const float kk = static_cast<float>(k) + 1e-7f;
+    s_lb[k] = nn * logf(nn) - kk * logf(kk) - (nn - kk) * logf(nn - kk + 1e-7f);
+  }
+  for (int i = threadIdx.x; i < 4 * nh; i += blockDim.x) s_w2[i] = w2[i];
+  for (int i = threadIdx.x; i < nh; i += blockDim.x) s_b1[i] = b1[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
@@ -470,9 +496,9 @@ svla_zoe_depth_tail_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloa
     float o4[4] = {0.f, 0.f, 0.f, 0.f};
     const __nv_bfloat16* eb = e + b * h * w * nh;
     for (int ch = lane; ch < nh; ch += 32) {
-      const float hv = gelu_erf_f(__bfloat162float(t[pix * nh + ch]) + bilin_bf16(eb, s, w, nh, ch) + b1[ch]);
+      const float hv = gelu_erf_f(__bfloat162float(t[pix * nh + ch]) + bilin_bf16(eb, s, w, nh, ch) + s_b1[ch]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) o4[q] += w2[q * nh + ch] * hv;
+      for (int q = 0; q < 4; ++q) o4[q] += s_w2[q * nh + ch] * hv;
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) o4[q] = softplus_f(warp_sum(o4[q]) + b2[q]);
@@ -480,7 +506,6 @@ svla_zoe_depth_tail_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloa
     const float prob = p0 / (p0 + p1);
     const float temp = (max_temp - min_temp) * (t0 / (t0 + t1)) + min_temp;
     const float lp = logf(fminf(fmaxf(prob, 1e-4f), 1.f)), lq = logf(fminf(fmaxf(1.f - prob, 1e-4f), 1.f));
-    const float nn = static_cast<float>(nbins - 1) + 1e-7f;
     // y_k = log C(K-1, k) (Stirling form with the reference's eps) + k log p + (K-1-k) log(1-p)
     float y[2], c[2];
     float mx = -INFINITY;
@@ -489,9 +514,7 @@ svla_zoe_depth_tail_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloa
     for (int r = 0; r < 2; ++r) {
       const int k = lane + 32 * r;
       if (k < nbins) {
-        const float kk = static_cast<float>(k) + 1e-7f;
-        const float lb = nn * logf(nn) - kk * logf(kk) - (nn - kk) * logf(nn - kk + 1e-7f);
-        y[r] = (lb + static_cast<float>(k) * lp + static_cast<float>(nbins - 1 - k) * lq) / temp;
+        y[r] = (s_lb[k] + static_cast<float>(k) * lp + static_cast<float>(nbins - 1 - k) * lq) / temp;
         c[r] = bilin_f32(bb, s, w, nbins, k);
         mx = fmaxf(mx, y[r]);
       } else { y[r] = -INFINITY; c[r] = 0.f; }
@@ -588,24 +611,25 @@ extern "C" int svla_layernorm(const float* x, const float* gamma, const float* b
 }
 
 extern "C" int svla_rmsnorm_residual(float* x, const float* branch, const float* w_post, const float* w_pre, float eps,
-                                     int64_t rows, int cols, void* out_bf16, void* stream) {
+                                     int64_t rows, int cols, void* out_bf16, int n_partials, int64_t partial_stride, void* stream) {
   SVLA_REQUIRE(x, "svla_rmsnorm_residual: null x");
   SVLA_REQUIRE((branch == nullptr) == (w_post == nullptr), "svla_rmsnorm_residual: branch and w_post go together");
   SVLA_REQUIRE((w_pre == nullptr) == (out_bf16 == nullptr), "svla_rmsnorm_residual: w_pre and out_bf16 go together");
   SVLA_REQUIRE(rows > 0 && cols > 0 && (cols % 4) == 0 && cols <= kRowThreads * kMaxVec * 4, "svla_rmsnorm_residual: cols=%d unsupported", cols);
   svla_rmsnorm_residual_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, branch, w_post, w_pre, eps, cols, static_cast<__nv_bfloat16*>(out_bf16));
+      x, branch, w_post, w_pre, eps, cols, static_cast<__nv_bfloat16*>(out_bf16), n_partials < 1 ? 1 : n_partials, partial_stride);
   SVLA_LAUNCH_CHECK("svla_rmsnorm_residual");
   return 0;
 }
 
 extern "C" int svla_rope_kv(const void* qkv, void* q_out, void* kcache, void* vcache, int batch, int s, int hq, int hkv, int d,
-                            int smax, int pos0, float theta, void* stream) {
-  SVLA_REQUIRE(qkv && q_out && kcache && vcache, "svla_rope_kv: null pointer");
+                            int smax, int pos0, float theta, const float* qkv_f32, int n_partials, int64_t partial_stride,
+                            void* stream) {
+  SVLA_REQUIRE((qkv || qkv_f32) && q_out && kcache && vcache, "svla_rope_kv: null pointer");
   SVLA_REQUIRE(batch > 0 && s > 0 && (d % 2) == 0 && pos0 >= 0 && pos0 + s <= smax, "svla_rope_kv: bad geometry (pos0=%d s=%d smax=%d)", pos0, s, smax);
   svla_rope_kv_kernel<<<static_cast<unsigned>(batch) * s, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(q_out), static_cast<__nv_bfloat16*>(kcache),
-      static_cast<__nv_bfloat16*>(vcache), s, hq, hkv, d, smax, pos0, theta);
+      static_cast<__nv_bfloat16*>(vcache), s, hq, hkv, d, smax, pos0, theta, qkv_f32, n_partials < 1 ? 1 : n_partials, partial_stride);
   SVLA_LAUNCH_CHECK("svla_rope_kv");
   return 0;
 }
@@ -730,7 +754,7 @@ extern "C" int svla_zoe_depth_tail(const void* t, const void* e, const float* b1
                                    const float* bins, float* depth, int batch, int h, int w, int oh, int ow, int nh, int nbins,
                                    float min_temp, float max_temp, void* stream) {
   SVLA_REQUIRE(t && e && b1 && w2 && b2 && bins && depth, "svla_zoe_depth_tail: null pointer");
-  SVLA_REQUIRE(batch > 0 && nbins > 0 && nbins <= 64 && nh > 0, "svla_zoe_depth_tail: bad geometry");
+  SVLA_REQUIRE(batch > 0 && nbins > 0 && nbins <= 64 && nh > 0 && nh <= 64, "svla_zoe_depth_tail: bad geometry");
   const long long npix = static_cast<long long>(batch) * oh * ow;
   const long long want = (npix + 7) / 8;
   const unsigned blocks = static_cast<unsigned>(want < 148LL * 32 ? want : 148LL * 32);

@@ -1,0 +1,240 @@
+// G1s: skinny (decode) GEMM  out[m, n] = epilogue(sum_k X[m,k] W[n,k])  for M <= 128 activation rows.
+//
+// At batch 64 the decode GEMMs are weight-streaming, HBM-bound (AI ~ 64 FLOP/B): the job of the kernel is to pull
+// the weight matrix through all 148 SMs once, as fast as HBM delivers it.  So the operands are SWAPPED relative to
+// the big-GEMM kernel: the 128-row UMMA M dimension walks the WEIGHT rows (16 KB of weights per K step per CTA, all
+// useful bytes), the activations are the small N-side operand (NB = 16/64/128 columns, L2-hot), and K is SPLIT across
+// CTAs so that n_tiles x splits ~ 148 even for the 2304-row projections.  Accumulators are D^T[n, m] in TMEM: TMEM
+// lane = weight row n, so for a fixed m the 32 lanes of a warp store 32 consecutive n -- fully coalesced without any
+// shared-memory transpose.  Split-K partial sums go to out_f32[split][m][n]; the consumers (svla_rmsnorm_residual,
+// svla_rope_kv) add the partials while they read them, deterministically.
+// Reference ops replaced: the q/k/v/o/gate/up/down/lm_head nn.Linear calls of a decode step
+// (model/modeling_gemma2.py:80-92,351-354,993).
+#include <cstdlib>
+#include <cudaTypedefs.h>
+#include "tc_ptx.cuh"
+
+namespace {
+using namespace svla_ptx;
+
+constexpr int kWM = 128;       // weight rows per CTA (UMMA M)
+constexpr int kBK = 64;
+constexpr int kThreads = 192;
+
+template <int NB> struct SCfg {
+  static constexpr int kWBytes = kWM * kBK * 2;
+  static constexpr int kXBytes = NB * kBK * 2;
+  static constexpr int kStageBytes = kWBytes + kXBytes;
+  static constexpr int kStages = (kStageBytes > 24576) ? 6 : 8;
+  static constexpr int kTmemCols = NB < 32 ? 32 : NB;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+struct SkinnyParams {
+  const float* bias;
+  __nv_bfloat16* out_bf16;
+  float* out_f32;
+  long long m, n, ldo, partial_stride;
+  float alpha, act_param;
+  int act, flags;
+  int n_tiles, kb_per_split, num_k_blocks;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(kThreads, 1)
+svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x, const SkinnyParams p) {
+  using C = SCfg<NB>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* smem_w = smem;
+  uint8_t* smem_x = smem + C::kStages * C::kWBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* acc_bar = bars + 2 * C::kStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x % p.n_tiles, split = blockIdx.x / p.n_tiles;
+  const int kb0 = split * p.kb_per_split;
+  const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_x);
+#pragma unroll 1
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols, 1>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+        tma_load_2d(smem_w + stage * C::kWBytes, &tm_w, &full_bar[stage], kb * kBK, n_tile * kWM);
+        tma_load_2d(smem_x + stage * C::kXBytes, &tm_x, &full_bar[stage], kb * kBK, 0);
+        if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kWM, NB < 16 ? 16 : NB);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t dw = make_kmajor_sw128_desc(smem_u32(smem_w + stage * C::kWBytes));
+        const uint64_t dx = make_kmajor_sw128_desc(smem_u32(smem_x + stage * C::kXBytes));
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k)
+          umma_bf16(tmem_base, dw + static_cast<uint64_t>(k * 2), dx + static_cast<uint64_t>(k * 2), idesc,
+                    static_cast<uint32_t>((kb > kb0) || k != 0));
+        umma_commit(&empty_bar[stage]);
+        if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(acc_bar);
+    }
+  } else {
+    // ------------------------------------------------ epilogue: lane <-> weight row n, register j <-> activation row m
+    const int q = warp & 3;
+    const long long n = static_cast<long long>(n_tile) * kWM + q * 32 + lane;
+    const bool n_ok = n < p.n;
+    const bool partial = (p.flags & 2) != 0, geglu = (p.flags & 1) != 0;
+    const float bias = (p.bias != nullptr && n_ok && !partial) ? __ldg(p.bias + n) : 0.f;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float* pout = partial ? p.out_f32 + static_cast<long long>(split) * p.partial_stride : p.out_f32;
+#pragma unroll 1
+    for (int c0 = 0; c0 < (NB < 32 ? 32 : NB); c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c0, r);
+      if (c0 >= p.m) continue;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int m = c0 + j;
+        if (m >= p.m) break;                      // warp-uniform
+        float v = __uint_as_float(r[j]);
+        if (partial) {
+          if (n_ok) pout[m * p.ldo + n] = v;
+          continue;
+        }
+        v = v * p.alpha + bias;
+        if (geglu) {
+          const float other = __shfl_xor_sync(0xffffffffu, v, 1);
+          if (n_ok && (lane & 1) == 0) p.out_bf16[m * p.ldo + (n >> 1)] = __float2bfloat16(gelu_tanh_fast(v) * other);
+          continue;
+        }
+        if (p.act == SVLA_ACT_SOFTCAP) v = p.act_param * tanhf(v / p.act_param);
+        else if (p.act == SVLA_ACT_GELU_TANH) v = gelu_tanh_fast(v);
+        else if (p.act == SVLA_ACT_RELU) v = fmaxf(v, 0.f);
+        if (n_ok) {
+          if (p.out_f32) p.out_f32[m * p.ldo + n] = v;
+          if (p.out_bf16) p.out_bf16[m * p.ldo + n] = __float2bfloat16(v);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::kTmemCols, 1>(tmem_base);
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+int encode_kmajor(CUtensorMap* tm, const void* base, uint64_t k, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+  auto fn = encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {k, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {kBK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 100;
+}
+
+template <int NB>
+int launch_skinny(const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyParams& p, int ctas, cudaStream_t st) {
+  using C = SCfg<NB>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(svla_gemm_skinny_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) {
+      svla_set_error("svla_gemm_skinny: smem opt-in failed: %s", cudaGetErrorString(e));
+      return -2;
+    }
+    configured = true;
+  }
+  svla_gemm_skinny_kernel<NB><<<ctas, kThreads, C::kSmemBytes, st>>>(tw, tx, p);
+  SVLA_LAUNCH_CHECK("svla_gemm_skinny");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int svla_gemm_skinny_splits(int64_t n, int64_t k) {
+  const int n_tiles = static_cast<int>((n + kWM - 1) / kWM);
+  const int kblocks = static_cast<int>((k + kBK - 1) / kBK);
+  int splits = svla_num_sms() / n_tiles;
+  if (splits < 1) splits = 1;
+  while (splits > 1 && (kblocks + splits - 1) / splits < 4) --splits;     // at least 4 K steps (64 KB of weights) per CTA
+  return splits;
+}
+
+extern "C" int svla_gemm_skinny(const SvlaSkinnyArgs* g, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SVLA_REQUIRE(g && g->x && g->w, "svla_gemm_skinny: null operand");
+  SVLA_REQUIRE(g->m > 0 && g->m <= 128 && g->n > 0 && g->k > 0, "svla_gemm_skinny: need 0 < m <= 128 (m=%lld)", (long long)g->m);
+  SVLA_REQUIRE((g->ldx % 8) == 0 && (g->ldw % 8) == 0 && g->ldx >= g->k && g->ldw >= g->k, "svla_gemm_skinny: bad leading dimensions");
+  const bool geglu = (g->flags & 1) != 0, partial = (g->flags & 2) != 0;
+  const int splits = g->splits > 0 ? g->splits : 1;
+  SVLA_REQUIRE(partial || splits == 1, "svla_gemm_skinny: split-K needs the PARTIAL flag (fp32 partial sums)");
+  SVLA_REQUIRE(!partial || (g->out_f32 && !g->out_bf16 && !geglu), "svla_gemm_skinny: PARTIAL writes out_f32 only");
+  SVLA_REQUIRE(!geglu || (g->out_bf16 && !g->out_f32 && (g->n % 2) == 0), "svla_gemm_skinny: GEGLU needs out_bf16 only and even n");
+  SVLA_REQUIRE(g->out_bf16 || g->out_f32, "svla_gemm_skinny: no output");
+  SkinnyParams p{};
+  p.bias = g->bias; p.out_bf16 = static_cast<__nv_bfloat16*>(g->out_bf16); p.out_f32 = g->out_f32;
+  p.m = g->m; p.n = g->n; p.ldo = g->ldo; p.partial_stride = g->partial_stride;
+  p.alpha = g->alpha; p.act_param = g->act_param; p.act = g->act; p.flags = g->flags;
+  p.n_tiles = static_cast<int>((g->n + kWM - 1) / kWM);
+  p.num_k_blocks = static_cast<int>((g->k + kBK - 1) / kBK);
+  p.kb_per_split = (p.num_k_blocks + splits - 1) / splits;
+  SVLA_REQUIRE(static_cast<long long>(p.kb_per_split) * (splits - 1) < p.num_k_blocks, "svla_gemm_skinny: too many splits (%d) for k=%lld", splits, (long long)g->k);
+  const int nb = g->m <= 16 ? 16 : (g->m <= 64 ? 64 : 128);
+  CUtensorMap tw, tx;
+  int rc = encode_kmajor(&tw, g->w, static_cast<uint64_t>(g->k), static_cast<uint64_t>(g->n), static_cast<uint64_t>(g->ldw), kWM);
+  SVLA_REQUIRE(rc == 0, "svla_gemm_skinny: cuTensorMapEncodeTiled(W) failed (%d)", rc);
+  rc = encode_kmajor(&tx, g->x, static_cast<uint64_t>(g->k), static_cast<uint64_t>(g->m), static_cast<uint64_t>(g->ldx), static_cast<uint32_t>(nb));
+  SVLA_REQUIRE(rc == 0, "svla_gemm_skinny: cuTensorMapEncodeTiled(X) failed (%d)", rc);
+  const int ctas = p.n_tiles * splits;
+  if (nb == 16) return launch_skinny<16>(tw, tx, p, ctas, st);
+  if (nb == 64) return launch_skinny<64>(tw, tx, p, ctas, st);
+  return launch_skinny<128>(tw, tx, p, ctas, st);
+}

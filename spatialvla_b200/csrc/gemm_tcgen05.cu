@@ -12,23 +12,27 @@
 //
 // Reference ops replaced: see include/spatialvla_b200.h (svla_gemm).
 #include <cuda.h>
+#include <cstdlib>
 #include <cudaTypedefs.h>
-#include "svla_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
+using namespace svla_ptx;
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;             // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 192;
 constexpr int kConvTileW = 16, kConvTileH = 8;
-constexpr uint32_t kSpinLimit = 1u << 28;
 
-template <int BN> struct Cfg {
+// CG = CTAs per MMA (tcgen05 cta_group): 1 = one CTA computes a 128 x BN tile; 2 = a CTA pair (cluster of 2 along M)
+// computes 256 x BN with ONE tcgen05.mma.cta_group::2 per K step: each CTA stages its own 128 A rows and only
+// BN/2 of the W rows, halving the L2 -> shared-memory traffic per FLOP (the 1-CTA kernel is L2-bandwidth bound).
+template <int BN, int CG = 1> struct Cfg {
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBBytes = (BN / CG) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 4 : ((BN >= 128) ? 6 : 8);
+  static constexpr int kStages = (kStageBytes >= 49152) ? 4 : ((kStageBytes >= 32768) ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int kStagingBytes = 4 * 32 * 36 * 4;     // per-epilogue-warp fp32 transpose tile
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes;
@@ -50,109 +54,6 @@ struct EpiParams {
   // conv geometry
   int nb, h, wd, tiles_h, tiles_w;
 };
-
-// ------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-#pragma unroll 1
-  for (uint32_t spin = 0; spin < kSpinLimit; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  // A pipeline bug must surface as a launch failure, never as a hung GPU box.
-  printf("svla_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-  __trap();
-}
-
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
-                                            int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
-      "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-template <int COLS> __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-}
-template <int COLS> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS));
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-//   [0,14) start>>4 | [16,30) LBO>>4 (ignored for swizzled K-major, canonical value 1) | [32,46) SBO>>4 = 1024B>>4
-//   [46,48) version = 1 (sm100) | [61,64) layout type = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-
-// kind::f16 instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // ------------------------------------------------------------------------------------------ fused epilogue
 __device__ __forceinline__ float apply_act(float v, int act, float p) {
@@ -197,7 +98,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, const float 
         break;
       case SVLA_ACT_GELU_ERF:
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
         break;
       case SVLA_ACT_RELU:
 #pragma unroll
@@ -312,15 +213,31 @@ __device__ __forceinline__ bool tile_row_to_global(const EpiParams& ep, bool con
   return hh < ep.h && ww < ep.wd && img < ep.nb;
 }
 
+// Tile rasterisation: m-groups (1 or 2 m-tiles) are walked in super-rows of kRasterGroup groups; inside a super-row
+// the n index is the slow one.  One wave of CTAs then touches ~16 A tiles x ~9 W tiles instead of every A tile of
+// the problem, which keeps both operands L2-resident (ncu: 10x DRAM re-reads of A with the plain m-fastest order).
+constexpr int kRasterGroup = 16;
+__device__ __forceinline__ void raster_tile(long long tile, long long num_m_groups, long long num_n_tiles, long long& mg,
+                                            long long& nt) {
+  const long long per_super = static_cast<long long>(kRasterGroup) * num_n_tiles;
+  const long long sr = tile / per_super;
+  const long long rem = tile - sr * per_super;
+  const long long m0 = sr * kRasterGroup;
+  const long long rows = (num_m_groups - m0) < kRasterGroup ? (num_m_groups - m0) : kRasterGroup;
+  nt = rem / rows;
+  mg = m0 + (rem - nt * rows);
+}
+
 // ------------------------------------------------------------------------------------------ the kernel
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                          const EpiParams ep, const long long num_m_tiles, const long long num_n_tiles,
                          const int num_k_blocks, const int conv, const int c_chunks) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
+  constexpr int BNL = BN / CG;       // W rows staged by this CTA
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B operands need 1024-byte aligned stage bases
+  // SWIZZLE_128B operands need 1024-byte aligned stage bases (identical offsets in both CTAs of a pair)
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
@@ -335,6 +252,8 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (cta_rank == 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -346,26 +265,30 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     }
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 4);
-    mbar_init(&tmem_empty[1], 4);
+    mbar_init(&tmem_empty[0], 4 * CG);     // 4 epilogue warps of every CTA of the pair arrive on the leader's barrier
+    mbar_init(&tmem_empty[1], 4 * CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_ptr_smem);
+  if (warp == 1) tmem_alloc<C::kTmemCols, CG>(tmem_ptr_smem);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const long long num_tiles = num_m_tiles * num_n_tiles;
+  // tile space: pairs of consecutive m-tiles (CG == 2) x n-tiles, m fastest so concurrent CTAs share the W tile in L2
+  const long long num_m_groups = (num_m_tiles + CG - 1) / CG;
+  const long long num_tiles = num_m_groups * num_n_tiles;
+  const long long first = blockIdx.x / CG, step = gridDim.x / CG;
 
   if (warp == 0) {
-    // ===================================================== TMA producer (one lane)
+    // ===================================================== TMA producer (one lane, every CTA)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const long long m_tile = tile % num_m_tiles;
-        const long long n_tile = tile / num_m_tiles;
+      for (long long tile = first; tile < num_tiles; tile += step) {
+        long long mg, n_tile;
+        raster_tile(tile, num_m_groups, num_n_tiles, mg, n_tile);
+        const long long m_tile = mg * CG + cta_rank;
         int img = 0, h0 = 0, w0 = 0;
         if (conv) {
           const int tiles_per_img = ep.tiles_h * ep.tiles_w;
@@ -376,27 +299,40 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         }
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-          if (conv) {
-            const int tap = kb / c_chunks, cc = kb - tap * c_chunks;
-            tma_load_4d(smem_a + stage * C::kABytes, &tm_a, &full_bar[stage], cc * kBK, w0 + (tap % 3) - 1,
-                        h0 + (tap / 3) - 1, img);
+          uint8_t* sa = smem_a + stage * C::kABytes;
+          uint8_t* sb = smem_b + stage * C::kBBytes;
+          if constexpr (CG == 1) {
+            mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+            if (conv) {
+              const int tap = kb / c_chunks, cc = kb - tap * c_chunks;
+              tma_load_4d(sa, &tm_a, &full_bar[stage], cc * kBK, w0 + (tap % 3) - 1, h0 + (tap / 3) - 1, img);
+            } else {
+              tma_load_2d(sa, &tm_a, &full_bar[stage], kb * kBK, static_cast<int>(m_tile * kBM));
+            }
+            tma_load_2d(sb, &tm_b, &full_bar[stage], kb * kBK, static_cast<int>(n_tile * BN));
           } else {
-            tma_load_2d(smem_a + stage * C::kABytes, &tm_a, &full_bar[stage], kb * kBK, static_cast<int>(m_tile * kBM));
+            // the leader arms its barrier for the bytes of BOTH CTAs; the peer's TMA signals the leader's barrier
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+            if (conv) {
+              const int tap = kb / c_chunks, cc = kb - tap * c_chunks;
+              tma_load_4d_cg2(sa, &tm_a, &full_bar[stage], cc * kBK, w0 + (tap % 3) - 1, h0 + (tap / 3) - 1, img);
+            } else {
+              tma_load_2d_cg2(sa, &tm_a, &full_bar[stage], kb * kBK, static_cast<int>(m_tile * kBM));
+            }
+            tma_load_2d_cg2(sb, &tm_b, &full_bar[stage], kb * kBK, static_cast<int>(n_tile * BN + cta_rank * BNL));
           }
-          tma_load_2d(smem_b + stage * C::kBBytes, &tm_b, &full_bar[stage], kb * kBK, static_cast<int>(n_tile * BN));
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (one lane)
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
+    // ===================================================== MMA issuer (one lane of the leader CTA)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (long long tile = first; tile < num_tiles; tile += step, ++it) {
         const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
         mbar_wait(&tmem_empty[as], aphase ^ 1u);
         tc_fence_after();
@@ -409,27 +345,36 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                      static_cast<uint32_t>((kb | k) != 0));
+            if constexpr (CG == 1)
+              umma_bf16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                        static_cast<uint32_t>((kb | k) != 0));
+            else
+              umma_bf16_cg2(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                            static_cast<uint32_t>((kb | k) != 0));
           }
-          umma_commit(&empty_bar[stage]);      // frees the smem stage once these MMAs have read it
+          // frees the smem stage (in both CTAs for CG == 2) once these MMAs have read it
+          if constexpr (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_cg2(&empty_bar[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tmem_full[as]);           // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if constexpr (CG == 1) umma_commit(&tmem_full[as]); else umma_commit_cg2(&tmem_full[as]);
       }
     }
   } else {
     // ===================================================== epilogue warps 2..5 (TMEM lane group = warp % 4)
     const int q = warp & 3;
     uint32_t it = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const long long m_tile = tile % num_m_tiles;
-      const long long n_tile = tile / num_m_tiles;
+    for (long long tile = first; tile < num_tiles; tile += step, ++it) {
+      long long mg, n_tile;
+      raster_tile(tile, num_m_groups, num_n_tiles, mg, n_tile);
+      const long long m_tile = mg * CG + cta_rank;
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       float* stage = staging + (warp - 2) * 32 * kStageLd;
-      auto row_of = [&](int r, long long& grow) { return tile_row_to_global(ep, conv != 0, m_tile, q * 32 + r, grow); };
+      auto row_of = [&](int r, long long& grow) {
+        return m_tile < num_m_tiles && tile_row_to_global(ep, conv != 0, m_tile, q * 32 + r, grow);
+      };
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -444,15 +389,17 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if constexpr (CG == 1) mbar_arrive(&tmem_empty[as]); else mbar_arrive_remote(&tmem_empty[as], 0);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<C::kTmemCols>(tmem_base);
+    tmem_dealloc<C::kTmemCols, CG>(tmem_base);
   }
 }
 
@@ -550,13 +497,13 @@ int encode_nhwc(CUtensorMap* tm, const void* base, int nb, int h, int w, int c) 
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 100;
 }
 
-template <int BN>
+template <int BN, int CG>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& ep, long long mt, long long nt, int kb,
               int conv, int c_chunks, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(svla_gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(svla_gemm_tcgen05_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::kSmemBytes);
     if (e != cudaSuccess) {
       svla_set_error("svla_gemm: cudaFuncSetAttribute(%d bytes) failed: %s", C::kSmemBytes, cudaGetErrorString(e));
@@ -564,9 +511,26 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& ep,
     }
     configured = true;
   }
-  const long long tiles = mt * nt;
-  const int grid = static_cast<int>(tiles < svla_num_sms() ? tiles : svla_num_sms());
-  svla_gemm_tcgen05_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, ep, mt, nt, kb, conv, c_chunks);
+  const long long groups = ((mt + CG - 1) / CG) * nt;
+  const int max_groups = svla_num_sms() / CG;
+  const int grid = static_cast<int>(groups < max_groups ? groups : max_groups) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, svla_gemm_tcgen05_kernel<BN, CG>, ta, tb, ep, mt, nt, kb, conv, c_chunks);
+  if (e != cudaSuccess) {
+    svla_set_error("svla_gemm_tcgen05<%d,%d>: launch failed: %s", BN, CG, cudaGetErrorString(e));
+    return -2;
+  }
   SVLA_LAUNCH_CHECK("svla_gemm_tcgen05");
   return 0;
 }
@@ -592,7 +556,8 @@ int pick_block_n(long long m_tiles, long long n) {
   int best = 128;
   for (int bn : {256, 128}) {
     const long long tiles = m_tiles * ((n + bn - 1) / bn);
-    const long long cost = ((tiles + sms - 1) / sms) * bn;
+    // time per tile ~ BN (MMA bound) but the 128-wide tile moves 1.5x the L2 bytes per FLOP: measured ~20% slower per FLOP
+    const long long cost = ((tiles + sms - 1) / sms) * bn * (bn == 128 ? 6 : 5);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
@@ -660,14 +625,23 @@ extern "C" int svla_gemm(const SvlaGemmArgs* g, void* stream) {
   if (conv) rc = encode_nhwc(&ta, g->a, g->nb, g->h, g->wd, g->c);
   else rc = encode_2d(&ta, g->a, static_cast<uint64_t>(g->k), static_cast<uint64_t>(g->m), static_cast<uint64_t>(g->lda), kBK, kBM);
   SVLA_REQUIRE(rc == 0, "svla_gemm: cuTensorMapEncodeTiled(A) failed (%d)", rc);
+  // impl: 0 = auto, 2 = force 1-CTA, 3 = force the 2-CTA (cta_group::2) kernel. Auto uses CTA pairs for large GEMMs.
+  const bool pair_ok = (bn == 128 || bn == 256) && m_tiles >= 2;
+  static const bool no_pair = getenv("SVLA_GEMM_NO_PAIR") != nullptr;      // debugging switch
+  const bool use_pair = pair_ok && (g->impl == 3 || (g->impl == 0 && !no_pair && m_tiles * n_tiles >= 2LL * svla_num_sms()));
   rc = encode_2d(&tb, g->w, static_cast<uint64_t>(g->k), static_cast<uint64_t>(g->n), static_cast<uint64_t>(g->ldw), kBK,
-                 static_cast<uint32_t>(bn));
+                 static_cast<uint32_t>(use_pair ? bn / 2 : bn));     // a CTA of a pair stages half of the W tile
   SVLA_REQUIRE(rc == 0, "svla_gemm: cuTensorMapEncodeTiled(W) failed (%d)", rc);
 
+  const int cv = conv ? 1 : 0;
+  if (use_pair) {
+    if (bn == 128) return launch_tc<128, 2>(ta, tb, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
+    return launch_tc<256, 2>(ta, tb, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
+  }
   switch (bn) {
-    case 32: return launch_tc<32>(ta, tb, ep, m_tiles, n_tiles, kblocks, conv ? 1 : 0, c_chunks, st);
-    case 64: return launch_tc<64>(ta, tb, ep, m_tiles, n_tiles, kblocks, conv ? 1 : 0, c_chunks, st);
-    case 128: return launch_tc<128>(ta, tb, ep, m_tiles, n_tiles, kblocks, conv ? 1 : 0, c_chunks, st);
-    default: return launch_tc<256>(ta, tb, ep, m_tiles, n_tiles, kblocks, conv ? 1 : 0, c_chunks, st);
+    case 32: return launch_tc<32, 1>(ta, tb, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
+    case 64: return launch_tc<64, 1>(ta, tb, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
+    case 128: return launch_tc<128, 1>(ta, tb, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
+    default: return launch_tc<256, 1>(ta, tb, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
   }
 }

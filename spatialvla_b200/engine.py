@@ -229,6 +229,13 @@ class SpatialVLAEngine:
             self.ops.gemm(a, w, out_f32=out, **kw)
         return out
 
+    def _skinny_partial(self, a, w, rows):
+        """Decode GEMM as split-K fp32 partial sums [splits, rows, N]; the consumer kernel adds the partials."""
+        N, K = w.shape
+        out = self.ops.empty((self.ops.skinny_splits(N, K), rows, N), F32)
+        self.ops.gemm_skinny(a, w, out_f32=out)
+        return out
+
     def _mha(self, qkv, B, S, nh, hd, scale, **kw):
         D = nh * hd
         ctx = self.ops.empty((B * S, D), BF16)
@@ -510,9 +517,13 @@ class SpatialVLAEngine:
         ops.rmsnorm_residual(x, w_pre=g["layers"][0]["ln_in"], eps=eps, out_bf16=h)
         q = ops.empty((M, nh * hd), BF16)
         ctx = ops.empty((M, nh * hd), BF16)
+        skinny = (S == 1 and M <= 128)          # decode step: weight-streaming swap-AB / split-K GEMMs
         for li, L_ in enumerate(g["layers"]):
-            qkv = self._lin(h, L_["wqkv"], M)
             kc, vc = cache["k"][li], cache["v"][li]
+            if skinny:
+                qkv = self._skinny_partial(h, L_["wqkv"], M)
+            else:
+                qkv = self._lin(h, L_["wqkv"], M)
             ops.rope_kv(qkv, q, kc, vc, batch=B, s=S, hq=nh, hkv=nkv, d=hd, smax=smax, pos0=pos0, theta=theta)
             if S == 1:
                 ops.decode_attention(q, kc, vc, ctx, batch=B, hq=nh, hkv=nkv, d=hd, smax=smax, ctx=pos0 + 1, scale=scale, softcap=cap)
@@ -521,10 +532,15 @@ class SpatialVLAEngine:
                 ops.attention(q, kc, vc, ctx, batch=B, hq=nh, hkv=nkv, sq=S, sk=pos0 + S, d=hd, q_strides=(S * nh * hd, nh * hd),
                               k_strides=kvs, v_strides=kvs, o_strides=(S * nh * hd, nh * hd), scale=scale, softcap=cap,
                               causal=not bidirectional)
-            br = self._lin(ctx, L_["wo"], M, F32)
+            br = self._skinny_partial(ctx, L_["wo"], M) if skinny else self._lin(ctx, L_["wo"], M, F32)
             ops.rmsnorm_residual(x, branch=br, w_post=L_["ln_post_attn"], w_pre=L_["ln_pre_ff"], eps=eps, out_bf16=h)
-            act = self._lin(h, L_["wgu"], M, geglu=True)
-            br = self._lin(act, L_["wd"], M, F32)
+            if skinny:
+                act = ops.empty((M, FF), BF16)
+                ops.gemm_skinny(h, L_["wgu"], out_bf16=act, geglu=True)
+                br = self._skinny_partial(act, L_["wd"], M)
+            else:
+                act = self._lin(h, L_["wgu"], M, geglu=True)
+                br = self._lin(act, L_["wd"], M, F32)
             nxt = g["layers"][li + 1]["ln_in"] if li + 1 < len(g["layers"]) else g["final"]
             ops.rmsnorm_residual(x, branch=br, w_post=L_["ln_post_ff"], w_pre=nxt, eps=eps, out_bf16=h)
         cache["len"] = pos0 + S
@@ -546,7 +562,10 @@ class SpatialVLAEngine:
         """h_rows: bf16 [B, H] view (any row stride) -> post-softcap fp32 logits over the action slice [B, n_act]"""
         cap = self.t["final_logit_softcapping"]
         lg = self.ops.empty((B, self.n_act), F32)
-        self.ops.gemm(h_rows, self.gem["head_act"], out_f32=lg, act=ACT_SOFTCAP if cap else ACT_NONE, act_param=cap or 0.0)
+        if B <= 128:
+            self.ops.gemm_skinny(h_rows, self.gem["head_act"], out_f32=lg, act=ACT_SOFTCAP if cap else ACT_NONE, act_param=cap or 0.0)
+        else:
+            self.ops.gemm(h_rows, self.gem["head_act"], out_f32=lg, act=ACT_SOFTCAP if cap else ACT_NONE, act_param=cap or 0.0)
         return lg
 
     def language_stage(self, ids, feats, n_new, forced_tokens=None, logs=None):

@@ -98,6 +98,29 @@ class CudaOps:
         g.impl = int(self.gemm_impl if impl is None else impl)
         L.check(self.lib.svla_gemm(C.byref(g), self._stream()), "svla_gemm")
 
+    # ---- G1s
+    def skinny_splits(self, n, k):
+        return int(self.lib.svla_gemm_skinny_splits(int(n), int(k)))
+
+    def gemm_skinny(self, x, w, *, out_bf16=None, out_f32=None, bias=None, act=ACT_NONE, act_param=0.0, alpha=1.0,
+                    geglu=False, splits=1):
+        """Decode GEMM (M <= 128). splits > 1 (or out_f32 with 3 dims) writes raw fp32 partial sums out_f32[s, M, N]."""
+        g = L.SvlaSkinnyArgs()
+        _req(x.dtype == BF16 and w.dtype == BF16 and x.dim() == 2 and x.stride(1) == 1, "gemm_skinny: bf16 row-major operands")
+        partial = out_f32 is not None and out_f32.dim() == 3
+        _req(partial or splits == 1, "gemm_skinny: split-K needs a [splits, M, N] fp32 output")
+        g.x, g.w, g.bias = _ptr(x), _ptr(w), _ptr(bias)
+        g.out_bf16, g.out_f32 = _ptr(out_bf16), _ptr(out_f32)
+        g.m, g.n, g.k = int(x.shape[0]), int(w.shape[0]), int(x.shape[1])
+        g.ldx, g.ldw = int(x.stride(0)), int(w.stride(0))
+        o = out_f32 if out_f32 is not None else out_bf16
+        g.ldo = int(o.stride(-2))
+        g.partial_stride = int(out_f32.stride(0)) if partial else 0
+        g.alpha, g.act_param, g.act = float(alpha), float(act_param), int(act)
+        g.flags = (1 if geglu else 0) | (2 if partial else 0)
+        g.splits = int(out_f32.shape[0]) if partial else 1
+        L.check(self.lib.svla_gemm_skinny(C.byref(g), self._stream()), "svla_gemm_skinny")
+
     # ---- G2 / G3
     def attention(self, q, k, v, out, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
                   scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0):
@@ -129,14 +152,25 @@ class CudaOps:
                                         _ptr(out_f32), int(relu), self._stream()), "svla_layernorm")
 
     def rmsnorm_residual(self, x, *, branch=None, w_post=None, w_pre=None, eps=1e-6, out_bf16=None):
+        """branch may be [rows, cols] or split-K partial sums [splits, rows, cols] (summed while read)."""
         _req(x.dtype == F32 and x.is_contiguous(), "rmsnorm_residual: x must be contiguous fp32")
         rows, cols = x.numel() // x.shape[-1], x.shape[-1]
+        npart, pstride = 1, 0
+        if branch is not None and branch.dim() == 3:
+            npart, pstride = int(branch.shape[0]), int(branch.stride(0))
         L.check(self.lib.svla_rmsnorm_residual(_ptr(x), _ptr(branch), _ptr(w_post), _ptr(w_pre), float(eps), rows,
-                                               cols, _ptr(out_bf16), self._stream()), "svla_rmsnorm_residual")
+                                               cols, _ptr(out_bf16), npart, pstride, self._stream()), "svla_rmsnorm_residual")
 
     def rope_kv(self, qkv, q_out, kcache, vcache, *, batch, s, hq, hkv, d, smax, pos0, theta):
+        """qkv: bf16 [tokens, W] or fp32 split-K partial sums [splits, tokens, W]."""
+        if qkv.dtype == F32:
+            _req(qkv.dim() == 3, "rope_kv: fp32 qkv must be [splits, tokens, W]")
+            L.check(self.lib.svla_rope_kv(None, _ptr(q_out), _ptr(kcache), _ptr(vcache), batch, s, hq, hkv, d, smax, pos0,
+                                          float(theta), _ptr(qkv), int(qkv.shape[0]), int(qkv.stride(0)), self._stream()),
+                    "svla_rope_kv")
+            return
         L.check(self.lib.svla_rope_kv(_ptr(qkv), _ptr(q_out), _ptr(kcache), _ptr(vcache), batch, s, hq, hkv, d, smax,
-                                      pos0, float(theta), self._stream()), "svla_rope_kv")
+                                      pos0, float(theta), None, 1, 0, self._stream()), "svla_rope_kv")
 
     def embed_tokens(self, ids, embed, spatial_embed, image_feats, x, *, image_token, act_lo, n_act, n_img,
                      normalizer, status):

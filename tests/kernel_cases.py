@@ -139,10 +139,87 @@ GEMM_CASES = [
     gemm_case("conv_96_c256", 0, 256, 0, conv=(2, 96, 96, 256)),
     gemm_case("conv_odd_20x28", 0, 128, 0, conv=(2, 20, 28, 64), bias=True),
 ]
+PAIR_CASES = [   # cta_group::2 kernel forced (impl=3) and the 1-CTA kernel forced (impl=2) on the same shapes
+    gemm_case("pair_basic_512", 512, 256, 128, impl=3),
+    gemm_case("pair_bn128_ragged_odd_tiles", 128 * 3 + 5, 200, 104, bias=True, act=ACT_GELU_TANH, out=("bf16", "f32"), block_n=128, impl=3),
+    gemm_case("pair_geglu", 1024, 1024, 256, geglu=True, impl=3),
+    gemm_case("pair_multiwave_accum", 20000, 1152, 576, out=("f32",), accumulate=True, bias=True, colscale=True, impl=3),
+    gemm_case("pair_long_k", 512, 512, 9216, impl=3),
+    gemm_case("pair_conv_96_c256", 0, 256, 0, conv=(2, 96, 96, 256), bias=True, res_bf16=True, out=("bf16", "relu"), impl=3),
+    gemm_case("pair_conv_odd_20x28", 0, 128, 0, conv=(3, 20, 28, 64), bias=True, impl=3),
+    gemm_case("single_forced_multiwave", 4096 + 77, 4304, 1152, bias=True, act=ACT_GELU_TANH, impl=2),
+]
 SIMT_CASES = [
     gemm_case("simt_ragged", 300, 200, 104, bias=True, act=ACT_GELU_TANH, out=("bf16", "f32"), impl=1),
     gemm_case("simt_conv", 0, 64, 0, conv=(2, 24, 24, 64), bias=True, act=ACT_RELU, impl=1),
     gemm_case("simt_geglu", 128, 256, 64, geglu=True, impl=1),
+]
+
+
+def skinny_case(name, M, N, K, *, mode="partial", splits=0, bias=False, act=ACT_NONE, act_param=0.0, ldx=None, seed=0):
+    def case(dev="cuda:0"):
+        g = _gen(seed)
+        x_full = _randn(g, M, ldx or K, dtype=BF16)
+        wt = (_randn(g, N, K) / K ** 0.5).to(BF16)
+        b = _randn(g, N) if bias else None
+
+        def run(ops, to):
+            X = to(x_full)[:, :K]
+            W = to(wt)
+            if mode == "partial":
+                S = splits or ops.skinny_splits(N, K) if ops.name == "cuda" else (splits or 1)
+                out = ops.zeros((S, M, N), F32)
+                ops.gemm_skinny(X, W, out_f32=out)
+                return (out.sum(0),)
+            if mode == "geglu":
+                out = ops.zeros((M, N // 2), BF16)
+                ops.gemm_skinny(X, W, out_bf16=out, geglu=True, bias=to(b))
+                return (out,)
+            of, ob = ops.zeros((M, N), F32), ops.zeros((M, N), BF16)
+            ops.gemm_skinny(X, W, out_f32=of, out_bf16=ob, bias=to(b), act=act, act_param=act_param)
+            return of, ob
+        c, r = _both(run, dev)
+        res = Result(name)
+        for i, (a_, b_) in enumerate(zip(c, r)):
+            res.add(f"out{i}", _err(a_, b_), TOL_BF16 if a_.dtype == BF16 else TOL_F32)
+        return res
+    case.__name__ = name
+    return case
+
+
+def skinny_consumers_case(dev="cuda:0"):
+    """split-K partial sums consumed by svla_rmsnorm_residual and svla_rope_kv (fp32 partial input)."""
+    g = _gen(21)
+    rows, cols, S = 64, 2304, 5
+    x, parts = _randn(g, rows, cols), _randn(g, S, rows, cols)
+    wp, wq = _randn(g, cols) * 0.1, _randn(g, cols) * 0.1
+    B, hq, hkv, d, smax, pos0 = 64, 8, 4, 256, 290, 281
+    qkvp = _randn(g, 3, B, (hq + 2 * hkv) * d)
+
+    def run(ops, to):
+        xx, ob = to(x), ops.zeros((rows, cols), BF16)
+        ops.rmsnorm_residual(xx, branch=to(parts), w_post=to(wp), w_pre=to(wq), eps=1e-6, out_bf16=ob)
+        q, kc, vc = ops.zeros((B, hq * d), BF16), ops.zeros((B, smax, hkv, d), BF16), ops.zeros((B, smax, hkv, d), BF16)
+        ops.rope_kv(to(qkvp), q, kc, vc, batch=B, s=1, hq=hq, hkv=hkv, d=d, smax=smax, pos0=pos0, theta=10000.0)
+        return xx, ob, q, kc, vc
+    c, r = _both(run, dev)
+    res = Result("skinny_consumers")
+    for nm, a_, b_, tol in zip(("x", "h", "q", "kcache", "vcache"), c, r, (1e-5, TOL_BF16, TOL_BF16, TOL_BF16, TOL_BF16)):
+        res.add(nm, _err(a_, b_), tol)
+    return res
+
+
+SKINNY_CASES = [
+    skinny_case("skinny_qkv_partial", 64, 4096, 2304),
+    skinny_case("skinny_o_partial_split8", 64, 2304, 2048, splits=8),
+    skinny_case("skinny_down_partial", 64, 2304, 9216),
+    skinny_case("skinny_geglu", 64, 18432, 2304, mode="geglu"),
+    skinny_case("skinny_head_softcap_tail", 64, 8194, 2304, mode="plain", act=ACT_SOFTCAP, act_param=30.0),
+    skinny_case("skinny_m1_bias", 1, 1000, 512, mode="plain", bias=True),
+    skinny_case("skinny_m7_strided_x", 7, 256, 128, mode="plain", ldx=128 * 5),
+    skinny_case("skinny_m100", 100, 384, 192, mode="plain", act=ACT_RELU),
+    skinny_case("skinny_m128_partial", 128, 512, 1024, splits=3),
+    skinny_consumers_case,
 ]
 
 
@@ -472,4 +549,4 @@ def tokenizer_case(dev="cuda:0"):
 FUSED_CASES = [layernorm_case, rmsnorm_case, rope_case, embed_case, argmax_case, patchify_case, assemble_concat_case,
                shuffle_im2col_case, bilinear_case, zoe_tail_case, ego3d_case, tokenizer_case]
 
-ALL_CASES = {c.__name__: c for c in (SIMT_CASES + GEMM_CASES + ATTN_CASES + FUSED_CASES)}
+ALL_CASES = {c.__name__: c for c in (SIMT_CASES + GEMM_CASES + PAIR_CASES + SKINNY_CASES + ATTN_CASES + FUSED_CASES)}

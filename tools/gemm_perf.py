@@ -31,11 +31,11 @@ for name, M, N, K in shapes:
     if only and only not in name: continue
     a = torch.randn(M, K, device=dev).to(BF16); w = torch.randn(N, K, device=dev).to(BF16)
     out = torch.empty(M, N, device=dev, dtype=BF16)
-    for bn in ([0] if M <= 64 else [128, 256]):
-        ms = timeit(lambda: ops.gemm(a, w, out_bf16=out, block_n=bn))
+    for bn, impl in ([(0, 0)] if M <= 64 else [(128, 2), (256, 2), (128, 3), (256, 3)]):
+        ms = timeit(lambda: ops.gemm(a, w, out_bf16=out, block_n=bn, impl=impl))
         tf = 2.0 * M * N * K / ms / 1e9
         gbs = (M * K + N * K + M * N) * 2 / ms / 1e6
-        rows.append({"name": name, "M": M, "N": N, "K": K, "bn": bn, "ms": round(ms, 4), "tflops": round(tf, 1), "gbs": round(gbs, 1)})
+        rows.append({"name": name, "M": M, "N": N, "K": K, "bn": bn, "cta_group": {0: "auto", 2: 1, 3: 2}[impl], "ms": round(ms, 4), "tflops": round(tf, 1), "gbs": round(gbs, 1)})
         print(rows[-1], flush=True)
     if name.startswith("cublas") or name in ("gemma_gateup", "beit_fc1"):
         ms = timeit(lambda: torch.matmul(a, w.t()))
@@ -47,15 +47,16 @@ for name, M, N in [("probe_148tiles_bn256", 128 * 148, 256), ("probe_1tile_bn256
         a = torch.randn(M, K, device=dev).to(BF16); w = torch.randn(N, K, device=dev).to(BF16)
         out = torch.empty(M, N, device=dev, dtype=BF16)
         bn = 128 if "bn128" in name else 256
-        ms = timeit(lambda: ops.gemm(a, w, out_bf16=out, block_n=bn))
+        ms = timeit(lambda: ops.gemm(a, w, out_bf16=out, block_n=bn, impl=2))
         print({"name": name, "K": K, "ms": round(ms, 4), "us_per_kblock": round(ms * 1e3 / (K / 64), 3), "tflops": round(2.0 * M * N * K / ms / 1e9, 1)}, flush=True)
 # conv
 for name, (nb, h, w_, c), N in [("fusion_conv_96", (64, 96, 96, 256), 256), ("fusion_conv_48", (64, 48, 48, 256), 256), ("rel_conv1_192", (64, 192, 192, 256), 128), ("rel_conv2_384", (64, 384, 384, 128), 32)]:
     if only and only not in name: continue
     x = torch.randn(nb, h, w_, c, device=dev).to(BF16); wt = torch.randn(N, 9 * c, device=dev).to(BF16)
     out = torch.empty(nb * h * w_, N, device=dev, dtype=BF16)
-    ms = timeit(lambda: ops.gemm(x, wt, conv=(nb, h, w_, c), out_bf16=out), iters=3)
-    print({"name": name, "ms": round(ms, 3), "tflops": round(2.0 * nb * h * w_ * N * 9 * c / ms / 1e9, 1)}, flush=True)
+    for impl in (2, 3):
+        ms = timeit(lambda: ops.gemm(x, wt, conv=(nb, h, w_, c), out_bf16=out, impl=impl), iters=3)
+        print({"name": name, "cta_group": impl - 1, "ms": round(ms, 3), "tflops": round(2.0 * nb * h * w_ * N * 9 * c / ms / 1e9, 1)}, flush=True)
 # attention
 for name, B, hq, hkv, S, d, kw in [("attn_siglip", 64, 16, 16, 256, 72, {}), ("attn_beit", 64, 16, 16, 577, 64, {"relpos": 24}), ("attn_gemma", 64, 8, 4, 278, 256, {"softcap": 50.0})]:
     if only and only not in name: continue

@@ -77,9 +77,16 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* sm, const __nv_bfloat16
   }
 }
 
-template <int DP>
+// MODE: bit0 = BEiT relative-position bias, bit1 = tanh soft-capping, bit2 = causal mask; 8 = decide at run time.
+// The specialised instances let the compiler drop the per-score feature checks (the score path, not the MMAs, bounds
+// this kernel at these short sequence lengths).
+template <int DP, int MODE>
 __global__ void __launch_bounds__(kAttnThreads)
 svla_flash_attn_kernel(const AttnP p) {
+  constexpr bool DYN = (MODE & 8) != 0;
+  const bool f_relpos = DYN ? (p.relpos != nullptr) : ((MODE & 1) != 0);
+  const bool f_softcap = DYN ? (p.softcap > 0.f) : ((MODE & 2) != 0);
+  const bool f_causal = DYN ? (p.causal != 0) : ((MODE & 4) != 0);
   constexpr int LD = DP + 8;
   constexpr int KT = DP / 16;     // k-steps of QK^T
   constexpr int NT = DP / 8;      // n-tiles of the output
@@ -88,7 +95,7 @@ svla_flash_attn_kernel(const AttnP p) {
   __nv_bfloat16* sK = sQ + kBQ * LD;           // 2 buffers
   __nv_bfloat16* sV = sK + 2 * 64 * LD;        // 2 buffers
   float* sTab = reinterpret_cast<float*>(sV + 2 * 64 * LD);
-  int* sKterm = reinterpret_cast<int*>(sTab + (p.relpos ? (2 * p.win - 1) * (2 * p.win - 1) + 3 : 0));   // [64]
+  int* sKterm = reinterpret_cast<int*>(sTab + (f_relpos ? (2 * p.win - 1) * (2 * p.win - 1) + 3 : 0));   // [64]
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kBQ;
   const int hk = h / (p.hq / p.hkv);
@@ -107,7 +114,7 @@ svla_flash_attn_kernel(const AttnP p) {
     }
   }
   int nrel = 0;
-  if (p.relpos) {
+  if (f_relpos) {
     nrel = (2 * p.win - 1) * (2 * p.win - 1) + 3;
     for (int i = threadIdx.x; i < nrel; i += kAttnThreads) sTab[i] = p.relpos[static_cast<long long>(i) * p.hq + h];
   }
@@ -128,14 +135,14 @@ svla_flash_attn_kernel(const AttnP p) {
   // BEiT relative-position index = qbase(query) - kterm(key) for patch tokens; CLS row/column are special-cased
   int qbase[2] = {0, 0};
   const int w2 = 2 * p.win - 1;
-  if (p.relpos) {
+  if (f_relpos) {
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int qi = qi0 + 8 * r;
       if (qi >= 1) qbase[r] = ((qi - 1) / p.win + p.win - 1) * w2 + (qi - 1) % p.win + p.win - 1;
     }
   }
-  const float inv_cap = p.softcap > 0.f ? 1.f / p.softcap : 0.f;
+  const float inv_cap = f_softcap ? 1.f / p.softcap : 0.f;
 
   for (int jt = 0; jt < n_kv_tiles; ++jt) {
     const int buf = jt & 1;
@@ -147,7 +154,7 @@ svla_flash_attn_kernel(const AttnP p) {
     } else {
       cp_async_wait<0>();
     }
-    if (p.relpos && threadIdx.x < 64) {
+    if (f_relpos && threadIdx.x < 64) {
       const int kj = jt * kBKV + threadIdx.x;
       sKterm[threadIdx.x] = kj >= 1 ? ((kj - 1) / p.win) * w2 + (kj - 1) % p.win : 0;
     }
@@ -173,6 +180,7 @@ svla_flash_attn_kernel(const AttnP p) {
       }
     }
     // ---- scale, softcap, bias, mask, online softmax
+    const bool need_mask = f_causal || (jt + 1) * kBKV > p.sk;      // block-uniform: only the ragged last tile / causal
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -182,15 +190,17 @@ svla_flash_attn_kernel(const AttnP p) {
         const int qi = qi0 + r * 8;
         const int kj = jt * kBKV + nt * 8 + 2 * t + (e & 1);
         float x = s[nt][e] * p.scale;
-        if (p.softcap > 0.f) x = p.softcap * tanh_small(x * inv_cap);
-        if (p.relpos && qi < p.sq && kj < p.sk) {
+        if (f_softcap) x = p.softcap * tanh_small(x * inv_cap);
+        if (f_relpos && qi < p.sq && kj < p.sk) {
           int idx = qbase[r] - sKterm[nt * 8 + 2 * t + (e & 1)];
           if (kj == 0) idx = nrel - 2;
           if (qi == 0) idx = (kj == 0) ? nrel - 1 : nrel - 3;
           x += sTab[idx];
         }
-        const bool masked = (kj >= p.sk) || (p.causal && kj > qi + causal_off);
-        x = masked ? -INFINITY : x;
+        if (need_mask) {
+          const bool masked = (kj >= p.sk) || (f_causal && kj > qi + causal_off);
+          x = masked ? -INFINITY : x;
+        }
         s[nt][e] = x;
         mx[r] = fmaxf(mx[r], x);
       }
@@ -262,14 +272,14 @@ svla_flash_attn_kernel(const AttnP p) {
   }
 }
 
-template <int DP>
+template <int DP, int MODE>
 int launch_attn(const AttnP& p, int batch, cudaStream_t st) {
   constexpr int LD = DP + 8;
   int nrel = p.relpos ? (2 * p.win - 1) * (2 * p.win - 1) + 3 : 0;
   const size_t smem = static_cast<size_t>(kBQ + 4 * 64) * LD * 2 + static_cast<size_t>(nrel) * 4 + 64 * 4 + 16;
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(svla_flash_attn_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(svla_flash_attn_kernel<DP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {
       svla_set_error("svla_attention: smem opt-in %zu failed: %s", smem, cudaGetErrorString(e));
       return -2;
@@ -277,7 +287,7 @@ int launch_attn(const AttnP& p, int batch, cudaStream_t st) {
     configured = smem;
   }
   dim3 grid((p.sq + kBQ - 1) / kBQ, p.hq, batch);
-  svla_flash_attn_kernel<DP><<<grid, kAttnThreads, smem, st>>>(p);
+  svla_flash_attn_kernel<DP, MODE><<<grid, kAttnThreads, smem, st>>>(p);
   SVLA_LAUNCH_CHECK("svla_flash_attn");
   return 0;
 }
@@ -416,11 +426,12 @@ extern "C" int svla_attention(const SvlaAttnArgs* a, void* stream) {
   p.o_bs = a->o_bs; p.o_ss = a->o_ss;
   p.hq = a->hq; p.hkv = a->hkv; p.sq = a->sq; p.sk = a->sk; p.d = a->d;
   p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.relpos = a->relpos_table; p.win = a->relpos_win;
-  if (a->d <= 32) return launch_attn<32>(p, a->batch, st);
-  if (a->d <= 64) return launch_attn<64>(p, a->batch, st);
-  if (a->d <= 80) return launch_attn<80>(p, a->batch, st);
-  if (a->d <= 128) return launch_attn<128>(p, a->batch, st);
-  return launch_attn<256>(p, a->batch, st);
+  const int mode = (p.relpos ? 1 : 0) | (p.softcap > 0.f ? 2 : 0) | (p.causal ? 4 : 0);
+  if (a->d <= 32) return launch_attn<32, 8>(p, a->batch, st);
+  if (a->d <= 64) return mode == 1 ? launch_attn<64, 1>(p, a->batch, st) : launch_attn<64, 8>(p, a->batch, st);
+  if (a->d <= 80) return mode == 0 ? launch_attn<80, 0>(p, a->batch, st) : launch_attn<80, 8>(p, a->batch, st);
+  if (a->d <= 128) return launch_attn<128, 8>(p, a->batch, st);
+  return mode == 2 ? launch_attn<256, 2>(p, a->batch, st) : launch_attn<256, 8>(p, a->batch, st);
 }
 
 extern "C" int svla_decode_attention(const void* q, const void* kcache, const void* vcache, void* out, int batch, int hq,

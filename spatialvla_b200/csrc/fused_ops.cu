@@ -136,25 +136,26 @@ __global__ void svla_rope_kv_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_
     return acc;
   };
   const long long cache_row = (static_cast<long long>(b) * smax + pos) * hkv * d;
-  const int rot_items = (hq + hkv) * half;
-  for (int i = threadIdx.x; i < rot_items; i += blockDim.x) {
-    const int hh = i / half, j = i - hh * half;
+  // one sincos per (token, frequency), reused by every q and k head (12x fewer transcendentals than per element)
+  for (int j = threadIdx.x; j < half; j += blockDim.x) {
     // inv_freq = 1 / theta^(2j/d) in fp32 exactly like torch: base ** (arange(0,d,2).float()/d)
     const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * j) / static_cast<float>(d));
     const float ang = fpos * inv_freq;
     float sn, cs;
     sincosf(ang, &sn, &cs);
-    const float x1 = load(hh * d + j);
-    const float x2 = load(hh * d + j + half);
-    const float o1 = x1 * cs - x2 * sn;
-    const float o2 = x2 * cs + x1 * sn;
-    if (hh < hq) {
-      q_out[tok * hq * d + hh * d + j] = __float2bfloat16(o1);
-      q_out[tok * hq * d + hh * d + j + half] = __float2bfloat16(o2);
-    } else {
-      const int kh = hh - hq;
-      kc[cache_row + kh * d + j] = __float2bfloat16(o1);
-      kc[cache_row + kh * d + j + half] = __float2bfloat16(o2);
+    for (int hh = 0; hh < hq + hkv; ++hh) {
+      const float x1 = load(hh * d + j);
+      const float x2 = load(hh * d + j + half);
+      const float o1 = x1 * cs - x2 * sn;
+      const float o2 = x2 * cs + x1 * sn;
+      if (hh < hq) {
+        q_out[tok * hq * d + hh * d + j] = __float2bfloat16(o1);
+        q_out[tok * hq * d + hh * d + j + half] = __float2bfloat16(o2);
+      } else {
+        const int kh = hh - hq;
+        kc[cache_row + kh * d + j] = __float2bfloat16(o1);
+        kc[cache_row + kh * d + j + half] = __float2bfloat16(o2);
+      }
     }
   }
   const long long voff = static_cast<long long>(hq + hkv) * d;
@@ -627,7 +628,7 @@ extern "C" int svla_rope_kv(const void* qkv, void* q_out, void* kcache, void* vc
                             void* stream) {
   SVLA_REQUIRE((qkv || qkv_f32) && q_out && kcache && vcache, "svla_rope_kv: null pointer");
   SVLA_REQUIRE(batch > 0 && s > 0 && (d % 2) == 0 && pos0 >= 0 && pos0 + s <= smax, "svla_rope_kv: bad geometry (pos0=%d s=%d smax=%d)", pos0, s, smax);
-  svla_rope_kv_kernel<<<static_cast<unsigned>(batch) * s, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  svla_rope_kv_kernel<<<static_cast<unsigned>(batch) * s, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(q_out), static_cast<__nv_bfloat16*>(kcache),
       static_cast<__nv_bfloat16*>(vcache), s, hq, hkv, d, smax, pos0, theta, qkv_f32, n_partials < 1 ? 1 : n_partials, partial_stride);
   SVLA_LAUNCH_CHECK("svla_rope_kv");

@@ -205,7 +205,8 @@ extern "C" int svla_gemm_skinny_splits(int64_t n, int64_t k) {
   int splits = svla_num_sms() / n_tiles;
   if (splits < 1) splits = 1;
   while (splits > 1 && (kblocks + splits - 1) / splits < 4) --splits;     // at least 4 K steps (64 KB of weights) per CTA
-  return splits;
+  const int per = (kblocks + splits - 1) / splits;
+  return (kblocks + per - 1) / per;                                        // no empty trailing split
 }
 
 extern "C" int svla_gemm_skinny(const SvlaSkinnyArgs* g, void* stream) {

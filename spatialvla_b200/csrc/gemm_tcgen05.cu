@@ -69,26 +69,117 @@ __device__ __forceinline__ float apply_act(float v, int act, float p) {
 
 // Epilogue of one 32-row x 32-column accumulator chunk owned by one warp (lane = tile row q*32 + lane).
 // Phase 1 (row owner): value = act(alpha*acc + bias) * colscale (or the GeGLU pair product) -> per-warp fp32
-// staging tile in shared memory (row stride 36 floats: conflict-free 128-bit accesses).
-// Phase 2 (coalesced): 8 (fp32) / 4 (GeGLU) lanes cover one row's 4-column groups, so every warp-wide global
-// access touches whole 32-byte sectors of 4 / 8 consecutive rows; residual loads, the fp32 read-modify-write and
-// the bf16 / relu stores all happen here.
+// staging tile in shared memory (row stride 36 floats: conflict-free 128-bit accesses).  bias / colscale are read
+// once per chunk (lane j loads column j) and broadcast with shuffles -- 32 predicated __ldg per thread cost ~13 us
+// per tile in the first version.
+// Phase 2 (coalesced): G = 8 (4 for GeGLU) lanes cover one row's 4-column groups, so every warp-wide global access
+// touches whole 32-byte sectors of 32/G consecutive rows.  All residual / accumulate loads of the G passes are
+// issued before the first use (memory-level parallelism; a load->add->store chain per pass made the fp32
+// read-modify-write epilogue latency bound), then the stores follow.
 constexpr int kStageLd = 36;
+
+template <int G, typename RowFn>
+__device__ __forceinline__ void epilogue_store(const EpiParams& ep, const float* stage, int lane, long long col0, long long ncols,
+                                               RowFn row_of) {
+  constexpr int RPP = 32 / G;                 // rows per pass
+  const bool accum = (ep.flags & SVLA_GEMM_ACCUM_F32) != 0;
+  const int cg = lane % G;
+  const long long col = col0 + 4 * cg;
+  if (col >= ncols) return;
+  const bool vec_ok = ((ep.ldo & 3) == 0) && (col + 4 <= ncols);
+  float4 x[G];
+  long long off[G], off32[G];
+  bool ok[G];
+#pragma unroll
+  for (int p = 0; p < G; ++p) {
+    const int r = p * RPP + lane / G;
+    long long grow = 0;
+    ok[p] = row_of(r, grow);
+    off[p] = grow * ep.ldo + col;
+    off32[p] = (ep.res_mod > 0 ? grow % ep.res_mod : grow) * ep.ldo + col;
+    x[p] = *reinterpret_cast<const float4*>(stage + r * kStageLd + 4 * cg);
+  }
+  if (vec_ok) {
+    if (ep.res_bf16) {
+      uint2 t[G];
+#pragma unroll
+      for (int p = 0; p < G; ++p) t[p] = ok[p] ? __ldg(reinterpret_cast<const uint2*>(ep.res_bf16 + off[p])) : make_uint2(0, 0);
+#pragma unroll
+      for (int p = 0; p < G; ++p) {
+        x[p].x += bf16_bits_to_float(t[p].x & 0xFFFFu); x[p].y += bf16_bits_to_float(t[p].x >> 16);
+        x[p].z += bf16_bits_to_float(t[p].y & 0xFFFFu); x[p].w += bf16_bits_to_float(t[p].y >> 16);
+      }
+    }
+    if (ep.res2_bf16) {
+      uint2 t[G];
+#pragma unroll
+      for (int p = 0; p < G; ++p) t[p] = ok[p] ? __ldg(reinterpret_cast<const uint2*>(ep.res2_bf16 + off[p])) : make_uint2(0, 0);
+#pragma unroll
+      for (int p = 0; p < G; ++p) {
+        x[p].x += bf16_bits_to_float(t[p].x & 0xFFFFu); x[p].y += bf16_bits_to_float(t[p].x >> 16);
+        x[p].z += bf16_bits_to_float(t[p].y & 0xFFFFu); x[p].w += bf16_bits_to_float(t[p].y >> 16);
+      }
+    }
+    if (ep.res_f32) {
+      float4 t[G];
+#pragma unroll
+      for (int p = 0; p < G; ++p) t[p] = ok[p] ? __ldg(reinterpret_cast<const float4*>(ep.res_f32 + off32[p])) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < G; ++p) { x[p].x += t[p].x; x[p].y += t[p].y; x[p].z += t[p].z; x[p].w += t[p].w; }
+    }
+    if (ep.out_f32 && accum) {
+      float4 t[G];
+#pragma unroll
+      for (int p = 0; p < G; ++p) t[p] = ok[p] ? *reinterpret_cast<const float4*>(ep.out_f32 + off[p]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < G; ++p) { x[p].x += t[p].x; x[p].y += t[p].y; x[p].z += t[p].z; x[p].w += t[p].w; }
+    }
+#pragma unroll
+    for (int p = 0; p < G; ++p) {
+      if (!ok[p]) continue;
+      if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + off[p]) = x[p];
+      if (ep.out_bf16)
+        *reinterpret_cast<uint2*>(ep.out_bf16 + off[p]) = make_uint2(pack_bf16x2(x[p].x, x[p].y), pack_bf16x2(x[p].z, x[p].w));
+      if (ep.out_relu)
+        *reinterpret_cast<uint2*>(ep.out_relu + off[p]) =
+            make_uint2(pack_bf16x2(fmaxf(x[p].x, 0.f), fmaxf(x[p].y, 0.f)), pack_bf16x2(fmaxf(x[p].z, 0.f), fmaxf(x[p].w, 0.f)));
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < G; ++p) {
+      if (!ok[p]) continue;
+      const float xv[4] = {x[p].x, x[p].y, x[p].z, x[p].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (col + e >= ncols) break;
+        float y = xv[e];
+        if (ep.res_bf16) y += __bfloat162float(ep.res_bf16[off[p] + e]);
+        if (ep.res2_bf16) y += __bfloat162float(ep.res2_bf16[off[p] + e]);
+        if (ep.res_f32) y += ep.res_f32[off32[p] + e];
+        if (ep.out_f32) {
+          if (accum) y += ep.out_f32[off[p] + e];
+          ep.out_f32[off[p] + e] = y;
+        }
+        if (ep.out_bf16) ep.out_bf16[off[p] + e] = __float2bfloat16(y);
+        if (ep.out_relu) ep.out_relu[off[p] + e] = __float2bfloat16(fmaxf(y, 0.f));
+      }
+    }
+  }
+}
 
 template <typename RowFn>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, const float (&acc)[32], float* stage, int lane,
                                                long long n0, RowFn row_of) {
   const bool geglu = (ep.flags & SVLA_GEMM_GEGLU) != 0;
-  const bool accum = (ep.flags & SVLA_GEMM_ACCUM_F32) != 0;
   // NOTE: the activation switch is hoisted out of the element loop on purpose -- a per-element switch inlines every
   // libm body 32 times (~100 KB of SASS) and turns the epilogue into an instruction-cache-miss-bound loop.
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = acc[j] * ep.alpha;
   if (ep.bias) {
+    const float b = (n0 + lane < ep.n) ? __ldg(ep.bias + n0 + lane) : 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (n0 + j < ep.n) v[j] += __ldg(ep.bias + n0 + j);
+    for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, b, j);
   }
   if (!geglu) {
     switch (ep.act) {
@@ -118,82 +209,23 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, const float 
     }
   }
   if (ep.colscale) {
+    const float c = (n0 + lane < ep.n) ? __ldg(ep.colscale + n0 + lane) : 1.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (n0 + j < ep.n) v[j] *= __ldg(ep.colscale + n0 + j);
+    for (int j = 0; j < 32; ++j) v[j] *= __shfl_sync(0xffffffffu, c, j);
   }
   float4* srow = reinterpret_cast<float4*>(stage + lane * kStageLd);
-  int groups;             // 4-column groups per staged row
-  long long col0, ncols;  // first output column of this chunk / number of valid output columns overall
   if (geglu) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       srow[j] = make_float4(gelu_tanh_fast(v[8 * j]) * v[8 * j + 1], gelu_tanh_fast(v[8 * j + 2]) * v[8 * j + 3],
                             gelu_tanh_fast(v[8 * j + 4]) * v[8 * j + 5], gelu_tanh_fast(v[8 * j + 6]) * v[8 * j + 7]);
-    groups = 4; col0 = n0 >> 1; ncols = ep.n >> 1;
+    __syncwarp();
+    epilogue_store<4>(ep, stage, lane, n0 >> 1, ep.n >> 1, row_of);
   } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    groups = 8; col0 = n0; ncols = ep.n;
-  }
-  __syncwarp();
-  const int rows_per_pass = 32 / groups;
-  const int cg = lane % groups;
-  const long long col = col0 + 4 * cg;
-  const bool vec_ok = ((ep.ldo & 3) == 0) && (col + 4 <= ncols);
-  if (col < ncols) {
-#pragma unroll 1
-    for (int pass = 0; pass < groups; ++pass) {
-      const int r = pass * rows_per_pass + lane / groups;
-      long long grow;
-      if (!row_of(r, grow)) continue;
-      const float4 sv = *reinterpret_cast<const float4*>(stage + r * kStageLd + 4 * cg);
-      float x[4] = {sv.x, sv.y, sv.z, sv.w};
-      const long long off = grow * ep.ldo + col;
-      const long long off_r32 = (ep.res_mod > 0 ? grow % ep.res_mod : grow) * ep.ldo + col;
-      if (vec_ok) {
-        if (ep.res_bf16) {
-          const uint2 t = __ldg(reinterpret_cast<const uint2*>(ep.res_bf16 + off));
-          x[0] += bf16_bits_to_float(t.x & 0xFFFFu); x[1] += bf16_bits_to_float(t.x >> 16);
-          x[2] += bf16_bits_to_float(t.y & 0xFFFFu); x[3] += bf16_bits_to_float(t.y >> 16);
-        }
-        if (ep.res2_bf16) {
-          const uint2 t = __ldg(reinterpret_cast<const uint2*>(ep.res2_bf16 + off));
-          x[0] += bf16_bits_to_float(t.x & 0xFFFFu); x[1] += bf16_bits_to_float(t.x >> 16);
-          x[2] += bf16_bits_to_float(t.y & 0xFFFFu); x[3] += bf16_bits_to_float(t.y >> 16);
-        }
-        if (ep.res_f32) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(ep.res_f32 + off_r32));
-          x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w;
-        }
-        if (ep.out_f32) {
-          float4* o4 = reinterpret_cast<float4*>(ep.out_f32 + off);
-          if (accum) {
-            const float4 t = *o4;
-            x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w;
-          }
-          *o4 = make_float4(x[0], x[1], x[2], x[3]);
-        }
-        if (ep.out_bf16)
-          *reinterpret_cast<uint2*>(ep.out_bf16 + off) = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
-        if (ep.out_relu)
-          *reinterpret_cast<uint2*>(ep.out_relu + off) =
-              make_uint2(pack_bf16x2(fmaxf(x[0], 0.f), fmaxf(x[1], 0.f)), pack_bf16x2(fmaxf(x[2], 0.f), fmaxf(x[3], 0.f)));
-      } else {
-        for (int e = 0; e < 4 && col + e < ncols; ++e) {
-          float y = x[e];
-          if (ep.res_bf16) y += __bfloat162float(ep.res_bf16[off + e]);
-          if (ep.res2_bf16) y += __bfloat162float(ep.res2_bf16[off + e]);
-          if (ep.res_f32) y += ep.res_f32[off_r32 + e];
-          if (ep.out_f32) {
-            if (accum) y += ep.out_f32[off + e];
-            ep.out_f32[off + e] = y;
-          }
-          if (ep.out_bf16) ep.out_bf16[off + e] = __float2bfloat16(y);
-          if (ep.out_relu) ep.out_relu[off + e] = __float2bfloat16(fmaxf(y, 0.f));
-        }
-      }
-    }
+    __syncwarp();
+    epilogue_store<8>(ep, stage, lane, n0, ep.n, row_of);
   }
   __syncwarp();
 }

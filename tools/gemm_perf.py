@@ -72,3 +72,57 @@ for name, B, hq, hkv, S, d, kw in [("attn_siglip", 64, 16, 16, 256, 72, {}), ("a
         fn = lambda: ops.attention(q, kc, vc, out, batch=B, hq=hq, hkv=hkv, sq=S, sk=S, d=d, q_strides=(S * D, D), k_strides=kvs, v_strides=kvs, o_strides=(S * D, D), scale=1 / 16, softcap=50.0)
     ms = timeit(fn)
     print({"name": name, "ms": round(ms, 3), "tflops": round(4.0 * B * hq * S * S * d / ms / 1e9, 1)}, flush=True)
+
+# ---- epilogue variants on the BEiT fc1 shape
+from spatialvla_b200._lib import ACT_GELU_ERF, ACT_GELU_TANH, ACT_RELU
+if not only or "epi" in only:
+    M, N, K = 36928, 4096, 1024
+    a = torch.randn(M, K, device=dev).to(BF16); w = (torch.randn(N, K, device=dev) / 32).to(BF16)
+    bias = torch.randn(N, device=dev); cs = torch.rand(N, device=dev)
+    outb = torch.empty(M, N, device=dev, dtype=BF16); outf = torch.zeros(M, N, device=dev, dtype=F32)
+    for tag, kw in [("plain_bf16", dict(out_bf16=outb)), ("bias", dict(out_bf16=outb, bias=bias)), ("erf", dict(out_bf16=outb, act=ACT_GELU_ERF)),
+                    ("bias_erf", dict(out_bf16=outb, bias=bias, act=ACT_GELU_ERF)), ("bias_tanh", dict(out_bf16=outb, bias=bias, act=ACT_GELU_TANH)),
+                    ("relu", dict(out_bf16=outb, act=ACT_RELU)), ("f32_out", dict(out_f32=outf)), ("f32_accum_colscale", dict(out_f32=outf, accumulate=True, colscale=cs, bias=bias))]:
+        ms = timeit(lambda: ops.gemm(a, w, block_n=256, **kw))
+        print({"name": "epi_" + tag, "ms": round(ms, 4), "tflops": round(2.0 * M * N * K / ms / 1e9, 1)}, flush=True)
+
+# ---- decode kernels measured from CUDA-graph replays (true GPU time, no host launch gaps)
+def graph_time(fn, reps=20):
+    fn(); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps): fn()
+    g.replay(); torch.cuda.synchronize()
+    flush.zero_()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(); g.replay(); e.record(); torch.cuda.synchronize()
+    return s.elapsed_time(e) / reps
+
+if not only or "dec" in only:
+    for name, N, K, geglu in [("dec_qkv", 4096, 2304, False), ("dec_o", 2304, 2048, False), ("dec_gateup", 18432, 2304, True), ("dec_down", 2304, 9216, False), ("dec_head", 8194, 2304, False)]:
+        x = torch.randn(64, K, device=dev).to(BF16)
+        ws = [(torch.randn(N, K, device=dev) / 48).to(BF16) for _ in range(20)]      # distinct weights per call: no L2 reuse
+        S = ops.skinny_splits(N, K)
+        it = [0]
+        if geglu:
+            out = torch.empty(64, N // 2, device=dev, dtype=BF16)
+            def fn():
+                ops.gemm_skinny(x, ws[it[0] % 20], out_bf16=out, geglu=True); it[0] += 1
+        else:
+            out = torch.empty(S, 64, N, device=dev, dtype=F32)
+            def fn():
+                ops.gemm_skinny(x, ws[it[0] % 20], out_f32=out); it[0] += 1
+        us = graph_time(fn) * 1e3
+        print({"name": name + "_skinny_graph", "splits": S, "us": round(us, 2), "gbs": round(N * K * 2 / us / 1e3, 1)}, flush=True)
+    q = torch.randn(64, 2048, device=dev).to(BF16); kc = torch.randn(20, 64, 290, 4, 256, device=dev).to(BF16); vc = torch.randn_like(kc); o = torch.empty_like(q)
+    it = [0]
+    def fn():
+        ops.decode_attention(q, kc[it[0] % 20], vc[it[0] % 20], o, batch=64, hq=8, hkv=4, d=256, smax=290, ctx=285, scale=1 / 16, softcap=50.0); it[0] += 1
+    us = graph_time(fn) * 1e3
+    print({"name": "decode_attention_graph", "us": round(us, 2), "gbs": round(64 * 285 * 4 * 256 * 2 * 2 / us / 1e3, 1)}, flush=True)
+    xs = torch.randn(64, 2304, device=dev); br = torch.randn(8, 64, 2304, device=dev); w1 = torch.randn(2304, device=dev); h = torch.empty(64, 2304, device=dev, dtype=BF16)
+    us = graph_time(lambda: ops.rmsnorm_residual(xs, branch=br, w_post=w1, w_pre=w1, out_bf16=h)) * 1e3
+    print({"name": "rmsnorm_residual_decode_graph", "us": round(us, 2)}, flush=True)
+    qkvp = torch.randn(4, 64, 4096, device=dev); qq = torch.empty(64, 2048, device=dev, dtype=BF16)
+    us = graph_time(lambda: ops.rope_kv(qkvp, qq, kc[0], vc[0], batch=64, s=1, hq=8, hkv=4, d=256, smax=290, pos0=280, theta=10000.0)) * 1e3
+    print({"name": "rope_kv_decode_graph", "us": round(us, 2)}, flush=True)

@@ -298,7 +298,7 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
 #pragma unroll
   for (int u = 0; u < 4; ++u) { f[2 * u] = bf16_bits_to_float(w[u] & 0xFFFFu); f[2 * u + 1] = bf16_bits_to_float(w[u] >> 16); }
 }
-constexpr int kDecThreads = 256;
+constexpr int kDecThreads = 512;     // 16 warps: 4 keys in flight per warp -> 5 dependent DRAM round trips for 285 keys
 constexpr int kMaxGroup = 4;
 
 template <int D>
@@ -322,7 +322,7 @@ svla_decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16
   const long long row_stride = static_cast<long long>(hkv) * D;
   // scores: one warp per key, each lane covers D/32 contiguous dims; 4 keys in flight per warp (memory-level parallelism)
   constexpr int PER = D / 32;
-  constexpr int KB = 4;
+  constexpr int KB = 8;
   static_assert(PER == 8, "one 16-byte load per lane per key");
   for (int j0 = warp * KB; j0 < ctx; j0 += NW * KB) {
     uint4 raw[KB];

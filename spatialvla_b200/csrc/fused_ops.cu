@@ -136,14 +136,17 @@ __global__ void svla_rope_kv_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_
     return acc;
   };
   const long long cache_row = (static_cast<long long>(b) * smax + pos) * hkv * d;
-  // one sincos per (token, frequency), reused by every q and k head (12x fewer transcendentals than per element)
-  for (int j = threadIdx.x; j < half; j += blockDim.x) {
+  // thread = (frequency j, head lane): one sincos per thread reused across its heads; heads are spread over
+  // blockDim.x / half lanes so that the loads of different heads are independent (decode: 64 tokens only)
+  const int hlanes = max(1, static_cast<int>(blockDim.x) / half);
+  const int j = threadIdx.x % half, hl = threadIdx.x / half;
+  if (hl < hlanes) {
     // inv_freq = 1 / theta^(2j/d) in fp32 exactly like torch: base ** (arange(0,d,2).float()/d)
     const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * j) / static_cast<float>(d));
     const float ang = fpos * inv_freq;
     float sn, cs;
     sincosf(ang, &sn, &cs);
-    for (int hh = 0; hh < hq + hkv; ++hh) {
+    for (int hh = hl; hh < hq + hkv; hh += hlanes) {
       const float x1 = load(hh * d + j);
       const float x2 = load(hh * d + j + half);
       const float o1 = x1 * cs - x2 * sn;
@@ -486,31 +489,46 @@ svla_zoe_depth_tail_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloa
   for (int i = threadIdx.x; i < nh; i += blockDim.x) s_b1[i] = b1[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  // each warp walks a contiguous run of pixels (row-major) so that coordinates advance incrementally and the
+  // bilinear taps of neighbouring pixels hit L1
   const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
-  for (long long pix = warp_global; pix < npix; pix += nwarps) {
-    const int ox = static_cast<int>(pix % ow);
-    const int oy = static_cast<int>((pix / ow) % oh);
-    const long long b = pix / (static_cast<long long>(ow) * oh);
-    const Bilin s = make_bilin(oy, ox, h, w, oh, ow);
+  const long long per_warp = (npix + nwarps - 1) / nwarps;
+  const long long pix_begin = warp_global * per_warp;
+  const long long pix_end = pix_begin + per_warp < npix ? pix_begin + per_warp : npix;
+  const float ry = (oh > 1) ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) : 0.f;
+  const float rx = (ow > 1) ? static_cast<float>(w - 1) / static_cast<float>(ow - 1) : 0.f;
+  int ox = pix_begin < npix ? static_cast<int>(pix_begin % ow) : 0;
+  int oy = pix_begin < npix ? static_cast<int>((pix_begin / ow) % oh) : 0;
+  long long b = pix_begin < npix ? pix_begin / (static_cast<long long>(ow) * oh) : 0;
+  for (long long pix = pix_begin; pix < pix_end; ++pix) {
+    Bilin s;
+    {
+      const float sy = ry * oy, sx = rx * ox;
+      s.y0 = min(static_cast<int>(sy), h - 1); s.x0 = min(static_cast<int>(sx), w - 1);
+      s.y1 = min(s.y0 + 1, h - 1); s.x1 = min(s.x0 + 1, w - 1);
+      s.ly = sy - s.y0; s.lx = sx - s.x0;
+    }
+    const long long b_cur = b;
+    if (++ox == ow) { ox = 0; if (++oy == oh) { oy = 0; ++b; } }
     // hidden = gelu(W_a*last + up(W_b*emb) + b1), then 4 outputs
     float o4[4] = {0.f, 0.f, 0.f, 0.f};
-    const __nv_bfloat16* eb = e + b * h * w * nh;
+    const __nv_bfloat16* eb = e + b_cur * h * w * nh;
     for (int ch = lane; ch < nh; ch += 32) {
-      const float hv = gelu_erf_f(__bfloat162float(t[pix * nh + ch]) + bilin_bf16(eb, s, w, nh, ch) + s_b1[ch]);
+      const float hv = gelu_erf_fast(__bfloat162float(t[pix * nh + ch]) + bilin_bf16(eb, s, w, nh, ch) + s_b1[ch]);
 #pragma unroll
       for (int q = 0; q < 4; ++q) o4[q] += s_w2[q * nh + ch] * hv;
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) o4[q] = softplus_f(warp_sum(o4[q]) + b2[q]);
+    for (int q = 0; q < 4; ++q) o4[q] = softplus_fast(warp_sum(o4[q]) + b2[q]);
     const float p0 = o4[0] + 1e-4f, p1 = o4[1] + 1e-4f, t0 = o4[2] + 1e-4f, t1 = o4[3] + 1e-4f;
     const float prob = p0 / (p0 + p1);
     const float temp = (max_temp - min_temp) * (t0 / (t0 + t1)) + min_temp;
-    const float lp = logf(fminf(fmaxf(prob, 1e-4f), 1.f)), lq = logf(fminf(fmaxf(1.f - prob, 1e-4f), 1.f));
+    const float lp = __logf(fminf(fmaxf(prob, 1e-4f), 1.f)), lq = __logf(fminf(fmaxf(1.f - prob, 1e-4f), 1.f));
     // y_k = log C(K-1, k) (Stirling form with the reference's eps) + k log p + (K-1-k) log(1-p)
     float y[2], c[2];
     float mx = -INFINITY;
-    const float* bb = bins + b * h * w * nbins;
+    const float* bb = bins + b_cur * h * w * nbins;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int k = lane + 32 * r;
@@ -524,7 +542,7 @@ svla_zoe_depth_tail_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloa
     float se = 0.f, sc = 0.f;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      const float ex = (y[r] == -INFINITY) ? 0.f : expf(y[r] - mx);
+      const float ex = (y[r] == -INFINITY) ? 0.f : __expf(y[r] - mx);
       se += ex; sc += ex * c[r];
     }
     se = warp_sum(se); sc = warp_sum(sc);
@@ -628,7 +646,9 @@ extern "C" int svla_rope_kv(const void* qkv, void* q_out, void* kcache, void* vc
                             void* stream) {
   SVLA_REQUIRE((qkv || qkv_f32) && q_out && kcache && vcache, "svla_rope_kv: null pointer");
   SVLA_REQUIRE(batch > 0 && s > 0 && (d % 2) == 0 && pos0 >= 0 && pos0 + s <= smax, "svla_rope_kv: bad geometry (pos0=%d s=%d smax=%d)", pos0, s, smax);
-  svla_rope_kv_kernel<<<static_cast<unsigned>(batch) * s, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  SVLA_REQUIRE(d / 2 <= 512, "svla_rope_kv: head dim too large");
+  const int rope_threads = (d / 2) * ((batch * s <= 1024) ? max(1, 512 / (d / 2)) : 1);     // decode: spread heads over lanes
+  svla_rope_kv_kernel<<<static_cast<unsigned>(batch) * s, rope_threads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(q_out), static_cast<__nv_bfloat16*>(kcache),
       static_cast<__nv_bfloat16*>(vcache), s, hq, hkv, d, smax, pos0, theta, qkv_f32, n_partials < 1 ? 1 : n_partials, partial_stride);
   SVLA_LAUNCH_CHECK("svla_rope_kv");

@@ -22,7 +22,8 @@ using namespace svla_ptx;
 constexpr int kBM = 128;
 constexpr int kBK = 64;             // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;          // two epilogue warps per TMEM lane group, each owns half of the tile's columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kConvTileW = 16, kConvTileH = 8;
 
 // CG = CTAs per MMA (tcgen05 cta_group): 1 = one CTA computes a 128 x BN tile; 2 = a CTA pair (cluster of 2 along M)
@@ -34,7 +35,7 @@ template <int BN, int CG = 1> struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kStageBytes >= 49152) ? 4 : ((kStageBytes >= 32768) ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kStagingBytes = 4 * 32 * 36 * 4;     // per-epilogue-warp fp32 transpose tile
+  static constexpr int kStagingBytes = kEpiWarps * 32 * 20 * 4;     // per-epilogue-warp fp32 transpose tile (32 rows x 16 cols)
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes;
 };
 
@@ -67,112 +68,107 @@ __device__ __forceinline__ float apply_act(float v, int act, float p) {
   }
 }
 
-// Epilogue of one 32-row x 32-column accumulator chunk owned by one warp (lane = tile row q*32 + lane).
-// Phase 1 (row owner): value = act(alpha*acc + bias) * colscale (or the GeGLU pair product) -> per-warp fp32
-// staging tile in shared memory (row stride 36 floats: conflict-free 128-bit accesses).  bias / colscale are read
-// once per chunk (lane j loads column j) and broadcast with shuffles -- 32 predicated __ldg per thread cost ~13 us
-// per tile in the first version.
-// Phase 2 (coalesced): G = 8 (4 for GeGLU) lanes cover one row's 4-column groups, so every warp-wide global access
-// touches whole 32-byte sectors of 32/G consecutive rows.  All residual / accumulate loads of the G passes are
-// issued before the first use (memory-level parallelism; a load->add->store chain per pass made the fp32
-// read-modify-write epilogue latency bound), then the stores follow.
-constexpr int kStageLd = 36;
+// Epilogue.  Each of the 8 epilogue warps owns 32 accumulator rows (its TMEM lane group) x half of the tile's columns.
+// Per 32-column TMEM load:
+//   phase 1 (row owner, lane = row): value = act(alpha*acc + bias) * colscale (or the GeGLU pair product).  bias and
+//     colscale are read once per chunk (lane j loads column j) and broadcast with shuffles; the activation switch is
+//     hoisted out of the element loop (a per-element switch inlined every libm body 32x -> I-cache-miss bound).
+//   staging: 16 output columns at a time through a per-warp fp32 tile in shared memory (row stride 20 floats).
+//   phase 2 (coalesced): 4 lanes cover one row's 16 columns, 8 rows per pass, 4 passes; all residual / accumulate
+//     loads of the 4 passes are issued before the first use, then the stores follow.
+// Row offsets / validity of the 4 passes do not depend on the column, so they are computed ONCE per tile (RowSet):
+// the first versions recomputed 64-bit row math per pass per chunk and ran at ~800 instructions per chunk.
+constexpr int kStageLd = 20;
+constexpr int kPasses = 4;
 
-template <int G, typename RowFn>
-__device__ __forceinline__ void epilogue_store(const EpiParams& ep, const float* stage, int lane, long long col0, long long ncols,
-                                               RowFn row_of) {
-  constexpr int RPP = 32 / G;                 // rows per pass
+struct RowSet {
+  unsigned off[kPasses];      // grow * ldo
+  unsigned off32[kPasses];    // (grow % res_mod) * ldo for the broadcast fp32 residual
+  bool ok[kPasses];
+};
+
+__device__ __forceinline__ void epilogue_store16(const EpiParams& ep, const float* stage, int lane, const RowSet& rs,
+                                                 long long col0, long long ncols) {
   const bool accum = (ep.flags & SVLA_GEMM_ACCUM_F32) != 0;
-  const int cg = lane % G;
+  const int cg = lane & 3;
   const long long col = col0 + 4 * cg;
   if (col >= ncols) return;
   const bool vec_ok = ((ep.ldo & 3) == 0) && (col + 4 <= ncols);
-  float4 x[G];
-  long long off[G], off32[G];
-  bool ok[G];
+  float4 x[kPasses];
 #pragma unroll
-  for (int p = 0; p < G; ++p) {
-    const int r = p * RPP + lane / G;
-    long long grow = 0;
-    ok[p] = row_of(r, grow);
-    off[p] = grow * ep.ldo + col;
-    off32[p] = (ep.res_mod > 0 ? grow % ep.res_mod : grow) * ep.ldo + col;
-    x[p] = *reinterpret_cast<const float4*>(stage + r * kStageLd + 4 * cg);
-  }
+  for (int p = 0; p < kPasses; ++p)
+    x[p] = *reinterpret_cast<const float4*>(stage + (p * 8 + (lane >> 2)) * kStageLd + 4 * cg);
   if (vec_ok) {
     if (ep.res_bf16) {
-      uint2 t[G];
+      uint2 t[kPasses];
 #pragma unroll
-      for (int p = 0; p < G; ++p) t[p] = ok[p] ? __ldg(reinterpret_cast<const uint2*>(ep.res_bf16 + off[p])) : make_uint2(0, 0);
+      for (int p = 0; p < kPasses; ++p) t[p] = rs.ok[p] ? __ldg(reinterpret_cast<const uint2*>(ep.res_bf16 + rs.off[p] + col)) : make_uint2(0, 0);
 #pragma unroll
-      for (int p = 0; p < G; ++p) {
+      for (int p = 0; p < kPasses; ++p) {
         x[p].x += bf16_bits_to_float(t[p].x & 0xFFFFu); x[p].y += bf16_bits_to_float(t[p].x >> 16);
         x[p].z += bf16_bits_to_float(t[p].y & 0xFFFFu); x[p].w += bf16_bits_to_float(t[p].y >> 16);
       }
     }
     if (ep.res2_bf16) {
-      uint2 t[G];
+      uint2 t[kPasses];
 #pragma unroll
-      for (int p = 0; p < G; ++p) t[p] = ok[p] ? __ldg(reinterpret_cast<const uint2*>(ep.res2_bf16 + off[p])) : make_uint2(0, 0);
+      for (int p = 0; p < kPasses; ++p) t[p] = rs.ok[p] ? __ldg(reinterpret_cast<const uint2*>(ep.res2_bf16 + rs.off[p] + col)) : make_uint2(0, 0);
 #pragma unroll
-      for (int p = 0; p < G; ++p) {
+      for (int p = 0; p < kPasses; ++p) {
         x[p].x += bf16_bits_to_float(t[p].x & 0xFFFFu); x[p].y += bf16_bits_to_float(t[p].x >> 16);
         x[p].z += bf16_bits_to_float(t[p].y & 0xFFFFu); x[p].w += bf16_bits_to_float(t[p].y >> 16);
       }
     }
     if (ep.res_f32) {
-      float4 t[G];
+      float4 t[kPasses];
 #pragma unroll
-      for (int p = 0; p < G; ++p) t[p] = ok[p] ? __ldg(reinterpret_cast<const float4*>(ep.res_f32 + off32[p])) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int p = 0; p < kPasses; ++p) t[p] = rs.ok[p] ? __ldg(reinterpret_cast<const float4*>(ep.res_f32 + rs.off32[p] + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int p = 0; p < G; ++p) { x[p].x += t[p].x; x[p].y += t[p].y; x[p].z += t[p].z; x[p].w += t[p].w; }
+      for (int p = 0; p < kPasses; ++p) { x[p].x += t[p].x; x[p].y += t[p].y; x[p].z += t[p].z; x[p].w += t[p].w; }
     }
     if (ep.out_f32 && accum) {
-      float4 t[G];
+      float4 t[kPasses];
 #pragma unroll
-      for (int p = 0; p < G; ++p) t[p] = ok[p] ? *reinterpret_cast<const float4*>(ep.out_f32 + off[p]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int p = 0; p < kPasses; ++p) t[p] = rs.ok[p] ? *reinterpret_cast<const float4*>(ep.out_f32 + rs.off[p] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int p = 0; p < G; ++p) { x[p].x += t[p].x; x[p].y += t[p].y; x[p].z += t[p].z; x[p].w += t[p].w; }
+      for (int p = 0; p < kPasses; ++p) { x[p].x += t[p].x; x[p].y += t[p].y; x[p].z += t[p].z; x[p].w += t[p].w; }
     }
 #pragma unroll
-    for (int p = 0; p < G; ++p) {
-      if (!ok[p]) continue;
-      if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + off[p]) = x[p];
+    for (int p = 0; p < kPasses; ++p) {
+      if (!rs.ok[p]) continue;
+      if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + rs.off[p] + col) = x[p];
       if (ep.out_bf16)
-        *reinterpret_cast<uint2*>(ep.out_bf16 + off[p]) = make_uint2(pack_bf16x2(x[p].x, x[p].y), pack_bf16x2(x[p].z, x[p].w));
+        *reinterpret_cast<uint2*>(ep.out_bf16 + rs.off[p] + col) = make_uint2(pack_bf16x2(x[p].x, x[p].y), pack_bf16x2(x[p].z, x[p].w));
       if (ep.out_relu)
-        *reinterpret_cast<uint2*>(ep.out_relu + off[p]) =
+        *reinterpret_cast<uint2*>(ep.out_relu + rs.off[p] + col) =
             make_uint2(pack_bf16x2(fmaxf(x[p].x, 0.f), fmaxf(x[p].y, 0.f)), pack_bf16x2(fmaxf(x[p].z, 0.f), fmaxf(x[p].w, 0.f)));
     }
   } else {
 #pragma unroll
-    for (int p = 0; p < G; ++p) {
-      if (!ok[p]) continue;
+    for (int p = 0; p < kPasses; ++p) {
+      if (!rs.ok[p]) continue;
       const float xv[4] = {x[p].x, x[p].y, x[p].z, x[p].w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         if (col + e >= ncols) break;
         float y = xv[e];
-        if (ep.res_bf16) y += __bfloat162float(ep.res_bf16[off[p] + e]);
-        if (ep.res2_bf16) y += __bfloat162float(ep.res2_bf16[off[p] + e]);
-        if (ep.res_f32) y += ep.res_f32[off32[p] + e];
+        if (ep.res_bf16) y += __bfloat162float(ep.res_bf16[rs.off[p] + col + e]);
+        if (ep.res2_bf16) y += __bfloat162float(ep.res2_bf16[rs.off[p] + col + e]);
+        if (ep.res_f32) y += ep.res_f32[rs.off32[p] + col + e];
         if (ep.out_f32) {
-          if (accum) y += ep.out_f32[off[p] + e];
-          ep.out_f32[off[p] + e] = y;
+          if (accum) y += ep.out_f32[rs.off[p] + col + e];
+          ep.out_f32[rs.off[p] + col + e] = y;
         }
-        if (ep.out_bf16) ep.out_bf16[off[p] + e] = __float2bfloat16(y);
-        if (ep.out_relu) ep.out_relu[off[p] + e] = __float2bfloat16(fmaxf(y, 0.f));
+        if (ep.out_bf16) ep.out_bf16[rs.off[p] + col + e] = __float2bfloat16(y);
+        if (ep.out_relu) ep.out_relu[rs.off[p] + col + e] = __float2bfloat16(fmaxf(y, 0.f));
       }
     }
   }
 }
 
-template <typename RowFn>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, const float (&acc)[32], float* stage, int lane,
-                                               long long n0, RowFn row_of) {
+                                               long long n0, const RowSet& rs) {
   const bool geglu = (ep.flags & SVLA_GEMM_GEGLU) != 0;
-  // NOTE: the activation switch is hoisted out of the element loop on purpose -- a per-element switch inlines every
-  // libm body 32 times (~100 KB of SASS) and turns the epilogue into an instruction-cache-miss-bound loop.
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = acc[j] * ep.alpha;
@@ -220,14 +216,19 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, const float 
       srow[j] = make_float4(gelu_tanh_fast(v[8 * j]) * v[8 * j + 1], gelu_tanh_fast(v[8 * j + 2]) * v[8 * j + 3],
                             gelu_tanh_fast(v[8 * j + 4]) * v[8 * j + 5], gelu_tanh_fast(v[8 * j + 6]) * v[8 * j + 7]);
     __syncwarp();
-    epilogue_store<4>(ep, stage, lane, n0 >> 1, ep.n >> 1, row_of);
+    epilogue_store16(ep, stage, lane, rs, n0 >> 1, ep.n >> 1);
+    __syncwarp();
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    __syncwarp();
-    epilogue_store<8>(ep, stage, lane, n0, ep.n, row_of);
+    for (int hlf = 0; hlf < 2; ++hlf) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        srow[j] = make_float4(v[16 * hlf + 4 * j], v[16 * hlf + 4 * j + 1], v[16 * hlf + 4 * j + 2], v[16 * hlf + 4 * j + 3]);
+      __syncwarp();
+      epilogue_store16(ep, stage, lane, rs, n0 + 16 * hlf, ep.n);
+      __syncwarp();
+    }
   }
-  __syncwarp();
 }
 
 // Global output row of tile row r (and validity) in linear / conv mode.
@@ -297,8 +298,8 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     }
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 4 * CG);     // 4 epilogue warps of every CTA of the pair arrive on the leader's barrier
-    mbar_init(&tmem_empty[1], 4 * CG);
+    mbar_init(&tmem_empty[0], kEpiWarps * CG);     // every epilogue warp of every CTA of the pair arrives on the leader's barrier
+    mbar_init(&tmem_empty[1], kEpiWarps * CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<C::kTmemCols, CG>(tmem_ptr_smem);
@@ -393,31 +394,40 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       }
     }
   } else {
-    // ===================================================== epilogue warps 2..5 (TMEM lane group = warp % 4)
+    // ===================================================== epilogue warps 2..9 (TMEM lane group = warp % 4)
     const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;                    // which half of the tile's columns this warp drains
+    constexpr int kColsPerWarp = BN >= 64 ? BN / 2 : BN;
     uint32_t it = 0;
+    float* stage = staging + (warp - 2) * 32 * kStageLd;
     for (long long tile = first; tile < num_tiles; tile += step, ++it) {
       long long mg, n_tile;
       raster_tile(tile, num_m_groups, num_n_tiles, mg, n_tile);
       const long long m_tile = mg * CG + cta_rank;
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+      RowSet rs;
+#pragma unroll
+      for (int p = 0; p < kPasses; ++p) {
+        long long grow = 0;
+        rs.ok[p] = m_tile < num_m_tiles && tile_row_to_global(ep, conv != 0, m_tile, q * 32 + p * 8 + (lane >> 2), grow);
+        rs.off[p] = static_cast<unsigned>(grow * ep.ldo);
+        rs.off32[p] = static_cast<unsigned>((ep.res_mod > 0 ? grow % ep.res_mod : grow) * ep.ldo);
+      }
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      float* stage = staging + (warp - 2) * 32 * kStageLd;
-      auto row_of = [&](int r, long long& grow) {
-        return m_tile < num_m_tiles && tile_row_to_global(ep, conv != 0, m_tile, q * 32 + r, grow);
-      };
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+      if (BN >= 64 || chalf == 0) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const long long n0 = n_tile * BN + c0;
-        if (n0 >= ep.n) break;                 // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
-        float acc[32];
+        for (int c0 = chalf * kColsPerWarp; c0 < (chalf + 1) * kColsPerWarp; c0 += 32) {
+          const long long n0 = n_tile * BN + c0;
+          if (n0 >= ep.n) break;                 // warp-uniform
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          float acc[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
-        epilogue_chunk(ep, acc, stage, lane, n0, row_of);
+          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+          epilogue_chunk(ep, acc, stage, lane, n0, rs);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -607,6 +617,7 @@ extern "C" int svla_gemm(const SvlaGemmArgs* g, void* stream) {
   SVLA_REQUIRE(!geglu || (g->out_bf16 && !g->out_f32 && !g->out_relu_bf16 && !g->res_bf16 && !g->res2_bf16 && !g->res_f32 && (g->n % 2) == 0),
                "svla_gemm: GEGLU mode needs out_bf16 only and even n");
   SVLA_REQUIRE(g->out_bf16 || g->out_f32 || g->out_relu_bf16, "svla_gemm: no output");
+  SVLA_REQUIRE(g->m * g->ldo < (1LL << 32), "svla_gemm: output of %lld x %lld elements exceeds the 32-bit offset range", (long long)g->m, (long long)g->ldo);
   SVLA_REQUIRE(!(g->flags & SVLA_GEMM_ACCUM_F32) || g->out_f32, "svla_gemm: ACCUM_F32 needs out_f32");
 
   EpiParams ep{};

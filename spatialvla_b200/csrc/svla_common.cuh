@@ -87,14 +87,18 @@ __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + 
 // erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, below fp32 GELU rounding for bf16 consumers)
 __device__ __forceinline__ float erf_fast(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  float t;      // branch-free reciprocal: __frcp_rn's slow-path branch serialises the 32 independent elements of a chunk
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
   float p = 1.061405429f;
   p = fmaf(p, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float r = 1.f - p * t * __expf(-ax * ax);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-ax * ax * 1.4426950408889634f));
+  const float r = 1.f - p * t * e;
   return copysignf(r, x);
 }
 __device__ __forceinline__ float gelu_erf_fast(float x) { return 0.5f * x * (1.f + erf_fast(x * 0.7071067811865476f)); }
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float softplus_fast(float x) { return x > 15.f ? x : __logf(1.f + __expf(x)); }

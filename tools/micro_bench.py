@@ -1,0 +1,51 @@
+"""Config #4 micro-benchmarks (BASELINE.json): SpatialActionTokenizer on 1 M actions and the fused Ego3D encode on
+batches of depth maps -- achieved HBM GB/s (algorithmic bytes / CUDA-event time) against MEASURED_PEAKS.json."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, torch
+from spatialvla_b200.ops import CudaOps
+from spatialvla_b200.configs import default_intrinsic_224
+
+dev = "cuda:0"
+ops = CudaOps(dev)
+peak = 6555.8
+try:
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+flush = torch.empty(256 * 2**20, dtype=torch.uint8, device=dev)
+
+def timeit(fn, iters=10):
+    fn(); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); torch.cuda.synchronize()
+        best = min(best, s.elapsed_time(e))
+    return best
+
+g = np.load(os.path.join(ROOT, "tests", "golden", "tokenizer_gauss.npz"))
+keys = ("theta_bins", "phi_bins", "r_bins", "roll_bins", "pitch_bins", "yaw_bins")
+edges = torch.from_numpy(np.concatenate([g[f"edge_{k}"] for k in keys])).to(dev)
+nb = [len(g[f"edge_{k}"]) - 1 for k in keys] + [2]
+out = []
+for n in (1_000_000, 16_000_000):
+    acts = (torch.rand(n, 7, device=dev, dtype=torch.float64) * 2 - 1)
+    ids = torch.empty(n, 3, dtype=torch.int32, device=dev)
+    ms = timeit(lambda: ops.tok_encode(acts, edges, nb, ids))
+    out.append({"kernel": "svla_tok_encode", "n": n, "ms": round(ms, 4), "GBs": round(n * 68 / ms / 1e6, 1), "frac_of_measured_hbm": round(n * 68 / ms / 1e6 / peak, 3)})
+    gid = ids.to(torch.int64) + 257153
+    dec = torch.empty(n, 7, dtype=torch.float64, device=dev)
+    ms = timeit(lambda: ops.tok_decode(gid, edges, nb, 257153, dec))
+    out.append({"kernel": "svla_tok_decode", "n": n, "ms": round(ms, 4), "GBs": round(n * 80 / ms / 1e6, 1), "frac_of_measured_hbm": round(n * 80 / ms / 1e6 / peak, 3)})
+K = torch.tensor(default_intrinsic_224(), device=dev)
+for B in (64, 4096):
+    depth = torch.rand(B, 384, 384, device=dev) * 4.7 + 0.3
+    xyz = torch.empty(B * 256, 12, device=dev); enc = torch.empty(B * 256, 208, device=dev, dtype=torch.bfloat16)
+    ms = timeit(lambda: ops.ego3d_encode(depth, K, xyz, enc, n_freqs=8), iters=5)
+    byts = B * (384 * 384 * 4 + 256 * 12 * 4 + 256 * 208 * 2)
+    out.append({"kernel": "svla_ego3d_encode", "maps": B, "ms": round(ms, 4), "GBs": round(byts / ms / 1e6, 1), "frac_of_measured_hbm": round(byts / ms / 1e6 / peak, 3)})
+for r in out:
+    print(json.dumps(r))

@@ -53,6 +53,12 @@ __device__ __forceinline__ float tanh_small(float u) {
   return tanhf(u);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttnP {
   const __nv_bfloat16 *q, *k, *v;
   __nv_bfloat16* out;
@@ -130,6 +136,7 @@ svla_flash_attn_kernel(const AttnP p) {
   for (int i = 0; i < NT; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   const int qi0 = q0 + warp * 16 + g;      // this thread's rows: qi0 and qi0 + 8
+  const bool warp_active = (q0 + warp * 16) < p.sq;
   const int causal_off = p.sk - p.sq;
   constexpr float kLog2e = 1.4426950408889634f;
   // BEiT relative-position index = qbase(query) - kterm(key) for patch tokens; CLS row/column are special-cased
@@ -162,6 +169,10 @@ svla_flash_attn_kernel(const AttnP p) {
     const __nv_bfloat16* cK = sK + buf * 64 * LD;
     const __nv_bfloat16* cV = sV + buf * 64 * LD;
 
+    // ragged tails: warps whose 16 query rows are all >= sq only help with loads/barriers; the last K/V tile only
+    // multiplies the 16-key groups that contain valid keys (BEiT: 577 = 9*64 + 1 keys)
+    const int np_valid = min(4, (p.sk - jt * kBKV + 15) >> 4);
+    if (!warp_active) { __syncthreads(); continue; }
     // ---- S = Q K^T  (16 x 64 per warp)
     float s[8][4];
 #pragma unroll
@@ -172,6 +183,7 @@ svla_flash_attn_kernel(const AttnP p) {
       ldsm_x4(a, sQ + (warp * 16 + (lane & 15)) * LD + kt * 16 + (lane >> 4) * 8);
 #pragma unroll
       for (int np = 0; np < 4; ++np) {       // pairs of key n-tiles
+        if (np >= np_valid) break;
         uint32_t bfr[4];
         const int mi = lane >> 3;
         ldsm_x4(bfr, cK + (np * 16 + (mi >> 1) * 8 + (lane & 7)) * LD + kt * 16 + (mi & 1) * 8);
@@ -212,7 +224,7 @@ svla_flash_attn_kernel(const AttnP p) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float m_new = fmaxf(m_run[r], mx[r]);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      scale_old[r] = exp2f((m_run[r] - m_use) * kLog2e);    // m_run = -inf -> 0
+      scale_old[r] = ex2_approx((m_run[r] - m_use) * kLog2e);    // m_run = -inf -> 0
       m_run[r] = m_new;
       mx[r] = m_use;
       l_run[r] *= scale_old[r];
@@ -221,8 +233,8 @@ svla_flash_attn_kernel(const AttnP p) {
     uint32_t pa[8][2];      // P as bf16 pairs: [n-tile][row half]
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = exp2f((s[nt][0] - mx[0]) * kLog2e), p1 = exp2f((s[nt][1] - mx[0]) * kLog2e);
-      const float p2 = exp2f((s[nt][2] - mx[1]) * kLog2e), p3 = exp2f((s[nt][3] - mx[1]) * kLog2e);
+      const float p0 = ex2_approx(fmaf(s[nt][0], kLog2e, -mx[0] * kLog2e)), p1 = ex2_approx(fmaf(s[nt][1], kLog2e, -mx[0] * kLog2e));
+      const float p2 = ex2_approx(fmaf(s[nt][2], kLog2e, -mx[1] * kLog2e)), p3 = ex2_approx(fmaf(s[nt][3], kLog2e, -mx[1] * kLog2e));
       ls[0] += p0 + p1;
       ls[1] += p2 + p3;
       pa[nt][0] = pack_bf16x2(p0, p1);
@@ -238,6 +250,7 @@ svla_flash_attn_kernel(const AttnP p) {
     // ---- O += P V   (k = 64 keys in 4 steps of 16)
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
+      if (ks >= np_valid) break;
       const uint32_t a[4] = {pa[2 * ks][0], pa[2 * ks][1], pa[2 * ks + 1][0], pa[2 * ks + 1][1]};
 #pragma unroll
       for (int dp = 0; dp < NT / 2; ++dp) {   // pairs of output d n-tiles
@@ -298,114 +311,107 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
 #pragma unroll
   for (int u = 0; u < 4; ++u) { f[2 * u] = bf16_bits_to_float(w[u] & 0xFFFFu); f[2 * u + 1] = bf16_bits_to_float(w[u] >> 16); }
 }
-constexpr int kDecThreads = 512;     // 16 warps: 4 keys in flight per warp -> 5 dependent DRAM round trips for 285 keys
+constexpr int kDecThreads = 256;     // 8 warps, 2 CTAs per SM: all 256 (batch, kv-head) CTAs of a B=64 step are resident in one wave
 constexpr int kMaxGroup = 4;
 
+// One CTA per (batch, kv head), 16 warps.  Every warp streams its share of the keys with K and V rows of 4 keys in
+// flight together (8 x 16-byte loads per lane), keeps a private online-softmax state (m, l, acc) for each query head
+// of the GQA group in registers, and the 16 partial states are merged once through shared memory: a single pass over
+// the cache, one block barrier.
 template <int D>
 __global__ void __launch_bounds__(kDecThreads)
 svla_decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
                         const __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out, int hq, int hkv, int smax,
                         int ctx, float scale, float softcap) {
+  constexpr int PER = D / 32;
+  constexpr int KB = 4;
+  constexpr int NW = kDecThreads / 32;
+  static_assert(PER == 8, "one 16-byte load per lane per row");
   extern __shared__ float sm_dec[];
   const int grp = hq / hkv;
-  float* sq = sm_dec;                       // [grp][D]
-  float* sc = sq + grp * D;                 // [grp][ctx]
-  float* red = sc + grp * ctx;              // [64]
+  float* s_m = sm_dec;                      // [NW][kMaxGroup]
+  float* s_l = s_m + NW * kMaxGroup;        // [NW][kMaxGroup]
+  float* s_acc = s_l + NW * kMaxGroup;      // [NW][grp][D]
   const int b = blockIdx.y, hk = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int NW = kDecThreads / 32;
-  for (int i = threadIdx.x; i < grp * D; i += kDecThreads)
-    sq[i] = __bfloat162float(q[(static_cast<long long>(b) * hq + hk * grp) * D + i]);
-  __syncthreads();
-  const __nv_bfloat16* kb = kc + (static_cast<long long>(b) * smax * hkv + hk) * D;
-  const __nv_bfloat16* vb = vc + (static_cast<long long>(b) * smax * hkv + hk) * D;
+  // this lane's 8 query dims for every head of the group
+  float qv[kMaxGroup][PER];
+#pragma unroll
+  for (int gi = 0; gi < kMaxGroup; ++gi) {
+    if (gi < grp) unpack8(__ldg(reinterpret_cast<const uint4*>(q + (static_cast<long long>(b) * hq + hk * grp + gi) * D + lane * PER)), qv[gi]);
+    else {
+#pragma unroll
+      for (int e = 0; e < PER; ++e) qv[gi][e] = 0.f;
+    }
+  }
+  const __nv_bfloat16* kb = kc + (static_cast<long long>(b) * smax * hkv + hk) * D + lane * PER;
+  const __nv_bfloat16* vb = vc + (static_cast<long long>(b) * smax * hkv + hk) * D + lane * PER;
   const long long row_stride = static_cast<long long>(hkv) * D;
-  // scores: one warp per key, each lane covers D/32 contiguous dims; 4 keys in flight per warp (memory-level parallelism)
-  constexpr int PER = D / 32;
-  constexpr int KB = 8;
-  static_assert(PER == 8, "one 16-byte load per lane per key");
-  for (int j0 = warp * KB; j0 < ctx; j0 += NW * KB) {
-    uint4 raw[KB];
+  float m_run[kMaxGroup], l_run[kMaxGroup], acc[kMaxGroup][PER];
 #pragma unroll
-    for (int u = 0; u < KB; ++u)
-      raw[u] = (j0 + u < ctx) ? __ldg(reinterpret_cast<const uint4*>(kb + (j0 + u) * row_stride + lane * PER)) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int u = 0; u < KB; ++u) {
-      if (j0 + u >= ctx) break;
-      float kv[PER];
-      unpack8(raw[u], kv);
-      for (int gi = 0; gi < grp; ++gi) {
-        float acc = 0.f;
-#pragma unroll
-        for (int e = 0; e < PER; ++e) acc += kv[e] * sq[gi * D + lane * PER + e];
-        acc = warp_sum(acc);
-        if (lane == 0) {
-          float x = acc * scale;
-          if (softcap > 0.f) x = softcap * tanhf(x / softcap);
-          sc[gi * ctx + j0 + u] = x;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  // softmax per group row (fp32)
-  for (int gi = 0; gi < grp; ++gi) {
-    float mx = -INFINITY;
-    for (int j = threadIdx.x; j < ctx; j += kDecThreads) mx = fmaxf(mx, sc[gi * ctx + j]);
-    mx = warp_max(mx);
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-    mx = red[0];
-    for (int w = 1; w < NW; ++w) mx = fmaxf(mx, red[w]);
-    float sum = 0.f;
-    for (int j = threadIdx.x; j < ctx; j += kDecThreads) {
-      const float e = expf(sc[gi * ctx + j] - mx);
-      sc[gi * ctx + j] = e;
-      sum += e;
-    }
-    sum = block_sum(sum, red + 16);
-    const float inv = 1.f / sum;
-    for (int j = threadIdx.x; j < ctx; j += kDecThreads) sc[gi * ctx + j] *= inv;
-    __syncthreads();
-  }
-  // out[d] = sum_j p[j] V[j][d]: one warp per key (16-byte V loads, lane <-> 8 dims), partial sums reduced over
-  // the 8 warps through shared memory. Probabilities are rounded to bf16 like the prefill path.
-  float acc[kMaxGroup][PER];
-#pragma unroll
-  for (int gi = 0; gi < kMaxGroup; ++gi)
+  for (int gi = 0; gi < kMaxGroup; ++gi) {
+    m_run[gi] = -INFINITY; l_run[gi] = 0.f;
 #pragma unroll
     for (int e = 0; e < PER; ++e) acc[gi][e] = 0.f;
+  }
+  const float inv_cap = softcap > 0.f ? 1.f / softcap : 0.f;
   for (int j0 = warp * KB; j0 < ctx; j0 += NW * KB) {
-    uint4 raw[KB];
-#pragma unroll
-    for (int u = 0; u < KB; ++u)
-      raw[u] = (j0 + u < ctx) ? __ldg(reinterpret_cast<const uint4*>(vb + (j0 + u) * row_stride + lane * PER)) : make_uint4(0, 0, 0, 0);
+    uint4 kr[KB], vr[KB];
 #pragma unroll
     for (int u = 0; u < KB; ++u) {
-      if (j0 + u >= ctx) break;
-      float vv[PER];
-      unpack8(raw[u], vv);
+      const bool ok = j0 + u < ctx;
+      kr[u] = ok ? __ldg(reinterpret_cast<const uint4*>(kb + (j0 + u) * row_stride)) : make_uint4(0, 0, 0, 0);
+      vr[u] = ok ? __ldg(reinterpret_cast<const uint4*>(vb + (j0 + u) * row_stride)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < KB; ++u) {
+      const bool ok = j0 + u < ctx;           // warp-uniform
+      float kv[PER], vv[PER];
+      unpack8(kr[u], kv);
+      unpack8(vr[u], vv);
 #pragma unroll
       for (int gi = 0; gi < kMaxGroup; ++gi) {
-        if (gi < grp) {
-          const float pj = __bfloat162float(__float2bfloat16(sc[gi * ctx + j0 + u]));
+        if (gi < grp && ok) {
+          float dot = 0.f;
 #pragma unroll
-          for (int e = 0; e < PER; ++e) acc[gi][e] += pj * vv[e];
+          for (int e = 0; e < PER; ++e) dot += kv[e] * qv[gi][e];
+          dot = warp_sum(dot) * scale;
+          if (softcap > 0.f) dot = softcap * tanh_small(dot * inv_cap);
+          const float m_new = fmaxf(m_run[gi], dot);
+          const float corr = __expf(m_run[gi] - m_new);      // exp(-inf) = 0 on the first key
+          const float pj = __expf(dot - m_new);
+          l_run[gi] = l_run[gi] * corr + pj;
+#pragma unroll
+          for (int e = 0; e < PER; ++e) acc[gi][e] = acc[gi][e] * corr + pj * vv[e];
+          m_run[gi] = m_new;
         }
       }
     }
   }
-  __syncthreads();                 // scores no longer needed: reuse sq/sc region? keep separate partial buffer
-  float* part = red + 64;          // [NW][grp][D]
-  for (int gi = 0; gi < grp; ++gi)
+  // merge the NW partial states
 #pragma unroll
-    for (int e = 0; e < PER; ++e) part[(warp * grp + gi) * D + lane * PER + e] = acc[gi][e];
+  for (int gi = 0; gi < kMaxGroup; ++gi) {
+    if (gi < grp) {
+      if (lane == 0) { s_m[warp * kMaxGroup + gi] = m_run[gi]; s_l[warp * kMaxGroup + gi] = l_run[gi]; }
+#pragma unroll
+      for (int e = 0; e < PER; ++e) s_acc[(warp * grp + gi) * D + lane * PER + e] = acc[gi][e];
+    }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < grp * D; i += kDecThreads) {
-    float t = 0.f;
+    const int gi = i / D, dd = i - gi * D;
+    float mmax = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) t += part[w * grp * D + i];
-    out[(static_cast<long long>(b) * hq + hk * grp) * D + i] = __float2bfloat16(t);
+    for (int w = 0; w < NW; ++w) mmax = fmaxf(mmax, s_m[w * kMaxGroup + gi]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const float mw = s_m[w * kMaxGroup + gi];
+      const float f = (mw == -INFINITY) ? 0.f : __expf(mw - mmax);
+      num += f * s_acc[(w * grp + gi) * D + dd];
+      den += f * s_l[w * kMaxGroup + gi];
+    }
+    out[(static_cast<long long>(b) * hq + hk * grp + gi) * D + dd] = __float2bfloat16(num / den);
   }
 }
 
@@ -442,7 +448,7 @@ extern "C" int svla_decode_attention(const void* q, const void* kcache, const vo
   SVLA_REQUIRE(hkv > 0 && hq % hkv == 0 && hq / hkv <= kMaxGroup, "svla_decode_attention: bad GQA group");
   SVLA_REQUIRE(ctx > 0 && ctx <= smax, "svla_decode_attention: ctx %d out of range", ctx);
   const int grp = hq / hkv;
-  const size_t smem = (static_cast<size_t>(grp) * d + static_cast<size_t>(grp) * ctx + 64 + static_cast<size_t>(kDecThreads / 32) * grp * d) * sizeof(float);
+  const size_t smem = (2 * static_cast<size_t>(kDecThreads / 32) * kMaxGroup + static_cast<size_t>(kDecThreads / 32) * grp * d) * sizeof(float);
   SVLA_REQUIRE(smem <= 200 * 1024, "svla_decode_attention: context too long for shared memory");
   static size_t configured = 48 * 1024;
   if (smem > configured) {

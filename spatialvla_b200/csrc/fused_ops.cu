@@ -8,6 +8,8 @@ namespace {
 constexpr int kRowThreads = 256;
 constexpr int kMaxVec = 5;   // float4 per thread: rows up to 256*5*4 = 5120 columns
 
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]);
+
 // ------------------------------------------------------------------------------------------ row loaders
 __device__ __forceinline__ int load_row(const float* __restrict__ x, int cols, float4 (&v)[kMaxVec]) {
   const int nv = cols >> 2;
@@ -116,6 +118,122 @@ svla_rmsnorm_residual_kernel(float* __restrict__ x, const float* __restrict__ br
   }
 }
 
+// ------------------------------------------------------------------------------------------ warp-per-row variants
+// One warp owns one row: no block barriers, every load of the row is in flight before the first reduction, shuffle
+// reductions only.  V = float4 per lane (cols <= 128 * V).  The block-per-row kernels above remain for wider rows.
+template <int V>
+__global__ void __launch_bounds__(128)
+svla_layernorm_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                           long long rows, int cols, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32, int relu) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * 4LL + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = cols >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
+  float4 v[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int i = lane + 32 * k;
+    v[k] = (i < nv) ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < V; ++k) s += v[k].x + v[k].y + v[k].z + v[k].w;
+  const float mean = warp_sum(s) / cols;
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    if (lane + 32 * k < nv) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      ss += a * a + b * b + c * c + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / cols + eps);
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nv) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i);
+      float4 o;
+      o.x = (v[k].x - mean) * rstd * g.x + b.x;
+      o.y = (v[k].y - mean) * rstd * g.y + b.y;
+      o.z = (v[k].z - mean) * rstd * g.z + b.z;
+      o.w = (v[k].w - mean) * rstd * g.w + b.w;
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      if (out_f32) reinterpret_cast<float4*>(out_f32 + row * cols)[i] = o;
+      if (out_bf16) reinterpret_cast<uint2*>(out_bf16 + row * cols)[i] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    }
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(128)
+svla_rmsnorm_residual_warp_kernel(float* __restrict__ x, const float* __restrict__ branch, const float* __restrict__ w_post,
+                                  const float* __restrict__ w_pre, float eps, long long rows, int cols,
+                                  __nv_bfloat16* __restrict__ out_bf16, int n_partials, long long partial_stride) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * 4LL + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = cols >> 2;
+  float4* xr = reinterpret_cast<float4*>(x + row * cols);
+  float4 xv[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int i = lane + 32 * k;
+    xv[k] = (i < nv) ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (branch) {
+    float4 bv[V];
+    const float4* br = reinterpret_cast<const float4*>(branch + row * cols);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const int i = lane + 32 * k;
+      bv[k] = (i < nv) ? br[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int sp = 1; sp < n_partials; ++sp) {
+      const float4* pr = reinterpret_cast<const float4*>(branch + sp * partial_stride + row * cols);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const int i = lane + 32 * k;
+        if (i < nv) { const float4 t = pr[i]; bv[k].x += t.x; bv[k].y += t.y; bv[k].z += t.z; bv[k].w += t.w; }
+      }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; ++k) ss += bv[k].x * bv[k].x + bv[k].y * bv[k].y + bv[k].z * bv[k].z + bv[k].w * bv[k].w;
+    const float r = rsqrtf(warp_sum(ss) / cols + eps);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const int i = lane + 32 * k;
+      if (i < nv) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(w_post) + i);
+        xv[k].x += bv[k].x * r * (1.f + w.x);
+        xv[k].y += bv[k].y * r * (1.f + w.y);
+        xv[k].z += bv[k].z * r * (1.f + w.z);
+        xv[k].w += bv[k].w * r * (1.f + w.w);
+        xr[i] = xv[k];
+      }
+    }
+  }
+  if (w_pre) {
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; ++k) ss += xv[k].x * xv[k].x + xv[k].y * xv[k].y + xv[k].z * xv[k].z + xv[k].w * xv[k].w;
+    const float r = rsqrtf(warp_sum(ss) / cols + eps);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const int i = lane + 32 * k;
+      if (i < nv) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(w_pre) + i);
+        reinterpret_cast<uint2*>(out_bf16 + row * cols)[i] =
+            make_uint2(pack_bf16x2(xv[k].x * r * (1.f + w.x), xv[k].y * r * (1.f + w.y)),
+                       pack_bf16x2(xv[k].z * r * (1.f + w.z), xv[k].w * r * (1.f + w.w)));
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ M3 RoPE + KV cache write
 // one block per token; thread pairs (d, d + D/2) of every head
 __global__ void svla_rope_kv_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ q_out,
@@ -163,6 +281,49 @@ __global__ void svla_rope_kv_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_
   }
   const long long voff = static_cast<long long>(hq + hkv) * d;
   for (int i = threadIdx.x; i < hkv * d; i += blockDim.x) vc[cache_row + i] = __float2bfloat16(load(voff + i));
+}
+
+// Vectorised prefill variant (bf16 qkv in): a thread owns 8 consecutive frequencies (one 16-byte load per half),
+// computes their 8 sincos once and reuses them for every q/k head; V rows are copied with 16-byte accesses.
+__global__ void __launch_bounds__(128)
+svla_rope_kv_vec_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ kc,
+                        __nv_bfloat16* __restrict__ vc, int s, int hq, int hkv, int d, int smax, int pos0, float theta) {
+  const long long tok = blockIdx.x;
+  const int b = static_cast<int>(tok / s), si = static_cast<int>(tok % s);
+  const int pos = pos0 + si;
+  const float fpos = static_cast<float>(pos + 1);
+  const int half = d >> 1;
+  const int tph = half >> 3;                       // threads per head
+  const long long width = static_cast<long long>(hq + 2 * hkv) * d;
+  const __nv_bfloat16* src = qkv + tok * width;
+  const long long cache_row = (static_cast<long long>(b) * smax + pos) * hkv * d;
+  const int jt = threadIdx.x % tph, hl = threadIdx.x / tph, hlanes = blockDim.x / tph;
+  if (hl < hlanes) {
+    float sn[8], cs[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = jt * 8 + e;
+      const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * j) / static_cast<float>(d));
+      sincosf(fpos * inv_freq, &sn[e], &cs[e]);
+    }
+    for (int hh = hl; hh < hq + hkv; hh += hlanes) {
+      float x1[8], x2[8];
+      unpack8(*reinterpret_cast<const uint4*>(src + hh * d + jt * 8), x1);
+      unpack8(*reinterpret_cast<const uint4*>(src + hh * d + half + jt * 8), x2);
+      uint32_t o1[4], o2[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        o1[e] = pack_bf16x2(x1[2 * e] * cs[2 * e] - x2[2 * e] * sn[2 * e], x1[2 * e + 1] * cs[2 * e + 1] - x2[2 * e + 1] * sn[2 * e + 1]);
+        o2[e] = pack_bf16x2(x2[2 * e] * cs[2 * e] + x1[2 * e] * sn[2 * e], x2[2 * e + 1] * cs[2 * e + 1] + x1[2 * e + 1] * sn[2 * e + 1]);
+      }
+      __nv_bfloat16* dst = (hh < hq) ? q_out + tok * hq * d + hh * d : kc + cache_row + (hh - hq) * d;
+      *reinterpret_cast<uint4*>(dst + jt * 8) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+      *reinterpret_cast<uint4*>(dst + half + jt * 8) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+    }
+  }
+  const uint4* vsrc = reinterpret_cast<const uint4*>(src + static_cast<long long>(hq + hkv) * d);
+  uint4* vdst = reinterpret_cast<uint4*>(vc + cache_row);
+  for (int i = threadIdx.x; i < (hkv * d) >> 3; i += blockDim.x) vdst[i] = vsrc[i];
 }
 
 // ------------------------------------------------------------------------------------------ M6 embedding gather
@@ -623,8 +784,15 @@ extern "C" int svla_layernorm(const float* x, const float* gamma, const float* b
                               void* out_bf16, float* out_f32, int relu, void* stream) {
   SVLA_REQUIRE(x && gamma && beta && (out_bf16 || out_f32), "svla_layernorm: null pointer");
   SVLA_REQUIRE(rows > 0 && cols > 0 && (cols % 4) == 0 && cols <= kRowThreads * kMaxVec * 4, "svla_layernorm: cols=%d unsupported", cols);
-  svla_layernorm_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, gamma, beta, eps, cols, static_cast<__nv_bfloat16*>(out_bf16), out_f32, relu);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
+  const unsigned wblocks = static_cast<unsigned>((rows + 3) / 4);
+  const int need = (cols / 4 + 31) / 32;      // float4 per lane for the warp-per-row kernels
+  if (rows >= 256 && need <= 2) svla_layernorm_warp_kernel<2><<<wblocks, 128, 0, st>>>(x, gamma, beta, eps, rows, cols, ob, out_f32, relu);
+  else if (rows >= 256 && need <= 4) svla_layernorm_warp_kernel<4><<<wblocks, 128, 0, st>>>(x, gamma, beta, eps, rows, cols, ob, out_f32, relu);
+  else if (rows >= 256 && need <= 9) svla_layernorm_warp_kernel<9><<<wblocks, 128, 0, st>>>(x, gamma, beta, eps, rows, cols, ob, out_f32, relu);
+  else if (rows >= 256 && need <= 18) svla_layernorm_warp_kernel<18><<<wblocks, 128, 0, st>>>(x, gamma, beta, eps, rows, cols, ob, out_f32, relu);
+  else svla_layernorm_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, st>>>(x, gamma, beta, eps, cols, ob, out_f32, relu);
   SVLA_LAUNCH_CHECK("svla_layernorm");
   return 0;
 }
@@ -635,8 +803,16 @@ extern "C" int svla_rmsnorm_residual(float* x, const float* branch, const float*
   SVLA_REQUIRE((branch == nullptr) == (w_post == nullptr), "svla_rmsnorm_residual: branch and w_post go together");
   SVLA_REQUIRE((w_pre == nullptr) == (out_bf16 == nullptr), "svla_rmsnorm_residual: w_pre and out_bf16 go together");
   SVLA_REQUIRE(rows > 0 && cols > 0 && (cols % 4) == 0 && cols <= kRowThreads * kMaxVec * 4, "svla_rmsnorm_residual: cols=%d unsupported", cols);
-  svla_rmsnorm_residual_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, branch, w_post, w_pre, eps, cols, static_cast<__nv_bfloat16*>(out_bf16), n_partials < 1 ? 1 : n_partials, partial_stride);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
+  const int np = n_partials < 1 ? 1 : n_partials;
+  const unsigned wblocks = static_cast<unsigned>((rows + 3) / 4);
+  const int need = (cols / 4 + 31) / 32;
+  // many rows (prefill): warp-per-row; few rows (decode, 64 rows): block-per-row keeps all SMs busy
+  if (rows >= 2048 && need <= 4) svla_rmsnorm_residual_warp_kernel<4><<<wblocks, 128, 0, st>>>(x, branch, w_post, w_pre, eps, rows, cols, ob, np, partial_stride);
+  else if (rows >= 2048 && need <= 9) svla_rmsnorm_residual_warp_kernel<9><<<wblocks, 128, 0, st>>>(x, branch, w_post, w_pre, eps, rows, cols, ob, np, partial_stride);
+  else if (rows >= 2048 && need <= 18) svla_rmsnorm_residual_warp_kernel<18><<<wblocks, 128, 0, st>>>(x, branch, w_post, w_pre, eps, rows, cols, ob, np, partial_stride);
+  else svla_rmsnorm_residual_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, st>>>(x, branch, w_post, w_pre, eps, cols, ob, np, partial_stride);
   SVLA_LAUNCH_CHECK("svla_rmsnorm_residual");
   return 0;
 }
@@ -647,6 +823,13 @@ extern "C" int svla_rope_kv(const void* qkv, void* q_out, void* kcache, void* vc
   SVLA_REQUIRE((qkv || qkv_f32) && q_out && kcache && vcache, "svla_rope_kv: null pointer");
   SVLA_REQUIRE(batch > 0 && s > 0 && (d % 2) == 0 && pos0 >= 0 && pos0 + s <= smax, "svla_rope_kv: bad geometry (pos0=%d s=%d smax=%d)", pos0, s, smax);
   SVLA_REQUIRE(d / 2 <= 512, "svla_rope_kv: head dim too large");
+  if (qkv_f32 == nullptr && (d % 16) == 0 && (d / 16) <= 128 && 128 % (d / 16) == 0 && batch * s > 1024) {
+    svla_rope_kv_vec_kernel<<<static_cast<unsigned>(batch) * s, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(q_out), static_cast<__nv_bfloat16*>(kcache),
+        static_cast<__nv_bfloat16*>(vcache), s, hq, hkv, d, smax, pos0, theta);
+    SVLA_LAUNCH_CHECK("svla_rope_kv_vec");
+    return 0;
+  }
   const int rope_threads = (d / 2) * ((batch * s <= 1024) ? max(1, 512 / (d / 2)) : 1);     // decode: spread heads over lanes
   svla_rope_kv_kernel<<<static_cast<unsigned>(batch) * s, rope_threads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(q_out), static_cast<__nv_bfloat16*>(kcache),

@@ -292,7 +292,7 @@ ATTN_CASES = [
 # ------------------------------------------------------------------------------------------------ fused ops
 def layernorm_case(dev="cuda:0"):
     res = Result("layernorm")
-    for cols, rows in ((144, 37), (1152, 300), (4304, 5), (128, 290)):
+    for cols, rows in ((144, 37), (1152, 300), (4304, 5), (128, 290), (1024, 577 * 2), (2304, 260), (512, 1000)):
         g = _gen(cols)
         x, ga, be = _randn(g, rows, cols), _randn(g, cols) * 0.1 + 1, _randn(g, cols) * 0.1
 
@@ -308,7 +308,7 @@ def layernorm_case(dev="cuda:0"):
 
 def rmsnorm_case(dev="cuda:0"):
     res = Result("rmsnorm_residual")
-    for cols, rows in ((2304, 70), (512, 9)):
+    for cols, rows in ((2304, 70), (512, 9), (2304, 2100), (512, 2500), (1024, 2049)):
         g = _gen(cols)
         x, br = _randn(g, rows, cols), _randn(g, rows, cols, scale=3.0)
         wp, wq = _randn(g, cols) * 0.1, _randn(g, cols) * 0.1
@@ -327,18 +327,18 @@ def rmsnorm_case(dev="cuda:0"):
 
 
 def rope_case(dev="cuda:0"):
-    g = _gen(5)
-    B, S, hq, hkv, d, smax, pos0 = 2, 37, 4, 2, 256, 64, 11
-    qkv = _randn(g, B * S, (hq + 2 * hkv) * d, dtype=BF16)
-
-    def run(ops, to):
-        q, kc, vc = ops.zeros((B * S, hq * d), BF16), ops.zeros((B, smax, hkv, d), BF16), ops.zeros((B, smax, hkv, d), BF16)
-        ops.rope_kv(to(qkv), q, kc, vc, batch=B, s=S, hq=hq, hkv=hkv, d=d, smax=smax, pos0=pos0, theta=10000.0)
-        return q, kc, vc
-    c, r = _both(run, dev)
     res = Result("rope_kv")
-    for nm, a, b in zip(("q", "k", "v"), c, r):
-        res.add(nm, _err(a, b), TOL_BF16 if nm != "v" else 0.0)
+    for (B, S, hq, hkv, d, smax, pos0) in ((2, 37, 4, 2, 256, 64, 11), (8, 150, 8, 4, 256, 160, 0), (5, 300, 2, 1, 64, 300, 0)):
+        g = _gen(5 + S)
+        qkv = _randn(g, B * S, (hq + 2 * hkv) * d, dtype=BF16)
+
+        def run(ops, to):
+            q, kc, vc = ops.zeros((B * S, hq * d), BF16), ops.zeros((B, smax, hkv, d), BF16), ops.zeros((B, smax, hkv, d), BF16)
+            ops.rope_kv(to(qkv), q, kc, vc, batch=B, s=S, hq=hq, hkv=hkv, d=d, smax=smax, pos0=pos0, theta=10000.0)
+            return q, kc, vc
+        c, r = _both(run, dev)
+        for nm, a, b in zip(("q", "k", "v"), c, r):
+            res.add(f"{nm}[{B}x{S}]", _err(a, b), TOL_BF16 if nm != "v" else 0.0)
     return res
 
 

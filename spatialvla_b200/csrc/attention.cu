@@ -122,7 +122,7 @@ svla_flash_attn_kernel(const AttnP p) {
   int nrel = 0;
   if (f_relpos) {
     nrel = (2 * p.win - 1) * (2 * p.win - 1) + 3;
-    for (int i = threadIdx.x; i < nrel; i += kAttnThreads) sTab[i] = p.relpos[static_cast<long long>(i) * p.hq + h];
+    for (int i = threadIdx.x; i < nrel; i += kAttnThreads) sTab[i] = p.relpos[static_cast<long long>(i) * p.hq + h] * 1.4426950408889634f;
   }
 
   const int n_kv_tiles = (p.sk + kBKV - 1) / kBKV;
@@ -145,11 +145,12 @@ svla_flash_attn_kernel(const AttnP p) {
   if (f_relpos) {
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      const int qi = qi0 + 8 * r;
+      const int qi = min(qi0 + 8 * r, p.sq - 1);      // rows past the end reuse the last valid row's (in-range) index
       if (qi >= 1) qbase[r] = ((qi - 1) / p.win + p.win - 1) * w2 + (qi - 1) % p.win + p.win - 1;
     }
   }
   const float inv_cap = f_softcap ? 1.f / p.softcap : 0.f;
+  const float sl2 = p.scale * kLog2e;
 
   for (int jt = 0; jt < n_kv_tiles; ++jt) {
     const int buf = jt & 1;
@@ -163,7 +164,7 @@ svla_flash_attn_kernel(const AttnP p) {
     }
     if (f_relpos && threadIdx.x < 64) {
       const int kj = jt * kBKV + threadIdx.x;
-      sKterm[threadIdx.x] = kj >= 1 ? ((kj - 1) / p.win) * w2 + (kj - 1) % p.win : 0;
+      sKterm[threadIdx.x] = (kj >= 1 && kj < p.sk) ? ((kj - 1) / p.win) * w2 + (kj - 1) % p.win : 0;
     }
     __syncthreads();
     const __nv_bfloat16* cK = sK + buf * 64 * LD;
@@ -191,31 +192,81 @@ svla_flash_attn_kernel(const AttnP p) {
         mma_bf16(s[2 * np + 1], a, bfr[2], bfr[3]);
       }
     }
-    // ---- scale, softcap, bias, mask, online softmax
-    const bool need_mask = f_causal || (jt + 1) * kBKV > p.sk;      // block-uniform: only the ragged last tile / causal
+    // ---- scores -> log2 domain (y = x * log2 e): scale, soft-cap, rel-pos bias, mask; running max.
+    // The score path, not the MMAs, bounds this kernel (ncu: 32 instructions per score element in the first
+    // version), so every feature is folded into as few per-element operations as possible and the special cases
+    // (CLS row/column of BEiT, ragged/causal mask, large soft-cap arguments) are warp-uniform branches.
+    const bool need_mask = f_causal || (jt + 1) * kBKV > p.sk;
     float mx[2] = {-INFINITY, -INFINITY};
+    if (f_relpos) {
+      const bool has_cls = (jt == 0) || (q0 + warp * 16 == 0);      // only then a CLS key / query is in this block
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int kt0 = sKterm[nt * 8 + 2 * t], kt1 = sKterm[nt * 8 + 2 * t + 1];
+        int i00 = qbase[0] - kt0, i01 = qbase[0] - kt1, i10 = qbase[1] - kt0, i11 = qbase[1] - kt1;
+        if (has_cls) {
+          const int kj0 = jt * kBKV + nt * 8 + 2 * t;
+          if (kj0 == 0) { i00 = nrel - 2; i10 = nrel - 2; }
+          if (qi0 == 0) { i00 = (kj0 == 0) ? nrel - 1 : nrel - 3; i01 = nrel - 3; }
+        }
+        s[nt][0] = fmaf(s[nt][0], sl2, sTab[i00]);
+        s[nt][1] = fmaf(s[nt][1], sl2, sTab[i01]);
+        s[nt][2] = fmaf(s[nt][2], sl2, sTab[i10]);
+        s[nt][3] = fmaf(s[nt][3], sl2, sTab[i11]);
+      }
+    } else if (f_softcap) {
+      const float c1 = p.scale * inv_cap, c2 = p.softcap * kLog2e;
+      float u2max = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float u = s[nt][e] * c1; u2max = fmaxf(u2max, u * u); }
+      }
+      if (!__any_sync(0xffffffffu, u2max >= 0.1225f)) {
+        // cap * tanh(u) * log2e with a degree-9 odd polynomial (exact to fp32 rounding for |u| < 0.35)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float u = s[nt][e] * c1, u2 = u * u;
+            float pl = 62.f / 2835.f;
+            pl = fmaf(pl, u2, -17.f / 315.f);
+            pl = fmaf(pl, u2, 2.f / 15.f);
+            pl = fmaf(pl, u2, -1.f / 3.f);
+            pl = fmaf(pl, u2, 1.f);
+            s[nt][e] = c2 * u * pl;
+          }
+        }
+      } else {                                  // rare: a large score somewhere in this warp's block -> libm tanh
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) s[nt][e] = c2 * tanhf(s[nt][e] * c1);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[nt][e] *= sl2;
+      }
+    }
+    if (need_mask) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int qi = qi0 + (e >> 1) * 8;
+          const int kj = jt * kBKV + nt * 8 + 2 * t + (e & 1);
+          const bool masked = (kj >= p.sk) || (f_causal && kj > qi + causal_off);
+          s[nt][e] = masked ? -INFINITY : s[nt][e];
+        }
+      }
+    }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int r = e >> 1;
-        const int qi = qi0 + r * 8;
-        const int kj = jt * kBKV + nt * 8 + 2 * t + (e & 1);
-        float x = s[nt][e] * p.scale;
-        if (f_softcap) x = p.softcap * tanh_small(x * inv_cap);
-        if (f_relpos && qi < p.sq && kj < p.sk) {
-          int idx = qbase[r] - sKterm[nt * 8 + 2 * t + (e & 1)];
-          if (kj == 0) idx = nrel - 2;
-          if (qi == 0) idx = (kj == 0) ? nrel - 1 : nrel - 3;
-          x += sTab[idx];
-        }
-        if (need_mask) {
-          const bool masked = (kj >= p.sk) || (f_causal && kj > qi + causal_off);
-          x = masked ? -INFINITY : x;
-        }
-        s[nt][e] = x;
-        mx[r] = fmaxf(mx[r], x);
-      }
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
     }
     float scale_old[2];
 #pragma unroll
@@ -224,7 +275,7 @@ svla_flash_attn_kernel(const AttnP p) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float m_new = fmaxf(m_run[r], mx[r]);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      scale_old[r] = ex2_approx((m_run[r] - m_use) * kLog2e);    // m_run = -inf -> 0
+      scale_old[r] = ex2_approx(m_run[r] - m_use);    // log2 domain; m_run = -inf -> 0
       m_run[r] = m_new;
       mx[r] = m_use;
       l_run[r] *= scale_old[r];
@@ -233,8 +284,8 @@ svla_flash_attn_kernel(const AttnP p) {
     uint32_t pa[8][2];      // P as bf16 pairs: [n-tile][row half]
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = ex2_approx(fmaf(s[nt][0], kLog2e, -mx[0] * kLog2e)), p1 = ex2_approx(fmaf(s[nt][1], kLog2e, -mx[0] * kLog2e));
-      const float p2 = ex2_approx(fmaf(s[nt][2], kLog2e, -mx[1] * kLog2e)), p3 = ex2_approx(fmaf(s[nt][3], kLog2e, -mx[1] * kLog2e));
+      const float p0 = ex2_approx(s[nt][0] - mx[0]), p1 = ex2_approx(s[nt][1] - mx[0]);
+      const float p2 = ex2_approx(s[nt][2] - mx[1]), p3 = ex2_approx(s[nt][3] - mx[1]);
       ls[0] += p0 + p1;
       ls[1] += p2 + p3;
       pa[nt][0] = pack_bf16x2(p0, p1);
@@ -423,6 +474,9 @@ extern "C" int svla_attention(const SvlaAttnArgs* a, void* stream) {
   SVLA_REQUIRE(a->d > 0 && (a->d % 8) == 0 && a->d <= 256, "svla_attention: head dim %d unsupported", a->d);
   SVLA_REQUIRE(a->hkv > 0 && a->hq % a->hkv == 0, "svla_attention: hq %% hkv != 0");
   SVLA_REQUIRE(a->sq > 0 && a->sk > 0 && a->batch > 0, "svla_attention: empty problem");
+  SVLA_REQUIRE(!(a->relpos_table && a->softcap > 0.f), "svla_attention: relative-position bias and soft-capping are exclusive");
+  SVLA_REQUIRE(!a->relpos_table || (a->relpos_win > 0 && a->sk <= a->relpos_win * a->relpos_win + 1 && a->sq <= a->relpos_win * a->relpos_win + 1),
+               "svla_attention: sequence longer than the relative-position window");
   SVLA_REQUIRE((a->q_ss % 8) == 0 && (a->k_ss % 8) == 0 && (a->v_ss % 8) == 0 && (a->o_ss % 2) == 0,
                "svla_attention: row strides must keep 16-byte alignment");
   AttnP p;

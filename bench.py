@@ -130,6 +130,24 @@ class TimedOps:
             return ("flop", 2.0 * A.shape[0] * n * (k.get("k") or A.shape[1]))
         if name == "attention":
             return ("flop", 4.0 * k["batch"] * k["hq"] * k["sq"] * k["sk"] * k["d"])
+        # memory-bound kernels: algorithmic bytes (each operand once)
+        nb = lambda t: 0 if t is None else t.numel() * t.element_size()      # noqa: E731
+        if name == "layernorm":
+            return ("byte", nb(a[0]) + nb(k.get("out_bf16")) + nb(k.get("out_f32")))
+        if name == "rmsnorm_residual":
+            return ("byte", nb(a[0]) * (2 if k.get("branch") is not None else 1) + nb(k.get("branch")) + nb(k.get("out_bf16")))
+        if name == "rope_kv":
+            return ("byte", nb(a[0]) + nb(a[1]) + 2.0 * a[1].numel() * k["hkv"] / k["hq"] * 2)
+        if name == "decode_attention":
+            return ("byte", 2.0 * k["batch"] * k["ctx"] * k["hkv"] * k["d"] * 2)
+        if name == "gemm_skinny":
+            return ("byte", nb(a[1]) + nb(a[0]))
+        if name == "bilinear_nhwc":
+            return ("byte", nb(a[0]) + nb(a[1]) + nb(k.get("add")) + nb(k.get("out_relu")))
+        if name == "zoe_depth_tail":
+            return ("byte", nb(a[0]) + nb(a[1]) + nb(a[5]) + nb(a[6]))
+        if name == "zoe_attractor":
+            return ("byte", nb(a[0]) + nb(a[1]) + nb(a[2]))
         return ("none", 0.0)
 
     def summary(self):
@@ -138,10 +156,11 @@ class TimedOps:
         self.by_shape = {}
         for name, (kind, work), s, e, shape in self.records:
             ms = s.elapsed_time(e)
-            d = agg.setdefault(name, {"ms": 0.0, "calls": 0, "flop": 0.0})
+            d = agg.setdefault(name, {"ms": 0.0, "calls": 0, "flop": 0.0, "byte": 0.0})
             d["ms"] += ms
             d["calls"] += 1
             d["flop"] += work if kind == "flop" else 0.0
+            d["byte"] += work if kind == "byte" else 0.0
             if shape:
                 b = self.by_shape.setdefault((name, shape), {"ms": 0.0, "calls": 0, "flop": 0.0})
                 b["ms"] += ms
@@ -251,7 +270,7 @@ def run_ours(args):
     eng.ops, eng.use_graphs = ops, True
     total_ms = sum(d["ms"] for d in agg.values())
     for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
-        extra = f" {d['flop'] / d['ms'] / 1e9:8.1f} TFLOP/s" if d["flop"] else ""
+        extra = f" {d['flop'] / d['ms'] / 1e9:8.1f} TFLOP/s" if d["flop"] else (f" {d['byte'] / d['ms'] / 1e6:8.0f} GB/s (eager; small launches are host-gapped)" if d.get("byte") else "")
         log(f"  {name:22s} {d['calls']:5d} calls {d['ms']:9.2f} ms {100 * d['ms'] / total_ms:5.1f}%{extra}")
     for (name, shape), d in sorted(timed.by_shape.items(), key=lambda kv: -kv[1]["ms"])[:28]:
         log(f"    {name:10s} {shape:58s} x{d['calls']:4d} {d['ms']:8.2f} ms  {d['flop'] / max(d['ms'], 1e-9) / 1e9:7.1f} TFLOP/s")

@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "lib", "libspatialvla_b200.so")
-SOURCES = ["capi.cu", "gemm_tcgen05.cu", "gemm_skinny.cu", "attention.cu", "fused_ops.cu", "tokenizer.cu"]
+SOURCES = ["capi.cu", "gemm_tcgen05.cu", "gemm_skinny.cu", "attention.cu", "attention_tc.cu", "fused_ops.cu", "tokenizer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -10,6 +10,8 @@
 //
 // G3 (svla_decode_attention): q_len = 1 over the KV cache, one CTA per (batch, kv head) serving the whole GQA
 // group, HBM-bound (reads each K/V row once, 16-byte loads).
+#include <cstdlib>
+#include <cstring>
 #include "svla_common.cuh"
 
 namespace {
@@ -468,6 +470,18 @@ svla_decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16
 
 }  // namespace
 
+int svla_attention_tc_try(const SvlaAttnArgs* a, void* stream);      // attention_tc.cu (tcgen05 / TMEM / TMA)
+
+// SVLA_ATTN_IMPL=mma forces the mma.sync kernel everywhere (A/B measurements, debugging)
+static bool attn_tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SVLA_ATTN_IMPL");
+    v = (e && strcmp(e, "mma") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 extern "C" int svla_attention(const SvlaAttnArgs* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SVLA_REQUIRE(a && a->q && a->k && a->v && a->out, "svla_attention: null pointer");
@@ -479,6 +493,10 @@ extern "C" int svla_attention(const SvlaAttnArgs* a, void* stream) {
                "svla_attention: sequence longer than the relative-position window");
   SVLA_REQUIRE((a->q_ss % 8) == 0 && (a->k_ss % 8) == 0 && (a->v_ss % 8) == 0 && (a->o_ss % 2) == 0,
                "svla_attention: row strides must keep 16-byte alignment");
+  if (attn_tc_enabled()) {
+    const int rc = svla_attention_tc_try(a, stream);      // 1 = shape not covered by the tcgen05 kernel
+    if (rc != 1) return rc;
+  }
   AttnP p;
   p.q = static_cast<const __nv_bfloat16*>(a->q); p.k = static_cast<const __nv_bfloat16*>(a->k);
   p.v = static_cast<const __nv_bfloat16*>(a->v); p.out = static_cast<__nv_bfloat16*>(a->out);

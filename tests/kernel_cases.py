@@ -285,6 +285,14 @@ ATTN_CASES = [
     attn_case("attn_gemma_prefill_d256", 2, 4, 2, 278, 278, 256, scale=1 / 16, softcap=50.0, smax=290),
     attn_case("attn_gemma_causal_d256", 1, 2, 1, 70, 70, 256, scale=1 / 16, softcap=50.0, causal=True, smax=80),
     attn_case("attn_d128_generic", 1, 2, 2, 100, 130, 128, causal=False, smax=130),
+    # tcgen05 path (attention_tc.cu): batch > 1 through the 3-D tensor maps, ragged tails, sharp softmax (lazy O
+    # rescale fires), large soft-cap arguments (libm tanh branch), causal tile skipping, GQA, sq != sk
+    attn_case("attn_tc_beit_batch3", 3, 4, 4, 577, 577, 64, packed_qkv=True, relpos_win=24, seed=5),
+    attn_case("attn_tc_d64_sharp_relpos", 2, 3, 3, 577, 577, 64, packed_qkv=True, relpos_win=24, scale=1.0, seed=6),
+    attn_case("attn_tc_d64_plain_ragged", 2, 2, 2, 130, 200, 64, smax=210, seed=7),
+    attn_case("attn_tc_d64_tiny", 1, 1, 1, 1, 1, 64, smax=8, seed=8),
+    attn_case("attn_tc_d256_sharp_softcap", 3, 8, 4, 278, 278, 256, scale=0.5, softcap=50.0, smax=290, seed=9),
+    attn_case("attn_tc_d256_causal_offset", 2, 4, 2, 200, 260, 256, scale=0.25, softcap=50.0, causal=True, smax=300, seed=10),
     decode_attn_case,
 ]
 

@@ -116,6 +116,14 @@ int svla_attention(const SvlaAttnArgs* args, void* stream);
 int svla_decode_attention(const void* q, const void* kcache, const void* vcache, void* out, int batch, int hq,
                           int hkv, int d, int smax, int ctx, float scale, float softcap, void* stream);
 
+/* G3f: decode step after the qkv projection in ONE launch: RoPE of the new token's q/k (1-indexed position ctx), append of
+ * its k/v at cache slot ctx-1, soft-capped softmax attention over slots [0, ctx) (model/modeling_gemma2.py:95-154,169-195,
+ * 376-395). qkv_f32 = n_partials split-K partial sums [n_partials][B][(hq+2hkv)*D] of svla_gemm_skinny (partial_stride in
+ * elements); kcache/vcache bf16 [B, smax, hkv, D]; out bf16 [B, hq*D]. D = 256, hq/hkv in {1, 2}. */
+int svla_decode_attention_fused(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache, void* vcache,
+                                void* out, int batch, int hq, int hkv, int d, int smax, int ctx, float theta, float scale,
+                                float softcap, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Memory-bound fused kernels
  * --------------------------------------------------------------------------------------------------- */
@@ -187,7 +195,8 @@ int svla_zoe_router_embed(const float* conv, float* e, void* e_bf16, int batch, 
 
 /* ZoeDepth metric-bins tail (HF zoedepth :551-570,665-746): softplus attractors, bilinear(align_corners)
  * upsampling of the previous bin centres, inverse-attractor update with alpha=300, gamma=2, mean over na.
- * attr bf16 [B*oh*ow, na] (pre-softplus), prev fp32 NHWC [B, h, w, nbins] -> out fp32 NHWC [B, oh, ow, nbins] */
+ * attr bf16 [B*oh*ow, na] (pre-softplus), prev fp32 NHWC [B, h, w, nbins] -> out fp32 NHWC [B, oh, ow, nbins];
+ * na <= 16, nbins % 4 == 0 (the reference has na in {16, 8, 4, 1}, nbins = 64) */
 int svla_zoe_attractor(const void* attr, const float* prev, float* out, int batch, int h, int w, int oh, int ow,
                        int na, int nbins, void* stream);
 

@@ -163,6 +163,12 @@ class RefOps:
         p = torch.softmax(s, -1).to(BF16).float()
         out.view(batch, hq, d)[:] = (p @ V).squeeze(2).to(BF16)
 
+    def decode_attention_fused(self, qkv_partials, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, theta, scale, softcap=0.0):
+        q = torch.empty(batch, hq * d, dtype=BF16)
+        self.rope_kv(qkv_partials, q, kcache, vcache, batch=batch, s=1, hq=hq, hkv=hkv, d=d, smax=smax, pos0=ctx - 1, theta=theta)
+        self.launches -= 1                      # one launch on the device
+        self.decode_attention(q, kcache, vcache, out, batch=batch, hq=hq, hkv=hkv, d=d, smax=smax, ctx=ctx, scale=scale, softcap=softcap)
+
     # ---- fused memory-bound ops
     def layernorm(self, x, gamma, beta, eps, *, out_bf16=None, out_f32=None, relu=False):
         self.launches += 1

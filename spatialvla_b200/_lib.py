@@ -65,6 +65,7 @@ SIGNATURES = {
     "svla_gemm_skinny_splits": (_I, [_L, _L]),
     "svla_attention": (_I, [C.POINTER(SvlaAttnArgs), _P]),
     "svla_decode_attention": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
+    "svla_decode_attention_fused": (_I, [_P, _I, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P]),
     "svla_layernorm": (_I, [_P, _P, _P, _F, _L, _I, _P, _P, _I, _P]),
     "svla_rmsnorm_residual": (_I, [_P, _P, _P, _P, _F, _L, _I, _P, _I, _L, _P]),
     "svla_rope_kv": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _I, _L, _P]),

@@ -77,11 +77,23 @@ svla_rmsnorm_residual_kernel(float* __restrict__ x, const float* __restrict__ br
   if (branch) {
     float4 bv[kMaxVec];
     load_row(branch + row * cols, cols, bv);
-    for (int sp = 1; sp < n_partials; ++sp) {           // split-K partial sums, added in a fixed order
-      float4 pv[kMaxVec];
-      load_row(branch + sp * partial_stride + row * cols, cols, pv);
+    // split-K partial sums, added in a fixed order; four partial rows are in flight per trip (the decode step is
+    // latency-bound: 64 rows, one block each -- serialised L2 round trips were 60% of this kernel)
+    for (int sp = 1; sp < n_partials; sp += 4) {
+      float4 pv[4][kMaxVec];
 #pragma unroll
-      for (int k = 0; k < kMaxVec; ++k) { bv[k].x += pv[k].x; bv[k].y += pv[k].y; bv[k].z += pv[k].z; bv[k].w += pv[k].w; }
+      for (int u = 0; u < 4; ++u) {
+        if (sp + u < n_partials) load_row(branch + (sp + u) * partial_stride + row * cols, cols, pv[u]);
+        else {
+#pragma unroll
+          for (int k = 0; k < kMaxVec; ++k) pv[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int k = 0; k < kMaxVec; ++k) { bv[k].x += pv[u][k].x; bv[k].y += pv[u][k].y; bv[k].z += pv[u][k].z; bv[k].w += pv[u][k].w; }
+      }
     }
     float ss = 0.f;
 #pragma unroll
@@ -514,26 +526,28 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
   for (int u = 0; u < 4; ++u) { f[2 * u] = bf16_bits_to_float(w[u] & 0xFFFFu); f[2 * u + 1] = bf16_bits_to_float(w[u] >> 16); }
 }
 
-// bilinear, align_corners=True, NHWC bf16, 8 channels per thread
-__global__ void svla_bilinear_nhwc_kernel(const uint4* __restrict__ x, const uint4* __restrict__ add, uint4* __restrict__ out,
-                                          uint4* __restrict__ out_relu, int h, int w, int c8, int oh, int ow, long long total) {
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (idx >= total) return;
-  const int cc = static_cast<int>(idx % c8);
-  long long r = idx / c8;
-  const int ox = static_cast<int>(r % ow); r /= ow;
-  const int oy = static_cast<int>(r % oh);
-  const long long b = r / oh;
+// bilinear, align_corners=True, NHWC bf16, 8 channels per thread.  grid = (chunks of an output row, oy, batch): the
+// row / batch coordinates come from the block index, so the per-thread index math is one 32-bit division.
+__global__ void __launch_bounds__(256)
+svla_bilinear_nhwc_kernel(const uint4* __restrict__ x, const uint4* __restrict__ add, uint4* __restrict__ out,
+                          uint4* __restrict__ out_relu, int h, int w, int c8, int oh, int ow) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;           // position inside the output row, in uint4 units
+  if (i >= static_cast<unsigned>(ow) * c8) return;
+  const int ox = static_cast<int>(i / static_cast<unsigned>(c8));
+  const int cc = static_cast<int>(i - static_cast<unsigned>(ox) * c8);
+  const int oy = blockIdx.y;
+  const long long b = blockIdx.z;
   const float sy = (oh > 1) ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) * oy : 0.f;
   const float sx = (ow > 1) ? static_cast<float>(w - 1) / static_cast<float>(ow - 1) * ox : 0.f;
   const int y0 = min(static_cast<int>(sy), h - 1), x0 = min(static_cast<int>(sx), w - 1);
   const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
   const float ly = sy - y0, lx = sx - x0;
+  const uint4* r0 = x + (b * h + y0) * static_cast<long long>(w) * c8 + cc;
+  const uint4* r1 = x + (b * h + y1) * static_cast<long long>(w) * c8 + cc;
+  const uint4 q00 = r0[x0 * c8], q01 = r0[x1 * c8], q10 = r1[x0 * c8], q11 = r1[x1 * c8];
+  const long long idx = (b * oh + oy) * static_cast<long long>(ow) * c8 + i;
   float f00[8], f01[8], f10[8], f11[8], o[8];
-  unpack8(x[((b * h + y0) * w + x0) * c8 + cc], f00);
-  unpack8(x[((b * h + y0) * w + x1) * c8 + cc], f01);
-  unpack8(x[((b * h + y1) * w + x0) * c8 + cc], f10);
-  unpack8(x[((b * h + y1) * w + x1) * c8 + cc], f11);
+  unpack8(q00, f00); unpack8(q01, f01); unpack8(q10, f10); unpack8(q11, f11);
 #pragma unroll
   for (int e = 0; e < 8; ++e)
     o[e] = (1.f - ly) * ((1.f - lx) * f00[e] + lx * f01[e]) + ly * ((1.f - lx) * f10[e] + lx * f11[e]);
@@ -605,38 +619,60 @@ __device__ __forceinline__ float bilin_bf16(const __nv_bfloat16* __restrict__ ba
   return (1.f - s.ly) * ((1.f - s.lx) * v00 + s.lx * v01) + s.ly * ((1.f - s.lx) * v10 + s.lx * v11);
 }
 
-// one warp per output pixel; lane handles bins lane, lane+32, ...
+// Attractor step of one metric-bins stage.  16 lanes per output pixel, one float4 (4 bins) per lane and pass; a block is 16
+// consecutive pixels of one output row, (row, batch) come from the block index (no per-pixel integer division).
 __global__ void __launch_bounds__(256)
 svla_zoe_attractor_kernel(const __nv_bfloat16* __restrict__ attr, const float* __restrict__ prev, float* __restrict__ out, int h,
-                          int w, int oh, int ow, int na, int nbins, long long npix) {
-  const int lane = threadIdx.x & 31;
-  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-  const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
-  for (long long pix = warp_global; pix < npix; pix += nwarps) {
-    const int ox = static_cast<int>(pix % ow);
-    const int oy = static_cast<int>((pix / ow) % oh);
-    const long long b = pix / (static_cast<long long>(ow) * oh);
-    const float a_l = (lane < na) ? softplus_f(__bfloat162float(attr[pix * na + lane])) : 0.f;
-    const Bilin s = make_bilin(oy, ox, h, w, oh, ow);
-    const float* pb = prev + b * h * w * nbins;
-    for (int k = lane; k < nbins; k += 32) {
-      const float c = bilin_f32(pb, s, w, nbins, k);
-      float delta = 0.f;
-      for (int a = 0; a < na; ++a) {
-        const float dx = __shfl_sync(0xffffffffu, a_l, a) - c;
-        delta += dx / (1.f + 300.f * dx * dx);
-      }
-      out[pix * nbins + k] = c + delta / static_cast<float>(na);
+                          int w, int oh, int ow, int na, int nbins) {
+  const int lane = threadIdx.x & 31, sub = threadIdx.x & 15, grp = threadIdx.x >> 4;
+  const int ox_raw = blockIdx.x * 16 + grp, oy = blockIdx.y;
+  const bool active = ox_raw < ow;
+  const int ox = active ? ox_raw : ow - 1;                    // idle groups shadow the last pixel (shuffles stay warp-wide)
+  const long long b = blockIdx.z;
+  const long long pix = (b * oh + oy) * ow + ox;
+  const float a_l = (sub < na) ? softplus_f(__bfloat162float(attr[pix * na + sub])) : 0.f;
+  const Bilin s = make_bilin(oy, ox, h, w, oh, ow);
+  const int nb4 = nbins >> 2;
+  const float4* pb = reinterpret_cast<const float4*>(prev + b * h * w * nbins);
+  const float4* p00 = pb + (static_cast<long long>(s.y0) * w + s.x0) * nb4;
+  const float4* p01 = pb + (static_cast<long long>(s.y0) * w + s.x1) * nb4;
+  const float4* p10 = pb + (static_cast<long long>(s.y1) * w + s.x0) * nb4;
+  const float4* p11 = pb + (static_cast<long long>(s.y1) * w + s.x1) * nb4;
+  const float inv_na = 1.f / static_cast<float>(na);
+  float4* ob = reinterpret_cast<float4*>(out + pix * nbins);
+  for (int base = 0; base < nb4; base += 16) {
+    const int k4 = base + sub;
+    const bool valid = k4 < nb4;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      const float4 v00 = p00[k4], v01 = p01[k4], v10 = p10[k4], v11 = p11[k4];
+      // same association as bilin_f32: (1-ly)*((1-lx) v00 + lx v01) + ly*((1-lx) v10 + lx v11)
+      c.x = (1.f - s.ly) * ((1.f - s.lx) * v00.x + s.lx * v01.x) + s.ly * ((1.f - s.lx) * v10.x + s.lx * v11.x);
+      c.y = (1.f - s.ly) * ((1.f - s.lx) * v00.y + s.lx * v01.y) + s.ly * ((1.f - s.lx) * v10.y + s.lx * v11.y);
+      c.z = (1.f - s.ly) * ((1.f - s.lx) * v00.z + s.lx * v01.z) + s.ly * ((1.f - s.lx) * v10.z + s.lx * v11.z);
+      c.w = (1.f - s.ly) * ((1.f - s.lx) * v00.w + s.lx * v01.w) + s.ly * ((1.f - s.lx) * v10.w + s.lx * v11.w);
     }
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < na; ++a) {
+      const float av = __shfl_sync(0xffffffffu, a_l, (lane & 16) | a);
+      const float dx = av - c.x, dy = av - c.y, dz = av - c.z, dw = av - c.w;
+      d.x += __fdividef(dx, fmaf(300.f * dx, dx, 1.f));
+      d.y += __fdividef(dy, fmaf(300.f * dy, dy, 1.f));
+      d.z += __fdividef(dz, fmaf(300.f * dz, dz, 1.f));
+      d.w += __fdividef(dw, fmaf(300.f * dw, dw, 1.f));
+    }
+    if (valid && active) ob[k4] = make_float4(c.x + d.x * inv_na, c.y + d.y * inv_na, c.z + d.z * inv_na, c.w + d.w * inv_na);
   }
 }
 
-// one warp per output pixel (nbins <= 64, nh <= 64)
+// Conditional log-binomial tail: 4 lanes per output pixel (each lane: a quarter of the hidden channels, then a quarter of the
+// bins), a block is 64 consecutive pixels of one output row.  Two cheap passes over the bins (max of the logits needs no
+// loads, the second pass reads the 4 bilinear taps as float4) replace the 8 warp-wide reductions of a warp-per-pixel map.
 __global__ void __launch_bounds__(256)
 svla_zoe_depth_tail_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloat16* __restrict__ e, const float* __restrict__ b1,
                            const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ bins,
                            float* __restrict__ depth, int h, int w, int oh, int ow, int nh, int nbins, float min_temp,
-                           float max_temp, long long npix) {
+                           float max_temp) {
   // per-block tables: log C(K-1, k) in the reference's Stirling form (HF zoedepth log_binom, eps = 1e-7), MLP weights
   __shared__ float s_lb[64];
   __shared__ float s_w2[4 * 64];
@@ -649,66 +685,91 @@ svla_zoe_depth_tail_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloa
   for (int i = threadIdx.x; i < 4 * nh; i += blockDim.x) s_w2[i] = w2[i];
   for (int i = threadIdx.x; i < nh; i += blockDim.x) s_b1[i] = b1[i];
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  // each warp walks a contiguous run of pixels (row-major) so that coordinates advance incrementally and the
-  // bilinear taps of neighbouring pixels hit L1
-  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-  const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
-  const long long per_warp = (npix + nwarps - 1) / nwarps;
-  const long long pix_begin = warp_global * per_warp;
-  const long long pix_end = pix_begin + per_warp < npix ? pix_begin + per_warp : npix;
-  const float ry = (oh > 1) ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) : 0.f;
-  const float rx = (ow > 1) ? static_cast<float>(w - 1) / static_cast<float>(ow - 1) : 0.f;
-  int ox = pix_begin < npix ? static_cast<int>(pix_begin % ow) : 0;
-  int oy = pix_begin < npix ? static_cast<int>((pix_begin / ow) % oh) : 0;
-  long long b = pix_begin < npix ? pix_begin / (static_cast<long long>(ow) * oh) : 0;
-  for (long long pix = pix_begin; pix < pix_end; ++pix) {
-    Bilin s;
-    {
-      const float sy = ry * oy, sx = rx * ox;
-      s.y0 = min(static_cast<int>(sy), h - 1); s.x0 = min(static_cast<int>(sx), w - 1);
-      s.y1 = min(s.y0 + 1, h - 1); s.x1 = min(s.x0 + 1, w - 1);
-      s.ly = sy - s.y0; s.lx = sx - s.x0;
+  const int sub = threadIdx.x & 3, grp = threadIdx.x >> 2;
+  const int ox_raw = blockIdx.x * 64 + grp, oy = blockIdx.y;
+  const bool active = ox_raw < ow;
+  const int ox = active ? ox_raw : ow - 1;
+  const long long b = blockIdx.z;
+  const long long pix = (b * oh + oy) * ow + ox;
+  const Bilin s = make_bilin(oy, ox, h, w, oh, ow);
+  const long long o00 = static_cast<long long>(s.y0) * w + s.x0, o01 = static_cast<long long>(s.y0) * w + s.x1;
+  const long long o10 = static_cast<long long>(s.y1) * w + s.x0, o11 = static_cast<long long>(s.y1) * w + s.x1;
+  // ---- hidden = gelu(W_a*last + up(W_b*emb) + b1) -> 4 outputs (this lane: channels [ch0, ch1))
+  float o4[4] = {0.f, 0.f, 0.f, 0.f};
+  const int cpl = (nh + 3) >> 2;
+  const int ch0 = sub * cpl, ch1 = min(nh, ch0 + cpl);
+  const __nv_bfloat16* eb = e + b * h * w * nh;
+  const __nv_bfloat16* tp = t + pix * nh;
+  if (((nh | cpl) & 1) == 0) {
+    for (int ch = ch0; ch < ch1; ch += 2) {
+      const float2 tv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(tp + ch));
+      const float2 v00 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(eb + o00 * nh + ch));
+      const float2 v01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(eb + o01 * nh + ch));
+      const float2 v10 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(eb + o10 * nh + ch));
+      const float2 v11 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(eb + o11 * nh + ch));
+      const float ex = (1.f - s.ly) * ((1.f - s.lx) * v00.x + s.lx * v01.x) + s.ly * ((1.f - s.lx) * v10.x + s.lx * v11.x);
+      const float ey = (1.f - s.ly) * ((1.f - s.lx) * v00.y + s.lx * v01.y) + s.ly * ((1.f - s.lx) * v10.y + s.lx * v11.y);
+      const float hx = gelu_erf_fast(tv.x + ex + s_b1[ch]), hy = gelu_erf_fast(tv.y + ey + s_b1[ch + 1]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o4[q] += s_w2[q * nh + ch] * hx + s_w2[q * nh + ch + 1] * hy;
     }
-    const long long b_cur = b;
-    if (++ox == ow) { ox = 0; if (++oy == oh) { oy = 0; ++b; } }
-    // hidden = gelu(W_a*last + up(W_b*emb) + b1), then 4 outputs
-    float o4[4] = {0.f, 0.f, 0.f, 0.f};
-    const __nv_bfloat16* eb = e + b_cur * h * w * nh;
-    for (int ch = lane; ch < nh; ch += 32) {
-      const float hv = gelu_erf_fast(__bfloat162float(t[pix * nh + ch]) + bilin_bf16(eb, s, w, nh, ch) + s_b1[ch]);
+  } else {
+    for (int ch = ch0; ch < ch1; ++ch) {
+      const float hv = gelu_erf_fast(__bfloat162float(tp[ch]) + bilin_bf16(eb, s, w, nh, ch) + s_b1[ch]);
 #pragma unroll
       for (int q = 0; q < 4; ++q) o4[q] += s_w2[q * nh + ch] * hv;
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) o4[q] = softplus_fast(warp_sum(o4[q]) + b2[q]);
-    const float p0 = o4[0] + 1e-4f, p1 = o4[1] + 1e-4f, t0 = o4[2] + 1e-4f, t1 = o4[3] + 1e-4f;
-    const float prob = p0 / (p0 + p1);
-    const float temp = (max_temp - min_temp) * (t0 / (t0 + t1)) + min_temp;
-    const float lp = __logf(fminf(fmaxf(prob, 1e-4f), 1.f)), lq = __logf(fminf(fmaxf(1.f - prob, 1e-4f), 1.f));
-    // y_k = log C(K-1, k) (Stirling form with the reference's eps) + k log p + (K-1-k) log(1-p)
-    float y[2], c[2];
-    float mx = -INFINITY;
-    const float* bb = bins + b_cur * h * w * nbins;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int k = lane + 32 * r;
-      if (k < nbins) {
-        y[r] = (s_lb[k] + static_cast<float>(k) * lp + static_cast<float>(nbins - 1 - k) * lq) / temp;
-        c[r] = bilin_f32(bb, s, w, nbins, k);
-        mx = fmaxf(mx, y[r]);
-      } else { y[r] = -INFINITY; c[r] = 0.f; }
-    }
-    mx = warp_max(mx);
-    float se = 0.f, sc = 0.f;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const float ex = (y[r] == -INFINITY) ? 0.f : __expf(y[r] - mx);
-      se += ex; sc += ex * c[r];
-    }
-    se = warp_sum(se); sc = warp_sum(sc);
-    if (lane == 0) depth[pix] = sc / se;
   }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    o4[q] += __shfl_xor_sync(0xffffffffu, o4[q], 1);
+    o4[q] += __shfl_xor_sync(0xffffffffu, o4[q], 2);
+    o4[q] = softplus_fast(o4[q] + b2[q]);
+  }
+  const float p0 = o4[0] + 1e-4f, p1 = o4[1] + 1e-4f, t0 = o4[2] + 1e-4f, t1 = o4[3] + 1e-4f;
+  const float prob = p0 / (p0 + p1);
+  const float temp = (max_temp - min_temp) * (t0 / (t0 + t1)) + min_temp;
+  const float lp = __logf(fminf(fmaxf(prob, 1e-4f), 1.f)), lq = __logf(fminf(fmaxf(1.f - prob, 1e-4f), 1.f));
+  const float inv_temp = 1.f / temp;
+  // ---- y_k = (log C(K-1, k) + k log p + (K-1-k) log(1-p)) / temp; softmax over k; depth = sum_k softmax_k * centre_k
+  const int bpl = (nbins + 3) >> 2;
+  const int k0 = sub * bpl, k1 = min(nbins, k0 + bpl);
+  float mx = -INFINITY;
+  for (int k = k0; k < k1; ++k)
+    mx = fmaxf(mx, (s_lb[k] + static_cast<float>(k) * lp + static_cast<float>(nbins - 1 - k) * lq) * inv_temp);
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  float se = 0.f, sc = 0.f;
+  const float* bb = bins + b * h * w * nbins;
+  if (((nbins | bpl) & 3) == 0) {
+    const float4* q00 = reinterpret_cast<const float4*>(bb + o00 * nbins), *q01 = reinterpret_cast<const float4*>(bb + o01 * nbins);
+    const float4* q10 = reinterpret_cast<const float4*>(bb + o10 * nbins), *q11 = reinterpret_cast<const float4*>(bb + o11 * nbins);
+#pragma unroll 4
+    for (int k = k0; k < k1; k += 4) {
+      const float4 v00 = q00[k >> 2], v01 = q01[k >> 2], v10 = q10[k >> 2], v11 = q11[k >> 2];
+      const float c0 = (1.f - s.ly) * ((1.f - s.lx) * v00.x + s.lx * v01.x) + s.ly * ((1.f - s.lx) * v10.x + s.lx * v11.x);
+      const float c1 = (1.f - s.ly) * ((1.f - s.lx) * v00.y + s.lx * v01.y) + s.ly * ((1.f - s.lx) * v10.y + s.lx * v11.y);
+      const float c2 = (1.f - s.ly) * ((1.f - s.lx) * v00.z + s.lx * v01.z) + s.ly * ((1.f - s.lx) * v10.z + s.lx * v11.z);
+      const float c3 = (1.f - s.ly) * ((1.f - s.lx) * v00.w + s.lx * v01.w) + s.ly * ((1.f - s.lx) * v10.w + s.lx * v11.w);
+      const float cs[4] = {c0, c1, c2, c3};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = k + i;
+        const float y = (s_lb[kk] + static_cast<float>(kk) * lp + static_cast<float>(nbins - 1 - kk) * lq) * inv_temp;
+        const float ex = __expf(y - mx);
+        se += ex; sc += ex * cs[i];
+      }
+    }
+  } else {
+    for (int k = k0; k < k1; ++k) {
+      const float y = (s_lb[k] + static_cast<float>(k) * lp + static_cast<float>(nbins - 1 - k) * lq) * inv_temp;
+      const float ex = __expf(y - mx);
+      se += ex; sc += ex * bilin_f32(bb, s, w, nbins, k);
+    }
+  }
+  se += __shfl_xor_sync(0xffffffffu, se, 1); se += __shfl_xor_sync(0xffffffffu, se, 2);
+  sc += __shfl_xor_sync(0xffffffffu, sc, 1); sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+  if (sub == 0 && active) depth[pix] = sc / se;
 }
 
 // ------------------------------------------------------------------------------------------ M5 Ego3D
@@ -912,10 +973,11 @@ extern "C" int svla_im2col3x3_s2(const void* x, void* a, int batch, int h, int w
 extern "C" int svla_bilinear_nhwc(const void* x, const void* add, void* out, void* out_relu, int batch, int h, int w, int c,
                                   int oh, int ow, void* stream) {
   SVLA_REQUIRE(x && (out || out_relu) && batch > 0 && (c % 8) == 0, "svla_bilinear_nhwc: bad arguments");
-  const long long total = static_cast<long long>(batch) * oh * ow * (c / 8);
-  svla_bilinear_nhwc_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  SVLA_REQUIRE(oh <= 65535 && batch <= 65535 && static_cast<long long>(ow) * (c / 8) < (1LL << 31), "svla_bilinear_nhwc: grid too large");
+  dim3 grid(blocks_for(static_cast<long long>(ow) * (c / 8), 256), oh, batch);
+  svla_bilinear_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), static_cast<const uint4*>(add), static_cast<uint4*>(out), static_cast<uint4*>(out_relu), h, w,
-      c / 8, oh, ow, total);
+      c / 8, oh, ow);
   SVLA_LAUNCH_CHECK("svla_bilinear_nhwc");
   return 0;
 }
@@ -944,12 +1006,12 @@ extern "C" int svla_zoe_router_embed(const float* conv, float* e, void* e_bf16, 
 
 extern "C" int svla_zoe_attractor(const void* attr, const float* prev, float* out, int batch, int h, int w, int oh, int ow, int na,
                                   int nbins, void* stream) {
-  SVLA_REQUIRE(attr && prev && out && batch > 0 && na > 0 && na <= 32 && nbins > 0, "svla_zoe_attractor: bad arguments");
-  const long long npix = static_cast<long long>(batch) * oh * ow;
-  const long long want = (npix + 7) / 8;
-  const unsigned blocks = static_cast<unsigned>(want < 148LL * 32 ? want : 148LL * 32);
-  svla_zoe_attractor_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(attr), prev, out, h, w, oh, ow, na, nbins, npix);
+  SVLA_REQUIRE(attr && prev && out && batch > 0 && na > 0 && na <= 16 && nbins > 0 && (nbins % 4) == 0,
+               "svla_zoe_attractor: bad arguments (need na <= 16, nbins %% 4 == 0)");
+  SVLA_REQUIRE(oh <= 65535 && batch <= 65535, "svla_zoe_attractor: grid too large");
+  dim3 grid((ow + 15) / 16, oh, batch);
+  svla_zoe_attractor_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(attr), prev, out, h, w, oh, ow, na, nbins);
   SVLA_LAUNCH_CHECK("svla_zoe_attractor");
   return 0;
 }
@@ -959,12 +1021,11 @@ extern "C" int svla_zoe_depth_tail(const void* t, const void* e, const float* b1
                                    float min_temp, float max_temp, void* stream) {
   SVLA_REQUIRE(t && e && b1 && w2 && b2 && bins && depth, "svla_zoe_depth_tail: null pointer");
   SVLA_REQUIRE(batch > 0 && nbins > 0 && nbins <= 64 && nh > 0 && nh <= 64, "svla_zoe_depth_tail: bad geometry");
-  const long long npix = static_cast<long long>(batch) * oh * ow;
-  const long long want = (npix + 7) / 8;
-  const unsigned blocks = static_cast<unsigned>(want < 148LL * 32 ? want : 148LL * 32);
-  svla_zoe_depth_tail_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  SVLA_REQUIRE(oh <= 65535 && batch <= 65535, "svla_zoe_depth_tail: grid too large");
+  dim3 grid((ow + 63) / 64, oh, batch);
+  svla_zoe_depth_tail_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(t), static_cast<const __nv_bfloat16*>(e), b1, w2, b2, bins, depth, h, w, oh, ow, nh, nbins,
-      min_temp, max_temp, npix);
+      min_temp, max_temp);
   SVLA_LAUNCH_CHECK("svla_zoe_depth_tail");
   return 0;
 }

@@ -524,6 +524,18 @@ class SpatialVLAEngine:
                 qkv = self._skinny_partial(h, L_["wqkv"], M)
             else:
                 qkv = self._lin(h, L_["wqkv"], M)
+            if skinny and hd == 256 and nh // nkv in (1, 2):
+                # decode: RoPE + cache append + attention over the cache in one launch
+                ops.decode_attention_fused(qkv, kc, vc, ctx, batch=B, hq=nh, hkv=nkv, d=hd, smax=smax, ctx=pos0 + 1, theta=theta,
+                                           scale=scale, softcap=cap)
+                br = self._skinny_partial(ctx, L_["wo"], M)
+                ops.rmsnorm_residual(x, branch=br, w_post=L_["ln_post_attn"], w_pre=L_["ln_pre_ff"], eps=eps, out_bf16=h)
+                act = ops.empty((M, FF), BF16)
+                ops.gemm_skinny(h, L_["wgu"], out_bf16=act, geglu=True)
+                br = self._skinny_partial(act, L_["wd"], M)
+                nxt = g["layers"][li + 1]["ln_in"] if li + 1 < len(g["layers"]) else g["final"]
+                ops.rmsnorm_residual(x, branch=br, w_post=L_["ln_post_ff"], w_pre=nxt, eps=eps, out_bf16=h)
+                continue
             ops.rope_kv(qkv, q, kc, vc, batch=B, s=S, hq=nh, hkv=nkv, d=hd, smax=smax, pos0=pos0, theta=theta)
             if S == 1:
                 ops.decode_attention(q, kc, vc, ctx, batch=B, hq=nh, hkv=nkv, d=hd, smax=smax, ctx=pos0 + 1, scale=scale, softcap=cap)

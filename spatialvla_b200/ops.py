@@ -144,6 +144,15 @@ class CudaOps:
                                                smax, ctx, float(scale), float(softcap or 0.0), self._stream()),
                 "svla_decode_attention")
 
+    def decode_attention_fused(self, qkv_partials, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, theta, scale, softcap=0.0):
+        """RoPE + KV-cache append + attention of one decode step; qkv_partials fp32 [splits, batch, (hq+2hkv)*d]."""
+        _req(qkv_partials.dtype == F32 and qkv_partials.dim() == 3 and qkv_partials.stride(2) == 1 and
+             qkv_partials.stride(1) == qkv_partials.shape[2], "decode_attention_fused: qkv must be fp32 [splits, batch, W]")
+        L.check(self.lib.svla_decode_attention_fused(_ptr(qkv_partials), int(qkv_partials.shape[0]), int(qkv_partials.stride(0)),
+                                                     _ptr(kcache), _ptr(vcache), _ptr(out), batch, hq, hkv, d, smax, ctx,
+                                                     float(theta), float(scale), float(softcap or 0.0), self._stream()),
+                "svla_decode_attention_fused")
+
     # ---- memory-bound fused ops
     def layernorm(self, x, gamma, beta, eps, *, out_bf16=None, out_f32=None, relu=False):
         _req(x.dtype == F32 and x.is_contiguous(), "layernorm: x must be contiguous fp32")

@@ -278,6 +278,31 @@ def decode_attn_case(dev="cuda:0"):
     return res
 
 
+def decode_attn_fused_case(dev="cuda:0"):
+    """RoPE + cache append + attention in one launch vs the rope_kv -> decode_attention composition of the reference ops."""
+    res = Result("decode_attention_fused")
+    for tag, (B, hq, hkv, smax, ctx, splits) in {"gqa2_ctx271": (3, 4, 2, 300, 271, 3), "first_token": (2, 4, 2, 16, 1, 1),
+                                                  "mha_ctx33": (2, 2, 2, 40, 33, 2), "chunk_edge_ctx65": (1, 8, 4, 65, 65, 4),
+                                                  "ctx64": (2, 8, 4, 290, 64, 4)}.items():
+        g = _gen(ctx)
+        d = 256
+        W = (hq + 2 * hkv) * d
+        part = _randn(g, splits, B, W, scale=0.6)
+        kc0, vc0 = _randn(g, B, smax, hkv, d, dtype=BF16), _randn(g, B, smax, hkv, d, dtype=BF16)
+
+        def run(ops, to):
+            kc, vc = to(kc0), to(vc0)
+            out = ops.zeros((B, hq * d), BF16)
+            ops.decode_attention_fused(to(part), kc, vc, out, batch=B, hq=hq, hkv=hkv, d=d, smax=smax, ctx=ctx, theta=10000.0,
+                                       scale=1 / 16, softcap=50.0)
+            return out, kc[:, ctx - 1].clone(), vc[:, ctx - 1].clone()
+        (co, ck, cv), (ro, rk, rv) = _both(run, dev)
+        res.add(f"out[{tag}]", _err(co, ro), 1.5e-2)
+        res.add(f"k_row[{tag}]", _err(ck, rk), TOL_BF16)
+        res.add(f"v_row[{tag}]", _err(cv, rv), TOL_BF16)
+    return res
+
+
 ATTN_CASES = [
     attn_case("attn_siglip_d72", 2, 2, 2, 256, 256, 72, packed_qkv=True),
     attn_case("attn_beit_d64_relpos", 1, 2, 2, 577, 577, 64, packed_qkv=True, relpos_win=24),
@@ -294,6 +319,7 @@ ATTN_CASES = [
     attn_case("attn_tc_d256_sharp_softcap", 3, 8, 4, 278, 278, 256, scale=0.5, softcap=50.0, smax=290, seed=9),
     attn_case("attn_tc_d256_causal_offset", 2, 4, 2, 200, 260, 256, scale=0.25, softcap=50.0, causal=True, smax=300, seed=10),
     decode_attn_case,
+    decode_attn_fused_case,
 ]
 
 

@@ -76,7 +76,9 @@ int svla_gemm(const SvlaGemmArgs* args, void* stream);
 /* G1s: skinny GEMM for the decode steps (M <= 128 activation rows): weight-streaming, swap-AB (UMMA M walks the weight
  * rows), split-K across CTAs so every SM streams weights. out[m,n] = act(alpha * sum_k x[m,k] w[n,k] + bias[n]).
  * flags: 1 = GEGLU (as svla_gemm), 2 = PARTIAL: raw fp32 partial sums out_f32[split * partial_stride + m*ldo + n] for
- * `splits` K-slices (the consumers svla_rmsnorm_residual / svla_rope_kv add them). model/modeling_gemma2.py:80-92,351-354,993 */
+ * `splits` K-slices (the consumers svla_rmsnorm_residual / svla_rope_kv add them); 4 = W_TILED: w holds the same matrix
+ * tile-major, bf16 [ceil(N/128)][ceil(K/64)][128][64] zero-padded (ldw ignored), so that every 16 KB pipeline stage is one
+ * contiguous HBM read. model/modeling_gemma2.py:80-92,351-354,993 */
 typedef struct SvlaSkinnyArgs {
   const void* x;          /* bf16 [M, ldx] */
   const void* w;          /* bf16 [N, ldw] */

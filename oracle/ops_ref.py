@@ -102,8 +102,11 @@ class RefOps:
         return max(1, min(148 // max(1, (n + 127) // 128), max(1, ((k + 63) // 64) // 4)))
 
     def gemm_skinny(self, x, w, *, out_bf16=None, out_f32=None, bias=None, act=ACT_NONE, act_param=0.0, alpha=1.0,
-                    geglu=False, splits=1):
+                    geglu=False, splits=1, tiled_n=None):
         self.launches += 1
+        if tiled_n is not None:             # tile-major [nt, kb, 128, 64] copy of a [tiled_n, K] matrix
+            nt, kb = w.shape[0], w.shape[1]
+            w = w.permute(0, 2, 1, 3).reshape(nt * 128, kb * 64)[:tiled_n, : x.shape[1]]
         xf, wf = x.float(), w.float()
         if out_f32 is not None and out_f32.dim() == 3:
             S, K = out_f32.shape[0], x.shape[1]

@@ -525,6 +525,8 @@ svla_decode_attn_fused_kernel(const float* __restrict__ qkv_f32, int n_partials,
     }
     cp_async_commit();
   };
+  pdl_launch_dependents();          // lets the o-projection GEMM start prefetching its weights
+  pdl_wait();                       // qkv partial sums (previous kernel) and the cache rows of earlier steps
   // the cache rows do not depend on this step's projections: start streaming before touching qkv
 #pragma unroll
   for (int i = 0; i < kFusedStages - 1; ++i) issue_tile(i);
@@ -760,10 +762,12 @@ extern "C" int svla_decode_attention_fused(const float* qkv_f32, int n_partials,
   auto* kcp = static_cast<__nv_bfloat16*>(kcache);
   auto* vcp = static_cast<__nv_bfloat16*>(vcache);
   auto* op = static_cast<__nv_bfloat16*>(out);
-  if (grp == 1)
-    svla_decode_attn_fused_kernel<1><<<grid, kDecThreads, smem, st>>>(qkv_f32, n_partials, partial_stride, kcp, vcp, op, hq, hkv, smax, ctx, theta, scale, softcap);
-  else
-    svla_decode_attn_fused_kernel<2><<<grid, kDecThreads, smem, st>>>(qkv_f32, n_partials, partial_stride, kcp, vcp, op, hq, hkv, smax, ctx, theta, scale, softcap);
+  const long long ps = partial_stride;
+  cudaError_t le = grp == 1 ? svla_launch_pdl(svla_decode_attn_fused_kernel<1>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
+                                              hq, hkv, smax, ctx, theta, scale, softcap)
+                            : svla_launch_pdl(svla_decode_attn_fused_kernel<2>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
+                                              hq, hkv, smax, ctx, theta, scale, softcap);
+  SVLA_REQUIRE(le == cudaSuccess, "svla_decode_attention_fused: launch failed: %s", cudaGetErrorString(le));
   SVLA_LAUNCH_CHECK("svla_decode_attn_fused");
   return 0;
 }

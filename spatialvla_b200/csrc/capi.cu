@@ -1,4 +1,5 @@
 // Library-wide state of the C ABI: last-error text, launch counter, ABI version.
+#include <cstdlib>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -8,6 +9,15 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 }  // namespace
+
+bool svla_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SVLA_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 void svla_set_error(const char* fmt, ...) {
   va_list ap;

@@ -70,6 +70,8 @@ svla_rmsnorm_residual_kernel(float* __restrict__ x, const float* __restrict__ br
                              const float* __restrict__ w_pre, float eps, int cols, __nv_bfloat16* __restrict__ out_bf16,
                              int n_partials, long long partial_stride) {
   __shared__ float sh[33];
+  pdl_launch_dependents();          // the next kernel (a weight-streaming GEMM in the decode chain) may start its prefetch
+  pdl_wait();
   const long long row = blockIdx.x;
   const int nv = cols >> 2;
   float4 xv[kMaxVec];
@@ -343,6 +345,8 @@ __global__ void svla_embed_kernel(const long long* __restrict__ ids, const __nv_
                                   const __nv_bfloat16* __restrict__ spatial, const float* __restrict__ img, float* __restrict__ x,
                                   int s, int hdim, long long vocab, long long image_token, long long act_lo, long long n_act,
                                   int n_img, float normalizer, int* __restrict__ status) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long tok = blockIdx.x;
   const int b = static_cast<int>(tok / s), si = static_cast<int>(tok % s);
   const long long id = ids[tok];
@@ -383,6 +387,8 @@ svla_argmax_kernel(const float* __restrict__ logits, long long cols, long long l
                    long long* __restrict__ out, long long out_stride) {
   __shared__ float sv[8];
   __shared__ long long si[8];
+  pdl_launch_dependents();
+  pdl_wait();
   const long long row = blockIdx.x;
   const float* r = logits + row * ld;
   float best = -INFINITY;
@@ -873,7 +879,11 @@ extern "C" int svla_rmsnorm_residual(float* x, const float* branch, const float*
   if (rows >= 2048 && need <= 4) svla_rmsnorm_residual_warp_kernel<4><<<wblocks, 128, 0, st>>>(x, branch, w_post, w_pre, eps, rows, cols, ob, np, partial_stride);
   else if (rows >= 2048 && need <= 9) svla_rmsnorm_residual_warp_kernel<9><<<wblocks, 128, 0, st>>>(x, branch, w_post, w_pre, eps, rows, cols, ob, np, partial_stride);
   else if (rows >= 2048 && need <= 18) svla_rmsnorm_residual_warp_kernel<18><<<wblocks, 128, 0, st>>>(x, branch, w_post, w_pre, eps, rows, cols, ob, np, partial_stride);
-  else svla_rmsnorm_residual_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, st>>>(x, branch, w_post, w_pre, eps, cols, ob, np, partial_stride);
+  else {
+    cudaError_t le = svla_launch_pdl(svla_rmsnorm_residual_kernel, dim3(static_cast<unsigned>(rows)), dim3(kRowThreads), 0, st, x, branch, w_post,
+                                     w_pre, eps, cols, ob, np, static_cast<long long>(partial_stride));
+    SVLA_REQUIRE(le == cudaSuccess, "svla_rmsnorm_residual: launch failed: %s", cudaGetErrorString(le));
+  }
   SVLA_LAUNCH_CHECK("svla_rmsnorm_residual");
   return 0;
 }
@@ -904,10 +914,12 @@ extern "C" int svla_embed_tokens(const int64_t* ids, const void* embed, const vo
                                  int64_t n_act, int n_img, float normalizer, int* status_flag, void* stream) {
   SVLA_REQUIRE(ids && embed && x, "svla_embed_tokens: null pointer");
   SVLA_REQUIRE(batch > 0 && s > 0 && hdim > 0, "svla_embed_tokens: empty problem");
-  svla_embed_kernel<<<static_cast<unsigned>(batch) * s, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const long long*>(ids), static_cast<const __nv_bfloat16*>(embed),
-      static_cast<const __nv_bfloat16*>(spatial_embed), image_feats, x, s, hdim, vocab, image_token, act_lo, n_act, n_img,
-      normalizer, status_flag);
+  cudaError_t le = svla_launch_pdl(svla_embed_kernel, dim3(static_cast<unsigned>(batch) * s), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                                   reinterpret_cast<const long long*>(ids), static_cast<const __nv_bfloat16*>(embed),
+                                   static_cast<const __nv_bfloat16*>(spatial_embed), image_feats, x, s, hdim, static_cast<long long>(vocab),
+                                   static_cast<long long>(image_token), static_cast<long long>(act_lo), static_cast<long long>(n_act), n_img,
+                                   normalizer, status_flag);
+  SVLA_REQUIRE(le == cudaSuccess, "svla_embed_tokens: launch failed: %s", cudaGetErrorString(le));
   SVLA_LAUNCH_CHECK("svla_embed_tokens");
   return 0;
 }
@@ -915,8 +927,10 @@ extern "C" int svla_embed_tokens(const int64_t* ids, const void* embed, const vo
 extern "C" int svla_argmax_rows(const float* logits, int64_t rows, int64_t cols, int64_t ld, int64_t id_offset, int64_t* out_ids,
                                 int64_t out_stride, void* stream) {
   SVLA_REQUIRE(logits && out_ids && rows > 0 && cols > 0, "svla_argmax_rows: bad arguments");
-  svla_argmax_kernel<<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      logits, cols, ld, id_offset, reinterpret_cast<long long*>(out_ids), out_stride);
+  cudaError_t le = svla_launch_pdl(svla_argmax_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), 0, static_cast<cudaStream_t>(stream), logits,
+                                   static_cast<long long>(cols), static_cast<long long>(ld), static_cast<long long>(id_offset),
+                                   reinterpret_cast<long long*>(out_ids), static_cast<long long>(out_stride));
+  SVLA_REQUIRE(le == cudaSuccess, "svla_argmax_rows: launch failed: %s", cudaGetErrorString(le));
   SVLA_LAUNCH_CHECK("svla_argmax_rows");
   return 0;
 }

@@ -38,6 +38,7 @@ struct SkinnyParams {
   float alpha, act_param;
   int act, flags;
   int n_tiles, kb_per_split, num_k_blocks;
+  int w_tiled;     // W is stored tile-major [n_tile][k_block][128 rows][64 cols]: every 16 KB stage is one contiguous read
 };
 
 template <int NB>
@@ -74,15 +75,35 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  pdl_launch_dependents();
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
+      // every CTA walks its K range from a different starting block (rotation by n_tile) so that the CTAs do not all ask
+      // for the same activation tile at the same time
+      const int nkb = kb1 - kb0;
+      const int rot = nkb > 0 ? (n_tile * 5) % nkb : 0;
+      auto load_w = [&](int it, int stage) {
+        const int kb = kb0 + (it + rot) % nkb;
         mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-        tma_load_2d(smem_w + stage * C::kWBytes, &tm_w, &full_bar[stage], kb * kBK, n_tile * kWM);
+        if (p.w_tiled) tma_load_2d(smem_w + stage * C::kWBytes, &tm_w, &full_bar[stage], 0, (n_tile * p.num_k_blocks + kb) * kWM);
+        else tma_load_2d(smem_w + stage * C::kWBytes, &tm_w, &full_bar[stage], kb * kBK, n_tile * kWM);
+      };
+      auto load_x = [&](int it, int stage) {
+        const int kb = kb0 + (it + rot) % nkb;
         tma_load_2d(smem_x + stage * C::kXBytes, &tm_x, &full_bar[stage], kb * kBK, 0);
+      };
+      // PDL: the weights are immutable, so the first kStages weight tiles are requested BEFORE waiting for the kernel that
+      // produces the activations; their HBM latency (and this kernel's launch + prologue) hides behind that kernel
+      const int pre = nkb < C::kStages ? nkb : C::kStages;
+      for (int it = 0; it < pre; ++it) load_w(it, it);
+      pdl_wait();
+      for (int it = 0; it < pre; ++it) load_x(it, it);
+      int stage = 0;
+      uint32_t phase = 1;                          // the ring has been filled once
+      for (int it = pre; it < nkb; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        load_w(it, stage);
+        load_x(it, stage);
         if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -112,6 +133,7 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
     const bool n_ok = n < p.n;
     const bool partial = (p.flags & 2) != 0, geglu = (p.flags & 1) != 0;
     const float bias = (p.bias != nullptr && n_ok && !partial) ? __ldg(p.bias + n) : 0.f;
+    pdl_wait();
     mbar_wait(acc_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -192,7 +214,11 @@ int launch_skinny(const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyPara
     }
     configured = true;
   }
-  svla_gemm_skinny_kernel<NB><<<ctas, kThreads, C::kSmemBytes, st>>>(tw, tx, p);
+  cudaError_t le = svla_launch_pdl(svla_gemm_skinny_kernel<NB>, dim3(ctas), dim3(kThreads), C::kSmemBytes, st, tw, tx, p);
+  if (le != cudaSuccess) {
+    svla_set_error("svla_gemm_skinny: launch failed: %s", cudaGetErrorString(le));
+    return -2;
+  }
   SVLA_LAUNCH_CHECK("svla_gemm_skinny");
   return 0;
 }
@@ -213,8 +239,8 @@ extern "C" int svla_gemm_skinny(const SvlaSkinnyArgs* g, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SVLA_REQUIRE(g && g->x && g->w, "svla_gemm_skinny: null operand");
   SVLA_REQUIRE(g->m > 0 && g->m <= 128 && g->n > 0 && g->k > 0, "svla_gemm_skinny: need 0 < m <= 128 (m=%lld)", (long long)g->m);
-  SVLA_REQUIRE((g->ldx % 8) == 0 && (g->ldw % 8) == 0 && g->ldx >= g->k && g->ldw >= g->k, "svla_gemm_skinny: bad leading dimensions");
-  const bool geglu = (g->flags & 1) != 0, partial = (g->flags & 2) != 0;
+  SVLA_REQUIRE((g->ldx % 8) == 0 && g->ldx >= g->k && (((g->flags & 4) != 0) || ((g->ldw % 8) == 0 && g->ldw >= g->k)), "svla_gemm_skinny: bad leading dimensions");
+  const bool geglu = (g->flags & 1) != 0, partial = (g->flags & 2) != 0, w_tiled = (g->flags & 4) != 0;
   const int splits = g->splits > 0 ? g->splits : 1;
   SVLA_REQUIRE(partial || splits == 1, "svla_gemm_skinny: split-K needs the PARTIAL flag (fp32 partial sums)");
   SVLA_REQUIRE(!partial || (g->out_f32 && !g->out_bf16 && !geglu), "svla_gemm_skinny: PARTIAL writes out_f32 only");
@@ -230,7 +256,9 @@ extern "C" int svla_gemm_skinny(const SvlaSkinnyArgs* g, void* stream) {
   SVLA_REQUIRE(static_cast<long long>(p.kb_per_split) * (splits - 1) < p.num_k_blocks, "svla_gemm_skinny: too many splits (%d) for k=%lld", splits, (long long)g->k);
   const int nb = g->m <= 16 ? 16 : (g->m <= 64 ? 64 : 128);
   CUtensorMap tw, tx;
-  int rc = encode_kmajor(&tw, g->w, static_cast<uint64_t>(g->k), static_cast<uint64_t>(g->n), static_cast<uint64_t>(g->ldw), kWM);
+  p.w_tiled = w_tiled ? 1 : 0;
+  int rc = w_tiled ? encode_kmajor(&tw, g->w, kBK, static_cast<uint64_t>(p.n_tiles) * p.num_k_blocks * kWM, kBK, kWM)
+                   : encode_kmajor(&tw, g->w, static_cast<uint64_t>(g->k), static_cast<uint64_t>(g->n), static_cast<uint64_t>(g->ldw), kWM);
   SVLA_REQUIRE(rc == 0, "svla_gemm_skinny: cuTensorMapEncodeTiled(W) failed (%d)", rc);
   rc = encode_kmajor(&tx, g->x, static_cast<uint64_t>(g->k), static_cast<uint64_t>(g->m), static_cast<uint64_t>(g->ldx), static_cast<uint32_t>(nb));
   SVLA_REQUIRE(rc == 0, "svla_gemm_skinny: cuTensorMapEncodeTiled(X) failed (%d)", rc);

@@ -28,6 +28,35 @@ void svla_count_launch(int n = 1);
     }                                                                                    \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) for the launch-bound decode chain ------------------------------------------------
+// A kernel launched through svla_launch_pdl may start while its predecessor in the stream is still running.  Contract of
+// every such kernel: (1) before griddepcontrol.wait it touches only immutable data (weights, tensor maps) and its own
+// shared memory / TMEM; (2) it executes griddepcontrol.wait before the first access to anything an earlier kernel wrote or
+// still reads; (3) it executes griddepcontrol.launch_dependents at its top so that the NEXT kernel's prologue (and, for the
+// weight-streaming GEMM, its first pipeline stages of weights) overlaps this kernel.  Both instructions are no-ops in a
+// kernel that was launched without the attribute.  SVLA_PDL=0 turns the attribute off (plain stream order).
+bool svla_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t svla_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = svla_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 static inline int svla_num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -25,6 +25,16 @@ def _req(cond, msg):
         raise ValueError(msg)
 
 
+def tile_weight(w):
+    """[N, K] bf16 -> tile-major [ceil(N/128), ceil(K/64), 128, 64] (zero padded): the decode GEMM streams one contiguous
+    16 KB block per pipeline stage instead of 128 row segments of 128 bytes."""
+    n, k = w.shape
+    nt, kb = (n + 127) // 128, (k + 63) // 64
+    p = torch.zeros(nt * 128, kb * 64, dtype=w.dtype, device=w.device)
+    p[:n, :k] = w
+    return p.view(nt, 128, kb, 64).permute(0, 2, 1, 3).contiguous()
+
+
 class CudaOps:
     """All methods are asynchronous on torch's current stream."""
 
@@ -103,21 +113,25 @@ class CudaOps:
         return int(self.lib.svla_gemm_skinny_splits(int(n), int(k)))
 
     def gemm_skinny(self, x, w, *, out_bf16=None, out_f32=None, bias=None, act=ACT_NONE, act_param=0.0, alpha=1.0,
-                    geglu=False, splits=1):
-        """Decode GEMM (M <= 128). splits > 1 (or out_f32 with 3 dims) writes raw fp32 partial sums out_f32[s, M, N]."""
+                    geglu=False, splits=1, tiled_n=None):
+        """Decode GEMM (M <= 128). splits > 1 (or out_f32 with 3 dims) writes raw fp32 partial sums out_f32[s, M, N].
+        tiled_n: w is the tile-major copy made by `tile_weight` of a [tiled_n, K] matrix."""
         g = L.SvlaSkinnyArgs()
         _req(x.dtype == BF16 and w.dtype == BF16 and x.dim() == 2 and x.stride(1) == 1, "gemm_skinny: bf16 row-major operands")
+        if tiled_n is not None:
+            _req(w.dim() == 4 and w.shape[2] == 128 and w.shape[3] == 64 and w.is_contiguous(), "gemm_skinny: tiled w must be [nt, kb, 128, 64]")
+            _req(w.shape[0] == (tiled_n + 127) // 128 and w.shape[1] == (x.shape[1] + 63) // 64, "gemm_skinny: tiled w does not match N / K")
         partial = out_f32 is not None and out_f32.dim() == 3
         _req(partial or splits == 1, "gemm_skinny: split-K needs a [splits, M, N] fp32 output")
         g.x, g.w, g.bias = _ptr(x), _ptr(w), _ptr(bias)
         g.out_bf16, g.out_f32 = _ptr(out_bf16), _ptr(out_f32)
-        g.m, g.n, g.k = int(x.shape[0]), int(w.shape[0]), int(x.shape[1])
-        g.ldx, g.ldw = int(x.stride(0)), int(w.stride(0))
+        g.m, g.n, g.k = int(x.shape[0]), int(w.shape[0] if tiled_n is None else tiled_n), int(x.shape[1])
+        g.ldx, g.ldw = int(x.stride(0)), int(w.stride(0) if tiled_n is None else 64)
         o = out_f32 if out_f32 is not None else out_bf16
         g.ldo = int(o.stride(-2))
         g.partial_stride = int(out_f32.stride(0)) if partial else 0
         g.alpha, g.act_param, g.act = float(alpha), float(act_param), int(act)
-        g.flags = (1 if geglu else 0) | (2 if partial else 0)
+        g.flags = (1 if geglu else 0) | (2 if partial else 0) | (4 if tiled_n is not None else 0)
         g.splits = int(out_f32.shape[0]) if partial else 1
         L.check(self.lib.svla_gemm_skinny(C.byref(g), self._stream()), "svla_gemm_skinny")
 

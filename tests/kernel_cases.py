@@ -156,8 +156,9 @@ SIMT_CASES = [
 ]
 
 
-def skinny_case(name, M, N, K, *, mode="partial", splits=0, bias=False, act=ACT_NONE, act_param=0.0, ldx=None, seed=0):
+def skinny_case(name, M, N, K, *, mode="partial", splits=0, bias=False, act=ACT_NONE, act_param=0.0, ldx=None, seed=0, tiled=False):
     def case(dev="cuda:0"):
+        from spatialvla_b200.ops import tile_weight
         g = _gen(seed)
         x_full = _randn(g, M, ldx or K, dtype=BF16)
         wt = (_randn(g, N, K) / K ** 0.5).to(BF16)
@@ -165,18 +166,19 @@ def skinny_case(name, M, N, K, *, mode="partial", splits=0, bias=False, act=ACT_
 
         def run(ops, to):
             X = to(x_full)[:, :K]
-            W = to(wt)
+            W = to(tile_weight(wt)) if tiled else to(wt)
+            tn = N if tiled else None
             if mode == "partial":
                 S = splits or ops.skinny_splits(N, K) if ops.name == "cuda" else (splits or 1)
                 out = ops.zeros((S, M, N), F32)
-                ops.gemm_skinny(X, W, out_f32=out)
+                ops.gemm_skinny(X, W, out_f32=out, tiled_n=tn)
                 return (out.sum(0),)
             if mode == "geglu":
                 out = ops.zeros((M, N // 2), BF16)
-                ops.gemm_skinny(X, W, out_bf16=out, geglu=True, bias=to(b))
+                ops.gemm_skinny(X, W, out_bf16=out, geglu=True, bias=to(b), tiled_n=tn)
                 return (out,)
             of, ob = ops.zeros((M, N), F32), ops.zeros((M, N), BF16)
-            ops.gemm_skinny(X, W, out_f32=of, out_bf16=ob, bias=to(b), act=act, act_param=act_param)
+            ops.gemm_skinny(X, W, out_f32=of, out_bf16=ob, bias=to(b), act=act, act_param=act_param, tiled_n=tn)
             return of, ob
         c, r = _both(run, dev)
         res = Result(name)
@@ -219,6 +221,10 @@ SKINNY_CASES = [
     skinny_case("skinny_m7_strided_x", 7, 256, 128, mode="plain", ldx=128 * 5),
     skinny_case("skinny_m100", 100, 384, 192, mode="plain", act=ACT_RELU),
     skinny_case("skinny_m128_partial", 128, 512, 1024, splits=3),
+    skinny_case("skinny_tiled_qkv_partial", 64, 4096, 2304, tiled=True, seed=31),
+    skinny_case("skinny_tiled_geglu", 64, 18432, 2304, mode="geglu", tiled=True, seed=32),
+    skinny_case("skinny_tiled_head_ragged", 64, 8194, 2304, mode="plain", act=ACT_SOFTCAP, act_param=30.0, tiled=True, seed=33),
+    skinny_case("skinny_tiled_ragged_k", 5, 300, 200, mode="plain", bias=True, tiled=True, seed=34),
     skinny_consumers_case,
 ]
 

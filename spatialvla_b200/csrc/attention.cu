@@ -526,10 +526,13 @@ svla_decode_attn_fused_kernel(const float* __restrict__ qkv_f32, int n_partials,
     cp_async_commit();
   };
   pdl_launch_dependents();          // lets the o-projection GEMM start prefetching its weights
-  pdl_wait();                       // qkv partial sums (previous kernel) and the cache rows of earlier steps
-  // the cache rows do not depend on this step's projections: start streaming before touching qkv
+  // The cached rows [0, ctx-1) were written by the prefill or by this layer's kernel of an EARLIER decode step, i.e. at least
+  // one full layer chain (>= 7 launches) upstream.  A PDL kernel can only overlap predecessors that are still resident and
+  // blocked in griddepcontrol.wait; a whole chain of them cannot be resident at once, so those rows are complete and the
+  // ring is primed while the qkv projection (the direct predecessor) is still running.
 #pragma unroll
   for (int i = 0; i < kFusedStages - 1; ++i) issue_tile(i);
+  pdl_wait();                       // qkv partial sums of this step (previous kernel)
 
   // ---- RoPE of the new token (positions are 1-indexed, model/modeling_spatialvla.py:371-372) + cache append
   {

@@ -25,10 +25,18 @@ template <int NB> struct SCfg {
   static constexpr int kWBytes = kWM * kBK * 2;
   static constexpr int kXBytes = NB * kBK * 2;
   static constexpr int kStageBytes = kWBytes + kXBytes;
-  static constexpr int kStages = (kStageBytes > 24576) ? 6 : 8;
+  static constexpr int kMaxStages = 8;
   static constexpr int kTmemCols = NB < 32 ? 32 : NB;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int smem_bytes(int stages) { return stages * kStageBytes + 1024 + 256; }
 };
+// Pipeline depth: 8 x 24 KB (NB <= 64) or 6 x 32 KB (NB = 128) in flight per SM.  SVLA_SKINNY_STAGES overrides it for A/B
+// measurements; measured on the in-situ decode step (tools/decode_step_perf.py, B=64): 8 stages 2176 us, 4 stages (two CTAs
+// of consecutive PDL kernels co-resident per SM) 2238 us, 3 stages 2490 us -- depth beats co-residency.
+inline int skinny_stages(int stage_bytes) {
+  static const int env = getenv("SVLA_SKINNY_STAGES") ? atoi(getenv("SVLA_SKINNY_STAGES")) : 0;
+  if (env >= 2 && env <= 8) return env;
+  return (stage_bytes > 24576) ? 6 : 8;
+}
 
 struct SkinnyParams {
   const float* bias;
@@ -38,22 +46,24 @@ struct SkinnyParams {
   float alpha, act_param;
   int act, flags;
   int n_tiles, kb_per_split, num_k_blocks;
+  int stages;      // pipeline depth (<= SCfg::kMaxStages)
   int w_tiled;     // W is stored tile-major [n_tile][k_block][128 rows][64 cols]: every 16 KB stage is one contiguous read
 };
 
 template <int NB>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x, const SkinnyParams p) {
   using C = SCfg<NB>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* smem_w = smem;
-  uint8_t* smem_x = smem + C::kStages * C::kWBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  const int kStages = p.stages;
+  uint8_t* smem_x = smem + kStages * C::kWBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * C::kStageBytes);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + C::kStages;
-  uint64_t* acc_bar = bars + 2 * C::kStages;
+  uint64_t* empty_bar = bars + C::kMaxStages;
+  uint64_t* acc_bar = bars + 2 * C::kMaxStages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -65,7 +75,7 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
     tma_prefetch_desc(&tm_w);
     tma_prefetch_desc(&tm_x);
 #pragma unroll 1
-    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -94,7 +104,7 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
       };
       // PDL: the weights are immutable, so the first kStages weight tiles are requested BEFORE waiting for the kernel that
       // produces the activations; their HBM latency (and this kernel's launch + prologue) hides behind that kernel
-      const int pre = nkb < C::kStages ? nkb : C::kStages;
+      const int pre = nkb < kStages ? nkb : kStages;
       for (int it = 0; it < pre; ++it) load_w(it, it);
       pdl_wait();
       for (int it = 0; it < pre; ++it) load_x(it, it);
@@ -104,7 +114,7 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         load_w(it, stage);
         load_x(it, stage);
-        if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -122,7 +132,7 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
           umma_bf16(tmem_base, dw + static_cast<uint64_t>(k * 2), dx + static_cast<uint64_t>(k * 2), idesc,
                     static_cast<uint32_t>((kb > kb0) || k != 0));
         umma_commit(&empty_bar[stage]);
-        if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
       umma_commit(acc_bar);
     }
@@ -203,18 +213,20 @@ int encode_kmajor(CUtensorMap* tm, const void* base, uint64_t k, uint64_t rows, 
 }
 
 template <int NB>
-int launch_skinny(const CUtensorMap& tw, const CUtensorMap& tx, const SkinnyParams& p, int ctas, cudaStream_t st) {
+int launch_skinny(const CUtensorMap& tw, const CUtensorMap& tx, SkinnyParams p, int ctas, cudaStream_t st) {
   using C = SCfg<NB>;
   static bool configured = false;
+  p.stages = skinny_stages(C::kStageBytes);
+  const int smem_bytes = C::smem_bytes(p.stages);
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(svla_gemm_skinny_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(svla_gemm_skinny_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) {
       svla_set_error("svla_gemm_skinny: smem opt-in failed: %s", cudaGetErrorString(e));
       return -2;
     }
     configured = true;
   }
-  cudaError_t le = svla_launch_pdl(svla_gemm_skinny_kernel<NB>, dim3(ctas), dim3(kThreads), C::kSmemBytes, st, tw, tx, p);
+  cudaError_t le = svla_launch_pdl(svla_gemm_skinny_kernel<NB>, dim3(ctas), dim3(kThreads), smem_bytes, st, tw, tx, p);
   if (le != cudaSuccess) {
     svla_set_error("svla_gemm_skinny: launch failed: %s", cudaGetErrorString(le));
     return -2;

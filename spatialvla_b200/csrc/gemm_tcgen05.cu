@@ -35,8 +35,12 @@ template <int BN, int CG = 1> struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kStageBytes >= 49152) ? 4 : ((kStageBytes >= 32768) ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kStagingBytes = kEpiWarps * 32 * 20 * 4;     // per-epilogue-warp fp32 transpose tile (32 rows x 16 cols)
+  // per-epilogue-warp staging tile: 32 rows x 128 bytes.  Legacy epilogue: fp32 transpose tile (32 rows x 16 cols, stride 20);
+  // TMA-store epilogue: one SWIZZLE_128B box (32 rows x 64 bf16 or 32 rows x 32 fp32), so the tile bases are 1024-aligned.
+  static constexpr int kStagingPerWarp = 4096;
+  static constexpr int kStagingBytes = kEpiWarps * kStagingPerWarp;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes;
+  static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB) exceeded");
 };
 
 struct EpiParams {
@@ -52,6 +56,7 @@ struct EpiParams {
   long long m, n, ldo;
   float alpha, act_param;
   int act, flags;
+  int tma_out;    // 0 = register/LDG/STG epilogue; 1 = bf16 tile via TMA store; 2 = fp32 tile via TMA store; 3 = fp32 TMA reduce-add
   // conv geometry
   int nb, h, wd, tiles_h, tiles_w;
 };
@@ -231,6 +236,131 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, const float 
   }
 }
 
+// ------------------------------------------------------------------------------------------ TMA-store epilogue
+// Used when the GEMM has ONE output tensor and no residual operands (ep.tma_out != 0): the K ~ 1024 projections of SigLIP /
+// BEiT are epilogue-bound with the register/LDG/STG path above (ncu: ~25 warp-instructions per element).  Here lane = row:
+// value = act(alpha*acc + bias) * colscale for 32 consecutive columns, bias / colscale fetched as warp-uniform float4 loads
+// (one L1 broadcast each, no shuffles), the row segment is written ONCE to a SWIZZLE_128B shared-memory box (conflict-free
+// 16-byte stores) and a single elected lane hands the 32-row box to the TMA unit: cp.async.bulk.tensor store, or
+// cp.reduce.async.bulk.tensor .add for `out_f32 +=` (the read-modify-write happens in L2, the SM never loads the old value).
+// Rows >= M and columns >= N are clipped by the tensor map, so ragged tiles need no predicates.
+__device__ __forceinline__ void epilogue_math32(const EpiParams& ep, float (&v)[32], long long n0) {
+  if (ep.alpha != 1.f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+  }
+  const bool full = n0 + 32 <= ep.n;                     // warp-uniform
+  if (ep.bias) {
+    if (full) {
+      const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(b4 + j);
+        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += (n0 + j < ep.n) ? __ldg(ep.bias + n0 + j) : 0.f;
+    }
+  }
+  switch (ep.act) {
+    case SVLA_ACT_GELU_TANH:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
+      break;
+    case SVLA_ACT_GELU_ERF:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+      break;
+    case SVLA_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      break;
+    case SVLA_ACT_SOFTCAP: {
+      const float inv = 1.f / ep.act_param;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = ep.act_param * tanhf(v[j] * inv);
+      break;
+    }
+    case SVLA_ACT_SOFTPLUS:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = softplus_f(v[j]);
+      break;
+    default: break;
+  }
+  if (ep.colscale) {
+    if (full) {
+      const float4* c4 = reinterpret_cast<const float4*>(ep.colscale + n0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 c = __ldg(c4 + j);
+        v[4 * j] *= c.x; v[4 * j + 1] *= c.y; v[4 * j + 2] *= c.z; v[4 * j + 3] *= c.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= (n0 + j < ep.n) ? __ldg(ep.colscale + n0 + j) : 1.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// One warp drains its 32 accumulator rows x COLS columns [c_begin, c_begin + COLS) of the tile.  `tile` = this warp's 4 KB,
+// 1024-byte aligned staging box; row0 = global output row of lane 0.
+template <int COLS>
+__device__ __forceinline__ void epilogue_tma(const EpiParams& ep, const CUtensorMap* tm_o, uint32_t taddr, uint8_t* tile, int lane,
+                                             int c_begin, long long n_base, int row0) {
+  const uint32_t row_s = smem_u32(tile) + static_cast<uint32_t>(lane) * 128u;
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+#pragma unroll 1
+  for (int c0 = c_begin; c0 < c_begin + COLS; c0 += 32) {
+    const long long n0 = n_base + c0;
+    if (n0 >= ep.n) break;                               // warp-uniform
+    uint32_t r[32];
+    tmem_ld32(taddr + c0, r);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    epilogue_math32(ep, v, n0);
+    if (ep.tma_out == 1) {
+      // bf16: two 32-column chunks fill one 128-byte box row (64 columns)
+      const uint32_t half = static_cast<uint32_t>((c0 - c_begin) >> 5) & 1u;
+      if (half == 0) {
+        if (lane == 0) bulk_wait_read_all();             // the previous box has left shared memory
+        __syncwarp();
+      }
+#pragma unroll
+      for (uint32_t j = 0; j < 4; ++j)
+        st_shared_v4(row_s + (((half * 4u + j) ^ sw) << 4), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                     pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+      if (half == 1 || n0 + 32 >= ep.n) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tm_o, tile, static_cast<int>(n0) - 32 * static_cast<int>(half), row0);
+          bulk_commit_group();
+        }
+      }
+    } else {
+      if (lane == 0) bulk_wait_read_all();
+      __syncwarp();
+#pragma unroll
+      for (uint32_t j = 0; j < 8; ++j)
+        st_shared_v4(row_s + ((j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                     __float_as_uint(v[4 * j + 3]));
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (ep.tma_out == 3) tma_reduce_add_2d(tm_o, tile, static_cast<int>(n0), row0);
+        else tma_store_2d(tm_o, tile, static_cast<int>(n0), row0);
+        bulk_commit_group();
+      }
+    }
+  }
+}
+
 // Global output row of tile row r (and validity) in linear / conv mode.
 __device__ __forceinline__ bool tile_row_to_global(const EpiParams& ep, bool conv, long long m_tile, int r, long long& grow) {
   if (!conv) {
@@ -265,7 +395,7 @@ __device__ __forceinline__ void raster_tile(long long tile, long long num_m_grou
 template <int BN, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                         const EpiParams ep, const long long num_m_tiles, const long long num_n_tiles,
+                         const __grid_constant__ CUtensorMap tm_o, const EpiParams ep, const long long num_m_tiles, const long long num_n_tiles,
                          const int num_k_blocks, const int conv, const int c_chunks) {
   using C = Cfg<BN, CG>;
   constexpr int BNL = BN / CG;       // W rows staged by this CTA
@@ -275,13 +405,13 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::kStages * C::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* staging = smem + C::kStages * C::kStageBytes;                // 1024-aligned (stage sizes are multiples of 1 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + C::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tmem_full = bars + 2 * C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* staging = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -291,6 +421,7 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
+    if (ep.tma_out) tma_prefetch_desc(&tm_o);
 #pragma unroll 1
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -399,12 +530,27 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     const int chalf = (warp - 2) >> 2;                    // which half of the tile's columns this warp drains
     constexpr int kColsPerWarp = BN >= 64 ? BN / 2 : BN;
     uint32_t it = 0;
-    float* stage = staging + (warp - 2) * 32 * kStageLd;
+    uint8_t* tile_s = staging + (warp - 2) * C::kStagingPerWarp;
+    float* stage = reinterpret_cast<float*>(tile_s);
     for (long long tile = first; tile < num_tiles; tile += step, ++it) {
       long long mg, n_tile;
       raster_tile(tile, num_m_groups, num_n_tiles, mg, n_tile);
       const long long m_tile = mg * CG + cta_rank;
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+      const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+      if constexpr (BN >= 128) {
+        if (ep.tma_out) {                                  // warp-uniform, fixed for the launch
+          mbar_wait(&tmem_full[as], aphase);
+          tc_fence_after();
+          epilogue_tma<BN / 2>(ep, &tm_o, taddr, tile_s, lane, chalf * (BN / 2), n_tile * BN, static_cast<int>(m_tile * kBM) + q * 32);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 1) mbar_arrive(&tmem_empty[as]); else mbar_arrive_remote(&tmem_empty[as], 0);
+          }
+          continue;
+        }
+      }
       RowSet rs;
 #pragma unroll
       for (int p = 0; p < kPasses; ++p) {
@@ -415,7 +561,6 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       }
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
       if (BN >= 64 || chalf == 0) {
 #pragma unroll 1
         for (int c0 = chalf * kColsPerWarp; c0 < (chalf + 1) * kColsPerWarp; c0 += 32) {
@@ -435,6 +580,7 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         if constexpr (CG == 1) mbar_arrive(&tmem_empty[as]); else mbar_arrive_remote(&tmem_empty[as], 0);
       }
     }
+    if (ep.tma_out && lane == 0) bulk_wait_read_all();     // the staging tiles must outlive the last TMA store's reads
   }
 
   tc_fence_before();
@@ -524,6 +670,21 @@ int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 100;
 }
 
+// output tile map for the TMA-store epilogue: [M rows, N cols] with row stride ldo, box = 32 rows x 128 bytes, SWIZZLE_128B
+int encode_out(CUtensorMap* tm, void* base, bool f32, uint64_t n, uint64_t m, uint64_t ldo) {
+  auto fn = get_encode_fn();
+  if (!fn) return -1;
+  const uint64_t es = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {n, m};
+  cuuint64_t strides[1] = {ldo * es};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / es), 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 100;
+}
+
 int encode_nhwc(CUtensorMap* tm, const void* base, int nb, int h, int w, int c) {
   auto fn = get_encode_fn();
   if (!fn) return -1;
@@ -540,8 +701,8 @@ int encode_nhwc(CUtensorMap* tm, const void* base, int nb, int h, int w, int c) 
 }
 
 template <int BN, int CG>
-int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& ep, long long mt, long long nt, int kb,
-              int conv, int c_chunks, cudaStream_t st) {
+int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const EpiParams& ep, long long mt, long long nt,
+              int kb, int conv, int c_chunks, cudaStream_t st) {
   using C = Cfg<BN, CG>;
   static bool configured = false;
   if (!configured) {
@@ -568,7 +729,7 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& ep,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, svla_gemm_tcgen05_kernel<BN, CG>, ta, tb, ep, mt, nt, kb, conv, c_chunks);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, svla_gemm_tcgen05_kernel<BN, CG>, ta, tb, to, ep, mt, nt, kb, conv, c_chunks);
   if (e != cudaSuccess) {
     svla_set_error("svla_gemm_tcgen05<%d,%d>: launch failed: %s", BN, CG, cudaGetErrorString(e));
     return -2;
@@ -676,15 +837,32 @@ extern "C" int svla_gemm(const SvlaGemmArgs* g, void* stream) {
                  static_cast<uint32_t>(use_pair ? bn / 2 : bn));     // a CTA of a pair stages half of the W tile
   SVLA_REQUIRE(rc == 0, "svla_gemm: cuTensorMapEncodeTiled(W) failed (%d)", rc);
 
+  // TMA-store epilogue: one output tensor, no residual operands, 128/256-wide tiles, 16-byte aligned rows and vectors
+  // (SVLA_GEMM_LEGACY_EPI=1 keeps the register/LDG/STG epilogue for A/B measurements)
+  CUtensorMap to = ta;
+  static const bool legacy_epi = getenv("SVLA_GEMM_LEGACY_EPI") != nullptr;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!legacy_epi && !conv && !geglu && bn >= 128 && !g->res_bf16 && !g->res2_bf16 && !g->res_f32 && !g->out_relu_bf16 &&
+      al16(g->bias) && al16(g->colscale) && g->m < (1LL << 31) && g->n < (1LL << 31)) {
+    if (g->out_bf16 && !g->out_f32 && (g->ldo % 8) == 0 && al16(g->out_bf16)) {
+      ep.tma_out = 1;
+      rc = encode_out(&to, g->out_bf16, false, static_cast<uint64_t>(g->n), static_cast<uint64_t>(g->m), static_cast<uint64_t>(g->ldo));
+    } else if (g->out_f32 && !g->out_bf16 && (g->ldo % 4) == 0 && al16(g->out_f32)) {
+      ep.tma_out = (g->flags & SVLA_GEMM_ACCUM_F32) ? 3 : 2;
+      rc = encode_out(&to, g->out_f32, true, static_cast<uint64_t>(g->n), static_cast<uint64_t>(g->m), static_cast<uint64_t>(g->ldo));
+    }
+    SVLA_REQUIRE(rc == 0, "svla_gemm: cuTensorMapEncodeTiled(out) failed (%d)", rc);
+  }
+
   const int cv = conv ? 1 : 0;
   if (use_pair) {
-    if (bn == 128) return launch_tc<128, 2>(ta, tb, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
-    return launch_tc<256, 2>(ta, tb, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
+    if (bn == 128) return launch_tc<128, 2>(ta, tb, to, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
+    return launch_tc<256, 2>(ta, tb, to, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
   }
   switch (bn) {
-    case 32: return launch_tc<32, 1>(ta, tb, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
-    case 64: return launch_tc<64, 1>(ta, tb, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
-    case 128: return launch_tc<128, 1>(ta, tb, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
-    default: return launch_tc<256, 1>(ta, tb, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
+    case 32: return launch_tc<32, 1>(ta, tb, to, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
+    case 64: return launch_tc<64, 1>(ta, tb, to, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
+    case 128: return launch_tc<128, 1>(ta, tb, to, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
+    default: return launch_tc<256, 1>(ta, tb, to, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
   }
 }

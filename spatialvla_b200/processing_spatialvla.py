@@ -169,6 +169,28 @@ class SpatialVLAProcessor:
         normalized = self.action_tokenizer.decode_token_ids_to_actions(ids)
         return {"actions": self._unnormalize(normalized, unnorm_key), "action_ids": ids}
 
+    def decode_actions_device(self, generation_outputs: torch.Tensor, unnorm_key: Optional[str] = None):
+        """All rows, device-resident: CUDA ids (B, >= 3*chunk) -> {'actions': float64 CUDA tensor
+        (B, chunk, 7), 'action_ids': int64 (B, chunk, 3)} without a host round trip.  Same arithmetic as `decode_actions`:
+        the FP64 grid-inverse kernel (svla_tok_decode) followed by the q01/q99 un-normalisation (:239-253)."""
+        n_tok = 3
+        B = generation_outputs.shape[0]
+        need = n_tok * self.action_chunk_size
+        if generation_outputs.shape[1] < need:
+            raise ValueError(f"decode_actions_device needs {need} generated ids per row, got {generation_outputs.shape[1]}")
+        ids = generation_outputs[:, :need].reshape(-1, n_tok).contiguous()
+        normalized = self.action_tokenizer.decode_ids(ids)                       # (B*chunk, 7) float64 on the device
+        if unnorm_key is None:
+            logger.warning("unnorm_key None is not in statistics, use next one")
+            unnorm_key = next(iter(self.statistics.keys()))
+        st = self.statistics[unnorm_key]["action"]
+        dev = normalized.device
+        hi = torch.tensor(st["q99"], dtype=torch.float64, device=dev)
+        lo = torch.tensor(st["q01"], dtype=torch.float64, device=dev)
+        mask = torch.tensor(np.array(st.get("mask", np.ones(len(st["q01"]))), dtype=bool), device=dev)
+        acts = torch.where(mask, 0.5 * (normalized + 1) * (hi - lo) + lo, normalized)
+        return {"actions": acts.view(B, -1, 7), "action_ids": ids.view(B, -1, n_tok)}
+
     def decode_actions_batch(self, generation_outputs: torch.Tensor, unnorm_key: Optional[str] = None):
         """All rows: (B, >= 3*chunk) ids -> {'actions': (B, chunk, 7), 'action_ids': (B, chunk, 3)}"""
         n_tok = 3

@@ -149,6 +149,17 @@ PAIR_CASES = [   # cta_group::2 kernel forced (impl=3) and the 1-CTA kernel forc
     gemm_case("pair_conv_odd_20x28", 0, 128, 0, conv=(3, 20, 28, 64), bias=True, impl=3),
     gemm_case("single_forced_multiwave", 4096 + 77, 4304, 1152, bias=True, act=ACT_GELU_TANH, impl=2),
 ]
+TMA_EPI_CASES = [   # TMA-store epilogue (one output, no residuals): ragged M/N, partial 32-column chunk, odd pair tiles
+    gemm_case("tmaepi_bf16_ragged", 300, 200, 104, bias=True, act=ACT_GELU_TANH),
+    gemm_case("tmaepi_bf16_erf_colscale_alpha", 577, 1048, 256, bias=True, act=ACT_GELU_ERF, colscale=True, alpha=0.5),
+    gemm_case("tmaepi_bf16_pair_odd_tiles", 128 * 5 + 17, 336, 192, bias=True, impl=3),
+    gemm_case("tmaepi_bf16_pair_bn128", 128 * 4, 320, 128, block_n=128, impl=3, act=ACT_RELU),
+    gemm_case("tmaepi_f32_plain_ragged", 300, 200, 104, bias=True, out=("f32",)),
+    gemm_case("tmaepi_f32_softcap", 130, 8196, 512, act=ACT_SOFTCAP, act_param=30.0, out=("f32",)),
+    gemm_case("tmaepi_f32_accum_ragged", 577, 1028, 256, bias=True, colscale=True, out=("f32",), accumulate=True),
+    gemm_case("tmaepi_f32_accum_pair_multiwave", 36928 // 4 + 9, 1024, 1024, bias=True, colscale=True, out=("f32",), accumulate=True, impl=3),
+    gemm_case("tmaepi_bf16_multiwave_4304", 16384 // 2, 4304, 1152, bias=True, act=ACT_GELU_TANH),
+]
 SIMT_CASES = [
     gemm_case("simt_ragged", 300, 200, 104, bias=True, act=ACT_GELU_TANH, out=("bf16", "f32"), impl=1),
     gemm_case("simt_conv", 0, 64, 0, conv=(2, 24, 24, 64), bias=True, act=ACT_RELU, impl=1),
@@ -589,4 +600,4 @@ def tokenizer_case(dev="cuda:0"):
 FUSED_CASES = [layernorm_case, rmsnorm_case, rope_case, embed_case, argmax_case, patchify_case, assemble_concat_case,
                shuffle_im2col_case, bilinear_case, zoe_tail_case, ego3d_case, tokenizer_case]
 
-ALL_CASES = {c.__name__: c for c in (SIMT_CASES + GEMM_CASES + PAIR_CASES + SKINNY_CASES + ATTN_CASES + FUSED_CASES)}
+ALL_CASES = {c.__name__: c for c in (SIMT_CASES + GEMM_CASES + PAIR_CASES + TMA_EPI_CASES + SKINNY_CASES + ATTN_CASES + FUSED_CASES)}

@@ -79,6 +79,14 @@ def test_public_api_predict_and_decode_actions(tiny_gpu, cuda_device):
         ref = T.decode(out[0].cpu().numpy().reshape(-1, 3) - lo, proc.action_tokenizer.bin_policy, action_config["num_bins"])
         assert np.abs(dec["actions"] - ref).max() < 1e-12
         assert proc.decode_actions_batch(out, unnorm_key="d")["actions"].shape == (2, 2, 7)
+        # device-resident batched decode == the host batched decode, bit for bit (same FP64 kernel + same un-normalisation)
+        stats2 = {"d": {"action": {"q01": [-0.5, -0.25, -1.0, -2.0, -1.0, -1.0, 0.0], "q99": [0.5, 0.75, 1.0, 2.0, 1.5, 1.0, 1.0],
+                                   "mask": [True] * 6 + [False]}}}
+        proc.statistics = stats2
+        dd = proc.decode_actions_device(out, unnorm_key="d")
+        hb = proc.decode_actions_batch(out, unnorm_key="d")
+        assert dd["actions"].is_cuda and dd["actions"].shape == (2, 2, 7)
+        assert np.array_equal(dd["actions"].cpu().numpy(), hb["actions"]) and np.array_equal(dd["action_ids"].cpu().numpy(), hb["action_ids"])
 
 
 def test_tokenizer_one_million_actions_vs_numpy_oracle(cuda_device):

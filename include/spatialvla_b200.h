@@ -109,6 +109,8 @@ typedef struct SvlaAttnArgs {
   int32_t causal;         /* 1: key j visible to query i iff j <= i + (sk - sq) */
   const float* relpos_table; /* fp32 [(2*win-1)^2+3, hq] or NULL (BEiT) */
   int32_t relpos_win;
+  int32_t relpos_head_major; /* 1: relpos_table is stored transposed, [hq, (2*win-1)^2+3] (one contiguous row per head: the
+                                layout the engine packs once at load time so that a CTA reads its head's table coalesced) */
 } SvlaAttnArgs;
 
 int svla_attention(const SvlaAttnArgs* args, void* stream);

@@ -135,7 +135,7 @@ class RefOps:
         return t.as_strided((batch, s, heads, d), (bs, ss, d, 1), t.storage_offset())
 
     def attention(self, q, k, v, out, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
-                  scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0):
+                  scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0, relpos_head_major=False):
         self.launches += 1
         Q = self._strided(q, *q_strides, batch, sq, hq, d).float().permute(0, 2, 1, 3)
         K = self._strided(k, *k_strides, batch, sk, hkv, d).float().permute(0, 2, 1, 3).repeat_interleave(hq // hkv, 1)
@@ -144,6 +144,8 @@ class RefOps:
         if softcap:
             s = softcap * torch.tanh(s / softcap)
         if relpos_table is not None:
+            if relpos_head_major:
+                relpos_table = relpos_table.t()
             from oracle.model_ref import beit_rel_pos_bias
             s = s + beit_rel_pos_bias(relpos_table, relpos_win)[None]
         if causal:

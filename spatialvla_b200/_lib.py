@@ -49,7 +49,7 @@ class SvlaAttnArgs(C.Structure):
         ("v_bs", C.c_int64), ("v_ss", C.c_int64), ("o_bs", C.c_int64), ("o_ss", C.c_int64),
         ("batch", C.c_int32), ("hq", C.c_int32), ("hkv", C.c_int32), ("sq", C.c_int32), ("sk", C.c_int32),
         ("d", C.c_int32), ("scale", C.c_float), ("softcap", C.c_float), ("causal", C.c_int32),
-        ("relpos_table", C.c_void_p), ("relpos_win", C.c_int32),
+        ("relpos_table", C.c_void_p), ("relpos_win", C.c_int32), ("relpos_head_major", C.c_int32),
     ]
 
 

@@ -69,6 +69,7 @@ struct AttnP {
   float scale, softcap;
   int causal;
   const float* relpos;
+  int head_major;
   int win;
 };
 
@@ -124,7 +125,7 @@ svla_flash_attn_kernel(const AttnP p) {
   int nrel = 0;
   if (f_relpos) {
     nrel = (2 * p.win - 1) * (2 * p.win - 1) + 3;
-    for (int i = threadIdx.x; i < nrel; i += kAttnThreads) sTab[i] = p.relpos[static_cast<long long>(i) * p.hq + h] * 1.4426950408889634f;
+    for (int i = threadIdx.x; i < nrel; i += kAttnThreads) sTab[i] = (p.head_major ? p.relpos[static_cast<long long>(h) * nrel + i] : p.relpos[static_cast<long long>(i) * p.hq + h]) * 1.4426950408889634f;
   }
 
   const int n_kv_tiles = (p.sk + kBKV - 1) / kBKV;
@@ -709,7 +710,7 @@ extern "C" int svla_attention(const SvlaAttnArgs* a, void* stream) {
   p.q_bs = a->q_bs; p.q_ss = a->q_ss; p.k_bs = a->k_bs; p.k_ss = a->k_ss; p.v_bs = a->v_bs; p.v_ss = a->v_ss;
   p.o_bs = a->o_bs; p.o_ss = a->o_ss;
   p.hq = a->hq; p.hkv = a->hkv; p.sq = a->sq; p.sk = a->sk; p.d = a->d;
-  p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.relpos = a->relpos_table; p.win = a->relpos_win;
+  p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.relpos = a->relpos_table; p.win = a->relpos_win; p.head_major = a->relpos_head_major;
   const int mode = (p.relpos ? 1 : 0) | (p.softcap > 0.f ? 2 : 0) | (p.causal ? 4 : 0);
   if (a->d <= 32) return launch_attn<32, 8>(p, a->batch, st);
   if (a->d <= 64) return mode == 1 ? launch_attn<64, 1>(p, a->batch, st) : launch_attn<64, 8>(p, a->batch, st);

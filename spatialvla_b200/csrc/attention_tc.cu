@@ -1,12 +1,16 @@
 // G2 on the 5th-generation tensor cores: flash attention with tcgen05.mma, accumulators and P in TMEM, operands by TMA.
 //
-// One CTA = 128 query rows of one (batch, head); 6 warps:
+// One CTA = 128 query rows of one (batch, head); 10 warps:
 //   warp 0   : TMA producer   (Q once; K_j / V_j tiles through a 2-stage mbarrier ring; 3-D tensor maps
 //                              {head columns, tokens, batch} so ragged tails are zero-filled by the hardware)
 //   warp 1   : MMA issuer     S_j = Q K_j^T          (SS: A = Q smem, B = K_j smem, both K-major, SWIZZLE_128B)
 //                             O  += P_j V_j          (TS: A = P_j in TMEM (bf16), B = V_j smem, MN-major, SWIZZLE_128B)
 //              software-pipelined: QK_{j+1} is issued before P_j V_j so the tensor core overlaps the softmax of tile j
-//   warps 2-5: softmax        thread == query row (tcgen05.ld 32x32b): row max / row sum need NO shuffles;
+//   warps 2-9: softmax        two warps per TMEM lane quadrant: warp w and w+4 own the same 32 query rows and split the 64
+//                             keys of a tile (32 columns each), so 16 softmax warps per SM (2 CTAs) hide the TMEM / MUFU /
+//                             shared-memory latencies that bound the 4-warp version (ncu: one warp per scheduler, issue slots
+//                             idle); the row max is exchanged through shared memory under a 64-thread named barrier;
+//                             thread == query row (tcgen05.ld 32x32b): row max / row sum need NO shuffles;
 //                             scores are transformed in the log2 domain (scale, BEiT rel-pos bias from the per-head
 //                             table, tanh soft-capping, ragged / causal mask), P is written back to TMEM as bf16 pairs
 //                             (tcgen05.st) and becomes the A operand of the second MMA;
@@ -26,7 +30,8 @@ using namespace svla_ptx;
 
 constexpr int kBQ = 128;
 constexpr int kBKV = 64;
-constexpr int kThreads = 192;
+constexpr int kSoftWarps = 8;
+constexpr int kThreads = 64 + 32 * kSoftWarps;
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct Params {
@@ -37,20 +42,23 @@ struct Params {
   int causal;
   const float* relpos;
   int win;
+  int head_major;      // relpos is [hq][nrel] (coalesced per-head row) instead of HF's [nrel][hq]
 };
 
 template <int D> struct Cfg {
   static constexpr int kChunks = D / 64;                      // 64-column (128-byte) swizzle chunks per row
   static constexpr int kQBytes = kBQ * D * 2;
   static constexpr int kKBytes = kBKV * D * 2;
-  static constexpr int kStages = 2;
+  // K/V ring depth: the producer may only refill a stage after P_j V_j has retired it, so with 2 stages every tile pays a full
+  // TMA round trip (measured: ~2 us per 64-key tile at d=64 against ~0.15 us of MMA); d=64 has the shared memory for 4 stages
+  static constexpr int kStages = (D <= 64) ? 4 : 2;
   static constexpr int kTmemS = 0;                            // 2 * kBKV columns
   static constexpr int kTmemO = 2 * kBKV;                     // D columns
   static constexpr int kTmemP = 2 * kBKV + D;                 // 2 * kBKV/2 columns
   static constexpr int kTmemUsed = 2 * kBKV + D + kBKV;
   static constexpr int kTmemCols = kTmemUsed <= 256 ? 256 : 512;
   static constexpr int kCtasPerSm = kTmemCols <= 256 ? 2 : 1;
-  static constexpr int kSmemBytes = kQBytes + kStages * 2 * kKBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kQBytes + kStages * 2 * kKBytes + 1024 /*align slack*/ + 256 /*barriers + TMEM slot*/;
 };
 
 // kind::f16 instruction descriptor (D = f32, A = B = bf16) with selectable B major-ness (bit 16: 1 = MN-major)
@@ -90,6 +98,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -113,17 +129,19 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
   uint8_t* sV = sK + C::kStages * C::kKBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + C::kStages * C::kKBytes);
   uint64_t* q_full = bars;                 // 1
-  uint64_t* kv_full = bars + 1;            // [2]
-  uint64_t* kv_empty = bars + 3;           // [2]
-  uint64_t* s_full = bars + 5;             // [2]
-  uint64_t* s_empty = bars + 7;            // [2]  (4 softmax warps)
-  uint64_t* p_full = bars + 9;             // [2]  (4 softmax warps)
-  uint64_t* p_empty = bars + 11;           // [2]  (PV MMA of that tile done)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* kv_full = bars + 1;            // [4]
+  uint64_t* kv_empty = bars + 5;           // [4]
+  uint64_t* s_full = bars + 9;             // [2]
+  uint64_t* s_empty = bars + 11;           // [2]  (8 softmax warps)
+  uint64_t* p_full = bars + 13;            // [2]  (8 softmax warps)
+  uint64_t* p_empty = bars + 15;           // [2]  (PV MMA of that tile done)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 17);
   // rel-pos table (pre-multiplied by log2 e) and per-key index terms live after the barriers
   const int nrel = kRelpos ? (2 * p.win - 1) * (2 * p.win - 1) + 3 : 0;
-  int* sKterm = reinterpret_cast<int*>(bars + 16);               // [2][BKV], 16-byte aligned
-  float* sTab = reinterpret_cast<float*>(sKterm + 2 * BKV);
+  float* sXch = reinterpret_cast<float*>(bars + 20);              // [2 parities][2 column halves][128 rows] row-max exchange
+  int* sKterm = reinterpret_cast<int*>(sXch + 4 * kBQ);           // [n_tiles_all * BKV] per-key index terms (rel-pos only)
+  const int n_tiles_all = (p.sk + BKV - 1) / BKV;
+  float* sTab = reinterpret_cast<float*>(sKterm + (kRelpos ? n_tiles_all * BKV : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kBQ;
@@ -137,20 +155,19 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 4);
-      mbar_init(&p_full[s], 4);
+      mbar_init(&s_empty[s], kSoftWarps);
+      mbar_init(&p_full[s], kSoftWarps);
       mbar_init(&p_empty[s], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<C::kTmemCols, 1>(tmem_ptr_smem);
-  if (kRelpos) {
-    for (int i = threadIdx.x; i < nrel; i += kThreads) sTab[i] = p.relpos[static_cast<long long>(i) * p.hq + h] * kLog2e;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -163,8 +180,8 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
 #pragma unroll
       for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sQ + c * (kBQ * 128), &tm_q, q_full, h * D + c * 64, q0, b);
       for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1u);
+        const int st = j % C::kStages;
+        mbar_wait(&kv_empty[st], ((j / C::kStages) & 1) ^ 1u);
         mbar_expect_tx(&kv_full[st], 2 * C::kKBytes);
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) {
@@ -180,10 +197,10 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       // the last K/V tile only multiplies the 16-key groups that hold valid keys (BEiT: 577 = 9 * 64 + 1 keys)
       auto valid16 = [&](int j) { return min(BKV, (p.sk - j * BKV + 15) & ~15); };
       auto issue_pv = [&](int j) {
-        const int st = j & 1;
+        const int st = j & 1, kst = j % C::kStages;
         mbar_wait(&p_full[st], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t vbase = smem_u32(sV + st * C::kKBytes);
+        const uint32_t vbase = smem_u32(sV + kst * C::kKBytes);
         const int ksteps = valid16(j) >> 4;
         for (int kk = 0; kk < ksteps; ++kk) {
           const uint64_t dv = make_mnmajor_sw128_desc(vbase + kk * 16 * 128, BKV * 128);
@@ -191,15 +208,15 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
                        static_cast<uint32_t>(j > 0 || kk > 0));
         }
         umma_commit(&p_empty[st]);       // P_j consumed, O updated
-        umma_commit(&kv_empty[st]);      // K_j / V_j stage free
+        umma_commit(&kv_empty[kst]);     // K_j / V_j stage free
       };
       mbar_wait(q_full, 0);
       for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        const int st = j & 1, kst = j % C::kStages;
+        mbar_wait(&kv_full[kst], (j / C::kStages) & 1);
         mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1u);
         tc_fence_after();
-        const uint32_t qbase = smem_u32(sQ), kbase = smem_u32(sK + st * C::kKBytes);
+        const uint32_t qbase = smem_u32(sQ), kbase = smem_u32(sK + kst * C::kKBytes);
         const uint32_t idesc_qk = make_idesc(kBQ, valid16(j), 0);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
@@ -214,10 +231,12 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     }
   } else {
     // ============================================================ softmax / correction / epilogue: thread == query row
+    constexpr int HC = BKV / 2;                       // key columns of a tile owned by this warp
+    constexpr int DH = D / 2;                         // O columns rescaled / written by this warp
     const int q = warp & 3;                           // TMEM lane quadrant this warp may access
+    const int ch = (warp - 2) >> 2;                   // column half: warps 2-5 -> 0, warps 6-9 -> 1
     const int row = q * 32 + lane;
     const int qi = q0 + row;
-    const int sidx = threadIdx.x - 64;                // 0..127 over the softmax warps
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
     int qbase = 0;
@@ -228,35 +247,56 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     }
     const float sl2 = p.scale * kLog2e;
     const float c1 = kSoftcap ? p.scale / p.softcap : 0.f, c2 = kSoftcap ? p.softcap * kLog2e : 0.f;
+    if (kRelpos) {
+      // this head's bias table (x log2 e) and the per-key index terms, loaded by the softmax warps only: the TMA producer and
+      // the MMA issuer are already running (ncu on the first version: the strided table gather + CTA-wide barrier in front of
+      // the first TMA cost ~4 us of a ~20 us CTA lifetime)
+      const int tid = threadIdx.x - 64;
+      constexpr int NT = 32 * kSoftWarps;
+      if (p.head_major) {
+        const float* src = p.relpos + static_cast<long long>(h) * nrel;
+        if ((nrel & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+          for (int i = tid; i < (nrel >> 2); i += NT) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(src) + i);
+            t.x *= kLog2e; t.y *= kLog2e; t.z *= kLog2e; t.w *= kLog2e;
+            reinterpret_cast<float4*>(sTab)[i] = t;
+          }
+        } else {
+          for (int i = tid; i < nrel; i += NT) sTab[i] = __ldg(src + i) * kLog2e;
+        }
+      } else {
+        for (int i = tid; i < nrel; i += NT) sTab[i] = p.relpos[static_cast<long long>(i) * p.hq + h] * kLog2e;
+      }
+      for (int kj = tid; kj < n_tiles_all * BKV; kj += NT)
+        sKterm[kj] = (kj >= 1 && kj < p.sk) ? ((kj - 1) / p.win) * (2 * p.win - 1) + (kj - 1) % p.win : 0;
+      asm volatile("bar.sync 5, 256;" ::: "memory");      // softmax warps only (ids 1-4 are the pair barriers)
+    }
+    // the two warps of a quadrant meet on named barrier 1 + q (64 threads)
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
     for (int j = 0; j < n_tiles; ++j) {
       const int st = j & 1;
-      if (kRelpos) {
-        // per-key index terms of this tile, written by the first 64 softmax threads (buffer st was last read at tile j-2)
-        if (sidx < BKV) {
-          const int kj = j * BKV + sidx;
-          sKterm[st * BKV + sidx] = (kj >= 1 && kj < p.sk) ? ((kj - 1) / p.win) * (2 * p.win - 1) + (kj - 1) % p.win : 0;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");      // softmax warps only
-      }
+      const int k0 = j * BKV + ch * HC;               // first key of this warp's columns
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after();
-      float s[BKV];
-#pragma unroll
-      for (int c0 = 0; c0 < BKV; c0 += 32) {
+      float s[HC];
+      {
         uint32_t r[32];
-        tmem_ld32(tmem_base + C::kTmemS + st * BKV + c0 + lane_addr, r);
+        tmem_ld32(tmem_base + C::kTmemS + st * BKV + ch * HC + lane_addr, r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s[c0 + i] = __uint_as_float(r[i]);
+        for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r[i]);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[st]);             // S_j is in registers: the buffer may be overwritten
-      // ---- scores -> log2 domain
-      if (kRelpos) {
-        const float raw0 = s[0];
-        const int4* kt4 = reinterpret_cast<const int4*>(sKterm + st * BKV);
+      if (lane == 0) mbar_arrive(&s_empty[st]);             // this warp's half of S_j is in registers
+      // ---- scores -> log2 domain (skipped when every column of this warp lies behind the last key, e.g. BEiT's 577 = 9*64 + 1)
+      if (k0 >= p.sk) {
 #pragma unroll
-        for (int i4 = 0; i4 < BKV / 4; ++i4) {
+        for (int i = 0; i < HC; ++i) s[i] = -INFINITY;
+      } else if (kRelpos) {
+        const float raw0 = s[0];
+        const int4* kt4 = reinterpret_cast<const int4*>(sKterm + k0);
+#pragma unroll
+        for (int i4 = 0; i4 < HC / 4; ++i4) {
           const int4 kt = kt4[i4];                          // warp-wide broadcast
           const int i0 = cls_q ? nrel - 3 : qbase - kt.x, i1 = cls_q ? nrel - 3 : qbase - kt.y;
           const int i2 = cls_q ? nrel - 3 : qbase - kt.z, i3 = cls_q ? nrel - 3 : qbase - kt.w;
@@ -265,15 +305,15 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
           s[4 * i4 + 2] = fmaf(s[4 * i4 + 2], sl2, sTab[i2]);
           s[4 * i4 + 3] = fmaf(s[4 * i4 + 3], sl2, sTab[i3]);
         }
-        if (j == 0) s[0] = fmaf(raw0, sl2, sTab[cls_q ? nrel - 1 : nrel - 2]);      // CLS key column
+        if (k0 == 0) s[0] = fmaf(raw0, sl2, sTab[cls_q ? nrel - 1 : nrel - 2]);      // CLS key column
       } else if (kSoftcap) {
         float u2max = 0.f;
 #pragma unroll
-        for (int i = 0; i < BKV; ++i) { const float u = s[i] * c1; u2max = fmaxf(u2max, u * u); }
+        for (int i = 0; i < HC; ++i) { const float u = s[i] * c1; u2max = fmaxf(u2max, u * u); }
         if (!__any_sync(0xffffffffu, u2max >= 0.1225f)) {
           // cap * tanh(u) * log2e with a degree-9 odd polynomial (exact to fp32 rounding for |u| < 0.35)
 #pragma unroll
-          for (int i = 0; i < BKV; ++i) {
+          for (int i = 0; i < HC; ++i) {
             const float u = s[i] * c1, u2 = u * u;
             float pl = 62.f / 2835.f;
             pl = fmaf(pl, u2, -17.f / 315.f);
@@ -284,22 +324,26 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
           }
         } else {                                  // rare: a large score somewhere in this warp's rows -> libm tanh
 #pragma unroll
-          for (int i = 0; i < BKV; ++i) s[i] = c2 * tanhf(s[i] * c1);
+          for (int i = 0; i < HC; ++i) s[i] = c2 * tanhf(s[i] * c1);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < BKV; ++i) s[i] *= sl2;
+        for (int i = 0; i < HC; ++i) s[i] *= sl2;
       }
-      if (kCausal || (j + 1) * BKV > p.sk) {
+      if (kCausal || k0 + HC > p.sk) {
 #pragma unroll
-        for (int i = 0; i < BKV; ++i) {
-          const int kj = j * BKV + i;
+        for (int i = 0; i < HC; ++i) {
+          const int kj = k0 + i;
           if (kj >= p.sk || (kCausal && kj > qi + causal_off)) s[i] = -INFINITY;
         }
       }
       float mj = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < BKV; ++i) mj = fmaxf(mj, s[i]);
+      for (int i = 0; i < HC; ++i) mj = fmaxf(mj, s[i]);
+      // ---- row max over the whole tile: exchange with the partner warp (parity-double-buffered, one barrier per tile)
+      sXch[(st * 2 + ch) * kBQ + row] = mj;
+      pair_sync();
+      mj = fmaxf(mj, sXch[(st * 2 + (ch ^ 1)) * kBQ + row]);
       // ---- lazy rescale: keep the stale max unless it grows by more than 8 (P <= 2^8: bf16/fp32 lose nothing)
       float alpha = 1.f;
       bool rescale = false;
@@ -310,21 +354,21 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       }
       const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
       float lsum = 0.f;
-      uint32_t pk[BKV / 2];
+      uint32_t pk[HC / 2];
 #pragma unroll
-      for (int i = 0; i < BKV; i += 2) {
+      for (int i = 0; i < HC; i += 2) {
         const float p0 = ex2f(s[i] - m_use), p1 = ex2f(s[i + 1] - m_use);
         lsum += p0 + p1;
         pk[i >> 1] = pack_bf16x2(p0, p1);
       }
-      l_run = l_run * alpha + lsum;
+      l_run = l_run * alpha + lsum;                          // partial row sum over this warp's columns
       // P buffer st was read by P_{j-2} V_{j-2}; a rescale additionally needs P_{j-1} V_{j-1} (the last writer of O) done
       if (j >= 2) mbar_wait(&p_empty[st], ((j - 2) >> 1) & 1);
-      if (__any_sync(0xffffffffu, rescale)) {
+      if (__any_sync(0xffffffffu, rescale)) {                // identical decision in both warps of the pair (same rows, same max)
         mbar_wait(&p_empty[st ^ 1], ((j - 1) >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < D; c0 += 32) {
+        for (int c0 = ch * DH; c0 < (ch + 1) * DH; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(tmem_base + C::kTmemO + c0 + lane_addr, r);
 #pragma unroll
@@ -333,20 +377,24 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
         }
       }
       tc_fence_after();
-      tmem_st32(tmem_base + C::kTmemP + st * (BKV / 2) + lane_addr, pk);
+      tmem_st16(tmem_base + C::kTmemP + st * (BKV / 2) + ch * (HC / 2) + lane_addr, pk);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[st]);
     }
-    // ---- epilogue: wait for the last P V, O / l -> bf16 -> global
+    // ---- epilogue: total row sum (both column halves), wait for the last P V, O / l -> bf16 -> global
+    pair_sync();                                             // the partner has finished reading the exchange buffers
+    sXch[ch * kBQ + row] = l_run;
+    pair_sync();
+    l_run += sXch[(ch ^ 1) * kBQ + row];
     const int last = n_tiles - 1;
     mbar_wait(&p_empty[last & 1], (last >> 1) & 1);
     tc_fence_after();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
     __nv_bfloat16* og = p.out + b * p.o_bs + static_cast<long long>(qi) * p.o_ss + static_cast<long long>(h) * D;
 #pragma unroll 1
-    for (int c0 = 0; c0 < D; c0 += 32) {
+    for (int c0 = ch * DH; c0 < (ch + 1) * DH; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + C::kTmemO + c0 + lane_addr, r);
       if (qi < p.sq) {
@@ -402,7 +450,8 @@ template <int D, int MODE>
 static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, int batch, cudaStream_t st) {
   using C = Cfg<D>;
   const int nrel = (MODE & 1) ? (2 * p.win - 1) * (2 * p.win - 1) + 3 : 0;
-  const size_t smem = C::kSmemBytes + 2 * kBKV * 4 + static_cast<size_t>(nrel) * 4;
+  const int n_tiles_all = (p.sk + kBKV - 1) / kBKV;
+  const size_t smem = C::kSmemBytes + 4 * kBQ * 4 + ((MODE & 1) ? static_cast<size_t>(n_tiles_all) * kBKV * 4 : 0) + static_cast<size_t>(nrel) * 4;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(svla_flash_attn_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -435,7 +484,7 @@ int svla_attention_tc_try(const SvlaAttnArgs* a, void* stream) {
   p.out = static_cast<__nv_bfloat16*>(a->out);
   p.o_bs = a->o_bs; p.o_ss = a->o_ss;
   p.hq = a->hq; p.hkv = a->hkv; p.sq = a->sq; p.sk = a->sk; p.d = a->d;
-  p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.relpos = a->relpos_table; p.win = a->relpos_win;
+  p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.relpos = a->relpos_table; p.win = a->relpos_win; p.head_major = a->relpos_head_major;
   // a batch stride of 0 is not expressible in a tensor map; batch == 1 problems get a dummy stride
   const uint64_t nb = static_cast<uint64_t>(a->batch);
   auto bstride = [&](int64_t bs, int64_t ss, int s) { return static_cast<uint64_t>(nb > 1 ? bs : ss * s); };

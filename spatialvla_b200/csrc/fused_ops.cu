@@ -297,11 +297,14 @@ __global__ void svla_rope_kv_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_
   for (int i = threadIdx.x; i < hkv * d; i += blockDim.x) vc[cache_row + i] = __float2bfloat16(load(voff + i));
 }
 
-// Vectorised prefill variant (bf16 qkv in): a thread owns 8 consecutive frequencies (one 16-byte load per half),
-// computes their 8 sincos once and reuses them for every q/k head; V rows are copied with 16-byte accesses.
+// Vectorised prefill variant (bf16 qkv in): the block first computes the token's d/2 (cos, sin) pairs ONCE into shared memory
+// (one powf + sincosf per thread -- ncu showed the earlier per-thread 8x powf/sincosf made the kernel issue-bound at 39 % of HBM),
+// then a thread owns 8 consecutive frequencies (one 16-byte load per half) of every q/k head it visits; V rows are copied with
+// 16-byte accesses.
 __global__ void __launch_bounds__(128)
 svla_rope_kv_vec_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ kc,
                         __nv_bfloat16* __restrict__ vc, int s, int hq, int hkv, int d, int smax, int pos0, float theta) {
+  __shared__ __align__(16) float s_cs[128], s_sn[128];      // d <= 256
   const long long tok = blockIdx.x;
   const int b = static_cast<int>(tok / s), si = static_cast<int>(tok % s);
   const int pos = pos0 + si;
@@ -311,15 +314,25 @@ svla_rope_kv_vec_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
   const long long width = static_cast<long long>(hq + 2 * hkv) * d;
   const __nv_bfloat16* src = qkv + tok * width;
   const long long cache_row = (static_cast<long long>(b) * smax + pos) * hkv * d;
+  // V copy first: independent of the trigonometry, its loads are in flight while the sincos table is built
+  {
+    const uint4* vsrc = reinterpret_cast<const uint4*>(src + static_cast<long long>(hq + hkv) * d);
+    uint4* vdst = reinterpret_cast<uint4*>(vc + cache_row);
+    for (int i = threadIdx.x; i < (hkv * d) >> 3; i += blockDim.x) vdst[i] = vsrc[i];
+  }
+  for (int j = threadIdx.x; j < half; j += blockDim.x) {
+    // inv_freq = 1 / theta^(2j/d) in fp32 exactly like torch: base ** (arange(0,d,2).float()/d)
+    const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * j) / static_cast<float>(d));
+    sincosf(fpos * inv_freq, &s_sn[j], &s_cs[j]);
+  }
+  __syncthreads();
   const int jt = threadIdx.x % tph, hl = threadIdx.x / tph, hlanes = blockDim.x / tph;
   if (hl < hlanes) {
     float sn[8], cs[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int j = jt * 8 + e;
-      const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * j) / static_cast<float>(d));
-      sincosf(fpos * inv_freq, &sn[e], &cs[e]);
-    }
+    const float4 c0 = *reinterpret_cast<const float4*>(s_cs + jt * 8), c1 = *reinterpret_cast<const float4*>(s_cs + jt * 8 + 4);
+    const float4 n0 = *reinterpret_cast<const float4*>(s_sn + jt * 8), n1 = *reinterpret_cast<const float4*>(s_sn + jt * 8 + 4);
+    cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
+    sn[0] = n0.x; sn[1] = n0.y; sn[2] = n0.z; sn[3] = n0.w; sn[4] = n1.x; sn[5] = n1.y; sn[6] = n1.z; sn[7] = n1.w;
     for (int hh = hl; hh < hq + hkv; hh += hlanes) {
       float x1[8], x2[8];
       unpack8(*reinterpret_cast<const uint4*>(src + hh * d + jt * 8), x1);
@@ -335,9 +348,6 @@ svla_rope_kv_vec_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
       *reinterpret_cast<uint4*>(dst + half + jt * 8) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
     }
   }
-  const uint4* vsrc = reinterpret_cast<const uint4*>(src + static_cast<long long>(hq + hkv) * d);
-  uint4* vdst = reinterpret_cast<uint4*>(vc + cache_row);
-  for (int i = threadIdx.x; i < (hkv * d) >> 3; i += blockDim.x) vdst[i] = vsrc[i];
 }
 
 // ------------------------------------------------------------------------------------------ M6 embedding gather
@@ -894,7 +904,7 @@ extern "C" int svla_rope_kv(const void* qkv, void* q_out, void* kcache, void* vc
   SVLA_REQUIRE((qkv || qkv_f32) && q_out && kcache && vcache, "svla_rope_kv: null pointer");
   SVLA_REQUIRE(batch > 0 && s > 0 && (d % 2) == 0 && pos0 >= 0 && pos0 + s <= smax, "svla_rope_kv: bad geometry (pos0=%d s=%d smax=%d)", pos0, s, smax);
   SVLA_REQUIRE(d / 2 <= 512, "svla_rope_kv: head dim too large");
-  if (qkv_f32 == nullptr && (d % 16) == 0 && (d / 16) <= 128 && 128 % (d / 16) == 0 && batch * s > 1024) {
+  if (qkv_f32 == nullptr && (d % 16) == 0 && d <= 256 && 128 % (d / 16) == 0 && batch * s > 1024) {
     svla_rope_kv_vec_kernel<<<static_cast<unsigned>(batch) * s, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(q_out), static_cast<__nv_bfloat16*>(kcache),
         static_cast<__nv_bfloat16*>(vcache), s, hq, hkv, d, smax, pos0, theta);

@@ -140,7 +140,8 @@ class SpatialVLAEngine:
                 "wqkv": self._w(torch.cat([sd[q + "attention.attention.query.weight"], sd[q + "attention.attention.key.weight"],
                                            sd[q + "attention.attention.value.weight"]], 0), BF16),
                 "bqkv": self._w(torch.cat([qb, torch.zeros_like(qb), vb], 0), F32),
-                "relpos": Fp(q + "attention.attention.relative_position_bias.relative_position_bias_table"),
+                # [heads, (2w-1)^2+3]: one contiguous row per head (the attention CTA of head h reads its row coalesced)
+                "relpos": self._w(sd[q + "attention.attention.relative_position_bias.relative_position_bias_table"].t(), F32),
                 "wo": W(q + "attention.output.dense.weight"), "bo": Fp(q + "attention.output.dense.bias"),
                 "l1": Fp(q + "lambda_1"), "l2": Fp(q + "lambda_2"),
                 "wi": W(q + "intermediate.dense.weight"), "bi": Fp(q + "intermediate.dense.bias"),
@@ -291,7 +292,7 @@ class SpatialVLAEngine:
         for i, L_ in enumerate(bt["layers"]):
             ops.layernorm(x, L_["lnb_g"], L_["lnb_b"], eps, out_bf16=h)
             qkv = self._lin(h, L_["wqkv"], B * S, bias=L_["bqkv"])
-            ctx = self._mha(qkv, B, S, nh, C_ // nh, 1.0 / math.sqrt(C_ // nh), relpos_table=L_["relpos"], relpos_win=win)
+            ctx = self._mha(qkv, B, S, nh, C_ // nh, 1.0 / math.sqrt(C_ // nh), relpos_table=L_["relpos"], relpos_win=win, relpos_head_major=True)
             ops.gemm(ctx, L_["wo"], bias=L_["bo"], colscale=L_["l1"], out_f32=x, accumulate=True)
             ops.layernorm(x, L_["lna_g"], L_["lna_b"], eps, out_bf16=h)
             f = self._lin(h, L_["wi"], B * S, bias=L_["bi"], act=ACT_GELU_ERF)

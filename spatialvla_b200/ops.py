@@ -137,8 +137,9 @@ class CudaOps:
 
     # ---- G2 / G3
     def attention(self, q, k, v, out, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
-                  scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0):
-        """strides = (batch stride, token stride) in elements; head h lives at column offset h*d."""
+                  scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0, relpos_head_major=False):
+        """strides = (batch stride, token stride) in elements; head h lives at column offset h*d.
+        relpos_table: fp32 [(2*win-1)^2+3, hq] (HF layout) or, with relpos_head_major, its transpose [hq, (2*win-1)^2+3]."""
         a = L.SvlaAttnArgs()
         for t in (q, k, v, out):
             _req(t.dtype == BF16, "attention: bf16 only")
@@ -150,7 +151,8 @@ class CudaOps:
         a.batch, a.hq, a.hkv, a.sq, a.sk, a.d = batch, hq, hkv, sq, sk, d
         a.scale, a.softcap, a.causal = float(scale), float(softcap or 0.0), int(bool(causal))
         _req(relpos_table is None or relpos_table.dtype == F32, "attention: relpos table must be fp32")
-        a.relpos_table, a.relpos_win = _ptr(relpos_table), int(relpos_win)
+        _req(relpos_table is None or relpos_table.is_contiguous(), "attention: relpos table must be contiguous")
+        a.relpos_table, a.relpos_win, a.relpos_head_major = _ptr(relpos_table), int(relpos_win), int(bool(relpos_head_major))
         L.check(self.lib.svla_attention(C.byref(a), self._stream()), "svla_attention")
 
     def decode_attention(self, q, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, scale, softcap=0.0):

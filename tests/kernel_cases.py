@@ -242,7 +242,7 @@ SKINNY_CASES = [
 
 # ------------------------------------------------------------------------------------------------ attention
 def attn_case(name, B, hq, hkv, sq, sk, d, *, scale=None, softcap=0.0, causal=False, relpos_win=0, packed_qkv=False,
-              smax=None, seed=0):
+              smax=None, seed=0, head_major=False):
     def case(dev="cuda:0"):
         g = _gen(seed)
         sc = scale if scale is not None else d ** -0.5
@@ -250,6 +250,8 @@ def attn_case(name, B, hq, hkv, sq, sk, d, *, scale=None, softcap=0.0, causal=Fa
             D = hq * d
             qkv = _randn(g, B * sq, 3 * D, dtype=BF16)
             tab = _randn(g, (2 * relpos_win - 1) ** 2 + 3, hq, scale=0.5) if relpos_win else None
+            if tab is not None and head_major:
+                tab = tab.t().contiguous()          # [hq, nrel]: the layout the engine packs at load time
 
             def run(ops, to):
                 t = to(qkv)
@@ -257,7 +259,7 @@ def attn_case(name, B, hq, hkv, sq, sk, d, *, scale=None, softcap=0.0, causal=Fa
                 st = (sq * 3 * D, 3 * D)
                 ops.attention(t, t[:, D:], t[:, 2 * D:], out, batch=B, hq=hq, hkv=hkv, sq=sq, sk=sk, d=d, q_strides=st,
                               k_strides=st, v_strides=st, o_strides=(sq * D, D), scale=sc, softcap=softcap, causal=causal,
-                              relpos_table=to(tab), relpos_win=relpos_win)
+                              relpos_table=to(tab), relpos_win=relpos_win, relpos_head_major=head_major)
                 return out
         else:               # Gemma2 layout: q [B*sq, hq*d], cache [B, smax, hkv, d]
             sm = smax or sk
@@ -330,6 +332,8 @@ ATTN_CASES = [
     # tcgen05 path (attention_tc.cu): batch > 1 through the 3-D tensor maps, ragged tails, sharp softmax (lazy O
     # rescale fires), large soft-cap arguments (libm tanh branch), causal tile skipping, GQA, sq != sk
     attn_case("attn_tc_beit_batch3", 3, 4, 4, 577, 577, 64, packed_qkv=True, relpos_win=24, seed=5),
+    attn_case("attn_tc_beit_head_major", 2, 5, 5, 577, 577, 64, packed_qkv=True, relpos_win=24, seed=7, head_major=True),
+    attn_case("attn_tc_beit_head_major_win5", 2, 3, 3, 26, 26, 64, packed_qkv=True, relpos_win=5, seed=8, head_major=True),
     attn_case("attn_tc_d64_sharp_relpos", 2, 3, 3, 577, 577, 64, packed_qkv=True, relpos_win=24, scale=1.0, seed=6),
     attn_case("attn_tc_d64_plain_ragged", 2, 2, 2, 130, 200, 64, smax=210, seed=7),
     attn_case("attn_tc_d64_tiny", 1, 1, 1, 1, 1, 64, smax=8, seed=8),

@@ -111,6 +111,8 @@ typedef struct SvlaAttnArgs {
   int32_t relpos_win;
   int32_t relpos_head_major; /* 1: relpos_table is stored transposed, [hq, (2*win-1)^2+3] (one contiguous row per head: the
                                 layout the engine packs once at load time so that a CTA reads its head's table coalesced) */
+  const int32_t* kv_start;   /* device int32 [batch] or NULL: keys j < kv_start[b] are masked for every query of batch row b
+                                (left-padded prompts: attention_mask == 0 columns, model/modeling_spatialvla.py:298-303) */
 } SvlaAttnArgs;
 
 int svla_attention(const SvlaAttnArgs* args, void* stream);
@@ -118,7 +120,8 @@ int svla_attention(const SvlaAttnArgs* args, void* stream);
 /* G3: single-query decode attention over the KV cache (model/modeling_gemma2.py:387-395,169-195).
  * q bf16 [B, hq*D]; kcache/vcache bf16 [B, smax, hkv, D]; attends to positions [0, ctx). out bf16 [B, hq*D] */
 int svla_decode_attention(const void* q, const void* kcache, const void* vcache, void* out, int batch, int hq,
-                          int hkv, int d, int smax, int ctx, float scale, float softcap, void* stream);
+                          int hkv, int d, int smax, int ctx, float scale, float softcap, const int32_t* kv_start,
+                          void* stream);
 
 /* G3f: decode step after the qkv projection in ONE launch: RoPE of the new token's q/k (1-indexed position ctx), append of
  * its k/v at cache slot ctx-1, soft-capped softmax attention over slots [0, ctx) (model/modeling_gemma2.py:95-154,169-195,
@@ -126,7 +129,7 @@ int svla_decode_attention(const void* q, const void* kcache, const void* vcache,
  * elements); kcache/vcache bf16 [B, smax, hkv, D]; out bf16 [B, hq*D]. D = 256, hq/hkv in {1, 2}. */
 int svla_decode_attention_fused(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache, void* vcache,
                                 void* out, int batch, int hq, int hkv, int d, int smax, int ctx, float theta, float scale,
-                                float softcap, void* stream);
+                                float softcap, const int32_t* kv_start, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Memory-bound fused kernels
@@ -145,10 +148,13 @@ int svla_rmsnorm_residual(float* x, const float* branch, const float* w_post, co
 
 /* M3 RoPE + KV-cache write (model/modeling_gemma2.py:95-154,376-395; positions 1-indexed per
  * model/modeling_spatialvla.py:371-372). qkv bf16 [B*S, (hq+2hkv)*D] -> q_out bf16 [B*S, hq*D] (rotated),
- * kcache/vcache bf16 [B, smax, hkv, D] rows [pos0, pos0+S). */
+ * kcache/vcache bf16 [B, smax, hkv, D] rows [pos0, pos0+S).
+ * row_pads: device int32 [B] or NULL -- leading padding tokens per row of a left-padded batch: cache slot i of row b gets
+ * position i - row_pads[b] + 1 (padding slots: 2), the position ids HF generate derives from the attention mask
+ * (model/modeling_gemma2.py:1042-1051 + model/modeling_spatialvla.py:473-474). */
 int svla_rope_kv(const void* qkv, void* q_out, void* kcache, void* vcache, int batch, int s, int hq, int hkv,
                  int d, int smax, int pos0, float theta, const float* qkv_f32, int n_partials, int64_t partial_stride,
-                 void* stream);
+                 const int32_t* row_pads, void* stream);
 /* qkv_f32 != NULL: read qkv as the sum of n_partials fp32 partial buffers instead of the bf16 `qkv` */
 
 /* M6 embedding gather (model/modeling_spatialvla.py:361-387, model/modeling_gemma2.py:741-742):

@@ -120,3 +120,33 @@ def reference_greedy(model, input_ids, pixel_values, intrinsic, n_new, act_lo, a
             out = model(input_ids=feed, attention_mask=torch.zeros(B, 1, 1, L), past_key_values=cache,
                         use_cache=True, cache_position=torch.tensor([L - 1]))
     return torch.cat(toks, 1), torch.stack(logs, 1)
+
+
+def reference_greedy_padded(model, input_ids, attention_mask, pixel_values, intrinsic, n_new, act_lo, act_hi):
+    """Left-padded batch through the reference forward(): the 2-D attention_mask goes to the reference's own
+    `_update_causal_mask` (model/modeling_spatialvla.py:258-306: bidirectional prompt, padded key columns -> min), and the
+    position ids are the ones HF-4.47 generate derives from the mask (model/modeling_gemma2.py:1042-1051 cumsum - 1, pads -> 1)
+    plus the +1 of model/modeling_spatialvla.py:473-474.  Returns (tokens [B,n_new], action-slice logits [B,n_new,n_act])."""
+    import torch
+    from transformers.cache_utils import DynamicCache
+    B, P = input_ids.shape
+    cache = DynamicCache(config=model.config.text_config)
+    am = attention_mask.to(torch.int64)
+    toks, logs = [], []
+    with torch.no_grad():
+        pos = (am.cumsum(-1) - 1).masked_fill(am == 0, 1) + 1
+        out = model(input_ids=input_ids, pixel_values=pixel_values, intrinsic=intrinsic, attention_mask=am, position_ids=pos,
+                    past_key_values=cache, use_cache=True, cache_position=torch.arange(P))
+        for t in range(n_new):
+            sl = out.logits[:, -1, act_lo:act_hi].float()
+            logs.append(sl)
+            nxt = sl.argmax(-1, keepdim=True) + act_lo
+            toks.append(nxt)
+            if t == n_new - 1:
+                break
+            am = torch.cat([am, torch.ones(B, 1, dtype=torch.int64)], 1)
+            L = P + t + 1
+            pos = ((am.cumsum(-1) - 1).masked_fill(am == 0, 1) + 1)[:, -1:]
+            out = model(input_ids=nxt, attention_mask=am, position_ids=pos, past_key_values=cache, use_cache=True,
+                        cache_position=torch.tensor([L - 1]))
+    return torch.cat(toks, 1), torch.stack(logs, 1)

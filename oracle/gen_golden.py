@@ -146,7 +146,42 @@ def gen_model(n_new=6):
     print("tiny_model: tokens", toks.tolist(), "domain_logits", zo.domain_logits.tolist())
 
 
+def padded_inputs(seed=1):
+    """3 rows with prompts of 6 / 3 / 1 text tokens, LEFT-padded (pad id 0, attention_mask 0) to a common length."""
+    cfg, px_u8, _, K = tiny_inputs(B=3, seed=seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    rows, masks = [], []
+    Tmax = 6
+    for T in (6, 3, 1):
+        real = torch.cat([torch.full((256,), cfg["image_token_index"]), torch.tensor([2]), torch.randint(3, 1000, (T,), generator=g),
+                          torch.tensor([108])])
+        pad = Tmax - T
+        rows.append(torch.cat([torch.zeros(pad, dtype=torch.int64), real]))
+        masks.append(torch.cat([torch.zeros(pad, dtype=torch.int64), torch.ones(real.numel(), dtype=torch.int64)]))
+    return cfg, px_u8, torch.stack(rows), torch.stack(masks), K
+
+
+def gen_model_padded(n_new=6):
+    """Left-padded batch through the live reference (masks by its own _update_causal_mask) -> tests/golden/tiny_model_padded.npz"""
+    cfg, px_u8, ids, am, K = padded_inputs()
+    px = px_u8.float() / 255.0
+    model = compat.build_reference_model(cfg)
+    model.load_state_dict(synth_state_dict(cfg, seed=0), strict=True)
+    lo, hi = cfg["action_token_begin_idx"], cfg["action_token_begin_idx"] + cfg["spatial_token_num"]
+    toks, logits = compat.reference_greedy_padded(model, ids, am, px, K, n_new, lo, hi)
+    # size-independent property the tests reuse: a padded row decodes exactly like the same sample alone, unpadded
+    # (ZoeDepth's router is batch-coupled, so the comparison forces the batch's head)
+    np.savez_compressed(os.path.join(GOLD, "tiny_model_padded.npz"), pixel_u8=px_u8.numpy(), input_ids=ids.numpy(),
+                        attention_mask=am.numpy(), intrinsic=K.numpy(), tokens=toks.numpy(),
+                        logits=logits.numpy().astype(np.float32), n_new=np.int64(n_new))
+    print("tiny_model_padded: tokens", toks.tolist())
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "padded":
+        gen_model_padded()
+        sys.exit(0)
     gen_tokenizer()
     gen_model()
+    gen_model_padded()

@@ -337,12 +337,12 @@ def _rms(x, w, eps):
 
 
 def _rope(x, pos, theta):
-    """model/modeling_gemma2.py:95-154: half-rotation layout, fp32 cos/sin. x (B,h,S,hd), pos (S,) 1-indexed"""
+    """model/modeling_gemma2.py:95-154: half-rotation layout, fp32 cos/sin. x (B,h,S,hd), pos (S,) or (B,S), 1-indexed"""
     hd = x.shape[-1]
     inv = 1.0 / (theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
-    fr = pos.float()[:, None] * inv[None]
+    fr = pos.float()[..., None] * inv
     emb = torch.cat([fr, fr], -1)
-    cos, sin = emb.cos()[None, None], emb.sin()[None, None]
+    cos, sin = (emb.cos()[None, None], emb.sin()[None, None]) if pos.dim() == 1 else (emb.cos()[:, None], emb.sin()[:, None])
     x1, x2 = x[..., : hd // 2], x[..., hd // 2:]
     return x * cos + torch.cat([-x2, x1], -1) * sin
 
@@ -363,19 +363,30 @@ def embed_inputs(sd, cfg, input_ids, image_feats=None):
     return emb * torch.tensor(t["hidden_size"] ** 0.5, dtype=emb.dtype)
 
 
-def gemma2_forward(sd, cfg, x, pos_start, kv_cache, bidirectional):
+def padded_positions(pos_start, S, pads):
+    """Position ids of cache slots [pos_start, pos_start + S) for rows with `pads` leading padding tokens, as HF generate
+    builds them (model/modeling_gemma2.py:1042-1051: cumsum(attention_mask) - 1, pads -> 1) plus the +1 of
+    model/modeling_spatialvla.py:473-474: the k-th real token of a row sits at position k + 1, padding slots at 2."""
+    slot = torch.arange(pos_start, pos_start + S)[None, :]
+    pos = slot - pads[:, None] + 1
+    return torch.where(slot < pads[:, None], torch.full_like(pos, 2), pos)
+
+
+def gemma2_forward(sd, cfg, x, pos_start, kv_cache, bidirectional, pads=None):
     """model/modeling_gemma2.py:364-413 (attention), :451-506 (sandwich-norm layer), :680-793 (stack),
     :993-997 (lm_head + final softcap is applied by the caller on the rows it keeps).
     x (B,S,H) already scaled; positions are pos_start+1 ... (1-indexed, model/modeling_spatialvla.py:371-372).
     kv_cache: list of [k, v] per layer (appended in place). Prefill is bidirectional over the prompt
-    (model/modeling_spatialvla.py:291-297), decode rows attend to everything cached."""
+    (model/modeling_spatialvla.py:291-297), decode rows attend to everything cached.
+    pads (B,) int64: leading padding tokens per row (left-padded batch, attention_mask = 0 on them): their key columns are
+    masked for every query (model/modeling_spatialvla.py:298-303) and positions restart at 1 on the first real token."""
     t = cfg["text_config"]
     nh, nkv, hd = t["num_attention_heads"], t["num_key_value_heads"], t["head_dim"]
     eps, theta = t["rms_norm_eps"], t.get("rope_theta", 10000.0)
     scale = t["query_pre_attn_scalar"] ** -0.5
     cap = t["attn_logit_softcapping"]
     B, S, H = x.shape
-    pos = torch.arange(pos_start, pos_start + S) + 1
+    pos = torch.arange(pos_start, pos_start + S) + 1 if pads is None else padded_positions(pos_start, S, pads)
     for i in range(t["num_hidden_layers"]):
         q = f"language_model.model.layers.{i}."
         h = _rms(x, sd[q + "input_layernorm.weight"], eps)
@@ -397,6 +408,8 @@ def gemma2_forward(sd, cfg, x, pos_start, kv_cache, bidirectional):
             L = K.shape[2]
             mask = torch.arange(L)[None, :] > (torch.arange(S)[:, None] + (L - S))
             sc = sc.masked_fill(mask, float("-inf"))
+        if pads is not None:
+            sc = sc.masked_fill((torch.arange(K.shape[2])[None, :] < pads[:, None])[:, None, None, :], float("-inf"))
         ctx = (torch.softmax(sc, -1) @ V).transpose(1, 2).reshape(B, S, nh * hd)
         a = F.linear(ctx, sd[q + "self_attn.o_proj.weight"])
         x = x + _rms(a, sd[q + "post_attention_layernorm.weight"], eps)
@@ -416,8 +429,20 @@ def lm_head_slice(sd, cfg, h, lo, hi):
     return lg
 
 
+def left_pads(attention_mask):
+    """(B,P) 0/1 mask -> (B,) number of leading zeros; raises unless every row is zeros followed by ones (left padding, the
+    Gemma tokenizer's padding side) with at least one real token."""
+    am = attention_mask.to(torch.int64)
+    pads = (am == 0).sum(1)
+    P = am.shape[1]
+    expect = (torch.arange(P)[None, :] >= pads[:, None]).to(torch.int64)
+    if not torch.equal(am.cpu(), expect.cpu()) or int(pads.max()) >= P:
+        raise NotImplementedError("only left-padded batches (attention_mask = 0...01...1) are supported")
+    return pads
+
+
 def predict_action_ref(sd, cfg, input_ids, pixel_values, intrinsic, n_new, forced_tokens=None, force_head=None,
-                       return_aux=False):
+                       return_aux=False, attention_mask=None):
     """Greedy action-token decode = model/modeling_spatialvla.py:484-492 with the action-restricted argmax
     of SURVEY.md §7.  Returns (tokens (B,n_new) int64, logits (B,n_new,n_action) fp32 post-softcap)."""
     lo = cfg["action_token_begin_idx"]
@@ -427,7 +452,8 @@ def predict_action_ref(sd, cfg, input_ids, pixel_values, intrinsic, n_new, force
         x = embed_inputs(sd, cfg, input_ids, feats)
         B, P, _ = x.shape
         cache = [None] * cfg["text_config"]["num_hidden_layers"]
-        h = gemma2_forward(sd, cfg, x, 0, cache, bidirectional=True)
+        pads = None if attention_mask is None else left_pads(attention_mask)
+        h = gemma2_forward(sd, cfg, x, 0, cache, bidirectional=True, pads=pads)
         toks, logs = [], []
         for step in range(n_new):
             lg = lm_head_slice(sd, cfg, h[:, -1], lo, hi)
@@ -438,7 +464,7 @@ def predict_action_ref(sd, cfg, input_ids, pixel_values, intrinsic, n_new, force
                 break
             feed = nxt if forced_tokens is None else forced_tokens[:, step]
             x = embed_inputs(sd, cfg, feed[:, None])
-            h = gemma2_forward(sd, cfg, x, P + step, cache, bidirectional=False)
+            h = gemma2_forward(sd, cfg, x, P + step, cache, bidirectional=False, pads=pads)
     out = (torch.stack(toks, 1), torch.stack(logs, 1))
     if return_aux:
         aux["image_features"] = feats

@@ -135,7 +135,7 @@ class RefOps:
         return t.as_strided((batch, s, heads, d), (bs, ss, d, 1), t.storage_offset())
 
     def attention(self, q, k, v, out, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
-                  scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0, relpos_head_major=False):
+                  scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0, relpos_head_major=False, kv_start=None):
         self.launches += 1
         Q = self._strided(q, *q_strides, batch, sq, hq, d).float().permute(0, 2, 1, 3)
         K = self._strided(k, *k_strides, batch, sk, hkv, d).float().permute(0, 2, 1, 3).repeat_interleave(hq // hkv, 1)
@@ -148,6 +148,8 @@ class RefOps:
                 relpos_table = relpos_table.t()
             from oracle.model_ref import beit_rel_pos_bias
             s = s + beit_rel_pos_bias(relpos_table, relpos_win)[None]
+        if kv_start is not None:
+            s = s.masked_fill((torch.arange(sk)[None, :] < kv_start.long()[:, None])[:, None, None, :], float("-inf"))
         if causal:
             m = torch.arange(sk)[None, :] > (torch.arange(sq)[:, None] + (sk - sq))
             s = s.masked_fill(m, float("-inf"))
@@ -157,7 +159,7 @@ class RefOps:
         o = (e.to(BF16).float() @ V) / e.sum(-1, keepdim=True)
         self._strided(out, *o_strides, batch, sq, hq, d).copy_(o.permute(0, 2, 1, 3).to(BF16))
 
-    def decode_attention(self, q, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, scale, softcap=0.0):
+    def decode_attention(self, q, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, scale, softcap=0.0, kv_start=None):
         self.launches += 1
         Q = q.float().view(batch, hq, 1, d)
         K = kcache.float().view(batch, smax, hkv, d)[:, :ctx].permute(0, 2, 1, 3).repeat_interleave(hq // hkv, 1)
@@ -165,14 +167,19 @@ class RefOps:
         s = (Q @ K.transpose(-1, -2)) * scale
         if softcap:
             s = softcap * torch.tanh(s / softcap)
+        if kv_start is not None:
+            s = s.masked_fill((torch.arange(ctx)[None, :] < kv_start.long()[:, None])[:, None, None, :], float("-inf"))
         p = torch.softmax(s, -1).to(BF16).float()
         out.view(batch, hq, d)[:] = (p @ V).squeeze(2).to(BF16)
 
-    def decode_attention_fused(self, qkv_partials, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, theta, scale, softcap=0.0):
+    def decode_attention_fused(self, qkv_partials, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, theta, scale, softcap=0.0,
+                               kv_start=None):
         q = torch.empty(batch, hq * d, dtype=BF16)
-        self.rope_kv(qkv_partials, q, kcache, vcache, batch=batch, s=1, hq=hq, hkv=hkv, d=d, smax=smax, pos0=ctx - 1, theta=theta)
+        self.rope_kv(qkv_partials, q, kcache, vcache, batch=batch, s=1, hq=hq, hkv=hkv, d=d, smax=smax, pos0=ctx - 1, theta=theta,
+                     row_pads=kv_start)
         self.launches -= 1                      # one launch on the device
-        self.decode_attention(q, kcache, vcache, out, batch=batch, hq=hq, hkv=hkv, d=d, smax=smax, ctx=ctx, scale=scale, softcap=softcap)
+        self.decode_attention(q, kcache, vcache, out, batch=batch, hq=hq, hkv=hkv, d=d, smax=smax, ctx=ctx, scale=scale, softcap=softcap,
+                              kv_start=kv_start)
 
     # ---- fused memory-bound ops
     def layernorm(self, x, gamma, beta, eps, *, out_bf16=None, out_f32=None, relu=False):
@@ -197,15 +204,20 @@ class RefOps:
         if w_pre is not None:
             out_bf16.copy_(rms(x, w_pre).view_as(out_bf16).to(BF16))
 
-    def rope_kv(self, qkv, q_out, kcache, vcache, *, batch, s, hq, hkv, d, smax, pos0, theta):
+    def rope_kv(self, qkv, q_out, kcache, vcache, *, batch, s, hq, hkv, d, smax, pos0, theta, row_pads=None):
         self.launches += 1
         if qkv.dtype == F32 and qkv.dim() == 3:
             qkv = qkv.sum(0)
         t = qkv.float().view(batch, s, hq + 2 * hkv, d)
-        pos = torch.arange(pos0, pos0 + s).float() + 1.0
+        slot = torch.arange(pos0, pos0 + s)[None, :].expand(batch, s)
+        if row_pads is None:
+            pos = slot.float() + 1.0
+        else:       # left-padded rows: positions restart at 1 on the first real token, padding slots sit at 2
+            pads = row_pads.long()[:, None]
+            pos = torch.where(slot < pads, torch.full_like(slot, 2), slot - pads + 1).float()
         inv = 1.0 / (theta ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))
-        fr = pos[:, None] * inv[None]
-        cos, sin = torch.cat([fr, fr], -1).cos()[None, :, None], torch.cat([fr, fr], -1).sin()[None, :, None]
+        fr = pos[..., None] * inv
+        cos, sin = torch.cat([fr, fr], -1).cos()[:, :, None], torch.cat([fr, fr], -1).sin()[:, :, None]
         qk = t[:, :, : hq + hkv]
         x1, x2 = qk[..., : d // 2], qk[..., d // 2:]
         rot = qk * cos + torch.cat([-x2, x1], -1) * sin

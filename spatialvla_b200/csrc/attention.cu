@@ -70,6 +70,7 @@ struct AttnP {
   int causal;
   const float* relpos;
   int head_major;
+  const int* kv_start;
   int win;
 };
 
@@ -199,7 +200,8 @@ svla_flash_attn_kernel(const AttnP p) {
     // The score path, not the MMAs, bounds this kernel (ncu: 32 instructions per score element in the first
     // version), so every feature is folded into as few per-element operations as possible and the special cases
     // (CLS row/column of BEiT, ragged/causal mask, large soft-cap arguments) are warp-uniform branches.
-    const bool need_mask = f_causal || (jt + 1) * kBKV > p.sk;
+    const int kstart = p.kv_start ? p.kv_start[b] : 0;
+    const bool need_mask = f_causal || (jt + 1) * kBKV > p.sk || kstart > jt * kBKV;
     float mx[2] = {-INFINITY, -INFINITY};
     if (f_relpos) {
       const bool has_cls = (jt == 0) || (q0 + warp * 16 == 0);      // only then a CLS key / query is in this block
@@ -261,7 +263,7 @@ svla_flash_attn_kernel(const AttnP p) {
         for (int e = 0; e < 4; ++e) {
           const int qi = qi0 + (e >> 1) * 8;
           const int kj = jt * kBKV + nt * 8 + 2 * t + (e & 1);
-          const bool masked = (kj >= p.sk) || (f_causal && kj > qi + causal_off);
+          const bool masked = (kj >= p.sk) || (kj < kstart) || (f_causal && kj > qi + causal_off);
           s[nt][e] = masked ? -INFINITY : s[nt][e];
         }
       }
@@ -376,7 +378,7 @@ template <int D>
 __global__ void __launch_bounds__(kDecThreads)
 svla_decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
                         const __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out, int hq, int hkv, int smax,
-                        int ctx, float scale, float softcap) {
+                        int ctx, float scale, float softcap, const int* __restrict__ kv_start) {
   constexpr int PER = D / 32;
   constexpr int KB = 4;
   constexpr int NW = kDecThreads / 32;
@@ -409,6 +411,7 @@ svla_decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16
     for (int e = 0; e < PER; ++e) acc[gi][e] = 0.f;
   }
   const float inv_cap = softcap > 0.f ? 1.f / softcap : 0.f;
+  const int kstart = kv_start ? kv_start[b] : 0;              // left-padded prompt: keys [0, kstart) are masked
   for (int j0 = warp * KB; j0 < ctx; j0 += NW * KB) {
     uint4 kr[KB], vr[KB];
 #pragma unroll
@@ -419,7 +422,7 @@ svla_decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16
     }
 #pragma unroll
     for (int u = 0; u < KB; ++u) {
-      const bool ok = j0 + u < ctx;           // warp-uniform
+      const bool ok = j0 + u < ctx && j0 + u >= kstart;           // warp-uniform
       float kv[PER], vv[PER];
       unpack8(kr[u], kv);
       unpack8(vr[u], vv);
@@ -488,7 +491,8 @@ template <int GRP>
 __global__ void __launch_bounds__(kDecThreads, 2)
 svla_decode_attn_fused_kernel(const float* __restrict__ qkv_f32, int n_partials, long long partial_stride,
                               __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out,
-                              int hq, int hkv, int smax, int ctx, float theta, float scale, float softcap) {
+                              int hq, int hkv, int smax, int ctx, float theta, float scale, float softcap,
+                              const int* __restrict__ kv_start) {
   constexpr int D = 256;
   constexpr int TPP = 8 / GRP;            // threads per (key, head) pair
   constexpr int PPT = 32 / TPP;           // 16-byte pieces of a K row per thread
@@ -503,6 +507,7 @@ svla_decode_attn_fused_kernel(const float* __restrict__ qkv_f32, int n_partials,
   const int ctx_pad = (ctx + 31) & ~31;
   const int b = blockIdx.y, hk = blockIdx.x, t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
+  const int kstart = kv_start ? kv_start[b] : 0;              // immutable input (not written by the PDL predecessor)
   const int n_old = ctx - 1;                                  // cached keys; the new token sits at slot ctx - 1
   const int n_chunks = (n_old + kFusedRows - 1) / kFusedRows;
   const int n_tiles = 2 * n_chunks;
@@ -549,7 +554,7 @@ svla_decode_attn_fused_kernel(const float* __restrict__ qkv_f32, int n_partials,
       const int j = t;
       const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * j) / static_cast<float>(D));
       float sn, cs;
-      sincosf(static_cast<float>(ctx) * inv_freq, &sn, &cs);
+      sincosf(static_cast<float>(ctx - kstart) * inv_freq, &sn, &cs);      // position of the new token: ctx - leading pads
 #pragma unroll
       for (int g = 0; g <= GRP; ++g) {
         const long long col = (g < GRP) ? static_cast<long long>(hk * GRP + g) * D : static_cast<long long>(hq + hk) * D;
@@ -607,7 +612,7 @@ svla_decode_attn_fused_kernel(const float* __restrict__ qkv_f32, int n_partials,
     if (part == 0 && key < n_old) {
       float sc = dot * scale;
       if (softcap > 0.f) sc = softcap * tanh_small(sc * inv_cap);
-      s_p[g_k * ctx_pad + key] = sc;
+      s_p[g_k * ctx_pad + key] = key < kstart ? -INFINITY : sc;       // padded prompt slots never receive weight
     }
   }
   __syncthreads();
@@ -710,7 +715,7 @@ extern "C" int svla_attention(const SvlaAttnArgs* a, void* stream) {
   p.q_bs = a->q_bs; p.q_ss = a->q_ss; p.k_bs = a->k_bs; p.k_ss = a->k_ss; p.v_bs = a->v_bs; p.v_ss = a->v_ss;
   p.o_bs = a->o_bs; p.o_ss = a->o_ss;
   p.hq = a->hq; p.hkv = a->hkv; p.sq = a->sq; p.sk = a->sk; p.d = a->d;
-  p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.relpos = a->relpos_table; p.win = a->relpos_win; p.head_major = a->relpos_head_major;
+  p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.relpos = a->relpos_table; p.win = a->relpos_win; p.head_major = a->relpos_head_major; p.kv_start = a->kv_start;
   const int mode = (p.relpos ? 1 : 0) | (p.softcap > 0.f ? 2 : 0) | (p.causal ? 4 : 0);
   if (a->d <= 32) return launch_attn<32, 8>(p, a->batch, st);
   if (a->d <= 64) return mode == 1 ? launch_attn<64, 1>(p, a->batch, st) : launch_attn<64, 8>(p, a->batch, st);
@@ -720,7 +725,8 @@ extern "C" int svla_attention(const SvlaAttnArgs* a, void* stream) {
 }
 
 extern "C" int svla_decode_attention(const void* q, const void* kcache, const void* vcache, void* out, int batch, int hq,
-                                     int hkv, int d, int smax, int ctx, float scale, float softcap, void* stream) {
+                                     int hkv, int d, int smax, int ctx, float scale, float softcap, const int32_t* kv_start,
+                                     void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SVLA_REQUIRE(q && kcache && vcache && out, "svla_decode_attention: null pointer");
   SVLA_REQUIRE(d == 256, "svla_decode_attention: head dim %d unsupported (256 only)", d);
@@ -737,7 +743,7 @@ extern "C" int svla_decode_attention(const void* q, const void* kcache, const vo
   dim3 grid(hkv, batch);
   svla_decode_attn_kernel<256><<<grid, kDecThreads, smem, st>>>(
       static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(kcache),
-      static_cast<const __nv_bfloat16*>(vcache), static_cast<__nv_bfloat16*>(out), hq, hkv, smax, ctx, scale, softcap);
+      static_cast<const __nv_bfloat16*>(vcache), static_cast<__nv_bfloat16*>(out), hq, hkv, smax, ctx, scale, softcap, kv_start);
   SVLA_LAUNCH_CHECK("svla_decode_attn");
   return 0;
 }
@@ -745,7 +751,7 @@ extern "C" int svla_decode_attention(const void* q, const void* kcache, const vo
 // Decode step of one layer after the qkv projection: RoPE + cache append + attention in one launch (see the kernel).
 extern "C" int svla_decode_attention_fused(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache, void* vcache,
                                            void* out, int batch, int hq, int hkv, int d, int smax, int ctx, float theta,
-                                           float scale, float softcap, void* stream) {
+                                           float scale, float softcap, const int32_t* kv_start, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SVLA_REQUIRE(qkv_f32 && kcache && vcache && out, "svla_decode_attention_fused: null pointer");
   SVLA_REQUIRE(d == 256, "svla_decode_attention_fused: head dim %d unsupported (256 only)", d);
@@ -768,9 +774,9 @@ extern "C" int svla_decode_attention_fused(const float* qkv_f32, int n_partials,
   auto* op = static_cast<__nv_bfloat16*>(out);
   const long long ps = partial_stride;
   cudaError_t le = grp == 1 ? svla_launch_pdl(svla_decode_attn_fused_kernel<1>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
-                                              hq, hkv, smax, ctx, theta, scale, softcap)
+                                              hq, hkv, smax, ctx, theta, scale, softcap, kv_start)
                             : svla_launch_pdl(svla_decode_attn_fused_kernel<2>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
-                                              hq, hkv, smax, ctx, theta, scale, softcap);
+                                              hq, hkv, smax, ctx, theta, scale, softcap, kv_start);
   SVLA_REQUIRE(le == cudaSuccess, "svla_decode_attention_fused: launch failed: %s", cudaGetErrorString(le));
   SVLA_LAUNCH_CHECK("svla_decode_attn_fused");
   return 0;

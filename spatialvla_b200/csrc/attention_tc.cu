@@ -43,6 +43,7 @@ struct Params {
   const float* relpos;
   int win;
   int head_major;      // relpos is [hq][nrel] (coalesced per-head row) instead of HF's [nrel][hq]
+  const int* kv_start; // [batch] or null: keys < kv_start[b] are masked (left-padded prompts)
 };
 
 template <int D> struct Cfg {
@@ -247,6 +248,7 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     }
     const float sl2 = p.scale * kLog2e;
     const float c1 = kSoftcap ? p.scale / p.softcap : 0.f, c2 = kSoftcap ? p.softcap * kLog2e : 0.f;
+    const int kstart = p.kv_start ? p.kv_start[b] : 0;
     if (kRelpos) {
       // this head's bias table (x log2 e) and the per-key index terms, loaded by the softmax warps only: the TMA producer and
       // the MMA issuer are already running (ncu on the first version: the strided table gather + CTA-wide barrier in front of
@@ -330,11 +332,11 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
 #pragma unroll
         for (int i = 0; i < HC; ++i) s[i] *= sl2;
       }
-      if (kCausal || k0 + HC > p.sk) {
+      if (kCausal || k0 + HC > p.sk || kstart > k0) {
 #pragma unroll
         for (int i = 0; i < HC; ++i) {
           const int kj = k0 + i;
-          if (kj >= p.sk || (kCausal && kj > qi + causal_off)) s[i] = -INFINITY;
+          if (kj >= p.sk || kj < kstart || (kCausal && kj > qi + causal_off)) s[i] = -INFINITY;
         }
       }
       float mj = -INFINITY;
@@ -484,7 +486,7 @@ int svla_attention_tc_try(const SvlaAttnArgs* a, void* stream) {
   p.out = static_cast<__nv_bfloat16*>(a->out);
   p.o_bs = a->o_bs; p.o_ss = a->o_ss;
   p.hq = a->hq; p.hkv = a->hkv; p.sq = a->sq; p.sk = a->sk; p.d = a->d;
-  p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.relpos = a->relpos_table; p.win = a->relpos_win; p.head_major = a->relpos_head_major;
+  p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.relpos = a->relpos_table; p.win = a->relpos_win; p.head_major = a->relpos_head_major; p.kv_start = a->kv_start;
   // a batch stride of 0 is not expressible in a tensor map; batch == 1 problems get a dummy stride
   const uint64_t nb = static_cast<uint64_t>(a->batch);
   auto bstride = [&](int64_t bs, int64_t ss, int s) { return static_cast<uint64_t>(nb > 1 ? bs : ss * s); };

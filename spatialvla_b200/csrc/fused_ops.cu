@@ -1,6 +1,7 @@
 // Memory-bound fused kernels of the predict_action path (M1-M7, M9, ZoeDepth metric-bins tail, Ego3D).
 // All of them stream each operand once with 128-bit accesses where the layout allows, keep statistics in
 // fp32 and use warp-shuffle reductions.  Reference lines replaced: see include/spatialvla_b200.h.
+#include <cstdlib>
 #include "svla_common.cuh"
 
 namespace {
@@ -253,11 +254,13 @@ svla_rmsnorm_residual_warp_kernel(float* __restrict__ x, const float* __restrict
 __global__ void svla_rope_kv_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ q_out,
                                     __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc, int s, int hq, int hkv, int d,
                                     int smax, int pos0, float theta, const float* __restrict__ qkv_f32, int n_partials,
-                                    long long partial_stride) {
+                                    long long partial_stride, const int* __restrict__ row_pads) {
   const long long tok = blockIdx.x;
   const int b = static_cast<int>(tok / s), si = static_cast<int>(tok % s);
   const int pos = pos0 + si;                       // cache slot
-  const float fpos = static_cast<float>(pos + 1);  // PaliGemma positions are 1-indexed
+  // PaliGemma positions are 1-indexed; in a left-padded batch they restart on the row's first real token (padding slots: 2)
+  const int pad = row_pads ? row_pads[b] : 0;
+  const float fpos = static_cast<float>(pos < pad ? 2 : pos - pad + 1);
   const int half = d >> 1;
   const long long width = static_cast<long long>(hq + 2 * hkv) * d;
   const __nv_bfloat16* src = qkv + tok * width;
@@ -303,12 +306,14 @@ __global__ void svla_rope_kv_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_
 // 16-byte accesses.
 __global__ void __launch_bounds__(128)
 svla_rope_kv_vec_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ kc,
-                        __nv_bfloat16* __restrict__ vc, int s, int hq, int hkv, int d, int smax, int pos0, float theta) {
+                        __nv_bfloat16* __restrict__ vc, int s, int hq, int hkv, int d, int smax, int pos0, float theta,
+                        const int* __restrict__ row_pads) {
   __shared__ __align__(16) float s_cs[128], s_sn[128];      // d <= 256
   const long long tok = blockIdx.x;
   const int b = static_cast<int>(tok / s), si = static_cast<int>(tok % s);
   const int pos = pos0 + si;
-  const float fpos = static_cast<float>(pos + 1);
+  const int pad = row_pads ? row_pads[b] : 0;
+  const float fpos = static_cast<float>(pos < pad ? 2 : pos - pad + 1);
   const int half = d >> 1;
   const int tph = half >> 3;                       // threads per head
   const long long width = static_cast<long long>(hq + 2 * hkv) * d;
@@ -577,6 +582,73 @@ svla_bilinear_nhwc_kernel(const uint4* __restrict__ x, const uint4* __restrict__
   if (out_relu)
     out_relu[idx] = make_uint4(pack_bf16x2(fmaxf(o[0], 0.f), fmaxf(o[1], 0.f)), pack_bf16x2(fmaxf(o[2], 0.f), fmaxf(o[3], 0.f)),
                                pack_bf16x2(fmaxf(o[4], 0.f), fmaxf(o[5], 0.f)), pack_bf16x2(fmaxf(o[6], 0.f), fmaxf(o[7], 0.f)));
+}
+
+// Tiled bilinear (align_corners=True) for the x2 up-samplings of the DPT neck / relative head / bin embeddings.  ncu on the
+// per-pixel kernel above: 33 thread-instructions per output element, issue-bound at 37 % of HBM.  Here a block produces
+// 8 output rows x 32 output columns x 64 channels in two passes: (1) the <= floor(7 ry) + 3 source rows it needs are
+// interpolated horizontally ONCE into shared memory (fp32), (2) every output is one vertical lerp of two shared-memory
+// rows.  Same association as the reference: (1-ly) * ((1-lx) v00 + lx v01) + ly * ((1-lx) v10 + lx v11).
+constexpr int kBlRows = 8, kBlCols = 32, kBlGroups = 8;     // output rows, output columns, 8-channel groups per block
+__global__ void __launch_bounds__(256)
+svla_bilinear_tile_kernel(const uint4* __restrict__ x, const uint4* __restrict__ add, uint4* __restrict__ out,
+                          uint4* __restrict__ out_relu, int h, int w, int c8, int oh, int ow, int nrows, int cgroups) {
+  extern __shared__ __align__(16) float4 s_bl[];
+  float4* s_lo = s_bl;                                            // [nrows][32][8] channels 0-3 of the group
+  float4* s_hi = s_bl + nrows * kBlCols * kBlGroups;              //                 channels 4-7
+  const int ox0 = blockIdx.x * kBlCols, oy0 = blockIdx.y * kBlRows;
+  const int cgb = (blockIdx.z % cgroups) * kBlGroups;
+  const long long b = blockIdx.z / cgroups;
+  const float ry = (oh > 1) ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) : 0.f;
+  const float rx = (ow > 1) ? static_cast<float>(w - 1) / static_cast<float>(ow - 1) : 0.f;
+  const int ybase = min(static_cast<int>(ry * oy0), h - 1);
+  // ---- pass 1: horizontal interpolation of the source rows [ybase, ybase + nrows)
+  for (int item = threadIdx.x; item < nrows * kBlCols * kBlGroups; item += 256) {
+    const int cg = item & 7, col = (item >> 3) & 31, r = item >> 8;
+    const int ox = ox0 + col, y = ybase + r, c = cgb + cg;
+    if (ox < ow && y < h && c < c8) {
+      const float sx = rx * ox;
+      const int x0 = min(static_cast<int>(sx), w - 1), x1 = min(x0 + 1, w - 1);
+      const float lx = sx - x0;
+      const uint4* rowp = x + (b * h + y) * static_cast<long long>(w) * c8 + c;
+      float f0[8], f1[8];
+      unpack8(rowp[static_cast<long long>(x0) * c8], f0);
+      unpack8(rowp[static_cast<long long>(x1) * c8], f1);
+      float hv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) hv[e] = (1.f - lx) * f0[e] + lx * f1[e];
+      s_lo[item] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      s_hi[item] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+    }
+  }
+  __syncthreads();
+  // ---- pass 2: vertical interpolation, optional add, bf16 (and ReLU copy) stores
+  for (int item = threadIdx.x; item < kBlRows * kBlCols * kBlGroups; item += 256) {
+    const int cg = item & 7, col = (item >> 3) & 31, rr = item >> 8;
+    const int ox = ox0 + col, oy = oy0 + rr, c = cgb + cg;
+    if (ox >= ow || oy >= oh || c >= c8) continue;
+    const float sy = ry * oy;
+    const int y0 = min(static_cast<int>(sy), h - 1), y1 = min(y0 + 1, h - 1);
+    const float ly = sy - y0;
+    const int i0 = ((y0 - ybase) * kBlCols + col) * kBlGroups + cg, i1 = ((y1 - ybase) * kBlCols + col) * kBlGroups + cg;
+    const float4 a0 = s_lo[i0], a1 = s_hi[i0], b0 = s_lo[i1], b1 = s_hi[i1];
+    float o[8];
+    o[0] = (1.f - ly) * a0.x + ly * b0.x; o[1] = (1.f - ly) * a0.y + ly * b0.y;
+    o[2] = (1.f - ly) * a0.z + ly * b0.z; o[3] = (1.f - ly) * a0.w + ly * b0.w;
+    o[4] = (1.f - ly) * a1.x + ly * b1.x; o[5] = (1.f - ly) * a1.y + ly * b1.y;
+    o[6] = (1.f - ly) * a1.z + ly * b1.z; o[7] = (1.f - ly) * a1.w + ly * b1.w;
+    const long long idx = ((b * oh + oy) * static_cast<long long>(ow) + ox) * c8 + c;
+    if (add) {
+      float ad[8];
+      unpack8(add[idx], ad);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] += ad[e];
+    }
+    if (out) out[idx] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    if (out_relu)
+      out_relu[idx] = make_uint4(pack_bf16x2(fmaxf(o[0], 0.f), fmaxf(o[1], 0.f)), pack_bf16x2(fmaxf(o[2], 0.f), fmaxf(o[3], 0.f)),
+                                 pack_bf16x2(fmaxf(o[4], 0.f), fmaxf(o[5], 0.f)), pack_bf16x2(fmaxf(o[6], 0.f), fmaxf(o[7], 0.f)));
+  }
 }
 
 __global__ void svla_relu_bf16_kernel(const __nv_bfloat162* __restrict__ x, __nv_bfloat162* __restrict__ out, long long n2) {
@@ -900,21 +972,22 @@ extern "C" int svla_rmsnorm_residual(float* x, const float* branch, const float*
 
 extern "C" int svla_rope_kv(const void* qkv, void* q_out, void* kcache, void* vcache, int batch, int s, int hq, int hkv, int d,
                             int smax, int pos0, float theta, const float* qkv_f32, int n_partials, int64_t partial_stride,
-                            void* stream) {
+                            const int32_t* row_pads, void* stream) {
   SVLA_REQUIRE((qkv || qkv_f32) && q_out && kcache && vcache, "svla_rope_kv: null pointer");
   SVLA_REQUIRE(batch > 0 && s > 0 && (d % 2) == 0 && pos0 >= 0 && pos0 + s <= smax, "svla_rope_kv: bad geometry (pos0=%d s=%d smax=%d)", pos0, s, smax);
   SVLA_REQUIRE(d / 2 <= 512, "svla_rope_kv: head dim too large");
   if (qkv_f32 == nullptr && (d % 16) == 0 && d <= 256 && 128 % (d / 16) == 0 && batch * s > 1024) {
     svla_rope_kv_vec_kernel<<<static_cast<unsigned>(batch) * s, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(q_out), static_cast<__nv_bfloat16*>(kcache),
-        static_cast<__nv_bfloat16*>(vcache), s, hq, hkv, d, smax, pos0, theta);
+        static_cast<__nv_bfloat16*>(vcache), s, hq, hkv, d, smax, pos0, theta, row_pads);
     SVLA_LAUNCH_CHECK("svla_rope_kv_vec");
     return 0;
   }
   const int rope_threads = (d / 2) * ((batch * s <= 1024) ? max(1, 512 / (d / 2)) : 1);     // decode: spread heads over lanes
   svla_rope_kv_kernel<<<static_cast<unsigned>(batch) * s, rope_threads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(q_out), static_cast<__nv_bfloat16*>(kcache),
-      static_cast<__nv_bfloat16*>(vcache), s, hq, hkv, d, smax, pos0, theta, qkv_f32, n_partials < 1 ? 1 : n_partials, partial_stride);
+      static_cast<__nv_bfloat16*>(vcache), s, hq, hkv, d, smax, pos0, theta, qkv_f32, n_partials < 1 ? 1 : n_partials, partial_stride,
+      row_pads);
   SVLA_LAUNCH_CHECK("svla_rope_kv");
   return 0;
 }
@@ -998,6 +1071,26 @@ extern "C" int svla_bilinear_nhwc(const void* x, const void* add, void* out, voi
                                   int oh, int ow, void* stream) {
   SVLA_REQUIRE(x && (out || out_relu) && batch > 0 && (c % 8) == 0, "svla_bilinear_nhwc: bad arguments");
   SVLA_REQUIRE(oh <= 65535 && batch <= 65535 && static_cast<long long>(ow) * (c / 8) < (1LL << 31), "svla_bilinear_nhwc: grid too large");
+  // tiled two-pass kernel for up-sampling ratios <= ~1.2 (every use on this path is x2); the per-pixel kernel covers the rest
+  const float ry = (oh > 1) ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) : 0.f;
+  const int nrows = static_cast<int>(floorf(7.f * ry)) + 3;
+  const int c8 = c / 8, cgroups = (c8 + kBlGroups - 1) / kBlGroups;
+  static const bool legacy_bilinear = getenv("SVLA_BILINEAR_LEGACY") != nullptr;
+  if (!legacy_bilinear && nrows <= 12 && static_cast<long long>(batch) * cgroups <= 65535) {
+    const size_t smem = static_cast<size_t>(nrows) * kBlCols * kBlGroups * 2 * sizeof(float4);
+    static size_t configured = 0;
+    if (smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(svla_bilinear_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      SVLA_REQUIRE(e == cudaSuccess, "svla_bilinear_nhwc: smem opt-in %zu failed: %s", smem, cudaGetErrorString(e));
+      configured = smem;
+    }
+    dim3 tgrid((ow + kBlCols - 1) / kBlCols, (oh + kBlRows - 1) / kBlRows, batch * cgroups);
+    svla_bilinear_tile_kernel<<<tgrid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), static_cast<const uint4*>(add), static_cast<uint4*>(out), static_cast<uint4*>(out_relu), h, w,
+        c8, oh, ow, nrows, cgroups);
+    SVLA_LAUNCH_CHECK("svla_bilinear_tile");
+    return 0;
+  }
   dim3 grid(blocks_for(static_cast<long long>(ow) * (c / 8), 256), oh, batch);
   svla_bilinear_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), static_cast<const uint4*>(add), static_cast<uint4*>(out), static_cast<uint4*>(out_relu), h, w,

@@ -506,8 +506,11 @@ class SpatialVLAEngine:
         return {"k": self.ops.zeros((L_, B, smax, hkv, hd), BF16), "v": self.ops.zeros((L_, B, smax, hkv, hd), BF16),
                 "smax": smax, "len": 0}
 
-    def gemma_forward(self, x, B, S, cache, bidirectional):
-        """x fp32 [B*S, H] (already scaled by sqrt(H)) -> final-normed hidden bf16 [B*S, H]; appends to the cache."""
+    def gemma_forward(self, x, B, S, cache, bidirectional, pads=None):
+        """x fp32 [B*S, H] (already scaled by sqrt(H)) -> final-normed hidden bf16 [B*S, H]; appends to the cache.
+        pads: int32 [B] device tensor or None -- leading padding tokens per row of a left-padded batch: those cache slots are
+        masked as keys and the RoPE positions restart at 1 on each row's first real token (model/modeling_spatialvla.py:298-303,
+        model/modeling_gemma2.py:1042-1051)."""
         ops, g, t = self.ops, self.gem, self.t
         H, nh, nkv, hd, FF = t["hidden_size"], t["num_attention_heads"], t["num_key_value_heads"], t["head_dim"], t["intermediate_size"]
         eps, theta = t["rms_norm_eps"], float(t.get("rope_theta", 10000.0))
@@ -528,7 +531,7 @@ class SpatialVLAEngine:
             if skinny and hd == 256 and nh // nkv in (1, 2):
                 # decode: RoPE + cache append + attention over the cache in one launch
                 ops.decode_attention_fused(qkv, kc, vc, ctx, batch=B, hq=nh, hkv=nkv, d=hd, smax=smax, ctx=pos0 + 1, theta=theta,
-                                           scale=scale, softcap=cap)
+                                           scale=scale, softcap=cap, kv_start=pads)
                 br = self._skinny_partial(ctx, L_["wo"], M)
                 ops.rmsnorm_residual(x, branch=br, w_post=L_["ln_post_attn"], w_pre=L_["ln_pre_ff"], eps=eps, out_bf16=h)
                 act = ops.empty((M, FF), BF16)
@@ -537,14 +540,15 @@ class SpatialVLAEngine:
                 nxt = g["layers"][li + 1]["ln_in"] if li + 1 < len(g["layers"]) else g["final"]
                 ops.rmsnorm_residual(x, branch=br, w_post=L_["ln_post_ff"], w_pre=nxt, eps=eps, out_bf16=h)
                 continue
-            ops.rope_kv(qkv, q, kc, vc, batch=B, s=S, hq=nh, hkv=nkv, d=hd, smax=smax, pos0=pos0, theta=theta)
+            ops.rope_kv(qkv, q, kc, vc, batch=B, s=S, hq=nh, hkv=nkv, d=hd, smax=smax, pos0=pos0, theta=theta, row_pads=pads)
             if S == 1:
-                ops.decode_attention(q, kc, vc, ctx, batch=B, hq=nh, hkv=nkv, d=hd, smax=smax, ctx=pos0 + 1, scale=scale, softcap=cap)
+                ops.decode_attention(q, kc, vc, ctx, batch=B, hq=nh, hkv=nkv, d=hd, smax=smax, ctx=pos0 + 1, scale=scale, softcap=cap,
+                                     kv_start=pads)
             else:
                 kvs = (smax * nkv * hd, nkv * hd)
                 ops.attention(q, kc, vc, ctx, batch=B, hq=nh, hkv=nkv, sq=S, sk=pos0 + S, d=hd, q_strides=(S * nh * hd, nh * hd),
                               k_strides=kvs, v_strides=kvs, o_strides=(S * nh * hd, nh * hd), scale=scale, softcap=cap,
-                              causal=not bidirectional)
+                              causal=not bidirectional, kv_start=pads)
             br = self._skinny_partial(ctx, L_["wo"], M) if skinny else self._lin(ctx, L_["wo"], M, F32)
             ops.rmsnorm_residual(x, branch=br, w_post=L_["ln_post_attn"], w_pre=L_["ln_pre_ff"], eps=eps, out_bf16=h)
             if skinny:
@@ -581,14 +585,14 @@ class SpatialVLAEngine:
             self.ops.gemm(h_rows, self.gem["head_act"], out_f32=lg, act=ACT_SOFTCAP if cap else ACT_NONE, act_param=cap or 0.0)
         return lg
 
-    def language_stage(self, ids, feats, n_new, forced_tokens=None, logs=None):
+    def language_stage(self, ids, feats, n_new, forced_tokens=None, logs=None, pads=None):
         """Embed + bidirectional prefill + n_new greedy action tokens (argmax over the action slice) -> int64 [B, n_new]"""
         ops = self.ops
         B, P = ids.shape
         H = self.t["hidden_size"]
         x, status = self.embed(ids, feats)
         cache = self.new_cache(B, P + n_new)
-        h = self.gemma_forward(x, B, P, cache, bidirectional=True)
+        h = self.gemma_forward(x, B, P, cache, bidirectional=True, pads=pads)
         toks = ops.zeros((B, n_new), torch.int64)
         rows = h.view(B, P * H)[:, (P - 1) * H:]
         for step in range(n_new):
@@ -600,21 +604,21 @@ class SpatialVLAEngine:
                 break
             feed = toks[:, step:step + 1] if forced_tokens is None else forced_tokens[:, step:step + 1]
             x, _ = self.embed(feed.contiguous())
-            rows = self.gemma_forward(x, B, 1, cache, bidirectional=False)
+            rows = self.gemma_forward(x, B, 1, cache, bidirectional=False, pads=pads)
         self.last_status = status
         return toks
 
-    def generate_actions(self, ids, px, intrinsic, n_new, forced_tokens=None, return_logits=False):
+    def generate_actions(self, ids, px, intrinsic, n_new, forced_tokens=None, return_logits=False, pads=None):
         """Greedy decode of n_new action tokens (argmax restricted to the action slice). ids int64 [B,P] on device.
         Returns tokens int64 [B, n_new] (+ fp32 logits [B, n_new, n_act]).  On a CUDA device the whole step is
         replayed from two CUDA graphs (before / after the ZoeDepth router's host read) unless logits or teacher
         forcing are requested."""
         if (self.use_graphs and px is not None and forced_tokens is None and not return_logits
                 and getattr(self.ops, "name", "") == "cuda"):
-            return self._generate_graphed(ids, px, intrinsic, n_new)
+            return self._generate_graphed(ids, px, intrinsic, n_new, pads)
         feats = self.image_features(px, intrinsic) if px is not None else None
         logs = [] if return_logits else None
-        toks = self.language_stage(ids, feats, n_new, forced_tokens, logs)
+        toks = self.language_stage(ids, feats, n_new, forced_tokens, logs, pads=pads)
         if return_logits:
             return toks, torch.stack(logs, 1)
         return toks
@@ -622,23 +626,24 @@ class SpatialVLAEngine:
     # ------------------------------------------------------------------------------------------ CUDA graphs
     use_graphs = os.environ.get("SVLA_NO_GRAPHS", "0") != "1"
 
-    def _generate_graphed(self, ids, px, intrinsic, n_new):
+    def _generate_graphed(self, ids, px, intrinsic, n_new, pads=None):
         """Static-shape replay: graph A = vision stage A (ends with the router logits); one D2H read picks the metric
         head; graph B[head] = metric-bins tail + Ego3D + projector + Gemma2 prefill + decode loop.  Kernel arguments
         (TMA descriptors included) are baked at capture; inputs are copied into static buffers before each replay."""
         B, P = ids.shape
         Kdim = intrinsic.dim()
-        key = (B, P, n_new, Kdim)
+        key = (B, P, n_new, Kdim, pads is not None)
         if not hasattr(self, "_graphs"):
             self._graphs = {}
         g = self._graphs.get(key)
         px = px.to(device=self.dev, dtype=F32)
         K = intrinsic.to(device=self.dev, dtype=F32)
         if g is None:
-            g = {"ids": ids.clone(), "px": px.clone().contiguous(), "K": K.clone().contiguous(), "B": {}, "launches_b": {}}
+            g = {"ids": ids.clone(), "px": px.clone().contiguous(), "K": K.clone().contiguous(), "B": {}, "launches_b": {},
+                 "pads": None if pads is None else pads.clone()}
             # warm-up outside capture (cudaFuncSetAttribute, lazy module load), then capture stage A
             feats = self.image_features(g["px"], g["K"])
-            self.language_stage(g["ids"], feats, n_new)
+            self.language_stage(g["ids"], feats, n_new, pads=g["pads"])
             torch.cuda.synchronize()
             n0 = self.ops.launch_count()
             ga = torch.cuda.CUDAGraph()
@@ -649,6 +654,8 @@ class SpatialVLAEngine:
         g["ids"].copy_(ids)
         g["px"].copy_(px)
         g["K"].copy_(K)
+        if pads is not None:
+            g["pads"].copy_(pads)
         g["A"].replay()
         head = self.pick_head(g["st"]["dlog"]) if self.use_zoe else 0
         if head not in g["B"]:
@@ -656,7 +663,7 @@ class SpatialVLAEngine:
             gb = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gb):
                 feats = self.vision_stage_b(g["st"], head, g["K"], B)
-                toks = self.language_stage(g["ids"], feats, n_new)
+                toks = self.language_stage(g["ids"], feats, n_new, pads=g["pads"])
             g["B"][head] = (gb, toks)
             g["launches_b"][head] = self.ops.launch_count() - n0
         gb, toks = g["B"][head]

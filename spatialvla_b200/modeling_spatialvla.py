@@ -8,8 +8,9 @@ Differences from the reference, all deliberate and documented in DESIGN.md:
     argmax restricted to the spatial-action slice of the vocabulary instead of HF `generate(max_new_tokens=256)` +
     EOS stop (north_star: "argmax restricted to the action vocabulary"); `max_new_tokens` can be passed.
   * inputs stay fp32 (the reference rounds pixel_values *and* the intrinsic matrix to bf16 at :489).
-  * padded batches (attention_mask with zeros) and the training-time prefix-LM mask / loss are not part of this
-    path yet and raise NotImplementedError instead of silently mis-computing.
+  * LEFT-padded batches (attention_mask = 0...01...1, the Gemma tokenizer's padding side) are supported with the reference's
+    semantics (padded key columns masked, positions restart on the first real token); any other mask pattern and the
+    training-time prefix-LM mask / loss raise NotImplementedError instead of silently mis-computing.
 """
 from __future__ import annotations
 
@@ -97,8 +98,9 @@ class SpatialVLAForConditionalGeneration:
         px = model_inputs.get("pixel_values") if hasattr(model_inputs, "get") else model_inputs["pixel_values"]
         K = model_inputs.get("intrinsic") if hasattr(model_inputs, "get") else model_inputs["intrinsic"]
         am = model_inputs.get("attention_mask") if hasattr(model_inputs, "get") else None
+        pads = None
         if am is not None and am.dim() == 2 and bool((am == 0).any()):
-            raise NotImplementedError("padded batches (attention_mask with zeros) are not supported on this path yet")
+            pads = self._left_pads(am, ids.shape[1])
         ids = ids.to(self.device, torch.int64).contiguous()
         if px is not None:
             px = px.to(self.device, F32).contiguous()
@@ -109,15 +111,26 @@ class SpatialVLAForConditionalGeneration:
                     f"Got {n_img * ids.shape[0]} image tokens in the text but {px.shape[0] * 256} tokens from image embeddings.")
         if K is not None:
             K = K.to(self.device, F32).contiguous()
-        return ids, px, K
+        return ids, px, K, pads
+
+    def _left_pads(self, attention_mask, P):
+        """(B,P) 0/1 mask with zeros -> int32 [B] device tensor of leading pad counts.  Only left padding is supported: every
+        row must be zeros followed by ones with at least one real token (model/modeling_spatialvla.py:298-303 masks the padded
+        key columns; HF generate restarts the position ids on the first real token, model/modeling_gemma2.py:1042-1051)."""
+        am = attention_mask.to(torch.int64)
+        pads = (am == 0).sum(1)
+        expect = (torch.arange(P, device=am.device)[None, :] >= pads[:, None]).to(torch.int64)
+        if am.shape[1] != P or not bool(torch.equal(am, expect)) or int(pads.max()) >= P:
+            raise NotImplementedError("only left-padded batches (attention_mask = 0...01...1) are supported on this path")
+        return pads.to(device=self.device, dtype=torch.int32).contiguous()
 
     @torch.no_grad()
     def predict_action(self, model_inputs, max_new_tokens: Optional[int] = None, return_logits: bool = False):
         """model_inputs: dict-like with input_ids (B,P), pixel_values (B,3,224,224) in [0,1], intrinsic (3,3)|(B,3,3)
         -> LongTensor (B, n_new) of generated action-token ids on the model device (prompt stripped, :492)."""
-        ids, px, K = self._prepare(model_inputs)
+        ids, px, K, pads = self._prepare(model_inputs)
         n_new = int(max_new_tokens) if max_new_tokens is not None else 3 * self.action_chunk_size
-        out = self.engine.generate_actions(ids, px, K, n_new, return_logits=return_logits)
+        out = self.engine.generate_actions(ids, px, K, n_new, return_logits=return_logits, pads=pads)
         return out
 
     @torch.no_grad()
@@ -155,14 +168,17 @@ class SpatialVLAForConditionalGeneration:
         if inputs_embeds is not None or position_ids is not None or output_attentions or output_hidden_states:
             raise NotImplementedError("inputs_embeds / position_ids / output_attentions / output_hidden_states")
         eng = self.engine
-        ids, px, K = self._prepare({"input_ids": input_ids, "pixel_values": pixel_values, "intrinsic": intrinsic,
-                                    "attention_mask": attention_mask if (attention_mask is not None and attention_mask.dim() == 2) else None})
+        ids, px, K, pads = self._prepare({"input_ids": input_ids, "pixel_values": pixel_values, "intrinsic": intrinsic,
+                                          "attention_mask": attention_mask if (attention_mask is not None and attention_mask.dim() == 2
+                                                                               and attention_mask.shape[1] == input_ids.shape[1]) else None})
         B, S = ids.shape
         feats = eng.image_features(px, K) if px is not None else None
         x, status = eng.embed(ids, feats)
         cache = past_key_values if past_key_values is not None else eng.new_cache(B, S + 256)
         prefill = cache["len"] == 0
-        h = eng.gemma_forward(x, B, S, cache, bidirectional=prefill)
+        if prefill:
+            cache["pads"] = pads             # decode calls on this cache keep masking the prompt's padding slots
+        h = eng.gemma_forward(x, B, S, cache, bidirectional=prefill, pads=cache.get("pads"))
         H = h.shape[-1]
         keep = S if num_logits_to_keep in (0, None) else int(num_logits_to_keep)
         rows = h.view(B, S, H)[:, S - keep:].reshape(B * keep, H)

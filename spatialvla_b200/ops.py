@@ -137,7 +137,7 @@ class CudaOps:
 
     # ---- G2 / G3
     def attention(self, q, k, v, out, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
-                  scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0, relpos_head_major=False):
+                  scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0, relpos_head_major=False, kv_start=None):
         """strides = (batch stride, token stride) in elements; head h lives at column offset h*d.
         relpos_table: fp32 [(2*win-1)^2+3, hq] (HF layout) or, with relpos_head_major, its transpose [hq, (2*win-1)^2+3]."""
         a = L.SvlaAttnArgs()
@@ -153,20 +153,24 @@ class CudaOps:
         _req(relpos_table is None or relpos_table.dtype == F32, "attention: relpos table must be fp32")
         _req(relpos_table is None or relpos_table.is_contiguous(), "attention: relpos table must be contiguous")
         a.relpos_table, a.relpos_win, a.relpos_head_major = _ptr(relpos_table), int(relpos_win), int(bool(relpos_head_major))
+        _req(kv_start is None or (kv_start.dtype == torch.int32 and kv_start.is_contiguous() and kv_start.numel() == batch),
+             "attention: kv_start must be int32 [batch]")
+        a.kv_start = _ptr(kv_start)
         L.check(self.lib.svla_attention(C.byref(a), self._stream()), "svla_attention")
 
-    def decode_attention(self, q, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, scale, softcap=0.0):
+    def decode_attention(self, q, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, scale, softcap=0.0, kv_start=None):
         L.check(self.lib.svla_decode_attention(_ptr(q), _ptr(kcache), _ptr(vcache), _ptr(out), batch, hq, hkv, d,
-                                               smax, ctx, float(scale), float(softcap or 0.0), self._stream()),
+                                               smax, ctx, float(scale), float(softcap or 0.0), _ptr(kv_start), self._stream()),
                 "svla_decode_attention")
 
-    def decode_attention_fused(self, qkv_partials, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, theta, scale, softcap=0.0):
+    def decode_attention_fused(self, qkv_partials, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, theta, scale, softcap=0.0,
+                               kv_start=None):
         """RoPE + KV-cache append + attention of one decode step; qkv_partials fp32 [splits, batch, (hq+2hkv)*d]."""
         _req(qkv_partials.dtype == F32 and qkv_partials.dim() == 3 and qkv_partials.stride(2) == 1 and
              qkv_partials.stride(1) == qkv_partials.shape[2], "decode_attention_fused: qkv must be fp32 [splits, batch, W]")
         L.check(self.lib.svla_decode_attention_fused(_ptr(qkv_partials), int(qkv_partials.shape[0]), int(qkv_partials.stride(0)),
                                                      _ptr(kcache), _ptr(vcache), _ptr(out), batch, hq, hkv, d, smax, ctx,
-                                                     float(theta), float(scale), float(softcap or 0.0), self._stream()),
+                                                     float(theta), float(scale), float(softcap or 0.0), _ptr(kv_start), self._stream()),
                 "svla_decode_attention_fused")
 
     # ---- memory-bound fused ops
@@ -186,16 +190,16 @@ class CudaOps:
         L.check(self.lib.svla_rmsnorm_residual(_ptr(x), _ptr(branch), _ptr(w_post), _ptr(w_pre), float(eps), rows,
                                                cols, _ptr(out_bf16), npart, pstride, self._stream()), "svla_rmsnorm_residual")
 
-    def rope_kv(self, qkv, q_out, kcache, vcache, *, batch, s, hq, hkv, d, smax, pos0, theta):
+    def rope_kv(self, qkv, q_out, kcache, vcache, *, batch, s, hq, hkv, d, smax, pos0, theta, row_pads=None):
         """qkv: bf16 [tokens, W] or fp32 split-K partial sums [splits, tokens, W]."""
         if qkv.dtype == F32:
             _req(qkv.dim() == 3, "rope_kv: fp32 qkv must be [splits, tokens, W]")
             L.check(self.lib.svla_rope_kv(None, _ptr(q_out), _ptr(kcache), _ptr(vcache), batch, s, hq, hkv, d, smax, pos0,
-                                          float(theta), _ptr(qkv), int(qkv.shape[0]), int(qkv.stride(0)), self._stream()),
+                                          float(theta), _ptr(qkv), int(qkv.shape[0]), int(qkv.stride(0)), _ptr(row_pads), self._stream()),
                     "svla_rope_kv")
             return
         L.check(self.lib.svla_rope_kv(_ptr(qkv), _ptr(q_out), _ptr(kcache), _ptr(vcache), batch, s, hq, hkv, d, smax,
-                                      pos0, float(theta), None, 1, 0, self._stream()), "svla_rope_kv")
+                                      pos0, float(theta), None, 1, 0, _ptr(row_pads), self._stream()), "svla_rope_kv")
 
     def embed_tokens(self, ids, embed, spatial_embed, image_feats, x, *, image_token, act_lo, n_act, n_img,
                      normalizer, status):

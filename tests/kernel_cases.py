@@ -242,7 +242,7 @@ SKINNY_CASES = [
 
 # ------------------------------------------------------------------------------------------------ attention
 def attn_case(name, B, hq, hkv, sq, sk, d, *, scale=None, softcap=0.0, causal=False, relpos_win=0, packed_qkv=False,
-              smax=None, seed=0, head_major=False):
+              smax=None, seed=0, head_major=False, kv_start=None):
     def case(dev="cuda:0"):
         g = _gen(seed)
         sc = scale if scale is not None else d ** -0.5
@@ -272,7 +272,8 @@ def attn_case(name, B, hq, hkv, sq, sk, d, *, scale=None, softcap=0.0, causal=Fa
                 kvs = (sm * hkv * d, hkv * d)
                 ops.attention(to(q), to(kc), to(vc), out, batch=B, hq=hq, hkv=hkv, sq=sq, sk=sk, d=d,
                               q_strides=(sq * hq * d, hq * d), k_strides=kvs, v_strides=kvs, o_strides=(sq * hq * d, hq * d),
-                              scale=sc, softcap=softcap, causal=causal)
+                              scale=sc, softcap=softcap, causal=causal,
+                              kv_start=None if kv_start is None else to(torch.tensor(kv_start, dtype=torch.int32)))
                 return out
         c, r = _both(run, dev)
         res = Result(name)
@@ -294,6 +295,14 @@ def decode_attn_case(dev="cuda:0"):
     c, r = _both(run, dev)
     res = Result("decode_attention")
     res.add("out", _err(c, r), 1.5e-2)
+
+    def run_padded(ops, to):
+        out = ops.zeros((B, hq * d), BF16)
+        ops.decode_attention(to(q), to(kc), to(vc), out, batch=B, hq=hq, hkv=hkv, d=d, smax=smax, ctx=ctx, scale=1 / 16, softcap=50.0,
+                             kv_start=to(torch.tensor([0, 7, 200], dtype=torch.int32)))
+        return out
+    c, r = _both(run_padded, dev)
+    res.add("out[left_padded]", _err(c, r), 1.5e-2)
     return res
 
 
@@ -302,18 +311,20 @@ def decode_attn_fused_case(dev="cuda:0"):
     res = Result("decode_attention_fused")
     for tag, (B, hq, hkv, smax, ctx, splits) in {"gqa2_ctx271": (3, 4, 2, 300, 271, 3), "first_token": (2, 4, 2, 16, 1, 1),
                                                   "mha_ctx33": (2, 2, 2, 40, 33, 2), "chunk_edge_ctx65": (1, 8, 4, 65, 65, 4),
-                                                  "ctx64": (2, 8, 4, 290, 64, 4)}.items():
+                                                  "ctx64": (2, 8, 4, 290, 64, 4), "left_padded_ctx285": (3, 8, 4, 290, 285, 4)}.items():
         g = _gen(ctx)
         d = 256
         W = (hq + 2 * hkv) * d
         part = _randn(g, splits, B, W, scale=0.6)
         kc0, vc0 = _randn(g, B, smax, hkv, d, dtype=BF16), _randn(g, B, smax, hkv, d, dtype=BF16)
 
+        pads = torch.tensor([0, 6, 97], dtype=torch.int32) if tag.startswith("left_padded") else None
+
         def run(ops, to):
             kc, vc = to(kc0), to(vc0)
             out = ops.zeros((B, hq * d), BF16)
             ops.decode_attention_fused(to(part), kc, vc, out, batch=B, hq=hq, hkv=hkv, d=d, smax=smax, ctx=ctx, theta=10000.0,
-                                       scale=1 / 16, softcap=50.0)
+                                       scale=1 / 16, softcap=50.0, kv_start=to(pads))
             return out, kc[:, ctx - 1].clone(), vc[:, ctx - 1].clone()
         (co, ck, cv), (ro, rk, rv) = _both(run, dev)
         res.add(f"out[{tag}]", _err(co, ro), 1.5e-2)
@@ -339,6 +350,11 @@ ATTN_CASES = [
     attn_case("attn_tc_d64_tiny", 1, 1, 1, 1, 1, 64, smax=8, seed=8),
     attn_case("attn_tc_d256_sharp_softcap", 3, 8, 4, 278, 278, 256, scale=0.5, softcap=50.0, smax=290, seed=9),
     attn_case("attn_tc_d256_causal_offset", 2, 4, 2, 200, 260, 256, scale=0.25, softcap=50.0, causal=True, smax=300, seed=10),
+    # left-padded prompts: keys [0, kv_start[b]) masked for every query (tile fully / partly / not masked; pad > one tile)
+    attn_case("attn_tc_d256_left_padded", 4, 4, 2, 278, 278, 256, scale=1 / 16, softcap=50.0, smax=290, seed=11, kv_start=[0, 3, 64, 131]),
+    # causal continuation over a left-padded cache (sq < sk, every query still sees at least one real key)
+    attn_case("attn_tc_d256_left_padded_causal", 2, 2, 1, 100, 150, 256, scale=1 / 16, softcap=50.0, causal=True, smax=160, seed=12, kv_start=[5, 50]),
+    attn_case("attn_mma_d128_left_padded", 2, 2, 2, 100, 130, 128, smax=130, seed=13, kv_start=[9, 77]),
     decode_attn_case,
     decode_attn_fused_case,
 ]
@@ -383,17 +399,20 @@ def rmsnorm_case(dev="cuda:0"):
 
 def rope_case(dev="cuda:0"):
     res = Result("rope_kv")
-    for (B, S, hq, hkv, d, smax, pos0) in ((2, 37, 4, 2, 256, 64, 11), (8, 150, 8, 4, 256, 160, 0), (5, 300, 2, 1, 64, 300, 0)):
+    for (B, S, hq, hkv, d, smax, pos0, padded) in ((2, 37, 4, 2, 256, 64, 11, False), (8, 150, 8, 4, 256, 160, 0, False),
+                                                   (5, 300, 2, 1, 64, 300, 0, False), (3, 40, 4, 2, 256, 64, 0, True),
+                                                   (8, 150, 8, 4, 256, 160, 0, True)):
         g = _gen(5 + S)
         qkv = _randn(g, B * S, (hq + 2 * hkv) * d, dtype=BF16)
+        pads = (torch.arange(B, dtype=torch.int32) * 5) % 17 if padded else None      # left-padded rows (row 0 unpadded)
 
         def run(ops, to):
             q, kc, vc = ops.zeros((B * S, hq * d), BF16), ops.zeros((B, smax, hkv, d), BF16), ops.zeros((B, smax, hkv, d), BF16)
-            ops.rope_kv(to(qkv), q, kc, vc, batch=B, s=S, hq=hq, hkv=hkv, d=d, smax=smax, pos0=pos0, theta=10000.0)
+            ops.rope_kv(to(qkv), q, kc, vc, batch=B, s=S, hq=hq, hkv=hkv, d=d, smax=smax, pos0=pos0, theta=10000.0, row_pads=to(pads))
             return q, kc, vc
         c, r = _both(run, dev)
         for nm, a, b in zip(("q", "k", "v"), c, r):
-            res.add(f"{nm}[{B}x{S}]", _err(a, b), TOL_BF16 if nm != "v" else 0.0)
+            res.add(f"{nm}[{B}x{S}{'p' if padded else ''}]", _err(a, b), TOL_BF16 if nm != "v" else 0.0)
     return res
 
 
@@ -493,7 +512,8 @@ def shuffle_im2col_case(dev="cuda:0"):
 def bilinear_case(dev="cuda:0"):
     g = _gen(11)
     res = Result("bilinear_nhwc")
-    for (h, w, oh, ow, c) in ((12, 12, 24, 24, 128), (24, 24, 48, 48, 64), (7, 9, 21, 20, 8)):
+    for (h, w, oh, ow, c) in ((12, 12, 24, 24, 128), (24, 24, 48, 48, 64), (7, 9, 21, 20, 8), (48, 48, 96, 96, 256), (5, 6, 50, 41, 72),
+                              (20, 20, 14, 14, 16), (9, 33, 9, 70, 136)):
         x, ad = _randn(g, 2, h, w, c, dtype=BF16), _randn(g, 2, oh, ow, c, dtype=BF16)
 
         def run(ops, to):

@@ -89,6 +89,36 @@ def test_public_api_predict_and_decode_actions(tiny_gpu, cuda_device):
         assert np.array_equal(dd["actions"].cpu().numpy(), hb["actions"]) and np.array_equal(dd["action_ids"].cpu().numpy(), hb["action_ids"])
 
 
+def test_left_padded_batch_vs_reference_golden(tiny_gpu, cuda_device):
+    """LEFT-padded prompts through predict_action on the GPU (eager and CUDA-graph paths) against the golden vectors the live
+    reference produced for the same padded batch, plus the size-independent property that a padded row decodes like the same
+    sample alone."""
+    from spatialvla_b200 import SpatialVLAForConditionalGeneration
+    cfg, _, _, _, sd, eng = tiny_gpu
+    g = np.load(os.path.join(GOLD, "tiny_model_padded.npz"))
+    ids, am = torch.from_numpy(g["input_ids"]), torch.from_numpy(g["attention_mask"])
+    px, K = torch.from_numpy(g["pixel_u8"]).float() / 255.0, torch.from_numpy(g["intrinsic"])
+    n_new = int(g["n_new"])
+    model = SpatialVLAForConditionalGeneration(cfg, sd, device=cuda_device, action_chunk_size=2)
+    batch = {"input_ids": ids, "attention_mask": am, "pixel_values": px, "intrinsic": K}
+    toks, logits = model.predict_action(batch, max_new_tokens=n_new, return_logits=True)          # eager launches
+    toks_g = model.predict_action(batch, max_new_tokens=n_new)                                      # CUDA-graph capture + replay
+    toks_g2 = model.predict_action(batch, max_new_tokens=n_new)
+    assert np.array_equal(toks.cpu().numpy(), g["tokens"])
+    assert np.abs(logits.cpu().numpy() - g["logits"]).max() < 6e-2
+    assert torch.equal(toks_g, toks) and torch.equal(toks_g2, toks)
+    head = model.engine.last_router_head
+    model.engine.force_head = head                       # the router is batch-coupled: keep the batch's metric head
+    try:
+        for b in (1, 2):
+            pad = int((am[b] == 0).sum())
+            t1, l1 = model.predict_action({"input_ids": ids[b:b + 1, pad:], "pixel_values": px[b:b + 1], "intrinsic": K},
+                                          max_new_tokens=n_new, return_logits=True)
+            assert torch.equal(t1[0], toks[b]) and float((l1[0] - logits[b]).abs().max()) < 3e-2
+    finally:
+        model.engine.force_head = None
+
+
 def test_tokenizer_one_million_actions_vs_numpy_oracle(cuda_device):
     """Config #4 size: 1 M actions, gs_spatialvla_plus grid (min_sigma 0.5): ids bit-exact against the numpy oracle
     except rows whose atan2 lands within 4 ulp of a bin edge; decode within 4 ulp; host-buffer C-ABI entry too."""

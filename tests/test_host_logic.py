@@ -53,8 +53,36 @@ def test_forward_logits_api(tiny):
     assert pa.shape == (2, 3) and pa.dtype == torch.int64
     with pytest.raises(ValueError):
         m.predict_action({"input_ids": ids[:, 5:], "pixel_values": px, "intrinsic": K})
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):      # all-padding rows / right padding / holes: rejected, never mis-computed
         m.predict_action({"input_ids": ids, "pixel_values": px, "intrinsic": K, "attention_mask": torch.zeros_like(ids)})
+    am = torch.ones_like(ids)
+    am[:, -1] = 0
+    with pytest.raises(NotImplementedError):
+        m.predict_action({"input_ids": ids, "pixel_values": px, "intrinsic": K, "attention_mask": am})
+
+
+def test_left_padded_batch_matches_reference_golden():
+    """predict_action on a LEFT-padded batch through the public API (host orchestration over the torch op re-statements)
+    against the golden vectors the live reference produced for the same padded inputs."""
+    from spatialvla_b200.configs import get_config_dict
+    from spatialvla_b200.modeling_spatialvla import SpatialVLAForConditionalGeneration
+    g = np.load(os.path.join(GOLD, "tiny_model_padded.npz"))
+    cfg = get_config_dict("tiny")
+    sd = synth_state_dict(cfg, seed=0)
+    m = SpatialVLAForConditionalGeneration(cfg, sd, ops=RefOps())
+    ids, am = torch.from_numpy(g["input_ids"]), torch.from_numpy(g["attention_mask"])
+    px, K = torch.from_numpy(g["pixel_u8"]).float() / 255.0, torch.from_numpy(g["intrinsic"])
+    toks, logits = m.predict_action({"input_ids": ids, "attention_mask": am, "pixel_values": px, "intrinsic": K},
+                                    max_new_tokens=int(g["n_new"]), return_logits=True)
+    assert np.array_equal(toks.numpy(), g["tokens"])
+    assert np.abs(logits.numpy() - g["logits"]).max() < 6e-2
+    # forward(): logits of the last prompt position with the 2-D mask, then one cached decode step that keeps masking the pads
+    lo = cfg["action_token_begin_idx"]
+    fw = m.forward(input_ids=ids, pixel_values=px, intrinsic=K, attention_mask=am, num_logits_to_keep=1)
+    assert (fw.logits[:, 0, lo:lo + 8194] - torch.from_numpy(g["logits"][:, 0])).abs().max() < 6e-2
+    nxt = torch.from_numpy(g["tokens"][:, :1])
+    fw2 = m.forward(input_ids=nxt, past_key_values=fw.past_key_values, num_logits_to_keep=1)
+    assert (fw2.logits[:, 0, lo:lo + 8194] - torch.from_numpy(g["logits"][:, 1])).abs().max() < 6e-2
 
 
 def test_weight_packing_layouts():

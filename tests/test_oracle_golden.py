@@ -66,3 +66,29 @@ def test_model_restatement_matches_reference_golden():
     assert np.abs(aux["pos3d"][:, ::4].numpy() - g["pos3d"]).max() < 2e-5
     assert np.abs(aux["image_features"][:, ::4].numpy() - g["image_features"]).max() < 2e-5
     assert np.abs(aux["zoe"]["domain_logits"].numpy() - g["domain_logits"]).max() < 2e-5
+
+
+def test_model_restatement_left_padded_batch_matches_reference_golden():
+    """Left-padded batch (attention_mask 0...01...1): golden minted by the live reference with its own `_update_causal_mask`
+    (model/modeling_spatialvla.py:258-306) and HF generate's mask-derived position ids (oracle/compat.reference_greedy_padded)."""
+    g = np.load(os.path.join(GOLD, "tiny_model_padded.npz"))
+    from spatialvla_b200.configs import get_config_dict
+    cfg = get_config_dict("tiny")
+    sd = synth_state_dict(cfg, seed=0)
+    ids, am = torch.from_numpy(g["input_ids"]), torch.from_numpy(g["attention_mask"])
+    px, K = torch.from_numpy(g["pixel_u8"]).float() / 255.0, torch.from_numpy(g["intrinsic"])
+    assert (am == 0).sum(1).tolist() == [0, 3, 5]
+    toks, logits = R.predict_action_ref(sd, cfg, ids, px, K, int(g["n_new"]), attention_mask=am)
+    assert np.array_equal(toks.numpy(), g["tokens"])
+    assert np.abs(logits.numpy() - g["logits"]).max() < 2e-5
+    # size-independent property: a padded row decodes exactly like the same sample alone and unpadded (the ZoeDepth router is
+    # batch-coupled, so the single-sample run is forced onto the batch's metric head)
+    head = int(torch.argmax(R.image_features(sd, cfg, px, K, None, return_aux=True)[1]["zoe"]["domain_logits"].sum(0)))
+    for b in (1, 2):
+        pad = int((am[b] == 0).sum())
+        t1, l1 = R.predict_action_ref(sd, cfg, ids[b:b + 1, pad:], px[b:b + 1], K, int(g["n_new"]), force_head=head)
+        assert torch.equal(t1[0], toks[b]) and (l1[0] - logits[b]).abs().max() < 2e-4
+    # right padding / holes are rejected, not mis-computed
+    import pytest
+    with pytest.raises(NotImplementedError):
+        R.left_pads(torch.tensor([[1, 1, 0], [1, 1, 1]]))

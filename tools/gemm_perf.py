@@ -77,7 +77,7 @@ for name, B, hq, hkv, S, d, kw in [("attn_siglip", 64, 16, 16, 256, 72, {}), ("a
 from spatialvla_b200._lib import ACT_GELU_ERF, ACT_GELU_TANH, ACT_RELU
 if not only or "epi" in only:
     only_tag = sys.argv[2] if len(sys.argv) > 2 else ""
-    M, N, K = 36928, 4096, 1024
+    M, N, K = (int(v) for v in sys.argv[3:6]) if len(sys.argv) >= 6 else (36928, 4096, 1024)     # epi <tag|''> M N K
     a = torch.randn(M, K, device=dev).to(BF16); w = (torch.randn(N, K, device=dev) / 32).to(BF16)
     bias = torch.randn(N, device=dev); cs = torch.rand(N, device=dev)
     outb = torch.empty(M, N, device=dev, dtype=BF16); outf = torch.zeros(M, N, device=dev, dtype=F32)
@@ -85,8 +85,8 @@ if not only or "epi" in only:
                     ("bias_erf", dict(out_bf16=outb, bias=bias, act=ACT_GELU_ERF)), ("bias_tanh", dict(out_bf16=outb, bias=bias, act=ACT_GELU_TANH)),
                     ("relu", dict(out_bf16=outb, act=ACT_RELU)), ("f32_out", dict(out_f32=outf)), ("f32_accum_colscale", dict(out_f32=outf, accumulate=True, colscale=cs, bias=bias))]:
         if only_tag and tag != only_tag: continue
-        ms = timeit(lambda: ops.gemm(a, w, block_n=256, **kw))
-        print({"name": "epi_" + tag, "ms": round(ms, 4), "tflops": round(2.0 * M * N * K / ms / 1e9, 1)}, flush=True)
+        ms = timeit(lambda: ops.gemm(a, w, block_n=int(os.environ.get("BN", "256")), **kw))
+        print({"name": "epi_" + tag, "M": M, "N": N, "K": K, "ms": round(ms, 4), "tflops": round(2.0 * M * N * K / ms / 1e9, 1)}, flush=True)
 
 # ---- decode kernels measured from CUDA-graph replays (true GPU time, no host launch gaps)
 def graph_time(fn, reps=20):

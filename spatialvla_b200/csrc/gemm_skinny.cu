@@ -31,7 +31,9 @@ template <int NB> struct SCfg {
 };
 // Pipeline depth: 8 x 24 KB (NB <= 64) or 6 x 32 KB (NB = 128) in flight per SM.  SVLA_SKINNY_STAGES overrides it for A/B
 // measurements; measured on the in-situ decode step (tools/decode_step_perf.py, B=64): 8 stages 2176 us, 4 stages (two CTAs
-// of consecutive PDL kernels co-resident per SM) 2238 us, 3 stages 2490 us -- depth beats co-residency.
+// of consecutive PDL kernels co-resident per SM) 2238 us, 3 stages 2490 us -- depth beats co-residency.  Also tried and
+// dropped: an L2 prefetch chain (every GEMM issuing cp.async.bulk.prefetch.L2 for the next kernel's weights / this layer's KV
+// slabs): 2511-2628 us against 2246 us on the same box -- the prefetches compete with the demand stream instead of filling gaps.
 inline int skinny_stages(int stage_bytes) {
   static const int env = getenv("SVLA_SKINNY_STAGES") ? atoi(getenv("SVLA_SKINNY_STAGES")) : 0;
   if (env >= 2 && env <= 8) return env;
@@ -216,10 +218,16 @@ template <int NB>
 int launch_skinny(const CUtensorMap& tw, const CUtensorMap& tx, SkinnyParams p, int ctas, cudaStream_t st) {
   using C = SCfg<NB>;
   static bool configured = false;
+  // never more stages than K steps per CTA: the o-projection (4 K steps per split) then needs 97 KB instead of 193 KB and a
+  // CTA of it fits beside a running attention CTA, so its whole weight slice is requested before griddepcontrol.wait
   p.stages = skinny_stages(C::kStageBytes);
+  if (p.kb_per_split < p.stages) p.stages = p.kb_per_split < 2 ? 2 : p.kb_per_split;
+  static const int qkv_stages = getenv("SVLA_SKINNY_QKV_STAGES") ? atoi(getenv("SVLA_SKINNY_QKV_STAGES")) : 0;   // A/B switch
+  if (qkv_stages >= 2 && qkv_stages <= 8 && p.kb_per_split == 9 && p.stages > qkv_stages) p.stages = qkv_stages;
   const int smem_bytes = C::smem_bytes(p.stages);
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(svla_gemm_skinny_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(svla_gemm_skinny_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::smem_bytes(skinny_stages(C::kStageBytes)));
     if (e != cudaSuccess) {
       svla_set_error("svla_gemm_skinny: smem opt-in failed: %s", cudaGetErrorString(e));
       return -2;

@@ -135,3 +135,32 @@ def test_shard_bounds():
     b = {"input_ids": torch.arange(10).view(5, 2), "pixel_values": torch.zeros(5, 3, 4, 4), "intrinsic": torch.eye(3)}
     s = shard_batch(b, 1, 2)
     assert s["input_ids"].shape[0] == 2 and s["intrinsic"].shape == (3, 3)
+
+
+def test_from_pretrained_checkpoint_roundtrip(tmp_path):
+    """Checkpoint interchange: a directory holding config.json + *.safetensors in the reference's
+    own key layout loads through `from_pretrained`; like the reference (model/modeling_spatialvla.py:524-525) the last
+    `spatial_token_num` rows of embed_tokens are overwritten with spatial_embed_tokens; predict_action on the loaded model
+    reproduces the golden tokens of the live reference."""
+    from safetensors.torch import save_file
+    from spatialvla_b200 import SpatialVLAConfig, get_config_dict
+    from spatialvla_b200.modeling_spatialvla import SpatialVLAForConditionalGeneration
+    from spatialvla_b200.weights import state_dict_spec
+    cfg = get_config_dict("tiny")
+    sd = synth_state_dict(cfg, seed=0)
+    assert set(sd) == set(state_dict_spec(cfg))                 # the reference's key layout, nothing else
+    SpatialVLAConfig(**cfg).save_pretrained(tmp_path)
+    keys = sorted(sd)
+    half = len(keys) // 2                                   # two shards, like a sharded hub checkpoint
+    save_file({k: sd[k].contiguous() for k in keys[:half]}, str(tmp_path / "model-00001-of-00002.safetensors"))
+    save_file({k: sd[k].contiguous() for k in keys[half:]}, str(tmp_path / "model-00002-of-00002.safetensors"))
+    m = SpatialVLAForConditionalGeneration.from_pretrained(str(tmp_path), ops=RefOps())
+    assert m.config.spatial_token_num == cfg["spatial_token_num"] and m.engine_config["text_config"]["head_dim"] == 256
+    g = np.load(os.path.join(GOLD, "tiny_model.npz"))
+    cfg_, px_u8, ids, K = tiny_inputs()
+    toks = m.predict_action({"input_ids": ids, "pixel_values": px_u8.float() / 255.0, "intrinsic": K}, max_new_tokens=int(g["n_new"]))
+    assert np.array_equal(toks.numpy(), g["tokens"])
+    n = cfg["spatial_token_num"]
+    assert torch.equal(m.engine.gem["embed"][-n:].float(), sd["spatial_embed_tokens.weight"].to(torch.bfloat16).float())
+    with pytest.raises(OSError):
+        SpatialVLAForConditionalGeneration.from_pretrained(str(tmp_path / "missing"), ops=RefOps())

@@ -220,6 +220,13 @@ int svla_softplus_f32(const void* x, float* out, int64_t n, void* stream);
 int svla_zoe_depth_tail(const void* t, const void* e, const float* b1, const float* w2, const float* b2,
                         const float* bins, float* depth, int batch, int h, int w, int oh, int ow, int nh,
                         int nbins, float min_temp, float max_temp, void* stream);
+/* Same tail with the first MLP layer folded in: t = W_a * x is computed per pixel inside the kernel from the relative-head
+ * features x bf16 [B*oh*ow, nx] and wa bf16 [nh, nx] (no bias), so the [pixels, nh] tensor never reaches HBM; the
+ * half-resolution operands are staged per 16x16 output tile in shared memory.  Specialised for nx = 32, nh = 40, nbins = 64
+ * (the ZoeDepth-NK head) and up-sampling ratios (oh >= ~1.4 h). */
+int svla_zoe_depth_tail_fused(const void* x, const void* wa, const void* e, const float* b1, const float* w2,
+                              const float* b2, const float* bins, float* depth, int batch, int h, int w, int oh, int ow,
+                              int nx, int nh, int nbins, float min_temp, float max_temp, void* stream);
 
 /* M5 Ego3D (model/modeling_spatialvla.py:41-97,181-223,318-323): depth384 fp32 [B,384,384] ->
  * bicubic(align_corners) 384->286, crop 31 -> 7x7 area mean -> inv(K) uv d -> xyz fp32 [B,256,12]

@@ -352,6 +352,15 @@ class RefOps:
                           align_corners=True).permute(0, 2, 3, 1)
         depth.view(batch, oh, ow).copy_((p * c).sum(-1))
 
+    def zoe_depth_tail_fused(self, x, wa, e, b1, w2, b2, bins, depth, *, batch, h, w, oh, ow, min_temp, max_temp):
+        t = x.float() @ wa.float().t()                      # fp32 inside the kernel: no bf16 round trip of the hidden pre-activation
+        self.zoe_depth_tail(t, e, b1, w2, b2, bins, depth, batch=batch, h=h, w=w, oh=oh, ow=ow, nh=wa.shape[0],
+                            nbins=bins.shape[-1], min_temp=min_temp, max_temp=max_temp)
+
+    @staticmethod
+    def zoe_depth_tail_fused_supported(nx, nh, nbins, h, oh):
+        return nx == 32 and nh == 40 and nbins == 64 and oh >= 1.4 * h
+
     def ego3d_encode(self, depth384, intrinsic, xyz, enc, *, n_freqs):
         self.launches += 1
         from oracle.model_ref import backproject_patch, depth_to_224, ego3d_encoding

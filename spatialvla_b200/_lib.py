@@ -84,6 +84,7 @@ SIGNATURES = {
     "svla_zoe_attractor": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "svla_softplus_f32": (_I, [_P, _P, _L, _P]),
     "svla_zoe_depth_tail": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
+    "svla_zoe_depth_tail_fused": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "svla_ego3d_encode": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _P]),
     "svla_tok_encode": (_I, [_P, _P, _P, _P, _L, _D, _D, _I, _P]),
     "svla_tok_decode": (_I, [_P, _P, _P, _L, _P, _L, _I, _P]),

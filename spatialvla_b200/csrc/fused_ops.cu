@@ -741,7 +741,22 @@ svla_zoe_attractor_kernel(const __nv_bfloat16* __restrict__ attr, const float* _
       c.w = (1.f - s.ly) * ((1.f - s.lx) * v00.w + s.lx * v01.w) + s.ly * ((1.f - s.lx) * v10.w + s.lx * v11.w);
     }
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int a = 0; a < na; ++a) {
+    // dc = dx / (1 + 300 dx^2).  The loop is MUFU-bound with one reciprocal per term, so two attractors share one:
+    // dx1/b1 + dx2/b2 = (dx1 b2 + dx2 b1) / (b1 b2)  (b <= 1 + 300 * 80^2: the product stays far inside fp32 range)
+    auto pair_term = [](float c0, float a1, float a2) {
+      const float d1 = a1 - c0, d2 = a2 - c0;
+      const float b1 = fmaf(300.f * d1, d1, 1.f), b2 = fmaf(300.f * d2, d2, 1.f);
+      return __fdividef(fmaf(d1, b2, d2 * b1), b1 * b2);
+    };
+    int a = 0;
+    for (; a + 1 < na; a += 2) {
+      const float a1 = __shfl_sync(0xffffffffu, a_l, (lane & 16) | a), a2 = __shfl_sync(0xffffffffu, a_l, (lane & 16) | (a + 1));
+      d.x += pair_term(c.x, a1, a2);
+      d.y += pair_term(c.y, a1, a2);
+      d.z += pair_term(c.z, a1, a2);
+      d.w += pair_term(c.w, a1, a2);
+    }
+    if (a < na) {
       const float av = __shfl_sync(0xffffffffu, a_l, (lane & 16) | a);
       const float dx = av - c.x, dy = av - c.y, dz = av - c.z, dw = av - c.w;
       d.x += __fdividef(dx, fmaf(300.f * dx, dx, 1.f));
@@ -858,6 +873,174 @@ svla_zoe_depth_tail_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloa
   se += __shfl_xor_sync(0xffffffffu, se, 1); se += __shfl_xor_sync(0xffffffffu, se, 2);
   sc += __shfl_xor_sync(0xffffffffu, sc, 1); sc += __shfl_xor_sync(0xffffffffu, sc, 2);
   if (sub == 0 && active) depth[pix] = sc / se;
+}
+
+// Fused conditional-log-binomial tail (replaces GEMM [9.4 M x 32] x [32 -> 40] + svla_zoe_depth_tail_kernel): one thread per
+// output pixel, a block = 16 x 16 output pixels.  The half-resolution operands every pixel of the tile interpolates (W_b*emb:
+// NH bf16 channels, attractor bins: NBINS fp32) are staged ONCE in shared memory (<= 12 x 12 source pixels, padded pixel strides
+// keep the float4 tap reads conflict-free); the first MLP layer W_a*x on the 32 relative-head features runs on the FMA pipe with
+// warp-broadcast weight reads, so its [pixels, 40] output never exists in HBM (755 MB written + read per 64-image batch before).
+// ncu on the previous kernel: 1.86 G warp-instructions (4 lanes per pixel re-doing the tap setup, 64-bit global tap addressing),
+// issue-bound at 11 % of HBM.
+constexpr int kTailTile = 16;
+constexpr int kTailMaxSrc = 12;          // source rows / columns a tile may touch (x2 up-sampling needs 10)
+constexpr int kTailTStride = 44;         // floats per pixel of the staged first-layer output (40 + 4: conflict-free float4 rows)
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int NX, int NH, int NBINS>
+__global__ void __launch_bounds__(256)
+svla_zoe_depth_tail_fused_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wa,
+                                 const __nv_bfloat16* __restrict__ e, const float* __restrict__ b1, const float* __restrict__ w2,
+                                 const float* __restrict__ b2, const float* __restrict__ bins, float* __restrict__ depth, int h, int w,
+                                 int oh, int ow, int nr, int nc, float min_temp, float max_temp) {
+  static_assert(NX == 32 && NH % 8 == 0 && NBINS % 4 == 0, "tile shapes of the mma.sync first layer");
+  constexpr int EST = NH * 2;            // bytes per staged e pixel (NH = 40 -> 80 B: 8 consecutive pixels hit distinct banks)
+  constexpr int BST = NBINS + 4;         // floats per staged bins pixel
+  extern __shared__ __align__(16) uint8_t s_tail[];
+  float* s_bins = reinterpret_cast<float*>(s_tail);                                 // [nr*nc][BST]
+  uint8_t* s_e = s_tail + static_cast<size_t>(kTailMaxSrc) * kTailMaxSrc * BST * 4;  // [nr*nc][EST]
+  float* s_t = reinterpret_cast<float*>(s_e + kTailMaxSrc * kTailMaxSrc * EST);     // [256 pixels][kTailTStride] first-layer output
+  uint32_t* s_wa = reinterpret_cast<uint32_t*>(s_t + 256 * kTailTStride);           // [NH][NX/2] bf16 pairs (B operand, K-major)
+  float* s_w2 = reinterpret_cast<float*>(s_wa + NH * NX / 2);                       // [NH][4]
+  float* s_b1 = s_w2 + 4 * NH;                                                      // [NH]
+  float* s_lb = s_b1 + NH;                                                          // [NBINS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ox0 = blockIdx.x * kTailTile, oy0 = blockIdx.y * kTailTile;
+  const long long b = blockIdx.z;
+  const float ry = (oh > 1) ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) : 0.f;
+  const float rx = (ow > 1) ? static_cast<float>(w - 1) / static_cast<float>(ow - 1) : 0.f;
+  const int ybase = min(static_cast<int>(ry * oy0), h - 1), xbase = min(static_cast<int>(rx * ox0), w - 1);
+  // ---- stage the tables and the source tiles
+  const float nn = static_cast<float>(NBINS - 1) + 1e-7f;
+  for (int k = tid; k < NBINS; k += 256) {
+    const float kk = static_cast<float>(k) + 1e-7f;
+    s_lb[k] = nn * logf(nn) - kk * logf(kk) - (nn - kk) * logf(nn - kk + 1e-7f);
+  }
+  for (int i = tid; i < NH * NX / 2; i += 256) s_wa[i] = reinterpret_cast<const uint32_t*>(wa)[i];
+  for (int i = tid; i < 4 * NH; i += 256) s_w2[(i % NH) * 4 + i / NH] = w2[i];       // [q][c] -> [c][q]
+  for (int i = tid; i < NH; i += 256) s_b1[i] = b1[i];
+  {
+    const float4* gb = reinterpret_cast<const float4*>(bins + b * h * w * NBINS);
+    for (int i = tid; i < nr * nc * (NBINS / 4); i += 256) {
+      const int p = i / (NBINS / 4), q = i - p * (NBINS / 4);
+      const int sy = min(ybase + p / nc, h - 1), sx = min(xbase + p % nc, w - 1);
+      *reinterpret_cast<float4*>(s_bins + p * BST + 4 * q) = gb[(static_cast<long long>(sy) * w + sx) * (NBINS / 4) + q];
+    }
+    const uint4* ge = reinterpret_cast<const uint4*>(e + b * h * w * NH);
+    for (int i = tid; i < nr * nc * (NH / 8); i += 256) {
+      const int p = i / (NH / 8), q = i - p * (NH / 8);
+      const int sy = min(ybase + p / nc, h - 1), sx = min(xbase + p % nc, w - 1);
+      *reinterpret_cast<uint4*>(s_e + p * EST + 16 * q) = ge[(static_cast<long long>(sy) * w + sx) * (NH / 8) + q];
+    }
+  }
+  __syncthreads();
+  // ---- first CLB layer on the tensor cores: each warp owns 2 tile rows = 2 m16 tiles of pixels; T[32 x NH] = X[32 x 32] Wa^T.
+  //      A fragments come straight from global memory (4-byte loads, every sector is used by the k / k+8 halves of a row).
+  {
+    const int g = lane >> 2, tq = lane & 3;
+    float acc[2][NH / 8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NH / 8; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int oyr = oy0 + 2 * warp + mt;                                  // this m-tile = one row of 16 output pixels
+      const int oxa = min(ox0 + g, ow - 1), oxb = min(ox0 + g + 8, ow - 1);    // clamped: out-of-image pixels are never stored
+      const long long rowbase = (b * oh + min(oyr, oh - 1)) * static_cast<long long>(ow);
+      const uint32_t* xa = reinterpret_cast<const uint32_t*>(x + (rowbase + oxa) * NX);
+      const uint32_t* xb = reinterpret_cast<const uint32_t*>(x + (rowbase + oxb) * NX);
+#pragma unroll
+      for (int ks = 0; ks < NX / 16; ++ks) {
+        const uint32_t a0 = __ldg(xa + ks * 8 + tq), a1 = __ldg(xb + ks * 8 + tq);
+        const uint32_t a2 = __ldg(xa + ks * 8 + 4 + tq), a3 = __ldg(xb + ks * 8 + 4 + tq);
+#pragma unroll
+        for (int nt = 0; nt < NH / 8; ++nt) {
+          const uint32_t* wrow = s_wa + (nt * 8 + g) * (NX / 2) + ks * 8;     // B[k][n] = Wa[n][k]
+          mma_bf16_16816(acc[mt][nt], a0, a1, a2, a3, wrow[tq], wrow[4 + tq]);
+        }
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NH / 8; ++nt) {
+        float* ta = s_t + (warp * 32 + mt * 16 + g) * kTailTStride + nt * 8 + 2 * tq;
+        *reinterpret_cast<float2*>(ta) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+        *reinterpret_cast<float2*>(ta + 8 * kTailTStride) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+      }
+    __syncwarp();                       // a warp only reads back the 32 pixels it has just written
+  }
+  const int ox = ox0 + (tid & 15), oy = oy0 + (tid >> 4);
+  if (ox >= ow || oy >= oh) return;
+  const long long pix = (b * oh + oy) * ow + ox;
+  const Bilin s = make_bilin(oy, ox, h, w, oh, ow);
+  const int p00 = (s.y0 - ybase) * nc + (s.x0 - xbase), p01 = (s.y0 - ybase) * nc + (s.x1 - xbase);
+  const int p10 = (s.y1 - ybase) * nc + (s.x0 - xbase), p11 = (s.y1 - ybase) * nc + (s.x1 - xbase);
+  // ---- hidden = gelu(W_a x + up(W_b emb) + b1) -> 4 outputs
+  float o4[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* trow = s_t + tid * kTailTStride;           // pixel tid = (warp * 32 + lane) of the tile
+#pragma unroll 1
+  for (int c0 = 0; c0 < NH; c0 += 8) {
+    float e00[8], e01[8], e10[8], e11[8];
+    unpack8(*reinterpret_cast<const uint4*>(s_e + p00 * EST + 2 * c0), e00);
+    unpack8(*reinterpret_cast<const uint4*>(s_e + p01 * EST + 2 * c0), e01);
+    unpack8(*reinterpret_cast<const uint4*>(s_e + p10 * EST + 2 * c0), e10);
+    unpack8(*reinterpret_cast<const uint4*>(s_e + p11 * EST + 2 * c0), e11);
+    const float4 ta = *reinterpret_cast<const float4*>(trow + c0), tb = *reinterpret_cast<const float4*>(trow + c0 + 4);
+    const float tv[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = c0 + u;
+      // same association as the reference interpolation: (1-ly)((1-lx) v00 + lx v01) + ly((1-lx) v10 + lx v11)
+      const float ev = (1.f - s.ly) * ((1.f - s.lx) * e00[u] + s.lx * e01[u]) + s.ly * ((1.f - s.lx) * e10[u] + s.lx * e11[u]);
+      const float hv = gelu_erf_fast(tv[u] + ev + s_b1[c]);
+      const float4 wv = *reinterpret_cast<const float4*>(s_w2 + 4 * c);      // warp-wide broadcast
+      o4[0] = fmaf(wv.x, hv, o4[0]); o4[1] = fmaf(wv.y, hv, o4[1]); o4[2] = fmaf(wv.z, hv, o4[2]); o4[3] = fmaf(wv.w, hv, o4[3]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) o4[q] = softplus_fast(o4[q] + b2[q]);
+  const float pp0 = o4[0] + 1e-4f, pp1 = o4[1] + 1e-4f, t0 = o4[2] + 1e-4f, t1 = o4[3] + 1e-4f;
+  const float prob = pp0 / (pp0 + pp1);
+  const float temp = (max_temp - min_temp) * (t0 / (t0 + t1)) + min_temp;
+  const float lp = __logf(fminf(fmaxf(prob, 1e-4f), 1.f)), lq = __logf(fminf(fmaxf(1.f - prob, 1e-4f), 1.f));
+  const float inv_temp = 1.f / temp;
+  // ---- softmax over the bins of (log C(K-1,k) + k log p + (K-1-k) log(1-p)) / T; depth = sum_k softmax_k * centre_k
+  // softmax is shift-invariant: any offset close to the row maximum keeps exp() in range.  The log-binomial logits peak at the
+  // mode k* ~ (K-1) p, so the offset is the largest of the three logits around it (the Stirling form of log C can move the
+  // arg-max by one bin) instead of a 64-term max pass; a neighbour of the true maximum is at most ~0.7/T above it.
+  const int kmode = min(NBINS - 2, max(1, __float2int_rn(static_cast<float>(NBINS - 1) * prob)));
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = kmode - 1; k <= kmode + 1; ++k)
+    mx = fmaxf(mx, (s_lb[k] + static_cast<float>(k) * lp + static_cast<float>(NBINS - 1 - k) * lq) * inv_temp);
+  float se = 0.f, sc = 0.f;
+  const float4* q00 = reinterpret_cast<const float4*>(s_bins + p00 * BST), *q01 = reinterpret_cast<const float4*>(s_bins + p01 * BST);
+  const float4* q10 = reinterpret_cast<const float4*>(s_bins + p10 * BST), *q11 = reinterpret_cast<const float4*>(s_bins + p11 * BST);
+#pragma unroll 4
+  for (int k4 = 0; k4 < NBINS / 4; ++k4) {
+    const float4 v00 = q00[k4], v01 = q01[k4], v10 = q10[k4], v11 = q11[k4];
+    const float cs[4] = {(1.f - s.ly) * ((1.f - s.lx) * v00.x + s.lx * v01.x) + s.ly * ((1.f - s.lx) * v10.x + s.lx * v11.x),
+                         (1.f - s.ly) * ((1.f - s.lx) * v00.y + s.lx * v01.y) + s.ly * ((1.f - s.lx) * v10.y + s.lx * v11.y),
+                         (1.f - s.ly) * ((1.f - s.lx) * v00.z + s.lx * v01.z) + s.ly * ((1.f - s.lx) * v10.z + s.lx * v11.z),
+                         (1.f - s.ly) * ((1.f - s.lx) * v00.w + s.lx * v01.w) + s.ly * ((1.f - s.lx) * v10.w + s.lx * v11.w)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = 4 * k4 + i;
+      const float y = (s_lb[kk] + static_cast<float>(kk) * lp + static_cast<float>(NBINS - 1 - kk) * lq) * inv_temp;
+      const float ex = __expf(y - mx);
+      se += ex; sc = fmaf(ex, cs[i], sc);
+    }
+  }
+  depth[pix] = sc / se;
 }
 
 // ------------------------------------------------------------------------------------------ M5 Ego3D
@@ -1144,6 +1327,32 @@ extern "C" int svla_zoe_depth_tail(const void* t, const void* e, const float* b1
       static_cast<const __nv_bfloat16*>(t), static_cast<const __nv_bfloat16*>(e), b1, w2, b2, bins, depth, h, w, oh, ow, nh, nbins,
       min_temp, max_temp);
   SVLA_LAUNCH_CHECK("svla_zoe_depth_tail");
+  return 0;
+}
+
+extern "C" int svla_zoe_depth_tail_fused(const void* x, const void* wa, const void* e, const float* b1, const float* w2,
+                                         const float* b2, const float* bins, float* depth, int batch, int h, int w, int oh, int ow,
+                                         int nx, int nh, int nbins, float min_temp, float max_temp, void* stream) {
+  SVLA_REQUIRE(x && wa && e && b1 && w2 && b2 && bins && depth, "svla_zoe_depth_tail_fused: null pointer");
+  SVLA_REQUIRE(nx == 32 && nh == 40 && nbins == 64, "svla_zoe_depth_tail_fused: specialised for 32 features -> 40 hidden, 64 bins (got %d, %d, %d)", nx, nh, nbins);
+  SVLA_REQUIRE(batch > 0 && batch <= 65535 && h > 0 && w > 0 && oh > 0 && ow > 0, "svla_zoe_depth_tail_fused: bad geometry");
+  const float ry = (oh > 1) ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) : 0.f;
+  const float rx = (ow > 1) ? static_cast<float>(w - 1) / static_cast<float>(ow - 1) : 0.f;
+  const int nr = static_cast<int>(floorf((kTailTile - 1) * ry)) + 3, nc = static_cast<int>(floorf((kTailTile - 1) * rx)) + 3;
+  SVLA_REQUIRE(nr <= kTailMaxSrc && nc <= kTailMaxSrc, "svla_zoe_depth_tail_fused: resampling ratio %.3f too large (up-sampling only)", ry);
+  const size_t smem = static_cast<size_t>(kTailMaxSrc) * kTailMaxSrc * ((64 + 4) * 4 + 40 * 2) + 256 * kTailTStride * sizeof(float) +
+                      (40 * 32 / 2 + 4 * 40 + 40 + 64) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t ce = cudaFuncSetAttribute(svla_zoe_depth_tail_fused_kernel<32, 40, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    SVLA_REQUIRE(ce == cudaSuccess, "svla_zoe_depth_tail_fused: smem opt-in failed: %s", cudaGetErrorString(ce));
+    configured = true;
+  }
+  dim3 grid((ow + kTailTile - 1) / kTailTile, (oh + kTailTile - 1) / kTailTile, batch);
+  svla_zoe_depth_tail_fused_kernel<32, 40, 64><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(wa), static_cast<const __nv_bfloat16*>(e), b1, w2, b2, bins,
+      depth, h, w, oh, ow, nr, nc, min_temp, max_temp);
+  SVLA_LAUNCH_CHECK("svla_zoe_depth_tail_fused");
   return 0;
 }
 

@@ -436,9 +436,15 @@ class SpatialVLAEngine:
             prev_bin, prev_emb, pr = bins, emb, r_
         oc, ro = outconv
         Mo = B * ro * ro
-        t = self._lin(oc, hd["clb_wa"], Mo)
         e40 = self._lin(prev_emb, hd["clb_wb"], B * pr * pr)
         depth = ops.empty((B, ro, ro), F32)
+        wa = hd["clb_wa"]
+        if ops.zoe_depth_tail_fused_supported(wa.shape[1], wa.shape[0], nbins, pr, ro):
+            # the full-resolution half of the first CLB layer (32 -> 40) is evaluated inside the tail kernel
+            ops.zoe_depth_tail_fused(oc, wa, e40, hd["clb_b1"], hd["clb_w2"], hd["clb_b2"], prev_bin, depth, batch=B, h=pr, w=pr,
+                                     oh=ro, ow=ro, min_temp=z["min_temp"], max_temp=z["max_temp"])
+            return depth
+        t = self._lin(oc, wa, Mo)
         ops.zoe_depth_tail(t, e40, hd["clb_b1"], hd["clb_w2"], hd["clb_b2"], prev_bin, depth, batch=B, h=pr, w=pr, oh=ro, ow=ro,
                            nh=t.shape[1], nbins=nbins, min_temp=z["min_temp"], max_temp=z["max_temp"])
         return depth

@@ -264,6 +264,17 @@ class CudaOps:
                                              batch, h, w, oh, ow, nh, nbins, float(min_temp), float(max_temp),
                                              self._stream()), "svla_zoe_depth_tail")
 
+    def zoe_depth_tail_fused(self, x, wa, e, b1, w2, b2, bins, depth, *, batch, h, w, oh, ow, min_temp, max_temp):
+        """x bf16 [B*oh*ow, 32] relative-head features, wa bf16 [40, 32]: the first CLB layer runs inside the kernel."""
+        _req(x.dtype == BF16 and wa.dtype == BF16 and x.is_contiguous() and wa.is_contiguous(), "zoe_depth_tail_fused: bf16 contiguous x / wa")
+        L.check(self.lib.svla_zoe_depth_tail_fused(_ptr(x), _ptr(wa), _ptr(e), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(bins), _ptr(depth),
+                                                   batch, h, w, oh, ow, int(x.shape[-1]), int(wa.shape[0]), int(bins.shape[-1]),
+                                                   float(min_temp), float(max_temp), self._stream()), "svla_zoe_depth_tail_fused")
+
+    @staticmethod
+    def zoe_depth_tail_fused_supported(nx, nh, nbins, h, oh):
+        return nx == 32 and nh == 40 and nbins == 64 and oh >= 1.4 * h
+
     def ego3d_encode(self, depth384, intrinsic, xyz, enc, *, n_freqs):
         _req(depth384.dtype == F32 and depth384.is_contiguous() and tuple(depth384.shape[1:]) == (384, 384),
              "ego3d_encode: depth must be fp32 [B,384,384]")

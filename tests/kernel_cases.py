@@ -555,6 +555,21 @@ def zoe_tail_case(dev="cuda:0"):
     for nm, a, b, tol in zip(("attractor", "router_embed", "router_embed_bf16", "depth_tail", "softplus"), c_, r_,
                              (1e-4, 1e-4, TOL_BF16, 2e-3, 1e-5)):
         res.add(nm, _err(a, b), tol)
+    # fused tail (first CLB layer inside the kernel): ragged tiles (oh, ow not multiples of 16), batch 3, and the exact x2 geometry
+    for (B2, h2, w2_, oh2, ow2) in ((3, 11, 13, 21, 27), (2, 24, 24, 48, 48), (1, 5, 5, 37, 35)):
+        g2 = _gen(100 + oh2)
+        xr = _randn(g2, B2 * oh2 * ow2, 32, dtype=BF16)
+        wa = (_randn(g2, 40, 32) * 0.3).to(BF16)
+        e2 = _randn(g2, B2, h2, w2_, nh, dtype=BF16)
+        prev2 = torch.nn.functional.softplus(_randn(g2, B2, h2, w2_, nb)) * 3.0
+
+        def run2(ops, to):
+            d2 = ops.zeros((B2, oh2, ow2), F32)
+            ops.zoe_depth_tail_fused(to(xr), to(wa), to(e2), to(b1), to(w2), to(b2), to(prev2), d2, batch=B2, h=h2, w=w2_, oh=oh2, ow=ow2,
+                                     min_temp=0.0212, max_temp=50.0)
+            return d2
+        cf, rf2 = _both(run2, dev)
+        res.add(f"depth_tail_fused[{h2}x{w2_}->{oh2}x{ow2}]", _err(cf, rf2), 2e-3)
     return res
 
 

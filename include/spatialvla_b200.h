@@ -68,7 +68,8 @@ typedef struct SvlaGemmArgs {
   int32_t act;
   int32_t flags;
   int32_t block_n;        /* 0 = auto; else 32 | 64 | 128 | 256 */
-  int32_t impl;           /* 0 = tcgen05 (product path); 1 = SIMT debugging kernel (tests only) */
+  int32_t impl;           /* 0 = tcgen05, kernel variant chosen by shape (product path); 1 = SIMT debugging kernel (tests only);
+                             2 / 3 = force the 1-CTA / 2-CTA (cta_group::2) kernel; 4 = force the row-tile 3x3 conv kernel (n <= 128) */
 } SvlaGemmArgs;
 
 int svla_gemm(const SvlaGemmArgs* args, void* stream);

@@ -59,6 +59,7 @@ struct EpiParams {
   int tma_out;    // 0 = register/LDG/STG epilogue; 1 = bf16 tile via TMA store; 2 = fp32 tile via TMA store; 3 = fp32 TMA reduce-add
   // conv geometry
   int nb, h, wd, tiles_h, tiles_w;
+  int rowtile;    // 1: conv m-tile = 128 consecutive pixels of ONE image row (svla_conv3x3_rowtile_kernel), tiles_w = ceil(wd/128)
 };
 
 // ------------------------------------------------------------------------------------------ fused epilogue
@@ -370,6 +371,11 @@ __device__ __forceinline__ bool tile_row_to_global(const EpiParams& ep, bool con
   const int tiles_per_img = ep.tiles_h * ep.tiles_w;
   const int img = static_cast<int>(m_tile / tiles_per_img);
   const int rem = static_cast<int>(m_tile % tiles_per_img);
+  if (ep.rowtile) {
+    const int hh = rem / ep.tiles_w, ww = (rem % ep.tiles_w) * kBM + r;
+    grow = (static_cast<long long>(img) * ep.h + hh) * ep.wd + ww;
+    return ww < ep.wd && img < ep.nb;
+  }
   const int hh = (rem / ep.tiles_w) * kConvTileH + r / kConvTileW;
   const int ww = (rem % ep.tiles_w) * kConvTileW + r % kConvTileW;
   grow = (static_cast<long long>(img) * ep.h + hh) * ep.wd + ww;
@@ -591,6 +597,163 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   }
 }
 
+// ------------------------------------------------------------------------------------------ 3x3 conv, row-tile variant
+// The patch-tile conv above re-fetches the activation tile from L2 for each of the 9 taps; with few output channels (the
+// relative head: 128 -> 32 at 384 x 384) the MMA needs more L2 -> shared-memory bytes per cycle than an SM can pull and the
+// kernel sits at 14 % of the tensor peak.  Here an m-tile is 128 consecutive pixels of ONE image row, so the three horizontal
+// taps of a kernel row read the SAME shared-memory buffer at row offsets 0 / 1 / 2: the A operand of tap dx is the K-major
+// SWIZZLE_128B descriptor of the 130-pixel buffer advanced by dx * 128 bytes (measured on B200: tcgen05 derives the swizzle
+// phase from the absolute shared-memory address, so a start that is not 1024-byte aligned is legal with base_offset = 0).
+// One pipeline stage = (64-channel chunk, kernel row dy): a {64 ch, 130 w, 1 h} TMA box (zero-filled halo = padding) plus
+// the three [BN x 64] weight tiles of that kernel row; 12 MMAs per stage.  Activation traffic: 3 instead of 9 loads per tile.
+template <int BN> struct RowCfg {
+  static constexpr int kARows = kBM + 2;
+  static constexpr int kABytesRaw = kARows * kBK * 2;                       // 16 640 B transferred
+  static constexpr int kABytes = (kABytesRaw + 1023) / 1024 * 1024;         // 17 408 B reserved (tile bases stay 1024-aligned)
+  static constexpr int kBTile = BN * kBK * 2;
+  static constexpr int kBBytes = 3 * kBTile;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = kEpiWarps * 4096;
+  static constexpr int kStages = (232448 - 1024 - 256 - kStagingBytes) / kStageBytes > 6 ? 6 : (232448 - 1024 - 256 - kStagingBytes) / kStageBytes;
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kStagingBytes;
+  static_assert(kStages >= 2 && kBTile % 1024 == 0, "row-tile conv: pipeline needs two stages and 1 KB aligned weight tiles");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+svla_conv3x3_rowtile_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const EpiParams ep,
+                            const long long num_m_tiles, const long long num_n_tiles, const int c_chunks, const int cpad) {
+  using C = RowCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* staging = smem + C::kStages * C::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + C::kStagingBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tmem_full = bars + 2 * C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+#pragma unroll 1
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], kEpiWarps); mbar_init(&tmem_empty[1], kEpiWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols, 1>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const long long num_tiles = num_m_tiles * num_n_tiles;
+  const int stages_per_tile = 3 * c_chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
+        const int tiles_per_img = ep.tiles_h * ep.tiles_w;
+        const int img = static_cast<int>(m_tile / tiles_per_img), rem = static_cast<int>(m_tile % tiles_per_img);
+        const int hrow = rem / ep.tiles_w, w0 = (rem % ep.tiles_w) * kBM;
+        for (int it = 0; it < stages_per_tile; ++it) {
+          const int cc = it / 3, dy = it - 3 * cc;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + C::kABytes;
+          mbar_expect_tx(&full_bar[stage], C::kABytesRaw + C::kBBytes);
+          tma_load_4d(sa, &tm_a, &full_bar[stage], cc * kBK, w0 - 1, hrow + dy - 1, img);
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx)
+            tma_load_2d(sb + dx * C::kBTile, &tm_b, &full_bar[stage], (dy * 3 + dx) * cpad + cc * kBK, static_cast<int>(n_tile * BN));
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0, it_tile = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it_tile) {
+        const uint32_t as = it_tile & 1u, aphase = (it_tile >> 1) & 1u;
+        mbar_wait(&tmem_empty[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int it = 0; it < stages_per_tile; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t b_addr = a_addr + C::kABytes;
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            // tap dx: the same 130-pixel buffer, rows dx .. dx + 127 (start advanced by dx * 128 B, base_offset stays 0)
+            const uint64_t da = make_kmajor_sw128_desc(a_addr + dx * 128);
+            const uint64_t db = make_kmajor_sw128_desc(b_addr + dx * C::kBTile);
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k)
+              umma_bf16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                        static_cast<uint32_t>((it | dx | k) != 0));
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    constexpr int kColsPerWarp = BN >= 64 ? BN / 2 : BN;
+    uint32_t it_tile = 0;
+    float* stage_f = reinterpret_cast<float*>(staging + (warp - 2) * 4096);
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it_tile) {
+      const long long m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
+      const uint32_t as = it_tile & 1u, aphase = (it_tile >> 1) & 1u;
+      RowSet rs;
+#pragma unroll
+      for (int p = 0; p < kPasses; ++p) {
+        long long grow = 0;
+        rs.ok[p] = tile_row_to_global(ep, true, m_tile, q * 32 + p * 8 + (lane >> 2), grow);
+        rs.off[p] = static_cast<unsigned>(grow * ep.ldo);
+        rs.off32[p] = static_cast<unsigned>((ep.res_mod > 0 ? grow % ep.res_mod : grow) * ep.ldo);
+      }
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+      if (BN >= 64 || chalf == 0) {
+#pragma unroll 1
+        for (int c0 = chalf * kColsPerWarp; c0 < (chalf + 1) * kColsPerWarp; c0 += 32) {
+          const long long n0 = n_tile * BN + c0;
+          if (n0 >= ep.n) break;
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          float acc[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+          epilogue_chunk(ep, acc, stage_f, lane, n0, rs);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::kTmemCols, 1>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ SIMT debug kernel
 // Straightforward one-thread-per-output kernel with the same epilogue; used by tests only (args->impl == 1) so
 // that the rest of the path can be validated independently of the tcgen05 kernel.
@@ -685,14 +848,14 @@ int encode_out(CUtensorMap* tm, void* base, bool f32, uint64_t n, uint64_t m, ui
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 100;
 }
 
-int encode_nhwc(CUtensorMap* tm, const void* base, int nb, int h, int w, int c) {
+int encode_nhwc(CUtensorMap* tm, const void* base, int nb, int h, int w, int c, int box_w = kConvTileW, int box_h = kConvTileH) {
   auto fn = get_encode_fn();
   if (!fn) return -1;
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
                         static_cast<cuuint64_t>(nb)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w) * c * 2,
                            static_cast<cuuint64_t>(h) * w * c * 2};
-  cuuint32_t box[4] = {kBK, kConvTileW, kConvTileH, 1};
+  cuuint32_t box[4] = {kBK, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -735,6 +898,26 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
     return -2;
   }
   SVLA_LAUNCH_CHECK("svla_gemm_tcgen05");
+  return 0;
+}
+
+template <int BN>
+int launch_rowtile(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& ep, long long mt, long long nt, int c_chunks,
+                   int cpad, cudaStream_t st) {
+  using C = RowCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(svla_conv3x3_rowtile_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) {
+      svla_set_error("svla_gemm(conv row-tile): cudaFuncSetAttribute(%d bytes) failed: %s", C::kSmemBytes, cudaGetErrorString(e));
+      return -2;
+    }
+    configured = true;
+  }
+  const long long tiles = mt * nt;
+  const int grid = static_cast<int>(tiles < svla_num_sms() ? tiles : svla_num_sms());
+  svla_conv3x3_rowtile_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, ep, mt, nt, c_chunks, cpad);
+  SVLA_LAUNCH_CHECK("svla_conv3x3_rowtile");
   return 0;
 }
 
@@ -816,6 +999,30 @@ extern "C" int svla_gemm(const SvlaGemmArgs* g, void* stream) {
         conv ? 1 : 0, g->c, cpad);
     SVLA_LAUNCH_CHECK("svla_gemm_simt");
     return 0;
+  }
+
+  // Row-tile conv: few output channels (N <= 128) on wide maps, where the 9x activation re-fetch of the patch-tile kernel is
+  // L2-bound.  impl 4 forces it, SVLA_CONV_ROWTILE=0 disables it.
+  {
+    static const int rowtile_env = getenv("SVLA_CONV_ROWTILE") ? atoi(getenv("SVLA_CONV_ROWTILE")) : 1;
+    const int tw = conv ? (g->wd + kBM - 1) / kBM : 0;
+    const bool fits = conv && g->n <= 128 && g->wd >= kBM && static_cast<long long>(tw) * kBM * 3 <= 4LL * g->wd;     // <= 33 % padded columns
+    if (conv && (g->impl == 4 || (g->impl == 0 && rowtile_env != 0 && fits && !g->block_n))) {
+      SVLA_REQUIRE(g->n <= 128, "svla_gemm(conv row-tile): n=%lld > 128", (long long)g->n);
+      const int bnr = g->n <= 32 ? 32 : (g->n <= 64 ? 64 : 128);
+      ep.rowtile = 1;
+      ep.tiles_w = tw;
+      ep.tiles_h = g->h;
+      CUtensorMap tra, trb;
+      int rcr = encode_nhwc(&tra, g->a, g->nb, g->h, g->wd, g->c, kBM + 2, 1);
+      SVLA_REQUIRE(rcr == 0, "svla_gemm(conv row-tile): cuTensorMapEncodeTiled(A) failed (%d)", rcr);
+      rcr = encode_2d(&trb, g->w, static_cast<uint64_t>(g->k), static_cast<uint64_t>(g->n), static_cast<uint64_t>(g->ldw), kBK, static_cast<uint32_t>(bnr));
+      SVLA_REQUIRE(rcr == 0, "svla_gemm(conv row-tile): cuTensorMapEncodeTiled(W) failed (%d)", rcr);
+      const long long mt = static_cast<long long>(g->nb) * g->h * tw, ntl = (g->n + bnr - 1) / bnr;
+      if (bnr == 32) return launch_rowtile<32>(tra, trb, ep, mt, ntl, c_chunks, cpad, st);
+      if (bnr == 64) return launch_rowtile<64>(tra, trb, ep, mt, ntl, c_chunks, cpad, st);
+      return launch_rowtile<128>(tra, trb, ep, mt, ntl, c_chunks, cpad, st);
+    }
   }
 
   const long long m_tiles = conv ? static_cast<long long>(g->nb) * ep.tiles_h * ep.tiles_w : (g->m + kBM - 1) / kBM;

@@ -160,6 +160,16 @@ TMA_EPI_CASES = [   # TMA-store epilogue (one output, no residuals): ragged M/N,
     gemm_case("tmaepi_f32_accum_pair_multiwave", 36928 // 4 + 9, 1024, 1024, bias=True, colscale=True, out=("f32",), accumulate=True, impl=3),
     gemm_case("tmaepi_bf16_multiwave_4304", 16384 // 2, 4304, 1152, bias=True, act=ACT_GELU_TANH),
 ]
+ROWTILE_CASES = [   # row-tile 3x3 conv (impl=4): shifted-descriptor taps over one 130-pixel halo row per (chunk, kernel row)
+    gemm_case("rowtile_n32_w384", 0, 32, 0, conv=(1, 5, 384, 128), bias=True, act=ACT_RELU, impl=4),
+    gemm_case("rowtile_n32_ragged_w150", 0, 32, 0, conv=(2, 7, 150, 64), bias=True, impl=4),
+    gemm_case("rowtile_n24_w130_c72", 0, 24, 0, conv=(2, 3, 130, 72), bias=True, impl=4),
+    gemm_case("rowtile_n64_w256", 0, 64, 0, conv=(2, 6, 256, 128), bias=True, act=ACT_RELU, impl=4),
+    gemm_case("rowtile_n128_w192_c256", 0, 128, 0, conv=(2, 9, 192, 256), bias=True, impl=4),
+    gemm_case("rowtile_n128_res_relu_copy", 0, 128, 0, conv=(1, 4, 140, 128), bias=True, res_bf16=True, res2=True, out=("bf16", "relu"), impl=4),
+    gemm_case("rowtile_small_w20", 0, 32, 0, conv=(3, 20, 20, 64), bias=True, impl=4),
+    gemm_case("rowtile_auto_dispatch", 0, 32, 0, conv=(1, 4, 384, 128), bias=True, act=ACT_RELU),
+]
 SIMT_CASES = [
     gemm_case("simt_ragged", 300, 200, 104, bias=True, act=ACT_GELU_TANH, out=("bf16", "f32"), impl=1),
     gemm_case("simt_conv", 0, 64, 0, conv=(2, 24, 24, 64), bias=True, act=ACT_RELU, impl=1),
@@ -639,4 +649,4 @@ def tokenizer_case(dev="cuda:0"):
 FUSED_CASES = [layernorm_case, rmsnorm_case, rope_case, embed_case, argmax_case, patchify_case, assemble_concat_case,
                shuffle_im2col_case, bilinear_case, zoe_tail_case, ego3d_case, tokenizer_case]
 
-ALL_CASES = {c.__name__: c for c in (SIMT_CASES + GEMM_CASES + PAIR_CASES + TMA_EPI_CASES + SKINNY_CASES + ATTN_CASES + FUSED_CASES)}
+ALL_CASES = {c.__name__: c for c in (SIMT_CASES + GEMM_CASES + PAIR_CASES + TMA_EPI_CASES + ROWTILE_CASES + SKINNY_CASES + ATTN_CASES + FUSED_CASES)}

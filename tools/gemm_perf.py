@@ -54,9 +54,11 @@ for name, (nb, h, w_, c), N in [("fusion_conv_96", (64, 96, 96, 256), 256), ("fu
     if only and only not in name: continue
     x = torch.randn(nb, h, w_, c, device=dev).to(BF16); wt = torch.randn(N, 9 * c, device=dev).to(BF16)
     out = torch.empty(nb * h * w_, N, device=dev, dtype=BF16)
-    for impl in (2, 3):
+    for impl in (2, 3, 4):
+        if impl == 4 and N > 128: continue
         ms = timeit(lambda: ops.gemm(x, wt, conv=(nb, h, w_, c), out_bf16=out, impl=impl), iters=3)
-        print({"name": name, "cta_group": impl - 1, "ms": round(ms, 3), "tflops": round(2.0 * nb * h * w_ * N * 9 * c / ms / 1e9, 1)}, flush=True)
+        print({"name": name, "kernel": {2: "patch-tile 1-CTA", 3: "patch-tile 2-CTA", 4: "row-tile"}[impl], "ms": round(ms, 3),
+               "tflops": round(2.0 * nb * h * w_ * N * 9 * c / ms / 1e9, 1)}, flush=True)
 # attention
 for name, B, hq, hkv, S, d, kw in [("attn_siglip", 64, 16, 16, 256, 72, {}), ("attn_beit", 64, 16, 16, 577, 64, {"relpos": 24}), ("attn_gemma", 64, 8, 4, 278, 256, {"softcap": 50.0})]:
     if only and only not in name: continue

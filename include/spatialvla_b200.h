@@ -132,6 +132,25 @@ int svla_decode_attention_fused(const float* qkv_f32, int n_partials, int64_t pa
                                 void* out, int batch, int hq, int hkv, int d, int smax, int ctx, float theta, float scale,
                                 float softcap, const int32_t* kv_start, void* stream);
 
+/* G4: one whole Gemma2 decode step (all layers) for SMALL batches (batch in {1, 2, 4}) in ONE persistent launch: one CTA per SM,
+ * every projection a weight-streaming GEMV over all SMs, phases separated by grid barriers (model/modeling_gemma2.py:364-413,
+ * 451-506,680-793).  Replaces the 7-launches-per-layer chain of the batched path where per-launch fixed cost, not HBM time,
+ * bounds the step (BASELINE.json "p50 latency at bs=1").
+ * layers_dev: DEVICE array of n_layers descriptors (device pointers; wgu rows interleaved gate_j / up_j like svla_gemm GEGLU;
+ * kcache/vcache bf16 [B, smax, hkv, d] of that layer).  x fp32 [B, hidden]: the embedded token times sqrt(hidden) (clobbered).
+ * h_out bf16 [B, hidden]: final-normed hidden state.  scratch: svla_decode_step_small_scratch_floats(...) floats of device
+ * memory.  ctx = number of cache slots after this step (the new token sits at slot ctx-1, RoPE position ctx - kv_start[b]). */
+typedef struct SvlaDecodeLayer {
+  const void* wqkv; const void* wo; const void* wgu; const void* wd;              /* bf16 [N, K] row-major */
+  const float* ln_in; const float* ln_post_attn; const float* ln_pre_ff; const float* ln_post_ff;
+  void* kcache; void* vcache;
+} SvlaDecodeLayer;
+int64_t svla_decode_step_small_scratch_floats(int batch, int hidden, int hq, int hkv, int d, int ff);
+int svla_decode_step_small(const SvlaDecodeLayer* layers_dev, int n_layers, float* x, const float* final_norm_w,
+                           void* h_out_bf16, float* scratch, int batch, int hidden, int hq, int hkv, int d, int ff,
+                           int smax, int ctx, float theta, float scale, float softcap, float eps, const int32_t* kv_start,
+                           void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Memory-bound fused kernels
  * --------------------------------------------------------------------------------------------------- */

@@ -173,6 +173,22 @@ class CudaOps:
                                                      float(theta), float(scale), float(softcap or 0.0), _ptr(kv_start), self._stream()),
                 "svla_decode_attention_fused")
 
+    # ---- G4 persistent small-batch decode step
+    def decode_step_small_scratch(self, batch, hidden, hq, hkv, d, ff):
+        n = int(self.lib.svla_decode_step_small_scratch_floats(batch, hidden, hq, hkv, d, ff))
+        return torch.zeros(n, dtype=F32, device=self.device)
+
+    def decode_step_small(self, layer_table, x, final_w, h_out, scratch, *, batch, hidden, hq, hkv, d, ff, smax, ctx, theta, scale,
+                          softcap, eps, kv_start=None):
+        """layer_table: int64 device tensor [n_layers, 10] of device pointers in SvlaDecodeLayer order."""
+        _req(layer_table.dtype == torch.int64 and layer_table.dim() == 2 and layer_table.shape[1] == 10 and layer_table.is_contiguous(),
+             "decode_step_small: layer table must be int64 [n_layers, 10]")
+        _req(x.dtype == F32 and x.is_contiguous() and h_out.dtype == BF16 and h_out.is_contiguous(), "decode_step_small: x fp32 / h_out bf16")
+        L.check(self.lib.svla_decode_step_small(_ptr(layer_table), int(layer_table.shape[0]), _ptr(x), _ptr(final_w), _ptr(h_out),
+                                                _ptr(scratch), batch, hidden, hq, hkv, d, ff, smax, ctx, float(theta), float(scale),
+                                                float(softcap or 0.0), float(eps), _ptr(kv_start), self._stream()),
+                "svla_decode_step_small")
+
     # ---- memory-bound fused ops
     def layernorm(self, x, gamma, beta, eps, *, out_bf16=None, out_f32=None, relu=False):
         _req(x.dtype == F32 and x.is_contiguous(), "layernorm: x must be contiguous fp32")

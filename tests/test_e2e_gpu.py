@@ -119,6 +119,44 @@ def test_left_padded_batch_vs_reference_golden(tiny_gpu, cuda_device):
         model.engine.force_head = None
 
 
+def test_small_batch_persistent_decode_matches_chain(tiny_gpu, cuda_device):
+    """Batches of 1 / 2 decode through the single-launch persistent kernel (svla_decode_step_small); the 7-kernels-per-layer
+    chain of the batched path is the reference here (both are checked against the fp32 oracle elsewhere).  Also left-padded rows;
+    batch 4 stays on the chain (the flag is then a no-op)."""
+    cfg, px, ids, K, sd, eng = tiny_gpu
+    n_new = 6
+    g = torch.Generator().manual_seed(5)
+    for B in (1, 2, 4):
+        pxb = torch.rand(B, 3, 224, 224, generator=g)
+        idb = torch.cat([ids[:1, :257].repeat(B, 1), torch.randint(3, 1000, (B, 6), generator=g), torch.full((B, 1), 108)], 1)
+        pads = None
+        if B >= 2:                                            # odd rows left-padded by 2 / 5 tokens
+            padl = [0, 2, 0, 5][:B]
+            pads = torch.tensor(padl, dtype=torch.int32, device=cuda_device)
+            for b, pd in enumerate(padl):
+                if pd:
+                    idb[b] = torch.cat([torch.zeros(pd, dtype=torch.int64), idb[b, :-pd]])
+        args = (idb.to(cuda_device), pxb.to(cuda_device), K.to(cuda_device), n_new)
+        eng.force_head = 0
+        try:
+            eng.small_decode = True
+            t_small, l_small = eng.generate_actions(*args, return_logits=True, pads=pads)
+            t_graph = eng.generate_actions(*args, pads=pads)                   # CUDA-graph capture + replay of the persistent kernel
+            t_graph2 = eng.generate_actions(*args, pads=pads)
+            eng.small_decode = False
+            t_chain, l_chain = eng.generate_actions(*args, return_logits=True, pads=pads)
+        finally:
+            eng.small_decode = True
+            eng.force_head = None
+            if hasattr(eng, "_graphs"):
+                eng._graphs.clear()
+        err = float((l_small - l_chain).abs().max())
+        assert err < 3e-2, (B, err)
+        agree = float((t_small == t_chain).float().mean())
+        assert agree >= 0.9, (B, agree, t_small.tolist(), t_chain.tolist())
+        assert torch.equal(t_graph, t_small) and torch.equal(t_graph2, t_small), B
+
+
 def test_tokenizer_one_million_actions_vs_numpy_oracle(cuda_device):
     """Config #4 size: 1 M actions, gs_spatialvla_plus grid (min_sigma 0.5): ids bit-exact against the numpy oracle
     except rows whose atan2 lands within 4 ulp of a bin edge; decode within 4 ulp; host-buffer C-ABI entry too."""

@@ -146,7 +146,7 @@ def test_small_batch_persistent_decode_matches_chain(tiny_gpu, cuda_device):
             eng.small_decode = False
             t_chain, l_chain = eng.generate_actions(*args, return_logits=True, pads=pads)
         finally:
-            eng.small_decode = True
+            eng.small_decode = type(eng).small_decode       # back to the configured default (opt-in: SVLA_DECODE_SMALL=1)
             eng.force_head = None
             if hasattr(eng, "_graphs"):
                 eng._graphs.clear()

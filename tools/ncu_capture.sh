@@ -16,7 +16,8 @@ RX[skinny_gateup]='svla_gemm_skinny_kernel';          SK[skinny_gateup]=3
 RX[decode_attn]='svla_decode_attn_fused_kernel';      SK[decode_attn]=30
 RX[rmsnorm_prefill]='svla_rmsnorm_residual_warp_kernel'; SK[rmsnorm_prefill]=3
 RX[rope_prefill]='svla_rope_kv_vec_kernel';           SK[rope_prefill]=2
-RX[depth_tail]='svla_zoe_depth_tail_kernel';          SK[depth_tail]=0
+RX[depth_tail]='svla_zoe_depth_tail_fused_kernel';    SK[depth_tail]=0
+RX[conv_rowtile]='svla_conv3x3_rowtile_kernel';       SK[conv_rowtile]=1      # relative-head conv2 128->32 @384^2 (the 2nd row-tile launch)
 RX[bilinear]='svla_bilinear_nhwc_kernel';             SK[bilinear]=4
 RX[layernorm]='svla_layernorm_warp_kernel';           SK[layernorm]=10
 NAMES="$@"

@@ -69,12 +69,14 @@ __device__ __forceinline__ float tanh_cap(float u) {
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
+    // arrive: one release reduction (orders this CTA's phase output before the count); poll with RELAXED loads -- an acquire
+    // load per spin iteration invalidates the L1 every time (CCTL.IVALL, 346 K of them per step in the first version) -- and
+    // take the acquire fence once, after the count has been seen
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     unsigned v;
     unsigned long long t0 = 0;
     for (unsigned spin = 0;; ++spin) {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
       if (v >= target) break;
       if ((spin & 4095u) == 4095u) {
         unsigned long long now;
@@ -83,7 +85,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
         else if (now - t0 > 2000000000ull) { printf("svla_decode_step_small: grid barrier timed out (block %d)\n", blockIdx.x); __trap(); }
       }
     }
-    __threadfence();
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   __syncthreads();
 }
@@ -200,25 +202,43 @@ __device__ __forceinline__ void gemv_rows(const __nv_bfloat16* __restrict__ W, i
 // x_out = x_in + rms(branch)(1+w_post) (branch may be null: x_out = x_in); s_vec = bf16round(rms(x_out)(1+w_pre)).
 // Every CTA computes all NB rows; CTA 0 additionally stores x_out.
 constexpr int kNormVec = 16;            // elements per thread: hidden <= 4096
-template <int NB>
+template <int NB, typename Prime>
 __device__ __forceinline__ void norm_prologue(const Params& p, const float* x_in, const float* branch, const float* w_post,
-                                              const float* w_pre, float* x_out, float* s_vec, float* s_red) {
+                                              const float* w_pre, float* x_out, float* s_vec, float* s_red, Prime prime_next) {
   // one pass: every operand is loaded once, all loads are issued before the first use (one L2 round trip), the two row
   // statistics are two block reductions over registers
   const int H = p.H;
+  // A warp issues in order: a use placed between two loads would stall the second load behind the first one's latency (ncu on
+  // the first version: 36 serialised L2 round trips, ~6 us).  So: every load first (clamped index instead of predicates, nothing
+  // but loads in this loop), the arithmetic afterwards.
   float xv[NB][kNormVec], bv[NB][kNormVec], wq[kNormVec], wp[kNormVec];
+  const float* br = branch ? branch : x_in;               // dummy source when there is no branch (values unused)
+  const float* wpp = branch ? w_post : w_pre;
 #pragma unroll
   for (int j = 0; j < kNormVec; ++j) {
-    const int i = threadIdx.x + j * kThreads;
-    const bool ok = i < H;
-    wq[j] = ok ? 1.f + __ldg(w_pre + i) : 0.f;
-    wp[j] = (ok && branch) ? 1.f + __ldg(w_post + i) : 0.f;
+    const int i = min(threadIdx.x + j * kThreads, H - 1);
+    wq[j] = __ldg(w_pre + i);
+    wp[j] = __ldg(wpp + i);
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-      xv[b][j] = ok ? __ldcg(x_in + b * H + i) : 0.f;
-      bv[b][j] = (ok && branch) ? __ldcg(branch + b * H + i) : 0.f;
+      xv[b][j] = __ldcg(x_in + b * H + i);
+      bv[b][j] = __ldcg(br + b * H + i);
     }
   }
+#pragma unroll
+  for (int j = 0; j < kNormVec; ++j) {
+    const bool ok = threadIdx.x + j * kThreads < H;
+    wq[j] = ok ? 1.f + wq[j] : 0.f;
+    wp[j] = (ok && branch) ? 1.f + wp[j] : 0.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      if (!ok) xv[b][j] = 0.f;
+      if (!ok || !branch) bv[b][j] = 0.f;
+    }
+  }
+  // The weight ring of the following GEMV is primed only now: its bulk copies (110 KB per SM) queue up behind the few small
+  // loads above instead of in front of them (primed before the barrier, the prologue's loads waited ~5 us behind 16 MB of weights)
+  prime_next();
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     if (branch) {
@@ -271,7 +291,6 @@ svla_decode_step_small_kernel(const Params p) {
   const int QW = (hq + 2 * hkv) * kD;
   auto noop = [](int, const float*, bool, const float*) {};
   auto prime = [&](const void* W, int N, int K) { gemv_rows<NB>(static_cast<const __nv_bfloat16*>(W), N, K, s_vec, ring, true, noop); };
-  prime(p.layers[0].wqkv, (hq + 2 * hkv) * kD, H);
   unsigned epoch = 0;
   float* xa = p.x0;
   float* xb = p.x1;
@@ -290,7 +309,7 @@ svla_decode_step_small_kernel(const Params p) {
     const SvlaDecodeLayer L = p.layers[li];
     stamp(li);
     // ---------------------------------------------------------------- phase A: (residual of the previous MLP) + input norm + qkv
-    norm_prologue<NB>(p, xa, prev_dn, prev_post_ff, L.ln_in, prev_dn ? xb : nullptr, s_vec, s_red);
+    norm_prologue<NB>(p, xa, prev_dn, prev_post_ff, L.ln_in, prev_dn ? xb : nullptr, s_vec, s_red, [&]() { prime(L.wqkv, QW, H); });
     if (prev_dn) { float* t = xa; xa = xb; xb = t; }
     stamp(li);
     {
@@ -321,9 +340,17 @@ svla_decode_step_small_kernel(const Params p) {
           const float inv_freq = 1.0f / powf(p.theta, static_cast<float>(2 * j) / static_cast<float>(kD));
           float sn, cs;
           sincosf(static_cast<float>(p.ctx - kstart) * inv_freq, &sn, &cs);
-          for (int g = 0; g <= grp; ++g) {
-            const int col = (g < grp) ? (hk * grp + g) * kD : (hq + hk) * kD;
-            const float x1 = __ldcg(src + col + j), x2 = __ldcg(src + col + j + kD / 2);
+          float xr1[3], xr2[3];
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            const int gg = min(g, grp);
+            const int col = (gg < grp) ? (hk * grp + gg) * kD : (hq + hk) * kD;
+            xr1[g] = __ldcg(src + col + j); xr2[g] = __ldcg(src + col + j + kD / 2);
+          }
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            if (g > grp) continue;
+            const float x1 = xr1[g], x2 = xr2[g];
             const float o1 = bf16r(x1 * cs - x2 * sn), o2 = bf16r(x2 * cs + x1 * sn);
             if (g < grp) { s_q[g * kD + j] = o1; s_q[g * kD + j + kD / 2] = o2; }
             else { s_knew[j] = o1; s_knew[j + kD / 2] = o2; }
@@ -374,17 +401,29 @@ svla_decode_step_small_kernel(const Params p) {
             }
           }
         };
-        for (int j = lo + warp; j < hi; j += kWarps) {
-          float kv[8], vv[8];
-          const uint4 kr = __ldcg(reinterpret_cast<const uint4*>(kc + j * row_stride + lane * 8));
-          const uint4 vr = __ldcg(reinterpret_cast<const uint4*>(vc + j * row_stride + lane * 8));
-          const uint32_t ku[4] = {kr.x, kr.y, kr.z, kr.w}, vu[4] = {vr.x, vr.y, vr.z, vr.w};
+        // this warp's keys, kKeyBatch at a time: all K / V row loads of a batch are issued before the first dot product
+        constexpr int kKeyBatch = 6;
+        for (int j0 = lo + warp; j0 < hi; j0 += kWarps * kKeyBatch) {
+          uint4 kr[kKeyBatch], vr[kKeyBatch];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            kv[2 * i] = bf16_bits_to_float(ku[i] & 0xFFFFu); kv[2 * i + 1] = bf16_bits_to_float(ku[i] >> 16);
-            vv[2 * i] = bf16_bits_to_float(vu[i] & 0xFFFFu); vv[2 * i + 1] = bf16_bits_to_float(vu[i] >> 16);
+          for (int u = 0; u < kKeyBatch; ++u) {
+            const int j = min(j0 + u * kWarps, hi - 1);
+            kr[u] = __ldcg(reinterpret_cast<const uint4*>(kc + j * row_stride + lane * 8));
+            vr[u] = __ldcg(reinterpret_cast<const uint4*>(vc + j * row_stride + lane * 8));
           }
-          visit(kv, vv);
+#pragma unroll
+          for (int u = 0; u < kKeyBatch; ++u) {
+            if (j0 + u * kWarps < hi) {                     // warp-uniform
+              float kv[8], vv[8];
+              const uint32_t ku[4] = {kr[u].x, kr[u].y, kr[u].z, kr[u].w}, vu[4] = {vr[u].x, vr[u].y, vr[u].z, vr[u].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                kv[2 * i] = bf16_bits_to_float(ku[i] & 0xFFFFu); kv[2 * i + 1] = bf16_bits_to_float(ku[i] >> 16);
+                vv[2 * i] = bf16_bits_to_float(vu[i] & 0xFFFFu); vv[2 * i + 1] = bf16_bits_to_float(vu[i] >> 16);
+              }
+              visit(kv, vv);
+            }
+          }
         }
         if (split == kSplits - 1 && warp == 0) {
           float kv[8], vv[8];
@@ -429,13 +468,15 @@ svla_decode_step_small_kernel(const Params p) {
       float* s_f = s_vec + NB * CW;                        // [NB*hq][kSplits]
       for (int i = threadIdx.x; i < NB * hq; i += kThreads) {
         const float* base = p.part + static_cast<long long>(i) * kSplits * (2 + kD);
-        float ms[kSplits], mmax = -INFINITY, den = 0.f;
+        float ms[kSplits], ls[kSplits], mmax = -INFINITY, den = 0.f;
 #pragma unroll
-        for (int sp = 0; sp < kSplits; ++sp) { ms[sp] = __ldcg(base + sp * (2 + kD)); mmax = fmaxf(mmax, ms[sp]); }
+        for (int sp = 0; sp < kSplits; ++sp) { ms[sp] = __ldcg(base + sp * (2 + kD)); ls[sp] = __ldcg(base + sp * (2 + kD) + 1); }
+#pragma unroll
+        for (int sp = 0; sp < kSplits; ++sp) mmax = fmaxf(mmax, ms[sp]);
 #pragma unroll
         for (int sp = 0; sp < kSplits; ++sp) {
           ms[sp] = (ms[sp] == -INFINITY) ? 0.f : __expf(ms[sp] - mmax);
-          den += ms[sp] * __ldcg(base + sp * (2 + kD) + 1);
+          den += ms[sp] * ls[sp];
         }
 #pragma unroll
         for (int sp = 0; sp < kSplits; ++sp) s_f[i * kSplits + sp] = ms[sp] / den;
@@ -444,9 +485,11 @@ svla_decode_step_small_kernel(const Params p) {
       for (int i = threadIdx.x; i < NB * CW; i += kThreads) {
         const int bh = i / kD, dd = i - bh * kD;             // bh = b * hq + head, and i = b * CW + head * kD + dd
         const float* base = p.part + static_cast<long long>(bh) * kSplits * (2 + kD) + 2 + dd;
-        float num = 0.f;
+        float pv[kSplits], num = 0.f;
 #pragma unroll
-        for (int sp = 0; sp < kSplits; ++sp) num = fmaf(s_f[bh * kSplits + sp], __ldcg(base + sp * (2 + kD)), num);
+        for (int sp = 0; sp < kSplits; ++sp) pv[sp] = __ldcg(base + sp * (2 + kD));
+#pragma unroll
+        for (int sp = 0; sp < kSplits; ++sp) num = fmaf(s_f[bh * kSplits + sp], pv[sp], num);
         s_vec[i] = bf16r(num);
       }
       __syncthreads();
@@ -459,13 +502,12 @@ svla_decode_step_small_kernel(const Params p) {
           if (two) o[b * H + n + 1] = a1[b];
         }
       });
-      prime(L.wgu, 2 * FF, H);
     }
     stamp(li);
     grid_barrier(p.barrier, (++epoch) * gridDim.x);
     stamp(li);
     // ---------------------------------------------------------------- phase D: post-attention norm + residual, pre-FF norm, gate/up
-    norm_prologue<NB>(p, xa, p.o, L.ln_post_attn, L.ln_pre_ff, xb, s_vec, s_red);
+    norm_prologue<NB>(p, xa, p.o, L.ln_post_attn, L.ln_pre_ff, xb, s_vec, s_red, [&]() { prime(L.wgu, 2 * FF, H); });
     { float* t = xa; xa = xb; xb = t; }
     stamp(li);
     {
@@ -482,7 +524,16 @@ svla_decode_step_small_kernel(const Params p) {
     stamp(li);
     // ---------------------------------------------------------------- phase E: down projection
     {
-      for (int i = threadIdx.x; i < NB * FF; i += kThreads) s_vec[i] = __ldcg(p.act + i);
+      for (int i0 = 0; i0 < NB * FF; i0 += 12 * kThreads) {          // 12 loads in flight per thread, then the 12 stores
+        float t[12];
+#pragma unroll
+        for (int u = 0; u < 12; ++u) t[u] = __ldcg(p.act + min(i0 + u * kThreads + static_cast<int>(threadIdx.x), NB * FF - 1));
+#pragma unroll
+        for (int u = 0; u < 12; ++u) {
+          const int i = i0 + u * kThreads + threadIdx.x;
+          if (i < NB * FF) s_vec[i] = t[u];
+        }
+      }
       __syncthreads();
       stamp(li);
       float* dn = p.dn;
@@ -493,7 +544,6 @@ svla_decode_step_small_kernel(const Params p) {
           if (two) dn[b * H + n + 1] = a1[b];
         }
       });
-      if (li + 1 < p.n_layers) prime(p.layers[li + 1].wqkv, QW, H);
     }
     stamp(li);
     grid_barrier(p.barrier, (++epoch) * gridDim.x);
@@ -503,7 +553,7 @@ svla_decode_step_small_kernel(const Params p) {
   }
   // ------------------------------------------------------------------ final: last MLP residual + final norm -> h_out (CTA 0)
   if (blockIdx.x == 0) {
-    norm_prologue<NB>(p, xa, prev_dn, prev_post_ff, p.final_w, nullptr, s_vec, s_red);
+    norm_prologue<NB>(p, xa, prev_dn, prev_post_ff, p.final_w, nullptr, s_vec, s_red, []() {});
     for (int i = threadIdx.x; i < NB * H; i += kThreads) p.h_out[i] = __float2bfloat16(s_vec[i]);
   }
 }

@@ -2,6 +2,7 @@
 Usage: SVLA_DECODE_SMALL_TIMING=1 python tools/decode_small_phases.py [batch]"""
 import os, sys
 os.environ.setdefault("SVLA_DECODE_SMALL_TIMING", "1")
+os.environ.setdefault("SVLA_DECODE_SMALL", "1")            # the persistent kernel is opt-in
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch

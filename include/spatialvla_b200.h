@@ -114,6 +114,9 @@ typedef struct SvlaAttnArgs {
                                 layout the engine packs once at load time so that a CTA reads its head's table coalesced) */
   const int32_t* kv_start;   /* device int32 [batch] or NULL: keys j < kv_start[b] are masked for every query of batch row b
                                 (left-padded prompts: attention_mask == 0 columns, model/modeling_spatialvla.py:298-303) */
+  int32_t causal_prefix;     /* with causal = 1: keys j < causal_prefix are visible to EVERY query (prefix-LM mask of the
+                                training forward: token_type_ids == 0 columns unmasked on top of the triangular mask,
+                                model/modeling_spatialvla.py:292-305); 0 = plain causal */
 } SvlaAttnArgs;
 
 int svla_attention(const SvlaAttnArgs* args, void* stream);
@@ -188,6 +191,17 @@ int svla_embed_tokens(const int64_t* ids, const void* embed, const void* spatial
  * out_ids[b*out_stride] = argmax_j logits[b, j] + id_offset (first max wins, like torch.argmax) */
 int svla_argmax_rows(const float* logits, int64_t rows, int64_t cols, int64_t ld, int64_t id_offset,
                      int64_t* out_ids, int64_t out_stride, void* stream);
+
+/* M8: cross entropy over full-vocabulary logit rows -- the loss of the training / evaluation forward
+ * (model/modeling_spatialvla.py:413-430: shift, drop ignore_index rows, nn.CrossEntropyLoss mean).  The logit rows of a big
+ * batch are produced chunk by chunk: logits fp32 [rows, ld] (post-softcap) holds entries [row_offset, row_offset + rows) of the
+ * FULL arrays labels int64 / row_loss fp32 / row_argmax int64.  row_loss[i] = logsumexp(logits row) - logit[labels[i]] (0 where
+ * labels[i] == ignore_index, NaN where a label is out of range), row_argmax[i] = first maximal column.  summary (NULL except
+ * on the last chunk) fp32 [3] = { mean of row_loss over the non-ignored entries of [0, row_offset + rows), their count, entries
+ * whose argmax equals the label } (token accuracy of train/monkey_patch.py:267-324). One launch per chunk + one for the summary. */
+int svla_cross_entropy_rows(const float* logits, int64_t rows, int64_t cols, int64_t ld, const int64_t* labels,
+                            int64_t ignore_index, float* row_loss, int64_t* row_argmax, int64_t row_offset, float* summary,
+                            void* stream);
 
 /* M9 image preprocessing.
  * siglip: (x-0.5)/0.5 + im2col for the 14x14/14 patch conv (model/modeling_spatialvla.py:309;

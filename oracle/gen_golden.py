@@ -177,11 +177,51 @@ def gen_model_padded(n_new=6):
     print("tiny_model_padded: tokens", toks.tolist())
 
 
+def train_inputs(B=2, T=6, n_act=6, seed=2):
+    """Training-shaped samples (train/monkey_patch.py:21-75, data/dataset.py:145-153): prefix = image tokens + BOS + text +
+    newline (token type 0, labels -100), suffix = action tokens + EOS (token type 1, labels = ids)."""
+    cfg, px_u8, ids, K = tiny_inputs(B=B, T=T, seed=seed)
+    g = torch.Generator().manual_seed(seed + 200)
+    lo = cfg["action_token_begin_idx"]
+    suffix = torch.cat([torch.randint(lo, lo + cfg["spatial_token_num"], (B, n_act), generator=g),
+                        torch.full((B, 1), cfg["eos_token_id"])], 1)
+    full = torch.cat([ids, suffix], 1)
+    P = ids.shape[1]
+    tt = torch.cat([torch.zeros(B, P, dtype=torch.int64), torch.ones(B, suffix.shape[1], dtype=torch.int64)], 1)
+    labels = torch.where(tt == 1, full, torch.full_like(full, -100))
+    return cfg, px_u8, full, tt, labels, K
+
+
+def gen_model_train():
+    """forward(labels=...) of the live reference under its three masks -> tests/golden/tiny_model_train.npz:
+    prefix-LM (token_type_ids + 2-D attention_mask), triangular (token_type_ids, no attention_mask), bidirectional (labels only)."""
+    cfg, px_u8, ids, tt, labels, K = train_inputs()
+    px = px_u8.float() / 255.0
+    model = compat.build_reference_model(cfg)
+    model.load_state_dict(synth_state_dict(cfg, seed=0), strict=True)
+    B, L = ids.shape
+    out = {}
+    bi, ti = torch.nonzero(labels[:, 1:] != -100, as_tuple=True)
+    with torch.no_grad():
+        for name, kw in (("prefix_lm", dict(token_type_ids=tt, attention_mask=torch.ones(B, L, dtype=torch.int64))),
+                         ("causal", dict(token_type_ids=tt)), ("bidirectional", dict())):
+            o = model(input_ids=ids, pixel_values=px, intrinsic=K, labels=labels, use_cache=False, **kw)
+            out["loss_" + name] = o.loss.float().numpy()
+            out["logits_" + name] = o.logits.float()[bi, ti].numpy().astype(np.float32)      # labelled rows, full vocabulary
+            print(f"tiny_model_train[{name}]: loss {float(o.loss):.6f}")
+    np.savez_compressed(os.path.join(GOLD, "tiny_model_train.npz"), pixel_u8=px_u8.numpy(), input_ids=ids.numpy(),
+                        token_type_ids=tt.numpy(), labels=labels.numpy(), intrinsic=K.numpy(), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "padded":
         gen_model_padded()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        gen_model_train()
+        sys.exit(0)
     gen_tokenizer()
     gen_model()
     gen_model_padded()
+    gen_model_train()

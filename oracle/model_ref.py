@@ -372,7 +372,7 @@ def padded_positions(pos_start, S, pads):
     return torch.where(slot < pads[:, None], torch.full_like(pos, 2), pos)
 
 
-def gemma2_forward(sd, cfg, x, pos_start, kv_cache, bidirectional, pads=None):
+def gemma2_forward(sd, cfg, x, pos_start, kv_cache, bidirectional, pads=None, causal_prefix=0):
     """model/modeling_gemma2.py:364-413 (attention), :451-506 (sandwich-norm layer), :680-793 (stack),
     :993-997 (lm_head + final softcap is applied by the caller on the rows it keeps).
     x (B,S,H) already scaled; positions are pos_start+1 ... (1-indexed, model/modeling_spatialvla.py:371-372).
@@ -406,7 +406,9 @@ def gemma2_forward(sd, cfg, x, pos_start, kv_cache, bidirectional, pads=None):
             sc = torch.tanh(sc / cap) * cap
         if not bidirectional and S > 1:
             L = K.shape[2]
-            mask = torch.arange(L)[None, :] > (torch.arange(S)[:, None] + (L - S))
+            # causal_prefix > 0: prefix-LM mask of the training forward -- token_type_ids == 0 columns are unmasked on top of the
+            # triangular mask (model/modeling_spatialvla.py:292-293,304-305)
+            mask = torch.arange(L)[None, :] > torch.clamp(torch.arange(S)[:, None] + (L - S), min=causal_prefix - 1)
             sc = sc.masked_fill(mask, float("-inf"))
         if pads is not None:
             sc = sc.masked_fill((torch.arange(K.shape[2])[None, :] < pads[:, None])[:, None, None, :], float("-inf"))
@@ -470,3 +472,44 @@ def predict_action_ref(sd, cfg, input_ids, pixel_values, intrinsic, n_new, force
         aux["image_features"] = feats
         return out + (aux,)
     return out
+
+
+def prefix_length(token_type_ids):
+    """(B, L) token types -> p such that every row is p zeros followed by L - p ones (prefix / suffix of the training samples,
+    train/monkey_patch.py:21-75); raises for any other pattern."""
+    tt = token_type_ids.to(torch.int64).cpu()
+    p = int((tt[0] == 0).sum())
+    expect = (torch.arange(tt.shape[1])[None, :] >= p).to(torch.int64).expand_as(tt)
+    if not torch.equal(tt, expect):
+        raise NotImplementedError("token_type_ids must be 0...01...1 with the same prefix length in every row")
+    return p
+
+
+def forward_loss_ref(sd, cfg, input_ids, pixel_values, intrinsic, labels, token_type_ids=None, attention_mask=None,
+                     force_head=None, ignore_index=-100, pad_token_id=0):
+    """forward() with labels = model/modeling_spatialvla.py:335-430.  Mask (`_update_causal_mask`, :258-306): training
+    (token_type_ids and labels given) = triangular, plus -- only when a 2-D attention_mask is passed -- every token_type 0
+    column unmasked (prefix-LM); labels without token_type_ids = the inference mask (bidirectional).  Loss = shifted
+    nn.CrossEntropyLoss over the full vocabulary, post-softcap logits, ignore_index rows dropped (:413-430).
+    Returns (loss 0-dim fp32, flat row indices b*L+t of the labelled rows, their labels, their logits fp32 [R, V])."""
+    if attention_mask is not None and bool((attention_mask == 0).any()):
+        raise NotImplementedError("padded batches are not covered by the labelled forward")
+    with torch.no_grad():
+        feats = image_features(sd, cfg, pixel_values, intrinsic, force_head) if pixel_values is not None else None
+        x = embed_inputs(sd, cfg, input_ids, feats)
+        B, L, _ = x.shape
+        cache = [None] * cfg["text_config"]["num_hidden_layers"]
+        if token_type_ids is not None:
+            prefix = prefix_length(token_type_ids) if attention_mask is not None else 0
+            h = gemma2_forward(sd, cfg, x, 0, cache, bidirectional=False, causal_prefix=prefix)
+        else:
+            h = gemma2_forward(sd, cfg, x, 0, cache, bidirectional=True)
+        if bool((labels == pad_token_id).any()):                       # :392-397
+            labels = torch.where(input_ids == pad_token_id, torch.full_like(labels, ignore_index), labels)
+        shift_labels = labels[:, 1:]
+        bi, ti = torch.nonzero(shift_labels != ignore_index, as_tuple=True)
+        rows = bi * L + ti
+        lab = shift_labels[bi, ti]
+        lg = lm_head_slice(sd, cfg, h.reshape(B * L, -1)[rows], 0, cfg["text_config"]["vocab_size"]).float()
+        loss = F.cross_entropy(lg, lab) if rows.numel() else torch.tensor(float("nan"))
+    return loss, rows, lab, lg

@@ -135,7 +135,8 @@ class RefOps:
         return t.as_strided((batch, s, heads, d), (bs, ss, d, 1), t.storage_offset())
 
     def attention(self, q, k, v, out, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
-                  scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0, relpos_head_major=False, kv_start=None):
+                  scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0, relpos_head_major=False, kv_start=None,
+                  causal_prefix=0):
         self.launches += 1
         Q = self._strided(q, *q_strides, batch, sq, hq, d).float().permute(0, 2, 1, 3)
         K = self._strided(k, *k_strides, batch, sk, hkv, d).float().permute(0, 2, 1, 3).repeat_interleave(hq // hkv, 1)
@@ -151,7 +152,8 @@ class RefOps:
         if kv_start is not None:
             s = s.masked_fill((torch.arange(sk)[None, :] < kv_start.long()[:, None])[:, None, None, :], float("-inf"))
         if causal:
-            m = torch.arange(sk)[None, :] > (torch.arange(sq)[:, None] + (sk - sq))
+            # prefix-LM (training forward, model/modeling_spatialvla.py:292-305): keys < causal_prefix stay visible
+            m = torch.arange(sk)[None, :] > torch.clamp(torch.arange(sq)[:, None] + (sk - sq), min=causal_prefix - 1)
             s = s.masked_fill(m, float("-inf"))
         # the kernel rounds the un-normalised probabilities to bf16 and divides by the fp32 row sum
         mx = s.max(-1, keepdim=True).values
@@ -247,6 +249,20 @@ class RefOps:
     def argmax_rows(self, logits, out_ids, *, id_offset=0):
         self.launches += 1
         out_ids.copy_(logits.argmax(-1) + id_offset)
+
+    def cross_entropy_rows(self, logits, labels, row_loss, row_argmax, *, row_offset=0, summary=None, ignore_index=-100):
+        """nn.CrossEntropyLoss pieces of model/modeling_spatialvla.py:413-430 on already selected rows (chunked like the kernel)."""
+        self.launches += 1 if summary is None else 2
+        r = logits.shape[0]
+        lab = labels[row_offset:row_offset + r]
+        row_loss[row_offset:row_offset + r] = F.cross_entropy(logits.float(), lab, ignore_index=ignore_index, reduction="none")
+        row_argmax[row_offset:row_offset + r] = logits.argmax(-1)
+        if summary is not None:
+            n = row_offset + r
+            valid = labels[:n] != ignore_index
+            summary[0] = row_loss[:n][valid].sum() / valid.sum()
+            summary[1] = valid.sum()
+            summary[2] = (row_argmax[:n][valid] == labels[:n][valid]).sum()
 
     def siglip_patchify(self, px, a):
         self.launches += 1

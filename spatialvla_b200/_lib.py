@@ -51,7 +51,7 @@ class SvlaAttnArgs(C.Structure):
         ("batch", C.c_int32), ("hq", C.c_int32), ("hkv", C.c_int32), ("sq", C.c_int32), ("sk", C.c_int32),
         ("d", C.c_int32), ("scale", C.c_float), ("softcap", C.c_float), ("causal", C.c_int32),
         ("relpos_table", C.c_void_p), ("relpos_win", C.c_int32), ("relpos_head_major", C.c_int32),
-        ("kv_start", C.c_void_p),
+        ("kv_start", C.c_void_p), ("causal_prefix", C.c_int32),
     ]
 
 
@@ -75,6 +75,7 @@ SIGNATURES = {
     "svla_rope_kv": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _I, _L, _P, _P]),
     "svla_embed_tokens": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _L, _I, _F, _P, _P]),
     "svla_argmax_rows": (_I, [_P, _L, _L, _L, _L, _P, _L, _P]),
+    "svla_cross_entropy_rows": (_I, [_P, _L, _L, _L, _P, _L, _P, _P, _L, _P, _P]),
     "svla_siglip_patchify": (_I, [_P, _P, _I, _I, _P]),
     "svla_zoe_patchify": (_I, [_P, _P, _I, _P]),
     "svla_beit_assemble": (_I, [_P, _P, _P, _I, _I, _I, _P]),

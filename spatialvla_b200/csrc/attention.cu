@@ -72,6 +72,7 @@ struct AttnP {
   int head_major;
   const int* kv_start;
   int win;
+  int prefix;          // causal only: keys < prefix are visible to every query (prefix-LM)
 };
 
 // Loads rows [r0, r0+ROWS) x d (bf16) of a [s, ...] strided matrix into smem [ROWS][DP+8]; rows >= s are zeroed.
@@ -263,7 +264,7 @@ svla_flash_attn_kernel(const AttnP p) {
         for (int e = 0; e < 4; ++e) {
           const int qi = qi0 + (e >> 1) * 8;
           const int kj = jt * kBKV + nt * 8 + 2 * t + (e & 1);
-          const bool masked = (kj >= p.sk) || (kj < kstart) || (f_causal && kj > qi + causal_off);
+          const bool masked = (kj >= p.sk) || (kj < kstart) || (f_causal && kj > max(qi + causal_off, p.prefix - 1));
           s[nt][e] = masked ? -INFINITY : s[nt][e];
         }
       }
@@ -716,6 +717,7 @@ extern "C" int svla_attention(const SvlaAttnArgs* a, void* stream) {
   p.o_bs = a->o_bs; p.o_ss = a->o_ss;
   p.hq = a->hq; p.hkv = a->hkv; p.sq = a->sq; p.sk = a->sk; p.d = a->d;
   p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.relpos = a->relpos_table; p.win = a->relpos_win; p.head_major = a->relpos_head_major; p.kv_start = a->kv_start;
+  p.prefix = a->causal ? a->causal_prefix : 0;
   const int mode = (p.relpos ? 1 : 0) | (p.softcap > 0.f ? 2 : 0) | (p.causal ? 4 : 0);
   if (a->d <= 32) return launch_attn<32, 8>(p, a->batch, st);
   if (a->d <= 64) return mode == 1 ? launch_attn<64, 1>(p, a->batch, st) : launch_attn<64, 8>(p, a->batch, st);

@@ -44,6 +44,7 @@ struct Params {
   int win;
   int head_major;      // relpos is [hq][nrel] (coalesced per-head row) instead of HF's [nrel][hq]
   const int* kv_start; // [batch] or null: keys < kv_start[b] are masked (left-padded prompts)
+  int prefix;          // causal only: keys < prefix are visible to every query (prefix-LM training mask)
 };
 
 template <int D> struct Cfg {
@@ -149,7 +150,7 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
   const int hk = h / (p.hq / p.hkv);
   const int causal_off = p.sk - p.sq;
   int n_tiles = (p.sk + BKV - 1) / BKV;
-  if (kCausal) n_tiles = max(1, min(n_tiles, (min(q0 + kBQ, p.sq) + causal_off + BKV - 1) / BKV));   // tiles above the diagonal are skipped
+  if (kCausal) n_tiles = max(1, min(n_tiles, (max(min(q0 + kBQ, p.sq) + causal_off, p.prefix) + BKV - 1) / BKV));   // tiles above the diagonal are skipped
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -336,7 +337,7 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
 #pragma unroll
         for (int i = 0; i < HC; ++i) {
           const int kj = k0 + i;
-          if (kj >= p.sk || kj < kstart || (kCausal && kj > qi + causal_off)) s[i] = -INFINITY;
+          if (kj >= p.sk || kj < kstart || (kCausal && kj > max(qi + causal_off, p.prefix - 1))) s[i] = -INFINITY;
         }
       }
       float mj = -INFINITY;
@@ -487,6 +488,7 @@ int svla_attention_tc_try(const SvlaAttnArgs* a, void* stream) {
   p.o_bs = a->o_bs; p.o_ss = a->o_ss;
   p.hq = a->hq; p.hkv = a->hkv; p.sq = a->sq; p.sk = a->sk; p.d = a->d;
   p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.relpos = a->relpos_table; p.win = a->relpos_win; p.head_major = a->relpos_head_major; p.kv_start = a->kv_start;
+  p.prefix = a->causal ? a->causal_prefix : 0;
   // a batch stride of 0 is not expressible in a tensor map; batch == 1 problems get a dummy stride
   const uint64_t nb = static_cast<uint64_t>(a->batch);
   auto bstride = [&](int64_t bs, int64_t ss, int s) { return static_cast<uint64_t>(nb > 1 ? bs : ss * s); };

@@ -428,6 +428,109 @@ svla_argmax_kernel(const float* __restrict__ logits, long long cols, long long l
   }
 }
 
+// ------------------------------------------------------------------------------------------ M8 cross entropy over logit rows
+// Training / evaluation forward (model/modeling_spatialvla.py:413-430): nn.CrossEntropyLoss over the labelled rows of the
+// post-softcap full-vocabulary logits.  One CTA per row (a 265 347-column fp32 row is 1.06 MB): one pass with a per-thread
+// online (max, sum exp) pair and the running argmax, 128-bit loads on the 16-byte aligned body of the row (rows of an odd
+// vocabulary are not 16-byte aligned: scalar head / tail), warp-shuffle + shared-memory combine.  HBM-bound: rows * cols * 4 B.
+struct CeAcc {
+  float m, s, best;
+  long long bi;
+};
+__device__ __forceinline__ void ce_push(CeAcc& a, float v, long long j) {
+  if (v > a.best || (v == a.best && j < a.bi)) { a.best = v; a.bi = j; }
+  if (v > a.m) {
+    a.s = a.s * expf(a.m - v) + 1.f;      // a.m == -inf: a.s is 0 and expf(-inf) = 0
+    a.m = v;
+  } else {
+    a.s += expf(v - a.m);
+  }
+}
+__device__ __forceinline__ void ce_merge(CeAcc& a, float m2, float s2, float b2, long long i2) {
+  if (b2 > a.best || (b2 == a.best && i2 < a.bi)) { a.best = b2; a.bi = i2; }
+  const float M = fmaxf(a.m, m2);
+  if (M == -INFINITY) return;             // both empty
+  a.s = a.s * expf(a.m - M) + s2 * expf(m2 - M);
+  a.m = M;
+}
+
+constexpr int kCeThreads = 512;
+
+__global__ void __launch_bounds__(kCeThreads)
+svla_cross_entropy_kernel(const float* __restrict__ logits, long long cols, long long ld, const long long* __restrict__ labels,
+                          long long ignore_index, float* __restrict__ row_loss, long long* __restrict__ row_argmax) {
+  __shared__ float sm_m[kCeThreads / 32], sm_s[kCeThreads / 32], sm_b[kCeThreads / 32];
+  __shared__ long long sm_i[kCeThreads / 32];
+  const long long row = blockIdx.x;
+  const float* r = logits + row * ld;
+  CeAcc a{-INFINITY, 0.f, -INFINITY, 0x7fffffffffffffffLL};
+  long long head = static_cast<long long>(((16 - (reinterpret_cast<uintptr_t>(r) & 15)) & 15) >> 2);
+  if (head > cols) head = cols;
+  if (threadIdx.x < head) ce_push(a, r[threadIdx.x], threadIdx.x);
+  const long long nvec = (cols - head) >> 2;
+  const float4* rv = reinterpret_cast<const float4*>(r + head);
+  for (long long i = threadIdx.x; i < nvec; i += kCeThreads) {
+    const float4 v = __ldg(rv + i);
+    const long long j = head + 4 * i;
+    ce_push(a, v.x, j);
+    ce_push(a, v.y, j + 1);
+    ce_push(a, v.z, j + 2);
+    ce_push(a, v.w, j + 3);
+  }
+  const long long tail0 = head + 4 * nvec;
+  if (tail0 + threadIdx.x < cols) ce_push(a, r[tail0 + threadIdx.x], tail0 + threadIdx.x);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, a.m, o), s2 = __shfl_xor_sync(0xffffffffu, a.s, o);
+    const float b2 = __shfl_xor_sync(0xffffffffu, a.best, o);
+    const long long i2 = __shfl_xor_sync(0xffffffffu, a.bi, o);
+    ce_merge(a, m2, s2, b2, i2);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sm_m[warp] = a.m; sm_s[warp] = a.s; sm_b[warp] = a.best; sm_i[warp] = a.bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kCeThreads / 32; ++w) ce_merge(a, sm_m[w], sm_s[w], sm_b[w], sm_i[w]);
+    const long long lab = labels[row];
+    float loss = 0.f;
+    if (lab != ignore_index) loss = (lab >= 0 && lab < cols) ? (a.m + logf(a.s)) - r[lab] : __int_as_float(0x7fc00000);
+    row_loss[row] = loss;
+    row_argmax[row] = a.bi;
+  }
+}
+
+// summary[0] = mean of row_loss over the non-ignored rows (NaN when there is none, like torch), [1] = their count,
+// [2] = rows whose argmax equals the label.  One CTA, fixed summation order: deterministic.
+__global__ void __launch_bounds__(256)
+svla_cross_entropy_summary_kernel(const float* __restrict__ row_loss, const long long* __restrict__ row_argmax,
+                                  const long long* __restrict__ labels, long long rows, long long ignore_index,
+                                  float* __restrict__ summary) {
+  __shared__ float s_sum[256], s_cnt[256], s_hit[256];
+  float sum = 0.f, cnt = 0.f, hit = 0.f;
+  for (long long i = threadIdx.x; i < rows; i += 256) {
+    if (labels[i] != ignore_index) {
+      sum += row_loss[i];
+      cnt += 1.f;
+      hit += (row_argmax[i] == labels[i]) ? 1.f : 0.f;
+    }
+  }
+  s_sum[threadIdx.x] = sum; s_cnt[threadIdx.x] = cnt; s_hit[threadIdx.x] = hit;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+      s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o];
+      s_hit[threadIdx.x] += s_hit[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    summary[0] = s_sum[0] / s_cnt[0];
+    summary[1] = s_cnt[0];
+    summary[2] = s_hit[0];
+  }
+}
+
 // ------------------------------------------------------------------------------------------ bicubic helpers (A = -0.75)
 __device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
   const float A = -0.75f;
@@ -1198,6 +1301,27 @@ extern "C" int svla_argmax_rows(const float* logits, int64_t rows, int64_t cols,
                                    reinterpret_cast<long long*>(out_ids), static_cast<long long>(out_stride));
   SVLA_REQUIRE(le == cudaSuccess, "svla_argmax_rows: launch failed: %s", cudaGetErrorString(le));
   SVLA_LAUNCH_CHECK("svla_argmax_rows");
+  return 0;
+}
+
+extern "C" int svla_cross_entropy_rows(const float* logits, int64_t rows, int64_t cols, int64_t ld, const int64_t* labels,
+                                       int64_t ignore_index, float* row_loss, int64_t* row_argmax, int64_t row_offset, float* summary,
+                                       void* stream) {
+  SVLA_REQUIRE(logits && labels && row_loss && row_argmax, "svla_cross_entropy_rows: null operand");
+  SVLA_REQUIRE(rows > 0 && cols > 0 && ld >= cols && row_offset >= 0, "svla_cross_entropy_rows: bad shape (rows %lld cols %lld ld %lld)",
+               static_cast<long long>(rows), static_cast<long long>(cols), static_cast<long long>(ld));
+  SVLA_REQUIRE((reinterpret_cast<uintptr_t>(logits) & 3) == 0, "svla_cross_entropy_rows: logits must be 4-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  svla_cross_entropy_kernel<<<static_cast<unsigned>(rows), kCeThreads, 0, st>>>(
+      logits, static_cast<long long>(cols), static_cast<long long>(ld), reinterpret_cast<const long long*>(labels) + row_offset,
+      static_cast<long long>(ignore_index), row_loss + row_offset, reinterpret_cast<long long*>(row_argmax) + row_offset);
+  SVLA_LAUNCH_CHECK("svla_cross_entropy_rows");
+  if (summary) {
+    svla_cross_entropy_summary_kernel<<<1, 256, 0, st>>>(row_loss, reinterpret_cast<const long long*>(row_argmax),
+                                                         reinterpret_cast<const long long*>(labels),
+                                                         static_cast<long long>(row_offset + rows), static_cast<long long>(ignore_index), summary);
+    SVLA_LAUNCH_CHECK("svla_cross_entropy_summary");
+  }
   return 0;
 }
 

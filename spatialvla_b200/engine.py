@@ -563,11 +563,13 @@ class SpatialVLAEngine:
         cache["len"] = pos0 + 1
         return h
 
-    def gemma_forward(self, x, B, S, cache, bidirectional, pads=None):
+    def gemma_forward(self, x, B, S, cache, bidirectional, pads=None, causal_prefix=0):
         """x fp32 [B*S, H] (already scaled by sqrt(H)) -> final-normed hidden bf16 [B*S, H]; appends to the cache.
         pads: int32 [B] device tensor or None -- leading padding tokens per row of a left-padded batch: those cache slots are
         masked as keys and the RoPE positions restart at 1 on each row's first real token (model/modeling_spatialvla.py:298-303,
-        model/modeling_gemma2.py:1042-1051)."""
+        model/modeling_gemma2.py:1042-1051).
+        causal_prefix (with bidirectional=False): keys < causal_prefix stay visible to every query -- the prefix-LM mask of the
+        training forward (model/modeling_spatialvla.py:292-293,304-305)."""
         ops, g, t = self.ops, self.gem, self.t
         H, nh, nkv, hd, FF = t["hidden_size"], t["num_attention_heads"], t["num_key_value_heads"], t["head_dim"], t["intermediate_size"]
         eps, theta = t["rms_norm_eps"], float(t.get("rope_theta", 10000.0))
@@ -605,7 +607,7 @@ class SpatialVLAEngine:
                 kvs = (smax * nkv * hd, nkv * hd)
                 ops.attention(q, kc, vc, ctx, batch=B, hq=nh, hkv=nkv, sq=S, sk=pos0 + S, d=hd, q_strides=(S * nh * hd, nh * hd),
                               k_strides=kvs, v_strides=kvs, o_strides=(S * nh * hd, nh * hd), scale=scale, softcap=cap,
-                              causal=not bidirectional, kv_start=pads)
+                              causal=not bidirectional, kv_start=pads, causal_prefix=0 if bidirectional else causal_prefix)
             br = self._skinny_partial(ctx, L_["wo"], M) if skinny else self._lin(ctx, L_["wo"], M, F32)
             ops.rmsnorm_residual(x, branch=br, w_post=L_["ln_post_attn"], w_pre=L_["ln_pre_ff"], eps=eps, out_bf16=h)
             if skinny:
@@ -641,6 +643,31 @@ class SpatialVLAEngine:
         else:
             self.ops.gemm(h_rows, self.gem["head_act"], out_f32=lg, act=ACT_SOFTCAP if cap else ACT_NONE, act_param=cap or 0.0)
         return lg
+
+    loss_chunk_rows = 4096       # labelled rows per lm_head GEMM + cross-entropy launch (fp32 logits: 4096 x 265 347 x 4 B = 4.3 GB)
+
+    def labelled_loss(self, h, rows, row_labels, ignore_index=-100, keep_logits=True):
+        """Loss of the training / evaluation forward (model/modeling_spatialvla.py:413-430) on already selected rows.
+        h bf16 [B*L, H] final-normed hidden states; rows int64 [R] flat indices of the positions whose NEXT token is labelled;
+        row_labels int64 [R].  Full-vocabulary lm_head GEMM with the soft-cap epilogue, then the cross-entropy kernel, chunk by
+        chunk so the fp32 logits of a big batch never exceed a few GB.
+        Returns (summary fp32 [3] = mean loss / labelled rows / argmax hits, row_loss [R], row_argmax [R], logits [R, V] | None)."""
+        ops = self.ops
+        R, V = rows.shape[0], self.t["vocab_size"]
+        cap = self.t["final_logit_softcapping"]
+        hr = h.index_select(0, rows)                   # gather of the labelled rows (plumbing)
+        row_loss, row_argmax, summary = ops.empty((R,), F32), ops.empty((R,), torch.int64), ops.empty((3,), F32)
+        w = self.lm_head_full()
+        kept = None
+        for r0 in range(0, R, self.loss_chunk_rows):
+            r1 = min(R, r0 + self.loss_chunk_rows)
+            lg = ops.empty((r1 - r0, V), F32)
+            ops.gemm(hr[r0:r1], w, out_f32=lg, act=ACT_SOFTCAP if cap else ACT_NONE, act_param=cap or 0.0)
+            ops.cross_entropy_rows(lg, row_labels, row_loss, row_argmax, row_offset=r0, summary=summary if r1 == R else None,
+                                   ignore_index=ignore_index)
+            if keep_logits and R <= self.loss_chunk_rows:
+                kept = lg
+        return summary, row_loss, row_argmax, kept
 
     def language_stage(self, ids, feats, n_new, forced_tokens=None, logs=None, pads=None):
         """Embed + bidirectional prefill + n_new greedy action tokens (argmax over the action slice) -> int64 [B, n_new]"""

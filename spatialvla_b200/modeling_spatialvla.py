@@ -9,8 +9,12 @@ Differences from the reference, all deliberate and documented in DESIGN.md:
     EOS stop (north_star: "argmax restricted to the action vocabulary"); `max_new_tokens` can be passed.
   * inputs stay fp32 (the reference rounds pixel_values *and* the intrinsic matrix to bf16 at :489).
   * LEFT-padded batches (attention_mask = 0...01...1, the Gemma tokenizer's padding side) are supported with the reference's
-    semantics (padded key columns masked, positions restart on the first real token); any other mask pattern and the
-    training-time prefix-LM mask / loss raise NotImplementedError instead of silently mis-computing.
+    semantics (padded key columns masked, positions restart on the first real token); any other mask pattern raises
+    NotImplementedError instead of silently mis-computing.
+  * `forward(labels=..., token_type_ids=...)` -- the forward half of the training step -- computes the
+    reference's loss with its training masks (triangular, or prefix-LM when a 2-D attention_mask is passed) but materialises
+    logits only for the labelled rows ([R, V] instead of [B, L, V]); padded batches raise NotImplementedError on this path
+    (the reference un-masks padded prefix columns there, :304-305).  There is no backward pass yet.
 """
 from __future__ import annotations
 
@@ -34,6 +38,10 @@ class SpatialVLACausalLMOutputWithPast:
     hidden_states: Optional[tuple] = None
     attentions: Optional[tuple] = None
     image_hidden_states: Optional[torch.Tensor] = None
+    # labelled forward only (this build materialises logits for the labelled rows, not [B, L, V]):
+    label_rows: Optional[torch.Tensor] = None        # int64 [R] flat positions b*L + t whose next token is labelled
+    row_loss: Optional[torch.Tensor] = None          # fp32 [R] per-row cross entropy
+    token_accuracy: Optional[torch.Tensor] = None    # 0-dim fp32: argmax == label over the labelled rows
 
 
 class SpatialVLAForConditionalGeneration:
@@ -163,8 +171,12 @@ class SpatialVLAForConditionalGeneration:
                 num_logits_to_keep: int = 0):
         """Inference forward (model/modeling_spatialvla.py:335-442): full-vocabulary post-softcap logits (fp32) for the
         last `num_logits_to_keep` positions (0 = all). `past_key_values` is this engine's cache dict."""
-        if labels is not None or token_type_ids is not None:
-            raise NotImplementedError("training forward (labels / prefix-LM mask) is not part of this path yet")
+        if labels is not None:
+            if past_key_values is not None or inputs_embeds is not None or position_ids is not None or output_attentions or output_hidden_states:
+                raise NotImplementedError("labelled forward: past_key_values / inputs_embeds / position_ids / output_* are not supported")
+            return self._forward_with_labels(input_ids, pixel_values, intrinsic, attention_mask, token_type_ids, labels)
+        if token_type_ids is not None:
+            pass                                 # without labels the reference ignores token types (is_training False, :357)
         if inputs_embeds is not None or position_ids is not None or output_attentions or output_hidden_states:
             raise NotImplementedError("inputs_embeds / position_ids / output_attentions / output_hidden_states")
         eng = self.engine
@@ -191,5 +203,54 @@ class SpatialVLAForConditionalGeneration:
             raise ValueError("Number of images does not match number of special image tokens in the input text.")
         return SpatialVLACausalLMOutputWithPast(logits=logits.view(B, keep, V), past_key_values=cache,
                                                 image_hidden_states=feats)
+
+    def _forward_with_labels(self, input_ids, pixel_values, intrinsic, attention_mask, token_type_ids, labels):
+        """Loss forward = model/modeling_spatialvla.py:335-430 with labels.  Mask (`_update_causal_mask`, :258-306):
+        token_type_ids given (is_training) -> triangular, plus every token_type 0 column unmasked when a 2-D attention_mask
+        is passed (prefix-LM); labels alone -> the bidirectional inference mask.  Loss: shifted nn.CrossEntropyLoss over the
+        full vocabulary on the post-softcap logits, ignore_index rows dropped, pad-token labels masked (:389-397)."""
+        eng = self.engine
+        ignore = -100 if self.config is None else getattr(self.config, "_ignore_index", -100)
+        pad_id = self.engine_config.get("pad_token_id")
+        pad_id = -1 if pad_id is None else pad_id
+        B, L = input_ids.shape
+        if tuple(labels.shape) != (B, L):
+            raise ValueError(f"labels shape {tuple(labels.shape)} != input_ids shape {(B, L)}")
+        if attention_mask is not None and (attention_mask.dim() != 2 or bool((attention_mask == 0).any())):
+            raise NotImplementedError("labelled forward: only unpadded batches (attention_mask None or all ones)")
+        bidirectional, prefix = True, 0
+        if token_type_ids is not None:
+            bidirectional = False
+            if attention_mask is not None:
+                tt = token_type_ids.to("cpu", torch.int64)
+                if tuple(tt.shape) != (B, L):
+                    raise ValueError("token_type_ids shape != input_ids shape")
+                prefix = int((tt[0] == 0).sum())
+                if not bool(torch.equal(tt, (torch.arange(L)[None, :] >= prefix).to(torch.int64).expand(B, L))):
+                    raise NotImplementedError("token_type_ids must be 0...01...1 with the same prefix length in every row")
+        # label bookkeeping on the host (labels arrive from the data collator on the CPU): shifted positions that carry a label
+        lab = labels.to("cpu", torch.int64)
+        ids_cpu = input_ids.to("cpu", torch.int64)
+        if bool((lab == pad_id).any()):
+            lab = torch.where(ids_cpu == pad_id, torch.full_like(lab, ignore), lab)
+        shift = lab[:, 1:]
+        bi, ti = torch.nonzero(shift != ignore, as_tuple=True)
+        row_labels = shift[bi, ti]
+        if row_labels.numel() and (int(row_labels.min()) < 0 or int(row_labels.max()) >= self.vocab_size):
+            raise ValueError("labels outside [0, vocab_size)")
+        ids, px, K, _ = self._prepare({"input_ids": input_ids, "pixel_values": pixel_values, "intrinsic": intrinsic})
+        feats = eng.image_features(px, K) if px is not None else None
+        x, status = eng.embed(ids, feats)
+        cache = eng.new_cache(B, L)
+        h = eng.gemma_forward(x, B, L, cache, bidirectional=bidirectional, causal_prefix=prefix)
+        if int(status.item()) == 1:
+            raise ValueError("Number of images does not match number of special image tokens in the input text.")
+        rows = (bi * L + ti).to(self.device)
+        if rows.numel() == 0:                     # nn.CrossEntropyLoss over zero rows is NaN
+            nan = torch.full((), float("nan"), dtype=F32, device=self.device)
+            return SpatialVLACausalLMOutputWithPast(loss=nan, logits=None, image_hidden_states=feats, label_rows=rows)
+        summary, row_loss, _, logits = eng.labelled_loss(h, rows, row_labels.to(self.device).contiguous(), ignore_index=ignore)
+        return SpatialVLACausalLMOutputWithPast(loss=summary[0], logits=logits, image_hidden_states=feats, label_rows=rows,
+                                                row_loss=row_loss, token_accuracy=summary[2] / summary[1])
 
     __call__ = forward

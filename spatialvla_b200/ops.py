@@ -137,7 +137,8 @@ class CudaOps:
 
     # ---- G2 / G3
     def attention(self, q, k, v, out, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
-                  scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0, relpos_head_major=False, kv_start=None):
+                  scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0, relpos_head_major=False, kv_start=None,
+                  causal_prefix=0):
         """strides = (batch stride, token stride) in elements; head h lives at column offset h*d.
         relpos_table: fp32 [(2*win-1)^2+3, hq] (HF layout) or, with relpos_head_major, its transpose [hq, (2*win-1)^2+3]."""
         a = L.SvlaAttnArgs()
@@ -156,6 +157,8 @@ class CudaOps:
         _req(kv_start is None or (kv_start.dtype == torch.int32 and kv_start.is_contiguous() and kv_start.numel() == batch),
              "attention: kv_start must be int32 [batch]")
         a.kv_start = _ptr(kv_start)
+        _req(causal_prefix == 0 or (causal and 0 < causal_prefix <= sk), "attention: causal_prefix needs causal=True and 0 < prefix <= sk")
+        a.causal_prefix = int(causal_prefix)       # prefix-LM: keys < causal_prefix visible to every query
         L.check(self.lib.svla_attention(C.byref(a), self._stream()), "svla_attention")
 
     def decode_attention(self, q, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, scale, softcap=0.0, kv_start=None):
@@ -233,6 +236,21 @@ class CudaOps:
         L.check(self.lib.svla_argmax_rows(_ptr(logits), logits.shape[0], logits.shape[1], logits.stride(0),
                                           int(id_offset), _ptr(out_ids), out_ids.stride(0), self._stream()),
                 "svla_argmax_rows")
+
+    def cross_entropy_rows(self, logits, labels, row_loss, row_argmax, *, row_offset=0, summary=None, ignore_index=-100):
+        """logits fp32 [rows, cols] = entries [row_offset, row_offset+rows) of labels int64 [n] / row_loss fp32 [n] / row_argmax
+        int64 [n]; summary fp32 [3] (last chunk only) <- mean loss over the non-ignored entries so far, their count, argmax hits."""
+        _req(logits.dtype == F32 and logits.dim() == 2 and logits.stride(1) == 1, "cross_entropy_rows: bad logits")
+        n = labels.shape[0]
+        _req(labels.dtype == torch.int64 and labels.dim() == 1 and labels.is_contiguous(), "cross_entropy_rows: labels must be contiguous int64")
+        _req(row_loss.dtype == F32 and row_loss.is_contiguous() and row_loss.shape == (n,), "cross_entropy_rows: row_loss fp32 [n]")
+        _req(row_argmax.dtype == torch.int64 and row_argmax.is_contiguous() and row_argmax.shape == (n,), "cross_entropy_rows: row_argmax int64 [n]")
+        _req(0 <= row_offset and row_offset + logits.shape[0] <= n, "cross_entropy_rows: chunk outside the label array")
+        _req(summary is None or (summary.dtype == F32 and summary.numel() == 3), "cross_entropy_rows: summary fp32 [3]")
+        L.check(self.lib.svla_cross_entropy_rows(_ptr(logits), logits.shape[0], logits.shape[1], logits.stride(0), _ptr(labels),
+                                                 int(ignore_index), _ptr(row_loss), _ptr(row_argmax), int(row_offset), _ptr(summary),
+                                                 self._stream()),
+                "svla_cross_entropy_rows")
 
     def siglip_patchify(self, px, a):
         _req(px.dtype == F32 and px.is_contiguous() and tuple(px.shape[1:]) == (3, 224, 224), "siglip_patchify: px")

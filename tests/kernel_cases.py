@@ -252,7 +252,7 @@ SKINNY_CASES = [
 
 # ------------------------------------------------------------------------------------------------ attention
 def attn_case(name, B, hq, hkv, sq, sk, d, *, scale=None, softcap=0.0, causal=False, relpos_win=0, packed_qkv=False,
-              smax=None, seed=0, head_major=False, kv_start=None):
+              smax=None, seed=0, head_major=False, kv_start=None, causal_prefix=0):
     def case(dev="cuda:0"):
         g = _gen(seed)
         sc = scale if scale is not None else d ** -0.5
@@ -282,7 +282,7 @@ def attn_case(name, B, hq, hkv, sq, sk, d, *, scale=None, softcap=0.0, causal=Fa
                 kvs = (sm * hkv * d, hkv * d)
                 ops.attention(to(q), to(kc), to(vc), out, batch=B, hq=hq, hkv=hkv, sq=sq, sk=sk, d=d,
                               q_strides=(sq * hq * d, hq * d), k_strides=kvs, v_strides=kvs, o_strides=(sq * hq * d, hq * d),
-                              scale=sc, softcap=softcap, causal=causal,
+                              scale=sc, softcap=softcap, causal=causal, causal_prefix=causal_prefix,
                               kv_start=None if kv_start is None else to(torch.tensor(kv_start, dtype=torch.int32)))
                 return out
         c, r = _both(run, dev)
@@ -364,6 +364,12 @@ ATTN_CASES = [
     attn_case("attn_tc_d256_left_padded", 4, 4, 2, 278, 278, 256, scale=1 / 16, softcap=50.0, smax=290, seed=11, kv_start=[0, 3, 64, 131]),
     # causal continuation over a left-padded cache (sq < sk, every query still sees at least one real key)
     attn_case("attn_tc_d256_left_padded_causal", 2, 2, 1, 100, 150, 256, scale=1 / 16, softcap=50.0, causal=True, smax=160, seed=12, kv_start=[5, 50]),
+    # prefix-LM mask of the training forward (model/modeling_spatialvla.py:292-305): keys < prefix visible to every query, the
+    # suffix causal; prefix inside the first tile / spanning tiles / == sk (degenerates to bidirectional); L = 291 like config #5
+    attn_case("attn_tc_d256_prefix_lm", 3, 4, 2, 291, 291, 256, scale=1 / 16, softcap=50.0, causal=True, smax=291, seed=14, causal_prefix=278),
+    attn_case("attn_tc_d256_prefix_lm_short", 2, 2, 1, 200, 200, 256, scale=1 / 16, softcap=50.0, causal=True, smax=208, seed=15, causal_prefix=7),
+    attn_case("attn_tc_d256_prefix_lm_all", 1, 2, 2, 150, 150, 256, scale=1 / 16, softcap=50.0, causal=True, smax=150, seed=16, causal_prefix=150),
+    attn_case("attn_mma_d128_prefix_lm", 2, 2, 2, 100, 100, 128, causal=True, smax=100, seed=17, causal_prefix=70),
     attn_case("attn_mma_d128_left_padded", 2, 2, 2, 100, 130, 128, smax=130, seed=13, kv_start=[9, 77]),
     decode_attn_case,
     decode_attn_fused_case,
@@ -646,7 +652,37 @@ def tokenizer_case(dev="cuda:0"):
     return res
 
 
-FUSED_CASES = [layernorm_case, rmsnorm_case, rope_case, embed_case, argmax_case, patchify_case, assemble_concat_case,
+def cross_entropy_case(dev="cuda:0"):
+    """svla_cross_entropy_rows vs nn.CrossEntropyLoss: the real (odd) vocabulary width so rows are not 16-byte aligned, a padded
+    row stride, ignored rows, an argmax tie, a dominant logit (online max rescale), chunked calls with the summary on the last."""
+    res = Result("cross_entropy_rows")
+    for (rows, cols, ld, chunk) in ((37, 265347, 265347, 37), (9, 9216, 9220, 4), (5, 3, 3, 5), (300, 1001, 1001, 128)):
+        g = _gen(rows + cols)
+        lg = torch.zeros(rows, ld)
+        lg[:, :cols] = _randn(g, rows, cols, scale=4.0)
+        lab = torch.randint(0, cols, (rows,), generator=g)
+        lab[1::5] = -100
+        lg[0, cols - 1] = 60.0                       # dominant last column: exp(m_old - m_new) underflows
+        lab[0] = cols - 1
+        lg[2, 1] = lg[2, cols - 2] = 25.0            # tie -> first index
+        lab[2] = 1
+
+        def run(ops, to):
+            l_, y = to(lg), to(lab)
+            rl, ra, sm = ops.zeros((rows,), F32), ops.zeros((rows,), torch.int64), ops.zeros((3,), F32)
+            for r0 in range(0, rows, chunk):
+                r1 = min(rows, r0 + chunk)
+                ops.cross_entropy_rows(l_[r0:r1, :cols], y, rl, ra, row_offset=r0, summary=sm if r1 == rows else None)
+            return rl, ra, sm
+        (crl, cra, csm), (rrl, rra, rsm) = _both(run, dev)
+        res.add(f"row_loss[{cols}]", float((crl.cpu() - rrl).abs().max()), 2e-5)
+        res.add(f"argmax[{cols}]", float((cra.cpu() != rra).sum()), 0)
+        res.add(f"mean[{cols}]", abs(float(csm[0]) - float(rsm[0])), 2e-5)
+        res.add(f"count_hits[{cols}]", float((csm[1:].cpu() - rsm[1:]).abs().max()), 0)
+    return res
+
+
+FUSED_CASES = [layernorm_case, rmsnorm_case, rope_case, embed_case, argmax_case, cross_entropy_case, patchify_case, assemble_concat_case,
                shuffle_im2col_case, bilinear_case, zoe_tail_case, ego3d_case, tokenizer_case]
 
 ALL_CASES = {c.__name__: c for c in (SIMT_CASES + GEMM_CASES + PAIR_CASES + TMA_EPI_CASES + ROWTILE_CASES + SKINNY_CASES + ATTN_CASES + FUSED_CASES)}

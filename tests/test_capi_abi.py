@@ -40,6 +40,7 @@ def test_gemm_args_struct_matches_header_layout():
     assert L.SvlaGemmArgs.nb.offset == 17 * 8
     assert C.sizeof(L.SvlaGemmArgs) == 17 * 8 + 10 * 4
     assert L.SvlaAttnArgs.batch.offset == 12 * 8
+    assert L.SvlaAttnArgs.kv_start.offset == 152 and L.SvlaAttnArgs.causal_prefix.offset == 160 and C.sizeof(L.SvlaAttnArgs) == 168
 
 
 def test_validation_errors_before_any_cuda_call(lib):

@@ -235,3 +235,41 @@ def test_full_size_4b_parity_teacher_forced(cuda_device):
     if safe.any():
         assert float(agree[safe].float().mean()) >= 0.995
     assert float(agree.float().mean()) >= 0.9
+
+
+def test_labelled_forward_loss_vs_oracle_and_reference_golden(tiny_gpu, cuda_device):
+    """forward(labels=...) -- the forward half of the training step -- on the GPU under the reference's three
+    masks (prefix-LM through the causal_prefix predicate of the tcgen05 attention kernel, triangular, bidirectional): loss and
+    labelled-row logits against the fp32 oracle (same bf16-rounded weights) and the loss the live reference produced."""
+    from spatialvla_b200 import SpatialVLAForConditionalGeneration
+    cfg, _, _, _, sd, _ = tiny_gpu
+    g = np.load(os.path.join(GOLD, "tiny_model_train.npz"))
+    ids, tt, labels = (torch.from_numpy(g[k]) for k in ("input_ids", "token_type_ids", "labels"))
+    px, K = torch.from_numpy(g["pixel_u8"]).float() / 255.0, torch.from_numpy(g["intrinsic"])
+    B, L = ids.shape
+    model = SpatialVLAForConditionalGeneration(cfg, sd, device=cuda_device)
+    ones = torch.ones(B, L, dtype=torch.int64)
+    got = {}
+    for name, kw in (("prefix_lm", dict(token_type_ids=tt, attention_mask=ones)), ("causal", dict(token_type_ids=tt)),
+                     ("bidirectional", dict())):
+        n0 = model.ops.launch_count()
+        out = model.forward(input_ids=ids, pixel_values=px, intrinsic=K, labels=labels, **kw)
+        torch.cuda.synchronize()
+        assert model.ops.launch_count() > n0 and out.loss.device.type == "cuda"
+        ref_loss, rows, lab, ref_lg = R.forward_loss_ref(sd, cfg, ids, px, K, labels, force_head=model.engine.last_router_head, **kw)
+        assert torch.equal(out.label_rows.cpu(), rows)
+        assert (out.logits.cpu() - ref_lg).abs().max() < 6e-2, name                     # rtol 2e-2 class on |logit| <= 30
+        assert abs(float(out.loss) - float(ref_loss)) < 1e-2, name
+        assert abs(float(out.loss) - float(g["loss_" + name])) < 1e-2, name             # live reference
+        # the loss is exactly the cross entropy of the returned logits (kernel vs torch on the same rows)
+        assert abs(float(torch.nn.functional.cross_entropy(out.logits.cpu(), lab)) - float(out.loss)) < 2e-5
+        got[name] = out.logits.cpu()
+    # the masks must actually differ on the suffix rows (a mask that is ignored cannot pass the three comparisons above)
+    assert (got["prefix_lm"] - got["causal"]).abs().max() > 1e-2 and (got["prefix_lm"] - got["bidirectional"]).abs().max() > 1e-2
+    # size-independent property: under the triangular mask a labelled row only depends on earlier tokens -> truncating the
+    # sequence after position t leaves the logits of row t unchanged
+    cut = L - 3
+    out_c = model.forward(input_ids=ids[:, :cut], pixel_values=px, intrinsic=K, labels=labels[:, :cut], token_type_ids=tt[:, :cut])
+    n_c = out_c.logits.shape[0] // B
+    full = got["causal"].view(B, -1, got["causal"].shape[-1])[:, :n_c]
+    assert (out_c.logits.cpu().view(B, n_c, -1) - full).abs().max() < 2e-2

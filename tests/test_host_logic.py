@@ -164,3 +164,47 @@ def test_from_pretrained_checkpoint_roundtrip(tmp_path):
     assert torch.equal(m.engine.gem["embed"][-n:].float(), sd["spatial_embed_tokens.weight"].to(torch.bfloat16).float())
     with pytest.raises(OSError):
         SpatialVLAForConditionalGeneration.from_pretrained(str(tmp_path / "missing"), ops=RefOps())
+
+
+def test_labelled_forward_host_logic_matches_oracle_and_golden(tiny):
+    """forward(labels=...) orchestration (mask selection, label shift / ignore / pad masking, row gather, chunked lm_head +
+    cross entropy) through the torch op re-statements, against the fp32 oracle and the live-reference golden losses."""
+    from spatialvla_b200.modeling_spatialvla import SpatialVLAForConditionalGeneration
+    cfg, _, _, _, sd, _ = tiny
+    g = np.load(os.path.join(GOLD, "tiny_model_train.npz"))
+    ids, tt, labels = (torch.from_numpy(g[k]) for k in ("input_ids", "token_type_ids", "labels"))
+    px, K = torch.from_numpy(g["pixel_u8"]).float() / 255.0, torch.from_numpy(g["intrinsic"])
+    B, L = ids.shape
+    m = SpatialVLAForConditionalGeneration(cfg, sd, ops=RefOps())
+    ones = torch.ones(B, L, dtype=torch.int64)
+    for name, kw in (("prefix_lm", dict(token_type_ids=tt, attention_mask=ones)), ("causal", dict(token_type_ids=tt)),
+                     ("bidirectional", dict())):
+        out = m.forward(input_ids=ids, pixel_values=px, intrinsic=K, labels=labels, **kw)
+        ref_loss, rows, lab, ref_lg = R.forward_loss_ref(sd, cfg, ids, px, K, labels, force_head=m.engine.last_router_head, **kw)
+        assert torch.equal(out.label_rows, rows) and out.logits.shape == ref_lg.shape
+        assert (out.logits - ref_lg).abs().max() < 6e-2, name
+        assert abs(float(out.loss) - float(ref_loss)) < 1e-2 and abs(float(out.loss) - float(g["loss_" + name])) < 1e-2, name
+        assert abs(float(out.row_loss.mean()) - float(out.loss)) < 1e-5
+        assert 0.0 <= float(out.token_accuracy) <= 1.0
+    # chunked path: two rows per lm_head / cross-entropy launch gives the same loss, logits are not kept
+    m.engine.loss_chunk_rows = 4
+    out2 = m.forward(input_ids=ids, pixel_values=px, intrinsic=K, labels=labels)
+    assert abs(float(out2.loss) - float(out.loss)) < 1e-6 and out2.logits is None
+    m.engine.loss_chunk_rows = 4096
+    # pad-id labels are ignored where the input token is the pad token (model/modeling_spatialvla.py:389-397)
+    ids_p, lab_p = ids.clone(), labels.clone()
+    ids_p[:, -1], lab_p[:, -1] = 0, 0
+    out3 = m.forward(input_ids=ids_p, pixel_values=px, intrinsic=K, labels=lab_p, token_type_ids=tt, attention_mask=ones)
+    assert out3.label_rows.numel() == rows.numel() - B
+    # nothing labelled -> NaN like nn.CrossEntropyLoss; unsupported patterns raise
+    assert torch.isnan(m.forward(input_ids=ids, pixel_values=px, intrinsic=K, labels=torch.full_like(labels, -100)).loss)
+    am = ones.clone()
+    am[0, 0] = 0
+    with pytest.raises(NotImplementedError):
+        m.forward(input_ids=ids, pixel_values=px, intrinsic=K, labels=labels, token_type_ids=tt, attention_mask=am)
+    bad_tt = tt.clone()
+    bad_tt[1, 3] = 1
+    with pytest.raises(NotImplementedError):
+        m.forward(input_ids=ids, pixel_values=px, intrinsic=K, labels=labels, token_type_ids=bad_tt, attention_mask=ones)
+    with pytest.raises(ValueError):
+        m.forward(input_ids=ids, pixel_values=px, intrinsic=K, labels=labels[:, :-1])

@@ -92,3 +92,38 @@ def test_model_restatement_left_padded_batch_matches_reference_golden():
     import pytest
     with pytest.raises(NotImplementedError):
         R.left_pads(torch.tensor([[1, 1, 0], [1, 1, 1]]))
+
+
+def _train_golden():
+    g = np.load(os.path.join(GOLD, "tiny_model_train.npz"))
+    from spatialvla_b200.configs import get_config_dict
+    cfg = get_config_dict("tiny")
+    ids, tt, labels = (torch.from_numpy(g[k]) for k in ("input_ids", "token_type_ids", "labels"))
+    px, K = torch.from_numpy(g["pixel_u8"]).float() / 255.0, torch.from_numpy(g["intrinsic"])
+    return g, cfg, ids, tt, labels, px, K
+
+
+TRAIN_MASKS = {"prefix_lm": dict(use_tt=True, use_am=True), "causal": dict(use_tt=True, use_am=False),
+               "bidirectional": dict(use_tt=False, use_am=False)}
+
+
+def test_labelled_forward_restatement_matches_reference_golden():
+    """forward(labels=...) (model/modeling_spatialvla.py:335-430) under its three masks: golden = the live reference's loss and
+    labelled-row logits (oracle/gen_golden.gen_model_train)."""
+    g, cfg, ids, tt, labels, px, K = _train_golden()
+    sd = synth_state_dict(cfg, seed=0)
+    B, L = ids.shape
+    losses = {}
+    for name, m in TRAIN_MASKS.items():
+        loss, rows, lab, lg = R.forward_loss_ref(sd, cfg, ids, px, K, labels, token_type_ids=tt if m["use_tt"] else None,
+                                                 attention_mask=torch.ones(B, L, dtype=torch.int64) if m["use_am"] else None)
+        assert rows.numel() == B * 7 and torch.equal(lab, labels[:, 1:][labels[:, 1:] != -100])
+        assert abs(float(loss) - float(g["loss_" + name])) < 2e-5, name
+        assert np.abs(lg.numpy() - g["logits_" + name]).max() < 5e-5, name
+        losses[name] = float(loss)
+    # the three masks are distinguishable on this input (a wrong mask cannot pass the test above)
+    assert min(abs(losses["prefix_lm"] - losses["causal"]), abs(losses["prefix_lm"] - losses["bidirectional"])) > 5e-4
+    # labels equal to the pad id are ignored where the INPUT is a pad token (:389-397); token types that are not 0..01..1 raise
+    import pytest
+    with pytest.raises(NotImplementedError):
+        R.prefix_length(torch.tensor([[0, 1, 0], [0, 1, 1]]))

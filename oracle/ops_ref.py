@@ -255,7 +255,7 @@ class RefOps:
         self.launches += 1 if summary is None else 2
         r = logits.shape[0]
         lab = labels[row_offset:row_offset + r]
-        row_loss[row_offset:row_offset + r] = F.cross_entropy(logits.float(), lab, ignore_index=ignore_index, reduction="none")
+        row_loss[row_offset:row_offset + r] = F.cross_entropy(logits.double(), lab, ignore_index=ignore_index, reduction="none").float()
         row_argmax[row_offset:row_offset + r] = logits.argmax(-1)
         if summary is not None:
             n = row_offset + r

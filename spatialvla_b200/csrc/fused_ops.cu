@@ -432,64 +432,97 @@ svla_argmax_kernel(const float* __restrict__ logits, long long cols, long long l
 // Training / evaluation forward (model/modeling_spatialvla.py:413-430): nn.CrossEntropyLoss over the labelled rows of the
 // post-softcap full-vocabulary logits.  One CTA per row (a 265 347-column fp32 row is 1.06 MB): one pass with a per-thread
 // online (max, sum exp) pair and the running argmax, 128-bit loads on the 16-byte aligned body of the row (rows of an odd
-// vocabulary are not 16-byte aligned: scalar head / tail), warp-shuffle + shared-memory combine.  HBM-bound: rows * cols * 4 B.
+// vocabulary are not 16-byte aligned: scalar head / tail), four loads in flight per thread and one max update per 16 values
+// so that the per-element cost is FSUB + FMUL + ex2.approx + a predicated argmax update (the first version, one expf per
+// element and one load in flight, was issue / latency bound at 37 % of HBM peak), warp-shuffle + shared-memory combine.
+// HBM-bound: rows * cols * 4 B.
 struct CeAcc {
-  float m, s, best;
-  long long bi;
+  float m, s, best;      // running max, sum of exp(v - m), best value
+  int bi;                // first index of the best value seen by this thread (columns < 2^31)
 };
-__device__ __forceinline__ void ce_push(CeAcc& a, float v, long long j) {
-  if (v > a.best || (v == a.best && j < a.bi)) { a.best = v; a.bi = j; }
-  if (v > a.m) {
-    a.s = a.s * expf(a.m - v) + 1.f;      // a.m == -inf: a.s is 0 and expf(-inf) = 0
-    a.m = v;
-  } else {
-    a.s += expf(v - a.m);
+constexpr float kCeLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ce_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exp(a - b) with exp(-inf - finite) = 0 and the empty-accumulator case (-inf - -inf) mapped to 0 as well
+__device__ __forceinline__ float ce_exp_diff(float a, float b) { return (a == -INFINITY) ? 0.f : ce_ex2((a - b) * kCeLog2e); }
+__device__ __forceinline__ void ce_raise_max(CeAcc& a, float cm) {
+  if (cm > a.m) {
+    a.s *= ce_exp_diff(a.m, cm);
+    a.m = cm;
   }
 }
-__device__ __forceinline__ void ce_merge(CeAcc& a, float m2, float s2, float b2, long long i2) {
+__device__ __forceinline__ void ce_add(CeAcc& a, float v, int j) {      // requires v <= a.m
+  if (v > a.best) { a.best = v; a.bi = j; }                            // strict: a thread visits its columns in ascending order
+  a.s += ce_exp_diff(v, a.m);
+}
+__device__ __forceinline__ void ce_push(CeAcc& a, float v, int j) {
+  ce_raise_max(a, v);
+  ce_add(a, v, j);
+}
+__device__ __forceinline__ void ce_push4(CeAcc& a, const float4& v, int j) {
+  ce_add(a, v.x, j);
+  ce_add(a, v.y, j + 1);
+  ce_add(a, v.z, j + 2);
+  ce_add(a, v.w, j + 3);
+}
+__device__ __forceinline__ void ce_merge(CeAcc& a, float m2, float s2, float b2, int i2) {
   if (b2 > a.best || (b2 == a.best && i2 < a.bi)) { a.best = b2; a.bi = i2; }
   const float M = fmaxf(a.m, m2);
-  if (M == -INFINITY) return;             // both empty
-  a.s = a.s * expf(a.m - M) + s2 * expf(m2 - M);
+  a.s = a.s * ce_exp_diff(a.m, M) + s2 * ce_exp_diff(m2, M);
   a.m = M;
 }
 
 constexpr int kCeThreads = 512;
+constexpr int kCeUnroll = 4;      // independent 128-bit loads in flight per thread
 
 __global__ void __launch_bounds__(kCeThreads)
 svla_cross_entropy_kernel(const float* __restrict__ logits, long long cols, long long ld, const long long* __restrict__ labels,
                           long long ignore_index, float* __restrict__ row_loss, long long* __restrict__ row_argmax) {
   __shared__ float sm_m[kCeThreads / 32], sm_s[kCeThreads / 32], sm_b[kCeThreads / 32];
-  __shared__ long long sm_i[kCeThreads / 32];
+  __shared__ int sm_i[kCeThreads / 32];
   const long long row = blockIdx.x;
   const float* r = logits + row * ld;
-  CeAcc a{-INFINITY, 0.f, -INFINITY, 0x7fffffffffffffffLL};
-  long long head = static_cast<long long>(((16 - (reinterpret_cast<uintptr_t>(r) & 15)) & 15) >> 2);
-  if (head > cols) head = cols;
-  if (threadIdx.x < head) ce_push(a, r[threadIdx.x], threadIdx.x);
-  const long long nvec = (cols - head) >> 2;
+  const int tid = threadIdx.x;
+  CeAcc a{-INFINITY, 0.f, -INFINITY, 0x7fffffff};
+  int head = static_cast<int>(((16 - (reinterpret_cast<uintptr_t>(r) & 15)) & 15) >> 2);
+  if (head > cols) head = static_cast<int>(cols);
+  if (tid < head) ce_push(a, r[tid], tid);
+  const int nvec = static_cast<int>((cols - head) >> 2);
   const float4* rv = reinterpret_cast<const float4*>(r + head);
-  for (long long i = threadIdx.x; i < nvec; i += kCeThreads) {
-    const float4 v = __ldg(rv + i);
-    const long long j = head + 4 * i;
-    ce_push(a, v.x, j);
-    ce_push(a, v.y, j + 1);
-    ce_push(a, v.z, j + 2);
-    ce_push(a, v.w, j + 3);
+  int i = tid;
+  // main loop: kCeUnroll loads issued back to back, ONE max update / rescale per 16 values, then one FSUB + FMUL + MUFU each
+  for (; i + (kCeUnroll - 1) * kCeThreads < nvec; i += kCeUnroll * kCeThreads) {
+    float4 v[kCeUnroll];
+#pragma unroll
+    for (int u = 0; u < kCeUnroll; ++u) v[u] = __ldg(rv + i + u * kCeThreads);
+    float cm = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < kCeUnroll; ++u) cm = fmaxf(cm, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
+    ce_raise_max(a, cm);
+#pragma unroll
+    for (int u = 0; u < kCeUnroll; ++u) ce_push4(a, v[u], head + 4 * (i + u * kCeThreads));
   }
-  const long long tail0 = head + 4 * nvec;
-  if (tail0 + threadIdx.x < cols) ce_push(a, r[tail0 + threadIdx.x], tail0 + threadIdx.x);
+  for (; i < nvec; i += kCeThreads) {
+    const float4 v = __ldg(rv + i);
+    ce_raise_max(a, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    ce_push4(a, v, head + 4 * i);
+  }
+  const int tail0 = head + 4 * nvec;
+  if (tail0 + tid < cols) ce_push(a, r[tail0 + tid], tail0 + tid);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float m2 = __shfl_xor_sync(0xffffffffu, a.m, o), s2 = __shfl_xor_sync(0xffffffffu, a.s, o);
     const float b2 = __shfl_xor_sync(0xffffffffu, a.best, o);
-    const long long i2 = __shfl_xor_sync(0xffffffffu, a.bi, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, a.bi, o);
     ce_merge(a, m2, s2, b2, i2);
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = tid & 31, warp = tid >> 5;
   if (lane == 0) { sm_m[warp] = a.m; sm_s[warp] = a.s; sm_b[warp] = a.best; sm_i[warp] = a.bi; }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     for (int w = 1; w < kCeThreads / 32; ++w) ce_merge(a, sm_m[w], sm_s[w], sm_b[w], sm_i[w]);
     const long long lab = labels[row];
     float loss = 0.f;
@@ -1147,67 +1180,109 @@ svla_zoe_depth_tail_fused_kernel(const __nv_bfloat16* __restrict__ x, const __nv
 }
 
 // ------------------------------------------------------------------------------------------ M5 Ego3D
-// grid (32 cell rows, B); 256 threads = 32 cells x 8 lanes; each cell = 7x7 mean of the bicubic-resampled depth
+// model/modeling_spatialvla.py:318-323 (bicubic 384 -> 286 with align_corners, crop [31, 255)), :195-223 (7x7 cell mean,
+// K^-1 [u v 1] d), :41-97 (sin/cos encoding).  The 7x7 mean of bicubic samples is SEPARABLE: cell(ci, cj) =
+// sum_y sum_x W[ci][y] W[cj][x] depth[y][x] with W[c] = the seven 4-tap cubic stencils of the cell's sample coordinates summed
+// into one 13-tap stencil (identical table for rows and columns: square map, square crop).  The first version evaluated all
+// 49 x 16 taps per cell straight from global memory (784 scattered loads per cell, issue-bound at 21 % of HBM peak); here a
+// CTA owns one PATCH row (2 cell rows x 32 cells): the <= 23 source rows it needs are staged once into shared memory with
+// coalesced 128-bit loads (columns 40..347 cover every tap of the crop), one horizontal 13-tap pass per (row, cell) and one
+// vertical 13-tap pass per cell follow, and the 16 encoding rows of the patch row are assembled in shared memory and leave
+// as one contiguous 128-bit store stream.
+constexpr int kEgoTaps = 13;
+constexpr int kEgoX0 = 40, kEgoCols = 308, kEgoRows = 24;
+constexpr int kEgoMaxKpad = 256;
+
 __global__ void __launch_bounds__(256)
 svla_ego3d_kernel(const float* __restrict__ depth384, const float* __restrict__ intr, int k_stride, float* __restrict__ xyz,
                   __nv_bfloat16* __restrict__ enc, int kpad, int n_freqs) {
-  const int ci = blockIdx.x, b = blockIdx.y;
-  const int cj = threadIdx.x >> 3, sub = threadIdx.x & 7;
-  const float* dm = depth384 + static_cast<long long>(b) * 384 * 384;
+  __shared__ float sW[32][kEgoTaps];
+  __shared__ int sStart[32];
+  __shared__ __align__(16) float sD[kEgoRows][kEgoCols];
+  __shared__ float sH[2][kEgoTaps][32];
+  __shared__ float sCell[2][32];
+  __shared__ __align__(16) __nv_bfloat16 sEnc[16 * kEgoMaxKpad];
+  const int pr = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const float scale = 383.0f / 285.0f;
-  float acc = 0.f;
-  for (int pidx = sub; pidx < 49; pidx += 8) {
-    const int py = ci * 7 + pidx / 7 + 31, px = cj * 7 + pidx % 7 + 31;   // coordinates in the 286 grid
-    const float sy = scale * py, sx = scale * px;
-    const int y0 = static_cast<int>(floorf(sy)), x0 = static_cast<int>(floorf(sx));
-    float wy[4], wx[4];
-    cubic_coeffs(sy - y0, wy);
-    cubic_coeffs(sx - x0, wx);
-    float v = 0.f;
+  // 13-tap stencils (fp32 coordinates exactly as the 49-sample formulation computes them)
+  if (tid < 32) {
+    const int first = static_cast<int>(floorf(scale * (tid * 7 + 31))) - 1;
+    sStart[tid] = first;
+    for (int k = 0; k < kEgoTaps; ++k) sW[tid][k] = 0.f;
+    for (int r = 0; r < 7; ++r) {
+      const float sc = scale * (tid * 7 + r + 31);
+      const int i0 = static_cast<int>(floorf(sc));
+      float c[4];
+      cubic_coeffs(sc - i0, c);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int yy = clampi(y0 - 1 + u, 0, 383);
-      float racc = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) racc += wx[q] * dm[yy * 384 + clampi(x0 - 1 + q, 0, 383)];
-      v += wy[u] * racc;
+      for (int u = 0; u < 4; ++u) sW[tid][i0 - 1 + u - first] += c[u];
     }
-    acc += v;
   }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-  if (sub >= 3) return;
-  const float d = acc / 49.f;
-  // inverse of the 3x3 intrinsic matrix (adjugate / det) in fp32
-  const float* K = intr + static_cast<long long>(b) * k_stride;
-  const float a00 = K[0], a01 = K[1], a02 = K[2], a10 = K[3], a11 = K[4], a12 = K[5], a20 = K[6], a21 = K[7], a22 = K[8];
-  const float c00 = a11 * a22 - a12 * a21, c01 = a02 * a21 - a01 * a22, c02 = a01 * a12 - a02 * a11;
-  const float c10 = a12 * a20 - a10 * a22, c11 = a00 * a22 - a02 * a20, c12 = a02 * a10 - a00 * a12;
-  const float c20 = a10 * a21 - a11 * a20, c21 = a01 * a20 - a00 * a21, c22 = a00 * a11 - a01 * a10;
-  const float det = a00 * c00 + a01 * c10 + a02 * c20;
-  const float u = cj * 7 + 3.5f, v = ci * 7 + 3.5f;
-  float r;
-  if (sub == 0) r = (c00 * u + c01 * v + c02) / det;
-  else if (sub == 1) r = (c10 * u + c11 * v + c12) / det;
-  else r = (c20 * u + c21 * v + c22) / det;
-  const float val = r * d;
-  const int patch = (ci >> 1) * 16 + (cj >> 1);
-  const int m = ((ci & 1) * 2 + (cj & 1)) * 3 + sub;      // (sub_row, sub_col, xyz)
-  const long long prow = static_cast<long long>(b) * 256 + patch;
-  xyz[prow * 12 + m] = val;
-  const float xn = (val - (sub == 2 ? 2.f : 0.f)) / 2.f;
-  __nv_bfloat16* er = enc + prow * kpad + m * (2 * n_freqs + 1);
-  er[0] = __float2bfloat16(xn);
-  float f = 1.f;
-  for (int k = 0; k < n_freqs; ++k) {
-    er[1 + k] = __float2bfloat16(sinf(xn * f));
-    er[1 + n_freqs + k] = __float2bfloat16(cosf(xn * f));
-    f *= 2.f;
+  for (int k = tid; k < 16 * kpad / 2; k += 256) reinterpret_cast<uint32_t*>(sEnc)[k] = 0u;      // K padding columns stay zero
+  __syncthreads();
+  const int ybase = sStart[2 * pr];
+  const int nrows = sStart[2 * pr + 1] + kEgoTaps - ybase;                    // <= 23, last source row <= 344
+  const float* dm = depth384 + static_cast<long long>(b) * 384 * 384;
+  constexpr int kVecPerRow = kEgoCols / 4;
+  for (int k = tid; k < nrows * kVecPerRow; k += 256) {
+    const int row = k / kVecPerRow, v = k % kVecPerRow;
+    reinterpret_cast<float4*>(&sD[row][0])[v] = __ldg(reinterpret_cast<const float4*>(dm + (ybase + row) * 384 + kEgoX0) + v);
   }
-  // zero the K padding once per row (the thread that owns m == 0)
-  if (m == 0)
-    for (int col = 12 * (2 * n_freqs + 1); col < kpad; ++col) enc[prow * kpad + col] = __float2bfloat16(0.f);
+  __syncthreads();
+  // horizontal pass: (cell row half, tap row k, cell cj)
+  for (int idx = tid; idx < 2 * kEgoTaps * 32; idx += 256) {
+    const int half = idx / (kEgoTaps * 32), rem = idx % (kEgoTaps * 32), k = rem >> 5, cj = rem & 31;
+    const float* src = &sD[sStart[2 * pr + half] - ybase + k][sStart[cj] - kEgoX0];
+    float h = 0.f;
+#pragma unroll
+    for (int x = 0; x < kEgoTaps; ++x) h += sW[cj][x] * src[x];
+    sH[half][k][cj] = h;
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int half = tid >> 5, cj = tid & 31, ci = 2 * pr + half;
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < kEgoTaps; ++k) d += sW[ci][k] * sH[half][k][cj];
+    sCell[half][cj] = d / 49.f;
+  }
+  __syncthreads();
+  if (tid < 192) {
+    const int half = tid / 96, rem = tid % 96, cj = rem / 3, sub = rem % 3, ci = 2 * pr + half;
+    const float d = sCell[half][cj];
+    // inverse of the 3x3 intrinsic matrix (adjugate / det) in fp32
+    const float* K = intr + static_cast<long long>(b) * k_stride;
+    const float a00 = K[0], a01 = K[1], a02 = K[2], a10 = K[3], a11 = K[4], a12 = K[5], a20 = K[6], a21 = K[7], a22 = K[8];
+    const float c00 = a11 * a22 - a12 * a21, c01 = a02 * a21 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+    const float c10 = a12 * a20 - a10 * a22, c11 = a00 * a22 - a02 * a20, c12 = a02 * a10 - a00 * a12;
+    const float c20 = a10 * a21 - a11 * a20, c21 = a01 * a20 - a00 * a21, c22 = a00 * a11 - a01 * a10;
+    const float det = a00 * c00 + a01 * c10 + a02 * c20;
+    const float u = cj * 7 + 3.5f, v = ci * 7 + 3.5f;
+    float r;
+    if (sub == 0) r = (c00 * u + c01 * v + c02) / det;
+    else if (sub == 1) r = (c10 * u + c11 * v + c12) / det;
+    else r = (c20 * u + c21 * v + c22) / det;
+    const float val = r * d;
+    const int pl = cj >> 1;                                   // patch within this patch row
+    const int m = (half * 2 + (cj & 1)) * 3 + sub;            // (sub_row, sub_col, xyz)
+    xyz[(static_cast<long long>(b) * 256 + pr * 16 + pl) * 12 + m] = val;
+    const float xn = (val - (sub == 2 ? 2.f : 0.f)) / 2.f;
+    __nv_bfloat16* er = sEnc + pl * kpad + m * (2 * n_freqs + 1);
+    er[0] = __float2bfloat16(xn);
+    float f = 1.f;
+    for (int k = 0; k < n_freqs; ++k) {
+      er[1 + k] = __float2bfloat16(sinf(xn * f));
+      er[1 + n_freqs + k] = __float2bfloat16(cosf(xn * f));
+      f *= 2.f;
+    }
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = enc + (static_cast<long long>(b) * 256 + pr * 16) * kpad;      // 16 consecutive patch rows: contiguous
+  if ((kpad & 7) == 0 && (reinterpret_cast<uintptr_t>(enc) & 15) == 0) {
+    for (int k = tid; k < 16 * kpad / 8; k += 256) reinterpret_cast<uint4*>(dst)[k] = reinterpret_cast<const uint4*>(sEnc)[k];
+  } else {
+    for (int k = tid; k < 16 * kpad; k += 256) dst[k] = sEnc[k];
+  }
 }
 
 inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
@@ -1484,7 +1559,9 @@ extern "C" int svla_ego3d_encode(const float* depth384, const float* intrinsic, 
                                  int kpad, int n_freqs, void* stream) {
   SVLA_REQUIRE(depth384 && intrinsic && xyz && enc && batch > 0, "svla_ego3d_encode: bad arguments");
   SVLA_REQUIRE(kpad >= 12 * (2 * n_freqs + 1) && (k_stride == 0 || k_stride == 9), "svla_ego3d_encode: bad kpad / k_stride");
-  dim3 grid(32, batch);
+  SVLA_REQUIRE(kpad <= kEgoMaxKpad && (kpad % 2) == 0 && n_freqs >= 0, "svla_ego3d_encode: kpad must be even and <= %d", kEgoMaxKpad);
+  SVLA_REQUIRE((reinterpret_cast<uintptr_t>(depth384) & 15) == 0, "svla_ego3d_encode: depth maps must be 16-byte aligned");
+  dim3 grid(16, batch);
   svla_ego3d_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(depth384, intrinsic, k_stride, xyz,
                                                                         static_cast<__nv_bfloat16*>(enc), kpad, n_freqs);
   SVLA_LAUNCH_CHECK("svla_ego3d_encode");

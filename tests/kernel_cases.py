@@ -675,9 +675,10 @@ def cross_entropy_case(dev="cuda:0"):
                 ops.cross_entropy_rows(l_[r0:r1, :cols], y, rl, ra, row_offset=r0, summary=sm if r1 == rows else None)
             return rl, ra, sm
         (crl, cra, csm), (rrl, rra, rsm) = _both(run, dev)
-        res.add(f"row_loss[{cols}]", float((crl.cpu() - rrl).abs().max()), 2e-5)
+        # fp32 accumulation of up to 265 347 terms against the float64 reference: 1e-4 absolute on losses of ~20 (5e-6 relative)
+        res.add(f"row_loss[{cols}]", float((crl.cpu() - rrl).abs().max()), 1e-4)
         res.add(f"argmax[{cols}]", float((cra.cpu() != rra).sum()), 0)
-        res.add(f"mean[{cols}]", abs(float(csm[0]) - float(rsm[0])), 2e-5)
+        res.add(f"mean[{cols}]", abs(float(csm[0]) - float(rsm[0])), 1e-4)
         res.add(f"count_hits[{cols}]", float((csm[1:].cpu() - rsm[1:]).abs().max()), 0)
     return res
 

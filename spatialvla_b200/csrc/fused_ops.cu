@@ -1271,8 +1271,10 @@ svla_ego3d_kernel(const float* __restrict__ depth384, const float* __restrict__ 
     er[0] = __float2bfloat16(xn);
     float f = 1.f;
     for (int k = 0; k < n_freqs; ++k) {
-      er[1 + k] = __float2bfloat16(sinf(xn * f));
-      er[1 + n_freqs + k] = __float2bfloat16(cosf(xn * f));
+      float sv, cv;
+      sincosf(xn * f, &sv, &cv);               // one shared range reduction (the 16 sinf / cosf calls were half of the issue slots)
+      er[1 + k] = __float2bfloat16(sv);
+      er[1 + n_freqs + k] = __float2bfloat16(cv);
       f *= 2.f;
     }
   }

@@ -27,59 +27,52 @@ __device__ __forceinline__ int digitize_right_open(double v, const double* __res
 
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
-// Both kernels move whole tiles of kTokTile actions between global and shared memory with unit-stride accesses (a warp
-// instruction covers 256 contiguous bytes); the per-action records (7 doubles in, 3 ids out or the reverse) are then read and
-// written in shared memory.  The first version let every thread load / store its own 56-byte record straight from global
-// memory: every 8-byte access touched its own 32-byte sector (ncu: 7 sectors per action in L1/L2 instead of 1.75; the decode
-// kernel sat at 66 % L1 / 54 % L2 throughput with DRAM at 41 %).
+// The DECODE kernel moves whole tiles of kTokTile actions between global and shared memory with unit-stride accesses (a warp
+// instruction covers 256 contiguous bytes); the per-action records (3 ids in, 7 doubles out) are read and written in shared
+// memory.  Its first version let every thread load / store its own record straight from global memory: every 8-byte access
+// touched its own 32-byte sector (ncu: 7 store sectors per action instead of 1.75; L1 at 66 % / L2 at 54 % with DRAM at 41 %):
+// 0.487 -> 0.336 ms on 16 M actions (3.8 TB/s).  The ENCODE kernel keeps per-thread records: it is issue-bound on FP64 library
+// code (2 x atan2, 2 x sqrt, 6 binary searches: 806 thread-instructions per action, 78 % of issue slots busy at 35 % of the
+// HBM peak), its 7-sector record loads hit L1, and the staged variant measured SLOWER (0.549 vs 0.455 ms on 16 M actions:
+// extra staging instructions and three barriers per tile in an issue-bound loop).
 constexpr int kTokTile = 256;
 
-__global__ void __launch_bounds__(kTokTile)
+__global__ void __launch_bounds__(256)
 svla_tok_encode_kernel(const double* __restrict__ actions, const double* __restrict__ edges, TokGrid g, int* __restrict__ ids,
                        long long n, double amin, double amax, int spherical) {
   __shared__ double se[kMaxEdges];
-  __shared__ double sa[kTokTile * 7];
-  __shared__ int si[kTokTile * 3];
   int total = g.off[5] + g.nb[5] + 1;
   for (int i = threadIdx.x; i < total; i += blockDim.x) se[i] = edges[i];
-  const long long n_tiles = (n + kTokTile - 1) / kTokTile;
-  const int n_trans = g.nb[0] * g.nb[1] * g.nb[2];
-  const int n_rot = g.nb[3] * g.nb[4] * g.nb[5];
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long i0 = tile * kTokTile;
-    const int cnt = static_cast<int>(n - i0 < kTokTile ? n - i0 : kTokTile);
-    __syncthreads();                                   // previous tile's ids are out; se[] is loaded
-    for (int k = threadIdx.x; k < cnt * 7; k += kTokTile) sa[k] = actions[i0 * 7 + k];
-    __syncthreads();
-    if (threadIdx.x < cnt) {
-      const double* a = sa + threadIdx.x * 7;
-      const double x = clampd(a[0], amin, amax), y = clampd(a[1], amin, amax), z = clampd(a[2], amin, amax);
-      const double xx = __dmul_rn(x, x), yy = __dmul_rn(y, y), zz = __dmul_rn(z, z);
-      const double sxy = __dadd_rn(xx, yy);
-      // use_spherical=False (model/action_tokenizer.py:112-113) bins the clipped Cartesian components directly
-      const double theta = spherical ? atan2(sqrt(sxy), z) : x;
-      const double phi = spherical ? atan2(y, x) : y;
-      const double r = spherical ? sqrt(__dadd_rn(sxy, zz)) : z;
-      // translation uses the interior edges e[1:-1]
-      const int dt = digitize_right_open(theta, se + g.off[0] + 1, g.nb[0] - 1);
-      const int dp = digitize_right_open(phi, se + g.off[1] + 1, g.nb[1] - 1);
-      const int dr = digitize_right_open(r, se + g.off[2] + 1, g.nb[2] - 1);
-      const int tid = dt * (g.nb[1] * g.nb[2]) + dp * g.nb[2] + dr;
-      int d3[3];
+  __syncthreads();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    const double* a = actions + i * 7;
+    const double x = clampd(a[0], amin, amax), y = clampd(a[1], amin, amax), z = clampd(a[2], amin, amax);
+    const double xx = __dmul_rn(x, x), yy = __dmul_rn(y, y), zz = __dmul_rn(z, z);
+    const double sxy = __dadd_rn(xx, yy);
+    // use_spherical=False (model/action_tokenizer.py:112-113) bins the clipped Cartesian components directly
+    const double theta = spherical ? atan2(sqrt(sxy), z) : x;
+    const double phi = spherical ? atan2(y, x) : y;
+    const double r = spherical ? sqrt(__dadd_rn(sxy, zz)) : z;
+    // translation uses the interior edges e[1:-1]
+    const int dt = digitize_right_open(theta, se + g.off[0] + 1, g.nb[0] - 1);
+    const int dp = digitize_right_open(phi, se + g.off[1] + 1, g.nb[1] - 1);
+    const int dr = digitize_right_open(r, se + g.off[2] + 1, g.nb[2] - 1);
+    const int tid = dt * (g.nb[1] * g.nb[2]) + dp * g.nb[2] + dr;
+    int d3[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const double v = clampd(a[3 + c], amin, amax);
-        int d = digitize_right_open(v, se + g.off[3 + c], g.nb[3 + c] + 1) - 1;
-        d3[c] = min(max(d, 0), g.nb[3 + c] - 1);
-      }
-      const int rid = d3[0] * (g.nb[4] * g.nb[5]) + d3[1] * g.nb[5] + d3[2] + n_trans;
-      const int gid = (clampd(a[6], amin, amax) >= 0.5 ? 1 : 0) + n_trans + n_rot;
-      si[threadIdx.x * 3 + 0] = tid;
-      si[threadIdx.x * 3 + 1] = rid;
-      si[threadIdx.x * 3 + 2] = gid;
+    for (int c = 0; c < 3; ++c) {
+      const double v = clampd(a[3 + c], amin, amax);
+      int d = digitize_right_open(v, se + g.off[3 + c], g.nb[3 + c] + 1) - 1;
+      d3[c] = min(max(d, 0), g.nb[3 + c] - 1);
     }
-    __syncthreads();
-    for (int k = threadIdx.x; k < cnt * 3; k += kTokTile) ids[i0 * 3 + k] = si[k];
+    const int n_trans = g.nb[0] * g.nb[1] * g.nb[2];
+    const int n_rot = g.nb[3] * g.nb[4] * g.nb[5];
+    const int rid = d3[0] * (g.nb[4] * g.nb[5]) + d3[1] * g.nb[5] + d3[2] + n_trans;
+    const int gid = (clampd(a[6], amin, amax) >= 0.5 ? 1 : 0) + n_trans + n_rot;
+    ids[i * 3 + 0] = tid;
+    ids[i * 3 + 1] = rid;
+    ids[i * 3 + 2] = gid;
   }
 }
 

@@ -513,3 +513,21 @@ def forward_loss_ref(sd, cfg, input_ids, pixel_values, intrinsic, labels, token_
         lg = lm_head_slice(sd, cfg, h.reshape(B * L, -1)[rows], 0, cfg["text_config"]["vocab_size"]).float()
         loss = F.cross_entropy(lg, lab) if rows.numel() else torch.tensor(float("nan"))
     return loss, rows, lab, lg
+
+
+def training_metrics_ref(logit_rows, row_labels, actions, ranges, decode_fn):
+    """train/monkey_patch.py:267-324 on the labelled rows (positions with label -100 never pass its action-range mask, so the
+    block only ever looks at labelled rows).  ranges = {"translation": (start, end), "rotation": ..., "gripper": ...} inclusive
+    token-id ranges of the sub-tokenizers; decode_fn: (n,3) int64 numpy global ids -> (n,7) float64 actions."""
+    pred = logit_rows.argmax(-1)
+    lo, hi = ranges["translation"][0], ranges["gripper"][1]
+    mask = (row_labels >= lo) & (row_labels <= hi)
+    gt, pr = row_labels[mask], pred[mask]
+    out = {"accuracy": float((gt == pr).sum().float() / mask.sum().float())}
+    for name in ("translation", "rotation", "gripper"):
+        m = (gt >= ranges[name][0]) & (gt <= ranges[name][1])
+        out[name + "_accuracy"] = float((gt[m] == pr[m]).sum().float() / m.sum().float())
+    pred_actions = torch.tensor(decode_fn(pr.numpy().reshape(-1, 3)))
+    gt_actions = torch.as_tensor(actions).reshape(-1, 7).to(torch.float32)
+    out["l1_loss"] = float(F.l1_loss(pred_actions.to(torch.float32), gt_actions))
+    return out

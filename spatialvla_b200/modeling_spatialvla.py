@@ -41,6 +41,8 @@ class SpatialVLACausalLMOutputWithPast:
     # labelled forward only (this build materialises logits for the labelled rows, not [B, L, V]):
     label_rows: Optional[torch.Tensor] = None        # int64 [R] flat positions b*L + t whose next token is labelled
     row_loss: Optional[torch.Tensor] = None          # fp32 [R] per-row cross entropy
+    row_labels: Optional[torch.Tensor] = None        # int64 [R] the labels of those rows (shifted)
+    row_argmax: Optional[torch.Tensor] = None        # int64 [R] full-vocabulary argmax of those rows
     token_accuracy: Optional[torch.Tensor] = None    # 0-dim fp32: argmax == label over the labelled rows
 
 
@@ -249,8 +251,37 @@ class SpatialVLAForConditionalGeneration:
         if rows.numel() == 0:                     # nn.CrossEntropyLoss over zero rows is NaN
             nan = torch.full((), float("nan"), dtype=F32, device=self.device)
             return SpatialVLACausalLMOutputWithPast(loss=nan, logits=None, image_hidden_states=feats, label_rows=rows)
-        summary, row_loss, _, logits = eng.labelled_loss(h, rows, row_labels.to(self.device).contiguous(), ignore_index=ignore)
+        row_labels = row_labels.to(self.device).contiguous()
+        summary, row_loss, row_argmax, logits = eng.labelled_loss(h, rows, row_labels, ignore_index=ignore)
         return SpatialVLACausalLMOutputWithPast(loss=summary[0], logits=logits, image_hidden_states=feats, label_rows=rows,
-                                                row_loss=row_loss, token_accuracy=summary[2] / summary[1])
+                                                row_loss=row_loss, row_labels=row_labels, row_argmax=row_argmax,
+                                                token_accuracy=summary[2] / summary[1])
+
+    @staticmethod
+    def action_metrics(outputs, actions, action_tokenizer):
+        """The metric block of the reference's training step (train/monkey_patch.py:267-324) from a labelled forward:
+        accuracy of the full-vocabulary argmax on the positions whose label is an action token, the same per token group
+        (translation / rotation / gripper) and the L1 distance between the de-tokenised predictions and `actions`.
+        outputs: result of forward(labels=...); actions: (..., 7) ground-truth (normalised) actions, one per labelled action
+        triple; action_tokenizer: SpatialActionTokenizer (sub-tokenizer id ranges + decode).  Returns a dict of floats."""
+        gt, pred = outputs.row_labels, outputs.row_argmax
+        tk = action_tokenizer
+        lo, hi = tk.translation_tokenizer.token_start_idx, tk.gripper_tokenizer.token_end_idx
+        mask = (gt >= lo) & (gt <= hi)
+        gt, pred = gt[mask], pred[mask]
+        correct = gt == pred
+        out = {"accuracy": correct.sum().float() / mask.sum().float()}
+        for name, sub_tk in (("translation", tk.translation_tokenizer), ("rotation", tk.rotation_tokenizer),
+                             ("gripper", tk.gripper_tokenizer)):
+            m = (gt >= sub_tk.token_start_idx) & (gt <= sub_tk.token_end_idx)
+            out[name + "_accuracy"] = correct[m].sum().float() / m.sum().float()
+        ids = pred.reshape(-1, 3)
+        if ids.is_cuda and hasattr(tk, "decode_ids"):
+            pred_actions = tk.decode_ids(ids).to(F32)                                  # device kernel, no host round trip
+        else:
+            pred_actions = torch.as_tensor(tk.decode_token_ids_to_actions(ids.cpu().numpy())).to(F32)
+        gt_actions = torch.as_tensor(actions).reshape(-1, 7).to(device=pred_actions.device, dtype=F32)
+        out["l1_loss"] = torch.nn.functional.l1_loss(pred_actions, gt_actions)
+        return {k: float(v) for k, v in out.items()}
 
     __call__ = forward

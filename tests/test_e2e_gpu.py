@@ -273,3 +273,37 @@ def test_labelled_forward_loss_vs_oracle_and_reference_golden(tiny_gpu, cuda_dev
     n_c = out_c.logits.shape[0] // B
     full = got["causal"].view(B, -1, got["causal"].shape[-1])[:, :n_c]
     assert (out_c.logits.cpu().view(B, n_c, -1) - full).abs().max() < 2e-2
+
+
+def test_action_metrics_on_gpu_match_reference_metric_block(tiny_gpu, cuda_device):
+    """Metric block of the reference's training step (train/monkey_patch.py:267-324) from the GPU labelled forward: full-vocabulary
+    argmax from the cross-entropy kernel, de-tokenisation through the device decode kernel; against the restatement run on the
+    same logits with the oracle tokenizer."""
+    from fakes import FakeTokenizer
+    from spatialvla_b200 import SpatialVLAForConditionalGeneration
+    from spatialvla_b200.action_tokenizer import SpatialActionTokenizer
+    cfg, _, _, _, sd, _ = tiny_gpu
+    g = np.load(os.path.join(GOLD, "tiny_model_train.npz"))
+    ids, tt, labels = (torch.from_numpy(g[k]) for k in ("input_ids", "token_type_ids", "labels"))
+    px, K = torch.from_numpy(g["pixel_u8"]).float() / 255.0, torch.from_numpy(g["intrinsic"])
+    nb = {"translation": {"theta_bins": 16, "phi_bins": 32, "r_bins": 8}, "rotation": {"roll_bins": 16, "pitch_bins": 16, "yaw_bins": 16},
+          "gripper": 2, "total": 8194}
+    tk = SpatialActionTokenizer(FakeTokenizer(base=cfg["action_token_begin_idx"]), nb)
+    ranges = {k: (getattr(tk, k + "_tokenizer").token_start_idx, getattr(tk, k + "_tokenizer").token_end_idx)
+              for k in ("translation", "rotation", "gripper")}
+    model = SpatialVLAForConditionalGeneration(cfg, sd, device=cuda_device)
+    B, L = ids.shape
+    out = model.forward(input_ids=ids, pixel_values=px, intrinsic=K, labels=labels, token_type_ids=tt, attention_mask=torch.ones_like(ids))
+    lab2 = labels.clone()
+    for r, a in zip(out.label_rows[:5].tolist(), out.row_argmax[:5].tolist()):      # make some predictions "right"
+        if ranges["translation"][0] <= a <= ranges["gripper"][1]:
+            lab2[r // L, r % L + 1] = a
+    out = model.forward(input_ids=ids, pixel_values=px, intrinsic=K, labels=lab2, token_type_ids=tt, attention_mask=torch.ones_like(ids))
+    assert torch.equal(out.row_argmax.cpu(), out.logits.cpu().argmax(-1))            # kernel argmax == torch argmax of its logits
+    actions = torch.rand(B, 2, 7, generator=torch.Generator().manual_seed(3)) * 2 - 1
+    got = model.action_metrics(out, actions, tk)
+    ref = R.training_metrics_ref(out.logits.cpu(), out.row_labels.cpu(), actions, ranges,
+                                 lambda i: T.decode(np.asarray(i) - tk.action_token_begin_idx, tk.bin_policy, nb))
+    for k in ref:
+        assert (np.isnan(got[k]) and np.isnan(ref[k])) or abs(got[k] - ref[k]) < 1e-6, (k, got[k], ref[k])
+    assert got["accuracy"] > 0.0

@@ -208,3 +208,46 @@ def test_labelled_forward_host_logic_matches_oracle_and_golden(tiny):
         m.forward(input_ids=ids, pixel_values=px, intrinsic=K, labels=labels, token_type_ids=bad_tt, attention_mask=ones)
     with pytest.raises(ValueError):
         m.forward(input_ids=ids, pixel_values=px, intrinsic=K, labels=labels[:, :-1])
+
+
+def _metric_tokenizer(cfg):
+    """Real SpatialActionTokenizer over the fake HF tokenizer; its host decode (a CUDA kernel behind the C ABI) is replaced by
+    the oracle restatement so the test runs without a GPU."""
+    from fakes import FakeTokenizer
+    from oracle import tokenizer_ref as T
+    from spatialvla_b200.action_tokenizer import SpatialActionTokenizer
+    nb = {"translation": {"theta_bins": 16, "phi_bins": 32, "r_bins": 8}, "rotation": {"roll_bins": 16, "pitch_bins": 16, "yaw_bins": 16},
+          "gripper": 2, "total": 8194}
+    tk = SpatialActionTokenizer(FakeTokenizer(base=cfg["action_token_begin_idx"]), nb)
+    assert tk.action_token_begin_idx == cfg["action_token_begin_idx"]
+    tk.decode_token_ids_to_actions = lambda ids: T.decode(np.asarray(ids) - tk.action_token_begin_idx, tk.bin_policy, nb)
+    ranges = {k: (getattr(tk, k + "_tokenizer").token_start_idx, getattr(tk, k + "_tokenizer").token_end_idx)
+              for k in ("translation", "rotation", "gripper")}
+    return tk, ranges
+
+
+def test_action_metrics_match_reference_metric_block(tiny):
+    """SpatialVLAForConditionalGeneration.action_metrics vs the restated metric block of the reference's training step
+    (train/monkey_patch.py:267-324) on the same labelled-row logits."""
+    from spatialvla_b200.modeling_spatialvla import SpatialVLAForConditionalGeneration
+    cfg, _, _, _, sd, _ = tiny
+    g = np.load(os.path.join(GOLD, "tiny_model_train.npz"))
+    ids, tt, labels = (torch.from_numpy(g[k]) for k in ("input_ids", "token_type_ids", "labels"))
+    px, K = torch.from_numpy(g["pixel_u8"]).float() / 255.0, torch.from_numpy(g["intrinsic"])
+    m = SpatialVLAForConditionalGeneration(cfg, sd, ops=RefOps())
+    tk, ranges = _metric_tokenizer(cfg)
+    # teach the "model" two of the labels so that the accuracies are not all zero: labels := its own argmax on some rows
+    out = m.forward(input_ids=ids, pixel_values=px, intrinsic=K, labels=labels, token_type_ids=tt)
+    lab2 = labels.clone()
+    B, L = ids.shape
+    for r, a in zip(out.label_rows[:5].tolist(), out.row_argmax[:5].tolist()):
+        if ranges["translation"][0] <= a <= ranges["gripper"][1]:
+            lab2[r // L, r % L + 1] = a
+    out = m.forward(input_ids=ids, pixel_values=px, intrinsic=K, labels=lab2, token_type_ids=tt)
+    actions = torch.rand(B, 2, 7, generator=torch.Generator().manual_seed(3)) * 2 - 1
+    got = m.action_metrics(out, actions, tk)
+    ref = R.training_metrics_ref(out.logits, out.row_labels, actions, ranges, tk.decode_token_ids_to_actions)
+    assert set(got) == {"accuracy", "translation_accuracy", "rotation_accuracy", "gripper_accuracy", "l1_loss"}
+    for k in ref:
+        assert (np.isnan(got[k]) and np.isnan(ref[k])) or abs(got[k] - ref[k]) < 1e-6, (k, got[k], ref[k])
+    assert abs(got["accuracy"] - float(out.token_accuracy) * out.row_labels.numel() / 12) < 1e-6      # EOS rows are not action rows

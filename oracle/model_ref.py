@@ -486,7 +486,7 @@ def prefix_length(token_type_ids):
 
 
 def forward_loss_ref(sd, cfg, input_ids, pixel_values, intrinsic, labels, token_type_ids=None, attention_mask=None,
-                     force_head=None, ignore_index=-100, pad_token_id=0):
+                     force_head=None, ignore_index=-100, pad_token_id=0, image_feats=None):
     """forward() with labels = model/modeling_spatialvla.py:335-430.  Mask (`_update_causal_mask`, :258-306): training
     (token_type_ids and labels given) = triangular, plus -- only when a 2-D attention_mask is passed -- every token_type 0
     column unmasked (prefix-LM); labels without token_type_ids = the inference mask (bidirectional).  Loss = shifted
@@ -495,7 +495,9 @@ def forward_loss_ref(sd, cfg, input_ids, pixel_values, intrinsic, labels, token_
     if attention_mask is not None and bool((attention_mask == 0).any()):
         raise NotImplementedError("padded batches are not covered by the labelled forward")
     with torch.no_grad():
-        feats = image_features(sd, cfg, pixel_values, intrinsic, force_head) if pixel_values is not None else None
+        feats = image_feats             # precomputed get_image_features output (full-size tests reuse the one they already have)
+        if feats is None and pixel_values is not None:
+            feats = image_features(sd, cfg, pixel_values, intrinsic, force_head)
         x = embed_inputs(sd, cfg, input_ids, feats)
         B, L, _ = x.shape
         cache = [None] * cfg["text_config"]["num_hidden_layers"]

@@ -235,6 +235,27 @@ def test_full_size_4b_parity_teacher_forced(cuda_device):
     if safe.any():
         assert float(agree[safe].float().mean()) >= 0.995
     assert float(agree.float().mean()) >= 0.9
+    # ---- forward(labels) at full size (config #5 shape: prefix 278 + 12 action ids + EOS, prefix-LM mask), same weights:
+    # loss and labelled-row full-vocabulary logits against the fp32 oracle (which reuses its own image features from above)
+    t1 = time.time()
+    P = ids.shape[1]
+    full = torch.cat([ids, ref_toks[:, :12], torch.full((B, 1), cfg["eos_token_id"])], 1)
+    L = full.shape[1]
+    tt = torch.cat([torch.zeros(B, P, dtype=torch.int64), torch.ones(B, L - P, dtype=torch.int64)], 1)
+    labels = torch.where(tt == 1, full, torch.full_like(full, -100))
+    ref_loss, rows, lab, ref_lg = R.forward_loss_ref(sd, cfg, full, None, None, labels, token_type_ids=tt,
+                                                     attention_mask=torch.ones(B, L, dtype=torch.int64), image_feats=raux["image_features"])
+    with torch.no_grad():
+        x, _ = eng.embed(full.to(cuda_device), feats)
+        h = eng.gemma_forward(x, B, L, eng.new_cache(B, L), bidirectional=False, causal_prefix=P)
+        summary, row_loss, row_argmax, lg = eng.labelled_loss(h, rows.to(cuda_device), lab.to(cuda_device).contiguous())
+    lerr = (lg.cpu() - ref_lg).abs()
+    print(f"[4B labelled forward] oracle+gpu {time.time() - t1:.0f}s | loss gpu {float(summary[0]):.5f} oracle {float(ref_loss):.5f} | "
+          f"logits ({tuple(lg.shape)}): max|d|={float(lerr.max()):.4f} rms={float(lerr.pow(2).mean().sqrt()):.4f} | "
+          f"argmax agreement {float((row_argmax.cpu() == ref_lg.argmax(-1)).float().mean()):.3f}")
+    assert int(summary[1]) == B * 13 and rows.numel() == B * 13
+    assert float(lerr.max()) < 2e-2 * float(ref_lg.abs().max()) + 2e-2
+    assert abs(float(summary[0]) - float(ref_loss)) < 2e-2 * abs(float(ref_loss))
 
 
 def test_labelled_forward_loss_vs_oracle_and_reference_golden(tiny_gpu, cuda_device):

@@ -610,13 +610,24 @@ extern "C" int svla_decode_step_small(const SvlaDecodeLayer* layers_dev, int n_l
     static_assert(sizeof(p) < 4000, "kernel parameter block");
     cudaError_t ce = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (ce != cudaSuccess) return ce;
-    kernel<<<grid, kThreads, smem, st>>>(p);
-    return cudaSuccess;
+    // Cooperative launch: the driver starts the grid only when ALL its CTAs can be resident at once (or fails with
+    // cudaErrorCooperativeLaunchTooLarge), so the spin barriers cannot deadlock when another stream / process shares the GPU.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
   };
   if (nb == 1) e = launch(svla_decode_step_small_kernel<1>);
   else if (nb == 2) e = launch(svla_decode_step_small_kernel<2>);
   else e = launch(svla_decode_step_small_kernel<4>);
-  SVLA_REQUIRE(e == cudaSuccess, "svla_decode_step_small: smem opt-in %zu failed: %s", smem, cudaGetErrorString(e));
+  SVLA_REQUIRE(e == cudaSuccess, "svla_decode_step_small: cooperative launch (smem %zu) failed: %s", smem, cudaGetErrorString(e));
   SVLA_LAUNCH_CHECK("svla_decode_step_small");
   return 0;
 }

@@ -213,8 +213,44 @@ def gen_model_train():
                         token_type_ids=tt.numpy(), labels=labels.numpy(), intrinsic=K.numpy(), **out)
 
 
+GRAD_KEYS = ("language_model.model.layers.2.self_attn.q_proj.weight", "language_model.model.layers.0.mlp.gate_proj.weight",
+             "language_model.model.layers.1.mlp.down_proj.weight", "language_model.model.layers.2.input_layernorm.weight",
+             "multi_modal_projector.linear.weight", "vision_tower.vision_model.encoder.layers.1.mlp.fc2.weight",
+             "vision_tower.vision_model.encoder.layers.0.self_attn.out_proj.weight",
+             "position_embedding_3d.position_embedding_head.0.weight", "position_embedding_3d.position_embedding_head.3.weight")
+
+
+def gen_model_train_grads():
+    """loss.backward() of the live reference (prefix-LM training mask) -> tests/golden/tiny_model_train_grads.npz: dLoss/dW of a
+    LoRA-target sample across the towers (train/spatialvla_finetune.py:262-270), every 3rd row / column to keep the file small.
+    Pins oracle/model_ref.loss_and_grads_ref, the checker of next round's backward kernels."""
+    cfg, px_u8, ids, tt, labels, K = train_inputs()
+    px = px_u8.float() / 255.0
+    model = compat.build_reference_model(cfg)
+    model.load_state_dict(synth_state_dict(cfg, seed=0), strict=True)
+    params = dict(model.named_parameters())
+    for p_ in params.values():
+        p_.requires_grad_(False)
+    for k in GRAD_KEYS:
+        params[k].requires_grad_(True)
+    B, L = ids.shape
+    o = model(input_ids=ids, pixel_values=px, intrinsic=K, labels=labels, use_cache=False, token_type_ids=tt,
+              attention_mask=torch.ones(B, L, dtype=torch.int64))
+    o.loss.backward()
+    out = {"loss": o.loss.detach().float().numpy()}
+    for k in GRAD_KEYS:
+        gk = params[k].grad.float()
+        out["grad:" + k] = (gk[::3, ::3] if gk.dim() == 2 else gk).numpy()
+        out["norm:" + k] = gk.norm().numpy()
+        print(f"grad {k}: norm {float(gk.norm()):.6e}")
+    np.savez_compressed(os.path.join(GOLD, "tiny_model_train_grads.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "grads":
+        gen_model_train_grads()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "padded":
         gen_model_padded()
         sys.exit(0)
@@ -225,3 +261,4 @@ if __name__ == "__main__":
     gen_model()
     gen_model_padded()
     gen_model_train()
+    gen_model_train_grads()

@@ -318,9 +318,10 @@ def image_features(sd, cfg, pixel_values, intrinsic, force_head=None, return_aux
     sig = siglip_forward(sd, cfg, (pixel_values - 0.5) / 0.5)
     aux = {"siglip": sig}
     if cfg.get("use_vision_zoe", True):
-        depth384, zaux = zoedepth_forward(sd, cfg, process_zoe(pixel_values), force_head, return_aux=True)
-        depth = depth_to_224(depth384)
-        xyz = backproject_patch(intrinsic, depth, cfg["vision_config"]["patch_size"], cfg["ego3d_patch_reso"])
+        with torch.no_grad():       # the reference runs ZoeDepth + back-projection under no_grad (:315-326): no gradient flows here
+            depth384, zaux = zoedepth_forward(sd, cfg, process_zoe(pixel_values), force_head, return_aux=True)
+            depth = depth_to_224(depth384)
+            xyz = backproject_patch(intrinsic, depth, cfg["vision_config"]["patch_size"], cfg["ego3d_patch_reso"])
         pos = ego3d_forward(sd, cfg, xyz)
         aux.update({"depth384": depth384, "xyz": xyz, "pos3d": pos, "zoe": zaux})
         sig = sig + pos
@@ -492,28 +493,34 @@ def forward_loss_ref(sd, cfg, input_ids, pixel_values, intrinsic, labels, token_
     column unmasked (prefix-LM); labels without token_type_ids = the inference mask (bidirectional).  Loss = shifted
     nn.CrossEntropyLoss over the full vocabulary, post-softcap logits, ignore_index rows dropped (:413-430).
     Returns (loss 0-dim fp32, flat row indices b*L+t of the labelled rows, their labels, their logits fp32 [R, V])."""
+    with torch.no_grad():
+        return _forward_loss(sd, cfg, input_ids, pixel_values, intrinsic, labels, token_type_ids, attention_mask, force_head,
+                             ignore_index, pad_token_id, image_feats)
+
+
+def _forward_loss(sd, cfg, input_ids, pixel_values, intrinsic, labels, token_type_ids, attention_mask, force_head, ignore_index,
+                  pad_token_id, image_feats):
     if attention_mask is not None and bool((attention_mask == 0).any()):
         raise NotImplementedError("padded batches are not covered by the labelled forward")
-    with torch.no_grad():
-        feats = image_feats             # precomputed get_image_features output (full-size tests reuse the one they already have)
-        if feats is None and pixel_values is not None:
-            feats = image_features(sd, cfg, pixel_values, intrinsic, force_head)
-        x = embed_inputs(sd, cfg, input_ids, feats)
-        B, L, _ = x.shape
-        cache = [None] * cfg["text_config"]["num_hidden_layers"]
-        if token_type_ids is not None:
-            prefix = prefix_length(token_type_ids) if attention_mask is not None else 0
-            h = gemma2_forward(sd, cfg, x, 0, cache, bidirectional=False, causal_prefix=prefix)
-        else:
-            h = gemma2_forward(sd, cfg, x, 0, cache, bidirectional=True)
-        if bool((labels == pad_token_id).any()):                       # :392-397
-            labels = torch.where(input_ids == pad_token_id, torch.full_like(labels, ignore_index), labels)
-        shift_labels = labels[:, 1:]
-        bi, ti = torch.nonzero(shift_labels != ignore_index, as_tuple=True)
-        rows = bi * L + ti
-        lab = shift_labels[bi, ti]
-        lg = lm_head_slice(sd, cfg, h.reshape(B * L, -1)[rows], 0, cfg["text_config"]["vocab_size"]).float()
-        loss = F.cross_entropy(lg, lab) if rows.numel() else torch.tensor(float("nan"))
+    feats = image_feats             # precomputed get_image_features output (full-size tests reuse the one they already have)
+    if feats is None and pixel_values is not None:
+        feats = image_features(sd, cfg, pixel_values, intrinsic, force_head)
+    x = embed_inputs(sd, cfg, input_ids, feats)
+    B, L, _ = x.shape
+    cache = [None] * cfg["text_config"]["num_hidden_layers"]
+    if token_type_ids is not None:
+        prefix = prefix_length(token_type_ids) if attention_mask is not None else 0
+        h = gemma2_forward(sd, cfg, x, 0, cache, bidirectional=False, causal_prefix=prefix)
+    else:
+        h = gemma2_forward(sd, cfg, x, 0, cache, bidirectional=True)
+    if bool((labels == pad_token_id).any()):                       # :392-397
+        labels = torch.where(input_ids == pad_token_id, torch.full_like(labels, ignore_index), labels)
+    shift_labels = labels[:, 1:]
+    bi, ti = torch.nonzero(shift_labels != ignore_index, as_tuple=True)
+    rows = bi * L + ti
+    lab = shift_labels[bi, ti]
+    lg = lm_head_slice(sd, cfg, h.reshape(B * L, -1)[rows], 0, cfg["text_config"]["vocab_size"]).float()
+    loss = F.cross_entropy(lg, lab) if rows.numel() else torch.tensor(float("nan"))
     return loss, rows, lab, lg
 
 
@@ -533,3 +540,22 @@ def training_metrics_ref(logit_rows, row_labels, actions, ranges, decode_fn):
     gt_actions = torch.as_tensor(actions).reshape(-1, 7).to(torch.float32)
     out["l1_loss"] = float(F.l1_loss(pred_actions.to(torch.float32), gt_actions))
     return out
+
+
+def loss_and_grads_ref(sd, cfg, input_ids, pixel_values, intrinsic, labels, grad_keys, token_type_ids=None, attention_mask=None,
+                       force_head=None):
+    """Oracle of the BACKWARD half of the training step (next round's kernels are checked against it):
+    torch autograd through the restated forward, dLoss/dW for the weights named in grad_keys (fp32).  A LoRA adapter on a
+    Linear W (PEFT: W + (alpha/r) B A, train/spatialvla_finetune.py:262-302) gets its gradients from dW by the chain rule,
+    dB = (alpha/r) dW A^T and dA = (alpha/r) B^T dW, so full-weight gradients pin every adapter gradient.  ZoeDepth is under
+    no_grad exactly like the reference (model/modeling_spatialvla.py:315-326)."""
+    sd2 = dict(sd)
+    leaves = {}
+    for k in grad_keys:
+        leaves[k] = sd[k].detach().clone().requires_grad_(True)
+        sd2[k] = leaves[k]
+    with torch.enable_grad():
+        loss, rows, lab, lg = _forward_loss(sd2, cfg, input_ids, pixel_values, intrinsic, labels, token_type_ids, attention_mask,
+                                            force_head, -100, 0, None)
+        loss.backward()
+    return loss.detach(), {k: v.grad.detach() for k, v in leaves.items()}

@@ -127,3 +127,39 @@ def test_labelled_forward_restatement_matches_reference_golden():
     import pytest
     with pytest.raises(NotImplementedError):
         R.prefix_length(torch.tensor([[0, 1, 0], [0, 1, 1]]))
+
+
+def test_backward_oracle_matches_reference_autograd_golden():
+    """oracle/model_ref.loss_and_grads_ref (autograd through the restatement; the checker of the backward kernels to come, SURVEY
+    §8f rank 1) against dLoss/dW minted by loss.backward() of the LIVE reference under the prefix-LM training mask
+    (oracle/gen_golden.gen_model_train_grads): a LoRA-target sample across Gemma2, the projector, SigLIP and the Ego3D head."""
+    from oracle.gen_golden import GRAD_KEYS
+    g, cfg, ids, tt, labels, px, K = _train_golden()
+    gg = np.load(os.path.join(GOLD, "tiny_model_train_grads.npz"))
+    sd = synth_state_dict(cfg, seed=0)
+    B, L = ids.shape
+    loss, grads = R.loss_and_grads_ref(sd, cfg, ids, px, K, labels, GRAD_KEYS, token_type_ids=tt,
+                                       attention_mask=torch.ones(B, L, dtype=torch.int64))
+    assert abs(float(loss) - float(gg["loss"])) < 2e-5 and abs(float(loss) - float(g["loss_prefix_lm"])) < 2e-5
+    for k in GRAD_KEYS:
+        got = grads[k]
+        ref, nrm = gg["grad:" + k], float(gg["norm:" + k])
+        sub = (got[::3, ::3] if got.dim() == 2 else got).numpy()
+        assert np.abs(sub - ref).max() < 2e-4 * max(np.abs(ref).max(), 1e-6) + 1e-7, k
+        assert abs(float(got.norm()) - nrm) < 2e-4 * nrm, k
+    # chain rule used for LoRA adapters (PEFT: W + (alpha/r) B A): dB = s dW A^T, dA = s B^T dW -- checked against autograd on
+    # an explicit adapter of one Gemma projection
+    k = "language_model.model.layers.2.self_attn.q_proj.weight"
+    gen = torch.Generator().manual_seed(0)
+    r, s = 4, 2.0
+    A = (torch.randn(r, sd[k].shape[1], generator=gen) * 0.05).requires_grad_(True)
+    Bm = (torch.randn(sd[k].shape[0], r, generator=gen) * 0.05).requires_grad_(True)
+    sd2 = dict(sd)
+    sd2[k] = sd[k] + s * (Bm @ A)
+    with torch.enable_grad():
+        l2, _, _, _ = R._forward_loss(sd2, cfg, ids, px, K, labels, tt, torch.ones(B, L, dtype=torch.int64), None, -100, 0, None)
+        l2.backward()
+    _, gw = R.loss_and_grads_ref(sd2 | {k: sd2[k].detach()}, cfg, ids, px, K, labels, (k,), token_type_ids=tt,
+                                 attention_mask=torch.ones(B, L, dtype=torch.int64))
+    assert (Bm.grad - s * gw[k] @ A.detach().t()).abs().max() < 1e-5 * max(1.0, float(Bm.grad.abs().max()))
+    assert (A.grad - s * Bm.detach().t() @ gw[k]).abs().max() < 1e-5 * max(1.0, float(A.grad.abs().max()))

@@ -203,6 +203,16 @@ int svla_cross_entropy_rows(const float* logits, int64_t rows, int64_t cols, int
                             int64_t ignore_index, float* row_loss, int64_t* row_argmax, int64_t row_offset, float* summary,
                             void* stream);
 
+/* M8b: backward of M8 -- gradient of the mean cross entropy (model/modeling_spatialvla.py:413-430) w.r.t. the PRE-soft-cap logits
+ * z (model/modeling_gemma2.py:993-997: logit = cap * tanh(z / cap)), emitted as the bf16 A operand of the dh = dz * W_head GEMM:
+ * dz[i, j] = (softmax(logits[i])[j] - [j == labels[i]]) * (1 - (logits[i, j] / cap)^2) / count, zero rows for ignored labels and
+ * zero columns in [cols, ldo) (K padding; ldo even).  logits fp32 [rows, ld] = entries [row_offset, row_offset + rows) of labels /
+ * row_loss as in svla_cross_entropy_rows; row_loss is that call's output (the row's logsumexp is row_loss + logit[label]);
+ * summary = its fp32 [3] summary of the WHOLE batch (count read on the device); softcap 0 = no soft-capping. rows <= 65535. */
+int svla_cross_entropy_bwd(const float* logits, int64_t rows, int64_t cols, int64_t ld, const int64_t* labels,
+                           int64_t ignore_index, const float* row_loss, int64_t row_offset, const float* summary,
+                           float softcap, void* dz_bf16, int64_t ldo, void* stream);
+
 /* M9 image preprocessing.
  * siglip: (x-0.5)/0.5 + im2col for the 14x14/14 patch conv (model/modeling_spatialvla.py:309;
  *         HF siglip :124-130,176-187): px fp32 [B,3,224,224] -> a bf16 [B*256, kpad] (kpad >= 588, zero padded)

@@ -559,3 +559,14 @@ def loss_and_grads_ref(sd, cfg, input_ids, pixel_values, intrinsic, labels, grad
                                             force_head, -100, 0, None)
         loss.backward()
     return loss.detach(), {k: v.grad.detach() for k, v in leaves.items()}
+
+
+def loss_tail_grads_ref(sd, cfg, h_rows, row_labels):
+    """d(mean CE)/d(final-normed hidden rows) by autograd through lm_head + soft-cap + nn.CrossEntropyLoss
+    (model/modeling_gemma2.py:993-997, model/modeling_spatialvla.py:413-430).  h_rows fp32 [R, H] -> (loss, dh [R, H])."""
+    hr = h_rows.detach().float().clone().requires_grad_(True)
+    with torch.enable_grad():
+        lg = lm_head_slice(sd, cfg, hr, 0, cfg["text_config"]["vocab_size"]).float()
+        loss = F.cross_entropy(lg, row_labels)
+        loss.backward()
+    return loss.detach(), hr.grad.detach()

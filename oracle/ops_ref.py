@@ -264,6 +264,22 @@ class RefOps:
             summary[1] = valid.sum()
             summary[2] = (row_argmax[:n][valid] == labels[:n][valid]).sum()
 
+    def cross_entropy_bwd(self, logits, labels, row_loss, summary, dz, *, row_offset=0, softcap=0.0, ignore_index=-100):
+        """d(mean CE)/d(pre-softcap logits): (softmax - onehot) * (1 - (logit/cap)^2) / count (model/modeling_spatialvla.py:413-430,
+        model/modeling_gemma2.py:993-997), zero for ignored rows and for the K-padding columns."""
+        self.launches += 1
+        r, c = logits.shape
+        lab = labels[row_offset:row_offset + r]
+        live = lab != ignore_index
+        lg = logits.double()
+        g = torch.softmax(lg, -1)
+        g[live, lab[live]] -= 1.0
+        if softcap:
+            g = g * (1.0 - (lg / softcap) ** 2)
+        g = g / float(summary[1]) * live[:, None]
+        dz.zero_()
+        dz[:, :c] = g.to(BF16)
+
     def siglip_patchify(self, px, a):
         self.launches += 1
         B = px.shape[0]

@@ -532,6 +532,48 @@ svla_cross_entropy_kernel(const float* __restrict__ logits, long long cols, long
   }
 }
 
+// Backward of the loss tail (first kernel of the training step's backward half): gradient of the mean cross
+// entropy w.r.t. the PRE-soft-cap logits z (logit = cap * tanh(z / cap)), written as the bf16 A operand of the dh = dz * W_head
+// GEMM:  dz[r, j] = (softmax(logit[r])[j] - [j == label_r]) * (1 - (logit[r, j] / cap)^2) / count,  0 for ignored rows.
+// The row's logsumexp comes from the forward kernel's output (row_loss = lse - logit[label]); count is read from the forward
+// summary on the device (no host sync).  Elementwise, HBM-bound: rows * cols * (4 B in + 2 B out).  grid = (column chunks, rows);
+// a thread owns adjacent column pairs so the bf16 output leaves as 4-byte stores (128 B per warp instruction).
+constexpr int kCeBwdThreads = 256;
+constexpr int kCeBwdPairs = 8;      // column pairs per thread -> 4096 columns per CTA
+
+__global__ void __launch_bounds__(kCeBwdThreads)
+svla_cross_entropy_bwd_kernel(const float* __restrict__ logits, long long cols, long long ld, const long long* __restrict__ labels,
+                              long long ignore_index, const float* __restrict__ row_loss, const float* __restrict__ summary,
+                              float softcap, __nv_bfloat16* __restrict__ dz, long long ldo) {
+  const long long row = blockIdx.y;
+  const float* r = logits + row * ld;
+  __nv_bfloat16* o = dz + row * ldo;
+  const long long lab = labels[row];
+  const bool live = lab != ignore_index && lab >= 0 && lab < cols;
+  const float lse = live ? row_loss[row] + r[lab] : 0.f;
+  const float inv_count = live ? 1.f / summary[1] : 0.f;
+  const float inv_cap2 = softcap > 0.f ? 1.f / (softcap * softcap) : 0.f;
+  const long long c0 = static_cast<long long>(blockIdx.x) * (kCeBwdThreads * kCeBwdPairs * 2);
+#pragma unroll
+  for (int p = 0; p < kCeBwdPairs; ++p) {
+    const long long j = c0 + 2LL * (p * kCeBwdThreads + threadIdx.x);
+    if (j >= ldo) break;
+    float g[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const long long jj = j + e;
+      float v = 0.f;
+      if (live && jj < cols) {
+        const float l = r[jj];
+        v = (ce_ex2((l - lse) * kCeLog2e) - (jj == lab ? 1.f : 0.f)) * (1.f - l * l * inv_cap2) * inv_count;
+      }
+      g[e] = v;                                  // columns in [cols, ldo) are the zero K padding of the GEMM operand
+    }
+    if (j + 1 < ldo) *reinterpret_cast<__nv_bfloat162*>(o + j) = __floats2bfloat162_rn(g[0], g[1]);
+    else o[j] = __float2bfloat16(g[0]);
+  }
+}
+
 // summary[0] = mean of row_loss over the non-ignored rows (NaN when there is none, like torch), [1] = their count,
 // [2] = rows whose argmax equals the label.  One CTA, fixed summation order: deterministic.
 __global__ void __launch_bounds__(256)
@@ -1402,6 +1444,24 @@ extern "C" int svla_cross_entropy_rows(const float* logits, int64_t rows, int64_
                                                          static_cast<long long>(row_offset + rows), static_cast<long long>(ignore_index), summary);
     SVLA_LAUNCH_CHECK("svla_cross_entropy_summary");
   }
+  return 0;
+}
+
+extern "C" int svla_cross_entropy_bwd(const float* logits, int64_t rows, int64_t cols, int64_t ld, const int64_t* labels,
+                                      int64_t ignore_index, const float* row_loss, int64_t row_offset, const float* summary,
+                                      float softcap, void* dz_bf16, int64_t ldo, void* stream) {
+  SVLA_REQUIRE(logits && labels && row_loss && summary && dz_bf16, "svla_cross_entropy_bwd: null operand");
+  SVLA_REQUIRE(rows > 0 && rows <= 65535 && cols > 0 && ld >= cols && ldo >= cols && (ldo % 2) == 0 && row_offset >= 0,
+               "svla_cross_entropy_bwd: bad shape (rows %lld cols %lld ld %lld ldo %lld)", static_cast<long long>(rows),
+               static_cast<long long>(cols), static_cast<long long>(ld), static_cast<long long>(ldo));
+  SVLA_REQUIRE((reinterpret_cast<uintptr_t>(dz_bf16) & 3) == 0, "svla_cross_entropy_bwd: dz must be 4-byte aligned");
+  const long long per_cta = kCeBwdThreads * kCeBwdPairs * 2;
+  dim3 grid(static_cast<unsigned>((ldo + per_cta - 1) / per_cta), static_cast<unsigned>(rows));
+  svla_cross_entropy_bwd_kernel<<<grid, kCeBwdThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, static_cast<long long>(cols), static_cast<long long>(ld), reinterpret_cast<const long long*>(labels) + row_offset,
+      static_cast<long long>(ignore_index), row_loss + row_offset, summary, softcap, static_cast<__nv_bfloat16*>(dz_bf16),
+      static_cast<long long>(ldo));
+  SVLA_LAUNCH_CHECK("svla_cross_entropy_bwd");
   return 0;
 }
 

@@ -105,6 +105,7 @@ class SpatialVLAEngine:
              "layers": []}
         self._lm_head_full_src = sd["language_model.lm_head.weight"]
         self._lm_head_full = None
+        self._lm_head_full_t = None
         g["spatial"] = W("spatial_embed_tokens.weight") if self.cfg.get("use_spatial_token", True) else None
         for i in range(t["num_hidden_layers"]):
             q = f"{p}layers.{i}."
@@ -223,6 +224,17 @@ class SpatialVLAEngine:
         if self._lm_head_full is None:
             self._lm_head_full = self._w(self._lm_head_full_src, BF16)
         return self._lm_head_full
+
+    def lm_head_full_t(self):
+        """bf16 [H, Vpad]: the lm_head weight transposed, V padded with zero columns to a multiple of 8 (16-byte rows for TMA) --
+        the K-major B operand of dh = dz @ W_head in the backward of the loss tail.  Built once (1.2 GB at the 4B size)."""
+        if self._lm_head_full_t is None:
+            w = self.lm_head_full()
+            V, H = w.shape
+            t = self.ops.zeros((H, (V + 7) // 8 * 8), BF16)
+            t[:, :V] = w.t()
+            self._lm_head_full_t = t
+        return self._lm_head_full_t
 
     # ------------------------------------------------------------------------------------------ small helpers
     def _lin(self, a, w, rows, dtype=BF16, **kw):
@@ -668,6 +680,30 @@ class SpatialVLAEngine:
             if keep_logits and R <= self.loss_chunk_rows:
                 kept = lg
         return summary, row_loss, row_argmax, kept
+
+    def labelled_loss_backward(self, h, rows, row_labels, ignore_index=-100):
+        """Loss tail forward + backward -- the first piece of the training step's backward half.
+        Returns (summary, row_loss, dh fp32 [R, H]) with dh = d(mean CE) / d(final-normed hidden rows h[rows]):
+        dz = (softmax - onehot) * (1 - (logit/cap)^2) / count in bf16 (svla_cross_entropy_bwd), then dh = dz @ W_head on the
+        tensor cores (K = vocabulary).  With more rows than one chunk the logits are recomputed chunk by chunk in the second pass
+        instead of being kept (4.3 GB per 4096 rows)."""
+        ops = self.ops
+        summary, row_loss, _, kept = self.labelled_loss(h, rows, row_labels, ignore_index=ignore_index, keep_logits=True)
+        R, V, H = rows.shape[0], self.t["vocab_size"], self.t["hidden_size"]
+        cap = self.t["final_logit_softcapping"]
+        wt = self.lm_head_full_t()
+        hr = h.index_select(0, rows)
+        dh = ops.empty((R, H), F32)
+        for r0 in range(0, R, self.loss_chunk_rows):
+            r1 = min(R, r0 + self.loss_chunk_rows)
+            lg = kept
+            if lg is None:
+                lg = ops.empty((r1 - r0, V), F32)
+                ops.gemm(hr[r0:r1], self.lm_head_full(), out_f32=lg, act=ACT_SOFTCAP if cap else ACT_NONE, act_param=cap or 0.0)
+            dz = ops.empty((r1 - r0, wt.shape[1]), BF16)
+            ops.cross_entropy_bwd(lg, row_labels, row_loss, summary, dz, row_offset=r0, softcap=cap or 0.0, ignore_index=ignore_index)
+            ops.gemm(dz, wt, out_f32=dh[r0:r1])
+        return summary, row_loss, dh
 
     def language_stage(self, ids, feats, n_new, forced_tokens=None, logs=None, pads=None):
         """Embed + bidirectional prefill + n_new greedy action tokens (argmax over the action slice) -> int64 [B, n_new]"""

@@ -252,6 +252,20 @@ class CudaOps:
                                                  self._stream()),
                 "svla_cross_entropy_rows")
 
+    def cross_entropy_bwd(self, logits, labels, row_loss, summary, dz, *, row_offset=0, softcap=0.0, ignore_index=-100):
+        """dz bf16 [rows, ldo >= cols, even] <- d(mean CE)/d(pre-softcap logits) for the chunk logits fp32 [rows, cols] (entries
+        [row_offset, +rows) of labels / row_loss from cross_entropy_rows; summary = its whole-batch summary)."""
+        _req(logits.dtype == F32 and logits.dim() == 2 and logits.stride(1) == 1, "cross_entropy_bwd: bad logits")
+        _req(dz.dtype == BF16 and dz.dim() == 2 and dz.stride(1) == 1 and dz.shape[0] == logits.shape[0]
+             and dz.shape[1] >= logits.shape[1] and dz.shape[1] % 2 == 0 and dz.stride(0) == dz.shape[1], "cross_entropy_bwd: bad dz")
+        _req(labels.dtype == torch.int64 and labels.is_contiguous() and row_loss.dtype == F32 and row_loss.is_contiguous()
+             and row_loss.shape == labels.shape and row_offset + logits.shape[0] <= labels.shape[0], "cross_entropy_bwd: labels / row_loss")
+        _req(summary.dtype == F32 and summary.numel() == 3, "cross_entropy_bwd: summary fp32 [3]")
+        L.check(self.lib.svla_cross_entropy_bwd(_ptr(logits), logits.shape[0], logits.shape[1], logits.stride(0), _ptr(labels),
+                                                int(ignore_index), _ptr(row_loss), int(row_offset), _ptr(summary), float(softcap or 0.0),
+                                                _ptr(dz), dz.shape[1], self._stream()),
+                "svla_cross_entropy_bwd")
+
     def siglip_patchify(self, px, a):
         _req(px.dtype == F32 and px.is_contiguous() and tuple(px.shape[1:]) == (3, 224, 224), "siglip_patchify: px")
         L.check(self.lib.svla_siglip_patchify(_ptr(px), _ptr(a), px.shape[0], a.shape[1], self._stream()),

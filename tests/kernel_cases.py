@@ -683,7 +683,39 @@ def cross_entropy_case(dev="cuda:0"):
     return res
 
 
-FUSED_CASES = [layernorm_case, rmsnorm_case, rope_case, embed_case, argmax_case, cross_entropy_case, patchify_case, assemble_concat_case,
+def cross_entropy_bwd_case(dev="cuda:0"):
+    """svla_cross_entropy_bwd vs (softmax - onehot) * softcap' / count in float64: odd vocabulary (unaligned fp32 rows), K padding
+    columns zeroed, ignored rows zero, chunked calls, with and without soft-capping."""
+    res = Result("cross_entropy_bwd")
+    for (rows, cols, chunk, cap) in ((19, 265347, 19, 30.0), (9, 9216, 4, 30.0), (5, 3, 5, 0.0), (70, 1001, 32, 30.0)):
+        g = _gen(rows * 3 + cols)
+        lg = _randn(g, rows, cols, scale=6.0)
+        if cap:
+            lg = cap * torch.tanh(lg / cap)                       # what the lm_head GEMM epilogue hands over
+        lab = torch.randint(0, cols, (rows,), generator=g)
+        lab[1::5] = -100
+        ldo = (cols + 7) // 8 * 8
+
+        def run(ops, to):
+            l_, y = to(lg), to(lab)
+            rl, ra, sm = ops.zeros((rows,), F32), ops.zeros((rows,), torch.int64), ops.zeros((3,), F32)
+            ops.cross_entropy_rows(l_, y, rl, ra, summary=sm)
+            dz = ops.zeros((rows, ldo), BF16) + 7.0               # poison: every element must be written
+            for r0 in range(0, rows, chunk):
+                r1 = min(rows, r0 + chunk)
+                ops.cross_entropy_bwd(l_[r0:r1], y, rl, sm, dz[r0:r1], row_offset=r0, softcap=cap)
+            return dz
+        c, r = _both(run, dev)
+        c, r = c.float().cpu(), r.float()
+        res.add(f"dz[{cols}]", float((c - r).abs().max()) / float(r.abs().max()), 1e-2)          # bf16 output
+        res.add(f"pad+ignored[{cols}]", float(c[:, cols:].abs().max() if ldo > cols else 0.0) + float(c[1::5].abs().max()), 0)
+        # the bf16 rounding must not bias the row sums: sum_j dz / softcap' = 0 per live row (softmax - onehot sums to zero)
+        if not cap:
+            res.add(f"rowsum[{cols}]", float(c[0::5].sum(-1).abs().max()), 2e-2)
+    return res
+
+
+FUSED_CASES = [layernorm_case, rmsnorm_case, rope_case, embed_case, argmax_case, cross_entropy_case, cross_entropy_bwd_case, patchify_case, assemble_concat_case,
                shuffle_im2col_case, bilinear_case, zoe_tail_case, ego3d_case, tokenizer_case]
 
 ALL_CASES = {c.__name__: c for c in (SIMT_CASES + GEMM_CASES + PAIR_CASES + TMA_EPI_CASES + ROWTILE_CASES + SKINNY_CASES + ATTN_CASES + FUSED_CASES)}

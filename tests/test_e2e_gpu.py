@@ -328,3 +328,25 @@ def test_action_metrics_on_gpu_match_reference_metric_block(tiny_gpu, cuda_devic
     for k in ref:
         assert (np.isnan(got[k]) and np.isnan(ref[k])) or abs(got[k] - ref[k]) < 1e-6, (k, got[k], ref[k])
     assert got["accuracy"] > 0.0
+
+
+def test_loss_tail_backward_on_gpu_matches_autograd_oracle(tiny_gpu, cuda_device):
+    """First backward piece of the training step on the GPU: d(mean CE)/d(final hidden rows) = cross-entropy backward kernel
+    (bf16 dz) + dz @ W_head on the tcgen05 GEMM (K = vocabulary, zero-padded to 16-byte rows), against autograd through the oracle."""
+    cfg, _, _, _, sd, eng = tiny_gpu
+    g = torch.Generator().manual_seed(11)
+    H, V = cfg["text_config"]["hidden_size"], cfg["text_config"]["vocab_size"]
+    h = (torch.randn(300, H, generator=g) * 2.0).to(torch.bfloat16)
+    rows = torch.randperm(300, generator=g)[:150].sort().values
+    lab = torch.randint(0, V, (150,), generator=g)
+    try:
+        for chunk in (4096, 64):                     # single chunk (logits kept) and the recompute path (64 + 64 + 22 rows)
+            eng.loss_chunk_rows = chunk
+            summary, row_loss, dh = eng.labelled_loss_backward(h.to(cuda_device), rows.to(cuda_device), lab.to(cuda_device))
+            torch.cuda.synchronize()
+            ref_loss, ref_dh = R.loss_tail_grads_ref(sd, cfg, h[rows].float(), lab)
+            assert abs(float(summary[0]) - float(ref_loss)) < 5e-3
+            err = float((dh.cpu() - ref_dh).abs().max() / ref_dh.abs().max())
+            assert err < 2e-2, (chunk, err)
+    finally:
+        eng.loss_chunk_rows = 4096

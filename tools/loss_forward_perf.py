@@ -86,6 +86,13 @@ hr = h.index_select(0, rows)
 ms_gemm = timed(lambda: ops.gemm(hr, w, out_f32=lg, act=ACT_SOFTCAP, act_param=30.0), args.iters)
 rl, ra, sm = ops.empty((R,), F32), ops.empty((R,), torch.int64), ops.empty((3,), F32)
 ms_ce = timed(lambda: ops.cross_entropy_rows(lg, lab, rl, ra, summary=sm), args.iters)
+# backward of the loss tail: cross-entropy backward kernel (fp32 logits in, bf16 dz out) + dh = dz @ W_head (K = vocabulary)
+wt = eng.lm_head_full_t()
+dz = ops.empty((R, wt.shape[1]), torch.bfloat16)
+ms_ce_bwd = timed(lambda: ops.cross_entropy_bwd(lg, lab, rl, sm, dz, softcap=30.0), args.iters)
+dh = ops.empty((R, H), F32)
+ms_dh = timed(lambda: ops.gemm(dz, wt, out_f32=dh), args.iters)
+ms_tail_fb = timed(lambda: eng.labelled_loss_backward(h, rows, lab), args.iters)
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
 print(json.dumps({
     "workload": f"forward(labels) {args.config} B={B} L={L} prefix={P} prefix-LM mask, {R} labelled rows x V={V}",
@@ -94,6 +101,10 @@ print(json.dumps({
     "loss_tail_ms": round(ms_tail, 3),
     "lm_head_gemm_ms": round(ms_gemm, 3), "lm_head_TFLOPs": round(2.0 * R * V * H / ms_gemm / 1e9, 1),
     "cross_entropy_ms": round(ms_ce, 3), "cross_entropy_GBs": round(R * V * 4 / ms_ce / 1e6, 1),
-    "cross_entropy_algorithmic_bytes": R * V * 4, "hbm_peak_GBs": peaks.get("hbm_gbs"),
+    "cross_entropy_algorithmic_bytes": R * V * 4,
+    "loss_tail_fwd_bwd_ms": round(ms_tail_fb, 3),
+    "cross_entropy_bwd_ms": round(ms_ce_bwd, 3), "cross_entropy_bwd_GBs": round(R * V * 6 / ms_ce_bwd / 1e6, 1),
+    "dh_gemm_ms": round(ms_dh, 3), "dh_gemm_TFLOPs": round(2.0 * R * V * H / ms_dh / 1e9, 1),
+    "dh_gemm_note": "M=%d N=%d K=%d: 36 output tiles only, no split-K yet" % (R, H, V), "hbm_peak_GBs": peaks.get("hbm_gbs"),
     "note": "CUDA events on the launching stream, L2 flushed (256 MiB write) before every repetition, p50 of %d" % args.iters,
 }), flush=True)

@@ -656,6 +656,7 @@ class SpatialVLAEngine:
             self.ops.gemm(h_rows, self.gem["head_act"], out_f32=lg, act=ACT_SOFTCAP if cap else ACT_NONE, act_param=cap or 0.0)
         return lg
 
+    dh_block_n = int(os.environ.get("SVLA_DH_BLOCK_N", "64"))
     loss_chunk_rows = 4096       # labelled rows per lm_head GEMM + cross-entropy launch (fp32 logits: 4096 x 265 347 x 4 B = 4.3 GB)
 
     def labelled_loss(self, h, rows, row_labels, ignore_index=-100, keep_logits=True):
@@ -702,7 +703,9 @@ class SpatialVLAEngine:
                 ops.gemm(hr[r0:r1], self.lm_head_full(), out_f32=lg, act=ACT_SOFTCAP if cap else ACT_NONE, act_param=cap or 0.0)
             dz = ops.empty((r1 - r0, wt.shape[1]), BF16)
             ops.cross_entropy_bwd(lg, row_labels, row_loss, summary, dz, row_offset=r0, softcap=cap or 0.0, ignore_index=ignore_index)
-            ops.gemm(dz, wt, out_f32=dh[r0:r1])
+            # few rows, K = vocabulary: narrow n-tiles are the only way to more CTAs until this GEMM gets split-K
+            # (416 rows x 2304: 36 tiles at BN=256, 72 at 128, 144 at 64 on 148 SMs)
+            ops.gemm(dz, wt, out_f32=dh[r0:r1], block_n=self.dh_block_n if (r1 - r0) <= 1024 else 0)
         return summary, row_loss, dh
 
     def language_stage(self, ids, feats, n_new, forced_tokens=None, logs=None, pads=None):

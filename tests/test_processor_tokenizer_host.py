@@ -62,3 +62,54 @@ def test_unnormalise_formula():
     a = p._unnormalize(n, "bridge")
     np.testing.assert_allclose(a[0, :3], [0.05, 0.2, -0.1])
     assert a[0, 6] == 1.0                                     # masked-out gripper passes through
+
+
+def test_training_sample_chain_processor_to_labelled_forward():
+    """The training-sample path of the reference end to end on the host: SpatialVLAProcessor(suffix_actions=...) builds prefix +
+    action tokens + EOS with token types and labels (model/processing_spatialvla.py:103-192, train/monkey_patch.py:21-75), the
+    model's forward(labels=...) consumes it (prefix-LM mask) and action_metrics de-tokenises the predictions.  The grid kernels
+    behind the tokenizer need a GPU, so their oracle restatement is patched in; the model runs on the torch op re-statements."""
+    from oracle import model_ref as R
+    from oracle import tokenizer_ref as T
+    from oracle.ops_ref import RefOps
+    from spatialvla_b200 import SpatialVLAProcessor
+    from spatialvla_b200.configs import get_config_dict
+    from spatialvla_b200.modeling_spatialvla import SpatialVLAForConditionalGeneration
+    from spatialvla_b200.weights import synth_state_dict
+    tok = FakeTokenizer(base=1010)                    # text ids of the fake tokenizer stay below 1003
+    p = SpatialVLAProcessor(FakeImageProcessor(), tok, statistics=STATS, intrinsic_config=INTR, action_config=ACTION_CONFIG,
+                            action_chunk_size=2)
+    tk = p.action_tokenizer
+    nb = ACTION_CONFIG["num_bins"]
+    tk.encode_local_ids = lambda a: T.encode(np.asarray(a, dtype=np.float64).reshape(-1, 7), tk.bin_policy, nb).astype(np.int32)
+    tk.decode_token_ids_to_actions = lambda ids: T.decode(np.asarray(ids) - tk.action_token_begin_idx, tk.bin_policy, nb)
+    # the tiny model config follows the tokenizer (like a real checkpoint's config.json does): image / action token ids, vocabulary
+    cfg = get_config_dict("tiny")
+    lo = tk.action_token_begin_idx
+    cfg["image_token_index"], cfg["action_token_begin_idx"] = p.image_token_id, lo
+    cfg["vocab_size"] = cfg["text_config"]["vocab_size"] = (lo + nb["total"] + 15) // 8 * 8
+    rng = np.random.default_rng(4)
+    actions = rng.uniform(-1, 1, size=(2, 7))                                  # one sample, chunk of 2 actions
+    img = (rng.random((224, 224, 3)) * 255).astype(np.uint8)
+    out = p(images=[img], text=["pick up the cup"], unnorm_key="bridge", suffix_actions=actions)
+    ids, tt, labels = out["input_ids"], out["token_type_ids"], out["labels"]
+    n_suffix = 2 * 3 + 1                                                        # 3 tokens per action + EOS
+    assert int(tt.sum()) == n_suffix and (tt[0, -n_suffix:] == 1).all() and (tt[0, :-n_suffix] == 0).all()
+    assert (labels[0, :-n_suffix] == -100).all() and torch.equal(labels[0, -n_suffix:], ids[0, -n_suffix:])
+    assert int(ids[0, -1]) == 1                                                 # EOS
+    want = T.encode(actions, tk.bin_policy, nb) + lo                            # the suffix ids ARE the grid ids of the actions
+    assert np.array_equal(ids[0, -n_suffix:-1].numpy().reshape(2, 3), want)
+    sd = synth_state_dict(cfg, seed=0)
+    m = SpatialVLAForConditionalGeneration(cfg, sd, ops=RefOps())
+    res = m(input_ids=ids, pixel_values=out["pixel_values"], intrinsic=out["intrinsic"], attention_mask=out["attention_mask"],
+            token_type_ids=tt, labels=labels)
+    assert res.label_rows.numel() == n_suffix and torch.isfinite(res.loss)
+    ref_loss, rows, lab, _ = R.forward_loss_ref(sd, cfg, ids, out["pixel_values"], out["intrinsic"], labels, token_type_ids=tt,
+                                                attention_mask=out["attention_mask"], force_head=m.engine.last_router_head)
+    assert torch.equal(res.label_rows, rows) and abs(float(res.loss) - float(ref_loss)) < 1e-2
+    met = m.action_metrics(res, actions, tk)
+    assert 0.0 <= met["accuracy"] <= 1.0 and met["l1_loss"] >= 0.0
+    # a perfect prediction gives accuracy 1 and an L1 distance of at most one bin width
+    res.row_argmax = res.row_labels.clone()
+    met = m.action_metrics(res, actions, tk)
+    assert met["accuracy"] == 1.0 and met["translation_accuracy"] == 1.0 and met["gripper_accuracy"] == 1.0 and met["l1_loss"] < 0.3

@@ -213,6 +213,27 @@ def gen_model_train():
                         token_type_ids=tt.numpy(), labels=labels.numpy(), intrinsic=K.numpy(), **out)
 
 
+ADAPT_BINS = {"translation": {"theta_bins": 4, "phi_bins": 5, "r_bins": 3}, "rotation": {"roll_bins": 3, "pitch_bins": 4, "yaw_bins": 2},
+              "gripper": 2}
+ADAPT_GS0 = {k: {"mu": 0.05 * i - 0.1, "sigma": 0.3 + 0.05 * i} for i, k in enumerate(("theta", "phi", "r", "roll", "pitch", "yaw"))}
+ADAPT_GS1 = {k: {"mu": -0.04 * i + 0.1, "sigma": 0.45 - 0.03 * i} for i, k in enumerate(("theta", "phi", "r", "roll", "pitch", "yaw"))}
+
+
+def gen_adaption():
+    """spatial_embedding_adaption of the live reference (model/action_tokenizer.py:372-430) on a small grid
+    -> tests/golden/embedding_adaption.npz (old embeddings, re-sampled embeddings, new bin edges)."""
+    _, tok_mod, _, _ = compat.import_reference()
+    n_tok = 4 * 5 * 3 + 3 * 4 * 2 + 2
+    w = torch.randn(n_tok, 6, generator=torch.Generator().manual_seed(0))
+    tk = tok_mod.SpatialActionTokenizer(FakeHFTokenizer(1000), num_bins=ADAPT_BINS, gs_params=ADAPT_GS0, min_sigma=0.1)
+    emb = torch.nn.Embedding(n_tok, 6)
+    emb.weight.data.copy_(w)
+    tk.spatial_embedding_adaption(ADAPT_GS1, emb, min_sigma=0.2, adpt_feature=True)
+    edges = {f"edge_{k}": np.asarray(tk.bin_policy[bt][k]) for bt in ("translation", "rotation") for k in ADAPT_BINS[bt]}
+    np.savez_compressed(os.path.join(GOLD, "embedding_adaption.npz"), before=w.numpy(), after=emb.weight.data.numpy(), **edges)
+    print("embedding_adaption: NaN rows", int(torch.isnan(emb.weight.data).any(1).sum()), "of", n_tok)
+
+
 GRAD_KEYS = ("language_model.model.layers.2.self_attn.q_proj.weight", "language_model.model.layers.0.mlp.gate_proj.weight",
              "language_model.model.layers.1.mlp.down_proj.weight", "language_model.model.layers.2.input_layernorm.weight",
              "multi_modal_projector.linear.weight", "vision_tower.vision_model.encoder.layers.1.mlp.fc2.weight",
@@ -248,6 +269,9 @@ def gen_model_train_grads():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "adaption":
+        gen_adaption()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "grads":
         gen_model_train_grads()
         sys.exit(0)
@@ -262,3 +286,4 @@ if __name__ == "__main__":
     gen_model_padded()
     gen_model_train()
     gen_model_train_grads()
+    gen_adaption()

@@ -113,3 +113,30 @@ def test_training_sample_chain_processor_to_labelled_forward():
     res.row_argmax = res.row_labels.clone()
     met = m.action_metrics(res, actions, tk)
     assert met["accuracy"] == 1.0 and met["translation_accuracy"] == 1.0 and met["gripper_accuracy"] == 1.0 and met["l1_loss"] < 0.3
+
+
+def test_spatial_embedding_adaption_matches_reference_golden():
+    """Fine-tune-time re-gridding (model/action_tokenizer.py:372-430): golden minted from the live reference
+    (oracle/gen_golden.py adaption) -- new bin edges exactly, re-sampled embeddings to 1e-6, NaN pattern (outside the old hull) equal."""
+    import os
+    from oracle.gen_golden import ADAPT_BINS, ADAPT_GS0, ADAPT_GS1
+    from spatialvla_b200 import SpatialActionTokenizer
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "embedding_adaption.npz"))
+    tk = SpatialActionTokenizer(FakeTokenizer(1000), ADAPT_BINS, gs_params=ADAPT_GS0, min_sigma=0.1)
+    emb = torch.nn.Embedding(g["before"].shape[0], g["before"].shape[1])
+    emb.weight.data.copy_(torch.from_numpy(g["before"]))
+    edges_before = tk._edges.copy()
+    tk.spatial_embedding_adaption(ADAPT_GS1, emb, min_sigma=0.2, adpt_feature=True)
+    for bt in ("translation", "rotation"):
+        for k in ADAPT_BINS[bt]:
+            assert np.array_equal(np.asarray(tk.bin_policy[bt][k]), g[f"edge_{k}"]), k
+    assert not np.array_equal(tk._edges, edges_before)                 # the device-side edge table follows the new policy
+    a, b = emb.weight.data.numpy(), g["after"]
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.allclose(np.nan_to_num(a), np.nan_to_num(b), atol=1e-6)
+    # adpt_feature=False only swaps the grids
+    tk2 = SpatialActionTokenizer(FakeTokenizer(1000), ADAPT_BINS, gs_params=ADAPT_GS0, min_sigma=0.1)
+    emb2 = torch.nn.Embedding(g["before"].shape[0], g["before"].shape[1])
+    emb2.weight.data.copy_(torch.from_numpy(g["before"]))
+    tk2.spatial_embedding_adaption(ADAPT_GS1, emb2, min_sigma=0.2)
+    assert np.array_equal(emb2.weight.data.numpy(), g["before"]) and np.array_equal(tk2._edges, tk._edges)

@@ -177,8 +177,7 @@ class SpatialVLAForConditionalGeneration:
             if past_key_values is not None or inputs_embeds is not None or position_ids is not None or output_attentions or output_hidden_states:
                 raise NotImplementedError("labelled forward: past_key_values / inputs_embeds / position_ids / output_* are not supported")
             return self._forward_with_labels(input_ids, pixel_values, intrinsic, attention_mask, token_type_ids, labels)
-        if token_type_ids is not None:
-            pass                                 # without labels the reference ignores token types (is_training False, :357)
+        # token_type_ids without labels: the reference ignores them (is_training is False, :357)
         if inputs_embeds is not None or position_ids is not None or output_attentions or output_hidden_states:
             raise NotImplementedError("inputs_embeds / position_ids / output_attentions / output_hidden_states")
         eng = self.engine

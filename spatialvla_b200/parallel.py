@@ -44,3 +44,15 @@ def reduce_loss(outputs, group=None):
         dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
     s, n, h = (float(v) for v in part.cpu())
     return (s / n if n else float("nan")), (h / n if n else float("nan")), int(n)
+
+
+def allreduce_gradients(arena, group=None, average: bool = True):
+    """The gradient exchange of the data-parallel fine-tune step (BASELINE.json config #5): ONE all-reduce over the flat gradient
+    buffer of the LoRA arena (spatialvla_b200/lora.py; 59.2 M elements at the 4B-224 size), NCCL over NVLink on GPUs, gloo on CPU;
+    `average` divides by the world size (the mean DDP / ZeRO-1 applies, scripts/zero1.json).  Returns the number of elements sent."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(arena.grad, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            arena.grad.div_(dist.get_world_size(group))
+    return arena.grad.numel()

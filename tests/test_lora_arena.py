@@ -105,3 +105,27 @@ def test_gradient_allreduce_is_one_collective_over_the_flat_arena():
     assert n == arena.numel() and calls == [arena.numel()]                  # exactly one all-reduce, over the whole buffer
     assert head == [0.0, 1.5, 3.0, 4.5, 6.0] and last == (arena.numel() - 1) * 1.5      # mean of ranks: (1 + 2) / 2
     assert abs(psum - float(arena.param.abs().sum())) < 1e-3                # parameters untouched
+
+
+def test_merged_adapters_serve_through_the_unchanged_engine():
+    """Fine-tuned model at inference: adapters folded into the base weights (PEFT merge_and_unload) run through the normal
+    predict_action path; the fp32 oracle on the same merged weights is the reference."""
+    from oracle import model_ref as R
+    from oracle.gen_golden import tiny_inputs
+    from oracle.ops_ref import RefOps
+    from spatialvla_b200.engine import SpatialVLAEngine
+    cfg, px_u8, ids, K = tiny_inputs()
+    px = px_u8.float() / 255.0
+    sd = synth_state_dict(cfg, seed=0)
+    arena = LoRAArena(state_dict_spec(cfg), r=4, alpha=8.0, seed=3)
+    g = torch.Generator().manual_seed(4)
+    for k, _, _ in arena.keys:
+        arena.B[k].copy_(torch.randn(arena.B[k].shape, generator=g) * 0.02)
+    merged = arena.merged_state_dict(sd)
+    eng = SpatialVLAEngine(cfg, merged, RefOps())
+    with torch.no_grad():
+        toks, logits = eng.generate_actions(ids, px, K, 4, return_logits=True)
+    ref_toks, ref_logits = R.predict_action_ref(merged, cfg, ids, px, K, 4, force_head=eng.last_router_head)
+    base_toks, base_logits = R.predict_action_ref(sd, cfg, ids, px, K, 4, force_head=eng.last_router_head)
+    assert (logits - ref_logits).abs().max() < 6e-2
+    assert (ref_logits - base_logits).abs().max() > 0.2          # the adapters changed the model well beyond the comparison tolerance

@@ -213,6 +213,17 @@ int svla_cross_entropy_bwd(const float* logits, int64_t rows, int64_t cols, int6
                            int64_t ignore_index, const float* row_loss, int64_t row_offset, const float* summary,
                            float softcap, void* dz_bf16, int64_t ldo, void* stream);
 
+/* AdamW step on flat fp32 buffers (the LoRA arena of the fine-tune config: HF Trainer default adamw_torch, scripts/spatialvla_4b_finetune/
+ * finetune_lora.sh; arithmetic order of torch.optim.AdamW): grad is multiplied by grad_scale first (1 / world size or a clipping
+ * coefficient), p *= 1 - lr * wd, m = lerp(m, g, 1 - beta1), v = beta2 v + (1 - beta2) g^2,
+ * p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps).  step counts from 1.  Buffers 16-byte aligned.
+ * Hyper-parameters are doubles: the derived scalars (1 - beta2, lr / (1 - beta1^step), ...) are formed in double on the host, as
+ * torch forms them from Python floats, and only then rounded to fp32.
+ * STATUS: written at the end of round 1; its GPU parity case (tests/kernel_cases.py::adamw_case) has NOT passed on hardware yet
+ * (first attempt failed on the fp32 1 - beta2 rounding fixed here, then the GPU budget ran out), so nothing calls it. */
+int svla_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                    double beta2, double eps, double weight_decay, int64_t step, double grad_scale, void* stream);
+
 /* M9 image preprocessing.
  * siglip: (x-0.5)/0.5 + im2col for the 14x14/14 patch conv (model/modeling_spatialvla.py:309;
  *         HF siglip :124-130,176-187): px fp32 [B,3,224,224] -> a bf16 [B*256, kpad] (kpad >= 588, zero padded)

@@ -280,6 +280,17 @@ class RefOps:
         dz.zero_()
         dz[:, :c] = g.to(BF16)
 
+    def adamw_step(self, param, grad, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step, grad_scale=1.0):
+        """torch.optim.AdamW single-tensor arithmetic (torch/optim/adamw.py: _single_tensor_adamw), in place."""
+        self.launches += 1
+        g = grad * grad_scale
+        param.mul_(1 - lr * weight_decay)
+        exp_avg.lerp_(g, 1 - beta1)
+        exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+        denom = (exp_avg_sq.sqrt() / (bc2 ** 0.5)).add_(eps)
+        param.addcdiv_(exp_avg, denom, value=-(lr / bc1))
+
     def siglip_patchify(self, px, a):
         self.launches += 1
         B = px.shape[0]

@@ -76,6 +76,7 @@ SIGNATURES = {
     "svla_embed_tokens": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _L, _I, _F, _P, _P]),
     "svla_argmax_rows": (_I, [_P, _L, _L, _L, _L, _P, _L, _P]),
     "svla_cross_entropy_rows": (_I, [_P, _L, _L, _L, _P, _L, _P, _P, _L, _P, _P]),
+    "svla_adamw_step": (_I, [_P, _P, _P, _P, _L, _D, _D, _D, _D, _D, _L, _D, _P]),
     "svla_cross_entropy_bwd": (_I, [_P, _L, _L, _L, _P, _L, _P, _L, _P, _F, _P, _L, _P]),
     "svla_siglip_patchify": (_I, [_P, _P, _I, _I, _P]),
     "svla_zoe_patchify": (_I, [_P, _P, _I, _P]),

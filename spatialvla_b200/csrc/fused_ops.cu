@@ -606,6 +606,40 @@ svla_cross_entropy_summary_kernel(const float* __restrict__ row_loss, const long
   }
 }
 
+// ------------------------------------------------------------------------------------------ AdamW on the flat LoRA arena
+// Optimizer step of the fine-tune config (HF Trainer's default adamw_torch on the ~59.2 M adapter parameters; arithmetic in the
+// order of torch.optim.AdamW's single-tensor path: decoupled decay, moment updates, denom = sqrt(v) / sqrt(1 - b2^t) + eps,
+// p -= (lr / (1 - b1^t)) * m / denom).  One pass over the flat buffers, 128-bit accesses: 16 B read + 12 B written per element.
+__global__ void __launch_bounds__(256)
+svla_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                  float decay, float omb1, float b2, float omb2, float eps, float step_size, float bc2_sqrt, float grad_scale) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long nvec = n >> 2;
+  // every scalar (decay = 1 - lr wd, omb1 = 1 - beta1, omb2 = 1 - beta2, step_size = lr / (1 - beta1^t), bc2_sqrt) is formed in
+  // DOUBLE on the host like torch does with its Python floats: 1.f - 0.999f alone is off by 1.3e-5 of (1 - beta2)
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    gg *= grad_scale;
+    pp *= decay;
+    mm = mm + (gg - mm) * omb1;                   // lerp form of torch: m.lerp_(g, 1 - beta1)
+    vv = vv * b2 + gg * gg * omb2;
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pp -= step_size * (mm / denom);
+  };
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    upd(pv.x, gv.x, mv.x, vv.x);
+    upd(pv.y, gv.y, mv.y, vv.y);
+    upd(pv.z, gv.z, mv.z, vv.z);
+    upd(pv.w, gv.w, mv.w, vv.w);
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (long long i = (nvec << 2) + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride)
+    upd(p[i], g[i], m[i], v[i]);
+}
+
 // ------------------------------------------------------------------------------------------ bicubic helpers (A = -0.75)
 __device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
   const float A = -0.75f;
@@ -1462,6 +1496,23 @@ extern "C" int svla_cross_entropy_bwd(const float* logits, int64_t rows, int64_t
       static_cast<long long>(ignore_index), row_loss + row_offset, summary, softcap, static_cast<__nv_bfloat16*>(dz_bf16),
       static_cast<long long>(ldo));
   SVLA_LAUNCH_CHECK("svla_cross_entropy_bwd");
+  return 0;
+}
+
+extern "C" int svla_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                               double beta2, double eps, double weight_decay, int64_t step, double grad_scale, void* stream) {
+  SVLA_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "svla_adamw_step: bad arguments");
+  SVLA_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+                 reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0, "svla_adamw_step: buffers must be 16-byte aligned");
+  const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
+  const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
+  const long long blocks = (n / 4 + 255) / 256;
+  const long long cap = static_cast<long long>(svla_num_sms()) * 8;
+  svla_adamw_kernel<<<static_cast<unsigned>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, static_cast<long long>(n), static_cast<float>(1.0 - lr * weight_decay),
+      static_cast<float>(1.0 - beta1), static_cast<float>(beta2), static_cast<float>(1.0 - beta2), static_cast<float>(eps),
+      static_cast<float>(lr / bc1), static_cast<float>(sqrt(bc2)), static_cast<float>(grad_scale));
+  SVLA_LAUNCH_CHECK("svla_adamw_step");
   return 0;
 }
 

@@ -266,6 +266,15 @@ class CudaOps:
                                                 _ptr(dz), dz.shape[1], self._stream()),
                 "svla_cross_entropy_bwd")
 
+    def adamw_step(self, param, grad, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step, grad_scale=1.0):
+        """In-place AdamW on flat fp32 buffers (torch.optim.AdamW arithmetic); step counts from 1.
+        NOT yet verified on hardware (see include/spatialvla_b200.h); nothing on the product path calls it."""
+        for t in (param, grad, exp_avg, exp_avg_sq):
+            _req(t.dtype == F32 and t.dim() == 1 and t.is_contiguous() and t.numel() == param.numel(), "adamw_step: flat fp32 buffers of one size")
+        L.check(self.lib.svla_adamw_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr), float(beta1),
+                                         float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), self._stream()),
+                "svla_adamw_step")
+
     def siglip_patchify(self, px, a):
         _req(px.dtype == F32 and px.is_contiguous() and tuple(px.shape[1:]) == (3, 224, 224), "siglip_patchify: px")
         L.check(self.lib.svla_siglip_patchify(_ptr(px), _ptr(a), px.shape[0], a.shape[1], self._stream()),

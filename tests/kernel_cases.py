@@ -715,7 +715,34 @@ def cross_entropy_bwd_case(dev="cuda:0"):
     return res
 
 
+def adamw_case(dev="cuda:0"):
+    """svla_adamw_step vs the torch.optim.AdamW arithmetic (oracle/ops_ref.py, itself checked against torch.optim.AdamW on the CPU):
+    three steps on flat buffers whose length is not a multiple of 4, with weight decay and a gradient scale."""
+    res = Result("adamw_step")
+    for (n, wd, gs) in ((1_000_003, 0.01, 0.5), (64, 0.0, 1.0), (7, 0.1, 1.0)):
+        g = _gen(n)
+        p0 = _randn(g, n)
+        grads = [_randn(g, n, scale=0.1 * (s + 1)) for s in range(3)]
+
+        def run(ops, to):
+            p, m, v = to(p0), ops.zeros((n,), F32), ops.zeros((n,), F32)
+            for s, gr in enumerate(grads):
+                ops.adamw_step(p, to(gr), m, v, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=wd, step=s + 1, grad_scale=gs)
+            return p, m, v
+        (cp, cm, cv), (rp, rm, rv) = _both(run, dev)
+        res.add(f"p[{n}]", _err(cp, rp), 2e-6)
+        res.add(f"m[{n}]", _err(cm, rm), 2e-6)
+        res.add(f"v[{n}]", _err(cv, rv), 2e-6)
+        res.add(f"moved[{n}]", 0.0 if float((rp - p0).abs().max()) > 1e-4 else 1.0, 0)
+    return res
+
+
 FUSED_CASES = [layernorm_case, rmsnorm_case, rope_case, embed_case, argmax_case, cross_entropy_case, cross_entropy_bwd_case, patchify_case, assemble_concat_case,
                shuffle_im2col_case, bilinear_case, zoe_tail_case, ego3d_case, tokenizer_case]
+
+# Written at the very end of round 1 and NOT yet green on hardware: the first GPU attempt failed on the fp32 rounding of 1 - beta2
+# (fixed since: hyper-parameters are doubles now) and the round's GPU budget was spent before a second attempt.  Kept out of
+# ALL_CASES so the -m gpu suite only holds verified cases; run it with `python -c "import kernel_cases as k; print(k.adamw_case())"`.
+PENDING_CASES = {"adamw_case": adamw_case}
 
 ALL_CASES = {c.__name__: c for c in (SIMT_CASES + GEMM_CASES + PAIR_CASES + TMA_EPI_CASES + ROWTILE_CASES + SKINNY_CASES + ATTN_CASES + FUSED_CASES)}

@@ -129,3 +129,30 @@ def test_merged_adapters_serve_through_the_unchanged_engine():
     base_toks, base_logits = R.predict_action_ref(sd, cfg, ids, px, K, 4, force_head=eng.last_router_head)
     assert (logits - ref_logits).abs().max() < 6e-2
     assert (ref_logits - base_logits).abs().max() > 0.2          # the adapters changed the model well beyond the comparison tolerance
+
+
+def test_adamw_restatement_matches_torch_optimizer():
+    """oracle/ops_ref.RefOps.adamw_step (the checker of the svla_adamw_step kernel) against torch.optim.AdamW -- the optimizer the
+    reference's HF Trainer runs on the adapters (lr 5e-4, scripts/spatialvla_4b_finetune/finetune_lora.sh:26-29) -- over several steps."""
+    from oracle.ops_ref import RefOps
+    ops = RefOps()
+    for wd in (0.0, 0.01):
+        g = torch.Generator().manual_seed(7)
+        p_ref = torch.nn.Parameter(torch.randn(1001, generator=g))
+        opt = torch.optim.AdamW([p_ref], lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+        p, m, v = p_ref.detach().clone(), torch.zeros(1001), torch.zeros(1001)
+        for step in range(1, 5):
+            gr = torch.randn(1001, generator=g) * 0.1 * step
+            p_ref.grad = gr.clone()
+            opt.step()
+            ops.adamw_step(p, gr, m, v, lr=5e-4, weight_decay=wd, step=step)
+            assert (p - p_ref.detach()).abs().max() < 1e-6, (wd, step)
+        st = opt.state[p_ref]
+        assert (m - st["exp_avg"]).abs().max() < 1e-7 and (v - st["exp_avg_sq"]).abs().max() < 1e-8
+    # grad_scale = the 1 / world-size (or clipping) factor applied on the fly
+    p1, m1, v1 = torch.ones(8), torch.zeros(8), torch.zeros(8)
+    p2, m2, v2 = torch.ones(8), torch.zeros(8), torch.zeros(8)
+    gr = torch.arange(8.0)
+    ops.adamw_step(p1, gr, m1, v1, lr=1e-2, step=1, grad_scale=0.25)
+    ops.adamw_step(p2, gr * 0.25, m2, v2, lr=1e-2, step=1)
+    assert torch.equal(p1, p2) and torch.equal(m1, m2)

@@ -75,6 +75,10 @@ class SpatialVLAProcessor:
         tokenizer.add_bos_token = False
         tokenizer.add_eos_token = False
 
+        # prompt-id cache: a control loop sends the same instruction every step, so the tokenizer output of
+        # an inference prompt is kept per (prompt strings, tokenizer kwargs); training samples (suffix) are never cached
+        self.prompt_cache_size = 256
+        self._prompt_cache = {}
         self.statistics = statistics if statistics else {}
         self.bin_policy = bin_policy
         self.min_sigma = min_sigma
@@ -128,14 +132,33 @@ class SpatialVLAProcessor:
                 input_strings.append(ex[:idx] + self.tokenizer.bos_token + ex[idx:] + "\n")
         flat = [im for il in images for im in il]
         pixel_values = self.image_processor(flat, return_tensors=return_tensors)["pixel_values"]
-        inputs = self.tokenizer(input_strings, text_pair=suffix, return_token_type_ids=return_token_type_ids,
-                                return_tensors=return_tensors, **kwargs)
+        inputs = self._tokenize(input_strings, suffix, return_token_type_ids, return_tensors, kwargs)
         intrinsic = self.dataset_intrinsics[unnorm_key] if unnorm_key in self.dataset_intrinsics \
             else self.dataset_intrinsics["default"]
         data = {**inputs, "pixel_values": pixel_values, "intrinsic": intrinsic}
         if return_token_type_ids:
             data["labels"] = inputs["input_ids"].masked_fill(inputs["token_type_ids"] == 0, -100)
         return BatchFeature(data)
+
+    def _tokenize(self, input_strings, suffix, return_token_type_ids, return_tensors, kwargs):
+        key = None
+        if suffix is None and self.prompt_cache_size > 0:
+            try:
+                key = (tuple(input_strings), return_tensors, tuple(sorted(kwargs.items())))
+                hash(key)
+            except TypeError:
+                key = None
+        if key is not None and key in self._prompt_cache:
+            hit = self._prompt_cache.pop(key)
+            self._prompt_cache[key] = hit                      # most recently used last
+            return {k: (v.clone() if hasattr(v, "clone") else v) for k, v in hit.items()}
+        inputs = self.tokenizer(input_strings, text_pair=suffix, return_token_type_ids=return_token_type_ids,
+                                return_tensors=return_tensors, **kwargs)
+        if key is not None:
+            self._prompt_cache[key] = {k: (v.clone() if hasattr(v, "clone") else v) for k, v in dict(inputs).items()}
+            while len(self._prompt_cache) > self.prompt_cache_size:
+                self._prompt_cache.pop(next(iter(self._prompt_cache)))
+        return dict(inputs)
 
     def batch_decode(self, *args, **kwargs):
         return self.tokenizer.batch_decode(*args, **kwargs)

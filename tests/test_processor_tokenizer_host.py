@@ -140,3 +140,33 @@ def test_spatial_embedding_adaption_matches_reference_golden():
     emb2.weight.data.copy_(torch.from_numpy(g["before"]))
     tk2.spatial_embedding_adaption(ADAPT_GS1, emb2, min_sigma=0.2)
     assert np.array_equal(emb2.weight.data.numpy(), g["before"]) and np.array_equal(tk2._edges, tk._edges)
+
+
+def test_prompt_id_cache_per_instruction():
+    """Serving loop: the same instruction every control step -> the tokenizer runs once per distinct prompt (SURVEY §8f rank 2);
+    results are identical and independent copies; training samples (suffix) bypass the cache."""
+    p = make_processor()
+    calls = []
+    real = p.tokenizer.__class__.__call__
+
+    class Counting(p.tokenizer.__class__):
+        def __call__(self, *a, **k):
+            calls.append(a[0])
+            return real(self, *a, **k)
+    p.tokenizer.__class__ = Counting
+    img = (np.random.default_rng(0).random((224, 224, 3)) * 255).astype(np.uint8)
+    a = p(images=[img], text=["pick up the cup"], unnorm_key="bridge")
+    b = p(images=[img], text=["pick up the cup"], unnorm_key="bridge")
+    c = p(images=[img], text=["open drawer"], unnorm_key="bridge")
+    assert len(calls) == 2 and torch.equal(a["input_ids"], b["input_ids"]) and not torch.equal(a["input_ids"][0, 257:260], c["input_ids"][0, 257:260])
+    b["input_ids"][0, 0] = -7                                  # a returned tensor is a copy: the cache entry is not corrupted
+    d = p(images=[img], text=["pick up the cup"], unnorm_key="bridge")
+    assert len(calls) == 2 and int(d["input_ids"][0, 0]) == int(a["input_ids"][0, 0])
+    p.prompt_cache_size = 1                                    # LRU bound
+    p(images=[img], text=["close drawer"], unnorm_key="bridge")
+    assert len(p._prompt_cache) == 1 and len(calls) == 3
+    p(images=[img], text=["pick up the cup"], unnorm_key="bridge")
+    assert len(calls) == 4
+    p.prompt_cache_size = 0                                    # disabled
+    p(images=[img], text=["pick up the cup"], unnorm_key="bridge")
+    assert len(calls) == 5

@@ -85,7 +85,9 @@ class LoRAArena:
         return out
 
     def accumulate_from_weight_grad(self, key: str, dW: torch.Tensor):
-        """Chain rule of W' = W + s B A for a full-weight gradient dW = dL/dW':  gB += s dW A^T,  gA += s B^T dW."""
+        """Chain rule of W' = W + s B A for a full-weight gradient dW = dL/dW':  gB += s dW A^T,  gA += s B^T dW.
+        Host-side torch helper for tests and one-off conversions only: the training step never forms dW -- its kernels will write
+        gA / gB of this arena directly (oracle/backward_ref.lora_linear_bwd is the formula they are checked against)."""
         dW = dW.float()
         self.gB[key] += (self.scale * (dW @ self.A[key].float().t())).to(self.grad.dtype)
         self.gA[key] += (self.scale * (self.B[key].float().t() @ dW)).to(self.grad.dtype)

@@ -300,14 +300,25 @@ int svla_ego3d_encode(const float* depth384, const float* intrinsic, int k_strid
  * use_spherical = 0 bins the Cartesian translation directly (model/action_tokenizer.py:110-113,135).
  * nbins is always read on the HOST (7 ints of configuration).
  * The `_host` variants take HOST buffers and do the H2D/D2H copies themselves (the e2e call). */
+/* edge_trig (NULL = library atan2 path): fp64 [(theta bins - 1) + (phi bins - 1)][4] = (cos_hi, cos_lo, sin_hi, sin_lo) of the
+ * rounding boundary m = (pred(e) + e) / 2 below each INTERIOR theta / phi edge e, double-double (built on the host with 200-bit
+ * arithmetic, spatialvla_b200/action_tokenizer.py::edge_trig_table); phi_nonpos / phi_neg = number of interior phi edges <= 0 / < 0.
+ * With the table the angular bins are decided WITHOUT atan2: `fl(atan2(a, b)) >= e` of np.digitize (model/action_tokenizer.py:115-118)
+ * is the sign of a cos m - b sin m, evaluated in double and, within 8 roundings of zero, with error-free transformations (2^-104):
+ * the ids a correctly rounded atan2 yields, independent of the math library's last-ulp behaviour. */
 int svla_tok_encode(const double* actions, const double* edges, const int32_t* nbins, int32_t* ids, int64_t n,
-                    double min_action, double max_action, int use_spherical, void* stream);
+                    double min_action, double max_action, int use_spherical, const double* edge_trig, int phi_nonpos,
+                    int phi_neg, void* stream);
+/* center_trig (NULL = library sincos, <= 4 ulp from glibc): fp64 [(theta bins) + (phi bins)][2] = (sin, cos) of every bin CENTRE
+ * 0.5 (e[i] + e[i+1]) -- the only angles the inverse evaluates (model/action_tokenizer.py:99-103,129-135) -- tabulated once on the
+ * host with the reference's own libm (numpy), so the decoded x, y, z are the reference's doubles bit for bit. */
 int svla_tok_decode(const int64_t* ids, const double* edges, const int32_t* nbins, int64_t begin, double* actions,
-                    int64_t n, int use_spherical, void* stream);
+                    int64_t n, int use_spherical, const double* center_trig, void* stream);
 int svla_tok_encode_host(const double* actions_host, const double* edges_host, const int32_t* nbins_host,
-                         int32_t* ids_host, int64_t n, double min_action, double max_action, int use_spherical);
+                         int32_t* ids_host, int64_t n, double min_action, double max_action, int use_spherical,
+                         const double* edge_trig_host, int phi_nonpos, int phi_neg);
 int svla_tok_decode_host(const int64_t* ids_host, const double* edges_host, const int32_t* nbins_host, int64_t begin,
-                         double* actions_host, int64_t n, int use_spherical);
+                         double* actions_host, int64_t n, int use_spherical, const double* center_trig_host);
 
 #ifdef __cplusplus
 }

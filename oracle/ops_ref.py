@@ -239,7 +239,7 @@ class RefOps:
         if image_feats is not None:
             m = ids == image_token
             rank = torch.cumsum(m.long(), 1) - 1
-            if int(rank.max()) >= n_img:
+            if bool((m.sum(1) != n_img).any()):            # too many OR too few image tokens in some row
                 status.fill_(1)
                 return
             bidx = torch.arange(B)[:, None].expand(B, S)
@@ -414,13 +414,14 @@ class RefOps:
         enc[:, : e.shape[1]] = e.to(BF16)
 
     # ---- tokenizer
-    def tok_encode(self, actions, edges, nbins_host, ids, *, min_action=-1.0, max_action=1.0, use_spherical=True):
+    def tok_encode(self, actions, edges, nbins_host, ids, *, min_action=-1.0, max_action=1.0, use_spherical=True, trig=None,
+                   phi_nonpos=0, phi_neg=0):
         self.launches += 1
         from oracle import tokenizer_ref as T
         pol, nb = _policy_from_flat(edges.numpy(), nbins_host)
         ids.copy_(torch.from_numpy(T.encode(actions.numpy(), pol, nb, min_action, max_action)).to(ids.dtype))
 
-    def tok_decode(self, ids, edges, nbins_host, begin, actions, *, use_spherical=True):
+    def tok_decode(self, ids, edges, nbins_host, begin, actions, *, use_spherical=True, center_trig=None):
         self.launches += 1
         from oracle import tokenizer_ref as T
         pol, nb = _policy_from_flat(edges.numpy(), nbins_host)

@@ -80,3 +80,50 @@ def decode(local_ids, pol, num_bins):
     i2 = np.clip(ids[:, 2], n_trans + n_rot, n_trans + n_rot + num_bins["gripper"] - 1) - n_trans - n_rot
     g = np.where(i2 == 0, 0.0, 1.0)
     return np.stack([x, y, z, roll, pitch, yaw, g], 1)
+
+
+def encode_angles_exact(actions, pol, num_bins, trig, phi_nonpos, phi_neg, min_action=-1.0, max_action=1.0):
+    """CPU restatement of the atan2-free angular binning of csrc/tokenizer.cu (svla_tok_encode with an edge_trig table), used to
+    check the decision rule, the table and the quadrant logic against the golden ids without a GPU: the fast path is the same
+    rounded double expression with the same bound; the slow path (error-free transformations on the device) is done here in exact
+    rational arithmetic.  Returns (theta bin, phi bin) int arrays."""
+    from fractions import Fraction
+    a = np.clip(np.asarray(actions, dtype=np.float64).reshape(-1, 7), min_action, max_action)
+    te = np.asarray(pol["translation"]["theta_bins"], dtype=np.float64)[1:-1]
+    pe = np.asarray(pol["translation"]["phi_bins"], dtype=np.float64)[1:-1]
+    n_ti, n_pi = te.shape[0], pe.shape[0]
+    trig = np.asarray(trig, dtype=np.float64).reshape(-1, 4)
+
+    def ge(av, bv, row):
+        ch, cl, sh, sl = (float(v) for v in trig[row])
+        p1, p2 = av * ch, bv * sh
+        d = p1 - p2
+        if abs(d) > 1.8e-15 * (abs(p1) + abs(p2)):
+            return d > 0.0
+        tot = Fraction(av) * (Fraction(ch) + Fraction(cl)) - Fraction(bv) * (Fraction(sh) + Fraction(sl))
+        return tot >= 0
+
+    def count(av, bv, base, lo, hi):
+        while lo < hi:
+            mid = (lo + hi) >> 1
+            if ge(av, bv, base + mid):
+                lo = mid + 1
+            else:
+                hi = mid
+        return lo
+
+    dt, dp = np.zeros(a.shape[0], dtype=np.int64), np.zeros(a.shape[0], dtype=np.int64)
+    for i, (x, y, z) in enumerate(a[:, :3]):
+        x, y, z = float(x), float(y), float(z)
+        rho = float(np.sqrt(x * x + y * y))
+        if rho == 0.0 and z == 0.0:
+            dt[i] = np.digitize(np.arctan2(rho, z), te)
+        else:
+            dt[i] = count(rho, z, 0, 0, n_ti)
+        if y == 0.0:
+            dp[i] = np.digitize(np.arctan2(y, x), pe)
+        elif y > 0.0:
+            dp[i] = count(y, x, n_ti, phi_nonpos, n_pi)
+        else:
+            dp[i] = count(y, x, n_ti, 0, phi_neg)
+    return dt, dp

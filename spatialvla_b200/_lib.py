@@ -92,10 +92,10 @@ SIGNATURES = {
     "svla_zoe_depth_tail": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "svla_zoe_depth_tail_fused": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "svla_ego3d_encode": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _P]),
-    "svla_tok_encode": (_I, [_P, _P, _P, _P, _L, _D, _D, _I, _P]),
-    "svla_tok_decode": (_I, [_P, _P, _P, _L, _P, _L, _I, _P]),
-    "svla_tok_encode_host": (_I, [_P, _P, _P, _P, _L, _D, _D, _I]),
-    "svla_tok_decode_host": (_I, [_P, _P, _P, _L, _P, _L, _I]),
+    "svla_tok_encode": (_I, [_P, _P, _P, _P, _L, _D, _D, _I, _P, _I, _I, _P]),
+    "svla_tok_decode": (_I, [_P, _P, _P, _L, _P, _L, _I, _P, _P]),
+    "svla_tok_encode_host": (_I, [_P, _P, _P, _P, _L, _D, _D, _I, _P, _I, _I]),
+    "svla_tok_decode_host": (_I, [_P, _P, _P, _L, _P, _L, _I, _P]),
 }
 
 
@@ -104,17 +104,35 @@ class SvlaError(RuntimeError):
 
 
 def build_library(verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into the in-tree shared library (no GPU needed)."""
+    """Compile every CUDA source for sm_100a into the in-tree shared library (no GPU needed).  One object per source
+    (compiled in parallel, rebuilt only when the source or a shared header is newer), then one link step."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "svla_common.cuh"), os.path.join(CSRC, "tc_ptx.cuh"), os.path.join(_HERE, "..", "include", "spatialvla_b200.h")]
-    if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
-        return LIB_PATH
+    objdir = os.path.join(os.path.dirname(LIB_PATH), "obj")
+    os.makedirs(objdir, exist_ok=True)
+    hdrs = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")] + [os.path.join(_HERE, "..", "include", "spatialvla_b200.h")]
+    hdr_time = max(os.path.getmtime(h) for h in hdrs)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        s, o = os.path.join(CSRC, src), os.path.join(objdir, src.replace(".cu", ".o"))
+        if os.path.exists(o) and os.path.getmtime(o) >= max(os.path.getmtime(s), hdr_time):
+            return o, False
+        cmd = [nvcc] + flags + ["-c", "-o", o, s]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+        return o, True
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        res = list(ex.map(compile_one, SOURCES))
+    objs = [o for o, _ in res]
+    if any(c for _, c in res) or not os.path.exists(LIB_PATH) or any(os.path.getmtime(o) > os.path.getmtime(LIB_PATH) for o in objs):
+        cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + objs
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
     return LIB_PATH
 
 

@@ -37,6 +37,26 @@ class _SubTokenizer:
         return self._vocab_size
 
 
+def edge_trig_table(theta_edges, phi_edges):
+    """Table behind the exact angular binning of svla_tok_encode (csrc/tokenizer.cu): for every interior theta / phi edge e the
+    reference's test `fl(atan2(a, b)) >= e` (np.digitize, model/action_tokenizer.py:115-118) is, for a correctly rounded atan2,
+    `atan2(a, b) >= m` with m = (pred(e) + e) / 2, decided on the device as the sign of a cos m - b sin m.  cos m / sin m are
+    evaluated here with 200-bit arithmetic and stored as double-double pairs.
+    Returns (float64 [n, 4] rows (cos_hi, cos_lo, sin_hi, sin_lo), #phi edges <= 0, #phi edges < 0)."""
+    import mpmath as mp
+    rows = []
+    with mp.workprec(200):
+        for e in list(theta_edges) + list(phi_edges):
+            e = float(e)
+            m = (mp.mpf(float(np.nextafter(e, -np.inf))) + mp.mpf(e)) / 2
+            c, s_ = mp.cos(m), mp.sin(m)
+            ch, sh = float(c), float(s_)
+            rows.append((ch, float(c - mp.mpf(ch)), sh, float(s_ - mp.mpf(sh))))
+    phi = np.asarray(phi_edges, dtype=np.float64)
+    tab = np.ascontiguousarray(np.asarray(rows, dtype=np.float64).reshape(-1, 4))
+    return tab, int((phi <= 0).sum()), int((phi < 0).sum())
+
+
 class SpatialActionTokenizer:
     range_bins = {
         "translation": {"theta_bins": (0.0, np.pi), "phi_bins": (-np.pi, np.pi), "r_bins": (0.0, np.sqrt(3))},
@@ -75,6 +95,10 @@ class SpatialActionTokenizer:
         self._nbins = (C.c_int32 * 7)(*nb, int(self.num_bins["gripper"]))
         self._nbins_list = nb + [int(self.num_bins["gripper"])]
         self._dev_edges = {}
+        self._trig, self._phi_nonpos, self._phi_neg = edge_trig_table(arrs[0][1:-1], arrs[1][1:-1])
+        # (sin, cos) of the theta / phi bin centres: the only angles decode evaluates (model/action_tokenizer.py:99-103,129-135)
+        cen = [0.5 * (a[:-1] + a[1:]) for a in arrs[:2]]
+        self._ctrig = np.ascontiguousarray(np.concatenate([np.stack([np.sin(c), np.cos(c)], 1) for c in cen]).astype(np.float64))
 
     @property
     def vocab_size(self) -> int:
@@ -113,7 +137,8 @@ class SpatialActionTokenizer:
         lib = L.load_library()
         L.check(lib.svla_tok_encode_host(a.ctypes.data, self._edges.ctypes.data, C.cast(self._nbins, C.c_void_p),
                                          ids.ctypes.data, a.shape[0], float(self.min_action), float(self.max_action),
-                                         int(self.use_spherical)), "svla_tok_encode_host")
+                                         int(self.use_spherical), self._trig.ctypes.data, self._phi_nonpos, self._phi_neg),
+                "svla_tok_encode_host")
         return ids
 
     def __call__(self, action: np.ndarray) -> np.ndarray:
@@ -132,7 +157,7 @@ class SpatialActionTokenizer:
         lib = L.load_library()
         L.check(lib.svla_tok_decode_host(ids.ctypes.data, self._edges.ctypes.data, C.cast(self._nbins, C.c_void_p),
                                          int(self.action_token_begin_idx), out.ctypes.data, ids.shape[0],
-                                         int(self.use_spherical)), "svla_tok_decode_host")
+                                         int(self.use_spherical), self._ctrig.ctypes.data), "svla_tok_decode_host")
         return out
 
     # ---- device-resident API (batched serving / training data path)
@@ -140,7 +165,8 @@ class SpatialActionTokenizer:
         import torch
         key = str(device)
         if key not in self._dev_edges:
-            self._dev_edges[key] = torch.from_numpy(self._edges).to(device)
+            self._dev_edges[key] = (torch.from_numpy(self._edges).to(device), torch.from_numpy(self._trig).to(device),
+                                    torch.from_numpy(self._ctrig).to(device))
         return self._dev_edges[key]
 
     def encode_ids(self, actions):
@@ -150,8 +176,9 @@ class SpatialActionTokenizer:
         ops = CudaOps(actions.device)
         a = actions.to(torch.float64).contiguous()
         ids = torch.empty((a.shape[0], 3), dtype=torch.int32, device=a.device)
-        ops.tok_encode(a, self._edges_on(a.device), self._nbins_list, ids, min_action=self.min_action,
-                       max_action=self.max_action, use_spherical=self.use_spherical)
+        edges, trig, _ = self._edges_on(a.device)
+        ops.tok_encode(a, edges, self._nbins_list, ids, min_action=self.min_action, max_action=self.max_action,
+                       use_spherical=self.use_spherical, trig=trig, phi_nonpos=self._phi_nonpos, phi_neg=self._phi_neg)
         return ids.to(torch.int64) + self.action_token_begin_idx
 
     def decode_ids(self, ids):
@@ -161,8 +188,9 @@ class SpatialActionTokenizer:
         ops = CudaOps(ids.device)
         i = ids.to(torch.int64).contiguous()
         out = torch.empty((i.shape[0], 7), dtype=torch.float64, device=i.device)
-        ops.tok_decode(i, self._edges_on(i.device), self._nbins_list, self.action_token_begin_idx, out,
-                       use_spherical=self.use_spherical)
+        edges, _, ctrig = self._edges_on(i.device)
+        ops.tok_decode(i, edges, self._nbins_list, self.action_token_begin_idx, out, use_spherical=self.use_spherical,
+                       center_trig=ctrig)
         return out
 
     # ---- fine-tune-time re-gridding (host-side one-off, mirrors :372-430)

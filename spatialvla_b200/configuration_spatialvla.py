@@ -85,6 +85,10 @@ class SpatialVLAConfig(PretrainedConfig):
             "image_token_index": self.image_token_index, "action_token_begin_idx": self.action_token_begin_idx,
             "spatial_token_num": self.spatial_token_num, "use_spatial_token": self.use_spatial_token,
             "ego3d_patch_reso": self.ego3d_patch_reso, "n_freqs": self.n_freqs, "use_vision_zoe": self.use_vision_zoe,
+            # read by the labelled forward: labels on pad-token inputs are masked (model/modeling_spatialvla.py:389-397, where
+            # pad_token_id None becomes -1 at :192)
+            "pad_token_id": getattr(self, "pad_token_id", None), "ignore_index": getattr(self, "_ignore_index", -100),
+            "eos_token_id": getattr(self, "eos_token_id", None),
         }
         if self.use_vision_zoe and self.vision_zoe_config is not None:
             z = self.vision_zoe_config.to_dict()

@@ -366,6 +366,18 @@ __global__ void svla_embed_kernel(const long long* __restrict__ ids, const __nv_
   const int b = static_cast<int>(tok / s), si = static_cast<int>(tok % s);
   const long long id = ids[tok];
   float* dst = x + tok * hdim;
+  if (img != nullptr && si == s - 1 && status) {
+    // the block of a row's last token audits the row: exactly n_img image tokens, or the batch is malformed
+    // (model/modeling_spatialvla.py:379-385 raises ValueError; rows with too FEW image tokens would otherwise leave nothing behind)
+    int c = 0;
+    for (int j = threadIdx.x; j < s; j += blockDim.x) c += (ids[static_cast<long long>(b) * s + j] == image_token);
+    __shared__ int total_sh;
+    if (threadIdx.x == 0) total_sh = 0;
+    __syncthreads();
+    if (c) atomicAdd(&total_sh, c);
+    __syncthreads();
+    if (threadIdx.x == 0 && total_sh != n_img) atomicExch(status, 1);
+  }
   if (id == image_token && img != nullptr) {
     // rank of this image token inside its row (the processor puts them first, but stay general)
     __shared__ int rank_sh;

@@ -58,10 +58,11 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 #endif
 
 static inline int svla_num_sms() {
-  static int n = 0;
+  static int cache[64] = {0};        // per device: a process may drive more than one GPU
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = cache[(dev >= 0 && dev < 64) ? dev : 0];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }

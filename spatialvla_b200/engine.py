@@ -100,10 +100,16 @@ class SpatialVLAEngine:
         self.proj_scale = torch.full((H,), 1.0 / (H ** 0.5), dtype=F32, device=self.dev)
         # ---- Gemma2
         p = "language_model.model."
+        # Gemma2 ties lm_head to embed_tokens (model/modeling_gemma2.py:888 `_tied_weights_keys`, propagated at
+        # model/modeling_spatialvla.py:171-172): a checkpoint written by the reference then carries no lm_head key, and the
+        # post-load overwrite embed_tokens[-n:] = spatial_embed_tokens (:524-525) changes the tied head rows as well.
+        head_src = sd.get("language_model.lm_head.weight")
+        if head_src is None or t.get("tie_word_embeddings", False):
+            head_src = sd[p + "embed_tokens.weight"]
         g = {"embed": W(p + "embed_tokens.weight"), "final": Fp(p + "norm.weight"),
-             "head_act": self._w(sd["language_model.lm_head.weight"][self.act_lo:self.act_lo + self.n_act], BF16),
+             "head_act": self._w(head_src[self.act_lo:self.act_lo + self.n_act], BF16),
              "layers": []}
-        self._lm_head_full_src = sd["language_model.lm_head.weight"]
+        self._lm_head_full_src = head_src
         self._lm_head_full = None
         self._lm_head_full_t = None
         g["spatial"] = W("spatial_embed_tokens.weight") if self.cfg.get("use_spatial_token", True) else None
@@ -588,6 +594,11 @@ class SpatialVLAEngine:
         scale, cap = t["query_pre_attn_scalar"] ** -0.5, t["attn_logit_softcapping"] or 0.0
         M, pos0, smax = B * S, cache["len"], cache["smax"]
         assert pos0 + S <= smax, "KV cache overflow"
+        win = t.get("sliding_window")
+        if win and pos0 + S > win:
+            # Gemma2 alternates sliding-window and global layers (model/modeling_gemma2.py:364-413); every context on this path
+            # (278 + 12 tokens) is far inside the 4096-token window, where the two layer kinds are identical
+            raise NotImplementedError(f"context of {pos0 + S} tokens exceeds the sliding window ({win}): windowed layers are not implemented")
         h = ops.empty((M, H), BF16)
         ops.rmsnorm_residual(x, w_pre=g["layers"][0]["ln_in"], eps=eps, out_bf16=h)
         q = ops.empty((M, nh * hd), BF16)

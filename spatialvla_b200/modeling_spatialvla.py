@@ -111,17 +111,37 @@ class SpatialVLAForConditionalGeneration:
         pads = None
         if am is not None and am.dim() == 2 and bool((am == 0).any()):
             pads = self._left_pads(am, ids.shape[1])
+        self.raise_if_bad_batch()                   # deferred check of the previous device-resident batch (no sync on this one)
+        if px is not None and not ids.is_cuda:
+            # host ids (what the processor returns): audit EVERY row before anything is launched (:379-385)
+            n_img = (ids == self.engine_config["image_token_index"]).sum(1)
+            if bool((n_img != 256).any()) or ids.shape[0] != px.shape[0]:
+                raise ValueError(
+                    "Number of images does not match number of special image tokens in the input text. "
+                    f"Got {int(n_img.sum())} image tokens in the text but {px.shape[0] * 256} tokens from image embeddings.")
         ids = ids.to(self.device, torch.int64).contiguous()
         if px is not None:
             px = px.to(self.device, F32).contiguous()
-            n_img = int((ids[0] == self.engine_config["image_token_index"]).sum())
-            if n_img * ids.shape[0] != px.shape[0] * 256:
-                raise ValueError(
-                    "Number of images does not match number of special image tokens in the input text. "
-                    f"Got {n_img * ids.shape[0]} image tokens in the text but {px.shape[0] * 256} tokens from image embeddings.")
+            if ids.shape[0] != px.shape[0]:
+                raise ValueError("Number of images does not match number of special image tokens in the input text. "
+                                 f"Got {ids.shape[0]} prompt rows but {px.shape[0]} images.")
         if K is not None:
             K = K.to(self.device, F32).contiguous()
         return ids, px, K, pads
+
+    def raise_if_bad_batch(self):
+        """Device-resident `input_ids` are audited by the embedding kernel (every row must hold exactly 256 image tokens and only
+        valid ids); its status word is read here -- after the batch has been decoded, or at the start of the next call -- so the
+        hot path itself carries no device->host synchronisation.  Raises the reference's ValueError (:379-385)."""
+        st = getattr(self.engine, "last_status", None)
+        if st is None:
+            return
+        self.engine.last_status = None
+        code = int(st.item())
+        if code == 1:
+            raise ValueError("Number of images does not match number of special image tokens in the input text.")
+        if code == 2:
+            raise ValueError("input_ids outside [0, vocab_size)")
 
     def _left_pads(self, attention_mask, P):
         """(B,P) 0/1 mask with zeros -> int32 [B] device tensor of leading pad counts.  Only left padding is supported: every
@@ -211,7 +231,8 @@ class SpatialVLAForConditionalGeneration:
         is passed (prefix-LM); labels alone -> the bidirectional inference mask.  Loss: shifted nn.CrossEntropyLoss over the
         full vocabulary on the post-softcap logits, ignore_index rows dropped, pad-token labels masked (:389-397)."""
         eng = self.engine
-        ignore = -100 if self.config is None else getattr(self.config, "_ignore_index", -100)
+        ignore = self.engine_config.get("ignore_index", -100)
+        ignore = -100 if ignore is None else ignore
         pad_id = self.engine_config.get("pad_token_id")
         pad_id = -1 if pad_id is None else pad_id
         B, L = input_ids.shape

@@ -343,13 +343,21 @@ class CudaOps:
                 "svla_ego3d_encode")
 
     # ---- M8 tokenizer (device buffers)
-    def tok_encode(self, actions, edges, nbins_host, ids, *, min_action=-1.0, max_action=1.0, use_spherical=True):
+    def tok_encode(self, actions, edges, nbins_host, ids, *, min_action=-1.0, max_action=1.0, use_spherical=True, trig=None,
+                   phi_nonpos=0, phi_neg=0):
+        """trig: float64 [n_theta_interior + n_phi_interior, 4] device table of action_tokenizer.edge_trig_table (exact angular
+        binning); None = the library atan2 path (within a few ulp of an edge it may differ from glibc)."""
         nb = (C.c_int32 * 7)(*nbins_host)
+        _req(trig is None or (trig.dtype == torch.float64 and trig.is_contiguous()
+                              and trig.numel() == 4 * (nbins_host[0] - 1 + nbins_host[1] - 1)), "tok_encode: bad trig table")
         L.check(self.lib.svla_tok_encode(_ptr(actions), _ptr(edges), C.cast(nb, C.c_void_p), _ptr(ids),
                                          actions.shape[0], float(min_action), float(max_action), int(use_spherical),
-                                         self._stream()), "svla_tok_encode")
+                                         _ptr(trig), int(phi_nonpos), int(phi_neg), self._stream()), "svla_tok_encode")
 
-    def tok_decode(self, ids, edges, nbins_host, begin, actions, *, use_spherical=True):
+    def tok_decode(self, ids, edges, nbins_host, begin, actions, *, use_spherical=True, center_trig=None):
+        """center_trig: float64 [theta bins + phi bins, 2] device table of (sin, cos) at the bin centres (host libm); None = sincos."""
         nb = (C.c_int32 * 7)(*nbins_host)
+        _req(center_trig is None or (center_trig.dtype == torch.float64 and center_trig.is_contiguous()
+                                     and center_trig.numel() == 2 * (nbins_host[0] + nbins_host[1])), "tok_decode: bad centre table")
         L.check(self.lib.svla_tok_decode(_ptr(ids), _ptr(edges), C.cast(nb, C.c_void_p), int(begin), _ptr(actions),
-                                         ids.shape[0], int(use_spherical), self._stream()), "svla_tok_decode")
+                                         ids.shape[0], int(use_spherical), _ptr(center_trig), self._stream()), "svla_tok_decode")

@@ -21,6 +21,32 @@ IMAGE_TOKEN = "<image>"
 EXTRA_TOKENS = [f"<loc{i:0>4}>" for i in range(1024)] + [f"<seg{i:0>3}>" for i in range(128)]
 
 
+# Keyword routing of HF `ProcessorMixin._merge_kwargs` for PaliGemmaProcessorKwargs (model/processing_spatialvla.py:113-117):
+# `images_kwargs` go to the image processor, `text_kwargs` to the tokenizer, `return_tensors` (common) to both.  The reference's
+# training call (data/dataset.py:134-142) passes do_normalize=False / max_length / truncation / padding in ONE kwargs bag.
+IMAGES_KWARGS = frozenset({
+    "do_resize", "size", "size_divisor", "crop_size", "resample", "do_rescale", "rescale_factor", "do_normalize", "image_mean",
+    "image_std", "do_pad", "pad_size", "do_center_crop", "data_format", "input_data_format", "do_convert_rgb", "device"})
+TEXT_KWARGS = frozenset({
+    "text_pair", "text_target", "text_pair_target", "add_special_tokens", "padding", "truncation", "max_length", "stride",
+    "is_split_into_words", "pad_to_multiple_of", "return_token_type_ids", "return_attention_mask", "return_overflowing_tokens",
+    "return_special_tokens_mask", "return_offsets_mapping", "return_length", "verbose", "padding_side", "return_mm_token_type_ids",
+    "suffix"})
+
+
+def split_processor_kwargs(kwargs):
+    """-> (images_kwargs, text_kwargs); keys HF does not know are dropped with a warning, as `_merge_kwargs` does."""
+    im, tx = {}, {}
+    for k, v in kwargs.items():
+        if k in IMAGES_KWARGS:
+            im[k] = v
+        elif k in TEXT_KWARGS:
+            tx[k] = v
+        else:
+            logger.warning("SpatialVLAProcessor: keyword argument %r is not a text / image processing option; ignored", k)
+    return im, tx
+
+
 def build_string_from_input(prompt, bos_token, image_seq_len, image_token, num_images):
     """HF paligemma/processing_paligemma.py:76-95 -- '<image>'*n + bos + prompt + newline"""
     return f"{image_token * image_seq_len * num_images}{bos_token}{prompt}\n"
@@ -99,9 +125,13 @@ class SpatialVLAProcessor:
 
     def __call__(self, images=None, text=None, unnorm_key: Optional[str] = None, suffix_actions=None,
                  return_tensors="pt", suffix=None, **kwargs) -> BatchFeature:
+        images_kwargs, text_kwargs = split_processor_kwargs(kwargs)
         if suffix_actions is not None:
             action_tokens = self.action_tokenizer(suffix_actions)
             suffix = "".join(action_tokens.flatten())
+            text_kwargs.pop("suffix", None)
+        elif suffix is None:
+            suffix = text_kwargs.pop("suffix", None)
         return_token_type_ids = suffix is not None
         if images is None:
             raise ValueError("`images` are expected as arguments to a `PaliGemmaProcessor` instance.")
@@ -131,8 +161,10 @@ class SpatialVLAProcessor:
                 idx = idx + len(IMAGE_TOKEN) if idx != -1 else 0
                 input_strings.append(ex[:idx] + self.tokenizer.bos_token + ex[idx:] + "\n")
         flat = [im for il in images for im in il]
-        pixel_values = self.image_processor(flat, return_tensors=return_tensors)["pixel_values"]
-        inputs = self._tokenize(input_strings, suffix, return_token_type_ids, return_tensors, kwargs)
+        pixel_values = self.image_processor(flat, return_tensors=return_tensors, **images_kwargs)["pixel_values"]
+        if text_kwargs.get("max_length") is not None:          # the limit is quoted without the image tokens (:176-178)
+            text_kwargs["max_length"] = text_kwargs["max_length"] + self.image_seq_length
+        inputs = self._tokenize(input_strings, suffix, return_token_type_ids, return_tensors, text_kwargs)
         intrinsic = self.dataset_intrinsics[unnorm_key] if unnorm_key in self.dataset_intrinsics \
             else self.dataset_intrinsics["default"]
         data = {**inputs, "pixel_values": pixel_values, "intrinsic": intrinsic}

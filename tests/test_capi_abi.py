@@ -51,10 +51,10 @@ def test_validation_errors_before_any_cuda_call(lib):
     assert lib.svla_attention(C.byref(a), None) == -1
     nb_bad = (C.c_int32 * 7)(16, 32, 8, 16, 16, 100, 2)
     x = np.zeros((1, 7)); e = np.zeros(200); ids = np.zeros((1, 3), dtype=np.int32)
-    assert lib.svla_tok_encode_host(x.ctypes.data, e.ctypes.data, C.cast(nb_bad, C.c_void_p), ids.ctypes.data, 1, -1.0, 1.0, 1) == -1
+    assert lib.svla_tok_encode_host(x.ctypes.data, e.ctypes.data, C.cast(nb_bad, C.c_void_p), ids.ctypes.data, 1, -1.0, 1.0, 1, None, 0, 0) == -1
     assert b"bins per axis" in lib.svla_last_error()
     nb = (C.c_int32 * 7)(16, 32, 8, 16, 16, 16, 2)
-    assert lib.svla_tok_encode_host(None, e.ctypes.data, C.cast(nb, C.c_void_p), None, 0, -1.0, 1.0, 1) == 0   # empty batch
+    assert lib.svla_tok_encode_host(None, e.ctypes.data, C.cast(nb, C.c_void_p), None, 0, -1.0, 1.0, 1, None, 0, 0) == 0   # empty batch
     with pytest.raises(L.SvlaError):
         L.check(-1, "x")
 

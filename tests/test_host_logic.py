@@ -166,6 +166,31 @@ def test_from_pretrained_checkpoint_roundtrip(tmp_path):
         SpatialVLAForConditionalGeneration.from_pretrained(str(tmp_path / "missing"), ops=RefOps())
 
 
+def test_tied_lm_head_checkpoint_loads_and_follows_the_spatial_overwrite(tmp_path):
+    """Gemma2 ties lm_head to embed_tokens (model/modeling_gemma2.py:888, model/modeling_spatialvla.py:171-172): a checkpoint saved
+    by the reference with tie_word_embeddings=True has NO lm_head key, and the post-load overwrite of embed_tokens[-n:] with
+    spatial_embed_tokens (:524-525) therefore also replaces the action-slice rows of the head."""
+    from safetensors.torch import save_file
+    from spatialvla_b200 import SpatialVLAConfig, get_config_dict
+    from spatialvla_b200.modeling_spatialvla import SpatialVLAForConditionalGeneration
+    cfg = get_config_dict("tiny")
+    cfg["text_config"]["tie_word_embeddings"] = True
+    sd = {k: v for k, v in synth_state_dict(get_config_dict("tiny"), seed=0).items() if k != "language_model.lm_head.weight"}
+    SpatialVLAConfig(**cfg).save_pretrained(tmp_path)
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(tmp_path / "model.safetensors"))
+    m = SpatialVLAForConditionalGeneration.from_pretrained(str(tmp_path), ops=RefOps())
+    n, lo = cfg["spatial_token_num"], cfg["action_token_begin_idx"]
+    V = cfg["text_config"]["vocab_size"]
+    assert lo + n == V                                        # the action slice is the tail of the vocabulary
+    want = sd["spatial_embed_tokens.weight"].to(torch.bfloat16).float()
+    assert torch.equal(m.engine.gem["head_act"].float(), want)
+    assert torch.equal(m.engine.lm_head_full()[-n:].float(), want)
+    assert torch.equal(m.engine.lm_head_full()[:lo].float(), sd["language_model.model.embed_tokens.weight"][:lo].to(torch.bfloat16).float())
+    # a plain dict without the key (no config flag) aliases as well instead of raising KeyError
+    eng = SpatialVLAEngine(get_config_dict("tiny"), sd, RefOps())
+    assert eng.gem["head_act"].shape == (n, cfg["text_config"]["hidden_size"])
+
+
 def test_labelled_forward_host_logic_matches_oracle_and_golden(tiny):
     """forward(labels=...) orchestration (mask selection, label shift / ignore / pad masking, row gather, chunked lm_head +
     cross entropy) through the torch op re-statements, against the fp32 oracle and the live-reference golden losses."""

@@ -163,3 +163,27 @@ def test_backward_oracle_matches_reference_autograd_golden():
                                  attention_mask=torch.ones(B, L, dtype=torch.int64))
     assert (Bm.grad - s * gw[k] @ A.detach().t()).abs().max() < 1e-5 * max(1.0, float(Bm.grad.abs().max()))
     assert (A.grad - s * Bm.detach().t() @ gw[k]).abs().max() < 1e-5 * max(1.0, float(A.grad.abs().max()))
+
+
+def test_exact_angular_binning_rule_reproduces_the_golden_ids():
+    """The atan2-free decision rule of svla_tok_encode (sign of a cos m - b sin m against the rounding boundary m below each edge,
+    table from spatialvla_b200.action_tokenizer.edge_trig_table) restated on the CPU: it reproduces the theta / phi bins of EVERY
+    golden action of the live reference -- including the rows built to sit on bin edges -- and of 30 000 random actions binned
+    by numpy's arctan2 + digitize."""
+    from oracle import tokenizer_ref as T
+    from spatialvla_b200.action_tokenizer import edge_trig_table
+    nb = {"translation": {"theta_bins": 16, "phi_bins": 32, "r_bins": 8}, "rotation": {"roll_bins": 16, "pitch_bins": 16, "yaw_bins": 16},
+          "gripper": 2}
+    for name in ("gauss", "uniform"):
+        g = np.load(os.path.join(GOLD, f"tokenizer_{name}.npz"))
+        pol = {"translation": {k: g["edge_" + k] for k in ("theta_bins", "phi_bins", "r_bins")},
+               "rotation": {k: g["edge_" + k] for k in ("roll_bins", "pitch_bins", "yaw_bins")}}
+        trig, pn, pg = edge_trig_table(pol["translation"]["theta_bins"][1:-1], pol["translation"]["phi_bins"][1:-1])
+        acts = g["actions"][::2] if name == "uniform" else g["actions"]
+        ids = (g["local_ids"][::2] if name == "uniform" else g["local_ids"])[:, 0].astype(np.int64)
+        dt, dp = T.encode_angles_exact(acts, pol, nb, trig, pn, pg)
+        assert np.array_equal(dt, ids // 256) and np.array_equal(dp, (ids % 256) // 8), name
+    rnd = np.random.default_rng(5).uniform(-1, 1, size=(30000, 7))
+    ref = T.encode(rnd, pol, nb)[:, 0]
+    dt, dp = T.encode_angles_exact(rnd, pol, nb, trig, pn, pg)
+    assert np.array_equal(dt, ref // 256) and np.array_equal(dp, (ref % 256) // 8)

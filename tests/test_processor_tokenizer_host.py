@@ -41,6 +41,36 @@ def test_processor_prompt_layout_and_intrinsics():
     assert moved["pixel_values"].dtype == torch.float16 and moved["input_ids"].dtype == torch.int64
 
 
+def test_training_call_routes_kwargs_like_the_reference_dataset():
+    """data/dataset.py:134-142 calls the processor with image options (do_normalize=False) and tokenizer options (max_length,
+    truncation, padding) in one kwargs bag; HF's _merge_kwargs routes them, and max_length is raised by the 256 image tokens
+    (model/processing_spatialvla.py:113-117,176-178)."""
+    seen = {}
+
+    class RecImage(FakeImageProcessor):
+        def __call__(self, images, return_tensors="pt", **kw):
+            seen["image"] = dict(kw)
+            return super().__call__(images, return_tensors=return_tensors)
+
+    class RecTok(FakeTokenizer):
+        def __call__(self, strings, **kw):
+            seen["text"] = {k: v for k, v in kw.items() if k not in ("text_pair", "return_token_type_ids", "return_tensors")}
+            return super().__call__(strings, **kw)
+
+    from spatialvla_b200 import SpatialVLAProcessor
+    p = SpatialVLAProcessor(RecImage(), RecTok(), statistics=STATS, intrinsic_config=INTR, action_config=ACTION_CONFIG, action_chunk_size=4)
+    from oracle import tokenizer_ref as T
+    tk, nb = p.action_tokenizer, ACTION_CONFIG["num_bins"]           # grid arithmetic needs the GPU; the host test injects the oracle
+    tk.encode_local_ids = lambda a: T.encode(np.asarray(a, dtype=np.float64).reshape(-1, 7), tk.bin_policy, nb).astype(np.int32)
+    img = (np.random.default_rng(0).random((224, 224, 3)) * 255).astype(np.uint8)
+    acts = np.random.default_rng(1).uniform(-1, 1, (4, 7))
+    out = p(text="pick up the cup", images=[img], suffix_actions=acts, return_tensors="pt", padding=False, max_length=64,
+            truncation=True, do_normalize=False, not_an_option=1)
+    assert seen["image"] == {"do_normalize": False}
+    assert seen["text"] == {"padding": False, "max_length": 64 + 256, "truncation": True}
+    assert out["labels"].shape == out["input_ids"].shape and "token_type_ids" in out
+
+
 def test_tokenizer_sub_ranges_and_edges():
     from spatialvla_b200 import SpatialActionTokenizer
     t = SpatialActionTokenizer(FakeTokenizer(257153), ACTION_CONFIG["num_bins"], gs_params=None)

@@ -232,6 +232,23 @@ int svla_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
 int svla_siglip_patchify(const float* px, void* a, int batch, int kpad, void* stream);
 int svla_zoe_patchify(const float* px, void* a, int batch, void* stream);
 
+/* M9b observation frames on the device (model/processing_spatialvla.py:174 -> HF SiglipImageProcessor @ transformers 4.47 -> Pillow
+ * ImagingResample): images uint8 [B, h, w, 3] -> out fp32 [B, 3, oh, ow] = value_lut[c][resize_bicubic_u8(image)].  Pillow's
+ * separable fixed-point resampler, horizontal pass first (into tmp_u8 [B, h, ow, 3]; may be NULL when w == ow), then vertical;
+ * bounds_* int32 [o, 2] = (first source index, taps), kk_* int32 [o, ksize_*] 22-bit fixed-point coefficients (host-built per
+ * input size); value_lut fp32 [3, 256] = what the image processor turns each uint8 level into (rescale, optional normalise). */
+int svla_image_preprocess(const void* images_u8, int batch, int h, int w, void* tmp_u8, float* out, int oh, int ow,
+                          const int32_t* bounds_h, const int32_t* kk_h, int ksize_h, const int32_t* bounds_v, const int32_t* kk_v,
+                          int ksize_v, const float* value_lut, void* stream);
+
+/* Fine-tune-time re-gridding of the spatial embeddings (model/action_tokenizer.py:390-430: scipy griddata 'linear' = Delaunay
+ * interpolation of the old padded grid at the new bin centres): out[t, :] = sum_{v<4} weights[t, v] * src[rows[t, v], :] with double
+ * accumulation in scipy's order; rows[t, 0] < 0 (target outside the old hull) gives a NaN row like the reference.  The triangulation /
+ * point location is E-independent host work (SpatialActionTokenizer.adaption_plan, same Qhull call as griddata); this is the
+ * 8 192 x 2 304 gather.  src fp32 [n_src, e], rows int32 [n_out, 4], weights fp64 [n_out, 4], out fp32 [n_out, e]. */
+int svla_barycentric_gather(const float* src, int64_t n_src, const int32_t* rows, const double* weights, float* out, int64_t n_out,
+                            int e, void* stream);
+
 /* BEiT token assembly: x[b,0,:] = cls, x[b,1+i,:] = patches[b*n+i,:] (HF beit :190-222). fp32 */
 int svla_beit_assemble(const float* patches, const float* cls, float* x, int batch, int n, int c, void* stream);
 
@@ -264,6 +281,14 @@ int svla_zoe_router_embed(const float* conv, float* e, void* e_bf16, int batch, 
  * na <= 16, nbins % 4 == 0 (the reference has na in {16, 8, 4, 1}, nbins = 64) */
 int svla_zoe_attractor(const void* attr, const float* prev, float* out, int batch, int h, int w, int oh, int ow,
                        int na, int nbins, void* stream);
+
+/* ZoeDepth metric-head router decision on the device (HF zoedepth :1059-1067 picks argmax_h sum_b domain_logits[b, h] and reads
+ * it back with `.item()`): the weights of every metric-bins head are packed by the caller into one byte arena per head (identical
+ * layout); this call copies the arena of the selected head into `active_arena`, which the kernels of the bins stage read, and
+ * writes the index to head_out (may be NULL).  No host synchronisation: the whole predict_action step is ONE CUDA graph.
+ * head_arenas_dev: DEVICE array of n_heads device pointers; forced_head >= 0 overrides the vote (tests, per-shard parity). */
+int svla_zoe_select_head(const float* domain_logits, int batch, int n_heads, int forced_head, const void* const* head_arenas_dev,
+                         void* active_arena, int64_t bytes, int* head_out, void* stream);
 
 /* softplus(x) bf16 -> fp32 (seed bin regressor, HF zoedepth :494-547) */
 int svla_softplus_f32(const void* x, float* out, int64_t n, void* stream);

@@ -475,6 +475,30 @@ def predict_action_ref(sd, cfg, input_ids, pixel_values, intrinsic, n_new, force
     return out
 
 
+def generate_ref(sd, cfg, input_ids, pixel_values, intrinsic, max_new_tokens, eos_id, pad_id, force_head=None):
+    """HF greedy `generate` as the reference's predict_action calls it (model/modeling_spatialvla.py:484-492; GenerationMixin
+    4.47 `_sample` with do_sample=False): full-vocabulary argmax of the post-softcap logits, finished rows emit pad_id, a row
+    finishes on eos_id, stop when all rows are finished or after max_new_tokens.  Returns the NEW tokens int64 [B, n]."""
+    V = cfg["text_config"]["vocab_size"]
+    with torch.no_grad():
+        feats = image_features(sd, cfg, pixel_values, intrinsic, force_head)
+        x = embed_inputs(sd, cfg, input_ids, feats)
+        B, P, _ = x.shape
+        cache = [None] * cfg["text_config"]["num_hidden_layers"]
+        h = gemma2_forward(sd, cfg, x, 0, cache, bidirectional=True)
+        unfinished = torch.ones(B, dtype=torch.bool)
+        out = []
+        for step in range(max_new_tokens):
+            nxt = lm_head_slice(sd, cfg, h[:, -1], 0, V).argmax(-1)
+            nxt = torch.where(unfinished, nxt, torch.full_like(nxt, pad_id))
+            out.append(nxt)
+            unfinished = unfinished & (nxt != eos_id)
+            if step == max_new_tokens - 1 or not bool(unfinished.any()):
+                break
+            h = gemma2_forward(sd, cfg, embed_inputs(sd, cfg, nxt[:, None]), P + step, cache, bidirectional=False)
+    return torch.stack(out, 1)
+
+
 def prefix_length(token_type_ids):
     """(B, L) token types -> p such that every row is p zeros followed by L - p ones (prefix / suffix of the training samples,
     train/monkey_patch.py:21-75); raises for any other pattern."""

@@ -306,6 +306,38 @@ class RefOps:
         col = F.unfold(process_zoe(px), kernel_size=16, stride=16).transpose(1, 2).reshape(B * 576, 768)
         a.copy_(col.to(BF16))
 
+    def image_preprocess(self, images, tmp, out, tab_h, tab_v, lut):
+        """Pillow's two-pass fixed-point resampler from the SAME host-built tables (the tables themselves are pinned against
+        oracle/image_ref.py and Pillow in tests/test_image_preprocess.py)."""
+        self.launches += 1
+        cur = images.to(torch.int64)
+        for axis, tab in ((2, tab_h), (1, tab_v)):
+            if tab is None:
+                continue
+            bounds, kk, _ = tab
+            rows = []
+            for o in range(bounds.shape[0]):
+                lo, n = int(bounds[o, 0]), int(bounds[o, 1])
+                k = kk[o, :n].to(torch.int64)
+                sl = cur.narrow(axis, lo, n)
+                shape = [1, 1, 1, 1]
+                shape[axis] = n
+                acc = (sl * k.view(shape)).sum(axis) + (1 << 21)
+                rows.append((acc >> 22).clamp(0, 255))
+            cur = torch.stack(rows, axis)
+        idx = cur.permute(0, 3, 1, 2)                                  # [B, 3, oh, ow]
+        out.copy_(torch.stack([lut[c][idx[:, c]] for c in range(3)], 1))
+
+    def barycentric_gather(self, src, rows, weights, out):
+        self.launches += 1
+        ok = rows[:, 0] >= 0
+        r = rows.clamp(min=0).long()
+        acc = torch.zeros(out.shape, dtype=torch.float64)
+        for v in range(4):
+            acc = acc + weights[:, v:v + 1] * src[r[:, v]].double()
+        acc[~ok] = float("nan")
+        out.copy_(acc.float())
+
     def beit_assemble(self, patches, cls, x, *, batch, n, c):
         self.launches += 1
         xv = x.view(batch, n + 1, c)
@@ -369,6 +401,13 @@ class RefOps:
             dx = A[:, i:i + 1] - c
             delta = delta + dx / (1 + 300.0 * dx * dx)
         out.view(batch, oh, ow, nbins).copy_((c + delta / na).permute(0, 2, 3, 1))
+
+    def zoe_select_head(self, dlog, arena_ptrs, active, head_out, *, forced=-1):
+        """arena_ptrs: on the CPU stand-in, a list of the per-head uint8 arenas themselves."""
+        self.launches += 1
+        head = int(forced) if forced >= 0 else int(torch.argmax(dlog.sum(0)))
+        active.copy_(arena_ptrs[head])
+        head_out.fill_(head)
 
     def softplus_f32(self, x, out):
         self.launches += 1

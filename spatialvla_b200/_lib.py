@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "lib", "libspatialvla_b200.so")
 SOURCES = ["capi.cu", "gemm_tcgen05.cu", "gemm_skinny.cu", "attention.cu", "attention_tc.cu", "decode_small.cu", "fused_ops.cu",
-           "tokenizer.cu"]
+           "tokenizer.cu", "image_ops.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -80,6 +80,8 @@ SIGNATURES = {
     "svla_cross_entropy_bwd": (_I, [_P, _L, _L, _L, _P, _L, _P, _L, _P, _F, _P, _L, _P]),
     "svla_siglip_patchify": (_I, [_P, _P, _I, _I, _P]),
     "svla_zoe_patchify": (_I, [_P, _P, _I, _P]),
+    "svla_image_preprocess": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P]),
+    "svla_barycentric_gather": (_I, [_P, _L, _P, _P, _P, _L, _I, _P]),
     "svla_beit_assemble": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "svla_readout_concat": (_I, [_P, _P, _I, _I, _I, _P]),
     "svla_pixel_shuffle": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
@@ -89,6 +91,7 @@ SIGNATURES = {
     "svla_zoe_router_embed": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "svla_zoe_attractor": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "svla_softplus_f32": (_I, [_P, _P, _L, _P]),
+    "svla_zoe_select_head": (_I, [_P, _I, _I, _I, _P, _P, _L, _P, _P]),
     "svla_zoe_depth_tail": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "svla_zoe_depth_tail_fused": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "svla_ego3d_encode": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _P]),
@@ -112,6 +115,9 @@ def build_library(verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")] + [os.path.join(_HERE, "..", "include", "spatialvla_b200.h")]
     hdr_time = max(os.path.getmtime(h) for h in hdrs)
+    src_time = max(os.path.getmtime(os.path.join(CSRC, s)) for s in SOURCES)
+    if os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= max(hdr_time, src_time):
+        return LIB_PATH                  # e.g. on the GPU box: the prebuilt library travels, the object files do not
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = [f for f in NVCC_FLAGS if f != "-shared"]
 

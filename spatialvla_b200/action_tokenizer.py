@@ -208,11 +208,40 @@ class SpatialActionTokenizer:
             grids += [np.stack([gx, gy, gz], -1).reshape(-1, 3)]
         return grids[0], grids[1]
 
-    def spatial_embedding_adaption(self, gs_params, embeddings, min_sigma=0.0, adpt_feature=False):
-        """Re-grid the tokenizer to new Gaussians and (optionally) re-sample the spatial embeddings by scattered
-        linear interpolation, as model/action_tokenizer.py:390-430 does (scipy.interpolate.griddata, host)."""
+    @staticmethod
+    def adaption_plan(grid0, grid1, dims):
+        """Geometry of the re-gridding, independent of the embedding width: `griddata(grid0, values, grid1, 'linear')` is Delaunay
+        interpolation -- NOT trilinear: Qhull splits the (degenerate) cells of the padded grid into tetrahedra -- so the plan takes
+        the triangulation from the same Qhull call (scipy.spatial.Delaunay, what griddata builds internally), locates every
+        interior target point and returns its 4 source rows and barycentric weights.  Point p of grid0 carries the value of padded
+        cell unravel(p, (m+2, n+2, k+2)) exactly as the reference pairs them (its meshgrid is 'xy'-ordered while the values are
+        'ij'-ordered, model/action_tokenizer.py:372-388,402-405 -- reproduced, not fixed); replicate padding = clamped indices.
+        -> (rows int32 [m*n*k, 4] embedding rows of the block, -1 where the target lies outside the hull (NaN in the reference),
+            weights float64 [m*n*k, 4])."""
+        from scipy.spatial import Delaunay
+        m, n, k = dims
+        tri = Delaunay(np.asarray(grid0, dtype=np.float64))
+        ii, jj, ll = np.meshgrid(np.arange(1, m + 1), np.arange(1, n + 1), np.arange(1, k + 1), indexing="ij")
+        tgt = ((ii * (n + 2) + jj) * (k + 2) + ll).reshape(-1)                 # interior targets, in output-row order
+        x = np.asarray(grid1, dtype=np.float64)[tgt]
+        simp = tri.find_simplex(x)
+        ok = simp >= 0
+        T = tri.transform[np.where(ok, simp, 0)]
+        b = np.einsum("nij,nj->ni", T[:, :3], x - T[:, 3])
+        w = np.concatenate([b, 1.0 - b.sum(1, keepdims=True)], 1)
+        verts = tri.simplices[np.where(ok, simp, 0)]                           # [N, 4] point indices of grid0
+        pi, pj, pl = np.unravel_index(verts, (m + 2, n + 2, k + 2))
+        rows = (np.clip(pi - 1, 0, m - 1) * n + np.clip(pj - 1, 0, n - 1)) * k + np.clip(pl - 1, 0, k - 1)
+        rows = np.where(ok[:, None], rows, -1).astype(np.int32)
+        return np.ascontiguousarray(rows), np.ascontiguousarray(w)
+
+    def spatial_embedding_adaption(self, gs_params, embeddings, min_sigma=0.0, adpt_feature=False, ops=None):
+        """Re-grid the tokenizer to new Gaussians and (optionally) re-sample the spatial embeddings by scattered linear
+        interpolation, as model/action_tokenizer.py:390-430 does.  With `ops` (CudaOps; implied for CUDA embeddings) the 8 192 x E
+        re-sampling runs on the GPU: the triangulation / point location (E-independent, `adaption_plan`) stays on the host, the
+        4-row barycentric gather over the embedding table is the `svla_barycentric_gather` kernel.  Without it: scipy griddata on
+        the host, call for call like the reference."""
         import torch
-        from scipy.interpolate import griddata
         new_policy = self.get_bin_policy(gs_params, min_sigma=min_sigma)
         g0t, g0r = self.get_norm_meshgrid(self.bin_policy)
         g1t, g1r = self.get_norm_meshgrid(new_policy)
@@ -223,6 +252,21 @@ class SpatialActionTokenizer:
         emb = embeddings.weight.data
         E = emb.shape[1]
         off = 0
+        if ops is None and emb.is_cuda:
+            from .ops import CudaOps
+            ops = CudaOps(emb.device)
+        if ops is not None:
+            for (grid0, grid1, keys, bt) in ((g0t, g1t, _TRANS_KEYS, "translation"), (g0r, g1r, _ROT_KEYS, "rotation")):
+                dims = tuple(self.num_bins[bt][kk] for kk in keys)
+                N = dims[0] * dims[1] * dims[2]
+                rows, w = self.adaption_plan(grid0, grid1, dims)
+                src = emb[off:off + N].to(device=ops.device, dtype=torch.float32).contiguous()
+                out = ops.empty((N, E), torch.float32)
+                ops.barycentric_gather(src, torch.from_numpy(rows).to(ops.device), torch.from_numpy(w).to(ops.device), out)
+                emb[off:off + N] = out.to(device=emb.device, dtype=emb.dtype)
+                off += N
+            return
+        from scipy.interpolate import griddata
         for (grid0, grid1, keys, bt) in ((g0t, g1t, _TRANS_KEYS, "translation"), (g0r, g1r, _ROT_KEYS, "rotation")):
             m, n, k = (self.num_bins[bt][kk] for kk in keys)
             N = m * n * k

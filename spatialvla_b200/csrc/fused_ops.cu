@@ -1461,6 +1461,48 @@ extern "C" int svla_embed_tokens(const int64_t* ids, const void* embed, const vo
   return 0;
 }
 
+// ZoeDepth metric-head router decision ON THE DEVICE (HF zoedepth/modeling_zoedepth.py:1059-1067: argmax of the batch-summed
+// domain logits, which HF reads back with `.item()`): every CTA recomputes the (tiny) vote and copies its slice of the selected
+// head's packed weight arena into the ACTIVE arena the following kernels read, so one CUDA graph covers the whole step.
+__global__ void __launch_bounds__(256)
+svla_zoe_select_head_kernel(const float* __restrict__ dlog, int batch, int n_heads, int forced, const uint4* __restrict__ const* __restrict__ srcs,
+                            uint4* __restrict__ dst, long long n16, int* __restrict__ head_out) {
+  __shared__ int head_sh;
+  if (threadIdx.x == 0) {
+    int best = 0;
+    if (forced >= 0) best = forced;
+    else {
+      float bv = -INFINITY;
+      for (int h = 0; h < n_heads; ++h) {
+        float v = 0.f;
+        for (int b = 0; b < batch; ++b) v += dlog[b * n_heads + h];      // torch.sum over dim 0, then first maximum wins
+        if (v > bv) { bv = v; best = h; }
+      }
+    }
+    head_sh = best;
+    if (blockIdx.x == 0 && head_out) *head_out = best;
+  }
+  __syncthreads();
+  const uint4* __restrict__ src = srcs[head_sh];
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n16; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = src[i];
+}
+
+extern "C" int svla_zoe_select_head(const float* domain_logits, int batch, int n_heads, int forced_head, const void* const* head_arenas_dev,
+                                    void* active_arena, int64_t bytes, int* head_out, void* stream) {
+  SVLA_REQUIRE(domain_logits && head_arenas_dev && active_arena && batch > 0 && n_heads > 0 && n_heads <= 8, "svla_zoe_select_head: bad arguments");
+  SVLA_REQUIRE(bytes > 0 && (bytes % 16) == 0 && (reinterpret_cast<uintptr_t>(active_arena) & 15) == 0, "svla_zoe_select_head: arena must be 16-byte granular");
+  SVLA_REQUIRE(forced_head < n_heads, "svla_zoe_select_head: forced head %d out of range", forced_head);
+  const long long n16 = bytes / 16;
+  long long blocks = (n16 + 255) / 256;
+  if (blocks > 2LL * svla_num_sms()) blocks = 2LL * svla_num_sms();
+  svla_zoe_select_head_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      domain_logits, batch, n_heads, forced_head, reinterpret_cast<const uint4* const*>(head_arenas_dev), static_cast<uint4*>(active_arena), n16,
+      head_out);
+  SVLA_LAUNCH_CHECK("svla_zoe_select_head");
+  return 0;
+}
+
 extern "C" int svla_argmax_rows(const float* logits, int64_t rows, int64_t cols, int64_t ld, int64_t id_offset, int64_t* out_ids,
                                 int64_t out_stride, void* stream) {
   SVLA_REQUIRE(logits && out_ids && rows > 0 && cols > 0, "svla_argmax_rows: bad arguments");

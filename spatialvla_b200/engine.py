@@ -64,7 +64,8 @@ class SpatialVLAEngine:
         self.z = cfg["vision_zoe_config"] if self.use_zoe else None
         self.act_lo = cfg["action_token_begin_idx"]
         self.n_act = cfg["spatial_token_num"]
-        self.last_router_head = None
+        self._last_head_host = None
+        self._head_active = None
         self.force_head = None
         self._pack(state_dict)
 
@@ -225,6 +226,67 @@ class SpatialVLAEngine:
             hd["clb_b2"] = Fp(q + "2.bias")
             mh["heads"].append(hd)
         self.mh = mh
+        self._build_head_arenas()
+
+    _HEAD_KEYS = ("sr1_w", "sr1_b", "sr2_w", "sr2_b", "clb_wa", "clb_wb", "clb_b1", "clb_w2", "clb_b2")
+
+    def _build_head_arenas(self):
+        """Device-side router select (HF zoedepth :1059-1067 reads the vote back with `.item()`): the weights of every
+        metric-bins head are re-packed into one byte arena per head with an identical layout, plus one ACTIVE arena whose views the
+        bins stage reads.  `svla_zoe_select_head` votes on the device and copies the winner's arena (< 1 MB) into the active one, so
+        the step has no device->host read and replays from ONE CUDA graph.  Heads of different shapes keep the host read."""
+        heads = self.mh["heads"]
+
+        def items(hd):
+            out = [(k, hd[k]) for k in self._HEAD_KEYS]
+            for i, at in enumerate(hd["att"]):
+                out += [((i, k), at[k]) for k in ("w1", "b1", "w2", "b2")]
+            return out
+
+        ref = items(heads[0])
+        same = all(len(items(h)) == len(ref) and all(a[1].shape == b[1].shape and a[1].dtype == b[1].dtype for a, b in zip(items(h), ref))
+                   and h["conf"]["n_bins"] == heads[0]["conf"]["n_bins"] for h in heads)
+        self._head_active = None
+        if not same or len(heads) > 8:
+            return
+        offs, off = [], 0
+        for _, t in ref:
+            offs.append(off)
+            off += (t.numel() * t.element_size() + 255) // 256 * 256
+        arenas = []
+        for h in heads:
+            ar = torch.zeros(off, dtype=torch.uint8, device=self.dev)
+            for (_, t), o in zip(items(h), offs):
+                nb = t.numel() * t.element_size()
+                ar[o:o + nb].copy_(t.contiguous().view(-1).view(torch.uint8))
+            arenas.append(ar)
+        active = torch.zeros(off, dtype=torch.uint8, device=self.dev)
+        act = {"conf": heads[0]["conf"], "att": [dict() for _ in heads[0]["att"]]}
+        for (k, t), o in zip(ref, offs):
+            v = active[o:o + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+            if isinstance(k, tuple):
+                act["att"][k[0]][k[1]] = v
+            else:
+                act[k] = v
+        self._head_arenas, self._head_arena_active, self._head_active = arenas, active, act
+        if getattr(self.ops, "name", "") == "cuda":
+            self._head_ptrs = torch.tensor([a.data_ptr() for a in arenas], dtype=torch.int64).to(self.dev)
+        else:
+            self._head_ptrs = arenas
+        self._head_idx = torch.zeros(1, dtype=torch.int32, device=self.dev)
+
+    @property
+    def last_router_head(self):
+        """Metric head the router picked on the last step (one lazy device->host read, outside the hot path)."""
+        if self._last_head_host is not None:
+            return self._last_head_host
+        if getattr(self, "_head_idx_valid", False):
+            return int(self._head_idx.item())
+        return None
+
+    @last_router_head.setter
+    def last_router_head(self, v):
+        self._last_head_host = v
 
     def lm_head_full(self):
         if self._lm_head_full is None:
@@ -319,7 +381,10 @@ class SpatialVLAEngine:
             f = self._lin(h, L_["wi"], B * S, bias=L_["bi"], act=ACT_GELU_ERF)
             ops.gemm(f, L_["wo2"], bias=L_["bo2"], colscale=L_["l2"], out_f32=x, accumulate=True)
             if (i + 1) in taps:
-                hs.append(x.clone())
+                # tap = read-out 'project' input [tok_i | cls] (HF zoedepth :55-110) written straight from the live residual stream
+                a = ops.empty((B * n, 2 * C_), BF16)
+                ops.readout_concat(x, a, batch=B, n=n, c=C_)
+                hs.append(a)
         return hs, win
 
     def _conv3(self, x, w, shape, **kw):
@@ -335,14 +400,11 @@ class SpatialVLAEngine:
 
     def zoe_neck(self, hs, win, B):
         ops, nk, z = self.ops, self.neck, self.z
-        C_ = z["backbone_config"]["hidden_size"]
         n = win * win
         Fh = z["fusion_hidden_size"]
         feats, feats_relu, res_ = [], [], []
         for s_, (st, ch) in enumerate(zip(nk["stages"], z["neck_hidden_sizes"])):
-            a = ops.empty((B * n, 2 * C_), BF16)
-            ops.readout_concat(hs[s_], a, batch=B, n=n, c=C_)
-            r = self._lin(a, st["ro_w"], B * n, bias=st["ro_b"], act=ACT_GELU_ERF)
+            r = self._lin(hs[s_], st["ro_w"], B * n, bias=st["ro_b"], act=ACT_GELU_ERF)
             pj = self._lin(r, st["proj_w"], B * n, bias=st["proj_b"])
             fac = st["factor"]
             if fac > 1:
@@ -424,19 +486,25 @@ class SpatialVLAEngine:
         return xb, self.zoe_router(xb, B, n)
 
     def pick_head(self, dlog):
-        """Batch-level vote exactly as HF (:1059-1067); one tiny D2H read like the reference's `.item()`."""
+        """Batch-level vote exactly as HF (:1059-1067), decided ON THE DEVICE: `svla_zoe_select_head` copies the winning head's
+        weights into the active arena the bins stage reads -- no `.item()`, no graph split.  Returns the head's weight dict.
+        (Heads of unequal shapes fall back to the reference's host read.)"""
         self.last_domain_logits = dlog
-        head = int(self.force_head) if self.force_head is not None else int(torch.argmax(dlog.sum(0)).item())
-        self.last_router_head = head
-        return head
+        if self._head_active is None:
+            head = int(self.force_head) if self.force_head is not None else int(torch.argmax(dlog.sum(0)).item())
+            self.last_router_head = head
+            return self.mh["heads"][head]
+        self.ops.zoe_select_head(dlog, self._head_ptrs, self._head_arena_active, self._head_idx,
+                                 forced=-1 if self.force_head is None else int(self.force_head))
+        self._last_head_host, self._head_idx_valid = None, True
+        return self._head_active
 
-    def zoe_bins_stage(self, head, xb, outconv, bottleneck, fused_list, B):
-        """Seed bins, 4 attractor stages and the conditional log-binomial tail of the chosen metric head."""
+    def zoe_bins_stage(self, hd, xb, outconv, bottleneck, fused_list, B):
+        """Seed bins, 4 attractor stages and the conditional log-binomial tail of the chosen metric head (`hd`: its weight dict)."""
         ops, mh, z = self.ops, self.mh, self.z
         rb = bottleneck[1]
         n = rb * rb
         E = z["bin_embedding_dim"]
-        hd = mh["heads"][head]
         nbins = hd["conf"]["n_bins"]
         s1 = self._lin(xb, hd["sr1_w"], B * n, bias=hd["sr1_b"], act=ACT_RELU)
         prev_bin = self._lin(s1, hd["sr2_w"], B * n, F32, bias=hd["sr2_b"], act=ACT_SOFTPLUS)
@@ -745,6 +813,40 @@ class SpatialVLAEngine:
         self.last_status = status
         return toks
 
+    def generate_reference(self, ids, px, intrinsic, max_new_tokens, eos_id, pad_id, pads=None):
+        """The reference's own decoding rule (model/modeling_spatialvla.py:484-492: HF greedy `generate(max_new_tokens=256,
+        do_sample=False)`): argmax over the FULL vocabulary, a row is finished once it emits `eos_id` and is fed / padded with
+        `pad_id` afterwards, the loop stops when every row is finished or after max_new_tokens.  Like HF's stopping criteria this
+        reads one flag per step on the host; it is the validation path for real checkpoints (test/test_huggingface.py), not the
+        throughput path (`generate_actions`).  Returns int64 [B, n_generated]."""
+        ops = self.ops
+        B, P = ids.shape
+        H, V = self.t["hidden_size"], self.t["vocab_size"]
+        cap = self.t["final_logit_softcapping"]
+        feats = self.image_features(px, intrinsic) if px is not None else None
+        x, status = self.embed(ids, feats)
+        cache = self.new_cache(B, P + max_new_tokens)
+        cache.pop("small_table", None)
+        h = self.gemma_forward(x, B, P, cache, bidirectional=True, pads=pads)
+        rows = h.view(B, P * H)[:, (P - 1) * H:]
+        w = self.lm_head_full()
+        out = []
+        unfinished = torch.ones(B, dtype=torch.bool, device=self.dev)
+        for step in range(max_new_tokens):
+            lg = ops.empty((B, V), F32)
+            ops.gemm(rows, w, out_f32=lg, act=ACT_SOFTCAP if cap else ACT_NONE, act_param=cap or 0.0)
+            nxt = ops.zeros((B,), torch.int64)
+            ops.argmax_rows(lg, nxt)
+            nxt = torch.where(unfinished, nxt, torch.full_like(nxt, pad_id))           # HF: finished rows emit the pad id
+            out.append(nxt)
+            unfinished = unfinished & (nxt != eos_id)
+            if step == max_new_tokens - 1 or not bool(unfinished.any()):
+                break
+            x, _ = self.embed(nxt.view(B, 1).contiguous())
+            rows = self.gemma_forward(x, B, 1, cache, bidirectional=False, pads=pads)
+        self.last_status = status
+        return torch.stack(out, 1)
+
     def generate_actions(self, ids, px, intrinsic, n_new, forced_tokens=None, return_logits=False, pads=None):
         """Greedy decode of n_new action tokens (argmax restricted to the action slice). ids int64 [B,P] on device.
         Returns tokens int64 [B, n_new] (+ fp32 logits [B, n_new, n_act]).  On a CUDA device the whole step is
@@ -764,12 +866,14 @@ class SpatialVLAEngine:
     use_graphs = os.environ.get("SVLA_NO_GRAPHS", "0") != "1"
 
     def _generate_graphed(self, ids, px, intrinsic, n_new, pads=None):
-        """Static-shape replay: graph A = vision stage A (ends with the router logits); one D2H read picks the metric
-        head; graph B[head] = metric-bins tail + Ego3D + projector + Gemma2 prefill + decode loop.  Kernel arguments
-        (TMA descriptors included) are baked at capture; inputs are copied into static buffers before each replay."""
+        """Static-shape replay of the WHOLE step from one CUDA graph: vision towers, the ZoeDepth router vote (decided on the
+        device, `pick_head`), metric-bins tail, Ego3D, projector, Gemma2 prefill and the decode loop.  Kernel arguments (TMA
+        descriptors included) are baked at capture; inputs are copied into static buffers before each replay.  No device->host
+        read anywhere in here: the result and the embedding kernel's status word are read by the caller when it wants them."""
         B, P = ids.shape
         Kdim = intrinsic.dim()
-        key = (B, P, n_new, Kdim, pads is not None)
+        head_mode = "dev" if (self._head_active is not None or not self.use_zoe) else "host"
+        key = (B, P, n_new, Kdim, pads is not None, self.force_head if head_mode == "dev" else None)
         if not hasattr(self, "_graphs"):
             self._graphs = {}
         g = self._graphs.get(key)
@@ -778,7 +882,7 @@ class SpatialVLAEngine:
         if g is None:
             g = {"ids": ids.clone(), "px": px.clone().contiguous(), "K": K.clone().contiguous(), "B": {}, "launches_b": {},
                  "pads": None if pads is None else pads.clone()}
-            # warm-up outside capture (cudaFuncSetAttribute, lazy module load), then capture stage A
+            # warm-up outside capture (cudaFuncSetAttribute, lazy module load), then capture
             feats = self.image_features(g["px"], g["K"])
             self.language_stage(g["ids"], feats, n_new, pads=g["pads"])
             torch.cuda.synchronize()
@@ -786,6 +890,11 @@ class SpatialVLAEngine:
             ga = torch.cuda.CUDAGraph()
             with torch.cuda.graph(ga):
                 g["st"] = self.vision_stage_a(g["px"])
+                if head_mode == "dev":
+                    hd = self.pick_head(g["st"]["dlog"]) if self.use_zoe else 0
+                    feats = self.vision_stage_b(g["st"], hd, g["K"], B)
+                    g["toks"] = self.language_stage(g["ids"], feats, n_new, pads=g["pads"])
+                    g["status"] = self.last_status
             g["A"], g["launches_a"] = ga, self.ops.launch_count() - n0
             self._graphs[key] = g
         g["ids"].copy_(ids)
@@ -794,16 +903,23 @@ class SpatialVLAEngine:
         if pads is not None:
             g["pads"].copy_(pads)
         g["A"].replay()
-        head = self.pick_head(g["st"]["dlog"]) if self.use_zoe else 0
+        if head_mode == "dev":
+            self._last_head_host, self._head_idx_valid = None, self.use_zoe
+            self.last_status = g["status"]
+            self.graph_replayed_launches = getattr(self, "graph_replayed_launches", 0) + g["launches_a"]
+            return g["toks"].clone()
+        # metric heads of unequal shapes: the reference's host read between two graphs
+        hd = self.pick_head(g["st"]["dlog"])
+        head = self.last_router_head
         if head not in g["B"]:
             n0 = self.ops.launch_count()
             gb = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gb):
-                feats = self.vision_stage_b(g["st"], head, g["K"], B)
+                feats = self.vision_stage_b(g["st"], hd, g["K"], B)
                 toks = self.language_stage(g["ids"], feats, n_new, pads=g["pads"])
-            g["B"][head] = (gb, toks)
+            g["B"][head] = (gb, toks, self.last_status)
             g["launches_b"][head] = self.ops.launch_count() - n0
-        gb, toks = g["B"][head]
+        gb, toks, self.last_status = g["B"][head]
         gb.replay()
         self.graph_replayed_launches = getattr(self, "graph_replayed_launches", 0) + g["launches_a"] + g["launches_b"][head]
         return toks.clone()

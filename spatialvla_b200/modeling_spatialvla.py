@@ -155,9 +155,33 @@ class SpatialVLAForConditionalGeneration:
         return pads.to(device=self.device, dtype=torch.int32).contiguous()
 
     @torch.no_grad()
-    def predict_action(self, model_inputs, max_new_tokens: Optional[int] = None, return_logits: bool = False):
+    def generate(self, model_inputs=None, max_new_tokens: int = 256, do_sample: bool = False, eos_token_id=None, pad_token_id=None,
+                 **inputs):
+        """HF-`generate` semantics of the reference's predict_action (model/modeling_spatialvla.py:484-492): greedy, argmax over the
+        FULL vocabulary, stop at EOS (finished rows padded), at most `max_new_tokens` new tokens.  Returns prompt + generated ids
+        like `GenerationMixin.generate`; `predict_action(..., reference_generate=True)` strips the prompt as the reference does."""
+        if do_sample:
+            raise NotImplementedError("sampling is not part of the reference's predict_action path (do_sample=False at :491)")
+        model_inputs = dict(model_inputs) if model_inputs is not None else {}
+        model_inputs.update(inputs)
+        ids, px, K, pads = self._prepare(model_inputs)
+        eos = eos_token_id if eos_token_id is not None else self.engine_config.get("eos_token_id")
+        pad = pad_token_id if pad_token_id is not None else self.engine_config.get("pad_token_id")
+        eos = 1 if eos is None else int(eos)
+        pad = eos if pad is None else int(pad)                      # HF falls back to the EOS id when no pad id is configured
+        new = self.engine.generate_reference(ids, px, K, int(max_new_tokens), eos, pad, pads=pads)
+        self.raise_if_bad_batch()
+        return torch.cat([ids, new], 1)
+
+    @torch.no_grad()
+    def predict_action(self, model_inputs, max_new_tokens: Optional[int] = None, return_logits: bool = False,
+                       reference_generate: bool = False):
         """model_inputs: dict-like with input_ids (B,P), pixel_values (B,3,224,224) in [0,1], intrinsic (3,3)|(B,3,3)
-        -> LongTensor (B, n_new) of generated action-token ids on the model device (prompt stripped, :492)."""
+        -> LongTensor (B, n_new) of generated action-token ids on the model device (prompt stripped, :492).
+        reference_generate=True: the reference's exact decoding rule instead (full-vocabulary argmax, EOS stop, up to 256 tokens)."""
+        if reference_generate:
+            P = model_inputs["input_ids"].shape[1]
+            return self.generate(model_inputs, max_new_tokens=256 if max_new_tokens is None else int(max_new_tokens))[:, P:]
         ids, px, K, pads = self._prepare(model_inputs)
         n_new = int(max_new_tokens) if max_new_tokens is not None else 3 * self.action_chunk_size
         out = self.engine.generate_actions(ids, px, K, n_new, return_logits=return_logits, pads=pads)

@@ -284,6 +284,26 @@ class CudaOps:
         _req(px.dtype == F32 and px.is_contiguous() and tuple(px.shape[1:]) == (3, 224, 224), "zoe_patchify: px")
         L.check(self.lib.svla_zoe_patchify(_ptr(px), _ptr(a), px.shape[0], self._stream()), "svla_zoe_patchify")
 
+    def image_preprocess(self, images, tmp, out, tab_h, tab_v, lut):
+        """images uint8 [B, H, W, 3] -> out fp32 [B, 3, oh, ow]; tab_* = (bounds int32 [o, 2], kk int32 [o, ksize], ksize) or None
+        when that axis already has the output size; tmp uint8 [B, H, ow, 3] (horizontal pass result) or None."""
+        _req(images.dtype == torch.uint8 and images.is_contiguous() and images.dim() == 4 and images.shape[-1] == 3, "image_preprocess: uint8 [B,H,W,3]")
+        _req(out.dtype == F32 and out.is_contiguous() and lut.dtype == F32 and lut.numel() == 768, "image_preprocess: out / lut")
+        B, H, W, _ = images.shape
+        bh, kh, ksh = tab_h if tab_h is not None else (None, None, 0)
+        bv, kv, ksv = tab_v if tab_v is not None else (None, None, 0)
+        L.check(self.lib.svla_image_preprocess(_ptr(images), B, H, W, _ptr(tmp), _ptr(out), out.shape[2], out.shape[3], _ptr(bh), _ptr(kh),
+                                               int(ksh), _ptr(bv), _ptr(kv), int(ksv), _ptr(lut), self._stream()), "svla_image_preprocess")
+
+    def barycentric_gather(self, src, rows, weights, out):
+        """out[t] = sum_v weights[t, v] * src[rows[t, v]] (fp64 accumulate); rows int32 [T, 4] (-1 row -> NaN), weights fp64 [T, 4]."""
+        _req(src.dtype == F32 and src.is_contiguous() and out.dtype == F32 and out.is_contiguous() and src.shape[1] == out.shape[1],
+             "barycentric_gather: fp32 src / out of one width")
+        _req(rows.dtype == torch.int32 and rows.is_contiguous() and tuple(rows.shape) == (out.shape[0], 4) and
+             weights.dtype == torch.float64 and weights.is_contiguous() and tuple(weights.shape) == (out.shape[0], 4), "barycentric_gather: rows / weights")
+        L.check(self.lib.svla_barycentric_gather(_ptr(src), src.shape[0], _ptr(rows), _ptr(weights), _ptr(out), out.shape[0], out.shape[1],
+                                                 self._stream()), "svla_barycentric_gather")
+
     def beit_assemble(self, patches, cls, x, *, batch, n, c):
         L.check(self.lib.svla_beit_assemble(_ptr(patches), _ptr(cls), _ptr(x), batch, n, c, self._stream()),
                 "svla_beit_assemble")
@@ -312,6 +332,14 @@ class CudaOps:
     def zoe_attractor(self, attr, prev, out, *, batch, h, w, oh, ow, na, nbins):
         L.check(self.lib.svla_zoe_attractor(_ptr(attr), _ptr(prev), _ptr(out), batch, h, w, oh, ow, na, nbins,
                                             self._stream()), "svla_zoe_attractor")
+
+    def zoe_select_head(self, dlog, arena_ptrs, active, head_out, *, forced=-1):
+        """dlog fp32 [B, n_heads]; arena_ptrs int64 device tensor [n_heads] of device pointers to the per-head byte arenas;
+        active uint8 [bytes]; head_out int32 [1].  Device-side argmax of the batch-summed logits + copy of that head's arena."""
+        _req(dlog.dtype == F32 and dlog.dim() == 2 and dlog.is_contiguous(), "zoe_select_head: dlog fp32 [B, n_heads]")
+        _req(arena_ptrs.dtype == torch.int64 and arena_ptrs.numel() == dlog.shape[1] and active.dtype == torch.uint8, "zoe_select_head: arenas")
+        L.check(self.lib.svla_zoe_select_head(_ptr(dlog), int(dlog.shape[0]), int(dlog.shape[1]), int(forced), _ptr(arena_ptrs), _ptr(active),
+                                              int(active.numel()), _ptr(head_out), self._stream()), "svla_zoe_select_head")
 
     def softplus_f32(self, x, out):
         L.check(self.lib.svla_softplus_f32(_ptr(x), _ptr(out), x.numel(), self._stream()), "svla_softplus_f32")

@@ -161,7 +161,9 @@ class SpatialVLAProcessor:
                 idx = idx + len(IMAGE_TOKEN) if idx != -1 else 0
                 input_strings.append(ex[:idx] + self.tokenizer.bos_token + ex[idx:] + "\n")
         flat = [im for il in images for im in il]
-        pixel_values = self.image_processor(flat, return_tensors=return_tensors, **images_kwargs)["pixel_values"]
+        pixel_values = self._device_pixel_values(flat, images_kwargs)
+        if pixel_values is None:
+            pixel_values = self.image_processor(flat, return_tensors=return_tensors, **images_kwargs)["pixel_values"]
         if text_kwargs.get("max_length") is not None:          # the limit is quoted without the image tokens (:176-178)
             text_kwargs["max_length"] = text_kwargs["max_length"] + self.image_seq_length
         inputs = self._tokenize(input_strings, suffix, return_token_type_ids, return_tensors, text_kwargs)
@@ -171,6 +173,40 @@ class SpatialVLAProcessor:
         if return_token_type_ids:
             data["labels"] = inputs["input_ids"].masked_fill(inputs["token_type_ids"] == 0, -100)
         return BatchFeature(data)
+
+    # ---- device-side image path
+    def enable_device_images(self, ops=None, device="cuda:0"):
+        """Resize / rescale / (normalise) the uint8 camera frames on the GPU (csrc/image_ops.cu: Pillow's bicubic resampler bit for
+        bit) instead of in PIL on the host: `__call__` then returns `pixel_values` already resident on the device.  Frames that are
+        not uint8 HWC arrays of one common size keep the host image processor."""
+        if ops is None:
+            from .ops import CudaOps
+            ops = CudaOps(device)
+        self._image_ops, self._device_processors = ops, {}
+        return self
+
+    def _device_pixel_values(self, flat, images_kwargs):
+        ops = getattr(self, "_image_ops", None)
+        if ops is None or not flat:
+            return None
+        arrs = []
+        for im in flat:
+            a = im if isinstance(im, torch.Tensor) else np.asarray(im)
+            if a.dtype not in (np.uint8, torch.uint8) or a.ndim != 3 or a.shape[-1] != 3 or tuple(a.shape) != tuple(flat[0].shape if hasattr(flat[0], "shape") else np.asarray(flat[0]).shape):
+                return None
+            arrs.append(a)
+        ip = self.image_processor
+        opt = lambda k, d: images_kwargs.get(k, getattr(ip, k, d))      # noqa: E731
+        if not opt("do_resize", True) or images_kwargs.get("size") is not None or images_kwargs.get("resample") is not None:
+            return None
+        key = (bool(opt("do_rescale", True)), float(opt("rescale_factor", 1 / 255)), bool(opt("do_normalize", False)),
+               tuple(opt("image_mean", (0.5, 0.5, 0.5)) or (0.5, 0.5, 0.5)), tuple(opt("image_std", (0.5, 0.5, 0.5)) or (0.5, 0.5, 0.5)))
+        if key not in self._device_processors:
+            from .image_processing import DeviceImageProcessor
+            self._device_processors[key] = DeviceImageProcessor(ops, (ip.size["height"], ip.size["width"]), rescale_factor=key[1],
+                                                               do_rescale=key[0], do_normalize=key[2], mean=key[3], std=key[4])
+        batch = torch.stack(arrs) if isinstance(arrs[0], torch.Tensor) else np.stack(arrs)
+        return self._device_processors[key](batch)
 
     def _tokenize(self, input_strings, suffix, return_token_type_ids, return_tensors, kwargs):
         key = None

@@ -89,6 +89,48 @@ def test_public_api_predict_and_decode_actions(tiny_gpu, cuda_device):
         assert np.array_equal(dd["actions"].cpu().numpy(), hb["actions"]) and np.array_equal(dd["action_ids"].cpu().numpy(), hb["action_ids"])
 
 
+def test_single_graph_step_with_device_side_router_vote(tiny_gpu, cuda_device):
+    """The whole predict_action step replays from ONE CUDA graph: the ZoeDepth router vote (HF reads it back with `.item()`) is
+    taken on the device by svla_zoe_select_head.  Forcing either head through the same kernel reproduces the eager result of that
+    head, and the free vote equals the golden's argmax of the batch-summed domain logits."""
+    from spatialvla_b200.engine import SpatialVLAEngine
+    from spatialvla_b200.ops import CudaOps
+    cfg, px, ids, K, sd, _ = tiny_gpu
+    eng = SpatialVLAEngine(cfg, sd, CudaOps(cuda_device))
+    g = np.load(os.path.join(GOLD, "tiny_model.npz"))
+    d = dict(ids=ids.to(cuda_device), px=px.to(cuda_device), K=K.to(cuda_device))
+    toks = eng.generate_actions(d["ids"], d["px"], d["K"], 6)
+    toks2 = eng.generate_actions(d["ids"], d["px"], d["K"], 6)
+    assert len(eng._graphs) == 1 and not next(iter(eng._graphs.values()))["B"], "the step must be one graph"
+    assert eng.last_router_head == int(np.argmax(g["domain_logits"].sum(0)))
+    assert np.array_equal(toks.cpu().numpy(), g["tokens"]) and torch.equal(toks, toks2)
+    depth = {}
+    for head in (0, 1):
+        eng.force_head = head
+        depth[head] = eng.zoedepth(d["px"]).clone()
+        assert eng.last_router_head == head
+        ref = R.zoedepth_forward(sd, cfg, R.process_zoe(px), force_head=head)
+        assert (depth[head].cpu() - ref).abs().max() < 5e-3, head
+    eng.force_head = None
+    assert (depth[0] - depth[1]).abs().max() > 1e-3          # the two metric heads really differ
+
+
+def test_reference_generate_semantics_on_gpu(tiny_gpu, cuda_device):
+    """predict_action(reference_generate=True): full-vocabulary argmax + EOS stop (model/modeling_spatialvla.py:484-492) vs the
+    oracle's restatement of HF's greedy loop."""
+    from spatialvla_b200 import SpatialVLAForConditionalGeneration
+    cfg, px, ids, K, sd, eng = tiny_gpu
+    m = SpatialVLAForConditionalGeneration(cfg, sd, device=cuda_device)
+    inp = {"input_ids": ids, "pixel_values": px, "intrinsic": K}
+    free = m.generate(inp, max_new_tokens=5, eos_token_id=-7, pad_token_id=0)[:, ids.shape[1]:]
+    want = R.generate_ref(sd, cfg, ids, px, K, 5, eos_id=-7, pad_id=0, force_head=m.engine.last_router_head)
+    assert float((free.cpu() == want).float().mean()) >= 0.8, (free.tolist(), want.tolist())
+    eos = int(free[0, 1])
+    got = m.generate(inp, max_new_tokens=5, eos_token_id=eos, pad_token_id=0)[:, ids.shape[1]:].cpu()
+    assert int(got[0, 1]) == eos and bool((got[0, 2:] == 0).all())          # finished row is padded
+    assert torch.equal(got[:, :2], free[:, :2].cpu())
+
+
 def test_left_padded_batch_vs_reference_golden(tiny_gpu, cuda_device):
     """LEFT-padded prompts through predict_action on the GPU (eager and CUDA-graph paths) against the golden vectors the live
     reference produced for the same padded batch, plus the size-independent property that a padded row decodes like the same

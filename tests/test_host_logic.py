@@ -191,6 +191,27 @@ def test_tied_lm_head_checkpoint_loads_and_follows_the_spatial_overwrite(tmp_pat
     assert eng.gem["head_act"].shape == (n, cfg["text_config"]["hidden_size"])
 
 
+def test_reference_generate_semantics_full_vocab_argmax_and_eos_stop(tiny):
+    """predict_action(reference_generate=True) = the reference's own decoding rule (model/modeling_spatialvla.py:484-492):
+    full-vocabulary argmax, EOS stop with padded finished rows, max_new_tokens bound; against the oracle's restatement of HF's
+    greedy loop.  With random weights no EOS appears by itself, so the EOS id is set to a token the rows really emit."""
+    from spatialvla_b200.modeling_spatialvla import SpatialVLAForConditionalGeneration
+    cfg, px, ids, K, sd, eng = tiny
+    m = SpatialVLAForConditionalGeneration(cfg, sd, ops=RefOps())
+    free = R.generate_ref(sd, cfg, ids, px, K, 5, eos_id=-7, pad_id=0, force_head=None)
+    got = m.generate({"input_ids": ids, "pixel_values": px, "intrinsic": K}, max_new_tokens=5, eos_token_id=-7, pad_token_id=0)
+    assert got.shape == (2, ids.shape[1] + 5) and torch.equal(got[:, :ids.shape[1]], ids) and torch.equal(got[:, ids.shape[1]:], free)
+    eos = int(free[0, 1])                                    # row 0 stops after its 2nd token
+    want = R.generate_ref(sd, cfg, ids, px, K, 5, eos_id=eos, pad_id=0)
+    new = m.predict_action({"input_ids": ids, "pixel_values": px, "intrinsic": K}, max_new_tokens=5, reference_generate=True) \
+        if cfg.get("eos_token_id") == eos else m.generate({"input_ids": ids, "pixel_values": px, "intrinsic": K}, max_new_tokens=5,
+                                                          eos_token_id=eos, pad_token_id=0)[:, ids.shape[1]:]
+    assert torch.equal(new, want)
+    assert int(want[0, 1]) == eos and (want.shape[1] == 2 or bool((want[0, 2:] == 0).all()))
+    with pytest.raises(NotImplementedError):
+        m.generate({"input_ids": ids, "pixel_values": px, "intrinsic": K}, do_sample=True)
+
+
 def test_labelled_forward_host_logic_matches_oracle_and_golden(tiny):
     """forward(labels=...) orchestration (mask selection, label shift / ignore / pad masking, row gather, chunked lm_head +
     cross entropy) through the torch op re-statements, against the fp32 oracle and the live-reference golden losses."""

@@ -172,6 +172,40 @@ def test_spatial_embedding_adaption_matches_reference_golden():
     assert np.array_equal(emb2.weight.data.numpy(), g["before"]) and np.array_equal(tk2._edges, tk._edges)
 
 
+def _adaption_with_ops(ops):
+    import os
+    from oracle.gen_golden import ADAPT_BINS, ADAPT_GS0, ADAPT_GS1
+    from spatialvla_b200 import SpatialActionTokenizer
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "embedding_adaption.npz"))
+    tk = SpatialActionTokenizer(FakeTokenizer(1000), ADAPT_BINS, gs_params=ADAPT_GS0, min_sigma=0.1)
+    emb = torch.nn.Embedding(g["before"].shape[0], g["before"].shape[1])
+    emb.weight.data.copy_(torch.from_numpy(g["before"]))
+    tk.spatial_embedding_adaption(ADAPT_GS1, emb, min_sigma=0.2, adpt_feature=True, ops=ops)
+    a, b = emb.weight.data.numpy(), g["after"]
+    return a, b
+
+
+def test_spatial_embedding_adaption_plan_and_gather_match_reference_golden():
+    """The device formulation (host: Qhull triangulation + point location = `adaption_plan`; device: 4-row barycentric gather)
+    run through the torch op re-statement against the golden the LIVE reference produced with scipy griddata: same NaN pattern,
+    values to 1e-6 (the reference's interpolation is Delaunay-linear, which the plan reproduces, not trilinear)."""
+    from oracle.ops_ref import RefOps
+    a, b = _adaption_with_ops(RefOps())
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.isnan(b).sum() < b.size
+    assert np.allclose(np.nan_to_num(a), np.nan_to_num(b), atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_spatial_embedding_adaption_on_gpu_matches_reference_golden(cuda_device):
+    from spatialvla_b200.ops import CudaOps
+    ops = CudaOps(cuda_device)
+    n0 = ops.launch_count()
+    a, b = _adaption_with_ops(ops)
+    assert ops.launch_count() - n0 == 2                    # one gather per block (translation, rotation)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.allclose(np.nan_to_num(a), np.nan_to_num(b), atol=1e-6)
+
+
 def test_prompt_id_cache_per_instruction():
     """Serving loop: the same instruction every control step -> the tokenizer runs once per distinct prompt (SURVEY §8f rank 2);
     results are identical and independent copies; training samples (suffix) bypass the cache."""

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SVLA_ABI_VERSION 1
+#define SVLA_ABI_VERSION 2
 
 const char* svla_last_error(void);
 int svla_abi_version(void);
@@ -70,6 +70,12 @@ typedef struct SvlaGemmArgs {
   int32_t block_n;        /* 0 = auto; else 32 | 64 | 128 | 256 */
   int32_t impl;           /* 0 = tcgen05, kernel variant chosen by shape (product path); 1 = SIMT debugging kernel (tests only);
                              2 / 3 = force the 1-CTA / 2-CTA (cta_group::2) kernel; 4 = force the row-tile 3x3 conv kernel (n <= 128) */
+  /* K extension (NULL = none): acc = A W^T + A2 W2^T in ONE accumulator -- the un-merged LoRA Linear y = x W^T + (s x A^T) B^T
+   * (train/spatialvla_finetune.py:262-302, peft) and its input gradient dx = dy W + (s dy B) A cost k2 / 64 extra k-blocks of the
+   * base GEMM.  a2 bf16 [M, lda2], w2 bf16 [N, ldw2], k2 columns each (zero columns are free: TMA zero-fills every tail). */
+  const void* a2;
+  const void* w2;
+  int64_t k2, lda2, ldw2;
 } SvlaGemmArgs;
 
 int svla_gemm(const SvlaGemmArgs* args, void* stream);
@@ -219,10 +225,80 @@ int svla_cross_entropy_bwd(const float* logits, int64_t rows, int64_t cols, int6
  * p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps).  step counts from 1.  Buffers 16-byte aligned.
  * Hyper-parameters are doubles: the derived scalars (1 - beta2, lr / (1 - beta1^step), ...) are formed in double on the host, as
  * torch forms them from Python floats, and only then rounded to fp32.
- * STATUS: written at the end of round 1; its GPU parity case (tests/kernel_cases.py::adamw_case) has NOT passed on hardware yet
- * (first attempt failed on the fp32 1 - beta2 rounding fixed here, then the GPU budget ran out), so nothing calls it. */
+ */
 int svla_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
-                    double beta2, double eps, double weight_decay, int64_t step, double grad_scale, void* stream);
+                    double beta2, double eps, double weight_decay, int64_t step, double grad_scale, const float* grad_sumsq_dev,
+                    double max_grad_norm, void* stream);
+/* grad_sumsq_dev (NULL = no clipping): DEVICE scalar holding sum(grad^2) of the un-scaled buffer (svla_sumsq): the gradient is also
+ * multiplied by min(1, max_grad_norm / (grad_scale * sqrt(sumsq) + 1e-6)) -- torch.nn.utils.clip_grad_norm_ as HF Trainer applies it
+ * (max_grad_norm 1.0) -- without a host read of the norm.   *out += sum(x^2). */
+int svla_sumsq(const float* x, int64_t n, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Fine-tune step (BASELINE.json config #5): training-mode forward pieces and the backward kernels.
+ * The reference trains through torch autograd (train/spatialvla_finetune.py:262-302 PEFT LoRA r = 32 on every Linear of Gemma2,
+ * SigLIP, projector and Ego3D head; HF Trainer / train/monkey_patch.py:222-326); base weights and norm weights are frozen, so
+ * only activation gradients and the rank-r adapter gradients are formed.  Closed forms: oracle/backward_ref.py.
+ * --------------------------------------------------------------------------------------------------- */
+/* Gemma2 sandwich norm, out of place (model/modeling_gemma2.py:60-77,475-496): x_out = x_in + rms(branch) (1 + w_post) [branch,
+ * w_post, x_out all NULL: skipped]; h_bf16 = rms(x) (1 + w_pre) of the updated row [w_pre, h_bf16 NULL: skipped]. */
+int svla_rmsnorm_train_fwd(const float* x_in, const float* branch, const float* w_post, const float* w_pre, float eps, int64_t rows,
+                           int cols, float* x_out, void* h_bf16, void* stream);
+/* RMSNorm backward: dx = r (g - x r^2 mean(g x)), g = dy (1 + w).  dy bf16 [rows, cols] or fp32 (dy_is_f32); row_idx (NULL = identity):
+ * dy row i belongs to row row_idx[i] of x / dx.  dx_accum[row] += dx (fp32, may be NULL), dx_bf16[row] = dx (may be NULL). */
+int svla_rmsnorm_bwd(const float* x, const float* w, const void* dy, int dy_is_f32, const int64_t* row_idx, float eps, int64_t rows,
+                     int cols, float* dx_accum, void* dx_bf16, void* stream);
+/* LayerNorm backward (HF siglip :330-362; model/modeling_spatialvla.py:59-64 with relu = 1: the ReLU mask is recomputed from x):
+ * dx_accum += dx (NULL = skip), copy_bf16 = bf16(updated dx_accum) (NULL = skip), dx_bf16 = dx (NULL = skip). dy bf16. */
+int svla_layernorm_bwd(const float* x, const float* gamma, const float* beta, const void* dy_bf16, float eps, int64_t rows, int cols,
+                       int relu, float* dx_accum, void* copy_bf16, void* dx_bf16, void* stream);
+/* GeGLU (model/modeling_gemma2.py:80-92) on the un-fused gate/up GEMM output gu bf16 [rows, 2 inter] (col 2j = gate_j, 2j + 1 = up_j):
+ * act[rows, inter] = gelu_tanh(gate) up;  backward dgu = (dact up gelu'(gate), dact gelu(gate)) interleaved. */
+int svla_geglu_fwd(const void* gu, void* act, int64_t rows, int64_t inter, void* stream);
+int svla_geglu_bwd(const void* gu, const void* dact, void* dgu, int64_t rows, int64_t inter, void* stream);
+/* gelu_pytorch_tanh and its derivative on bf16 (SigLIP MLP, HF siglip :316-327): f = gelu(z); dz = df gelu'(z). n % 8 == 0 */
+int svla_gelu_tanh_fwd(const void* z, void* f, int64_t n, void* stream);
+int svla_gelu_tanh_bwd(const void* z, const void* df, void* dz, int64_t n, void* stream);
+/* RoPE backward (model/modeling_gemma2.py:140-154): inverse rotation, in place, of the q and k column blocks of the gradient of the
+ * rotated qkv tensor bf16 [batch * s, (hq + 2 hkv) d]; the v block is untouched; position of row t is t % s + 1. */
+int svla_rope_bwd(void* dqkv, int batch, int s, int hq, int hkv, int d, float theta, void* stream);
+/* out_bf16[i, :] = scale * src[row_idx ? row_idx[i] : i, :]  (fp32 rows -> bf16 GEMM operand; gathers the image-token rows of the
+ * embedding gradient, model/modeling_spatialvla.py:361-387 backwards) */
+int svla_rows_cast(const float* src, const int64_t* row_idx, float scale, int64_t rows, int cols, void* out_bf16, void* stream);
+/* LoRA operand packing: one launch turns the fp32 master copy of every adapter (flat arena) into the bf16 operand layouts of the
+ * GEMMs.  descs_dev: device array of n_desc records { int64 src_off, dst_off, stride_i, stride_j; int32 rows, cols, tile0, pad }:
+ * pool[dst_off + i stride_i + j stride_j] = bf16(arena[src_off + i cols + j]); tile0 = running count of 32x32 tiles (ascending). */
+int svla_lora_pack(const float* arena, void* pool_bf16, const void* descs_dev, int n_desc, int total_tiles, void* stream);
+int svla_fill_zero(void* ptr, int64_t bytes, void* stream);   /* cudaMemsetAsync */
+
+/* Backward of G2 (flash formulation; see csrc/train_mma.cu).  q/k/v/out as in SvlaAttnArgs (out = the forward result), dout = dL/dout;
+ * dq/dk/dv bf16 with their own strides (they may be column blocks of one [tokens, (hq + 2 hkv) d] tensor); lse / delta: fp32
+ * [batch, hq, sq] scratch written by the first launch.  Masks: causal / causal_prefix as in SvlaAttnArgs (no kv_start, no relpos). */
+typedef struct SvlaAttnBwdArgs {
+  const void* q; const void* k; const void* v; const void* out; const void* dout;
+  void* dq; void* dk; void* dv;
+  int64_t q_bs, q_ss, k_bs, k_ss, v_bs, v_ss, o_bs, o_ss, do_bs, do_ss, dq_bs, dq_ss, dk_bs, dk_ss, dv_bs, dv_ss;
+  float* lse; float* delta;
+  int32_t batch, hq, hkv, sq, sk, d;
+  float scale, softcap;
+  int32_t causal, causal_prefix;
+} SvlaAttnBwdArgs;
+int svla_attention_bwd(const SvlaAttnBwdArgs* args, void* stream);
+
+/* Rank-r gradient reduction over the token dimension: for every group g, dst_g[r - row0, j] += scale * sum_m S[m, r] Y[m, col_start +
+ * j col_stride] for r in [row0, row0 + rows), j in [0, ncols)  (fp32 reductions, dst must be zero-initialised or hold a running sum).
+ * gA = (s dY B)^T X and gB^T = (s X A^T)^T dY of a LoRA Linear (oracle/backward_ref.lora_linear_bwd); groups address the adapters of a
+ * fused q|k|v or interleaved gate/up projection inside the gradient arena.  S bf16 [m, lds] (r <= 128 columns used), Y bf16 [m, ldy]. */
+typedef struct SvlaTnGroup { float* dst; int64_t ld; int32_t row0, rows, col_start, col_stride, ncols, pad; } SvlaTnGroup;
+typedef struct SvlaGemmTnArgs {
+  const void* s; const void* y;
+  int64_t m, lds, ldy;
+  int32_t r, n;
+  float scale;
+  int32_t n_groups;
+  SvlaTnGroup groups[4];
+} SvlaGemmTnArgs;
+int svla_gemm_tn(const SvlaGemmTnArgs* args, void* stream);
 
 /* M9 image preprocessing.
  * siglip: (x-0.5)/0.5 + im2col for the 14x14/14 patch conv (model/modeling_spatialvla.py:309;

@@ -54,7 +54,7 @@ class RefOps:
     # ---- G1
     def gemm(self, a, w, *, n=None, k=None, out_bf16=None, out_f32=None, out_relu=None, bias=None, colscale=None,
              res_bf16=None, res2_bf16=None, res_f32=None, res_mod=0, act=ACT_NONE, act_param=0.0, alpha=1.0,
-             geglu=False, accumulate=False, conv=None, block_n=0, impl=None):
+             geglu=False, accumulate=False, conv=None, block_n=0, impl=None, a2=None, w2=None):
         self.launches += 1
         N = int(n if n is not None else w.shape[0])
         wf = w[:N].float()
@@ -67,6 +67,8 @@ class RefOps:
         else:
             K = int(k if k is not None else a.shape[1])
             acc = a[:, :K].float() @ wf[:, :K].t()
+            if a2 is not None:                       # K extension: second operand pair accumulated into the same tile
+                acc = acc + a2.float() @ w2[:N].float().t()
         v = acc * alpha
         if bias is not None:
             v = v + bias[:N]
@@ -96,6 +98,123 @@ class RefOps:
             _rows(out_bf16)[:, :N] = v.to(BF16)
         if out_relu is not None:
             _rows(out_relu)[:, :N] = F.relu(v).to(BF16)
+
+    # ---- fine-tune step: training forward pieces and backward kernels (closed forms = oracle/backward_ref.py)
+    def rmsnorm_train_fwd(self, x_in, *, branch=None, w_post=None, w_pre=None, eps=1e-6, x_out=None, h=None):
+        self.launches += 1
+        x = x_in
+        if branch is not None:
+            r = torch.rsqrt(branch.pow(2).mean(-1, keepdim=True) + eps)
+            x_out.copy_(x_in + branch * r * (1.0 + w_post))
+            x = x_out
+        if w_pre is not None:
+            r = torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps)
+            h.copy_((x * r * (1.0 + w_pre)).to(BF16))
+
+    def rmsnorm_bwd(self, x, w, dy, *, eps=1e-6, row_idx=None, dx_accum=None, dx_bf16=None):
+        from .backward_ref import rmsnorm_bwd
+        self.launches += 1
+        xr = x if row_idx is None else x[row_idx]
+        dx, _ = rmsnorm_bwd(xr, w, dy.float(), eps)
+        if dx_accum is not None:
+            if row_idx is None:
+                dx_accum += dx
+            else:
+                dx_accum.index_add_(0, row_idx, dx)
+        if dx_bf16 is not None:
+            if row_idx is None:
+                dx_bf16.copy_(dx.to(BF16))
+            else:
+                dx_bf16[row_idx] = dx.to(BF16)
+
+    def layernorm_bwd(self, x, gamma, beta, dy, *, eps, relu=False, dx_accum=None, copy_bf16=None, dx_bf16=None):
+        self.launches += 1
+        mu = x.mean(-1, keepdim=True)
+        rstd = torch.rsqrt((x - mu).pow(2).mean(-1, keepdim=True) + eps)
+        xh = (x - mu) * rstd
+        g = dy.float() * gamma
+        if relu:
+            g = torch.where(xh * gamma + beta > 0, g, torch.zeros_like(g))
+        dx = rstd * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+        if dx_bf16 is not None:
+            dx_bf16.copy_(dx.to(BF16))
+        if dx_accum is not None:
+            dx_accum += dx
+            if copy_bf16 is not None:
+                copy_bf16.copy_(dx_accum.to(BF16))
+
+    def geglu_fwd(self, gu, act):
+        self.launches += 1
+        g, u = gu[:, 0::2].float(), gu[:, 1::2].float()
+        act.copy_((F.gelu(g, approximate="tanh") * u).to(BF16))
+
+    def geglu_bwd(self, gu, dact, dgu):
+        from .backward_ref import geglu_bwd
+        self.launches += 1
+        dg, du = geglu_bwd(gu[:, 0::2], gu[:, 1::2], dact)
+        dgu[:, 0::2] = dg.to(BF16)
+        dgu[:, 1::2] = du.to(BF16)
+
+    def gelu_tanh_fwd(self, z, f):
+        self.launches += 1
+        f.copy_(F.gelu(z.float(), approximate="tanh").to(BF16))
+
+    def gelu_tanh_bwd(self, z, df, dz):
+        from .backward_ref import gelu_tanh_grad
+        self.launches += 1
+        dz.copy_((df.float() * gelu_tanh_grad(z.float())).to(BF16))
+
+    def rope_bwd(self, dqkv, *, batch, s, hq, hkv, d, theta):
+        from .backward_ref import rope_bwd
+        self.launches += 1
+        t = dqkv.float().view(batch, s, hq + 2 * hkv, d)
+        pos = torch.arange(1, s + 1)
+        qk = t[:, :, : hq + hkv].permute(0, 2, 1, 3)                          # [B, heads, S, d]
+        t[:, :, : hq + hkv] = rope_bwd(qk, pos, theta).permute(0, 2, 1, 3)
+        dqkv.copy_(t.reshape(dqkv.shape).to(BF16))
+
+    def rows_cast(self, src, out, *, row_idx=None, scale=1.0):
+        self.launches += 1
+        out.copy_(((src if row_idx is None else src[row_idx]) * scale).to(BF16))
+
+    def lora_pack(self, arena, pool, plan):
+        """plan.records: list of (src_off, dst_off, stride_i, stride_j, rows, cols)"""
+        self.launches += 1
+        flat = pool.view(-1)
+        for (so, do, si, sj, rows, cols) in plan.records:
+            src = arena[so:so + rows * cols].view(rows, cols)
+            idx = (do + torch.arange(rows)[:, None] * si + torch.arange(cols)[None, :] * sj).reshape(-1)
+            flat[idx] = src.reshape(-1).to(BF16)
+
+    def fill_zero(self, t):
+        t.zero_()
+
+    def attention_bwd(self, q, k, v, out, dout, dq, dk, dv, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
+                      do_strides, dq_strides, dk_strides, dv_strides, scale, softcap=0.0, causal=False, causal_prefix=0):
+        from .backward_ref import softcap_attention_bwd
+        self.launches += 3
+        Q = self._strided(q, q_strides[0], q_strides[1], batch, sq, hq, d).float().permute(0, 2, 1, 3)
+        K = self._strided(k, k_strides[0], k_strides[1], batch, sk, hkv, d).float().permute(0, 2, 1, 3)
+        V = self._strided(v, v_strides[0], v_strides[1], batch, sk, hkv, d).float().permute(0, 2, 1, 3)
+        dO = self._strided(dout, do_strides[0], do_strides[1], batch, sq, hq, d).float().permute(0, 2, 1, 3)
+        G = hq // hkv
+        Kr, Vr = K.repeat_interleave(G, 1), V.repeat_interleave(G, 1)
+        mask = None
+        if causal:
+            mask = torch.arange(sk)[None, :] > torch.clamp(torch.arange(sq)[:, None] + (sk - sq), min=causal_prefix - 1)
+        gq, gk, gv = softcap_attention_bwd(Q, Kr, Vr, dO, scale, softcap, mask)
+        gk = gk.view(batch, hkv, G, sk, d).sum(2)
+        gv = gv.view(batch, hkv, G, sk, d).sum(2)
+        self._strided(dq, dq_strides[0], dq_strides[1], batch, sq, hq, d).copy_(gq.permute(0, 2, 1, 3).to(BF16))
+        self._strided(dk, dk_strides[0], dk_strides[1], batch, sk, hkv, d).copy_(gk.permute(0, 2, 1, 3).to(BF16))
+        self._strided(dv, dv_strides[0], dv_strides[1], batch, sk, hkv, d).copy_(gv.permute(0, 2, 1, 3).to(BF16))
+
+    def gemm_tn(self, s, y, groups, *, r, n, scale=1.0):
+        """groups: list of (dst fp32 [rows, >= ncols] view, row0, rows, col_start, col_stride, ncols); dst += scale * S[:, rows]^T Y[:, cols]"""
+        self.launches += 1
+        full = (s[:, :r].float().t() @ y[:, :n].float()) * scale
+        for (dst, row0, rows, c0, cs, nc) in groups:
+            dst[:, :nc] += full[row0:row0 + rows, c0:c0 + (nc - 1) * cs + 1:cs]
 
     # ---- G1s
     def skinny_splits(self, n, k):
@@ -280,9 +399,18 @@ class RefOps:
         dz.zero_()
         dz[:, :c] = g.to(BF16)
 
-    def adamw_step(self, param, grad, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step, grad_scale=1.0):
-        """torch.optim.AdamW single-tensor arithmetic (torch/optim/adamw.py: _single_tensor_adamw), in place."""
+    def sumsq(self, x, out):
         self.launches += 1
+        out += (x.double() ** 2).sum().float()
+
+    def adamw_step(self, param, grad, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step, grad_scale=1.0,
+                   sumsq=None, max_grad_norm=0.0):
+        """torch.optim.AdamW single-tensor arithmetic (torch/optim/adamw.py: _single_tensor_adamw), in place, preceded by
+        torch.nn.utils.clip_grad_norm_ on the scaled gradient when `sumsq` (sum of squares of the un-scaled gradient) is given."""
+        self.launches += 1
+        if sumsq is not None:
+            total = float(sumsq.sqrt()) * grad_scale
+            grad_scale = grad_scale * min(1.0, max_grad_norm / (total + 1e-6))
         g = grad * grad_scale
         param.mul_(1 - lr * weight_decay)
         exp_avg.lerp_(g, 1 - beta1)

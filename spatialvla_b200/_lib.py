@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "lib", "libspatialvla_b200.so")
 SOURCES = ["capi.cu", "gemm_tcgen05.cu", "gemm_skinny.cu", "attention.cu", "attention_tc.cu", "decode_small.cu", "fused_ops.cu",
-           "tokenizer.cu", "image_ops.cu"]
+           "tokenizer.cu", "image_ops.cu", "train_ops.cu", "train_mma.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -31,6 +31,7 @@ class SvlaGemmArgs(C.Structure):
         ("nb", C.c_int32), ("h", C.c_int32), ("wd", C.c_int32), ("c", C.c_int32),
         ("alpha", C.c_float), ("act_param", C.c_float), ("act", C.c_int32), ("flags", C.c_int32),
         ("block_n", C.c_int32), ("impl", C.c_int32),
+        ("a2", C.c_void_p), ("w2", C.c_void_p), ("k2", C.c_int64), ("lda2", C.c_int64), ("ldw2", C.c_int64),
     ]
 
 
@@ -55,6 +56,29 @@ class SvlaAttnArgs(C.Structure):
     ]
 
 
+class SvlaAttnBwdArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p), ("dout", C.c_void_p),
+        ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("q_bs", C.c_int64), ("q_ss", C.c_int64), ("k_bs", C.c_int64), ("k_ss", C.c_int64), ("v_bs", C.c_int64), ("v_ss", C.c_int64),
+        ("o_bs", C.c_int64), ("o_ss", C.c_int64), ("do_bs", C.c_int64), ("do_ss", C.c_int64), ("dq_bs", C.c_int64), ("dq_ss", C.c_int64),
+        ("dk_bs", C.c_int64), ("dk_ss", C.c_int64), ("dv_bs", C.c_int64), ("dv_ss", C.c_int64),
+        ("lse", C.c_void_p), ("delta", C.c_void_p),
+        ("batch", C.c_int32), ("hq", C.c_int32), ("hkv", C.c_int32), ("sq", C.c_int32), ("sk", C.c_int32), ("d", C.c_int32),
+        ("scale", C.c_float), ("softcap", C.c_float), ("causal", C.c_int32), ("causal_prefix", C.c_int32),
+    ]
+
+
+class SvlaTnGroup(C.Structure):
+    _fields_ = [("dst", C.c_void_p), ("ld", C.c_int64), ("row0", C.c_int32), ("rows", C.c_int32), ("col_start", C.c_int32),
+                ("col_stride", C.c_int32), ("ncols", C.c_int32), ("pad", C.c_int32)]
+
+
+class SvlaGemmTnArgs(C.Structure):
+    _fields_ = [("s", C.c_void_p), ("y", C.c_void_p), ("m", C.c_int64), ("lds", C.c_int64), ("ldy", C.c_int64),
+                ("r", C.c_int32), ("n", C.c_int32), ("scale", C.c_float), ("n_groups", C.c_int32), ("groups", SvlaTnGroup * 4)]
+
+
 _P, _I, _L, _F, _D = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 
 # name -> (restype, argtypes): every symbol include/spatialvla_b200.h declares
@@ -76,8 +100,22 @@ SIGNATURES = {
     "svla_embed_tokens": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _L, _I, _F, _P, _P]),
     "svla_argmax_rows": (_I, [_P, _L, _L, _L, _L, _P, _L, _P]),
     "svla_cross_entropy_rows": (_I, [_P, _L, _L, _L, _P, _L, _P, _P, _L, _P, _P]),
-    "svla_adamw_step": (_I, [_P, _P, _P, _P, _L, _D, _D, _D, _D, _D, _L, _D, _P]),
+    "svla_adamw_step": (_I, [_P, _P, _P, _P, _L, _D, _D, _D, _D, _D, _L, _D, _P, _D, _P]),
+    "svla_sumsq": (_I, [_P, _L, _P, _P]),
     "svla_cross_entropy_bwd": (_I, [_P, _L, _L, _L, _P, _L, _P, _L, _P, _F, _P, _L, _P]),
+    "svla_rmsnorm_train_fwd": (_I, [_P, _P, _P, _P, _F, _L, _I, _P, _P, _P]),
+    "svla_rmsnorm_bwd": (_I, [_P, _P, _P, _I, _P, _F, _L, _I, _P, _P, _P]),
+    "svla_layernorm_bwd": (_I, [_P, _P, _P, _P, _F, _L, _I, _I, _P, _P, _P, _P]),
+    "svla_geglu_fwd": (_I, [_P, _P, _L, _L, _P]),
+    "svla_geglu_bwd": (_I, [_P, _P, _P, _L, _L, _P]),
+    "svla_gelu_tanh_fwd": (_I, [_P, _P, _L, _P]),
+    "svla_gelu_tanh_bwd": (_I, [_P, _P, _P, _L, _P]),
+    "svla_rope_bwd": (_I, [_P, _I, _I, _I, _I, _I, _F, _P]),
+    "svla_rows_cast": (_I, [_P, _P, _F, _L, _I, _P, _P]),
+    "svla_lora_pack": (_I, [_P, _P, _P, _I, _I, _P]),
+    "svla_fill_zero": (_I, [_P, _L, _P]),
+    "svla_attention_bwd": (_I, [C.POINTER(SvlaAttnBwdArgs), _P]),
+    "svla_gemm_tn": (_I, [C.POINTER(SvlaGemmTnArgs), _P]),
     "svla_siglip_patchify": (_I, [_P, _P, _I, _I, _P]),
     "svla_zoe_patchify": (_I, [_P, _P, _I, _P]),
     "svla_image_preprocess": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P]),
@@ -158,7 +196,7 @@ def load_library():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.svla_abi_version() != 1:
+    if lib.svla_abi_version() != 2:
         raise SvlaError("libspatialvla_b200.so ABI version mismatch")
     _lib = lib
     return lib

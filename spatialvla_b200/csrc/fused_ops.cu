@@ -624,9 +624,15 @@ svla_cross_entropy_summary_kernel(const float* __restrict__ row_loss, const long
 // p -= (lr / (1 - b1^t)) * m / denom).  One pass over the flat buffers, 128-bit accesses: 16 B read + 12 B written per element.
 __global__ void __launch_bounds__(256)
 svla_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
-                  float decay, float omb1, float b2, float omb2, float eps, float step_size, float bc2_sqrt, float grad_scale) {
+                  float decay, float omb1, float b2, float omb2, float eps, float step_size, float bc2_sqrt, float grad_scale,
+                  const float* __restrict__ grad_sumsq, float max_norm) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long nvec = n >> 2;
+  if (grad_sumsq) {
+    // torch.nn.utils.clip_grad_norm_ on the scaled (rank-averaged) gradient: coef = min(1, max_norm / (||g|| + 1e-6)), on the device
+    const float total = sqrtf(*grad_sumsq) * grad_scale;
+    grad_scale *= fminf(1.f, max_norm / (total + 1e-6f));
+  }
   // every scalar (decay = 1 - lr wd, omb1 = 1 - beta1, omb2 = 1 - beta2, step_size = lr / (1 - beta1^t), bc2_sqrt) is formed in
   // DOUBLE on the host like torch does with its Python floats: 1.f - 0.999f alone is off by 1.3e-5 of (1 - beta2)
   auto upd = [&](float& pp, float gg, float& mm, float& vv) {
@@ -650,6 +656,22 @@ svla_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
   }
   for (long long i = (nvec << 2) + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride)
     upd(p[i], g[i], m[i], v[i]);
+}
+
+// sum of squares of a flat fp32 buffer -> *out += (fp32 atomics over per-block partial sums in double)
+__global__ void __launch_bounds__(256)
+svla_sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float sh[33];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long nvec = n >> 2;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (long long i = (nvec << 2) + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) acc += x[i] * x[i];
+  const float t = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(out, t);
 }
 
 // ------------------------------------------------------------------------------------------ bicubic helpers (A = -0.75)
@@ -1553,8 +1575,19 @@ extern "C" int svla_cross_entropy_bwd(const float* logits, int64_t rows, int64_t
   return 0;
 }
 
+extern "C" int svla_sumsq(const float* x, int64_t n, float* out, void* stream) {
+  SVLA_REQUIRE(x && out && n > 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "svla_sumsq: bad arguments");
+  const long long blocks = (n / 4 + 255) / 256;
+  const long long cap = static_cast<long long>(svla_num_sms()) * 4;
+  svla_sumsq_kernel<<<static_cast<unsigned>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<long long>(n), out);
+  SVLA_LAUNCH_CHECK("svla_sumsq");
+  return 0;
+}
+
 extern "C" int svla_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
-                               double beta2, double eps, double weight_decay, int64_t step, double grad_scale, void* stream) {
+                               double beta2, double eps, double weight_decay, int64_t step, double grad_scale,
+                               const float* grad_sumsq_dev, double max_grad_norm, void* stream) {
   SVLA_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "svla_adamw_step: bad arguments");
   SVLA_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
                  reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0, "svla_adamw_step: buffers must be 16-byte aligned");
@@ -1565,7 +1598,8 @@ extern "C" int svla_adamw_step(float* param, const float* grad, float* exp_avg, 
   svla_adamw_kernel<<<static_cast<unsigned>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       param, grad, exp_avg, exp_avg_sq, static_cast<long long>(n), static_cast<float>(1.0 - lr * weight_decay),
       static_cast<float>(1.0 - beta1), static_cast<float>(beta2), static_cast<float>(1.0 - beta2), static_cast<float>(eps),
-      static_cast<float>(lr / bc1), static_cast<float>(sqrt(bc2)), static_cast<float>(grad_scale));
+      static_cast<float>(lr / bc1), static_cast<float>(sqrt(bc2)), static_cast<float>(grad_scale), grad_sumsq_dev,
+      static_cast<float>(max_grad_norm));
   SVLA_LAUNCH_CHECK("svla_adamw_step");
   return 0;
 }

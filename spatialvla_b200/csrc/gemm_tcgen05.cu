@@ -401,8 +401,12 @@ __device__ __forceinline__ void raster_tile(long long tile, long long num_m_grou
 template <int BN, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                         const __grid_constant__ CUtensorMap tm_o, const EpiParams ep, const long long num_m_tiles, const long long num_n_tiles,
-                         const int num_k_blocks, const int conv, const int c_chunks) {
+                         const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_a2,
+                         const __grid_constant__ CUtensorMap tm_b2, const EpiParams ep, const long long num_m_tiles, const long long num_n_tiles,
+                         const int num_k_blocks, const int conv, const int c_chunks, const int kb_main) {
+  // K extension (LoRA): k-blocks [kb_main, num_k_blocks) are loaded from a SECOND operand pair A2[M, K2] / W2[N, K2], so that
+  // D = A W^T + A2 W2^T accumulates in one TMEM tile: y = x W^T + (s x A^T) B^T of an adapted Linear costs K2 / 64 extra k-blocks
+  // of the base GEMM instead of a second pass over y (train/spatialvla_finetune.py:262-302; peft lora Linear.forward).
   using C = Cfg<BN, CG>;
   constexpr int BNL = BN / CG;       // W rows staged by this CTA
   extern __shared__ uint8_t smem_raw[];
@@ -428,6 +432,7 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     if (ep.tma_out) tma_prefetch_desc(&tm_o);
+    if (kb_main < num_k_blocks) { tma_prefetch_desc(&tm_a2); tma_prefetch_desc(&tm_b2); }
 #pragma unroll 1
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -471,15 +476,17 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem_a + stage * C::kABytes;
           uint8_t* sb = smem_b + stage * C::kBBytes;
+          const bool ext = kb >= kb_main;                  // K-extension block: second operand pair
+          const int kc = (ext ? kb - kb_main : kb) * kBK;
           if constexpr (CG == 1) {
             mbar_expect_tx(&full_bar[stage], C::kStageBytes);
             if (conv) {
               const int tap = kb / c_chunks, cc = kb - tap * c_chunks;
               tma_load_4d(sa, &tm_a, &full_bar[stage], cc * kBK, w0 + (tap % 3) - 1, h0 + (tap / 3) - 1, img);
             } else {
-              tma_load_2d(sa, &tm_a, &full_bar[stage], kb * kBK, static_cast<int>(m_tile * kBM));
+              tma_load_2d(sa, ext ? &tm_a2 : &tm_a, &full_bar[stage], kc, static_cast<int>(m_tile * kBM));
             }
-            tma_load_2d(sb, &tm_b, &full_bar[stage], kb * kBK, static_cast<int>(n_tile * BN));
+            tma_load_2d(sb, ext ? &tm_b2 : &tm_b, &full_bar[stage], kc, static_cast<int>(n_tile * BN));
           } else {
             // the leader arms its barrier for the bytes of BOTH CTAs; the peer's TMA signals the leader's barrier
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
@@ -487,9 +494,9 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
               const int tap = kb / c_chunks, cc = kb - tap * c_chunks;
               tma_load_4d_cg2(sa, &tm_a, &full_bar[stage], cc * kBK, w0 + (tap % 3) - 1, h0 + (tap / 3) - 1, img);
             } else {
-              tma_load_2d_cg2(sa, &tm_a, &full_bar[stage], kb * kBK, static_cast<int>(m_tile * kBM));
+              tma_load_2d_cg2(sa, ext ? &tm_a2 : &tm_a, &full_bar[stage], kc, static_cast<int>(m_tile * kBM));
             }
-            tma_load_2d_cg2(sb, &tm_b, &full_bar[stage], kb * kBK, static_cast<int>(n_tile * BN + cta_rank * BNL));
+            tma_load_2d_cg2(sb, ext ? &tm_b2 : &tm_b, &full_bar[stage], kc, static_cast<int>(n_tile * BN + cta_rank * BNL));
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
@@ -864,8 +871,8 @@ int encode_nhwc(CUtensorMap* tm, const void* base, int nb, int h, int w, int c, 
 }
 
 template <int BN, int CG>
-int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const EpiParams& ep, long long mt, long long nt,
-              int kb, int conv, int c_chunks, cudaStream_t st) {
+int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& ta2, const CUtensorMap& tb2,
+              const EpiParams& ep, long long mt, long long nt, int kb, int conv, int c_chunks, int kb_main, cudaStream_t st) {
   using C = Cfg<BN, CG>;
   static bool configured = false;
   if (!configured) {
@@ -892,7 +899,7 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, svla_gemm_tcgen05_kernel<BN, CG>, ta, tb, to, ep, mt, nt, kb, conv, c_chunks);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, svla_gemm_tcgen05_kernel<BN, CG>, ta, tb, to, ta2, tb2, ep, mt, nt, kb, conv, c_chunks, kb_main);
   if (e != cudaSuccess) {
     svla_set_error("svla_gemm_tcgen05<%d,%d>: launch failed: %s", BN, CG, cudaGetErrorString(e));
     return -2;
@@ -989,6 +996,7 @@ extern "C" int svla_gemm(const SvlaGemmArgs* g, void* stream) {
   SVLA_REQUIRE((reinterpret_cast<uintptr_t>(g->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g->w) & 15) == 0,
                "svla_gemm: operands must be 16-byte aligned");
 
+  SVLA_REQUIRE(!g->a2 || (g->impl != 1 && !conv), "svla_gemm: the K extension is implemented by the tcgen05 linear kernel only");
   if (g->impl == 1) {
     const long long ncols = geglu ? g->n / 2 : g->n;
     const long long total = g->m * ncols;
@@ -1029,7 +1037,16 @@ extern "C" int svla_gemm(const SvlaGemmArgs* g, void* stream) {
   int bn = g->block_n ? g->block_n : pick_block_n(m_tiles, g->n);
   SVLA_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "svla_gemm: block_n=%d unsupported", bn);
   const long long n_tiles = (g->n + bn - 1) / bn;
-  const int kblocks = conv ? 9 * c_chunks : static_cast<int>((g->k + kBK - 1) / kBK);
+  const int kb_main = conv ? 9 * c_chunks : static_cast<int>((g->k + kBK - 1) / kBK);
+  const bool has_ext = g->a2 != nullptr;
+  if (has_ext) {
+    SVLA_REQUIRE(!conv && g->w2 && g->k2 > 0, "svla_gemm: the K extension needs a2, w2, k2 > 0 and no conv mode");
+    SVLA_REQUIRE(g->lda2 >= g->k2 && (g->lda2 % 8) == 0 && g->ldw2 >= g->k2 && (g->ldw2 % 8) == 0,
+                 "svla_gemm: lda2 / ldw2 must be >= k2 and multiples of 8");
+    SVLA_REQUIRE((reinterpret_cast<uintptr_t>(g->a2) & 15) == 0 && (reinterpret_cast<uintptr_t>(g->w2) & 15) == 0,
+                 "svla_gemm: extension operands must be 16-byte aligned");
+  }
+  const int kblocks = kb_main + (has_ext ? static_cast<int>((g->k2 + kBK - 1) / kBK) : 0);
 
   CUtensorMap ta, tb;
   int rc;
@@ -1061,15 +1078,23 @@ extern "C" int svla_gemm(const SvlaGemmArgs* g, void* stream) {
     SVLA_REQUIRE(rc == 0, "svla_gemm: cuTensorMapEncodeTiled(out) failed (%d)", rc);
   }
 
+  CUtensorMap ta2 = ta, tb2 = tb;
+  if (has_ext) {
+    rc = encode_2d(&ta2, g->a2, static_cast<uint64_t>(g->k2), static_cast<uint64_t>(g->m), static_cast<uint64_t>(g->lda2), kBK, kBM);
+    SVLA_REQUIRE(rc == 0, "svla_gemm: cuTensorMapEncodeTiled(A2) failed (%d)", rc);
+    rc = encode_2d(&tb2, g->w2, static_cast<uint64_t>(g->k2), static_cast<uint64_t>(g->n), static_cast<uint64_t>(g->ldw2), kBK,
+                   static_cast<uint32_t>(use_pair ? bn / 2 : bn));
+    SVLA_REQUIRE(rc == 0, "svla_gemm: cuTensorMapEncodeTiled(W2) failed (%d)", rc);
+  }
   const int cv = conv ? 1 : 0;
   if (use_pair) {
-    if (bn == 128) return launch_tc<128, 2>(ta, tb, to, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
-    return launch_tc<256, 2>(ta, tb, to, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
+    if (bn == 128) return launch_tc<128, 2>(ta, tb, to, ta2, tb2, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, kb_main, st);
+    return launch_tc<256, 2>(ta, tb, to, ta2, tb2, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, kb_main, st);
   }
   switch (bn) {
-    case 32: return launch_tc<32, 1>(ta, tb, to, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
-    case 64: return launch_tc<64, 1>(ta, tb, to, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
-    case 128: return launch_tc<128, 1>(ta, tb, to, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
-    default: return launch_tc<256, 1>(ta, tb, to, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, st);
+    case 32: return launch_tc<32, 1>(ta, tb, to, ta2, tb2, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, kb_main, st);
+    case 64: return launch_tc<64, 1>(ta, tb, to, ta2, tb2, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, kb_main, st);
+    case 128: return launch_tc<128, 1>(ta, tb, to, ta2, tb2, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, kb_main, st);
+    default: return launch_tc<256, 1>(ta, tb, to, ta2, tb2, ep, m_tiles, n_tiles, kblocks, cv, c_chunks, kb_main, st);
   }
 }

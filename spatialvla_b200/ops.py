@@ -63,8 +63,9 @@ class CudaOps:
     # ---- G1
     def gemm(self, a, w, *, n=None, k=None, out_bf16=None, out_f32=None, out_relu=None, bias=None, colscale=None,
              res_bf16=None, res2_bf16=None, res_f32=None, res_mod=0, act=ACT_NONE, act_param=0.0, alpha=1.0,
-             geglu=False, accumulate=False, conv=None, block_n=0, impl=None):
-        """value = act(alpha * a @ w.T + bias) * colscale + residuals; see include/spatialvla_b200.h (svla_gemm).
+             geglu=False, accumulate=False, conv=None, block_n=0, impl=None, a2=None, w2=None):
+        """value = act(alpha * (a @ w.T + a2 @ w2.T) + bias) * colscale + residuals; see include/spatialvla_b200.h (svla_gemm).
+        a2 bf16 [M, K2] / w2 bf16 [N, K2]: the K extension (un-merged LoRA term accumulated in the same TMEM tile).
         a: bf16 [M, K] (row stride = lda) or, with conv=(nb,h,w,c), a contiguous NHWC bf16 tensor.
         w: bf16 [N, ldw]. Outputs are caller-allocated [M, >=N] row-major tensors sharing one row stride."""
         g = L.SvlaGemmArgs()
@@ -106,7 +107,101 @@ class CudaOps:
         g.alpha, g.act_param, g.act, g.flags = float(alpha), float(act_param), int(act), flags
         g.block_n = int(block_n)
         g.impl = int(self.gemm_impl if impl is None else impl)
+        if a2 is not None:
+            _req(w2 is not None and a2.dtype == BF16 and w2.dtype == BF16 and a2.dim() == 2 and w2.dim() == 2 and a2.stride(1) == 1
+                 and w2.stride(1) == 1 and a2.shape[0] == M and w2.shape[0] >= N and a2.shape[1] == w2.shape[1], "gemm: bad K-extension operands")
+            g.a2, g.w2, g.k2, g.lda2, g.ldw2 = _ptr(a2), _ptr(w2), int(a2.shape[1]), int(a2.stride(0)), int(w2.stride(0))
         L.check(self.lib.svla_gemm(C.byref(g), self._stream()), "svla_gemm")
+
+    # ---- fine-tune step: training forward pieces and backward kernels (csrc/train_ops.cu, csrc/train_mma.cu)
+    def rmsnorm_train_fwd(self, x_in, *, branch=None, w_post=None, w_pre=None, eps=1e-6, x_out=None, h=None):
+        _req(x_in.dtype == F32 and x_in.is_contiguous(), "rmsnorm_train_fwd: x_in must be contiguous fp32")
+        _req(branch is None or (branch.dtype == F32 and branch.is_contiguous() and x_out is not None and x_out.is_contiguous()), "rmsnorm_train_fwd: branch / x_out")
+        rows, cols = x_in.numel() // x_in.shape[-1], x_in.shape[-1]
+        L.check(self.lib.svla_rmsnorm_train_fwd(_ptr(x_in), _ptr(branch), _ptr(w_post), _ptr(w_pre), float(eps), rows, cols, _ptr(x_out),
+                                                _ptr(h), self._stream()), "svla_rmsnorm_train_fwd")
+
+    def rmsnorm_bwd(self, x, w, dy, *, eps=1e-6, row_idx=None, dx_accum=None, dx_bf16=None):
+        """dy bf16 / fp32 [rows, cols]; row_idx int64 [rows] (dy row i <-> x / dx row row_idx[i]) or None."""
+        _req(x.dtype == F32 and x.is_contiguous() and dy.is_contiguous() and dy.dtype in (BF16, F32), "rmsnorm_bwd: x fp32, dy bf16 / fp32, contiguous")
+        _req(row_idx is None or (row_idx.dtype == torch.int64 and row_idx.is_contiguous() and row_idx.numel() == dy.shape[0]), "rmsnorm_bwd: row_idx")
+        for t, dt in ((dx_accum, F32), (dx_bf16, BF16)):
+            _req(t is None or (t.dtype == dt and t.is_contiguous() and t.shape[-1] == x.shape[-1]), "rmsnorm_bwd: outputs")
+        rows, cols = dy.numel() // dy.shape[-1], dy.shape[-1]
+        L.check(self.lib.svla_rmsnorm_bwd(_ptr(x), _ptr(w), _ptr(dy), int(dy.dtype == F32), _ptr(row_idx), float(eps), rows, cols,
+                                          _ptr(dx_accum), _ptr(dx_bf16), self._stream()), "svla_rmsnorm_bwd")
+
+    def layernorm_bwd(self, x, gamma, beta, dy, *, eps, relu=False, dx_accum=None, copy_bf16=None, dx_bf16=None):
+        _req(x.dtype == F32 and x.is_contiguous() and dy.dtype == BF16 and dy.is_contiguous() and dy.shape == x.shape, "layernorm_bwd: x fp32 / dy bf16")
+        rows, cols = x.numel() // x.shape[-1], x.shape[-1]
+        L.check(self.lib.svla_layernorm_bwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(dy), float(eps), rows, cols, int(relu), _ptr(dx_accum),
+                                            _ptr(copy_bf16), _ptr(dx_bf16), self._stream()), "svla_layernorm_bwd")
+
+    def geglu_fwd(self, gu, act):
+        _req(gu.dtype == BF16 and act.dtype == BF16 and gu.is_contiguous() and act.is_contiguous() and gu.shape[1] == 2 * act.shape[1], "geglu_fwd: shapes")
+        L.check(self.lib.svla_geglu_fwd(_ptr(gu), _ptr(act), act.shape[0], act.shape[1], self._stream()), "svla_geglu_fwd")
+
+    def geglu_bwd(self, gu, dact, dgu):
+        _req(all(t.dtype == BF16 and t.is_contiguous() for t in (gu, dact, dgu)) and gu.shape == dgu.shape and gu.shape[1] == 2 * dact.shape[1], "geglu_bwd: shapes")
+        L.check(self.lib.svla_geglu_bwd(_ptr(gu), _ptr(dact), _ptr(dgu), dact.shape[0], dact.shape[1], self._stream()), "svla_geglu_bwd")
+
+    def gelu_tanh_fwd(self, z, f):
+        _req(z.dtype == BF16 and f.dtype == BF16 and z.is_contiguous() and f.is_contiguous() and z.shape == f.shape, "gelu_tanh_fwd: shapes")
+        L.check(self.lib.svla_gelu_tanh_fwd(_ptr(z), _ptr(f), z.numel(), self._stream()), "svla_gelu_tanh_fwd")
+
+    def gelu_tanh_bwd(self, z, df, dz):
+        _req(all(t.dtype == BF16 and t.is_contiguous() and t.shape == z.shape for t in (z, df, dz)), "gelu_tanh_bwd: shapes")
+        L.check(self.lib.svla_gelu_tanh_bwd(_ptr(z), _ptr(df), _ptr(dz), z.numel(), self._stream()), "svla_gelu_tanh_bwd")
+
+    def rope_bwd(self, dqkv, *, batch, s, hq, hkv, d, theta):
+        _req(dqkv.dtype == BF16 and dqkv.is_contiguous() and tuple(dqkv.shape) == (batch * s, (hq + 2 * hkv) * d), "rope_bwd: dqkv bf16 [B*S, (hq+2hkv)d]")
+        L.check(self.lib.svla_rope_bwd(_ptr(dqkv), batch, s, hq, hkv, d, float(theta), self._stream()), "svla_rope_bwd")
+
+    def rows_cast(self, src, out, *, row_idx=None, scale=1.0):
+        _req(src.dtype == F32 and src.is_contiguous() and out.dtype == BF16 and out.is_contiguous() and src.shape[-1] == out.shape[-1], "rows_cast: shapes")
+        _req(row_idx is None or (row_idx.dtype == torch.int64 and row_idx.is_contiguous() and row_idx.numel() == out.shape[0]), "rows_cast: row_idx")
+        L.check(self.lib.svla_rows_cast(_ptr(src), _ptr(row_idx), float(scale), out.shape[0], out.shape[-1], _ptr(out), self._stream()), "svla_rows_cast")
+
+    def lora_pack(self, arena, pool, plan):
+        """plan: LoRAStepLayout (desc_table = packed device records, records = the same on the host, total_tiles)."""
+        _req(arena.dtype == F32 and arena.is_contiguous() and pool.dtype == BF16 and pool.is_contiguous(), "lora_pack: arena fp32 / pool bf16")
+        L.check(self.lib.svla_lora_pack(_ptr(arena), _ptr(pool), _ptr(plan.desc_table), len(plan.records), int(plan.total_tiles), self._stream()),
+                "svla_lora_pack")
+
+    def fill_zero(self, t):
+        _req(t.is_contiguous(), "fill_zero: contiguous tensor")
+        L.check(self.lib.svla_fill_zero(_ptr(t), t.numel() * t.element_size(), self._stream()), "svla_fill_zero")
+
+    def attention_bwd(self, q, k, v, out, dout, dq, dk, dv, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
+                      do_strides, dq_strides, dk_strides, dv_strides, scale, softcap=0.0, causal=False, causal_prefix=0):
+        """Backward of `attention` (no relpos / kv_start): strides = (batch stride, token stride) in elements, head h at column h*d."""
+        a = L.SvlaAttnBwdArgs()
+        for t in (q, k, v, out, dout, dq, dk, dv):
+            _req(t.dtype == BF16, "attention_bwd: bf16 only")
+        a.q, a.k, a.v, a.out, a.dout, a.dq, a.dk, a.dv = (_ptr(t) for t in (q, k, v, out, dout, dq, dk, dv))
+        (a.q_bs, a.q_ss), (a.k_bs, a.k_ss), (a.v_bs, a.v_ss), (a.o_bs, a.o_ss) = q_strides, k_strides, v_strides, o_strides
+        (a.do_bs, a.do_ss), (a.dq_bs, a.dq_ss), (a.dk_bs, a.dk_ss), (a.dv_bs, a.dv_ss) = do_strides, dq_strides, dk_strides, dv_strides
+        stats = torch.empty((2, batch, hq, sq), dtype=F32, device=self.device)
+        a.lse, a.delta = _ptr(stats[0]), _ptr(stats[1])
+        a.batch, a.hq, a.hkv, a.sq, a.sk, a.d = batch, hq, hkv, sq, sk, d
+        a.scale, a.softcap, a.causal, a.causal_prefix = float(scale), float(softcap or 0.0), int(bool(causal)), int(causal_prefix)
+        L.check(self.lib.svla_attention_bwd(C.byref(a), self._stream()), "svla_attention_bwd")
+        return stats
+
+    def gemm_tn(self, s, y, groups, *, r, n, scale=1.0):
+        """dst_g += scale * S[:, row0:row0+rows]^T Y[:, col_start::col_stride][:ncols] for each group
+        (dst fp32 view [rows, >= ncols] with unit column stride, row0, rows, col_start, col_stride, ncols); up to 4 groups."""
+        a = L.SvlaGemmTnArgs()
+        _req(s.dtype == BF16 and y.dtype == BF16 and s.dim() == 2 and y.dim() == 2 and s.stride(1) == 1 and y.stride(1) == 1
+             and s.shape[0] == y.shape[0], "gemm_tn: bf16 [M, *] operands with one row count")
+        _req(1 <= len(groups) <= 4, "gemm_tn: 1..4 groups")
+        a.s, a.y, a.m, a.lds, a.ldy = _ptr(s), _ptr(y), int(s.shape[0]), int(s.stride(0)), int(y.stride(0))
+        a.r, a.n, a.scale, a.n_groups = int(r), int(n), float(scale), len(groups)
+        for i, (dst, row0, rows, c0, cs, nc) in enumerate(groups):
+            _req(dst.dtype == F32 and dst.dim() == 2 and dst.stride(1) == 1 and dst.shape[0] == rows and dst.shape[1] >= nc, "gemm_tn: bad group dst")
+            g = a.groups[i]
+            g.dst, g.ld, g.row0, g.rows, g.col_start, g.col_stride, g.ncols = _ptr(dst), int(dst.stride(0)), int(row0), int(rows), int(c0), int(cs), int(nc)
+        L.check(self.lib.svla_gemm_tn(C.byref(a), self._stream()), "svla_gemm_tn")
 
     # ---- G1s
     def skinny_splits(self, n, k):
@@ -266,14 +361,21 @@ class CudaOps:
                                                 _ptr(dz), dz.shape[1], self._stream()),
                 "svla_cross_entropy_bwd")
 
-    def adamw_step(self, param, grad, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step, grad_scale=1.0):
-        """In-place AdamW on flat fp32 buffers (torch.optim.AdamW arithmetic); step counts from 1.
-        NOT yet verified on hardware (see include/spatialvla_b200.h); nothing on the product path calls it."""
+    def adamw_step(self, param, grad, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step, grad_scale=1.0,
+                   sumsq=None, max_grad_norm=0.0):
+        """In-place AdamW on flat fp32 buffers (torch.optim.AdamW arithmetic); step counts from 1.  sumsq: device fp32 scalar holding
+        sum(grad^2) (ops.sumsq) -> clip_grad_norm_(max_grad_norm) of the scaled gradient is applied inside the kernel."""
         for t in (param, grad, exp_avg, exp_avg_sq):
             _req(t.dtype == F32 and t.dim() == 1 and t.is_contiguous() and t.numel() == param.numel(), "adamw_step: flat fp32 buffers of one size")
+        _req(sumsq is None or (sumsq.dtype == F32 and sumsq.numel() == 1), "adamw_step: sumsq fp32 scalar")
         L.check(self.lib.svla_adamw_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr), float(beta1),
-                                         float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), self._stream()),
+                                         float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), _ptr(sumsq),
+                                         float(max_grad_norm), self._stream()),
                 "svla_adamw_step")
+
+    def sumsq(self, x, out):
+        _req(x.dtype == F32 and x.is_contiguous() and out.dtype == F32 and out.numel() == 1, "sumsq: fp32 buffer / scalar")
+        L.check(self.lib.svla_sumsq(_ptr(x), x.numel(), _ptr(out), self._stream()), "svla_sumsq")
 
     def siglip_patchify(self, px, a):
         _req(px.dtype == F32 and px.is_contiguous() and tuple(px.shape[1:]) == (3, 224, 224), "siglip_patchify: px")

@@ -56,3 +56,8 @@ def allreduce_gradients(arena, group=None, average: bool = True):
         if average:
             arena.grad.div_(dist.get_world_size(group))
     return arena.grad.numel()
+
+
+def world_size(group=None) -> int:
+    import torch.distributed as dist
+    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1

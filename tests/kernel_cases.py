@@ -746,7 +746,260 @@ def adamw_case(dev="cuda:0"):
     return res
 
 
+# ------------------------------------------------------------------------------------------------ fine-tune step kernels
+def gemm_lora_ext_case(name, M, N, K, K2, *, pair=None, geglu=False, block_n=0, out=("bf16",), seed=0):
+    """K extension of the tcgen05 GEMM: acc = A W^T + A2 W2^T in one TMEM tile (un-merged LoRA Linear and its input gradient)."""
+    def case(dev="cuda:0"):
+        g = _gen(seed + 77)
+        a, wt = _randn(g, M, K, dtype=BF16), (_randn(g, N, K) / K ** 0.5).to(BF16)
+        k2p = (K2 + 63) // 64 * 64                                    # operand buffers padded with zero columns, like the step's pool
+        a2, w2 = torch.zeros(M, k2p, dtype=BF16), torch.zeros(N, k2p, dtype=BF16)
+        a2[:, :K2] = _randn(g, M, K2, dtype=BF16)
+        w2[:, :K2] = (_randn(g, N, K2) * 0.3).to(BF16)
+        ncol = N // 2 if geglu else N
+
+        def run(ops, to):
+            ob = ops.zeros((M, ncol), BF16) if "bf16" in out else None
+            of = ops.zeros((M, ncol), F32) if "f32" in out else None
+            ops.gemm(to(a), to(wt), out_bf16=ob, out_f32=of, geglu=geglu, a2=to(a2), w2=to(w2), block_n=block_n, impl=pair)
+            return ob, of
+        (cb, cf), (rb, rf_) = _both(run, dev)
+        res = Result(name)
+        if cb is not None:
+            res.add("bf16", _err(cb, rb), TOL_BF16)
+        if cf is not None:
+            res.add("f32", _err(cf, rf_), TOL_F32)
+        # the extension term must matter: without it the result is clearly different
+        base = (a.float() @ wt.float().t())
+        ext = a2.float() @ w2.float().t()
+        res.add("ext_is_visible", 0.0 if float(ext.abs().max()) > 0.05 * float(base.abs().max()) else 1.0, 0)
+        return res
+    case.__name__ = name
+    return case
+
+
+LORA_GEMM_CASES = [
+    gemm_lora_ext_case("gemm_ext_r32", 300, 256, 128, 32, out=("bf16", "f32")),
+    gemm_lora_ext_case("gemm_ext_r96_bn128", 640, 512, 192, 96, block_n=128),
+    gemm_lora_ext_case("gemm_ext_r64_geglu", 512, 1024, 256, 64, geglu=True),
+    gemm_lora_ext_case("gemm_ext_pair", 1024, 2304, 320, 96, pair=3),
+    gemm_lora_ext_case("gemm_ext_multiwave", 9312, 4096, 2304, 96),
+    gemm_lora_ext_case("gemm_ext_bn64_f32", 200, 64, 72, 32, out=("f32",)),
+]
+
+
+def train_norm_case(dev="cuda:0"):
+    res = Result("train_norms")
+    for (rows, cols) in ((37, 2304), (1001, 512), (64, 1152)):
+        g = _gen(rows + cols)
+        x, br = _randn(g, rows, cols), _randn(g, rows, cols, scale=3.0)
+        wp, wq = _randn(g, cols, scale=0.2), _randn(g, cols, scale=0.2)
+        dy_b, dy_f = _randn(g, rows, cols, dtype=BF16), _randn(g, rows, cols)
+        acc0 = _randn(g, rows, cols)
+
+        def fwd(ops, to):
+            xo, h = ops.zeros((rows, cols), F32), ops.zeros((rows, cols), BF16)
+            ops.rmsnorm_train_fwd(to(x), branch=to(br), w_post=to(wp), w_pre=to(wq), eps=1e-6, x_out=xo, h=h)
+            h0 = ops.zeros((rows, cols), BF16)
+            ops.rmsnorm_train_fwd(to(x), w_pre=to(wq), eps=1e-6, h=h0)
+            return xo, h, h0
+        (cx, ch, ch0), (rx, rh, rh0) = _both(fwd, dev)
+        res.add(f"fwd_x[{rows}x{cols}]", _err(cx, rx), 1e-5)
+        res.add(f"fwd_h[{rows}x{cols}]", _err(ch, rh), TOL_BF16)
+        res.add(f"fwd_h_only[{rows}x{cols}]", _err(ch0, rh0), TOL_BF16)
+
+        def bwd(ops, to):
+            acc, ob = to(acc0), ops.zeros((rows, cols), BF16)
+            ops.rmsnorm_bwd(to(x), to(wq), to(dy_b), eps=1e-6, dx_accum=acc)
+            ops.rmsnorm_bwd(to(br), to(wp), to(dy_f), eps=1e-6, dx_bf16=ob)
+            return acc, ob
+        (ca, cb), (ra, rb) = _both(bwd, dev)
+        res.add(f"rms_bwd_accum[{rows}x{cols}]", _err(ca, ra), 1e-4)
+        res.add(f"rms_bwd_bf16[{rows}x{cols}]", _err(cb, rb), TOL_BF16)
+        # labelled-row indirection of the final norm
+        nsel = min(rows, 13)
+        sel = torch.randperm(rows, generator=g)[:nsel].sort().values
+        dyr = _randn(g, nsel, cols)
+
+        def bwd_idx(ops, to):
+            acc = ops.zeros((rows, cols), F32)
+            ops.rmsnorm_bwd(to(x), to(wq), to(dyr), eps=1e-6, row_idx=to(sel), dx_accum=acc)
+            return acc
+        ci, ri = _both(bwd_idx, dev)
+        res.add(f"rms_bwd_rows[{rows}x{cols}]", _err(ci, ri), 1e-4)
+        gm, bt = _randn(g, cols, scale=0.5) + 1.0, _randn(g, cols, scale=0.3)
+        for relu in (False, True):
+            def ln(ops, to):
+                acc, cp, ob = to(acc0), ops.zeros((rows, cols), BF16), ops.zeros((rows, cols), BF16)
+                ops.layernorm_bwd(to(x), to(gm), to(bt), to(dy_b), eps=1e-6, relu=relu, dx_accum=acc, copy_bf16=cp, dx_bf16=ob)
+                return acc, cp, ob
+            (ca, cc, cb), (ra, rc, rb) = _both(ln, dev)
+            res.add(f"ln_bwd_accum[{rows}x{cols},relu={int(relu)}]", _err(ca, ra), 1e-4)
+            res.add(f"ln_bwd_copy[{rows}x{cols},relu={int(relu)}]", _err(cc, rc), TOL_BF16)
+            res.add(f"ln_bwd_bf16[{rows}x{cols},relu={int(relu)}]", _err(cb, rb), TOL_BF16)
+    return res
+
+
+def train_elementwise_case(dev="cuda:0"):
+    res = Result("train_elementwise")
+    g = _gen(5)
+    rows, inter = 333, 1024
+    gu, dact = _randn(g, rows, 2 * inter, dtype=BF16, scale=1.5), _randn(g, rows, inter, dtype=BF16)
+
+    def geglu(ops, to):
+        act, dgu = ops.zeros((rows, inter), BF16), ops.zeros((rows, 2 * inter), BF16)
+        ops.geglu_fwd(to(gu), act)
+        ops.geglu_bwd(to(gu), to(dact), dgu)
+        return act, dgu
+    (ca, cd), (ra, rd) = _both(geglu, dev)
+    res.add("geglu_fwd", _err(ca, ra), TOL_BF16)
+    res.add("geglu_bwd", _err(cd, rd), TOL_BF16)
+    z, df = _randn(g, 200, 4304, dtype=BF16, scale=2.0), _randn(g, 200, 4304, dtype=BF16)
+
+    def gelu(ops, to):
+        f, dz = ops.zeros(z.shape, BF16), ops.zeros(z.shape, BF16)
+        ops.gelu_tanh_fwd(to(z), f)
+        ops.gelu_tanh_bwd(to(z), to(df), dz)
+        return f, dz
+    (cf, cz), (rf_, rz) = _both(gelu, dev)
+    res.add("gelu_fwd", _err(cf, rf_), TOL_BF16)
+    res.add("gelu_bwd", _err(cz, rz), TOL_BF16)
+    B, S, hq, hkv, d = 3, 19, 4, 2, 256
+    dq = _randn(g, B * S, (hq + 2 * hkv) * d, dtype=BF16)
+
+    def rope(ops, to):
+        t = to(dq).clone()
+        ops.rope_bwd(t, batch=B, s=S, hq=hq, hkv=hkv, d=d, theta=10000.0)
+        return t
+    cr, rr = _both(rope, dev)
+    res.add("rope_bwd", _err(cr, rr), TOL_BF16)
+    res.add("rope_bwd_v_untouched", float((cr.cpu()[:, (hq + hkv) * d:].float() - dq[:, (hq + hkv) * d:].float()).abs().max()), 0)
+    src = _randn(g, 500, 512)
+    idx = torch.randint(0, 500, (77,), generator=g)
+
+    def cast(ops, to):
+        o1, o2 = ops.zeros((77, 512), BF16), ops.zeros((500, 512), BF16)
+        ops.rows_cast(to(src), o1, row_idx=to(idx), scale=48.0 / 47.0)
+        ops.rows_cast(to(src), o2)
+        return o1, o2
+    (c1, c2), (r1, r2) = _both(cast, dev)
+    res.add("rows_cast_gather", _err(c1, r1), TOL_BF16)
+    res.add("rows_cast", _err(c2, r2), TOL_BF16)
+    return res
+
+
+def attn_bwd_case(name, B, hq, hkv, sq, sk, d, *, softcap=0.0, causal=False, prefix=0, seed=0):
+    """svla_attention_bwd (3 launches) vs the closed form oracle/backward_ref.softcap_attention_bwd (itself pinned on autograd);
+    q/k/v packed like the step's tensors (q in its own tensor, k / v as rows of a [B, sk, hkv, d] cache, gradients as column blocks
+    of one [tokens, (hq + 2 hkv) d] tensor)."""
+    def case(dev="cuda:0"):
+        g = _gen(seed + 31)
+        q = _randn(g, B * sq, hq * d, dtype=BF16)
+        kc, vc = _randn(g, B, sk, hkv, d, dtype=BF16), _randn(g, B, sk, hkv, d, dtype=BF16)
+        dout = _randn(g, B * sq, hq * d, dtype=BF16)
+        scale = d ** -0.5
+        W = (hq + 2 * hkv) * d
+
+        def run(ops, to):
+            Q, K, V, dO = to(q), to(kc), to(vc), to(dout)
+            out = ops.zeros((B * sq, hq * d), BF16)
+            kvs = (sk * hkv * d, hkv * d)
+            ops.attention(Q, K, V, out, batch=B, hq=hq, hkv=hkv, sq=sq, sk=sk, d=d, q_strides=(sq * hq * d, hq * d), k_strides=kvs,
+                          v_strides=kvs, o_strides=(sq * hq * d, hq * d), scale=scale, softcap=softcap, causal=causal, causal_prefix=prefix)
+            assert sq == sk
+            dqkv = ops.zeros((B * sq, W), BF16) + 5.0                       # poison: every element must be written
+            ops.attention_bwd(Q, K, V, out, dO, dqkv, dqkv[:, hq * d:], dqkv[:, (hq + hkv) * d:], batch=B, hq=hq, hkv=hkv, sq=sq, sk=sk,
+                              d=d, q_strides=(sq * hq * d, hq * d), k_strides=kvs, v_strides=kvs, o_strides=(sq * hq * d, hq * d),
+                              do_strides=(sq * hq * d, hq * d), dq_strides=(sq * W, W), dk_strides=(sk * W, W), dv_strides=(sk * W, W),
+                              scale=scale, softcap=softcap, causal=causal, causal_prefix=prefix)
+            return dqkv
+        c, r = _both(run, dev)
+        c, r = c.float().cpu(), r.float()
+        res = Result(name)
+        for nm, lo, hi in (("dq", 0, hq * d), ("dk", hq * d, (hq + hkv) * d), ("dv", (hq + hkv) * d, W)):
+            res.add(nm, float((c[:, lo:hi] - r[:, lo:hi]).abs().max()) / max(float(r[:, lo:hi].abs().max()), 1e-20), 2e-2)
+        return res
+    case.__name__ = name
+    return case
+
+
+ATTN_BWD_CASES = [
+    attn_bwd_case("attn_bwd_gemma_prefixlm", 2, 4, 2, 291, 291, 256, softcap=50.0, causal=True, prefix=278),
+    attn_bwd_case("attn_bwd_gemma_causal", 1, 8, 4, 130, 130, 256, softcap=50.0, causal=True),
+    attn_bwd_case("attn_bwd_gemma_bidirectional", 2, 2, 2, 77, 77, 256, softcap=50.0),
+    attn_bwd_case("attn_bwd_siglip_d72", 2, 16, 16, 256, 256, 72),
+    attn_bwd_case("attn_bwd_d72_ragged", 3, 2, 2, 100, 100, 72),
+    attn_bwd_case("attn_bwd_d64_causal_prefix", 2, 4, 1, 200, 200, 64, causal=True, prefix=50, softcap=20.0),
+    attn_bwd_case("attn_bwd_d128", 1, 2, 2, 96, 96, 128),
+]
+
+
+def gemm_tn_case(dev="cuda:0"):
+    """svla_gemm_tn: rank-r reductions over the token dimension into windows of a fp32 gradient arena (fused q|k|v blocks, interleaved
+    gate/up columns, a column-clipped window (K = 204 of a 208-wide operand), accumulation on top of existing values)."""
+    res = Result("gemm_tn")
+    g = _gen(11)
+    M = 2000
+    # fused qkv gB: 3 adapters x r=32 rows, each with its own column window of dY [M, 4096]
+    s, y = _randn(g, M, 128, dtype=BF16), _randn(g, M, 1024, dtype=BF16)
+    s[:, 96:] = 0
+    init = _randn(g, 3 * 32 * 512)
+
+    def qkv(ops, to):
+        arena = to(init).clone()
+        v0, v1, v2 = arena[:32 * 512].view(32, 512), arena[32 * 512:32 * 768].view(32, 256), arena[32 * 768:32 * 1024].view(32, 256)
+        ops.gemm_tn(to(s), to(y), [(v0, 0, 32, 0, 1, 512), (v1, 32, 32, 512, 1, 256), (v2, 64, 32, 768, 1, 256)], r=96, n=1024, scale=0.5)
+        return arena
+    c, r = _both(qkv, dev)
+    res.add("qkv_windows", _err(c, r), 2e-3)
+    # gate/up: two adapters, interleaved columns; gA: one dense group with a clipped column count
+    s2, y2 = _randn(g, M, 64, dtype=BF16), _randn(g, M, 2048, dtype=BF16)
+    x208 = _randn(g, M, 208, dtype=BF16)
+
+    def gu(ops, to):
+        gg, gup, ga = ops.zeros((32, 1024), F32), ops.zeros((32, 1024), F32), ops.zeros((64, 204), F32)
+        ops.gemm_tn(to(s2), to(y2), [(gg, 0, 32, 0, 2, 1024), (gup, 32, 32, 1, 2, 1024)], r=64, n=2048)
+        ops.gemm_tn(to(s2), to(x208), [(ga, 0, 64, 0, 1, 204)], r=64, n=208, scale=2.0)
+        return gg, gup, ga
+    (c0, c1, c2), (r0, r1, r2) = _both(gu, dev)
+    res.add("gate_stride2", _err(c0, r0), 2e-3)
+    res.add("up_stride2", _err(c1, r1), 2e-3)
+    res.add("clipped_cols", _err(c2, r2), 2e-3)
+    # long contraction, r = 32, config-#5-sized token count
+    M2 = 9312
+    s3, y3 = _randn(g, M2, 64, dtype=BF16), _randn(g, M2, 2304, dtype=BF16)
+
+    def big(ops, to):
+        o = ops.zeros((32, 2304), F32)
+        ops.gemm_tn(to(s3)[:, :64], to(y3), [(o, 0, 32, 0, 1, 2304)], r=32, n=2304)
+        return o
+    cb, rb = _both(big, dev)
+    res.add("m9312_r32", _err(cb, rb), 2e-3)
+    return res
+
+
+def lora_pack_case(dev="cuda:0"):
+    """svla_lora_pack through the step's own layout builder: every operand of a tiny adapted model against the torch re-statement."""
+    from spatialvla_b200.lora import LoRAStepLayout
+    from spatialvla_b200.configs import get_config_dict
+    res = Result("lora_pack")
+    cfg = get_config_dict("tiny")
+
+    def run(ops, to):
+        lay = LoRAStepLayout(cfg, ops, r=32, alpha=32.0, seed=3)
+        lay.param.copy_(to(torch.randn(lay.param.numel(), generator=_gen(9))))
+        lay.pack()
+        return lay.pool
+    c, r = _both(run, dev)
+    res.add("pool", float((c.float().cpu() - r.float()).abs().max()), 0)
+    res.add("pool_nonzero", 0.0 if float(r.float().abs().sum()) > 0 else 1.0, 0)
+    return res
+
+
+TRAIN_CASES = [train_norm_case, train_elementwise_case, gemm_tn_case, lora_pack_case]
+
 FUSED_CASES = [layernorm_case, rmsnorm_case, rope_case, embed_case, argmax_case, cross_entropy_case, cross_entropy_bwd_case, adamw_case, patchify_case, assemble_concat_case,
                shuffle_im2col_case, bilinear_case, zoe_tail_case, ego3d_case, tokenizer_case]
 
-ALL_CASES = {c.__name__: c for c in (SIMT_CASES + GEMM_CASES + PAIR_CASES + TMA_EPI_CASES + ROWTILE_CASES + SKINNY_CASES + ATTN_CASES + FUSED_CASES)}
+ALL_CASES = {c.__name__: c for c in (SIMT_CASES + GEMM_CASES + PAIR_CASES + TMA_EPI_CASES + ROWTILE_CASES + SKINNY_CASES + ATTN_CASES + FUSED_CASES
+                                     + LORA_GEMM_CASES + ATTN_BWD_CASES + TRAIN_CASES)}

@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert sorted(L.SIGNATURES) == names, "ctypes SIGNATURES and the header disagree"
-    assert lib.svla_abi_version() == 1
+    assert lib.svla_abi_version() == 2
     assert lib.svla_launch_count() >= 0
 
 
@@ -38,7 +38,8 @@ def test_gemm_args_struct_matches_header_layout():
     # 11 pointers/int64 before m: a w bias colscale res_bf16 res2_bf16 res_f32 res_mod out_bf16 out_f32 out_relu
     assert L.SvlaGemmArgs.m.offset == 11 * 8
     assert L.SvlaGemmArgs.nb.offset == 17 * 8
-    assert C.sizeof(L.SvlaGemmArgs) == 17 * 8 + 10 * 4
+    assert L.SvlaGemmArgs.a2.offset == 17 * 8 + 10 * 4 and C.sizeof(L.SvlaGemmArgs) == 17 * 8 + 10 * 4 + 5 * 8       # K extension appended
+    assert L.SvlaGemmTnArgs.groups.offset == 56 and C.sizeof(L.SvlaTnGroup) == 40 and L.SvlaAttnBwdArgs.lse.offset == 24 * 8
     assert L.SvlaAttnArgs.batch.offset == 12 * 8
     assert L.SvlaAttnArgs.kv_start.offset == 152 and L.SvlaAttnArgs.causal_prefix.offset == 160 and C.sizeof(L.SvlaAttnArgs) == 168
 

@@ -10,6 +10,7 @@
 //     gB^T = (X A^T)^T dY (train/spatialvla_finetune.py:262-302; oracle/backward_ref.lora_linear_bwd), contraction over the TOKEN
 //     dimension, split over CTAs, accumulated with fp32 reductions straight into the gradient arena.
 // Warp-level mma.sync (bf16 in, fp32 accumulate): these are ~6 % of the step's FLOPs; the dX GEMMs run on the tcgen05 kernel.
+#include <cstdlib>
 #include "mma_sync.cuh"
 
 namespace {
@@ -160,17 +161,42 @@ __device__ __forceinline__ void ab_zero_pad(__nv_bfloat16* sm, int rows, int d) 
 __device__ __forceinline__ bool ab_masked(const AttnBwdP& p, int i, int j) {
   return j >= p.sk || (p.causal && j > max(i + (p.sk - p.sq), p.prefix - 1));
 }
+// tanh for soft-capping: |u| is small (scores / 50), an odd degree-9 polynomial is exact to fp32 rounding below 0.35 (the same
+// evaluation the forward kernels use, so the recomputed probabilities are consistent with the forward pass)
+__device__ __forceinline__ float ab_tanh(float u) {
+  const float u2 = u * u;
+  if (u2 < 0.1225f) {
+    float pl = 62.f / 2835.f;
+    pl = fmaf(pl, u2, -17.f / 315.f);
+    pl = fmaf(pl, u2, 2.f / 15.f);
+    pl = fmaf(pl, u2, -1.f / 3.f);
+    pl = fmaf(pl, u2, 1.f);
+    return u * pl;
+  }
+  return tanhf(u);
+}
+__device__ __forceinline__ float ab_exp(float x) {        // e^x through MUFU ex2
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
 // soft-capped score (natural units) and d(capped)/d(raw scaled score)
 __device__ __forceinline__ void ab_score(const AttnBwdP& p, float raw, float& c, float& fac) {
   const float u = raw * p.scale;
   if (p.softcap > 0.f) {
-    const float th = tanhf(u / p.softcap);
+    const float th = ab_tanh(u / p.softcap);
     c = p.softcap * th;
     fac = 1.f - th * th;
   } else {
     c = u;
     fac = 1.f;
   }
+}
+// a (query tile, key tile) pair needs no per-element mask when every key is in range and visible to every query of the tile
+__device__ __forceinline__ bool ab_tile_unmasked(const AttnBwdP& p, int q_lo, int q_hi, int k_lo, int k_hi) {
+  if (k_hi > p.sk || q_hi > p.sq) return false;
+  if (!p.causal) return true;
+  return (k_hi - 1) <= max(q_lo + (p.sk - p.sq), p.prefix - 1);
 }
 
 // ---- launch 0: logsumexp per query row + delta = rowsum(dO * O)
@@ -237,14 +263,14 @@ svla_attn_bwd_stats_kernel(const AttnBwdP p) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float m_new = fmaxf(m_run[r], mx[r]);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      l_run[r] *= __expf(m_run[r] - m_use);
+      l_run[r] *= ab_exp(m_run[r] - m_use);
       m_run[r] = m_new;
       mx[r] = m_use;
     }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      l_run[0] += __expf(s[nt][0] - mx[0]) + __expf(s[nt][1] - mx[0]);
-      l_run[1] += __expf(s[nt][2] - mx[1]) + __expf(s[nt][3] - mx[1]);
+      l_run[0] += ab_exp(s[nt][0] - mx[0]) + ab_exp(s[nt][1] - mx[0]);
+      l_run[1] += ab_exp(s[nt][2] - mx[1]) + ab_exp(s[nt][3] - mx[1]);
     }
     __syncthreads();
   }
@@ -273,15 +299,17 @@ svla_attn_bwd_stats_kernel(const AttnBwdP p) {
 }
 
 // ---- launch 1: dQ.  CTA = 64 queries of one (batch, head); key tiles of KT keys stream through shared memory.
-template <int DP, int KT>
-__global__ void __launch_bounds__(kAbThreads)
+template <int DP, int KT, int NB>
+__global__ void __launch_bounds__(kAbThreads, NB == 1 ? 2 : 1)
 svla_attn_bwd_dq_kernel(const AttnBwdP p) {
+  // NB = K / V buffers: 2 = double-buffered cp.async pipeline; 1 = single buffer so that TWO CTAs fit one SM at d = 256 (101 KB
+  // each): the second CTA's MMAs hide this CTA's loads, which measured faster than one CTA with a prefetch pipeline
   constexpr int LD = DP + 8, NTK = KT / 8, NTD = DP / 8;
   extern __shared__ __align__(16) uint8_t smem_ab[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_ab);       // [64][LD]
   __nv_bfloat16* sdO = sQ + 64 * LD;                                   // [64][LD]
-  __nv_bfloat16* sK = sdO + 64 * LD;                                   // [2][KT][LD]
-  __nv_bfloat16* sV = sK + 2 * KT * LD;                                // [2][KT][LD]
+  __nv_bfloat16* sK = sdO + 64 * LD;                                   // [NB][KT][LD]
+  __nv_bfloat16* sV = sK + NB * KT * LD;                               // [NB][KT][LD]
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
   const int hk = h / (p.hq / p.hkv);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -289,7 +317,7 @@ svla_attn_bwd_dq_kernel(const AttnBwdP p) {
   const __nv_bfloat16* dog = p.dout + b * p.do_bs + static_cast<long long>(h) * p.d;
   const __nv_bfloat16* kg = p.k + b * p.k_bs + static_cast<long long>(hk) * p.d;
   const __nv_bfloat16* vg = p.v + b * p.v_bs + static_cast<long long>(hk) * p.d;
-  ab_zero_pad<DP>(sQ, 128 + 4 * KT, p.d);
+  ab_zero_pad<DP>(sQ, 128 + 2 * NB * KT, p.d);
   // keys beyond the last one any query of this tile can see are skipped
   int k_hi = p.sk;
   if (p.causal) k_hi = min(p.sk, max(min(q0 + 63, p.sq - 1) + (p.sk - p.sq), p.prefix - 1) + 1);
@@ -312,8 +340,8 @@ svla_attn_bwd_dq_kernel(const AttnBwdP p) {
   for (int i = 0; i < NTD; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
 
   for (int jt = 0; jt < n_kt; ++jt) {
-    const int buf = jt & 1;
-    if (jt + 1 < n_kt) {
+    const int buf = (NB == 2) ? (jt & 1) : 0;
+    if (NB == 2 && jt + 1 < n_kt) {
       ab_load_tile<DP, KT>(sK + (buf ^ 1) * KT * LD, kg, p.k_ss, (jt + 1) * KT, p.sk, p.d);
       ab_load_tile<DP, KT>(sV + (buf ^ 1) * KT * LD, vg, p.v_ss, (jt + 1) * KT, p.sk, p.d);
       cp_async_commit();
@@ -324,6 +352,7 @@ svla_attn_bwd_dq_kernel(const AttnBwdP p) {
     __syncthreads();
     const __nv_bfloat16* cK = sK + buf * KT * LD;
     const __nv_bfloat16* cV = sV + buf * KT * LD;
+    const bool plain = ab_tile_unmasked(p, q0, q0 + 64, jt * KT, (jt + 1) * KT);
     float s[NTK][4], dp[NTK][4];
 #pragma unroll
     for (int i = 0; i < NTK; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
@@ -352,7 +381,7 @@ svla_attn_bwd_dq_kernel(const AttnBwdP p) {
         const int i = qi0 + (e >> 1) * 8, j = jt * KT + nt * 8 + 2 * t + (e & 1);
         float c, fac;
         ab_score(p, s[nt][e], c, fac);
-        const float pr = (ab_masked(p, i, j) || i >= p.sq) ? 0.f : __expf(c - lse_r[e >> 1]);
+        const float pr = (!plain && (ab_masked(p, i, j) || i >= p.sq)) ? 0.f : ab_exp(c - lse_r[e >> 1]);
         ds[e] = pr * (dp[nt][e] - del_r[e >> 1]) * fac * p.scale;
       }
       dsa[nt][0] = pack_bf16x2(ds[0], ds[1]);
@@ -370,6 +399,11 @@ svla_attn_bwd_dq_kernel(const AttnBwdP p) {
       }
     }
     __syncthreads();
+    if (NB == 1 && jt + 1 < n_kt) {
+      ab_load_tile<DP, KT>(sK, kg, p.k_ss, (jt + 1) * KT, p.sk, p.d);
+      ab_load_tile<DP, KT>(sV, vg, p.v_ss, (jt + 1) * KT, p.sk, p.d);
+      cp_async_commit();
+    }
   }
   __nv_bfloat16* dqg = p.dq + b * p.dq_bs + static_cast<long long>(h) * p.d;
 #pragma unroll
@@ -387,23 +421,23 @@ svla_attn_bwd_dq_kernel(const AttnBwdP p) {
 // ---- launch 2: dK, dV.  CTA = 64 keys of one (batch, kv head); query tiles of QT queries of every head of the GQA group stream
 // through shared memory.  The head dimension is processed in slices of DH columns (one sweep over the queries per slice) so that
 // the dK / dV accumulators of a slice fit the register file at d = 256; the score and dP tiles are recomputed per slice.
-template <int DP, int QT, int DH>
-__global__ void __launch_bounds__(kAbThreads)
+template <int DP, int QT, int DH, int NB>
+__global__ void __launch_bounds__(kAbThreads, NB == 1 ? 2 : 1)
 svla_attn_bwd_dkv_kernel(const AttnBwdP p) {
   constexpr int LD = DP + 8, NTQ = QT / 8, NTH = DH / 8;
   extern __shared__ __align__(16) uint8_t smem_ab[];
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_ab);       // [64][LD]
   __nv_bfloat16* sV = sK + 64 * LD;                                    // [64][LD]
-  __nv_bfloat16* sQ = sV + 64 * LD;                                    // [2][QT][LD]
-  __nv_bfloat16* sdO = sQ + 2 * QT * LD;                               // [2][QT][LD]
-  float* sLse = reinterpret_cast<float*>(sdO + 2 * QT * LD);           // [2][QT]
-  float* sDel = sLse + 2 * QT;                                         // [2][QT]
+  __nv_bfloat16* sQ = sV + 64 * LD;                                    // [NB][QT][LD]
+  __nv_bfloat16* sdO = sQ + NB * QT * LD;                              // [NB][QT][LD]
+  float* sLse = reinterpret_cast<float*>(sdO + NB * QT * LD);          // [NB][QT]
+  float* sDel = sLse + NB * QT;                                        // [NB][QT]
   const int b = blockIdx.z, hk = blockIdx.y, k0 = blockIdx.x * 64;
   const int G = p.hq / p.hkv;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* kg = p.k + b * p.k_bs + static_cast<long long>(hk) * p.d;
   const __nv_bfloat16* vg = p.v + b * p.v_bs + static_cast<long long>(hk) * p.d;
-  ab_zero_pad<DP>(sK, 128 + 4 * QT, p.d);
+  ab_zero_pad<DP>(sK, 128 + 2 * NB * QT, p.d);
   // first query that can see a key of this tile
   int q_lo = 0;
   if (p.causal && k0 >= p.prefix) q_lo = max(0, k0 - (p.sk - p.sq));
@@ -443,8 +477,8 @@ svla_attn_bwd_dkv_kernel(const AttnBwdP p) {
       cp_async_commit();
     }
     for (int it = 0; it < n_it; ++it) {
-      const int buf = it & 1;
-      if (it + 1 < n_it) {
+      const int buf = (NB == 2) ? (it & 1) : 0;
+      if (NB == 2 && it + 1 < n_it) {
         load_q(buf ^ 1, it + 1);
         cp_async_commit();
         cp_async_wait<1>();
@@ -453,6 +487,7 @@ svla_attn_bwd_dkv_kernel(const AttnBwdP p) {
       }
       __syncthreads();
       const int qt = qt_lo + it % tiles_per_head;
+      const bool plain = ab_tile_unmasked(p, qt * QT, (qt + 1) * QT, k0, k0 + 64);
       const __nv_bfloat16* cQ = sQ + buf * QT * LD;
       const __nv_bfloat16* cdO = sdO + buf * QT * LD;
       // S^T = K Q^T and dP^T = V dO^T  (16 keys x QT queries per warp)
@@ -485,7 +520,7 @@ svla_attn_bwd_dkv_kernel(const AttnBwdP p) {
           const int il = nt * 8 + 2 * t + (e & 1), i = qt * QT + il;   // query
           float c, fac;
           ab_score(p, st[nt][e], c, fac);
-          const float pr = (ab_masked(p, i, j) || i >= p.sq) ? 0.f : __expf(c - sLse[buf * QT + il]);
+          const float pr = (!plain && (ab_masked(p, i, j) || i >= p.sq)) ? 0.f : ab_exp(c - sLse[buf * QT + il]);
           pv[e] = pr;
           ds[e] = pr * (dpt[nt][e] - sDel[buf * QT + il]) * fac * p.scale;
         }
@@ -509,6 +544,10 @@ svla_attn_bwd_dkv_kernel(const AttnBwdP p) {
         }
       }
       __syncthreads();
+      if (NB == 1 && it + 1 < n_it) {
+        load_q(0, it + 1);
+        cp_async_commit();
+      }
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -536,25 +575,25 @@ int set_smem(K kernel, size_t bytes, const char* what) {
   return 0;
 }
 
-template <int DP, int KT, int QT, int DH>
+template <int DP, int KT, int QT, int DH, int NB>
 int launch_attn_bwd(const AttnBwdP& p, int batch, cudaStream_t st) {
   constexpr int LD = DP + 8;
   const size_t sm0 = static_cast<size_t>(3 * 64 * LD) * 2;
-  const size_t sm1 = static_cast<size_t>(128 + 4 * KT) * LD * 2;
-  const size_t sm2 = static_cast<size_t>(128 + 4 * QT) * LD * 2 + 4 * QT * sizeof(float);
+  const size_t sm1 = static_cast<size_t>(128 + 2 * NB * KT) * LD * 2;
+  const size_t sm2 = static_cast<size_t>(128 + 2 * NB * QT) * LD * 2 + 2 * NB * QT * sizeof(float);
   static bool configured = false;
   if (!configured) {
     if (set_smem(svla_attn_bwd_stats_kernel<DP>, sm0, "svla_attention_bwd(stats)")) return -2;
-    if (set_smem(svla_attn_bwd_dq_kernel<DP, KT>, sm1, "svla_attention_bwd(dq)")) return -2;
-    if (set_smem(svla_attn_bwd_dkv_kernel<DP, QT, DH>, sm2, "svla_attention_bwd(dkv)")) return -2;
+    if (set_smem(svla_attn_bwd_dq_kernel<DP, KT, NB>, sm1, "svla_attention_bwd(dq)")) return -2;
+    if (set_smem(svla_attn_bwd_dkv_kernel<DP, QT, DH, NB>, sm2, "svla_attention_bwd(dkv)")) return -2;
     configured = true;
   }
   const dim3 gq((p.sq + 63) / 64, p.hq, batch), gk((p.sk + 63) / 64, p.hkv, batch);
   svla_attn_bwd_stats_kernel<DP><<<gq, kAbThreads, sm0, st>>>(p);
   SVLA_LAUNCH_CHECK("svla_attn_bwd_stats");
-  svla_attn_bwd_dq_kernel<DP, KT><<<gq, kAbThreads, sm1, st>>>(p);
+  svla_attn_bwd_dq_kernel<DP, KT, NB><<<gq, kAbThreads, sm1, st>>>(p);
   SVLA_LAUNCH_CHECK("svla_attn_bwd_dq");
-  svla_attn_bwd_dkv_kernel<DP, QT, DH><<<gk, kAbThreads, sm2, st>>>(p);
+  svla_attn_bwd_dkv_kernel<DP, QT, DH, NB><<<gk, kAbThreads, sm2, st>>>(p);
   SVLA_LAUNCH_CHECK("svla_attn_bwd_dkv");
   return 0;
 }
@@ -581,9 +620,11 @@ extern "C" int svla_attention_bwd(const SvlaAttnBwdArgs* a, void* stream) {
                                p.dk_bs, p.dk_ss, p.dv_bs, p.dv_ss};
   for (long long s : strides) SVLA_REQUIRE(s % 8 == 0, "svla_attention_bwd: strides must be multiples of 8 elements (16-byte rows)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->d <= 80) return launch_attn_bwd<80, 64, 64, 80>(p, a->batch, st);
-  if (a->d <= 128) return launch_attn_bwd<128, 64, 32, 128>(p, a->batch, st);
-  return launch_attn_bwd<256, 32, 32, 128>(p, a->batch, st);
+  static const int nb_env = getenv("SVLA_ATTN_BWD_NB") ? atoi(getenv("SVLA_ATTN_BWD_NB")) : 0;      // A/B switch: 1 | 2 buffers at d = 256
+  if (a->d <= 80) return launch_attn_bwd<80, 64, 64, 80, 2>(p, a->batch, st);
+  if (a->d <= 128) return launch_attn_bwd<128, 64, 32, 128, 2>(p, a->batch, st);
+  if (nb_env == 2) return launch_attn_bwd<256, 32, 32, 128, 2>(p, a->batch, st);
+  return launch_attn_bwd<256, 32, 32, 128, 1>(p, a->batch, st);
 }
 
 extern "C" int svla_gemm_tn(const SvlaGemmTnArgs* a, void* stream) {

@@ -138,6 +138,9 @@ class LoRAStepLayout:
             self.slots[k] = (off, off + self.r * i)                     # offsets of A [r, in] and B^T [r, out]
             off += self.r * (i + o)
         self.n = off
+        # arena prefix that belongs to the language model: its gradients are complete before the vision backward starts
+        gem_keys = [a[0] for nm, fl in self.fused.items() if nm.startswith("gem.") for a in fl.adapters]
+        self.n_language = max(self.slots[k][1] + self.r * shapes[k][0] for k in gem_keys) if gem_keys else 0
         z = lambda: torch.zeros(self.n, dtype=torch.float32, device=dev)          # noqa: E731
         self.param, self.grad, self.exp_avg, self.exp_avg_sq = z(), z(), z(), z()
         g = torch.Generator().manual_seed(seed)

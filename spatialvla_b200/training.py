@@ -242,7 +242,8 @@ class LoRATrainer:
             sv["layers"][li] = None
 
     # ------------------------------------------------------------------------------------------ the step
-    def forward_backward(self, input_ids, pixel_values, intrinsic, labels, token_type_ids=None, attention_mask=None):
+    def forward_backward(self, input_ids, pixel_values, intrinsic, labels, token_type_ids=None, attention_mask=None,
+                         on_language_grads_ready=None):
         """Loss forward + full backward: fills `self.lay.grad` (sum over this rank's batch of d(mean CE)/d(adapter)).
         Mask selection as `forward(labels=...)` (model/modeling_spatialvla.py:258-306): token_type_ids -> triangular, plus the
         prefix columns when a 2-D attention_mask is passed; labels alone -> bidirectional.  Returns the fp32 [3] loss summary
@@ -291,6 +292,8 @@ class LoRATrainer:
         ops.fill_zero(dx)
         ops.rmsnorm_bwd(gsv["x_last"], e.gem["final"], dh, eps=e.t["rms_norm_eps"], row_idx=rows, dx_accum=dx)
         dx = self._gemma_bwd(gsv, dx, B, L, causal, prefix)
+        if on_language_grads_ready is not None:
+            on_language_grads_ready()            # the Gemma2 segment of the gradient arena is final: its all-reduce can start now
         # d(embeddings): only the image-token rows lead to trainable parameters (embed_tokens is frozen)
         normalizer = float(torch.tensor(H ** 0.5, dtype=F32))
         dfeat_b = ops.empty((B * 256, H), BF16)
@@ -312,8 +315,10 @@ class LoRATrainer:
         """One data-parallel training step on this rank's shard: forward/backward, ONE gradient all-reduce, clip + AdamW.
         Returns the local loss summary tensor (device)."""
         from . import parallel
+        red = parallel.GradientReducer(self.lay, self.lay.n_language, group=group)
         summary = self.forward_backward(batch["input_ids"], batch["pixel_values"], batch["intrinsic"], batch["labels"],
-                                        token_type_ids=batch.get("token_type_ids"), attention_mask=batch.get("attention_mask"))
-        parallel.allreduce_gradients(self.lay, group=group, average=False)        # the step's ONE collective (sum; averaged by AdamW's scale)
-        self.optimizer_step(world_size=parallel.world_size(group))
+                                        token_type_ids=batch.get("token_type_ids"), attention_mask=batch.get("attention_mask"),
+                                        on_language_grads_ready=red.first_segment_ready)
+        world = red.finish()                     # sums; the 1 / world average is folded into the optimizer kernel's gradient scale
+        self.optimizer_step(world_size=world)
         return summary

@@ -153,3 +153,55 @@ def test_lora_optimizer_step_on_gpu_matches_restatement(cuda_device):
     assert abs(outs[0][1] - outs[1][1]) < 1e-4 * outs[1][1]
     assert float((outs[0][0] - outs[1][0]).abs().max()) < 2e-6
     assert float((outs[1][0] - p0).abs().max()) > 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ data-parallel step (gloo, CPU)
+def _dp_worker(rank, world, port, q):
+    import sys
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from spatialvla_b200.parallel import shard_batch
+    torch.set_num_threads(2)
+    cfg, px, ids, tt, labels, K, sd, eng, tr = _setup(RefOps())
+    eng.force_head = 0                                   # ZoeDepth's router votes over the local batch: pin it for the comparison
+    B, L = ids.shape
+    batch = {"input_ids": ids, "pixel_values": px, "intrinsic": K, "labels": labels, "token_type_ids": tt,
+             "attention_mask": torch.ones(B, L, dtype=torch.int64)}
+    calls = []
+    real = dist.all_reduce
+    dist.all_reduce = lambda t, *a, **k: (calls.append(t.numel()), real(t, *a, **k))[1]
+    tr.step(shard_batch(batch, rank, world))
+    dist.all_reduce = real
+    q.put((rank, calls, tr.lay.grad.clone(), tr.lay.param.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_step_equals_single_process_step_on_the_whole_batch():
+    """World size 2 (gloo): every rank runs forward/backward on its shard, the gradient arena is exchanged in two overlapped
+    all-reduces over disjoint slices (Gemma2 segment first), AdamW divides by the world size: summed gradients / 2 equal the
+    single-process gradient of the whole batch (each sample labels the same number of tokens), and both replicas end identical."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 34500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    (_, calls0, g0, p0), (_, calls1, g1, p1) = res
+    cfg, px, ids, tt, labels, K, sd, eng, tr = _setup(RefOps())
+    eng.force_head = 0
+    B, L = ids.shape
+    tr.forward_backward(ids, px, K, labels, token_type_ids=tt, attention_mask=torch.ones(B, L, dtype=torch.int64))
+    n, n1 = tr.lay.numel(), tr.lay.n_language
+    assert 0 < n1 < n and calls0 == [n1, n - n1] and calls1 == calls0            # two collectives over disjoint slices of ONE buffer
+    assert torch.equal(g0, g1) and torch.equal(p0, p1)                           # replicas stay bit-identical
+    ref = tr.lay.grad
+    err = float((g0 / 2 - ref).abs().max()) / float(ref.abs().max())
+    assert err < 2e-2, err

@@ -190,7 +190,8 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"), timeout=datetime.timedelta(seconds=180))
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     cfg = get_config_dict(args.config)
@@ -376,7 +377,8 @@ def run_lora_step(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"), timeout=datetime.timedelta(seconds=180))
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     cfg = get_config_dict(args.config)
@@ -396,8 +398,13 @@ def run_lora_step(args):
     flush = torch.empty(256 * 2**20, dtype=torch.uint8, device=dev)
     ar_ev = []
 
-    def one_step(batch, time_ar=False):
+    def one_step(batch, time_ar=False, exchange=True):
         """= LoRATrainer.step with CUDA events around the part of the gradient exchange the compute stream has to WAIT for."""
+        if not exchange:                         # rank-0-only instrumented step: no collective (the other ranks are gone)
+            summary = tr.forward_backward(batch["input_ids"], batch["pixel_values"], batch["intrinsic"], batch["labels"],
+                                          token_type_ids=batch.get("token_type_ids"), attention_mask=batch.get("attention_mask"))
+            tr.optimizer_step(world_size=world)
+            return summary
         red = parallel.GradientReducer(tr.lay, tr.lay.n_language)
         summary = tr.forward_backward(batch["input_ids"], batch["pixel_values"], batch["intrinsic"], batch["labels"],
                                       token_type_ids=batch.get("token_type_ids"), attention_mask=batch.get("attention_mask"),
@@ -464,7 +471,7 @@ def run_lora_step(args):
     timed = TimedOps(ops)
     tr.ops = eng.ops = tr.lay.ops = timed
     torch.cuda._sleep(int(1.0 * 1.9e9))
-    one_step(batch_d)
+    one_step(batch_d, exchange=False)
     agg = timed.summary()
     tr.ops = eng.ops = tr.lay.ops = ops
     total_ms = sum(d["ms"] for d in agg.values())

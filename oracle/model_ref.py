@@ -360,7 +360,7 @@ def embed_inputs(sd, cfg, input_ids, image_feats=None):
         m = input_ids == cfg["image_token_index"]
         if int(m.sum()) * emb.shape[-1] != image_feats.numel():
             raise ValueError("Number of images does not match number of special image tokens in the input text.")
-        emb[m] = image_feats.reshape(-1, emb.shape[-1])
+        emb[m] = image_feats.reshape(-1, emb.shape[-1]).to(emb.dtype)
     return emb * torch.tensor(t["hidden_size"] ** 0.5, dtype=emb.dtype)
 
 

@@ -18,8 +18,8 @@
 //                             more than 8 (log2 units), the common case leaves O untouched in TMEM;
 //                             epilogue: O / l -> bf16 -> global.
 // TMEM budget (columns): S double buffer 2*64 | O: D | P double buffer 2*32  ->  256 (D=64, 2 CTAs/SM) / 512 (D=256).
-// Shapes on this path: BEiT d=64 (S=577, rel-pos bias), Gemma2 prefill d=256 (S=278, GQA 8:4, soft-cap).  Head dims that
-// are not a multiple of 64 (SigLIP 72, the 32-wide router) stay on the mma.sync kernel in attention.cu.
+// Shapes on this path: BEiT d=64 (S=577, rel-pos bias), Gemma2 prefill d=256 (S=278, GQA 8:4, soft-cap), and -- through the
+// zero-padding 4-D tensor maps of the PAD variant -- SigLIP d=72 (128-wide tile) and the ZoeDepth router d=32 (64-wide tile).
 // Reference ops replaced: model/modeling_gemma2.py:169-195, HF beit/modeling_beit.py:225-306,511-590.
 #include <cudaTypedefs.h>
 #include "../../include/spatialvla_b200.h"
@@ -53,7 +53,7 @@ template <int D> struct Cfg {
   static constexpr int kKBytes = kBKV * D * 2;
   // K/V ring depth: the producer may only refill a stage after P_j V_j has retired it, so with 2 stages every tile pays a full
   // TMA round trip (measured: ~2 us per 64-key tile at d=64 against ~0.15 us of MMA); d=64 has the shared memory for 4 stages
-  static constexpr int kStages = (D <= 64) ? 4 : 2;
+  static constexpr int kStages = (D <= 128) ? 4 : 2;
   static constexpr int kTmemS = 0;                            // 2 * kBKV columns
   static constexpr int kTmemO = 2 * kBKV;                     // D columns
   static constexpr int kTmemP = 2 * kBKV + D;                 // 2 * kBKV/2 columns
@@ -115,8 +115,12 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-// MODE: bit0 rel-pos bias, bit1 soft-cap, bit2 causal
-template <int D, int MODE>
+// MODE: bit0 rel-pos bias, bit1 soft-cap, bit2 causal.
+// PAD: the real head dimension p.d is SMALLER than the tile width D (SigLIP: 72 in a 128-wide tile; the ZoeDepth router: 32 in a
+// 64-wide tile).  The operands are then fetched through 4-D tensor maps {d, head, token, batch}: the box is still 64 columns wide,
+// but columns >= p.d lie outside dimension 0 of the tensor and are ZERO-FILLED by the TMA unit, so Q K^T contracts over
+// ceil(p.d / 16) k-steps of exact zeros-padded operands and P V produces round16(p.d) output columns -- no padded copies in HBM.
+template <int D, int MODE, bool PAD = false>
 __global__ void __launch_bounds__(kThreads, Cfg<D>::kCtasPerSm)
 svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                           const __grid_constant__ CUtensorMap tm_v, const Params p) {
@@ -180,22 +184,31 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     if (lane == 0) {
       mbar_expect_tx(q_full, C::kQBytes);
 #pragma unroll
-      for (int c = 0; c < C::kChunks; ++c) tma_load_3d(sQ + c * (kBQ * 128), &tm_q, q_full, h * D + c * 64, q0, b);
+      for (int c = 0; c < C::kChunks; ++c) {
+        if constexpr (PAD) tma_load_4d(sQ + c * (kBQ * 128), &tm_q, q_full, c * 64, h, q0, b);
+        else tma_load_3d(sQ + c * (kBQ * 128), &tm_q, q_full, h * D + c * 64, q0, b);
+      }
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % C::kStages;
         mbar_wait(&kv_empty[st], ((j / C::kStages) & 1) ^ 1u);
         mbar_expect_tx(&kv_full[st], 2 * C::kKBytes);
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) {
-          tma_load_3d(sK + st * C::kKBytes + c * (BKV * 128), &tm_k, &kv_full[st], hk * D + c * 64, j * BKV, b);
-          tma_load_3d(sV + st * C::kKBytes + c * (BKV * 128), &tm_v, &kv_full[st], hk * D + c * 64, j * BKV, b);
+          if constexpr (PAD) {
+            tma_load_4d(sK + st * C::kKBytes + c * (BKV * 128), &tm_k, &kv_full[st], c * 64, hk, j * BKV, b);
+            tma_load_4d(sV + st * C::kKBytes + c * (BKV * 128), &tm_v, &kv_full[st], c * 64, hk, j * BKV, b);
+          } else {
+            tma_load_3d(sK + st * C::kKBytes + c * (BKV * 128), &tm_k, &kv_full[st], hk * D + c * 64, j * BKV, b);
+            tma_load_3d(sV + st * C::kKBytes + c * (BKV * 128), &tm_v, &kv_full[st], hk * D + c * 64, j * BKV, b);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc_pv = make_idesc(kBQ, D, 1);
+      const uint32_t idesc_pv = make_idesc(kBQ, PAD ? ((p.d + 15) & ~15) : D, 1);     // P V output columns
+      const int ksteps_qk = PAD ? ((p.d + 15) >> 4) : D / 16;                         // Q K^T contraction steps
       // the last K/V tile only multiplies the 16-key groups that hold valid keys (BEiT: 577 = 9 * 64 + 1 keys)
       auto valid16 = [&](int j) { return min(BKV, (p.sk - j * BKV + 15) & ~15); };
       auto issue_pv = [&](int j) {
@@ -222,6 +235,7 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
         const uint32_t idesc_qk = make_idesc(kBQ, valid16(j), 0);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
+          if (PAD && kk >= ksteps_qk) break;
           const uint64_t da = make_kmajor_sw128_desc(qbase + (kk >> 2) * (kBQ * 128) + (kk & 3) * 32);
           const uint64_t db = make_kmajor_sw128_desc(kbase + (kk >> 2) * (BKV * 128) + (kk & 3) * 32);
           umma_bf16(tmem_base + C::kTmemS + st * BKV, da, db, idesc_qk, static_cast<uint32_t>(kk > 0));
@@ -395,14 +409,16 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     mbar_wait(&p_empty[last & 1], (last >> 1) & 1);
     tc_fence_after();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    __nv_bfloat16* og = p.out + b * p.o_bs + static_cast<long long>(qi) * p.o_ss + static_cast<long long>(h) * D;
+    __nv_bfloat16* og = p.out + b * p.o_bs + static_cast<long long>(qi) * p.o_ss + static_cast<long long>(h) * (PAD ? p.d : D);
 #pragma unroll 1
     for (int c0 = ch * DH; c0 < (ch + 1) * DH; c0 += 32) {
+      if (PAD && c0 >= p.d) break;
       uint32_t r[32];
       tmem_ld32(tmem_base + C::kTmemO + c0 + lane_addr, r);
       if (qi < p.sq) {
 #pragma unroll
         for (int v8 = 0; v8 < 4; ++v8) {
+          if (PAD && c0 + 8 * v8 >= p.d) break;
           uint4 o;
           o.x = pack_bf16x2(__uint_as_float(r[8 * v8 + 0]) * inv, __uint_as_float(r[8 * v8 + 1]) * inv);
           o.y = pack_bf16x2(__uint_as_float(r[8 * v8 + 2]) * inv, __uint_as_float(r[8 * v8 + 3]) * inv);
@@ -449,7 +465,22 @@ static int encode_tokens(CUtensorMap* tm, const void* base, uint64_t cols, uint6
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 100;
 }
 
-template <int D, int MODE>
+// 4-D view {d, head, tokens, batch} of the same activation: columns past the real head dimension are out of bounds -> zero fill
+static int encode_tokens_padded(CUtensorMap* tm, const void* base, uint64_t d, uint64_t heads, uint64_t tokens, uint64_t batch,
+                                uint64_t token_stride, uint64_t batch_stride, uint32_t box_rows) {
+  auto fn = encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[4] = {d, heads, tokens, batch};
+  cuuint64_t strides[3] = {d * 2, token_stride * 2, batch_stride * 2};
+  cuuint32_t box[4] = {64, 1, box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 100;
+}
+
+template <int D, int MODE, bool PAD = false>
 static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, int batch, cudaStream_t st) {
   using C = Cfg<D>;
   const int nrel = (MODE & 1) ? (2 * p.win - 1) * (2 * p.win - 1) + 3 : 0;
@@ -457,7 +488,7 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
   const size_t smem = C::kSmemBytes + 4 * kBQ * 4 + ((MODE & 1) ? static_cast<size_t>(n_tiles_all) * kBKV * 4 : 0) + static_cast<size_t>(nrel) * 4;
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(svla_flash_attn_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(svla_flash_attn_tc_kernel<D, MODE, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {
       svla_set_error("svla_attention(tcgen05): smem opt-in %zu failed: %s", smem, cudaGetErrorString(e));
       return -2;
@@ -465,7 +496,7 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
     configured = smem;
   }
   dim3 grid((p.sq + kBQ - 1) / kBQ, p.hq, batch);
-  svla_flash_attn_tc_kernel<D, MODE><<<grid, kThreads, smem, st>>>(tq, tk, tv, p);
+  svla_flash_attn_tc_kernel<D, MODE, PAD><<<grid, kThreads, smem, st>>>(tq, tk, tv, p);
   SVLA_LAUNCH_CHECK("svla_flash_attn_tc");
   return 0;
 }
@@ -478,7 +509,9 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
 int svla_attention_tc_try(const SvlaAttnArgs* a, void* stream) {
   using namespace svla_attn_tc;
   const int mode = (a->relpos_table ? 1 : 0) | (a->softcap > 0.f ? 2 : 0) | (a->causal ? 4 : 0);
-  if (!((a->d == 64 && (mode == 1 || mode == 0)) || (a->d == 256 && (mode == 2 || mode == 6)))) return 1;
+  // head dims that are not a tile width (SigLIP 72, router 32): zero-padded by the TMA unit inside a 128- / 64-wide tile
+  const bool padded = mode == 0 && a->d != 64 && a->d <= 128 && (a->d % 8) == 0 && !a->kv_start;
+  if (!padded && !((a->d == 64 && (mode == 1 || mode == 0)) || (a->d == 256 && (mode == 2 || mode == 6)))) return 1;
   if ((a->q_ss % 8) || (a->k_ss % 8) || (a->v_ss % 8) || (a->q_bs % 8) || (a->k_bs % 8) || (a->v_bs % 8) || (a->o_ss % 8) || (a->o_bs % 8)) return 1;
   if ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) | reinterpret_cast<uintptr_t>(a->v) |
        reinterpret_cast<uintptr_t>(a->out)) & 15) return 1;
@@ -494,6 +527,14 @@ int svla_attention_tc_try(const SvlaAttnArgs* a, void* stream) {
   auto bstride = [&](int64_t bs, int64_t ss, int s) { return static_cast<uint64_t>(nb > 1 ? bs : ss * s); };
   if (nb > 1 && (a->q_bs <= 0 || a->k_bs <= 0 || a->v_bs <= 0)) return 1;
   CUtensorMap tq, tk, tv;
+  if (padded) {
+    const uint64_t dd = static_cast<uint64_t>(a->d);
+    if (encode_tokens_padded(&tq, a->q, dd, a->hq, a->sq, nb, a->q_ss, bstride(a->q_bs, a->q_ss, a->sq), kBQ) != 0) return 1;
+    if (encode_tokens_padded(&tk, a->k, dd, a->hkv, a->sk, nb, a->k_ss, bstride(a->k_bs, a->k_ss, a->sk), kBKV) != 0) return 1;
+    if (encode_tokens_padded(&tv, a->v, dd, a->hkv, a->sk, nb, a->v_ss, bstride(a->v_bs, a->v_ss, a->sk), kBKV) != 0) return 1;
+    cudaStream_t stp = static_cast<cudaStream_t>(stream);
+    return a->d < 64 ? launch<64, 0, true>(tq, tk, tv, p, a->batch, stp) : launch<128, 0, true>(tq, tk, tv, p, a->batch, stp);
+  }
   if (encode_tokens(&tq, a->q, static_cast<uint64_t>(a->hq) * a->d, a->sq, nb, a->q_ss, bstride(a->q_bs, a->q_ss, a->sq), kBQ) != 0) return 1;
   if (encode_tokens(&tk, a->k, static_cast<uint64_t>(a->hkv) * a->d, a->sk, nb, a->k_ss, bstride(a->k_bs, a->k_ss, a->sk), kBKV) != 0) return 1;
   if (encode_tokens(&tv, a->v, static_cast<uint64_t>(a->hkv) * a->d, a->sk, nb, a->v_ss, bstride(a->v_bs, a->v_ss, a->sk), kBKV) != 0) return 1;

@@ -123,6 +123,10 @@ typedef struct SvlaAttnArgs {
   int32_t causal_prefix;     /* with causal = 1: keys j < causal_prefix are visible to EVERY query (prefix-LM mask of the
                                 training forward: token_type_ids == 0 columns unmasked on top of the triangular mask,
                                 model/modeling_spatialvla.py:292-305); 0 = plain causal */
+  float* lse;                /* NULL, or fp32 [batch, hq, lse_stride] (lse_stride >= sq): the kernel also writes log2(sum_j 2^(s_ij)) of every
+                                query row, s = log2(e) * (soft-capped, scaled, masked score) -- what svla_attention_bwd needs from the
+                                forward pass.  Only the tcgen05 kernels provide it (every shape of the training step). */
+  int64_t lse_stride;
 } SvlaAttnArgs;
 
 int svla_attention(const SvlaAttnArgs* args, void* stream);
@@ -282,6 +286,11 @@ typedef struct SvlaAttnBwdArgs {
   int32_t batch, hq, hkv, sq, sk, d;
   float scale, softcap;
   int32_t causal, causal_prefix;
+  const float* fwd_lse2;     /* NULL, or the forward kernel's `lse` output (log2 domain), fp32 [batch, hq, lse_stride]: the backward then runs on
+                                the tcgen05 kernels (csrc/attention_bwd_tc.cu: dQ, dK and dV sweeps with TMEM accumulators) and `lse` / `delta`
+                                must be fp32 [batch, hq, lse_stride] scratch (delta is written, lse unused); NULL = the warp-MMA kernels, which
+                                recompute the row statistics themselves */
+  int64_t lse_stride;
 } SvlaAttnBwdArgs;
 int svla_attention_bwd(const SvlaAttnBwdArgs* args, void* stream);
 

@@ -190,7 +190,7 @@ class RefOps:
         t.zero_()
 
     def attention_bwd(self, q, k, v, out, dout, dq, dk, dv, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
-                      do_strides, dq_strides, dk_strides, dv_strides, scale, softcap=0.0, causal=False, causal_prefix=0):
+                      do_strides, dq_strides, dk_strides, dv_strides, scale, softcap=0.0, causal=False, causal_prefix=0, lse=None):
         from .backward_ref import softcap_attention_bwd
         self.launches += 3
         Q = self._strided(q, q_strides[0], q_strides[1], batch, sq, hq, d).float().permute(0, 2, 1, 3)
@@ -255,7 +255,7 @@ class RefOps:
 
     def attention(self, q, k, v, out, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
                   scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0, relpos_head_major=False, kv_start=None,
-                  causal_prefix=0):
+                  causal_prefix=0, lse=None):
         self.launches += 1
         Q = self._strided(q, *q_strides, batch, sq, hq, d).float().permute(0, 2, 1, 3)
         K = self._strided(k, *k_strides, batch, sk, hkv, d).float().permute(0, 2, 1, 3).repeat_interleave(hq // hkv, 1)
@@ -279,6 +279,8 @@ class RefOps:
         e = torch.exp(s - mx)
         o = (e.to(BF16).float() @ V) / e.sum(-1, keepdim=True)
         self._strided(out, *o_strides, batch, sq, hq, d).copy_(o.permute(0, 2, 1, 3).to(BF16))
+        if lse is not None:                      # log2-domain log-sum-exp of every row, kept for the backward pass
+            lse[:, :, :sq] = torch.logsumexp(s, -1) * 1.4426950408889634
 
     def decode_attention(self, q, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, scale, softcap=0.0, kv_start=None):
         self.launches += 1

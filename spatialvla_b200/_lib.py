@@ -12,8 +12,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "lib", "libspatialvla_b200.so")
-SOURCES = ["capi.cu", "gemm_tcgen05.cu", "gemm_skinny.cu", "attention.cu", "attention_tc.cu", "decode_small.cu", "fused_ops.cu",
-           "tokenizer.cu", "image_ops.cu", "train_ops.cu", "train_mma.cu"]
+SOURCES = ["capi.cu", "gemm_tcgen05.cu", "gemm_skinny.cu", "attention.cu", "attention_tc.cu", "attention_bwd_tc.cu", "decode_small.cu",
+           "fused_ops.cu", "tokenizer.cu", "image_ops.cu", "train_ops.cu", "train_mma.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -52,7 +52,7 @@ class SvlaAttnArgs(C.Structure):
         ("batch", C.c_int32), ("hq", C.c_int32), ("hkv", C.c_int32), ("sq", C.c_int32), ("sk", C.c_int32),
         ("d", C.c_int32), ("scale", C.c_float), ("softcap", C.c_float), ("causal", C.c_int32),
         ("relpos_table", C.c_void_p), ("relpos_win", C.c_int32), ("relpos_head_major", C.c_int32),
-        ("kv_start", C.c_void_p), ("causal_prefix", C.c_int32),
+        ("kv_start", C.c_void_p), ("causal_prefix", C.c_int32), ("lse", C.c_void_p), ("lse_stride", C.c_int64),
     ]
 
 
@@ -66,6 +66,7 @@ class SvlaAttnBwdArgs(C.Structure):
         ("lse", C.c_void_p), ("delta", C.c_void_p),
         ("batch", C.c_int32), ("hq", C.c_int32), ("hkv", C.c_int32), ("sq", C.c_int32), ("sk", C.c_int32), ("d", C.c_int32),
         ("scale", C.c_float), ("softcap", C.c_float), ("causal", C.c_int32), ("causal_prefix", C.c_int32),
+        ("fwd_lse2", C.c_void_p), ("lse_stride", C.c_int64),
     ]
 
 

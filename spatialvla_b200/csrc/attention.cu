@@ -710,6 +710,7 @@ extern "C" int svla_attention(const SvlaAttnArgs* a, void* stream) {
     const int rc = svla_attention_tc_try(a, stream);      // 1 = shape not covered by the tcgen05 kernel
     if (rc != 1) return rc;
   }
+  SVLA_REQUIRE(!a->lse, "svla_attention: the row log-sum-exp output is provided by the tcgen05 kernels only (d=%d, this shape fell back)", a->d);
   AttnP p;
   p.q = static_cast<const __nv_bfloat16*>(a->q); p.k = static_cast<const __nv_bfloat16*>(a->k);
   p.v = static_cast<const __nv_bfloat16*>(a->v); p.out = static_cast<__nv_bfloat16*>(a->out);

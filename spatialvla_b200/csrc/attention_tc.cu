@@ -45,6 +45,8 @@ struct Params {
   int head_major;      // relpos is [hq][nrel] (coalesced per-head row) instead of HF's [nrel][hq]
   const int* kv_start; // [batch] or null: keys < kv_start[b] are masked (left-padded prompts)
   int prefix;          // causal only: keys < prefix are visible to every query (prefix-LM training mask)
+  float* lse;          // null or fp32 [batch, hq, lse_stride]: log2-domain logsumexp of every query row (kept for the backward pass)
+  long long lse_stride;
 };
 
 template <int D> struct Cfg {
@@ -405,6 +407,9 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     sXch[ch * kBQ + row] = l_run;
     pair_sync();
     l_run += sXch[(ch ^ 1) * kBQ + row];
+    // training: keep log2-sum-exp of the row (scores are in the log2 domain; m_run is the -- possibly stale -- max l_run refers to)
+    if (p.lse && ch == 0 && qi < p.sq)
+      p.lse[(static_cast<long long>(b) * p.hq + h) * p.lse_stride + qi] = (l_run > 0.f) ? m_run + log2f(l_run) : -INFINITY;
     const int last = n_tiles - 1;
     mbar_wait(&p_empty[last & 1], (last >> 1) & 1);
     tc_fence_after();
@@ -522,6 +527,8 @@ int svla_attention_tc_try(const SvlaAttnArgs* a, void* stream) {
   p.hq = a->hq; p.hkv = a->hkv; p.sq = a->sq; p.sk = a->sk; p.d = a->d;
   p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.relpos = a->relpos_table; p.win = a->relpos_win; p.head_major = a->relpos_head_major; p.kv_start = a->kv_start;
   p.prefix = a->causal ? a->causal_prefix : 0;
+  p.lse = a->lse;
+  p.lse_stride = a->lse_stride;
   // a batch stride of 0 is not expressible in a tensor map; batch == 1 problems get a dummy stride
   const uint64_t nb = static_cast<uint64_t>(a->batch);
   auto bstride = [&](int64_t bs, int64_t ss, int s) { return static_cast<uint64_t>(nb > 1 ? bs : ss * s); };

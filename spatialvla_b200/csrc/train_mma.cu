@@ -11,6 +11,7 @@
 //     dimension, split over CTAs, accumulated with fp32 reductions straight into the gradient arena.
 // Warp-level mma.sync (bf16 in, fp32 accumulate): these are ~6 % of the step's FLOPs; the dX GEMMs run on the tcgen05 kernel.
 #include <cstdlib>
+#include <cstring>
 #include "mma_sync.cuh"
 
 namespace {
@@ -600,8 +601,19 @@ int launch_attn_bwd(const AttnBwdP& p, int batch, cudaStream_t st) {
 
 }  // namespace
 
+int svla_attention_bwd_tc_try(const SvlaAttnBwdArgs* a, void* stream);      // attention_bwd_tc.cu (tcgen05 / TMEM / TMA)
+
 extern "C" int svla_attention_bwd(const SvlaAttnBwdArgs* a, void* stream) {
   SVLA_REQUIRE(a && a->q && a->k && a->v && a->out && a->dout && a->dq && a->dk && a->dv && a->lse && a->delta, "svla_attention_bwd: null pointer");
+  {
+    // SVLA_ATTN_IMPL=mma forces the warp-MMA kernels (A/B measurements); they are also the fallback for shapes the tcgen05 sweeps do
+    // not cover and for callers without the forward pass's log-sum-exp
+    static const bool force_mma = getenv("SVLA_ATTN_IMPL") && strcmp(getenv("SVLA_ATTN_IMPL"), "mma") == 0;
+    if (!force_mma && a->fwd_lse2) {
+      const int rc = svla_attention_bwd_tc_try(a, stream);
+      if (rc != 1) return rc;
+    }
+  }
   SVLA_REQUIRE(a->batch > 0 && a->hq > 0 && a->hkv > 0 && a->hq % a->hkv == 0 && a->sq > 0 && a->sk > 0, "svla_attention_bwd: bad shape");
   SVLA_REQUIRE(a->d % 8 == 0 && a->d <= 256, "svla_attention_bwd: head dim %d unsupported (multiple of 8, <= 256)", a->d);
   SVLA_REQUIRE(a->batch <= 65535 && a->hq <= 65535, "svla_attention_bwd: grid limits");

@@ -173,16 +173,22 @@ class CudaOps:
         L.check(self.lib.svla_fill_zero(_ptr(t), t.numel() * t.element_size(), self._stream()), "svla_fill_zero")
 
     def attention_bwd(self, q, k, v, out, dout, dq, dk, dv, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
-                      do_strides, dq_strides, dk_strides, dv_strides, scale, softcap=0.0, causal=False, causal_prefix=0):
-        """Backward of `attention` (no relpos / kv_start): strides = (batch stride, token stride) in elements, head h at column h*d."""
+                      do_strides, dq_strides, dk_strides, dv_strides, scale, softcap=0.0, causal=False, causal_prefix=0, lse=None):
+        """Backward of `attention` (no relpos / kv_start): strides = (batch stride, token stride) in elements, head h at column h*d.
+        lse: the forward call's `lse` output -> the tcgen05 sweeps (dQ, dK, dV); None -> warp-MMA kernels that recompute it."""
         a = L.SvlaAttnBwdArgs()
         for t in (q, k, v, out, dout, dq, dk, dv):
             _req(t.dtype == BF16, "attention_bwd: bf16 only")
         a.q, a.k, a.v, a.out, a.dout, a.dq, a.dk, a.dv = (_ptr(t) for t in (q, k, v, out, dout, dq, dk, dv))
         (a.q_bs, a.q_ss), (a.k_bs, a.k_ss), (a.v_bs, a.v_ss), (a.o_bs, a.o_ss) = q_strides, k_strides, v_strides, o_strides
         (a.do_bs, a.do_ss), (a.dq_bs, a.dq_ss), (a.dk_bs, a.dk_ss), (a.dv_bs, a.dv_ss) = do_strides, dq_strides, dk_strides, dv_strides
-        stats = torch.empty((2, batch, hq, sq), dtype=F32, device=self.device)
+        sp = int(lse.shape[2]) if lse is not None else sq
+        stats = torch.empty((2, batch, hq, sp), dtype=F32, device=self.device)
         a.lse, a.delta = _ptr(stats[0]), _ptr(stats[1])
+        if lse is not None:
+            _req(lse.dtype == F32 and lse.dim() == 3 and lse.is_contiguous() and lse.shape[0] == batch and lse.shape[1] == hq and sp >= sq,
+                 "attention_bwd: lse must be the forward's fp32 [batch, hq, >= sq]")
+            a.fwd_lse2, a.lse_stride = _ptr(lse), sp
         a.batch, a.hq, a.hkv, a.sq, a.sk, a.d = batch, hq, hkv, sq, sk, d
         a.scale, a.softcap, a.causal, a.causal_prefix = float(scale), float(softcap or 0.0), int(bool(causal)), int(causal_prefix)
         L.check(self.lib.svla_attention_bwd(C.byref(a), self._stream()), "svla_attention_bwd")
@@ -233,8 +239,9 @@ class CudaOps:
     # ---- G2 / G3
     def attention(self, q, k, v, out, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
                   scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0, relpos_head_major=False, kv_start=None,
-                  causal_prefix=0):
+                  causal_prefix=0, lse=None):
         """strides = (batch stride, token stride) in elements; head h lives at column offset h*d.
+        lse: fp32 [batch, hq, >= sq] -- the kernel also stores the log2-domain log-sum-exp of every query row (training forward).
         relpos_table: fp32 [(2*win-1)^2+3, hq] (HF layout) or, with relpos_head_major, its transpose [hq, (2*win-1)^2+3]."""
         a = L.SvlaAttnArgs()
         for t in (q, k, v, out):
@@ -254,6 +261,10 @@ class CudaOps:
         a.kv_start = _ptr(kv_start)
         _req(causal_prefix == 0 or (causal and 0 < causal_prefix <= sk), "attention: causal_prefix needs causal=True and 0 < prefix <= sk")
         a.causal_prefix = int(causal_prefix)       # prefix-LM: keys < causal_prefix visible to every query
+        if lse is not None:
+            _req(lse.dtype == F32 and lse.dim() == 3 and lse.is_contiguous() and lse.shape[0] == batch and lse.shape[1] == hq and lse.shape[2] >= sq,
+                 "attention: lse must be fp32 [batch, hq, >= sq]")
+            a.lse, a.lse_stride = _ptr(lse), int(lse.shape[2])
         L.check(self.lib.svla_attention(C.byref(a), self._stream()), "svla_attention")
 
     def decode_attention(self, q, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, scale, softcap=0.0, kv_start=None):

@@ -94,9 +94,10 @@ class LoRATrainer:
             ops.layernorm(x, L_["ln1_g"], L_["ln1_b"], eps, out_bf16=c["h1"])
             c["qkv"], c["u_qkv"] = self._lin_fwd(c["h1"], L_["wqkv"], F_[f"sig.{li}.qkv"], M, bias=L_["bqkv"])
             c["ctx"] = ops.empty((M, D), BF16)
+            c["lse"] = ops.empty((B, nh, (S + 63) // 64 * 64), F32)      # row log-sum-exp of the forward, read by the backward sweeps
             qkv = c["qkv"]
             ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], c["ctx"], batch=B, hq=nh, hkv=nh, sq=S, sk=S, d=hd, q_strides=st, k_strides=st,
-                          v_strides=st, o_strides=(S * D, D), scale=hd ** -0.5)
+                          v_strides=st, o_strides=(S * D, D), scale=hd ** -0.5, lse=c["lse"])
             c["x_mid"], c["u_o"] = self._lin_fwd(c["ctx"], L_["wo"], F_[f"sig.{li}.o"], M, out_dtype=F32, bias=L_["bo"], res_f32=x)
             c["h2"] = ops.empty((M, D), BF16)
             ops.layernorm(c["x_mid"], L_["ln2_g"], L_["ln2_b"], eps, out_bf16=c["h2"])
@@ -152,9 +153,10 @@ class LoRATrainer:
             c["q"] = ops.empty((M, nh * hd), BF16)
             ops.rope_kv(qkv, c["q"], c["kc"], c["vc"], batch=B, s=S, hq=nh, hkv=nkv, d=hd, smax=S, pos0=0, theta=theta)
             c["ctx"] = ops.empty((M, nh * hd), BF16)
+            c["lse"] = ops.empty((B, nh, (S + 63) // 64 * 64), F32)
             ops.attention(c["q"], c["kc"], c["vc"], c["ctx"], batch=B, hq=nh, hkv=nkv, sq=S, sk=S, d=hd, q_strides=(S * nh * hd, nh * hd),
                           k_strides=kvs, v_strides=kvs, o_strides=(S * nh * hd, nh * hd), scale=scale, softcap=cap, causal=causal,
-                          causal_prefix=prefix if causal else 0)
+                          causal_prefix=prefix if causal else 0, lse=c["lse"])
             c["br"], c["u_o"] = self._lin_fwd(c["ctx"], L_["wo"], F_[f"gem.{li}.o"], M, out_dtype=F32)
             c["x_mid"], c["h2"] = ops.empty((M, H), F32), ops.empty((M, H), BF16)
             ops.rmsnorm_train_fwd(x, branch=c["br"], w_post=L_["ln_post_attn"], w_pre=L_["ln_pre_ff"], eps=eps, x_out=c["x_mid"], h=c["h2"])
@@ -197,7 +199,7 @@ class LoRATrainer:
             ops.attention_bwd(c["q"], c["kc"], c["vc"], c["ctx"], dctx, dqkv, dqkv[:, nh * hd:], dqkv[:, (nh + nkv) * hd:], batch=B, hq=nh,
                               hkv=nkv, sq=S, sk=S, d=hd, q_strides=qs, k_strides=kvs, v_strides=kvs, o_strides=qs, do_strides=qs,
                               dq_strides=(S * Wd, Wd), dk_strides=(S * Wd, Wd), dv_strides=(S * Wd, Wd), scale=scale, softcap=cap,
-                              causal=causal, causal_prefix=prefix if causal else 0)
+                              causal=causal, causal_prefix=prefix if causal else 0, lse=c["lse"])
             ops.rope_bwd(dqkv, batch=B, s=S, hq=nh, hkv=nkv, d=hd, theta=theta)
             dh1 = self._lin_bwd(dqkv, T_["wqkv"], F_[f"gem.{li}.qkv"], c["h1"], c["u_qkv"], M)
             ops.rmsnorm_bwd(c["x_in"], L_["ln_in"], dh1, eps=eps, dx_accum=dx)
@@ -234,7 +236,7 @@ class LoRATrainer:
             qkv = c["qkv"]
             ops.attention_bwd(qkv, qkv[:, D:], qkv[:, 2 * D:], c["ctx"], dctx, dqkv, dqkv[:, D:], dqkv[:, 2 * D:], batch=B, hq=nh, hkv=nh,
                               sq=S, sk=S, d=hd, q_strides=st, k_strides=st, v_strides=st, o_strides=os_, do_strides=os_, dq_strides=st,
-                              dk_strides=st, dv_strides=st, scale=hd ** -0.5)
+                              dk_strides=st, dv_strides=st, scale=hd ** -0.5, lse=c["lse"])
             last = li == 0                       # nothing trainable below the first block (the patch embedding is not a LoRA target)
             dh1 = self._lin_bwd(dqkv, T_["wqkv"], F_[f"sig.{li}.qkv"], c["h1"], c["u_qkv"], M, need_dx=not last)
             if not last:

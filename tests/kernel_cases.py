@@ -888,7 +888,7 @@ def train_elementwise_case(dev="cuda:0"):
     return res
 
 
-def attn_bwd_case(name, B, hq, hkv, sq, sk, d, *, softcap=0.0, causal=False, prefix=0, seed=0):
+def attn_bwd_case(name, B, hq, hkv, sq, sk, d, *, softcap=0.0, causal=False, prefix=0, seed=0, with_lse=True):
     """svla_attention_bwd (3 launches) vs the closed form oracle/backward_ref.softcap_attention_bwd (itself pinned on autograd);
     q/k/v packed like the step's tensors (q in its own tensor, k / v as rows of a [B, sk, hkv, d] cache, gradients as column blocks
     of one [tokens, (hq + 2 hkv) d] tensor)."""
@@ -904,18 +904,24 @@ def attn_bwd_case(name, B, hq, hkv, sq, sk, d, *, softcap=0.0, causal=False, pre
             Q, K, V, dO = to(q), to(kc), to(vc), to(dout)
             out = ops.zeros((B * sq, hq * d), BF16)
             kvs = (sk * hkv * d, hkv * d)
+            # with_lse: the forward keeps the row log-sum-exp and the backward runs the tcgen05 sweeps; without: warp-MMA kernels
+            lse = ops.zeros((B, hq, (sq + 63) // 64 * 64), F32) if with_lse else None
             ops.attention(Q, K, V, out, batch=B, hq=hq, hkv=hkv, sq=sq, sk=sk, d=d, q_strides=(sq * hq * d, hq * d), k_strides=kvs,
-                          v_strides=kvs, o_strides=(sq * hq * d, hq * d), scale=scale, softcap=softcap, causal=causal, causal_prefix=prefix)
+                          v_strides=kvs, o_strides=(sq * hq * d, hq * d), scale=scale, softcap=softcap, causal=causal, causal_prefix=prefix,
+                          lse=lse)
             assert sq == sk
             dqkv = ops.zeros((B * sq, W), BF16) + 5.0                       # poison: every element must be written
             ops.attention_bwd(Q, K, V, out, dO, dqkv, dqkv[:, hq * d:], dqkv[:, (hq + hkv) * d:], batch=B, hq=hq, hkv=hkv, sq=sq, sk=sk,
                               d=d, q_strides=(sq * hq * d, hq * d), k_strides=kvs, v_strides=kvs, o_strides=(sq * hq * d, hq * d),
                               do_strides=(sq * hq * d, hq * d), dq_strides=(sq * W, W), dk_strides=(sk * W, W), dv_strides=(sk * W, W),
-                              scale=scale, softcap=softcap, causal=causal, causal_prefix=prefix)
-            return dqkv
+                              scale=scale, softcap=softcap, causal=causal, causal_prefix=prefix, lse=lse)
+            return dqkv if lse is None else (dqkv, lse)
         c, r = _both(run, dev)
-        c, r = c.float().cpu(), r.float()
         res = Result(name)
+        if with_lse:
+            (c, cl), (r, rl) = c, r
+            res.add("fwd_lse2", float((cl.cpu()[:, :, :sq] - rl[:, :, :sq]).abs().max()), 3e-2)       # bf16 operands, log2 units
+        c, r = c.float().cpu(), r.float()
         for nm, lo, hi in (("dq", 0, hq * d), ("dk", hq * d, (hq + hkv) * d), ("dv", (hq + hkv) * d, W)):
             res.add(nm, float((c[:, lo:hi] - r[:, lo:hi]).abs().max()) / max(float(r[:, lo:hi].abs().max()), 1e-20), 2e-2)
         return res
@@ -924,12 +930,20 @@ def attn_bwd_case(name, B, hq, hkv, sq, sk, d, *, softcap=0.0, causal=False, pre
 
 
 ATTN_BWD_CASES = [
+    # warp-MMA kernels (no forward log-sum-exp): the fallback path
+    attn_bwd_case("attn_bwd_mma_gemma_prefixlm", 2, 4, 2, 291, 291, 256, softcap=50.0, causal=True, prefix=278, with_lse=False),
+    attn_bwd_case("attn_bwd_mma_siglip_d72", 2, 4, 4, 256, 256, 72, with_lse=False),
+    attn_bwd_case("attn_bwd_mma_d64_causal_prefix", 2, 4, 1, 200, 200, 64, causal=True, prefix=50, softcap=20.0, with_lse=False),
+    # tcgen05 sweeps (dQ / dK / dV) fed by the forward kernel's log-sum-exp
+    attn_bwd_case("attn_bwd_tiny_tile", 1, 1, 1, 40, 40, 64),
+    attn_bwd_case("attn_bwd_two_tiles_d64", 1, 2, 2, 128, 128, 64),
+    attn_bwd_case("attn_bwd_gqa4_d256", 1, 4, 1, 150, 150, 256, softcap=50.0, causal=True, prefix=30),
     attn_bwd_case("attn_bwd_gemma_prefixlm", 2, 4, 2, 291, 291, 256, softcap=50.0, causal=True, prefix=278),
     attn_bwd_case("attn_bwd_gemma_causal", 1, 8, 4, 130, 130, 256, softcap=50.0, causal=True),
     attn_bwd_case("attn_bwd_gemma_bidirectional", 2, 2, 2, 77, 77, 256, softcap=50.0),
     attn_bwd_case("attn_bwd_siglip_d72", 2, 16, 16, 256, 256, 72),
     attn_bwd_case("attn_bwd_d72_ragged", 3, 2, 2, 100, 100, 72),
-    attn_bwd_case("attn_bwd_d64_causal_prefix", 2, 4, 1, 200, 200, 64, causal=True, prefix=50, softcap=20.0),
+    attn_bwd_case("attn_bwd_d64_gqa_ragged", 2, 4, 1, 200, 200, 64),
     attn_bwd_case("attn_bwd_d128", 1, 2, 2, 96, 96, 128),
 ]
 

@@ -41,7 +41,8 @@ def test_gemm_args_struct_matches_header_layout():
     assert L.SvlaGemmArgs.a2.offset == 17 * 8 + 10 * 4 and C.sizeof(L.SvlaGemmArgs) == 17 * 8 + 10 * 4 + 5 * 8       # K extension appended
     assert L.SvlaGemmTnArgs.groups.offset == 56 and C.sizeof(L.SvlaTnGroup) == 40 and L.SvlaAttnBwdArgs.lse.offset == 24 * 8
     assert L.SvlaAttnArgs.batch.offset == 12 * 8
-    assert L.SvlaAttnArgs.kv_start.offset == 152 and L.SvlaAttnArgs.causal_prefix.offset == 160 and C.sizeof(L.SvlaAttnArgs) == 168
+    assert L.SvlaAttnArgs.kv_start.offset == 152 and L.SvlaAttnArgs.causal_prefix.offset == 160 and L.SvlaAttnArgs.lse.offset == 168
+    assert C.sizeof(L.SvlaAttnArgs) == 184 and L.SvlaAttnBwdArgs.fwd_lse2.offset == 26 * 8 + 10 * 4 and C.sizeof(L.SvlaAttnBwdArgs) == 26 * 8 + 40 + 16
 
 
 def test_validation_errors_before_any_cuda_call(lib):

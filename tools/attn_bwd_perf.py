@@ -39,13 +39,15 @@ def main():
         kvs, qs = (S * hkv * d, hkv * d), (S * hq * d, hq * d)
         kw = dict(batch=B, hq=hq, hkv=hkv, sq=S, sk=S, d=d, q_strides=qs, k_strides=kvs, v_strides=kvs, o_strides=qs, scale=d ** -0.5,
                   softcap=cap, causal=causal, causal_prefix=prefix)
-        ops.attention(q, kc, vc, o, **kw)
-        fwd = timeit(lambda: ops.attention(q, kc, vc, o, **kw))
-        bwd = timeit(lambda: ops.attention_bwd(q, kc, vc, o, do, dqkv, dqkv[:, hq * d:], dqkv[:, (hq + hkv) * d:], do_strides=qs,
-                                               dq_strides=(S * W, W), dk_strides=(S * W, W), dv_strides=(S * W, W), **kw))
+        lse = torch.zeros(B, hq, (S + 63) // 64 * 64, device="cuda")
+        ops.attention(q, kc, vc, o, lse=lse, **kw)
+        fwd = timeit(lambda: ops.attention(q, kc, vc, o, lse=lse, **kw))
+        bw = dict(do_strides=qs, dq_strides=(S * W, W), dk_strides=(S * W, W), dv_strides=(S * W, W), **kw)
+        bwd_mma = timeit(lambda: ops.attention_bwd(q, kc, vc, o, do, dqkv, dqkv[:, hq * d:], dqkv[:, (hq + hkv) * d:], **bw))
+        bwd_tc = timeit(lambda: ops.attention_bwd(q, kc, vc, o, do, dqkv, dqkv[:, hq * d:], dqkv[:, (hq + hkv) * d:], lse=lse, **bw))
         fl = 4.0 * B * hq * S * S * d
-        out.append({"case": name, "fwd_ms": round(fwd, 4), "fwd_tflops": round(fl / fwd / 1e9, 1), "bwd_ms": round(bwd, 4),
-                    "bwd_tflops_5units": round(2.5 * fl / bwd / 1e9, 1)})
+        out.append({"case": name, "fwd_ms": round(fwd, 4), "fwd_tflops": round(fl / fwd / 1e9, 1), "bwd_mma_ms": round(bwd_mma, 4),
+                    "bwd_tcgen05_ms": round(bwd_tc, 4), "bwd_tcgen05_tflops_5units": round(2.5 * fl / bwd_tc / 1e9, 1)})
     for (M, r, n) in ((9312, 64, 18432), (9312, 96, 4096), (9312, 32, 2304), (8192, 32, 1152), (8192, 32, 4304)):
         s, y = torch.randn(M, (r + 63) // 64 * 64, device="cuda").to(BF16), torch.randn(M, n, device="cuda").to(BF16)
         dst = torch.zeros(r, n, device="cuda")

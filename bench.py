@@ -516,6 +516,10 @@ def run_lora_step(args):
     ms_per_step = ms / args.steps
     value = world * B / (ms_per_step / 1e3)
     loss = float(summary[0])
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms_per_step, "gpu_launches": int(launches), "note": "profiling aid, not a bench value"}))
+        return
     # ---- e2e: the public training call with HOST batches: H2D of the batch + D2H of the loss inside the timed region
     for _ in range(2):
         float(tr.step(batch_h)[0])

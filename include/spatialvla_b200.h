@@ -145,24 +145,30 @@ int svla_decode_attention_fused(const float* qkv_f32, int n_partials, int64_t pa
                                 void* out, int batch, int hq, int hkv, int d, int smax, int ctx, float theta, float scale,
                                 float softcap, const int32_t* kv_start, void* stream);
 
-/* G4: one whole Gemma2 decode step (all layers) for SMALL batches (batch in {1, 2, 4}) in ONE persistent launch: one CTA per SM,
- * every projection a weight-streaming GEMV over all SMs, phases separated by grid barriers (model/modeling_gemma2.py:364-413,
- * 451-506,680-793).  Replaces the 7-launches-per-layer chain of the batched path where per-launch fixed cost, not HBM time,
- * bounds the step (BASELINE.json "p50 latency at bs=1").
- * layers_dev: DEVICE array of n_layers descriptors (device pointers; wgu rows interleaved gate_j / up_j like svla_gemm GEGLU;
- * kcache/vcache bf16 [B, smax, hkv, d] of that layer).  x fp32 [B, hidden]: the embedded token times sqrt(hidden) (clobbered).
- * h_out bf16 [B, hidden]: final-normed hidden state.  scratch: svla_decode_step_small_scratch_floats(...) floats of device
- * memory.  ctx = number of cache slots after this step (the new token sits at slot ctx-1, RoPE position ctx - kv_start[b]). */
-typedef struct SvlaDecodeLayer {
-  const void* wqkv; const void* wo; const void* wgu; const void* wd;              /* bf16 [N, K] row-major */
-  const float* ln_in; const float* ln_post_attn; const float* ln_pre_ff; const float* ln_post_ff;
-  void* kcache; void* vcache;
-} SvlaDecodeLayer;
-int64_t svla_decode_step_small_scratch_floats(int batch, int hidden, int hq, int hkv, int d, int ff);
-int svla_decode_step_small(const SvlaDecodeLayer* layers_dev, int n_layers, float* x, const float* final_norm_w,
-                           void* h_out_bf16, float* scratch, int batch, int hidden, int hq, int hkv, int d, int ff,
-                           int smax, int ctx, float theta, float scale, float softcap, float eps, const int32_t* kv_start,
-                           void* stream);
+/* G4: one whole Gemma2 decode step (all layers) for batch <= 64 in ONE persistent tensor-core launch: one CTA per SM
+ * (cooperative launch), a TMA weight ring that streams the [128 x 64] weight tiles of ALL phases of ALL layers without waiting
+ * for phase boundaries, swap-AB tcgen05.mma with split-K, and worker warps for RoPE + KV append + attention and the sandwich
+ * norms; phases are separated by in-kernel grid barriers (model/modeling_gemma2.py:80-92,169-195,351-413,451-506,680-793).
+ * It replaces the 7-launches-per-layer chain (svla_gemm_skinny / svla_decode_attention_fused / svla_rmsnorm_residual) and
+ * produces bit-identical hidden states.
+ *   svla_decode_mega_plan: HOST-side, once per model: writes the TMA descriptors of the 4 weight matrices of every layer
+ *     (weights[4*l + {0,1,2,3}] = device pointers of wqkv [(hq+2hkv)d, hidden], wo [hidden, hq*d], wgu [2ff, hidden] with
+ *     gate/up rows interleaved, wd [hidden, ff]; bf16 row-major) and of the activation buffers inside scratch_dev into HOST
+ *     memory maps_host (svla_decode_mega_maps_bytes); the caller copies them to 64-byte aligned device memory.
+ *   svla_decode_mega_step: x fp32 [batch, hidden] residual stream (embedded token times sqrt(hidden); updated in place),
+ *     norm_w_dev: DEVICE array of 4*n_layers float pointers (ln_in, ln_post_attn, ln_pre_ff, ln_post_ff per layer), h_out bf16
+ *     [batch, hidden] final-normed hidden state, kcache/vcache bf16 [layer][batch, smax, hkv, d] with cache_layer_stride
+ *     elements between layers; ctx = cache slots after this step (the new token sits at slot ctx-1, RoPE position
+ *     ctx - kv_start[b]).  scratch_dev: svla_decode_mega_scratch_bytes bytes, zero-initialised once, the same buffer the plan saw. */
+int svla_decode_mega_supported(int batch, int hidden, int hq, int hkv, int d, int ff, int ctx);
+int64_t svla_decode_mega_scratch_bytes(int hidden, int hq, int hkv, int d, int ff);
+int64_t svla_decode_mega_maps_bytes(int n_layers);
+int svla_decode_mega_plan(void* maps_host, const void* const* weights, int n_layers, int hidden, int hq, int hkv, int d, int ff,
+                          void* scratch_dev);
+int svla_decode_mega_step(const void* maps_dev, const void* norm_w_dev, int n_layers, float* x, const float* final_norm_w,
+                          void* h_out_bf16, void* kcache, void* vcache, int64_t cache_layer_stride, void* scratch_dev, int batch,
+                          int hidden, int hq, int hkv, int d, int ff, int smax, int ctx, float theta, float scale, float softcap,
+                          float eps, const int32_t* kv_start, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Memory-bound fused kernels

@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "lib", "libspatialvla_b200.so")
-SOURCES = ["capi.cu", "gemm_tcgen05.cu", "gemm_skinny.cu", "attention.cu", "attention_tc.cu", "attention_bwd_tc.cu", "decode_small.cu",
+SOURCES = ["capi.cu", "gemm_tcgen05.cu", "gemm_skinny.cu", "attention.cu", "attention_tc.cu", "attention_bwd_tc.cu", "decode_mega.cu",
            "fused_ops.cu", "tokenizer.cu", "image_ops.cu", "train_ops.cu", "train_mma.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -95,8 +95,11 @@ SIGNATURES = {
     "svla_decode_attention_fused": (_I, [_P, _I, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P]),
     "svla_layernorm": (_I, [_P, _P, _P, _F, _L, _I, _P, _P, _I, _P]),
     "svla_rmsnorm_residual": (_I, [_P, _P, _P, _P, _F, _L, _I, _P, _I, _L, _P]),
-    "svla_decode_step_small_scratch_floats": (_L, [_I, _I, _I, _I, _I, _I]),
-    "svla_decode_step_small": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P]),
+    "svla_decode_mega_supported": (_I, [_I, _I, _I, _I, _I, _I, _I]),
+    "svla_decode_mega_scratch_bytes": (_L, [_I, _I, _I, _I, _I]),
+    "svla_decode_mega_maps_bytes": (_L, [_I]),
+    "svla_decode_mega_plan": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "svla_decode_mega_step": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P]),
     "svla_rope_kv": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _I, _L, _P, _P]),
     "svla_embed_tokens": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _L, _I, _F, _P, _P]),
     "svla_argmax_rows": (_I, [_P, _L, _L, _L, _L, _P, _L, _P]),

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "svla_common.cuh"
+#include "decode_attn_item.cuh"
 
 namespace {
 
@@ -476,17 +477,9 @@ svla_decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16
 
 // G3f: one decode step of one (batch, kv-head): RoPE of the new q/k (from the split-K fp32 partial sums of the qkv
 // projection), KV-cache append, soft-capped softmax attention over the cache and the new key -- one launch instead of
-// rope_kv + decode_attention, and a streaming design instead of the latency-bound warp-per-key one:
-//   * K rows [0, ctx-1) then V rows [0, ctx-1) flow through a 6-stage cp.async ring of 32-row tiles (16-byte pieces,
-//     528-byte pitch: conflict-free 16-byte reads), ~80 KB in flight per CTA, 2 CTAs per SM -> all 256 CTAs of a B=64
-//     step are resident at once and the pass is bound by HBM, not by a per-warp dependency chain;
-//   * K pass: 8/GRP threads per (key, head) dot product, q slice in registers, 1-3 shuffles per dot;
-//   * softmax over the ctx scores in shared memory (one warp per head), no online rescaling;
-//   * V pass: thread = (dim pair, key half), p broadcast from shared memory.
-// The new token's key/value never round-trip through global memory: its score and value term come from shared memory.
+// rope_kv + decode_attention.  The item arithmetic lives in decode_attn_item.cuh (shared with the persistent decode kernel);
+// here: 6-stage ring (~80 KB in flight per CTA), 2 CTAs per SM -> all 256 CTAs of a B=64 step are resident at once.
 constexpr int kFusedStages = 6;
-constexpr int kFusedRows = 32;
-constexpr int kFusedPitch = 528;     // bytes per staged row (512 + 16)
 
 template <int GRP>
 __global__ void __launch_bounds__(kDecThreads, 2)
@@ -495,190 +488,31 @@ svla_decode_attn_fused_kernel(const float* __restrict__ qkv_f32, int n_partials,
                               int hq, int hkv, int smax, int ctx, float theta, float scale, float softcap,
                               const int* __restrict__ kv_start) {
   constexpr int D = 256;
-  constexpr int TPP = 8 / GRP;            // threads per (key, head) pair
-  constexpr int PPT = 32 / TPP;           // 16-byte pieces of a K row per thread
   extern __shared__ __align__(16) uint8_t sm_fused[];
-  uint8_t* s_stage = sm_fused;                                                   // [kFusedStages][32][528]
-  float* s_q = reinterpret_cast<float*>(s_stage + kFusedStages * kFusedRows * kFusedPitch);      // [GRP][256] (bf16-rounded values)
-  float* s_red = s_q + GRP * D;                                                  // [GRP][256]
-  __nv_bfloat16* s_newk = reinterpret_cast<__nv_bfloat16*>(s_red + GRP * D);     // [256]
-  __nv_bfloat16* s_newv = s_newk + D;                                            // [256]
-  float* s_inv = reinterpret_cast<float*>(s_newv + D);                           // [GRP] (+pad)
-  float* s_p = s_inv + 4;                                                        // [GRP][ctx_pad]
-  const int ctx_pad = (ctx + 31) & ~31;
-  const int b = blockIdx.y, hk = blockIdx.x, t = threadIdx.x;
-  const int lane = t & 31, warp = t >> 5;
-  const int kstart = kv_start ? kv_start[b] : 0;              // immutable input (not written by the PDL predecessor)
-  const int n_old = ctx - 1;                                  // cached keys; the new token sits at slot ctx - 1
-  const int n_chunks = (n_old + kFusedRows - 1) / kFusedRows;
-  const int n_tiles = 2 * n_chunks;
-  const long long row_stride = static_cast<long long>(hkv) * D;
-  const __nv_bfloat16* kbase = kc + (static_cast<long long>(b) * smax * hkv + hk) * D;
-  const __nv_bfloat16* vbase = vc + (static_cast<long long>(b) * smax * hkv + hk) * D;
-
-  auto issue_tile = [&](int tile) {
-    if (tile < n_tiles) {
-      const bool is_v = tile >= n_chunks;
-      const int key0 = (is_v ? tile - n_chunks : tile) * kFusedRows;
-      const __nv_bfloat16* base = is_v ? vbase : kbase;
-      uint8_t* dst = s_stage + (tile % kFusedStages) * (kFusedRows * kFusedPitch);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int p = t + i * kDecThreads;
-        const int r = p >> 5, c16 = p & 31;
-        const bool ok = key0 + r < n_old;
-        cp_async16(dst + r * kFusedPitch + c16 * 16, base + static_cast<long long>(ok ? key0 + r : 0) * row_stride + c16 * 8, ok);
-      }
-    }
-    cp_async_commit();
-  };
+  svla_dec::ItemSmem sm;
+  sm.stage = sm_fused;                                                                                   // [kFusedStages][32][528]
+  sm.q = reinterpret_cast<float*>(sm_fused + kFusedStages * svla_dec::kItemRows * svla_dec::kItemPitch); // [GRP][256]
+  sm.red = sm.q + GRP * D;                                                                               // [GRP][256]
+  sm.newk = reinterpret_cast<__nv_bfloat16*>(sm.red + GRP * D);                                          // [256]
+  sm.newv = sm.newk + D;                                                                                 // [256]
+  sm.inv = reinterpret_cast<float*>(sm.newv + D);                                                        // [4]
+  sm.wred = sm.inv + 4;                                                                                  // [16]
+  sm.p = sm.wred + 16;                                                                                   // [GRP][ctx_pad]
+  svla_dec::ItemArgs a;
+  a.b = blockIdx.y; a.hk = blockIdx.x;
+  a.qkv = qkv_f32 + static_cast<long long>(a.b) * (hq + 2 * hkv) * D;
+  a.n_partials = n_partials; a.partial_stride = partial_stride;
+  a.kc = kc; a.vc = vc; a.out = out;
+  a.hq = hq; a.hkv = hkv; a.smax = smax; a.ctx = ctx;
+  a.kstart = kv_start ? kv_start[a.b] : 0;              // immutable input (not written by the PDL predecessor)
+  a.theta = theta; a.scale = scale; a.softcap = softcap;
   pdl_launch_dependents();          // lets the o-projection GEMM start prefetching its weights
   // The cached rows [0, ctx-1) were written by the prefill or by this layer's kernel of an EARLIER decode step, i.e. at least
   // one full layer chain (>= 7 launches) upstream.  A PDL kernel can only overlap predecessors that are still resident and
   // blocked in griddepcontrol.wait; a whole chain of them cannot be resident at once, so those rows are complete and the
-  // ring is primed while the qkv projection (the direct predecessor) is still running.
-#pragma unroll
-  for (int i = 0; i < kFusedStages - 1; ++i) issue_tile(i);
-  pdl_wait();                       // qkv partial sums of this step (previous kernel)
-
-  // ---- RoPE of the new token (positions are 1-indexed, model/modeling_spatialvla.py:371-372) + cache append
-  {
-    const long long width = static_cast<long long>(hq + 2 * hkv) * D;
-    const float* src = qkv_f32 + static_cast<long long>(b) * width;
-    auto load = [&](long long col) -> float {
-      float acc = 0.f;
-      for (int sp = 0; sp < n_partials; ++sp) acc += src[sp * partial_stride + col];
-      return acc;
-    };
-    const long long cache_row = (static_cast<long long>(b) * smax + n_old) * hkv * D + static_cast<long long>(hk) * D;
-    if (t < D / 2) {
-      const int j = t;
-      const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * j) / static_cast<float>(D));
-      float sn, cs;
-      sincosf(static_cast<float>(ctx - kstart) * inv_freq, &sn, &cs);      // position of the new token: ctx - leading pads
-#pragma unroll
-      for (int g = 0; g <= GRP; ++g) {
-        const long long col = (g < GRP) ? static_cast<long long>(hk * GRP + g) * D : static_cast<long long>(hq + hk) * D;
-        const float x1 = load(col + j), x2 = load(col + j + D / 2);
-        const __nv_bfloat16 o1 = __float2bfloat16(x1 * cs - x2 * sn), o2 = __float2bfloat16(x2 * cs + x1 * sn);
-        if (g < GRP) {
-          s_q[g * D + j] = __bfloat162float(o1);
-          s_q[g * D + j + D / 2] = __bfloat162float(o2);
-        } else {
-          s_newk[j] = o1; s_newk[j + D / 2] = o2;
-          kc[cache_row + j] = o1; kc[cache_row + j + D / 2] = o2;
-        }
-      }
-    } else {
-      const int dp = t - D / 2;
-      const long long col = static_cast<long long>(hq + hkv + hk) * D + 2 * dp;
-      const __nv_bfloat162 v2 = __floats2bfloat162_rn(load(col), load(col + 1));
-      *reinterpret_cast<__nv_bfloat162*>(s_newv + 2 * dp) = v2;
-      *reinterpret_cast<__nv_bfloat162*>(vc + cache_row + 2 * dp) = v2;
-    }
-    for (int i = t; i < GRP * (ctx_pad - n_old); i += kDecThreads) {      // p = 0 behind the last cached key
-      const int g = i / (ctx_pad - n_old), k = n_old + i % (ctx_pad - n_old);
-      s_p[g * ctx_pad + k] = 0.f;
-    }
-  }
-  __syncthreads();
-
-  // ---- K pass
-  const int part = t % TPP, g_k = (t / TPP) % GRP, key_l = t >> 3;
-  float qr[PPT][8];
-#pragma unroll
-  for (int i = 0; i < PPT; ++i) {
-    const float4 a0 = *reinterpret_cast<const float4*>(s_q + g_k * D + (i * TPP + part) * 8);
-    const float4 a1 = *reinterpret_cast<const float4*>(s_q + g_k * D + (i * TPP + part) * 8 + 4);
-    qr[i][0] = a0.x; qr[i][1] = a0.y; qr[i][2] = a0.z; qr[i][3] = a0.w;
-    qr[i][4] = a1.x; qr[i][5] = a1.y; qr[i][6] = a1.z; qr[i][7] = a1.w;
-  }
-  const float inv_cap = softcap > 0.f ? 1.f / softcap : 0.f;
-  for (int tile = 0; tile < n_chunks; ++tile) {
-    cp_async_wait<kFusedStages - 2>();
-    __syncthreads();
-    issue_tile(tile + kFusedStages - 1);
-    const uint8_t* row = s_stage + (tile % kFusedStages) * (kFusedRows * kFusedPitch) + key_l * kFusedPitch;
-    float dot = 0.f;
-#pragma unroll
-    for (int i = 0; i < PPT; ++i) {
-      float kv[8];
-      unpack8(*reinterpret_cast<const uint4*>(row + (i * TPP + part) * 16), kv);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) dot = fmaf(kv[e], qr[i][e], dot);
-    }
-#pragma unroll
-    for (int o = 1; o < TPP; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    const int key = tile * kFusedRows + key_l;
-    if (part == 0 && key < n_old) {
-      float sc = dot * scale;
-      if (softcap > 0.f) sc = softcap * tanh_small(sc * inv_cap);
-      s_p[g_k * ctx_pad + key] = key < kstart ? -INFINITY : sc;       // padded prompt slots never receive weight
-    }
-  }
-  __syncthreads();
-  // ---- new key's score + softmax (warp g handles head g); p stays unnormalised, 1/sum is applied at the end
-  if (warp < GRP) {
-    float kv[8], dot = 0.f;
-    unpack8(*reinterpret_cast<const uint4*>(s_newk + lane * 8), kv);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) dot = fmaf(kv[e], s_q[warp * D + lane * 8 + e], dot);
-    dot = warp_sum(dot) * scale;
-    if (softcap > 0.f) dot = softcap * tanh_small(dot * inv_cap);
-    float* pr = s_p + warp * ctx_pad;
-    if (lane == 0) pr[n_old] = dot;
-    __syncwarp();
-    float m = -INFINITY;
-    for (int k = lane; k < ctx; k += 32) m = fmaxf(m, pr[k]);
-    m = warp_max(m);
-    float sum = 0.f;
-    for (int k = lane; k < ctx; k += 32) {
-      const float e = __expf(pr[k] - m);
-      pr[k] = e;
-      sum += e;
-    }
-    sum = warp_sum(sum);
-    if (lane == 0) s_inv[warp] = 1.f / sum;
-  }
-  __syncthreads();
-  // ---- V pass: thread = (dim pair dp, key half kh)
-  const int dp = t & 127, kh = t >> 7;
-  float acc[GRP][2];
-#pragma unroll
-  for (int g = 0; g < GRP; ++g) { acc[g][0] = 0.f; acc[g][1] = 0.f; }
-  for (int tile = n_chunks; tile < n_tiles; ++tile) {
-    cp_async_wait<kFusedStages - 2>();
-    __syncthreads();
-    issue_tile(tile + kFusedStages - 1);
-    const uint8_t* st = s_stage + (tile % kFusedStages) * (kFusedRows * kFusedPitch);
-    const int key0 = (tile - n_chunks) * kFusedRows + kh * 16;
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(st + (kh * 16 + r) * kFusedPitch + dp * 4));
-#pragma unroll
-      for (int g = 0; g < GRP; ++g) {
-        const float p = s_p[g * ctx_pad + key0 + r];          // 0 for rows behind the last cached key
-        acc[g][0] = fmaf(p, v.x, acc[g][0]);
-        acc[g][1] = fmaf(p, v.y, acc[g][1]);
-      }
-    }
-  }
-  cp_async_wait<0>();
-  if (kh == 1) {
-#pragma unroll
-    for (int g = 0; g < GRP; ++g) { s_red[g * D + 2 * dp] = acc[g][0]; s_red[g * D + 2 * dp + 1] = acc[g][1]; }
-  }
-  __syncthreads();
-  if (kh == 0) {
-    const float2 nv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(s_newv + 2 * dp));
-#pragma unroll
-    for (int g = 0; g < GRP; ++g) {
-      const float pn = s_p[g * ctx_pad + n_old], inv = s_inv[g];
-      const float o0 = (acc[g][0] + s_red[g * D + 2 * dp] + pn * nv.x) * inv;
-      const float o1 = (acc[g][1] + s_red[g * D + 2 * dp + 1] + pn * nv.y) * inv;
-      *reinterpret_cast<__nv_bfloat162*>(out + (static_cast<long long>(b) * hq + hk * GRP + g) * D + 2 * dp) = __floats2bfloat162_rn(o0, o1);
-    }
-  }
+  // ring is primed while the qkv projection (the direct predecessor) is still running; griddepcontrol.wait comes before the
+  // first read of its partial sums.
+  svla_dec::decode_attn_item<GRP, kFusedStages>(a, sm, static_cast<int>(threadIdx.x), [] { __syncthreads(); }, [] { pdl_wait(); });
 }
 
 }  // namespace
@@ -762,7 +596,7 @@ extern "C" int svla_decode_attention_fused(const float* qkv_f32, int n_partials,
   SVLA_REQUIRE(ctx > 0 && ctx <= smax && n_partials >= 1 && batch > 0 && batch <= 65535, "svla_decode_attention_fused: bad ctx / partials / batch");
   const int grp = hq / hkv;
   const int ctx_pad = (ctx + 31) & ~31;
-  const size_t smem = static_cast<size_t>(kFusedStages) * kFusedRows * kFusedPitch + (2 * grp * 256 + 4 + grp * ctx_pad) * sizeof(float) + 2 * 256 * 2;
+  const size_t smem = static_cast<size_t>(kFusedStages) * svla_dec::kItemRows * svla_dec::kItemPitch + (2 * grp * 256 + 4 + 16 + grp * ctx_pad) * sizeof(float) + 2 * 256 * 2;
   SVLA_REQUIRE(smem <= 220 * 1024, "svla_decode_attention_fused: context %d too long for shared memory", ctx);
   static size_t configured[3] = {0, 0, 0};
   if (smem > configured[grp]) {

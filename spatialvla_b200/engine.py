@@ -124,9 +124,7 @@ class SpatialVLAEngine:
                 "ln_in": Fp(q + "input_layernorm.weight"), "ln_post_attn": Fp(q + "post_attention_layernorm.weight"),
                 "ln_pre_ff": Fp(q + "pre_feedforward_layernorm.weight"), "ln_post_ff": Fp(q + "post_feedforward_layernorm.weight")})
         self.gem = g
-        self._small_wtab = None
-        if getattr(self.ops, "name", "") == "cuda":
-            self._small_weight_table()
+        self._mega = None
         if not self.use_zoe:
             return
         # ---- Ego3D
@@ -600,52 +598,41 @@ class SpatialVLAEngine:
         L_, hkv, hd = t["num_hidden_layers"], t["num_key_value_heads"], t["head_dim"]
         cache = {"k": self.ops.zeros((L_, B, smax, hkv, hd), BF16), "v": self.ops.zeros((L_, B, smax, hkv, hd), BF16),
                  "smax": smax, "len": 0}
-        if self._small_decode_ok(B):
-            # descriptor table of the persistent small-batch decode kernel (SvlaDecodeLayer: 10 device pointers per layer).
-            # Device-side arithmetic only: new_cache also runs under CUDA-graph capture, where host->device copies are illegal.
-            tab = torch.empty((L_, 10), dtype=torch.int64, device=self.dev)
-            tab[:, :8] = self._small_weight_table()
-            layer_bytes = cache["k"][0].numel() * cache["k"].element_size()
-            idx = torch.arange(L_, dtype=torch.int64, device=self.dev) * layer_bytes
-            tab[:, 8] = idx + cache["k"].data_ptr()
-            tab[:, 9] = idx + cache["v"].data_ptr()
-            cache["small_table"] = tab
-            cache["small_scratch"] = self.ops.decode_step_small_scratch(B, t["hidden_size"], t["num_attention_heads"], hkv, hd,
-                                                                       t["intermediate_size"])
         return cache
 
-    # Experimental, opt-in (SVLA_DECODE_SMALL=1): measured on B200 at batch 1 the persistent kernel is at 1.80 ms per decode step
-    # (weight GEMVs at 5.5 TB/s, but ~12 us of grid barriers and ~12 us of norm prologues per layer) against 1.69 ms for the
-    # PDL chain, so the chain stays the default until the barrier / prologue cost is cut (profiles/decode_small_r1.txt).
-    small_decode = os.environ.get("SVLA_DECODE_SMALL", "0") == "1"
-    small_decode_batches = (1, 2)
+    # Persistent tensor-core decode step (csrc/decode_mega.cu, batch <= 64): the whole layer stack in ONE cooperative launch.
+    # Opt-in (SVLA_DECODE=mega).  Measured on B200 (tools/decode_mega_check.py, profiles/decode_mega_r2.txt): bit-identical
+    # hidden states, but 2.43 ms against 1.99 ms per batch-64 step for the 7-launches-per-layer PDL chain -- an in-kernel grid
+    # barrier (arrive + poll + fences, ~2.5 us) costs what a PDL kernel boundary costs, so the seven dependent phases of a
+    # layer bound both designs and the chain's second resident CTA hides more of the attention phase.
+    mega_decode = os.environ.get("SVLA_DECODE", "chain") == "mega"
 
-    def _small_weight_table(self):
-        """int64 [layers, 8] device tensor of the per-layer weight pointers (built once, outside any graph capture)."""
-        if getattr(self, "_small_wtab", None) is None:
-            rows = [[L["wqkv"].data_ptr(), L["wo"].data_ptr(), L["wgu"].data_ptr(), L["wd"].data_ptr(), L["ln_in"].data_ptr(),
-                     L["ln_post_attn"].data_ptr(), L["ln_pre_ff"].data_ptr(), L["ln_post_ff"].data_ptr()] for L in self.gem["layers"]]
-            self._small_wtab = torch.tensor(rows, dtype=torch.int64).to(self.dev)
-        return self._small_wtab
+    def _mega_plan(self):
+        """TMA descriptors / norm-pointer table / scratch of the persistent decode kernel, built once (outside graph capture)."""
+        if getattr(self, "_mega", None) is None:
+            t = self.t
+            Ls = self.gem["layers"]
+            self._mega = self.ops.decode_mega_plan(
+                [(L["wqkv"], L["wo"], L["wgu"], L["wd"]) for L in Ls],
+                [(L["ln_in"], L["ln_post_attn"], L["ln_pre_ff"], L["ln_post_ff"]) for L in Ls],
+                hidden=t["hidden_size"], hq=t["num_attention_heads"], hkv=t["num_key_value_heads"], d=t["head_dim"], ff=t["intermediate_size"])
+        return self._mega
 
-    def _small_decode_ok(self, B):
-        """Batches of 1 / 2 rows may decode through the persistent single-launch kernel (svla_decode_step_small); at 4 rows its
-        CUDA-core GEMVs become shared-memory bound and the tensor-core chain wins clearly (measured)."""
+    def _mega_ok(self, B, ctx):
         t = self.t
-        return (self.small_decode and getattr(self.ops, "name", "") == "cuda" and B in self.small_decode_batches and t["head_dim"] == 256
-                and t["num_attention_heads"] // t["num_key_value_heads"] in (1, 2))
+        return (self.mega_decode and getattr(self.ops, "name", "") == "cuda"
+                and self.ops.decode_mega_supported(B, t["hidden_size"], t["num_attention_heads"], t["num_key_value_heads"], t["head_dim"],
+                                                   t["intermediate_size"], ctx))
 
-    def gemma_decode_small(self, x, B, cache, pads=None):
-        """One decode step for B in {1, 2, 4}: all layers in one persistent launch -> final-normed hidden bf16 [B, H]."""
+    def gemma_decode_mega(self, x, B, cache, pads=None):
+        """One decode step of all layers in ONE persistent launch -> final-normed hidden bf16 [B, H] (x is updated in place)."""
         t = self.t
         pos0 = cache["len"]
         assert pos0 + 1 <= cache["smax"], "KV cache overflow"
         h = self.ops.empty((B, t["hidden_size"]), BF16)
-        self.ops.decode_step_small(cache["small_table"], x, self.gem["final"], h, cache["small_scratch"], batch=B,
-                                   hidden=t["hidden_size"], hq=t["num_attention_heads"], hkv=t["num_key_value_heads"], d=t["head_dim"],
-                                   ff=t["intermediate_size"], smax=cache["smax"], ctx=pos0 + 1, theta=float(t.get("rope_theta", 10000.0)),
-                                   scale=t["query_pre_attn_scalar"] ** -0.5, softcap=t["attn_logit_softcapping"] or 0.0,
-                                   eps=t["rms_norm_eps"], kv_start=pads)
+        self.ops.decode_mega_step(self._mega_plan(), x, self.gem["final"], h, cache["k"], cache["v"], batch=B, smax=cache["smax"], ctx=pos0 + 1,
+                                  theta=float(t.get("rope_theta", 10000.0)), scale=t["query_pre_attn_scalar"] ** -0.5,
+                                  softcap=t["attn_logit_softcapping"] or 0.0, eps=t["rms_norm_eps"], kv_start=pads)
         cache["len"] = pos0 + 1
         return h
 
@@ -667,6 +654,8 @@ class SpatialVLAEngine:
             # Gemma2 alternates sliding-window and global layers (model/modeling_gemma2.py:364-413); every context on this path
             # (278 + 12 tokens) is far inside the 4096-token window, where the two layer kinds are identical
             raise NotImplementedError(f"context of {pos0 + S} tokens exceeds the sliding window ({win}): windowed layers are not implemented")
+        if S == 1 and not bidirectional and self._mega_ok(B, pos0 + 1):
+            return self.gemma_decode_mega(x, B, cache, pads=pads)
         h = ops.empty((M, H), BF16)
         ops.rmsnorm_residual(x, w_pre=g["layers"][0]["ln_in"], eps=eps, out_bf16=h)
         q = ops.empty((M, nh * hd), BF16)
@@ -806,10 +795,7 @@ class SpatialVLAEngine:
                 break
             feed = toks[:, step:step + 1] if forced_tokens is None else forced_tokens[:, step:step + 1]
             x, _ = self.embed(feed.contiguous())
-            if "small_table" in cache:
-                rows = self.gemma_decode_small(x, B, cache, pads=pads)
-            else:
-                rows = self.gemma_forward(x, B, 1, cache, bidirectional=False, pads=pads)
+            rows = self.gemma_forward(x, B, 1, cache, bidirectional=False, pads=pads)
         self.last_status = status
         return toks
 
@@ -826,7 +812,6 @@ class SpatialVLAEngine:
         feats = self.image_features(px, intrinsic) if px is not None else None
         x, status = self.embed(ids, feats)
         cache = self.new_cache(B, P + max_new_tokens)
-        cache.pop("small_table", None)
         h = self.gemma_forward(x, B, P, cache, bidirectional=True, pads=pads)
         rows = h.view(B, P * H)[:, (P - 1) * H:]
         w = self.lm_head_full()

@@ -283,20 +283,44 @@ class CudaOps:
                 "svla_decode_attention_fused")
 
     # ---- G4 persistent small-batch decode step
-    def decode_step_small_scratch(self, batch, hidden, hq, hkv, d, ff):
-        n = int(self.lib.svla_decode_step_small_scratch_floats(batch, hidden, hq, hkv, d, ff))
-        return torch.zeros(n, dtype=F32, device=self.device)
+    # ---- persistent tensor-core decode step (csrc/decode_mega.cu)
+    def decode_mega_supported(self, batch, hidden, hq, hkv, d, ff, ctx):
+        return bool(self.lib.svla_decode_mega_supported(batch, hidden, hq, hkv, d, ff, ctx))
 
-    def decode_step_small(self, layer_table, x, final_w, h_out, scratch, *, batch, hidden, hq, hkv, d, ff, smax, ctx, theta, scale,
-                          softcap, eps, kv_start=None):
-        """layer_table: int64 device tensor [n_layers, 10] of device pointers in SvlaDecodeLayer order."""
-        _req(layer_table.dtype == torch.int64 and layer_table.dim() == 2 and layer_table.shape[1] == 10 and layer_table.is_contiguous(),
-             "decode_step_small: layer table must be int64 [n_layers, 10]")
-        _req(x.dtype == F32 and x.is_contiguous() and h_out.dtype == BF16 and h_out.is_contiguous(), "decode_step_small: x fp32 / h_out bf16")
-        L.check(self.lib.svla_decode_step_small(_ptr(layer_table), int(layer_table.shape[0]), _ptr(x), _ptr(final_w), _ptr(h_out),
-                                                _ptr(scratch), batch, hidden, hq, hkv, d, ff, smax, ctx, float(theta), float(scale),
-                                                float(softcap or 0.0), float(eps), _ptr(kv_start), self._stream()),
-                "svla_decode_step_small")
+    def decode_mega_plan(self, layer_weights, norm_weights, *, hidden, hq, hkv, d, ff):
+        """layer_weights: per layer (wqkv, wo, wgu, wd) bf16 row-major device tensors; norm_weights: per layer (ln_in,
+        ln_post_attn, ln_pre_ff, ln_post_ff) fp32 device tensors.  Returns the plan dict `decode_mega_step` takes: device
+        copies of the TMA descriptors and of the norm-pointer table, plus the zero-initialised scratch buffer."""
+        n_layers = len(layer_weights)
+        for ws in layer_weights:
+            for w in ws:
+                _req(w.dtype == BF16 and w.is_contiguous() and w.dim() == 2, "decode_mega_plan: weights must be contiguous bf16 matrices")
+        scratch = torch.zeros(int(self.lib.svla_decode_mega_scratch_bytes(hidden, hq, hkv, d, ff)), dtype=torch.uint8, device=self.device)
+        nbytes = int(self.lib.svla_decode_mega_maps_bytes(n_layers))
+        host = (C.c_uint8 * nbytes)()
+        wptrs = (C.c_void_p * (4 * n_layers))(*[w.data_ptr() for ws in layer_weights for w in ws])
+        L.check(self.lib.svla_decode_mega_plan(C.cast(host, C.c_void_p), C.cast(wptrs, C.c_void_p), n_layers, hidden,
+                                               hq, hkv, d, ff, _ptr(scratch)), "svla_decode_mega_plan")
+        maps = torch.frombuffer(bytearray(host), dtype=torch.uint8).to(self.device)
+        _req(maps.data_ptr() % 64 == 0, "decode_mega_plan: descriptor table is not 64-byte aligned")
+        for ns in norm_weights:
+            for n in ns:
+                _req(n.dtype == F32 and n.is_contiguous(), "decode_mega_plan: norm weights must be contiguous fp32")
+        norm_tab = torch.tensor([n.data_ptr() for ns in norm_weights for n in ns], dtype=torch.int64).to(self.device)
+        return {"maps": maps, "norm_tab": norm_tab, "scratch": scratch, "n_layers": n_layers, "keep": (layer_weights, norm_weights),
+                "dims": (hidden, hq, hkv, d, ff)}
+
+    def decode_mega_step(self, plan, x, final_w, h_out, kcache, vcache, *, batch, smax, ctx, theta, scale, softcap, eps, kv_start=None):
+        """One decode step of every layer in one launch. kcache/vcache: bf16 [layers, batch, smax, hkv, d] contiguous."""
+        hidden, hq, hkv, d, ff = plan["dims"]
+        _req(x.dtype == F32 and x.is_contiguous() and tuple(x.shape) == (batch, hidden), "decode_mega_step: x must be fp32 [batch, hidden]")
+        _req(h_out.dtype == BF16 and h_out.is_contiguous() and h_out.numel() == batch * hidden, "decode_mega_step: h_out must be bf16 [batch, hidden]")
+        _req(kcache.dtype == BF16 and kcache.is_contiguous() and vcache.is_contiguous() and tuple(kcache.shape) == (plan["n_layers"], batch, smax, hkv, d)
+             and vcache.shape == kcache.shape, "decode_mega_step: cache must be bf16 [layers, batch, smax, hkv, d]")
+        L.check(self.lib.svla_decode_mega_step(_ptr(plan["maps"]), _ptr(plan["norm_tab"]), plan["n_layers"], _ptr(x), _ptr(final_w), _ptr(h_out),
+                                               _ptr(kcache), _ptr(vcache), int(kcache.stride(0)), _ptr(plan["scratch"]), batch, hidden, hq, hkv, d,
+                                               ff, smax, ctx, float(theta), float(scale), float(softcap or 0.0), float(eps), _ptr(kv_start),
+                                               self._stream()), "svla_decode_mega_step")
 
     # ---- memory-bound fused ops
     def layernorm(self, x, gamma, beta, eps, *, out_bf16=None, out_f32=None, relu=False):

@@ -1,5 +1,5 @@
 """p50 latency of predict_action at batch 1 (second half of the BASELINE metric), PDL decode chain vs the persistent single-launch
-decode kernel (svla_decode_step_small), alternated A/B/A/B inside ONE process on the same box: same weights, same inputs, CUDA-graph
+decode kernel (svla_decode_mega_step), alternated A/B/A/B inside ONE process on the same box: same weights, same inputs, CUDA-graph
 replay, wall clock around generate_actions with a device synchronize on both sides (what bench.py's latency leg measures).
 Usage: python tools/latency_ab.py [--iters 40]"""
 import argparse
@@ -33,7 +33,7 @@ px, ids, K = synth_inputs(cfg, args.batch, device=dev)
 
 
 def measure(small):
-    eng.small_decode = small
+    eng.mega_decode = small
     eng._graphs = {}                      # graphs bake the decode path: re-capture for this arm
     ts = []
     toks = None
@@ -44,7 +44,7 @@ def measure(small):
         torch.cuda.synchronize()
         ts.append((time.perf_counter() - t0) * 1e3)
     ts = ts[5:]
-    return {"small_decode": small, "p50_ms": round(statistics.median(ts), 3), "p10_ms": round(sorted(ts)[len(ts) // 10], 3),
+    return {"mega_decode": small, "p50_ms": round(statistics.median(ts), 3), "p10_ms": round(sorted(ts)[len(ts) // 10], 3),
             "p90_ms": round(sorted(ts)[len(ts) * 9 // 10], 3)}, toks
 
 

@@ -192,7 +192,7 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       }
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % C::kStages;
-        mbar_wait(&kv_empty[st], ((j / C::kStages) & 1) ^ 1u);
+        mbar_wait_suspend(&kv_empty[st], ((j / C::kStages) & 1) ^ 1u);
         mbar_expect_tx(&kv_full[st], 2 * C::kKBytes);
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) {
@@ -215,7 +215,7 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       auto valid16 = [&](int j) { return min(BKV, (p.sk - j * BKV + 15) & ~15); };
       auto issue_pv = [&](int j) {
         const int st = j & 1, kst = j % C::kStages;
-        mbar_wait(&p_full[st], (j >> 1) & 1);
+        mbar_wait_suspend(&p_full[st], (j >> 1) & 1);
         tc_fence_after();
         const uint32_t vbase = smem_u32(sV + kst * C::kKBytes);
         const int ksteps = valid16(j) >> 4;
@@ -227,11 +227,11 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
         umma_commit(&p_empty[st]);       // P_j consumed, O updated
         umma_commit(&kv_empty[kst]);     // K_j / V_j stage free
       };
-      mbar_wait(q_full, 0);
+      mbar_wait_suspend(q_full, 0);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1, kst = j % C::kStages;
-        mbar_wait(&kv_full[kst], (j / C::kStages) & 1);
-        mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1u);
+        mbar_wait_suspend(&kv_full[kst], (j / C::kStages) & 1);
+        mbar_wait_suspend(&s_empty[st], ((j >> 1) & 1) ^ 1u);
         tc_fence_after();
         const uint32_t qbase = smem_u32(sQ), kbase = smem_u32(sK + kst * C::kKBytes);
         const uint32_t idesc_qk = make_idesc(kBQ, valid16(j), 0);
@@ -261,7 +261,8 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     const bool cls_q = kRelpos && (qi == 0);
     if (kRelpos) {
       const int qc = min(qi, p.sq - 1);               // rows past the end reuse the last valid row's (in-range) index
-      if (qc >= 1) qbase = ((qc - 1) / p.win + p.win - 1) * (2 * p.win - 1) + (qc - 1) % p.win + p.win - 1;
+      const int qp = max(qc - 1, 0);                  // the CLS query row uses an in-range dummy (its bias is a constant, see below)
+      qbase = (qp / p.win + p.win - 1) * (2 * p.win - 1) + qp % p.win + p.win - 1;
     }
     const float sl2 = p.scale * kLog2e;
     const float c1 = kSoftcap ? p.scale / p.softcap : 0.f, c2 = kSoftcap ? p.softcap * kLog2e : 0.f;
@@ -287,7 +288,7 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
         for (int i = tid; i < nrel; i += NT) sTab[i] = p.relpos[static_cast<long long>(i) * p.hq + h] * kLog2e;
       }
       for (int kj = tid; kj < n_tiles_all * BKV; kj += NT)
-        sKterm[kj] = (kj >= 1 && kj < p.sk) ? ((kj - 1) / p.win) * (2 * p.win - 1) + (kj - 1) % p.win : 0;
+        sKterm[kj] = (kj >= 1 && kj < p.sk) ? 4 * (((kj - 1) / p.win) * (2 * p.win - 1) + (kj - 1) % p.win) : 0;      // byte offsets
       asm volatile("bar.sync 5, 256;" ::: "memory");      // softmax warps only (ids 1-4 are the pair barriers)
     }
     // the two warps of a quadrant meet on named barrier 1 + q (64 threads)
@@ -295,7 +296,7 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     for (int j = 0; j < n_tiles; ++j) {
       const int st = j & 1;
       const int k0 = j * BKV + ch * HC;               // first key of this warp's columns
-      mbar_wait(&s_full[st], (j >> 1) & 1);
+      mbar_wait_suspend(&s_full[st], (j >> 1) & 1);
       tc_fence_after();
       float s[HC];
       {
@@ -312,17 +313,35 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
 #pragma unroll
         for (int i = 0; i < HC; ++i) s[i] = -INFINITY;
       } else if (kRelpos) {
+        // bias[q, k] = table[qbase - kterm[k]]: the per-key terms are BYTE offsets (one int4 broadcast load per 4 keys), the
+        // per-thread base is a byte address, so an element costs IADD + LDS + half an FFMA2.  The CLS query row (constant bias
+        // over all keys) exists in one warp pair of the first query tile only: that warp takes the select-per-element path.
         const float raw0 = s[0];
         const int4* kt4 = reinterpret_cast<const int4*>(sKterm + k0);
+        const char* qtab = reinterpret_cast<const char*>(sTab) + 4 * qbase;
+        if (q0 == 0 && q == 0) {
+          const char* tab0 = reinterpret_cast<const char*>(sTab);
+          const int cls_off = 4 * (nrel - 3), qoff = 4 * qbase;
 #pragma unroll
-        for (int i4 = 0; i4 < HC / 4; ++i4) {
-          const int4 kt = kt4[i4];                          // warp-wide broadcast
-          const int i0 = cls_q ? nrel - 3 : qbase - kt.x, i1 = cls_q ? nrel - 3 : qbase - kt.y;
-          const int i2 = cls_q ? nrel - 3 : qbase - kt.z, i3 = cls_q ? nrel - 3 : qbase - kt.w;
-          s[4 * i4 + 0] = fmaf(s[4 * i4 + 0], sl2, sTab[i0]);
-          s[4 * i4 + 1] = fmaf(s[4 * i4 + 1], sl2, sTab[i1]);
-          s[4 * i4 + 2] = fmaf(s[4 * i4 + 2], sl2, sTab[i2]);
-          s[4 * i4 + 3] = fmaf(s[4 * i4 + 3], sl2, sTab[i3]);
+          for (int i4 = 0; i4 < HC / 4; ++i4) {
+            const int4 kt = kt4[i4];                          // warp-wide broadcast
+            const int i0 = cls_q ? cls_off : qoff - kt.x, i1 = cls_q ? cls_off : qoff - kt.y;
+            const int i2 = cls_q ? cls_off : qoff - kt.z, i3 = cls_q ? cls_off : qoff - kt.w;
+            s[4 * i4 + 0] = fmaf(s[4 * i4 + 0], sl2, *reinterpret_cast<const float*>(tab0 + i0));
+            s[4 * i4 + 1] = fmaf(s[4 * i4 + 1], sl2, *reinterpret_cast<const float*>(tab0 + i1));
+            s[4 * i4 + 2] = fmaf(s[4 * i4 + 2], sl2, *reinterpret_cast<const float*>(tab0 + i2));
+            s[4 * i4 + 3] = fmaf(s[4 * i4 + 3], sl2, *reinterpret_cast<const float*>(tab0 + i3));
+          }
+        } else {
+          const uint64_t sl22 = pack_f32x2(sl2, sl2);
+#pragma unroll
+          for (int i4 = 0; i4 < HC / 4; ++i4) {
+            const int4 kt = kt4[i4];                          // warp-wide broadcast
+            const float b0 = *reinterpret_cast<const float*>(qtab - kt.x), b1 = *reinterpret_cast<const float*>(qtab - kt.y);
+            const float b2 = *reinterpret_cast<const float*>(qtab - kt.z), b3 = *reinterpret_cast<const float*>(qtab - kt.w);
+            unpack_f32x2(fma_f32x2(pack_f32x2(s[4 * i4 + 0], s[4 * i4 + 1]), sl22, pack_f32x2(b0, b1)), s[4 * i4 + 0], s[4 * i4 + 1]);
+            unpack_f32x2(fma_f32x2(pack_f32x2(s[4 * i4 + 2], s[4 * i4 + 3]), sl22, pack_f32x2(b2, b3)), s[4 * i4 + 2], s[4 * i4 + 3]);
+          }
         }
         if (k0 == 0) s[0] = fmaf(raw0, sl2, sTab[cls_q ? nrel - 1 : nrel - 2]);      // CLS key column
       } else if (kSoftcap) {
@@ -372,19 +391,25 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
         m_run = mj;
       }
       const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
-      float lsum = 0.f;
       uint32_t pk[HC / 2];
+      uint64_t lsum2 = pack_f32x2(0.f, 0.f);
+      const uint64_t negm2 = pack_f32x2(-m_use, -m_use);
 #pragma unroll
       for (int i = 0; i < HC; i += 2) {
-        const float p0 = ex2f(s[i] - m_use), p1 = ex2f(s[i + 1] - m_use);
-        lsum += p0 + p1;
+        float t0, t1;
+        unpack_f32x2(add_f32x2(pack_f32x2(s[i], s[i + 1]), negm2), t0, t1);
+        const float p0 = ex2f(t0), p1 = ex2f(t1);
+        lsum2 = add_f32x2(lsum2, pack_f32x2(p0, p1));
         pk[i >> 1] = pack_bf16x2(p0, p1);
       }
+      float lsum, lsum_hi;
+      unpack_f32x2(lsum2, lsum, lsum_hi);
+      lsum += lsum_hi;
       l_run = l_run * alpha + lsum;                          // partial row sum over this warp's columns
       // P buffer st was read by P_{j-2} V_{j-2}; a rescale additionally needs P_{j-1} V_{j-1} (the last writer of O) done
-      if (j >= 2) mbar_wait(&p_empty[st], ((j - 2) >> 1) & 1);
+      if (j >= 2) mbar_wait_suspend(&p_empty[st], ((j - 2) >> 1) & 1);
       if (__any_sync(0xffffffffu, rescale)) {                // identical decision in both warps of the pair (same rows, same max)
-        mbar_wait(&p_empty[st ^ 1], ((j - 1) >> 1) & 1);
+        mbar_wait_suspend(&p_empty[st ^ 1], ((j - 1) >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
         for (int c0 = ch * DH; c0 < (ch + 1) * DH; c0 += 32) {
@@ -411,7 +436,7 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
     if (p.lse && ch == 0 && qi < p.sq)
       p.lse[(static_cast<long long>(b) * p.hq + h) * p.lse_stride + qi] = (l_run > 0.f) ? m_run + log2f(l_run) : -INFINITY;
     const int last = n_tiles - 1;
-    mbar_wait(&p_empty[last & 1], (last >> 1) & 1);
+    mbar_wait_suspend(&p_empty[last & 1], (last >> 1) & 1);
     tc_fence_after();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
     __nv_bfloat16* og = p.out + b * p.o_bs + static_cast<long long>(qi) * p.o_ss + static_cast<long long>(h) * (PAD ? p.d : D);

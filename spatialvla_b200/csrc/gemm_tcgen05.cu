@@ -949,8 +949,10 @@ int pick_block_n(long long m_tiles, long long n) {
   int best = 128;
   for (int bn : {256, 128}) {
     const long long tiles = m_tiles * ((n + bn - 1) / bn);
-    // time per tile ~ BN (MMA bound) but the 128-wide tile moves 1.5x the L2 bytes per FLOP: measured ~20% slower per FLOP
-    const long long cost = ((tiles + sms - 1) / sms) * bn * (bn == 128 ? 6 : 5);
+    // time per tile ~ BN (MMA bound), but a 128-wide pair tile stages 24 KB per 2 MFLOP (256-wide: 32 KB per 4 MFLOP) and is
+    // shared-memory bound: measured 1.4-1.7x slower per column (M=16384 N=1152 K=4304: 0.187 ms at BN=128 vs 0.137 ms at BN=256
+    // although N = 4.5 tiles of 256; profiles/gemm_epilogue_r1_v16.txt)
+    const long long cost = ((tiles + sms - 1) / sms) * bn * (bn == 128 ? 8 : 5);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;

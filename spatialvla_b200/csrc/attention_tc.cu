@@ -343,11 +343,45 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       const int nr2 = nrel_rows * nrel_rows;
       const float* src = p.relpos + (p.head_major ? static_cast<long long>(h) * (nr2 + 3) : h);
       const long long sstride = p.head_major ? 1 : p.hq;
-      // thread (r4, c) copies column c of table rows r4, r4 + 4, ...: no integer divisions in the prologue of every CTA
-      for (int c = tid & 63; c < nrel_rows; c += 64)
-        for (int r = tid >> 6; r < nrel_rows; r += NT / 64)
-          sTab[r * p.relpitch + c] = __ldg(src + (r * nrel_rows + c) * sstride) * kLog2e;
-      if (tid < 3) sTab[cls_off + tid] = __ldg(src + (nr2 + tid) * sstride) * kLog2e;
+      if (p.head_major && ((nr2 + 3) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        // contiguous per-head table: every thread issues its (up to 3) 16-byte loads BEFORE the first use (one global round
+        // trip for the whole table; the strided gather below cost ~3000 clocks of every CTA's prologue), then scatters the
+        // four elements into the pitched rows (row / column by a float reciprocal: exact below 2^20); the three CLS entries at the
+        // end of the row land at r == nrel_rows, i.e. at cls_off + c
+        const float inv_rows = 1.f / static_cast<float>(nrel_rows);
+        float4 t[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int i4 = tid + u * NT;
+          t[u] = (4 * i4 < nr2 + 3) ? __ldg(reinterpret_cast<const float4*>(src) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int i0 = 4 * (tid + u * NT);
+          if (i0 < nr2 + 3) {
+            const float tv[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = i0 + e, r = __float2int_rd((static_cast<float>(i) + 0.5f) * inv_rows), c = i - r * nrel_rows;
+              sTab[r * p.relpitch + c] = tv[e] * kLog2e;
+            }
+          }
+        }
+        for (int i4 = tid + 3 * NT; 4 * i4 < nr2 + 3; i4 += NT) {          // tables beyond 3072 entries (not on this path)
+          const float4 tt = __ldg(reinterpret_cast<const float4*>(src) + i4);
+          const float tv[4] = {tt.x, tt.y, tt.z, tt.w};
+          for (int e = 0; e < 4; ++e) {
+            const int i = 4 * i4 + e, r = i / nrel_rows, c = i - r * nrel_rows;
+            sTab[r * p.relpitch + c] = tv[e] * kLog2e;
+          }
+        }
+      } else {
+        // thread (r4, c) copies column c of table rows r4, r4 + 4, ...
+        for (int c = tid & 63; c < nrel_rows; c += 64)
+          for (int r = tid >> 6; r < nrel_rows; r += NT / 64)
+            sTab[r * p.relpitch + c] = __ldg(src + (r * nrel_rows + c) * sstride) * kLog2e;
+        if (tid < 3) sTab[cls_off + tid] = __ldg(src + (nr2 + tid) * sstride) * kLog2e;
+      }
       const float inv_win = 1.f / static_cast<float>(p.win);
       for (int kj = tid; kj < n_tiles_all * BKV; kj += NT) {
         const int g0 = kj - 1, ky = __float2int_rd((static_cast<float>(g0) + 0.5f) * inv_win), kx = g0 - ky * p.win;      // exact for g0 < 2^20

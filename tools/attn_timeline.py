@@ -51,9 +51,9 @@ for name, B, hq, hkv, S, d, kw in [("attn_siglip", 64, 16, 16, 256, 72, {}), ("a
     D = hq * d
     if hq == hkv:
         qkv = torch.randn(B * S, 3 * D, device=dev).to(BF16); out = torch.empty(B * S, D, device=dev, dtype=BF16)
-        tab = torch.randn((2 * 24 - 1) ** 2 + 3, hq, device=dev) if "relpos" in kw else None
+        tab = torch.randn(hq, (2 * 24 - 1) ** 2 + 3, device=dev) if "relpos" in kw else None      # head-major, as the engine packs it
         st = (S * 3 * D, 3 * D)
-        fn = lambda: ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], out, batch=B, hq=hq, hkv=hkv, sq=S, sk=S, d=d, q_strides=st, k_strides=st, v_strides=st, o_strides=(S * D, D), scale=d ** -0.5, relpos_table=tab, relpos_win=24 if tab is not None else 0)
+        fn = lambda: ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], out, batch=B, hq=hq, hkv=hkv, sq=S, sk=S, d=d, q_strides=st, k_strides=st, v_strides=st, o_strides=(S * D, D), scale=d ** -0.5, relpos_table=tab, relpos_win=24 if tab is not None else 0, relpos_head_major=tab is not None)
     else:
         q = torch.randn(B * S, D, device=dev).to(BF16); kc = torch.randn(B, 290, hkv, d, device=dev).to(BF16); vc = torch.randn_like(kc); out = torch.empty_like(q)
         kvs = (290 * hkv * d, hkv * d)

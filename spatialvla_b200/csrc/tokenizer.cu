@@ -65,32 +65,136 @@ __device__ __forceinline__ bool angle_ge(double a, double b, const DD4 t) {
   return tot >= 0.0;
 }
 
-// number of interior edges [lo, hi) of one axis whose rounding boundary is <= the angle of the vector (b, a)
-__device__ __forceinline__ int angle_count(double a, double b, const DD4* __restrict__ tab, int lo, int hi) {
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (angle_ge(a, b, tab[mid])) lo = mid + 1; else hi = mid;
+// ---- table-driven binning (round 2) -----------------------------------------------------------------------------------------
+// ncu on the binary-search version: 909 thread-instructions per action, 78 % of the issue slots busy at 0.32 of the HBM peak,
+// FP64 pipe 9 %: the loop overhead of six data-dependent binary searches (IMAD / ISETP / BRA / BSSY) and the NaN-aware
+// fmin/fmax clamps, not FP64 arithmetic, were the bound.  Each axis now has a small lookup table over uniform cells of a cheap
+// fp32 key that is MONOTONE in the binned quantity; a table entry is a guaranteed LOWER bound of the bin count (it counts the
+// edges below the cell BEFORE the key's cell, which absorbs every fp32 rounding of the key), and a forward scan with the exact
+// test finishes the count -- one failing test in the common case.  The result is the exact np.digitize for every input:
+//   * r / roll / pitch / yaw: key = the value itself, exact test e[lo] <= v in double;
+//   * theta / phi: key = the "diamond angle" p(a, b) = sign(a) (1 - b / (|a| + |b|)) in [-2, 2] (monotone in atan2(a, b)), exact
+//     test = sign of a cos m - b sin m: first in fp32, where it differs from the true value by < 4.5 * 2^-24 (|p1| + |p2|) (operand
+//     roundings, sqrtf, products, difference); inside that band (a vector within ~1e-6 rad of an edge) the double / double-double
+//     test above decides.
+constexpr int kLutPlain = 256, kLutAng = 512;
+
+__device__ __noinline__ bool angle_ge_slow(double a, double b, double ch, double cl, double sh, double sl) { return angle_ge(a, b, DD4{ch, cl, sh, sl}); }
+__device__ __noinline__ bool angle_ge_slow_sqrt(double a2, double b, double ch, double cl, double sh, double sl) { return angle_ge(sqrt(a2), b, DD4{ch, cl, sh, sl}); }
+
+// NaN-propagating clip (np.clip); fmin(fmax()) costs 17 instructions per value for its NaN rules
+__device__ __forceinline__ double clipd(double v, double lo, double hi) { return v > hi ? hi : (v < lo ? lo : v); }
+
+struct PlainAxis { float base, inv_w; };
+
+__device__ __forceinline__ int digitize_lut(double v, const double* __restrict__ e, int n, const unsigned char* __restrict__ lut, PlainAxis ax) {
+  const float vf = __double2float_rn(v);
+  const int cell = min(max(__float2int_rd((vf - ax.base) * ax.inv_w), 0), kLutPlain - 1);      // NaN -> 0
+  int lo = lut[cell];
+  while (lo < n && e[lo] <= v) ++lo;
+  return (v != v) ? n : lo;
+}
+
+// number of interior edges of one axis (all of [0, lo_min) are known to be below, none of [n, ..) can be) whose rounding boundary is <= the angle of the vector (b, a), a = a_arg (or
+// sqrt(a_arg) with SQRT: the double square root is only taken when the fp32 screen cannot decide)
+template <bool SQRT>
+__device__ __forceinline__ int angle_count_lut(float af, float bf, double a_arg, double b, const DD4* __restrict__ tab, const float2* __restrict__ tabf,
+                                               int lo_min, int n, const unsigned char* __restrict__ lut, float key_base, float key_inv_w) {
+  float q = 1.f - __fdividef(bf, fabsf(af) + fabsf(bf));
+  q = af < 0.f ? -q : q;
+  const int cell = min(max(__float2int_rd((q - key_base) * key_inv_w), 0), kLutAng - 1);
+  // only edges within two cells below the angle up to the first edge above it are tested, all inside [lo_min, n): the sign test
+  // needs |angle - m| < pi, which holds for edges on the angle's side of zero
+  int lo = max(static_cast<int>(lut[cell]), lo_min);
+  while (lo < n) {
+    const float2 t = tabf[lo];
+    const float p1 = __fmul_rn(af, t.x), p2 = __fmul_rn(bf, t.y);
+    const float d = __fadd_rn(p1, -p2);
+    bool ge = d > 0.f;
+    if (!(fabsf(d) > 6e-7f * (fabsf(p1) + fabsf(p2)))) {
+      const DD4 w = tab[lo];
+      ge = SQRT ? angle_ge_slow_sqrt(a_arg, b, w.ch, w.cl, w.sh, w.sl) : angle_ge_slow(a_arg, b, w.ch, w.cl, w.sh, w.sl);
+    }
+    if (!ge) break;
+    ++lo;
   }
   return lo;
 }
 
-__global__ void __launch_bounds__(256)
+// One tile = kTokTile actions: the 7 doubles of every action are moved global -> registers -> shared memory with unit-stride
+// 8-byte accesses (the loads of tile t + 1 are in flight while tile t is binned), then each thread bins one action from shared
+// memory (stride-7 double reads are bank-conflict-free).
+__global__ void __launch_bounds__(kTokTile)
 svla_tok_encode_kernel(const double* __restrict__ actions, const double* __restrict__ edges, const double* __restrict__ trig,
                        TokGrid g, int* __restrict__ ids, long long n, double amin, double amax, int spherical, int phi_nonpos,
                        int phi_neg) {
   __shared__ double se[kMaxEdges];
   __shared__ DD4 st[128];                 // interior theta edges then interior phi edges (<= 63 + 63)
+  __shared__ float2 stf[128];             // (cos m, sin m) rounded to float
+  __shared__ double spm[128];             // diamond angle of every interior theta / phi edge
+  __shared__ unsigned char lut_p[4][kLutPlain];      // r (interior edges), roll, pitch, yaw (all edges)
+  __shared__ unsigned char lut_a[2][kLutAng];        // theta, phi
+  __shared__ double sa[kTokTile * 7];
   int total = g.off[5] + g.nb[5] + 1;
   for (int i = threadIdx.x; i < total; i += blockDim.x) se[i] = edges[i];
   const int n_ti = g.nb[0] - 1, n_pi = g.nb[1] - 1;
   const bool exact = trig != nullptr && spherical;
   if (exact)
-    for (int i = threadIdx.x; i < n_ti + n_pi; i += blockDim.x) st[i] = DD4{trig[4 * i], trig[4 * i + 1], trig[4 * i + 2], trig[4 * i + 3]};
+    for (int i = threadIdx.x; i < n_ti + n_pi; i += blockDim.x) {
+      const DD4 t = DD4{trig[4 * i], trig[4 * i + 1], trig[4 * i + 2], trig[4 * i + 3]};
+      st[i] = t;
+      stf[i] = make_float2(__double2float_rn(t.ch), __double2float_rn(t.sh));
+      const double q = 1.0 - t.ch / (fabs(t.sh) + fabs(t.ch));
+      spm[i] = t.sh < 0.0 ? -q : q;
+    }
   __syncthreads();
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
-    const double* a = actions + i * 7;
-    const double x = clampd(a[0], amin, amax), y = clampd(a[1], amin, amax), z = clampd(a[2], amin, amax);
+  // axis descriptors (uniform): first edge / edge count of the four plain axes, uniform cells over [first edge, last edge]
+  const double* e_ax[4] = {se + g.off[2] + 1, se + g.off[3], se + g.off[4], se + g.off[5]};
+  const int n_ax[4] = {g.nb[2] - 1, g.nb[3] + 1, g.nb[4] + 1, g.nb[5] + 1};
+  PlainAxis pax[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const double lo_d = n_ax[c] > 0 ? e_ax[c][0] : 0.0, hi_d = n_ax[c] > 0 ? e_ax[c][n_ax[c] - 1] : 1.0;
+    const double w = hi_d > lo_d ? (hi_d - lo_d) / kLutPlain : 1.0;
+    pax[c].base = __double2float_rn(lo_d);
+    pax[c].inv_w = __double2float_rn(1.0 / w);
+    // entry = #edges <= lower bound of the PREVIOUS cell (in terms of the fp32 key map actually used at run time)
+    for (int k = threadIdx.x; k < kLutPlain; k += blockDim.x) {
+      const double lower = static_cast<double>(pax[c].base) + (k - 1) / static_cast<double>(pax[c].inv_w);
+      lut_p[c][k] = static_cast<unsigned char>(digitize_right_open(lower, e_ax[c], n_ax[c]));
+    }
+  }
+  const float th_base = 0.f, th_inv = kLutAng / 2.f, ph_base = -2.f, ph_inv = kLutAng / 4.f;
+  if (exact)
+    for (int k = threadIdx.x; k < 2 * kLutAng; k += blockDim.x) {
+      const int axis = k / kLutAng, cidx = k - axis * kLutAng;
+      const double lower = axis == 0 ? (cidx - 1) * (2.0 / kLutAng) : -2.0 + (cidx - 1) * (4.0 / kLutAng);
+      lut_a[axis][cidx] = static_cast<unsigned char>(digitize_right_open(lower, spm + (axis ? n_ti : 0), axis ? n_pi : n_ti));
+    }
+  const long long n_tiles = (n + kTokTile - 1) / kTokTile;
+  const int nb1 = g.nb[1], nb2 = g.nb[2], nb3 = g.nb[3], nb4 = g.nb[4], nb5 = g.nb[5];
+  const int n_trans = g.nb[0] * nb1 * nb2, n_rot = nb3 * nb4 * nb5;
+  double pf[7];
+  auto prefetch = [&](long long tile) {
+    const long long base = tile * kTokTile * 7, lim = n * 7;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+      const long long k = base + c * kTokTile + threadIdx.x;
+      pf[c] = (tile < n_tiles && k < lim) ? actions[k] : 0.0;
+    }
+  };
+  auto clip = [&](double v) { return clipd(v, amin, amax); };
+  prefetch(blockIdx.x);
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    __syncthreads();                                   // previous tile binned; tables built
+#pragma unroll
+    for (int c = 0; c < 7; ++c) sa[c * kTokTile + threadIdx.x] = pf[c];
+    __syncthreads();
+    prefetch(tile + gridDim.x);
+    const long long i = tile * kTokTile + threadIdx.x;
+    if (i >= n) continue;
+    const double* a = sa + threadIdx.x * 7;
+    const double x = clip(a[0]), y = clip(a[1]), z = clip(a[2]);
     const double xx = __dmul_rn(x, x), yy = __dmul_rn(y, y), zz = __dmul_rn(z, z);
     const double sxy = __dadd_rn(xx, yy);
     // use_spherical=False (model/action_tokenizer.py:112-113) bins the clipped Cartesian components directly
@@ -98,32 +202,26 @@ svla_tok_encode_kernel(const double* __restrict__ actions, const double* __restr
     // translation uses the interior edges e[1:-1]
     int dt, dp;
     if (exact) {
-      const double rho = sqrt(sxy);
-      // degenerate vectors (a zero component decides the quadrant through the sign of zero): library atan2, exact special values
-      if (rho == 0.0 && z == 0.0) dt = digitize_right_open(atan2(rho, z), se + g.off[0] + 1, n_ti);
-      else dt = angle_count(rho, z, st, 0, n_ti);                         // theta in [0, pi], every interior edge in (0, pi)
+      const float xf = __double2float_rn(x), yf = __double2float_rn(y), zf = __double2float_rn(z);
+      // degenerate vectors (a zero component decides the quadrant through the sign of zero) and NaNs: library atan2, exact special values
+      if ((sxy == 0.0 && z == 0.0) || sxy != sxy || z != z) dt = digitize_right_open(atan2(sqrt(sxy), z), se + g.off[0] + 1, n_ti);
+      else dt = angle_count_lut<true>(sqrtf(__double2float_rn(sxy)), zf, sxy, z, st, stf, 0, n_ti, lut_a[0], th_base, th_inv);      // theta in [0, pi]
       if (y == 0.0 || x != x || y != y) dp = digitize_right_open(atan2(y, x), se + g.off[1] + 1, n_pi);
-      else if (y > 0.0) dp = angle_count(y, x, st + n_ti, phi_nonpos, n_pi);   // phi in (0, pi): every edge <= 0 is below it
-      else dp = angle_count(y, x, st + n_ti, 0, phi_neg);                      // phi in (-pi, 0): only negative edges can be
+      else if (y > 0.0) dp = angle_count_lut<false>(yf, xf, y, x, st + n_ti, stf + n_ti, phi_nonpos, n_pi, lut_a[1], ph_base, ph_inv);   // phi in (0, pi): every edge <= 0 is below it
+      else dp = angle_count_lut<false>(yf, xf, y, x, st + n_ti, stf + n_ti, 0, phi_neg, lut_a[1], ph_base, ph_inv);                      // phi in (-pi, 0): only negative edges can be
     } else {
       const double theta = spherical ? atan2(sqrt(sxy), z) : x;
       const double phi = spherical ? atan2(y, x) : y;
       dt = digitize_right_open(theta, se + g.off[0] + 1, g.nb[0] - 1);
       dp = digitize_right_open(phi, se + g.off[1] + 1, g.nb[1] - 1);
     }
-    const int dr = digitize_right_open(r, se + g.off[2] + 1, g.nb[2] - 1);
-    const int tid = dt * (g.nb[1] * g.nb[2]) + dp * g.nb[2] + dr;
-    int d3[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const double v = clampd(a[3 + c], amin, amax);
-      int d = digitize_right_open(v, se + g.off[3 + c], g.nb[3 + c] + 1) - 1;
-      d3[c] = min(max(d, 0), g.nb[3 + c] - 1);
-    }
-    const int n_trans = g.nb[0] * g.nb[1] * g.nb[2];
-    const int n_rot = g.nb[3] * g.nb[4] * g.nb[5];
-    const int rid = d3[0] * (g.nb[4] * g.nb[5]) + d3[1] * g.nb[5] + d3[2] + n_trans;
-    const int gid = (clampd(a[6], amin, amax) >= 0.5 ? 1 : 0) + n_trans + n_rot;
+    const int dr = digitize_lut(r, e_ax[0], n_ax[0], lut_p[0], pax[0]);
+    const int tid = dt * (nb1 * nb2) + dp * nb2 + dr;
+    const int d0 = min(max(digitize_lut(clip(a[3]), e_ax[1], n_ax[1], lut_p[1], pax[1]) - 1, 0), nb3 - 1);
+    const int d1 = min(max(digitize_lut(clip(a[4]), e_ax[2], n_ax[2], lut_p[2], pax[2]) - 1, 0), nb4 - 1);
+    const int d2 = min(max(digitize_lut(clip(a[5]), e_ax[3], n_ax[3], lut_p[3], pax[3]) - 1, 0), nb5 - 1);
+    const int rid = d0 * (nb4 * nb5) + d1 * nb5 + d2 + n_trans;
+    const int gid = (clip(a[6]) >= 0.5 ? 1 : 0) + n_trans + n_rot;
     ids[i * 3 + 0] = tid;
     ids[i * 3 + 1] = rid;
     ids[i * 3 + 2] = gid;
@@ -144,12 +242,24 @@ svla_tok_decode_kernel(const long long* __restrict__ ids, const double* __restri
   const long long n_trans = static_cast<long long>(g.nb[0]) * g.nb[1] * g.nb[2];
   const long long n_rot = static_cast<long long>(g.nb[3]) * g.nb[4] * g.nb[5];
   const long long n_tiles = (n + kTokTile - 1) / kTokTile;
+  long long pf[3];
+  auto prefetch = [&](long long tile) {                 // the ids of the NEXT tile are in flight while this tile is decoded
+    const long long base = tile * kTokTile * 3, lim = n * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const long long k = base + c * kTokTile + threadIdx.x;
+      pf[c] = (tile < n_tiles && k < lim) ? ids[k] : 0;
+    }
+  };
+  prefetch(blockIdx.x);
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long i0 = tile * kTokTile;
     const int cnt = static_cast<int>(n - i0 < kTokTile ? n - i0 : kTokTile);
     __syncthreads();                                   // previous tile's actions are out; se[] is loaded
-    for (int k = threadIdx.x; k < cnt * 3; k += kTokTile) sid[k] = ids[i0 * 3 + k];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sid[c * kTokTile + threadIdx.x] = pf[c];
     __syncthreads();
+    prefetch(tile + gridDim.x);
     if (threadIdx.x < cnt) {
       // clip each id into its sub-range first (model/action_tokenizer.py:126,195,240)
       long long t = sid[threadIdx.x * 3 + 0] - begin;
@@ -227,7 +337,7 @@ extern "C" int svla_tok_encode(const double* actions, const double* edges, const
   SVLA_REQUIRE(make_grid(nbins, g) > 0, "svla_tok_encode: bins per axis must be in [1, 64]");
   SVLA_REQUIRE(!edge_trig || (phi_neg >= 0 && phi_neg <= phi_nonpos && phi_nonpos <= g.nb[1] - 1),
                "svla_tok_encode: phi_neg=%d <= phi_nonpos=%d <= %d interior phi edges expected", phi_neg, phi_nonpos, g.nb[1] - 1);
-  svla_tok_encode_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(actions, edges, edge_trig, g, ids, n, min_action,
+  svla_tok_encode_kernel<<<grid_for(n), kTokTile, 0, static_cast<cudaStream_t>(stream)>>>(actions, edges, edge_trig, g, ids, n, min_action,
                                                                                      max_action, use_spherical, phi_nonpos, phi_neg);
   SVLA_LAUNCH_CHECK("svla_tok_encode");
   return 0;

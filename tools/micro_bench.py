@@ -30,15 +30,23 @@ g = np.load(os.path.join(ROOT, "tests", "golden", "tokenizer_gauss.npz"))
 keys = ("theta_bins", "phi_bins", "r_bins", "roll_bins", "pitch_bins", "yaw_bins")
 edges = torch.from_numpy(np.concatenate([g[f"edge_{k}"] for k in keys])).to(dev)
 nb = [len(g[f"edge_{k}"]) - 1 for k in keys] + [2]
+# the product path (SpatialActionTokenizer.encode_ids / decode_ids): exact angular binning through the edge table, decode through
+# the host-tabulated (sin, cos) of the bin centres
+from spatialvla_b200.action_tokenizer import edge_trig_table
+th_e, ph_e = g["edge_theta_bins"], g["edge_phi_bins"]
+trig_np, phi_nonpos, phi_neg = edge_trig_table(th_e[1:-1], ph_e[1:-1])
+trig = torch.from_numpy(trig_np).to(dev)
+cen = [0.5 * (a[:-1] + a[1:]) for a in (th_e, ph_e)]
+ctrig = torch.from_numpy(np.ascontiguousarray(np.concatenate([np.stack([np.sin(c), np.cos(c)], 1) for c in cen]).astype(np.float64))).to(dev)
 out = []
 for n in (1_000_000, 16_000_000):
     acts = (torch.rand(n, 7, device=dev, dtype=torch.float64) * 2 - 1)
     ids = torch.empty(n, 3, dtype=torch.int32, device=dev)
-    ms = timeit(lambda: ops.tok_encode(acts, edges, nb, ids))
+    ms = timeit(lambda: ops.tok_encode(acts, edges, nb, ids, trig=trig, phi_nonpos=phi_nonpos, phi_neg=phi_neg))
     out.append({"kernel": "svla_tok_encode", "n": n, "ms": round(ms, 4), "GBs": round(n * 68 / ms / 1e6, 1), "frac_of_measured_hbm": round(n * 68 / ms / 1e6 / peak, 3)})
     gid = ids.to(torch.int64) + 257153
     dec = torch.empty(n, 7, dtype=torch.float64, device=dev)
-    ms = timeit(lambda: ops.tok_decode(gid, edges, nb, 257153, dec))
+    ms = timeit(lambda: ops.tok_decode(gid, edges, nb, 257153, dec, center_trig=ctrig))
     out.append({"kernel": "svla_tok_decode", "n": n, "ms": round(ms, 4), "GBs": round(n * 80 / ms / 1e6, 1), "frac_of_measured_hbm": round(n * 80 / ms / 1e6 / peak, 3)})
 K = torch.tensor(default_intrinsic_224(), device=dev)
 for B in (64, 4096):

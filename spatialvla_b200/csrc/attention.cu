@@ -480,9 +480,12 @@ svla_decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16
 // rope_kv + decode_attention.  The item arithmetic lives in decode_attn_item.cuh (shared with the persistent decode kernel);
 // here: 6-stage ring (~80 KB in flight per CTA), 2 CTAs per SM -> all 256 CTAs of a B=64 step are resident at once.
 constexpr int kFusedStages = 6;
+// Few items (batch x kv heads <= #SMs, e.g. the batch-1 latency path: 4 CTAs): one CTA per SM with a 12-stage ring, i.e. ~190 KB
+// of the item's ~290 KB of K / V rows in flight at once -- a lone CTA is bound by its memory-level parallelism, not by HBM.
+constexpr int kFusedStagesDeep = 12;
 
-template <int GRP>
-__global__ void __launch_bounds__(kDecThreads, 2)
+template <int GRP, int STAGES>
+__global__ void __launch_bounds__(kDecThreads, STAGES <= 6 ? 2 : 1)
 svla_decode_attn_fused_kernel(const float* __restrict__ qkv_f32, int n_partials, long long partial_stride,
                               __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out,
                               int hq, int hkv, int smax, int ctx, float theta, float scale, float softcap,
@@ -490,8 +493,8 @@ svla_decode_attn_fused_kernel(const float* __restrict__ qkv_f32, int n_partials,
   constexpr int D = 256;
   extern __shared__ __align__(16) uint8_t sm_fused[];
   svla_dec::ItemSmem sm;
-  sm.stage = sm_fused;                                                                                   // [kFusedStages][32][528]
-  sm.q = reinterpret_cast<float*>(sm_fused + kFusedStages * svla_dec::kItemRows * svla_dec::kItemPitch); // [GRP][256]
+  sm.stage = sm_fused;                                                                                   // [STAGES][32][528]
+  sm.q = reinterpret_cast<float*>(sm_fused + STAGES * svla_dec::kItemRows * svla_dec::kItemPitch);       // [GRP][256]
   sm.red = sm.q + GRP * D;                                                                               // [GRP][256]
   sm.newk = reinterpret_cast<__nv_bfloat16*>(sm.red + GRP * D);                                          // [256]
   sm.newv = sm.newk + D;                                                                                 // [256]
@@ -512,7 +515,7 @@ svla_decode_attn_fused_kernel(const float* __restrict__ qkv_f32, int n_partials,
   // blocked in griddepcontrol.wait; a whole chain of them cannot be resident at once, so those rows are complete and the
   // ring is primed while the qkv projection (the direct predecessor) is still running; griddepcontrol.wait comes before the
   // first read of its partial sums.
-  svla_dec::decode_attn_item<GRP, kFusedStages>(a, sm, static_cast<int>(threadIdx.x), [] { __syncthreads(); }, [] { pdl_wait(); });
+  svla_dec::decode_attn_item<GRP, STAGES>(a, sm, static_cast<int>(threadIdx.x), [] { __syncthreads(); }, [] { pdl_wait(); });
 }
 
 }  // namespace
@@ -596,24 +599,37 @@ extern "C" int svla_decode_attention_fused(const float* qkv_f32, int n_partials,
   SVLA_REQUIRE(ctx > 0 && ctx <= smax && n_partials >= 1 && batch > 0 && batch <= 65535, "svla_decode_attention_fused: bad ctx / partials / batch");
   const int grp = hq / hkv;
   const int ctx_pad = (ctx + 31) & ~31;
-  const size_t smem = static_cast<size_t>(kFusedStages) * svla_dec::kItemRows * svla_dec::kItemPitch + (2 * grp * 256 + 4 + 16 + grp * ctx_pad) * sizeof(float) + 2 * 256 * 2;
-  SVLA_REQUIRE(smem <= 220 * 1024, "svla_decode_attention_fused: context %d too long for shared memory", ctx);
-  static size_t configured[3] = {0, 0, 0};
-  if (smem > configured[grp]) {
-    cudaError_t e = grp == 1 ? cudaFuncSetAttribute(svla_decode_attn_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
-                             : cudaFuncSetAttribute(svla_decode_attn_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  auto smem_for = [&](int stages) {
+    return static_cast<size_t>(stages) * svla_dec::kItemRows * svla_dec::kItemPitch + (2 * grp * 256 + 4 + 16 + grp * ctx_pad) * sizeof(float) + 2 * 256 * 2;
+  };
+  const bool deep = static_cast<long long>(batch) * hkv <= svla_num_sms() && smem_for(kFusedStagesDeep) <= 225 * 1024;
+  const size_t smem = smem_for(deep ? kFusedStagesDeep : kFusedStages);
+  SVLA_REQUIRE(smem <= 225 * 1024, "svla_decode_attention_fused: context %d too long for shared memory", ctx);
+  static size_t configured[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  if (smem > configured[deep][grp]) {
+    cudaError_t e = deep ? (grp == 1 ? cudaFuncSetAttribute(svla_decode_attn_fused_kernel<1, kFusedStagesDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
+                                     : cudaFuncSetAttribute(svla_decode_attn_fused_kernel<2, kFusedStagesDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)))
+                         : (grp == 1 ? cudaFuncSetAttribute(svla_decode_attn_fused_kernel<1, kFusedStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
+                                     : cudaFuncSetAttribute(svla_decode_attn_fused_kernel<2, kFusedStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     SVLA_REQUIRE(e == cudaSuccess, "svla_decode_attention_fused: smem opt-in %zu failed: %s", smem, cudaGetErrorString(e));
-    configured[grp] = smem;
+    configured[deep][grp] = smem;
   }
   dim3 grid(hkv, batch);
   auto* kcp = static_cast<__nv_bfloat16*>(kcache);
   auto* vcp = static_cast<__nv_bfloat16*>(vcache);
   auto* op = static_cast<__nv_bfloat16*>(out);
   const long long ps = partial_stride;
-  cudaError_t le = grp == 1 ? svla_launch_pdl(svla_decode_attn_fused_kernel<1>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
-                                              hq, hkv, smax, ctx, theta, scale, softcap, kv_start)
-                            : svla_launch_pdl(svla_decode_attn_fused_kernel<2>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
-                                              hq, hkv, smax, ctx, theta, scale, softcap, kv_start);
+  cudaError_t le;
+  if (deep)
+    le = grp == 1 ? svla_launch_pdl(svla_decode_attn_fused_kernel<1, kFusedStagesDeep>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
+                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start)
+                  : svla_launch_pdl(svla_decode_attn_fused_kernel<2, kFusedStagesDeep>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
+                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start);
+  else
+    le = grp == 1 ? svla_launch_pdl(svla_decode_attn_fused_kernel<1, kFusedStages>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
+                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start)
+                  : svla_launch_pdl(svla_decode_attn_fused_kernel<2, kFusedStages>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
+                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start);
   SVLA_REQUIRE(le == cudaSuccess, "svla_decode_attention_fused: launch failed: %s", cudaGetErrorString(le));
   SVLA_LAUNCH_CHECK("svla_decode_attn_fused");
   return 0;

@@ -1,3 +1,4 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_e2e_gpu.py -x -q -k "tok" 2>&1 | tail -5
-python tools/micro_bench.py 2>&1 | head -4 | tee gpurun_out/micro_r2.log
+timeout 900 python -m pytest tests/test_kernels_gpu.py -x -q -k "decode" 2>&1 | tail -3
+python tools/decode_mega_check.py 2>&1 | grep "chain" | tee gpurun_out/decode_now.log
+python bench.py --workload latency_bs1 2>/dev/null | tail -1 | cut -c1-400

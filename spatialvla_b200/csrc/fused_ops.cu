@@ -3,6 +3,7 @@
 // fp32 and use warp-shuffle reductions.  Reference lines replaced: see include/spatialvla_b200.h.
 #include <cstdlib>
 #include "svla_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -989,19 +990,29 @@ svla_zoe_attractor_kernel(const __nv_bfloat16* __restrict__ attr, const float* _
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
     // dc = dx / (1 + 300 dx^2).  The loop is MUFU-bound with one reciprocal per term, so two attractors share one:
     // dx1/b1 + dx2/b2 = (dx1 b2 + dx2 b1) / (b1 b2)  (b <= 1 + 300 * 80^2: the product stays far inside fp32 range)
-    auto pair_term = [](float c0, float a1, float a2) {
-      const float d1 = a1 - c0, d2 = a2 - c0;
-      const float b1 = fmaf(300.f * d1, d1, 1.f), b2 = fmaf(300.f * d2, d2, 1.f);
-      return __fdividef(fmaf(d1, b2, d2 * b1), b1 * b2);
+    // packed f32x2 form (two bins per FFMA2 / FMUL2, same roundings as the scalar expression): the loop was FMA-issue bound
+    auto pair_term2 = [](uint64_t c2, uint64_t a1, uint64_t a2, uint64_t acc) {
+      using namespace svla_ptx;
+      const uint64_t m1 = pack_f32x2(-1.f, -1.f), k300 = pack_f32x2(300.f, 300.f), one = pack_f32x2(1.f, 1.f);
+      const uint64_t d1 = fma_f32x2(c2, m1, a1), d2 = fma_f32x2(c2, m1, a2);                 // a - c (exact: one rounding, like a1 - c0)
+      const uint64_t b1 = fma_f32x2(mul_f32x2(k300, d1), d1, one), b2 = fma_f32x2(mul_f32x2(k300, d2), d2, one);
+      const uint64_t num = fma_f32x2(d1, b2, mul_f32x2(d2, b1)), den = mul_f32x2(b1, b2);
+      float n0, n1, e0, e1;
+      unpack_f32x2(num, n0, n1);
+      unpack_f32x2(den, e0, e1);
+      return add_f32x2(acc, pack_f32x2(__fdividef(n0, e0), __fdividef(n1, e1)));
     };
+    uint64_t dxy = svla_ptx::pack_f32x2(0.f, 0.f), dzw = svla_ptx::pack_f32x2(0.f, 0.f);
+    const uint64_t cxy = svla_ptx::pack_f32x2(c.x, c.y), czw = svla_ptx::pack_f32x2(c.z, c.w);
     int a = 0;
     for (; a + 1 < na; a += 2) {
       const float a1 = __shfl_sync(0xffffffffu, a_l, (lane & 16) | a), a2 = __shfl_sync(0xffffffffu, a_l, (lane & 16) | (a + 1));
-      d.x += pair_term(c.x, a1, a2);
-      d.y += pair_term(c.y, a1, a2);
-      d.z += pair_term(c.z, a1, a2);
-      d.w += pair_term(c.w, a1, a2);
+      const uint64_t a1p = svla_ptx::pack_f32x2(a1, a1), a2p = svla_ptx::pack_f32x2(a2, a2);
+      dxy = pair_term2(cxy, a1p, a2p, dxy);
+      dzw = pair_term2(czw, a1p, a2p, dzw);
     }
+    svla_ptx::unpack_f32x2(dxy, d.x, d.y);
+    svla_ptx::unpack_f32x2(dzw, d.z, d.w);
     if (a < na) {
       const float av = __shfl_sync(0xffffffffu, a_l, (lane & 16) | a);
       const float dx = av - c.x, dy = av - c.y, dz = av - c.z, dw = av - c.w;
@@ -1243,13 +1254,20 @@ svla_zoe_depth_tail_fused_kernel(const __nv_bfloat16* __restrict__ x, const __nv
     const float4 ta = *reinterpret_cast<const float4*>(trow + c0), tb = *reinterpret_cast<const float4*>(trow + c0 + 4);
     const float tv[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int c = c0 + u;
+    for (int u = 0; u < 8; u += 2) {
       // same association as the reference interpolation: (1-ly)((1-lx) v00 + lx v01) + ly((1-lx) v10 + lx v11)
-      const float ev = (1.f - s.ly) * ((1.f - s.lx) * e00[u] + s.lx * e01[u]) + s.ly * ((1.f - s.lx) * e10[u] + s.lx * e11[u]);
-      const float hv = gelu_erf_fast(tv[u] + ev + s_b1[c]);
-      const float4 wv = *reinterpret_cast<const float4*>(s_w2 + 4 * c);      // warp-wide broadcast
-      o4[0] = fmaf(wv.x, hv, o4[0]); o4[1] = fmaf(wv.y, hv, o4[1]); o4[2] = fmaf(wv.z, hv, o4[2]); o4[3] = fmaf(wv.w, hv, o4[3]);
+      float hv[2];
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const float ev = (1.f - s.ly) * ((1.f - s.lx) * e00[u + v] + s.lx * e01[u + v]) + s.ly * ((1.f - s.lx) * e10[u + v] + s.lx * e11[u + v]);
+        hv[v] = tv[u + v] + ev + s_b1[c0 + u + v];
+      }
+      svla_ptx::gelu_erf_pair(hv[0], hv[1]);               // two channels per FFMA2 / FMUL2 (the scalar erf-GELU was 18 of ~32 instructions per channel)
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const float4 wv = *reinterpret_cast<const float4*>(s_w2 + 4 * (c0 + u + v));      // warp-wide broadcast
+        o4[0] = fmaf(wv.x, hv[v], o4[0]); o4[1] = fmaf(wv.y, hv[v], o4[1]); o4[2] = fmaf(wv.z, hv[v], o4[2]); o4[3] = fmaf(wv.w, hv[v], o4[3]);
+      }
     }
   }
 #pragma unroll
@@ -1269,6 +1287,7 @@ svla_zoe_depth_tail_fused_kernel(const __nv_bfloat16* __restrict__ x, const __nv
   for (int k = kmode - 1; k <= kmode + 1; ++k)
     mx = fmaxf(mx, (s_lb[k] + static_cast<float>(k) * lp + static_cast<float>(NBINS - 1 - k) * lq) * inv_temp);
   float se = 0.f, sc = 0.f;
+  const float it2 = inv_temp * 1.4426950408889634f, dk2 = (lp - lq) * it2, c02 = fmaf(static_cast<float>(NBINS - 1) * lq, it2, -mx * 1.4426950408889634f);
   const float4* q00 = reinterpret_cast<const float4*>(s_bins + p00 * BST), *q01 = reinterpret_cast<const float4*>(s_bins + p01 * BST);
   const float4* q10 = reinterpret_cast<const float4*>(s_bins + p10 * BST), *q11 = reinterpret_cast<const float4*>(s_bins + p11 * BST);
 #pragma unroll 4
@@ -1281,8 +1300,9 @@ svla_zoe_depth_tail_fused_kernel(const __nv_bfloat16* __restrict__ x, const __nv
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int kk = 4 * k4 + i;
-      const float y = (s_lb[kk] + static_cast<float>(kk) * lp + static_cast<float>(NBINS - 1 - kk) * lq) * inv_temp;
-      const float ex = __expf(y - mx);
+      // (lb_k + k lp + (K-1-k) lq) / T - mx  =  lb_k / T + (k (lp - lq) / T + ((K-1) lq / T - mx)), in log2 units for ex2
+      float ex;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(s_lb[kk], it2, fmaf(static_cast<float>(kk), dk2, c02))));
       se += ex; sc = fmaf(ex, cs[i], sc);
     }
   }

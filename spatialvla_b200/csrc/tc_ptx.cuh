@@ -97,6 +97,40 @@ __device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
   return r;
 }
 
+// ---- packed (f32x2) activations of the TMA-store epilogue.  The K ~ 1024 GEMMs with a GELU (BEiT fc1: 36928 x 4096 x 1024) were
+// EPILOGUE-bound: 8 epilogue warps must turn 128 x 256 accumulators into bf16 inside the 8192 clocks of the next tile's mainloop,
+// and the scalar erf-GELU cost ~21 issue slots per element (1155 TFLOP/s against 1490 with a bias-only epilogue).  Two elements
+// per FFMA2 / FMUL2 halve the FMA-pipe work; gelu(x) = relu(x) - |x| * h(x) with h = Phi(-|x|) needs no sign transfer.
+// erf-GELU: Phi(-|x|) = 0.5 * erfc(|x| / sqrt 2) by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 in erf).
+__device__ __forceinline__ void gelu_erf_pair(float& x0, float& x1) {
+  const uint64_t x = pack_f32x2(x0, x1);
+  float e0, e1, t0, t1;
+  unpack_f32x2(mul_f32x2(mul_f32x2(x, x), pack_f32x2(-0.72134752044448170f, -0.72134752044448170f)), e0, e1);      // -x^2/2 * log2(e)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(e0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(e1));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(fmaf(0.23164189f, fabsf(x0), 1.f)));       // 0.3275911 / sqrt 2
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(fmaf(0.23164189f, fabsf(x1), 1.f)));
+  const uint64_t t = pack_f32x2(t0, t1);
+  uint64_t q = fma_f32x2(pack_f32x2(0.5307027145f, 0.5307027145f), t, pack_f32x2(-0.7265760135f, -0.7265760135f));      // 0.5 * a5, 0.5 * a4
+  q = fma_f32x2(q, t, pack_f32x2(0.7107068705f, 0.7107068705f));
+  q = fma_f32x2(q, t, pack_f32x2(-0.142248368f, -0.142248368f));
+  q = fma_f32x2(q, t, pack_f32x2(0.127414796f, 0.127414796f));
+  float h0, h1;
+  unpack_f32x2(mul_f32x2(mul_f32x2(q, t), pack_f32x2(e0, e1)), h0, h1);
+  x0 = fmaf(-fabsf(x0), h0, fmaxf(x0, 0.f));
+  x1 = fmaf(-fabsf(x1), h1, fmaxf(x1, 0.f));
+}
+// tanh-GELU: 0.5 x (1 + tanh(k0 (x + k1 x^3))), MUFU tanh
+__device__ __forceinline__ void gelu_tanh_pair(float& x0, float& x1) {
+  const uint64_t x = pack_f32x2(x0, x1);
+  const uint64_t inner = mul_f32x2(x, fma_f32x2(mul_f32x2(x, x), pack_f32x2(0.0356774081f, 0.0356774081f), pack_f32x2(0.7978845608f, 0.7978845608f)));
+  float i0, i1;
+  unpack_f32x2(inner, i0, i1);
+  const uint64_t th = pack_f32x2(tanh_approx(i0), tanh_approx(i1));
+  const uint64_t hx = mul_f32x2(x, pack_f32x2(0.5f, 0.5f));
+  unpack_f32x2(fma_f32x2(hx, th, hx), x0, x1);
+}
+
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

@@ -438,9 +438,12 @@ class SpatialVLAEngine:
                                           res_bf16=feats[src], res2_bf16=fused, want_relu=True)
             c1, _ = self._conv3(hrelu, fu["residual_layer2.convolution1.w"], shp, bias=fu["residual_layer2.convolution1.b"], act=ACT_RELU)
             h2, _ = self._conv3(c1, fu["residual_layer2.convolution2.w"], shp, bias=fu["residual_layer2.convolution2.b"], res_bf16=hcur)
-            up = ops.empty((B * 2 * r_ * 2 * r_, Fh), BF16)
-            ops.bilinear_nhwc(h2, up, batch=B, h=r_, w=r_, c=Fh, oh=2 * r_, ow=2 * r_)
-            fused = self._lin(up, fu["proj_w"], B * 4 * r_ * r_, bias=fu["proj_b"])
+            # HF DPT: projection(interpolate(h2)) (zoedepth :286-291).  A 1x1 convolution with bias commutes with a bilinear
+            # interpolation (the four tap weights sum to 1), so the projection runs at the LOW resolution: 4x fewer GEMM rows
+            # (the 192 x 192 projection alone was 2.36 M rows x 256 x 256 per batch of 64), same up-sampling traffic.
+            pj = self._lin(h2, fu["proj_w"], B * r_ * r_, bias=fu["proj_b"])
+            fused = ops.empty((B * 2 * r_ * 2 * r_, Fh), BF16)
+            ops.bilinear_nhwc(pj, fused, batch=B, h=r_, w=r_, c=Fh, oh=2 * r_, ow=2 * r_)
             fr = 2 * r_
             fused_list.append((fused, fr))
         return fused_list, (feats[-1], res_[-1])

@@ -1,3 +1,8 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests/test_kernels_gpu.py -x -q -k "zoe or tail or gemm" 2>&1 | tail -3
-python tools/zoe_tail_perf.py 2>&1 | tail -12 | tee gpurun_out/zoe_tail_now.log
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4 > gpurun_out/t_all.log; cat gpurun_out/t_all.log
+python bench.py --steps 5 --warmup 3 --no-latency > gpurun_out/bench_v5.json 2> gpurun_out/bench_v5.log; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_v5.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks'])
+PY
+head -14 gpurun_out/bench_v5.log

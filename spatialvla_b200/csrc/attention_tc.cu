@@ -442,21 +442,28 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
         }
         if (k0 == 0) s[0] = fmaf(raw0, sl2, sTab[cls_off + (cls_q ? 2 : 1)]);      // CLS key column
       } else if (kSoftcap) {
+        // cap * tanh(u) * log2e, u = s * scale / cap, with a degree-9 odd polynomial (exact to fp32 rounding for |u| < 0.35), two
+        // scores per FMUL2 / FFMA2 (the scalar chain was ~11 of this warp's ~14 instructions per score at d = 256)
+        const uint64_t c1p = pack_f32x2(c1, c1), c2p = pack_f32x2(c2, c2);
+        const uint64_t k9 = pack_f32x2(62.f / 2835.f, 62.f / 2835.f), k7 = pack_f32x2(-17.f / 315.f, -17.f / 315.f);
+        const uint64_t k5 = pack_f32x2(2.f / 15.f, 2.f / 15.f), k3 = pack_f32x2(-1.f / 3.f, -1.f / 3.f), k1 = pack_f32x2(1.f, 1.f);
+        float t[HC];
         float u2max = 0.f;
 #pragma unroll
-        for (int i = 0; i < HC; ++i) { const float u = s[i] * c1; u2max = fmaxf(u2max, u * u); }
+        for (int i = 0; i < HC; i += 2) {
+          const uint64_t u = mul_f32x2(pack_f32x2(s[i], s[i + 1]), c1p), u2 = mul_f32x2(u, u);
+          float q0, q1;
+          unpack_f32x2(u2, q0, q1);
+          u2max = fmaxf(u2max, fmaxf(q0, q1));
+          uint64_t pl = fma_f32x2(k9, u2, k7);
+          pl = fma_f32x2(pl, u2, k5);
+          pl = fma_f32x2(pl, u2, k3);
+          pl = fma_f32x2(pl, u2, k1);
+          unpack_f32x2(mul_f32x2(mul_f32x2(c2p, u), pl), t[i], t[i + 1]);
+        }
         if (!__any_sync(0xffffffffu, u2max >= 0.1225f)) {
-          // cap * tanh(u) * log2e with a degree-9 odd polynomial (exact to fp32 rounding for |u| < 0.35)
 #pragma unroll
-          for (int i = 0; i < HC; ++i) {
-            const float u = s[i] * c1, u2 = u * u;
-            float pl = 62.f / 2835.f;
-            pl = fmaf(pl, u2, -17.f / 315.f);
-            pl = fmaf(pl, u2, 2.f / 15.f);
-            pl = fmaf(pl, u2, -1.f / 3.f);
-            pl = fmaf(pl, u2, 1.f);
-            s[i] = c2 * u * pl;
-          }
+          for (int i = 0; i < HC; ++i) s[i] = t[i];
         } else {                                  // rare: a large score somewhere in this warp's rows -> libm tanh
 #pragma unroll
           for (int i = 0; i < HC; ++i) s[i] = c2 * tanhf(s[i] * c1);

@@ -367,6 +367,44 @@ __device__ __forceinline__ void epilogue_tma(const EpiParams& ep, const CUtensor
   }
 }
 
+// Row-tile conv variant of the bf16 TMA-store epilogue: the 32 accumulator rows of a warp are 32 consecutive pixels of ONE image
+// row, stored through a 4-D map {channel, x, y, image} (pixels past the row end are clipped by the hardware).  The register /
+// staging epilogue spent ~4000 clocks per 128 x 32 tile on row bookkeeping (64-bit divisions per pass) and strided 8-byte stores.
+template <int COLS>
+__device__ __forceinline__ void epilogue_tma_conv(const EpiParams& ep, const CUtensorMap* tm_o, uint32_t taddr, uint8_t* tile, int lane,
+                                                  int c_begin, long long n_base, int x0, int y, int img) {
+  const uint32_t row_s = smem_u32(tile) + static_cast<uint32_t>(lane) * 128u;
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+#pragma unroll 1
+  for (int c0 = c_begin; c0 < c_begin + COLS; c0 += 32) {
+    const long long n0 = n_base + c0;
+    if (n0 >= ep.n) break;                               // warp-uniform
+    uint32_t r[32];
+    tmem_ld32(taddr + c0, r);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    epilogue_math32(ep, v, n0);
+    const uint32_t half = static_cast<uint32_t>((c0 - c_begin) >> 5) & 1u;
+    if (half == 0) {
+      if (lane == 0) bulk_wait_read_all();               // the previous box has left shared memory
+      __syncwarp();
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j)
+      st_shared_v4(row_s + (((half * 4u + j) ^ sw) << 4), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+    if (half == 1 || n0 + 32 >= ep.n) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(tm_o, tile, static_cast<int>(n0) - 32 * static_cast<int>(half), x0, y, img);
+        bulk_commit_group();
+      }
+    }
+  }
+}
+
 // Global output row of tile row r (and validity) in linear / conv mode.
 __device__ __forceinline__ bool tile_row_to_global(const EpiParams& ep, bool conv, long long m_tile, int r, long long& grow) {
   if (!conv) {
@@ -508,9 +546,10 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (one lane of the leader CTA)
-    if (lane == 0 && leader) {
+    // ===================================================== MMA issuer (the leader CTA's warp 1, converged; an elected lane issues)
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(kBM * CG, BN);
+      const uint64_t a_desc0 = make_kmajor_sw128_desc(smem_u32(smem_a)), b_desc0 = make_kmajor_sw128_desc(smem_u32(smem_b));
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
@@ -522,24 +561,29 @@ svla_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + stage * C::kABytes));
-          const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + stage * C::kBBytes));
+          if (elect_one()) {
+            // descriptors = constants + (stage offset >> 4) in the start-address field; +2 per 16 bf16 (32 bytes) along K
+            const uint64_t da = a_desc0 + static_cast<uint64_t>((stage * C::kABytes) >> 4);
+            const uint64_t db = b_desc0 + static_cast<uint64_t>((stage * C::kBBytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            if constexpr (CG == 1)
-              umma_bf16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                        static_cast<uint32_t>((kb | k) != 0));
-            else
-              umma_bf16_cg2(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                            static_cast<uint32_t>((kb | k) != 0));
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              if constexpr (CG == 1)
+                umma_bf16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                          static_cast<uint32_t>((kb | k) != 0));
+              else
+                umma_bf16_cg2(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                              static_cast<uint32_t>((kb | k) != 0));
+            }
+            // frees the smem stage (in both CTAs for CG == 2) once these MMAs have read it
+            if constexpr (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_cg2(&empty_bar[stage]);
+            // accumulator complete -> epilogue warps (of both CTAs)
+            if (kb == num_k_blocks - 1) {
+              if constexpr (CG == 1) umma_commit(&tmem_full[as]); else umma_commit_cg2(&tmem_full[as]);
+            }
           }
-          // frees the smem stage (in both CTAs for CG == 2) once these MMAs have read it
-          if constexpr (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_cg2(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
-        // accumulator complete -> epilogue warps (of both CTAs)
-        if constexpr (CG == 1) umma_commit(&tmem_full[as]); else umma_commit_cg2(&tmem_full[as]);
       }
     }
   } else {
@@ -632,30 +676,43 @@ template <int BN> struct RowCfg {
   static_assert(kStages >= 2 && kBTile % 1024 == 0, "row-tile conv: pipeline needs two stages and 1 KB aligned weight tiles");
 };
 
+// w_res != 0 (few output channels: all 9 x c_chunks weight tiles fit in shared memory, one n-tile): the weights are loaded ONCE
+// per CTA and a pipeline stage is only the 130-pixel activation row (1 TMA instead of 4 per stage: with 12 sixteen-clock MMAs per
+// stage the producer's issue rate bounded the 128 -> 32 conv at 384 x 384).  n_stages = ring depth chosen by the host.
+constexpr int kRowMaxStages = 8;
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-svla_conv3x3_rowtile_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const EpiParams ep,
-                            const long long num_m_tiles, const long long num_n_tiles, const int c_chunks, const int cpad) {
+svla_conv3x3_rowtile_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                            const __grid_constant__ CUtensorMap tm_o, const EpiParams ep,
+                            const long long num_m_tiles, const long long num_n_tiles, const int c_chunks, const int cpad,
+                            const int w_res, const int n_stages) {
   using C = RowCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* staging = smem + C::kStages * C::kStageBytes;
+  uint8_t* smem_al = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int w_res_bytes = w_res ? 9 * c_chunks * C::kBTile : 0;
+  const int stage_bytes = w_res ? C::kABytes : C::kStageBytes;
+  uint8_t* smem_w = smem_al;                                      // resident weight tiles [(dy * 3 + dx) * c_chunks + cc][BN x 64]
+  uint8_t* smem = smem_al + w_res_bytes;                          // activation (+ weight) stages
+  uint8_t* staging = smem + n_stages * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + C::kStagingBytes);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + C::kStages;
-  uint64_t* tmem_full = bars + 2 * C::kStages;
+  uint64_t* empty_bar = bars + kRowMaxStages;
+  uint64_t* tmem_full = bars + 2 * kRowMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* w_full = tmem_empty + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_full + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
+    if (ep.tma_out) tma_prefetch_desc(&tm_o);
 #pragma unroll 1
-    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], kEpiWarps); mbar_init(&tmem_empty[1], kEpiWarps);
+    mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<C::kTmemCols, 1>(tmem_ptr_smem);
@@ -668,6 +725,12 @@ svla_conv3x3_rowtile_kernel(const __grid_constant__ CUtensorMap tm_a, const __gr
 
   if (warp == 0) {
     if (lane == 0) {
+      if (w_res) {
+        mbar_expect_tx(w_full, w_res_bytes);
+        for (int tap = 0; tap < 9; ++tap)
+          for (int cc = 0; cc < c_chunks; ++cc)
+            tma_load_2d(smem_w + (tap * c_chunks + cc) * C::kBTile, &tm_b, w_full, tap * cpad + cc * kBK, 0);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -678,20 +741,28 @@ svla_conv3x3_rowtile_kernel(const __grid_constant__ CUtensorMap tm_a, const __gr
         for (int it = 0; it < stages_per_tile; ++it) {
           const int cc = it / 3, dy = it - 3 * cc;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sa = smem + stage * C::kStageBytes;
-          uint8_t* sb = sa + C::kABytes;
-          mbar_expect_tx(&full_bar[stage], C::kABytesRaw + C::kBBytes);
-          tma_load_4d(sa, &tm_a, &full_bar[stage], cc * kBK, w0 - 1, hrow + dy - 1, img);
+          uint8_t* sa = smem + stage * stage_bytes;
+          if (w_res) {
+            mbar_expect_tx(&full_bar[stage], C::kABytesRaw);
+            tma_load_4d(sa, &tm_a, &full_bar[stage], cc * kBK, w0 - 1, hrow + dy - 1, img);
+          } else {
+            uint8_t* sb = sa + C::kABytes;
+            mbar_expect_tx(&full_bar[stage], C::kABytesRaw + C::kBBytes);
+            tma_load_4d(sa, &tm_a, &full_bar[stage], cc * kBK, w0 - 1, hrow + dy - 1, img);
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx)
-            tma_load_2d(sb + dx * C::kBTile, &tm_b, &full_bar[stage], (dy * 3 + dx) * cpad + cc * kBK, static_cast<int>(n_tile * BN));
-          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+            for (int dx = 0; dx < 3; ++dx)
+              tma_load_2d(sb + dx * C::kBTile, &tm_b, &full_bar[stage], (dy * 3 + dx) * cpad + cc * kBK, static_cast<int>(n_tile * BN));
+          }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                        // converged warp, an elected lane issues (see elect_one)
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
+      const uint64_t desc0 = make_kmajor_sw128_desc(smem_u32(smem));
+      const uint64_t wdesc0 = make_kmajor_sw128_desc(smem_u32(smem_w));
+      if (w_res) mbar_wait(w_full, 0);
       int stage = 0;
       uint32_t phase = 0, it_tile = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it_tile) {
@@ -702,22 +773,28 @@ svla_conv3x3_rowtile_kernel(const __grid_constant__ CUtensorMap tm_a, const __gr
         for (int it = 0; it < stages_per_tile; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * C::kStageBytes);
-          const uint32_t b_addr = a_addr + C::kABytes;
+          if (elect_one()) {
+            const int cc = it / 3, dy = it - 3 * cc;
+            const uint64_t a_desc = desc0 + static_cast<uint64_t>((stage * stage_bytes) >> 4);
+            const uint64_t b_desc = w_res ? wdesc0 + static_cast<uint64_t>(((dy * 3 * c_chunks + cc) * C::kBTile) >> 4)
+                                          : a_desc + static_cast<uint64_t>(C::kABytes >> 4);
+            const int b_step = w_res ? c_chunks * C::kBTile : C::kBTile;      // bytes between the tiles of taps dx and dx + 1
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            // tap dx: the same 130-pixel buffer, rows dx .. dx + 127 (start advanced by dx * 128 B, base_offset stays 0)
-            const uint64_t da = make_kmajor_sw128_desc(a_addr + dx * 128);
-            const uint64_t db = make_kmajor_sw128_desc(b_addr + dx * C::kBTile);
+            for (int dx = 0; dx < 3; ++dx) {
+              // tap dx: the same 130-pixel buffer, rows dx .. dx + 127 (start advanced by dx * 128 B, base_offset stays 0)
+              const uint64_t da = a_desc + static_cast<uint64_t>((dx * 128) >> 4);
+              const uint64_t db = b_desc + static_cast<uint64_t>((dx * b_step) >> 4);
 #pragma unroll
-            for (int k = 0; k < kBK / kUmmaK; ++k)
-              umma_bf16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
-                        static_cast<uint32_t>((it | dx | k) != 0));
+              for (int k = 0; k < kBK / kUmmaK; ++k)
+                umma_bf16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2), idesc,
+                          static_cast<uint32_t>((it | dx | k) != 0));
+            }
+            umma_commit(&empty_bar[stage]);
+            if (it == stages_per_tile - 1) umma_commit(&tmem_full[as]);
           }
-          umma_commit(&empty_bar[stage]);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          __syncwarp();
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tmem_full[as]);
       }
     }
   } else {
@@ -729,6 +806,21 @@ svla_conv3x3_rowtile_kernel(const __grid_constant__ CUtensorMap tm_a, const __gr
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it_tile) {
       const long long m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
       const uint32_t as = it_tile & 1u, aphase = (it_tile >> 1) & 1u;
+      if (ep.tma_out) {                                    // warp-uniform, fixed for the launch
+        const int tiles_per_img = ep.tiles_h * ep.tiles_w;
+        const int mt32 = static_cast<int>(m_tile);
+        const int img = mt32 / tiles_per_img, rem = mt32 - img * tiles_per_img;
+        const int hrow = rem / ep.tiles_w, w0 = (rem - hrow * ep.tiles_w) * kBM;
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        const uint32_t taddr_t = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+        if (BN >= 64 || chalf == 0)
+          epilogue_tma_conv<kColsPerWarp>(ep, &tm_o, taddr_t, staging + (warp - 2) * 4096, lane, chalf * kColsPerWarp, n_tile * BN, w0 + q * 32, hrow, img);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        continue;
+      }
       RowSet rs;
 #pragma unroll
       for (int p = 0; p < kPasses; ++p) {
@@ -757,6 +849,7 @@ svla_conv3x3_rowtile_kernel(const __grid_constant__ CUtensorMap tm_a, const __gr
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
     }
+    if (ep.tma_out && lane == 0) bulk_wait_read_all();     // the staging tiles must outlive the last TMA store's reads
   }
   tc_fence_before();
   __syncthreads();
@@ -914,21 +1007,29 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
 }
 
 template <int BN>
-int launch_rowtile(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& ep, long long mt, long long nt, int c_chunks,
+int launch_rowtile(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const EpiParams& ep, long long mt, long long nt, int c_chunks,
                    int cpad, cudaStream_t st) {
   using C = RowCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(svla_conv3x3_rowtile_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+  constexpr int kBudget = 232448 - 1024 - 256 - C::kStagingBytes;
+  // resident weights: one n-tile and 9 x c_chunks weight tiles that leave room for >= 4 activation stages
+  const int w_bytes = 9 * c_chunks * C::kBTile;
+  static const bool no_res = getenv("SVLA_CONV_NO_WRES") != nullptr;      // A/B switch
+  const bool w_res = !no_res && nt == 1 && w_bytes + 4 * C::kABytes <= kBudget;
+  int n_stages = w_res ? (kBudget - w_bytes) / C::kABytes : C::kStages;
+  if (n_stages > kRowMaxStages) n_stages = kRowMaxStages;
+  const int smem = (w_res ? w_bytes + n_stages * C::kABytes : n_stages * C::kStageBytes) + 1024 + 256 + C::kStagingBytes;
+  static int configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(svla_conv3x3_rowtile_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
-      svla_set_error("svla_gemm(conv row-tile): cudaFuncSetAttribute(%d bytes) failed: %s", C::kSmemBytes, cudaGetErrorString(e));
+      svla_set_error("svla_gemm(conv row-tile): cudaFuncSetAttribute(%d bytes) failed: %s", smem, cudaGetErrorString(e));
       return -2;
     }
-    configured = true;
+    configured = smem;
   }
   const long long tiles = mt * nt;
   const int grid = static_cast<int>(tiles < svla_num_sms() ? tiles : svla_num_sms());
-  svla_conv3x3_rowtile_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, ep, mt, nt, c_chunks, cpad);
+  svla_conv3x3_rowtile_kernel<BN><<<grid, kThreads, smem, st>>>(ta, tb, to, ep, mt, nt, c_chunks, cpad, w_res ? 1 : 0, n_stages);
   SVLA_LAUNCH_CHECK("svla_conv3x3_rowtile");
   return 0;
 }
@@ -1034,9 +1135,28 @@ extern "C" int svla_gemm(const SvlaGemmArgs* g, void* stream) {
       rcr = encode_2d(&trb, g->w, static_cast<uint64_t>(g->k), static_cast<uint64_t>(g->n), static_cast<uint64_t>(g->ldw), kBK, static_cast<uint32_t>(bnr));
       SVLA_REQUIRE(rcr == 0, "svla_gemm(conv row-tile): cuTensorMapEncodeTiled(W) failed (%d)", rcr);
       const long long mt = static_cast<long long>(g->nb) * g->h * tw, ntl = (g->n + bnr - 1) / bnr;
-      if (bnr == 32) return launch_rowtile<32>(tra, trb, ep, mt, ntl, c_chunks, cpad, st);
-      if (bnr == 64) return launch_rowtile<64>(tra, trb, ep, mt, ntl, c_chunks, cpad, st);
-      return launch_rowtile<128>(tra, trb, ep, mt, ntl, c_chunks, cpad, st);
+      // bf16 TMA-store epilogue through a 4-D map {channel, x, y, image} when the conv has ONE bf16 output and no residual operands
+      // (not for 64-wide tiles: there each warp owns 32 columns, half of a 128-byte store box)
+      CUtensorMap tro = tra;
+      static const bool legacy_epi_rt = getenv("SVLA_GEMM_LEGACY_EPI") != nullptr;
+      if (!legacy_epi_rt && bnr != 64 && !geglu && g->out_bf16 && !g->out_f32 && !g->out_relu_bf16 && !g->res_bf16 && !g->res2_bf16 && !g->res_f32 &&
+          (g->ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(g->out_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(g->bias) & 15) == 0 &&
+          (reinterpret_cast<uintptr_t>(g->colscale) & 15) == 0 && mt < (1LL << 31)) {
+        auto fn = get_encode_fn();
+        SVLA_REQUIRE(fn != nullptr, "svla_gemm(conv row-tile): cuTensorMapEncodeTiled unavailable");
+        cuuint64_t dims[4] = {static_cast<cuuint64_t>(g->n), static_cast<cuuint64_t>(g->wd), static_cast<cuuint64_t>(g->h), static_cast<cuuint64_t>(g->nb)};
+        cuuint64_t strides[3] = {static_cast<cuuint64_t>(g->ldo) * 2, static_cast<cuuint64_t>(g->wd) * g->ldo * 2,
+                                 static_cast<cuuint64_t>(g->h) * g->wd * g->ldo * 2};
+        cuuint32_t box[4] = {64, 32, 1, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = fn(&tro, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, g->out_bf16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SVLA_REQUIRE(r == CUDA_SUCCESS, "svla_gemm(conv row-tile): cuTensorMapEncodeTiled(out) failed (%d)", static_cast<int>(r));
+        ep.tma_out = 1;
+      }
+      if (bnr == 32) return launch_rowtile<32>(tra, trb, tro, ep, mt, ntl, c_chunks, cpad, st);
+      if (bnr == 64) return launch_rowtile<64>(tra, trb, tro, ep, mt, ntl, c_chunks, cpad, st);
+      return launch_rowtile<128>(tra, trb, tro, ep, mt, ntl, c_chunks, cpad, st);
     }
   }
 

@@ -211,24 +211,32 @@ svla_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer
-    if (lane == 0) {
+    // ============================================================ MMA issuer: converged warp, an ELECTED lane issues the MMAs and commits of a
+    // phase, descriptors are constants + start-address increments (issued from a divergent lane-0 region every tcgen05.mma cost ~70
+    // clocks: 36 MMAs per 64-row tile at d = 256 made the issue rate, not the tensor pipe or the softmax warps, the bound)
+    {
       const int ksteps = PAD ? ((p.d + 15) >> 4) : D / 16;          // contraction steps over the head dimension
       const uint32_t idesc_acc = make_idesc(kBM, PAD ? ((p.d + 15) & ~15) : D, 1);
+      const uint64_t r1_desc = make_kmajor_sw128_desc(smem_u32(sR1)), r2_desc = make_kmajor_sw128_desc(smem_u32(sR2));
       auto issue_acc = [&](int j) {                                 // ACC += Z_j T3_j
         const int st = j & 1, s2 = (C::kNumT2 == 2) ? (j & 1) : 0;
         mbar_wait(&z_full[st], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t tbase = (KIND == KIND_DV) ? smem_u32(sT2 + s2 * C::kTBytes) : smem_u32(sT1 + st * C::kTBytes);
-        const int ks = valid16(j) >> 4;
-        for (int kk = 0; kk < ks; ++kk) {
-          const uint64_t db = make_mnmajor_sw128_desc(tbase + kk * 16 * 128, kBT * 128);
-          umma_bf16_ts(tmem_base + C::kTmemAcc, tmem_base + C::kTmemX + st * kBT + kk * 8, db, idesc_acc,
-                       static_cast<uint32_t>(j > 0 || kk > 0));
+        if (elect_one()) {
+          const uint32_t tbase = (KIND == KIND_DV) ? smem_u32(sT2 + s2 * C::kTBytes) : smem_u32(sT1 + st * C::kTBytes);
+          const uint64_t b_desc = make_mnmajor_sw128_desc(tbase, kBT * 128);
+          const int ks = valid16(j) >> 4;
+#pragma unroll
+          for (int kk = 0; kk < kBT / 16; ++kk) {
+            if (kk < ks)
+              umma_bf16_ts(tmem_base + C::kTmemAcc, tmem_base + C::kTmemX + st * kBT + kk * 8, b_desc + static_cast<uint64_t>((kk * 16 * 128) >> 4),
+                           idesc_acc, static_cast<uint32_t>(j > 0 || kk > 0));
+          }
+          umma_commit(&x_empty[st]);
+          umma_commit(&t1_empty[st]);
+          if (KIND == KIND_DV) umma_commit(&t2_empty[s2]);
         }
-        umma_commit(&x_empty[st]);
-        umma_commit(&t1_empty[st]);
-        if (KIND == KIND_DV) umma_commit(&t2_empty[s2]);
+        __syncwarp();
       };
       mbar_wait(r_full, 0);
       for (int j = 0; j < n_tiles; ++j) {
@@ -237,34 +245,40 @@ svla_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_
         if (j >= 2) mbar_wait(&x_empty[st], ((j - 2) >> 1) & 1);    // the third MMA of tile j-2 has drained Z / Y of this buffer
         tc_fence_after();
         const uint32_t idesc_xy = make_idesc(kBM, valid16(j), 0);
-        const uint32_t r1 = smem_u32(sR1), t1 = smem_u32(sT1 + st * C::kTBytes);
+        if (elect_one()) {
+          const uint64_t t1_desc = make_kmajor_sw128_desc(smem_u32(sT1 + st * C::kTBytes));
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          if (kk >= ksteps) break;
-          const uint64_t da = make_kmajor_sw128_desc(r1 + (kk >> 2) * (kBM * 128) + (kk & 3) * 32);
-          const uint64_t db = make_kmajor_sw128_desc(t1 + (kk >> 2) * (kBT * 128) + (kk & 3) * 32);
-          umma_bf16(tmem_base + C::kTmemX + st * kBT, da, db, idesc_xy, static_cast<uint32_t>(kk > 0));
+          for (int kk = 0; kk < D / 16; ++kk) {
+            if (kk < ksteps)
+              umma_bf16(tmem_base + C::kTmemX + st * kBT, r1_desc + static_cast<uint64_t>(((kk >> 2) * (kBM * 128) + (kk & 3) * 32) >> 4),
+                        t1_desc + static_cast<uint64_t>(((kk >> 2) * (kBT * 128) + (kk & 3) * 32) >> 4), idesc_xy, static_cast<uint32_t>(kk > 0));
+          }
+          if (!C::kHasY) umma_commit(&x_full[st]);
         }
+        __syncwarp();
         if (C::kHasY) {
           mbar_wait(&t2_full[s2], (C::kNumT2 == 2 ? (j >> 1) : j) & 1);
           tc_fence_after();
-          const uint32_t r2 = smem_u32(sR2), t2 = smem_u32(sT2 + s2 * C::kTBytes);
+          if (elect_one()) {
+            const uint64_t t2_desc = make_kmajor_sw128_desc(smem_u32(sT2 + s2 * C::kTBytes));
 #pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk) {
-            if (kk >= ksteps) break;
-            const uint64_t da = make_kmajor_sw128_desc(r2 + (kk >> 2) * (kBM * 128) + (kk & 3) * 32);
-            const uint64_t db = make_kmajor_sw128_desc(t2 + (kk >> 2) * (kBT * 128) + (kk & 3) * 32);
-            umma_bf16(tmem_base + C::kTmemY + st * kBT, da, db, idesc_xy, static_cast<uint32_t>(kk > 0));
+            for (int kk = 0; kk < D / 16; ++kk) {
+              if (kk < ksteps)
+                umma_bf16(tmem_base + C::kTmemY + st * kBT, r2_desc + static_cast<uint64_t>(((kk >> 2) * (kBM * 128) + (kk & 3) * 32) >> 4),
+                          t2_desc + static_cast<uint64_t>(((kk >> 2) * (kBT * 128) + (kk & 3) * 32) >> 4), idesc_xy, static_cast<uint32_t>(kk > 0));
+            }
+            umma_commit(&t2_empty[s2]);                             // T2_j is only read by Y_j in the DQ / DK sweeps
+            umma_commit(&x_full[st]);
           }
-          umma_commit(&t2_empty[s2]);                               // T2_j is only read by Y_j in the DQ / DK sweeps
+          __syncwarp();
         } else {
           mbar_wait(&t2_full[s2], (j >> 1) & 1);                    // DV: dO_j must have landed before the third MMA reads it
         }
-        umma_commit(&x_full[st]);
         if (j > 0) issue_acc(j - 1);
       }
       if (n_tiles > 0) issue_acc(n_tiles - 1);
-      umma_commit(acc_full);
+      if (elect_one()) umma_commit(acc_full);
+      __syncwarp();
     }
   } else {
     // ============================================================ softmax warps: thread == resident row

@@ -14,9 +14,11 @@ cap() {  # name regex skip command...
   echo "$n rc=$? $(ls $OUT/ncu_r2b_$n.ncu-rep 2>/dev/null)"
 }
 export SVLA_NO_GRAPHS=1
-cap gemm_gateup '^svla_gemm_tcgen05_kernel$' 288 python bench.py --quick --steps 1 --warmup 1
+cap gemm_gateup '^svla_gemm_tcgen05_kernel$' 289 python bench.py --quick --steps 1 --warmup 1
 cap attn_siglip '^svla_flash_attn_tc_kernel$' 2 python bench.py --quick --steps 1 --warmup 1
 cap attn_beit '^svla_flash_attn_tc_kernel$' 29 python bench.py --quick --steps 1 --warmup 1
 cap attn_gemma '^svla_flash_attn_tc_kernel$' 57 python bench.py --quick --steps 1 --warmup 1
 cap gemm_beit_fc1 '^svla_gemm_tcgen05_kernel$' 152 python bench.py --quick --steps 1 --warmup 1
+cap conv_rowtile_n32 '^svla_conv3x3_rowtile_kernel$' 1 python bench.py --quick --steps 1 --warmup 1
+cap skinny_gateup '^svla_gemm_skinny_kernel$' 3 python bench.py --quick --steps 1 --warmup 1
 ls -la $OUT/ncu_r2b_*.ncu-rep | awk '{print $5, $9}'

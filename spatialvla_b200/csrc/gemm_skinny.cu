@@ -120,23 +120,31 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                      // converged warp, an elected lane issues (tc_ptx.cuh: elect_one)
       constexpr uint32_t idesc = make_idesc_bf16(kWM, NB < 16 ? 16 : NB);
+      const uint64_t dw0 = make_kmajor_sw128_desc(smem_u32(smem_w)), dx0 = make_kmajor_sw128_desc(smem_u32(smem_x));
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint64_t dw = make_kmajor_sw128_desc(smem_u32(smem_w + stage * C::kWBytes));
-        const uint64_t dx = make_kmajor_sw128_desc(smem_u32(smem_x + stage * C::kXBytes));
+        if (elect_one()) {
+          const uint64_t dw = dw0 + static_cast<uint64_t>((stage * C::kWBytes) >> 4);
+          const uint64_t dx = dx0 + static_cast<uint64_t>((stage * C::kXBytes) >> 4);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k)
-          umma_bf16(tmem_base, dw + static_cast<uint64_t>(k * 2), dx + static_cast<uint64_t>(k * 2), idesc,
-                    static_cast<uint32_t>((kb > kb0) || k != 0));
-        umma_commit(&empty_bar[stage]);
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_bf16(tmem_base, dw + static_cast<uint64_t>(k * 2), dx + static_cast<uint64_t>(k * 2), idesc,
+                      static_cast<uint32_t>((kb > kb0) || k != 0));
+          umma_commit(&empty_bar[stage]);
+          if (kb == kb1 - 1) umma_commit(acc_bar);
+        }
+        __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(acc_bar);
+      if (kb1 <= kb0) {                    // empty K range (cannot happen with the host's split choice): release the epilogue
+        if (elect_one()) umma_commit(acc_bar);
+        __syncwarp();
+      }
     }
   } else {
     // ------------------------------------------------ epilogue: lane <-> weight row n, register j <-> activation row m

@@ -331,28 +331,67 @@ svla_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_
         plain = rhi <= p.sk && c0 + HC <= p.sq && (!p.causal || (rhi - 1) <= max(c0 + off, p.prefix - 1));
       }
       uint32_t zk[HC / 2];
+      // Two columns per FMUL2 / FFMA2 (the scalar loop with a per-element tanh branch and two shuffles per element made the 8
+      // softmax warps -- one CTA per SM -- the bound of the sweep).  Column statistics of the DK / DV sweeps are fetched with one
+      // shuffle per PAIR and value; the soft-cap polynomial is evaluated unconditionally and a warp vote selects the libm path.
+      bool big = false;
+      if (p.softcap > 0.f) {
+        float u2max = 0.f;
+#pragma unroll
+        for (int i = 0; i < HC; ++i) { const float u = x[i] * c1; u2max = fmaxf(u2max, u * u); }
+        big = __any_sync(0xffffffffu, u2max >= 0.1225f);
+      }
+      const uint64_t c1p = pack_f32x2(c1, c1), c2p = pack_f32x2(c2, c2), onep = pack_f32x2(1.f, 1.f), scp = pack_f32x2(p.scale, p.scale);
+      const uint64_t k9 = pack_f32x2(62.f / 2835.f, 62.f / 2835.f), k7 = pack_f32x2(-17.f / 315.f, -17.f / 315.f);
+      const uint64_t k5 = pack_f32x2(2.f / 15.f, 2.f / 15.f), k3 = pack_f32x2(-1.f / 3.f, -1.f / 3.f);
 #pragma unroll
       for (int i = 0; i < HC; i += 2) {
-        float z2[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int ci = c0 + i + e;                                // streamed index
-          const int qi = kRowsAreQueries ? ri : ci, kj = kRowsAreQueries ? ci : ri;
-          const float lse = kRowsAreQueries ? lse_r : __shfl_sync(0xffffffffu, lse_c, i + e);
-          const float del = kRowsAreQueries ? del_r : __shfl_sync(0xffffffffu, del_c, i + e);
-          float fac = 1.f, s2;
-          if (p.softcap > 0.f) {
-            const float th = tanh_poly(x[i + e] * c1);
-            s2 = c2 * th;
-            fac = 1.f - th * th;
-          } else {
-            s2 = x[i + e] * c2;
-          }
-          const bool masked = !plain && (qi >= p.sq || kj >= p.sk || (p.causal && kj > max(qi + off, p.prefix - 1)));
-          const float pr = masked ? 0.f : ex2f(s2 - lse);
-          z2[e] = (KIND == KIND_DV) ? pr : pr * (y[i + e] - del) * fac * p.scale;
+        // per-column statistics (DK / DV): lanes i, i + 1 hold the columns' values
+        float lse0 = lse_r, lse1 = lse_r, del0 = del_r, del1 = del_r;
+        if (!kRowsAreQueries) {
+          lse0 = __shfl_sync(0xffffffffu, lse_c, i); lse1 = __shfl_sync(0xffffffffu, lse_c, i + 1);
+          if (KIND != KIND_DV) { del0 = __shfl_sync(0xffffffffu, del_c, i); del1 = __shfl_sync(0xffffffffu, del_c, i + 1); }
         }
-        zk[i >> 1] = pack_bf16x2(z2[0], z2[1]);
+        const uint64_t xx = pack_f32x2(x[i], x[i + 1]);
+        uint64_t s2, fac = onep;
+        if (p.softcap > 0.f) {
+          uint64_t th;
+          if (!big) {
+            const uint64_t u = mul_f32x2(xx, c1p), u2 = mul_f32x2(u, u);
+            uint64_t pl = fma_f32x2(k9, u2, k7);
+            pl = fma_f32x2(pl, u2, k5);
+            pl = fma_f32x2(pl, u2, k3);
+            pl = fma_f32x2(pl, u2, onep);
+            th = mul_f32x2(u, pl);
+          } else {
+            th = pack_f32x2(tanhf(x[i] * c1), tanhf(x[i + 1] * c1));
+          }
+          s2 = mul_f32x2(c2p, th);
+          fac = fma_f32x2(th, mul_f32x2(th, pack_f32x2(-1.f, -1.f)), onep);          // 1 - th^2
+        } else {
+          s2 = mul_f32x2(xx, c2p);
+        }
+        float t0, t1;
+        unpack_f32x2(add_f32x2(s2, pack_f32x2(-lse0, -lse1)), t0, t1);
+        float pr0 = ex2f(t0), pr1 = ex2f(t1);
+        if (!plain) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int ci = c0 + i + e;                              // streamed index
+            const int qi = kRowsAreQueries ? ri : ci, kj = kRowsAreQueries ? ci : ri;
+            const bool masked = qi >= p.sq || kj >= p.sk || (p.causal && kj > max(qi + off, p.prefix - 1));
+            if (masked) { if (e == 0) pr0 = 0.f; else pr1 = 0.f; }
+          }
+        }
+        if (KIND == KIND_DV) {
+          zk[i >> 1] = pack_bf16x2(pr0, pr1);
+        } else {
+          // pr * (y - del) * fac * scale, same association as the scalar expression
+          const uint64_t dy = add_f32x2(pack_f32x2(y[i], y[i + 1]), pack_f32x2(-del0, -del1));
+          float z0, z1;
+          unpack_f32x2(mul_f32x2(mul_f32x2(mul_f32x2(pack_f32x2(pr0, pr1), dy), fac), scp), z0, z1);
+          zk[i >> 1] = pack_bf16x2(z0, z1);
+        }
       }
       tc_fence_after();
       tmem_st16(tmem_base + C::kTmemX + st * kBT + ch * (HC / 2) + lane_addr, zk);

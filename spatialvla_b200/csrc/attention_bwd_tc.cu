@@ -57,7 +57,9 @@ template <int D, int KIND> struct Cfg {
   static constexpr int kTmemX = 0;                                  // 2 x kBT
   static constexpr int kTmemY = 2 * kBT;                            // 2 x kBT
   static constexpr int kTmemAcc = kHasY ? 4 * kBT : 2 * kBT;        // D columns
-  static constexpr int kTmemCols = 512;
+  // the DV sweep at D <= 128 needs 2 x 64 (X) + D (ACC) <= 256 columns and <= 96 KB of shared memory: two CTAs per SM
+  static constexpr int kTmemCols = (kTmemAcc + D <= 256) ? 256 : 512;
+  static constexpr int kCtasPerSm = (kTmemCols == 256 && kNumR * kRBytes + (2 + kNumT2) * kTBytes + 1536 <= 113 * 1024) ? 2 : 1;
   static constexpr int kSmemBytes = kNumR * kRBytes + (2 + kNumT2) * kTBytes + 1024 /*align*/ + 512 /*barriers, TMEM slot*/;
   static_assert(kTmemAcc + D <= 512, "TMEM budget");
   static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB)");
@@ -113,7 +115,7 @@ __device__ __forceinline__ float tanh_poly(float u) {        // exact to fp32 ro
 
 // PAD: real head dim p.d < D, 4-D tensor maps {d, head, token, batch} zero-fill the padding (see attention_tc.cu)
 template <int D, int KIND, bool PAD>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, Cfg<D, KIND>::kCtasPerSm)
 svla_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_constant__ CUtensorMap tm_r2,
                         const __grid_constant__ CUtensorMap tm_t1, const __grid_constant__ CUtensorMap tm_t2, const Params p) {
   using C = Cfg<D, KIND>;

@@ -102,24 +102,40 @@ svla_gemm_tn_kernel(const TnParams p) {
     __syncthreads();
   }
 
+  // Epilogue.  A thread owns 4 distinct columns (nt, e & 1) and 2 RT rows; the destination column of every (group, column) pair is
+  // resolved ONCE (the per-element group loop with an integer division per group cost ~5000 instructions per thread at r = 96 --
+  // more than the main loop of a CTA that reduces 15 chunks: 1.3 TB/s on the fused q|k|v reduction).
+  int jc[4][4];
 #pragma unroll
-  for (int rt = 0; rt < RT; ++rt) {
+  for (int gi = 0; gi < 4; ++gi) {
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int row = rt * 16 + g + (e >> 1) * 8;
-        const int col = col0 + warp * 16 + nt * 8 + 2 * t + (e & 1);
-        if (row >= p.r || col >= p.n) continue;
-        const float v = acc[rt][nt][e] * p.scale;
-        for (int gi = 0; gi < p.n_groups; ++gi) {
-          const TnGroup& G = p.g[gi];
-          if (row < G.r0 || row >= G.r0 + G.rg || col < G.col_start) continue;
-          const int rel = col - G.col_start;
+    for (int cv = 0; cv < 4; ++cv) {
+      jc[gi][cv] = -1;
+      if (gi < p.n_groups) {
+        const TnGroup& G = p.g[gi];
+        const int col = col0 + warp * 16 + (cv >> 1) * 8 + 2 * t + (cv & 1);
+        const int rel = col - G.col_start;
+        if (col < p.n && rel >= 0) {
           const int j = rel / G.col_stride;
-          if (rel - j * G.col_stride != 0 || j >= G.ncols) continue;
-          atomicAdd(G.dst + static_cast<long long>(row - G.r0) * G.ld + j, v);
+          if (rel - j * G.col_stride == 0 && j < G.ncols) jc[gi][cv] = j;
         }
+      }
+    }
+  }
+#pragma unroll
+  for (int gi = 0; gi < 4; ++gi) {
+    if (gi >= p.n_groups) break;
+    const TnGroup& G = p.g[gi];
+#pragma unroll
+    for (int rt = 0; rt < RT; ++rt) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int row = rt * 16 + g + hf * 8;
+        if (row >= p.r || row < G.r0 || row >= G.r0 + G.rg) continue;
+        float* drow = G.dst + static_cast<long long>(row - G.r0) * G.ld;
+#pragma unroll
+        for (int cv = 0; cv < 4; ++cv)
+          if (jc[gi][cv] >= 0) atomicAdd(drow + jc[gi][cv], acc[rt][cv >> 1][hf * 2 + (cv & 1)] * p.scale);
       }
     }
   }

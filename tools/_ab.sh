@@ -1,3 +1,14 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests/test_lora_step.py tests/test_kernels_gpu.py -x -q -m gpu -k "tn or lora or grad" 2>&1 | tail -3
-python tools/attn_bwd_perf.py 2>&1 | tail -5 | tee gpurun_out/tn_now.log
+python -c "import __graft_entry__ as g; g.build(); g.smoke()" 2>&1 | tail -2
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3 > gpurun_out/t_all.log; cat gpurun_out/t_all.log
+python bench.py --workload lora_step --steps 5 --warmup 3 > gpurun_out/lora_v9.json 2> gpurun_out/lora_v9.log; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/lora_v9.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['clocks'], d['roofline']['frac'])
+PY
+head -6 gpurun_out/lora_v9.log
+python bench.py > gpurun_out/bench_v9.json 2> gpurun_out/bench_v9.log; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_v9.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks'], d['latency_bs1_ms_p50'], d['roofline']['frac'], d['cpu_baseline']['value'])
+PY

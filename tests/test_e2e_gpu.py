@@ -305,7 +305,8 @@ def test_full_size_parity_832_positions(cuda_device):
     """north_star's gate at the size it is stated for: SpatialVLA-4B-224, batch 64, 64 x 13 = 832 teacher-forced positions (SURVEY.md
     §8d) against the fp32 oracle's offline golden (oracle/gen_golden_full.py -> tests/golden/full_4b_b64.npz).
     MEASURED (profiles/parity_r2_*.txt): element-wise logits |d| <= 2e-2 + 2e-2 |ref| on 100 % of the sampled logits (rms 0.005), RAW
-    action-slice argmax agreement 99.16 % (7 of 832) -- BELOW north_star's 99.5 % (<= 4 of 832).  Every mismatch is an oracle near-tie
+    action-slice argmax agreement 98.9-99.2 % (9 / 7 of 832 in two code versions with identical logit rms: the flipped near-ties move
+    with the rounding order) -- BELOW north_star's 99.5 % (<= 4 of 832).  Every mismatch is an oracle near-tie
     (top-1/top-2 margin <= 0.014 against a median of 0.156, i.e. inside 3 sigma of the bf16 logit noise, which comes from the 26 Gemma2
     layers: feeding the oracle's fp32 image features changes the noise from 0.0050 to 0.0047, tools/parity_sources.py); the oracle's
     OWN bf16 run flips 2.9 % of its positions.  The assertions below state exactly that and nothing softer: all logits inside the
@@ -319,7 +320,7 @@ def test_full_size_parity_832_positions(cuda_device):
     assert res["logit_rms"] < 8e-3 and res["logit_max_abs"] < 4e-2, res
     noise_band = 4.0 * (2 ** 0.5) * res["logit_rms"]                          # 4 sigma of the difference of two noisy logits
     assert all(m <= noise_band for m in res["mismatch_margins"]), (noise_band, res["mismatch_margins"])
-    assert res["agreement"] >= 0.985, res                                     # measured 0.9916; north_star's 0.995 is NOT met (see docstring)
+    assert res["agreement"] >= 0.985, res                                     # measured 0.9892 - 0.9916; north_star's 0.995 is NOT met (see docstring)
     assert res["agreement"] >= res["calibration"]["agreement"] + 0.01          # clearly above what the reference arithmetic in bf16 reaches
     assert res["router_head"] == res["router_head_oracle"]
 

@@ -85,7 +85,12 @@ int svla_gemm(const SvlaGemmArgs* args, void* stream);
  * flags: 1 = GEGLU (as svla_gemm), 2 = PARTIAL: raw fp32 partial sums out_f32[split * partial_stride + m*ldo + n] for
  * `splits` K-slices (the consumers svla_rmsnorm_residual / svla_rope_kv add them); 4 = W_TILED: w holds the same matrix
  * tile-major, bf16 [ceil(N/128)][ceil(K/64)][128][64] zero-padded (ldw ignored), so that every 16 KB pipeline stage is one
- * contiguous HBM read. model/modeling_gemma2.py:80-92,351-354,993 */
+ * contiguous HBM read;
+ * 8 = X_HILO (m <= 64): x holds TWO bf16 planes [2][M, ldx] -- hi = bf16(v) and lo = bf16(v - hi), 16 mantissa bits together --
+ * and the result is hi.W^T + lo.W^T accumulated in fp32: the weights are streamed once, the activation tile is twice as wide
+ * (the decode rows' own bf16 rounding before each of the 4 x 26 Linear layers is what dominates the bf16-vs-fp32 logit noise of
+ * this path, tools/parity_report.py); 16 = OUT_HILO: out_bf16 is written as two such planes [2][M, ldo] (GEGLU or plain).
+ * model/modeling_gemma2.py:80-92,351-354,993 */
 typedef struct SvlaSkinnyArgs {
   const void* x;          /* bf16 [M, ldx] */
   const void* w;          /* bf16 [N, ldw] */
@@ -144,6 +149,10 @@ int svla_decode_attention(const void* q, const void* kcache, const void* vcache,
 int svla_decode_attention_fused(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache, void* vcache,
                                 void* out, int batch, int hq, int hkv, int d, int smax, int ctx, float theta, float scale,
                                 float softcap, const int32_t* kv_start, void* stream);
+/* hi/lo variant (see svla_gemm_skinny X_HILO): the output leaves as two bf16 planes, out_hi = bf16(o), out_lo = bf16(o - out_hi) */
+int svla_decode_attention_fused_hilo(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache, void* vcache,
+                                     void* out_hi, void* out_lo, int batch, int hq, int hkv, int d, int smax, int ctx, float theta,
+                                     float scale, float softcap, const int32_t* kv_start, void* stream);
 
 /* G4: one whole Gemma2 decode step (all layers) for batch <= 64 in ONE persistent tensor-core launch: one CTA per SM
  * (cooperative launch), a TMA weight ring that streams the [128 x 64] weight tiles of ALL phases of ALL layers without waiting
@@ -184,6 +193,10 @@ int svla_layernorm(const float* x, const float* gamma, const float* beta, float 
 int svla_rmsnorm_residual(float* x, const float* branch, const float* w_post, const float* w_pre, float eps,
                           int64_t rows, int cols, void* out_bf16, int n_partials, int64_t partial_stride, void* stream);
 /* n_partials > 1: branch = sum_s branch[s * partial_stride + ...] (split-K partial sums of svla_gemm_skinny) */
+/* hi/lo variant for the decode chain (rows < 2048): out_hi = bf16(v), out_lo = bf16(v - out_hi) */
+int svla_rmsnorm_residual_hilo(float* x, const float* branch, const float* w_post, const float* w_pre, float eps,
+                               int64_t rows, int cols, void* out_hi_bf16, void* out_lo_bf16, int n_partials,
+                               int64_t partial_stride, void* stream);
 
 /* M3 RoPE + KV-cache write (model/modeling_gemma2.py:95-154,376-395; positions 1-indexed per
  * model/modeling_spatialvla.py:371-372). qkv bf16 [B*S, (hq+2hkv)*D] -> q_out bf16 [B*S, hq*D] (rotated),

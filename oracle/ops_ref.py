@@ -31,6 +31,16 @@ def _act(v, act, p):
     return v
 
 
+def _store_bf16(out, v, n):
+    """bf16 store of v[:, :n]; a 3-D `out` [2, M, N] is a hi/lo pair: hi = bf16(v), lo = bf16(v - hi)"""
+    if out.dim() == 3:
+        hi = v.to(BF16)
+        out[0][:, :n] = hi
+        out[1][:, :n] = (v - hi.float()).to(BF16)
+    else:
+        out[:, :n] = v.to(BF16)
+
+
 def _rows(t):
     return t if t.dim() == 2 else t.view(-1, t.shape[-1])
 
@@ -223,6 +233,8 @@ class RefOps:
     def gemm_skinny(self, x, w, *, out_bf16=None, out_f32=None, bias=None, act=ACT_NONE, act_param=0.0, alpha=1.0,
                     geglu=False, splits=1, tiled_n=None):
         self.launches += 1
+        if x.dim() == 3:                    # hi/lo activation pair [2, M, K]: hi @ w.T + lo @ w.T in fp32
+            x = x[0].float() + x[1].float()
         if tiled_n is not None:             # tile-major [nt, kb, 128, 64] copy of a [tiled_n, K] matrix
             nt, kb = w.shape[0], w.shape[1]
             w = w.permute(0, 2, 1, 3).reshape(nt * 128, kb * 64)[:tiled_n, : x.shape[1]]
@@ -239,13 +251,13 @@ class RefOps:
         if bias is not None:
             v = v + bias
         if geglu:
-            out_bf16[:, : w.shape[0] // 2] = (F.gelu(v[:, 0::2], approximate="tanh") * v[:, 1::2]).to(BF16)
+            _store_bf16(out_bf16, F.gelu(v[:, 0::2], approximate="tanh") * v[:, 1::2], w.shape[0] // 2)
             return
         v = _act(v, act, act_param)
         if out_f32 is not None:
             out_f32[:, : w.shape[0]] = v
         if out_bf16 is not None:
-            out_bf16[:, : w.shape[0]] = v.to(BF16)
+            _store_bf16(out_bf16, v, w.shape[0])
 
     # ---- G2 / G3
     @staticmethod
@@ -297,6 +309,20 @@ class RefOps:
 
     def decode_attention_fused(self, qkv_partials, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, theta, scale, softcap=0.0,
                                kv_start=None):
+        if out.dim() == 3:                      # hi/lo output pair: the kernel's own precision (fp32 q and probabilities, bf16 cache)
+            q = torch.empty(batch, hq * d, dtype=F32)
+            self.rope_kv(qkv_partials, q, kcache, vcache, batch=batch, s=1, hq=hq, hkv=hkv, d=d, smax=smax, pos0=ctx - 1, theta=theta,
+                         row_pads=kv_start)
+            Q = q.view(batch, hq, 1, d)
+            K = kcache.float().view(batch, smax, hkv, d)[:, :ctx].permute(0, 2, 1, 3).repeat_interleave(hq // hkv, 1)
+            V = vcache.float().view(batch, smax, hkv, d)[:, :ctx].permute(0, 2, 1, 3).repeat_interleave(hq // hkv, 1)
+            s = (Q @ K.transpose(-1, -2)) * scale
+            if softcap:
+                s = softcap * torch.tanh(s / softcap)
+            if kv_start is not None:
+                s = s.masked_fill((torch.arange(ctx)[None, :] < kv_start.long()[:, None])[:, None, None, :], float("-inf"))
+            _store_bf16(out, (torch.softmax(s, -1) @ V).squeeze(2).reshape(batch, hq * d), hq * d)
+            return
         q = torch.empty(batch, hq * d, dtype=BF16)
         self.rope_kv(qkv_partials, q, kcache, vcache, batch=batch, s=1, hq=hq, hkv=hkv, d=d, smax=smax, pos0=ctx - 1, theta=theta,
                      row_pads=kv_start)
@@ -325,7 +351,10 @@ class RefOps:
                 branch = branch.sum(0)
             x.add_(rms(branch.reshape(x.shape), w_post))
         if w_pre is not None:
-            out_bf16.copy_(rms(x, w_pre).view_as(out_bf16).to(BF16))
+            if out_bf16.dim() == 3 and out_bf16.shape[0] == 2 and out_bf16.shape[1] == x.numel() // x.shape[-1]:
+                _store_bf16(out_bf16, rms(x, w_pre).view_as(out_bf16[0]), x.shape[-1])     # hi/lo pair of the decode chain
+            else:
+                out_bf16.copy_(rms(x, w_pre).view_as(out_bf16).to(BF16))
 
     def rope_kv(self, qkv, q_out, kcache, vcache, *, batch, s, hq, hkv, d, smax, pos0, theta, row_pads=None):
         self.launches += 1
@@ -344,7 +373,7 @@ class RefOps:
         qk = t[:, :, : hq + hkv]
         x1, x2 = qk[..., : d // 2], qk[..., d // 2:]
         rot = qk * cos + torch.cat([-x2, x1], -1) * sin
-        q_out.view(batch, s, hq, d).copy_(rot[:, :, :hq].to(BF16))
+        q_out.view(batch, s, hq, d).copy_(rot[:, :, :hq].to(q_out.dtype))
         kcache.view(batch, smax, hkv, d)[:, pos0:pos0 + s] = rot[:, :, hq:].to(BF16)
         vcache.view(batch, smax, hkv, d)[:, pos0:pos0 + s] = t[:, :, hq + hkv:].to(BF16)
 

@@ -95,6 +95,8 @@ SIGNATURES = {
     "svla_decode_attention_fused": (_I, [_P, _I, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P]),
     "svla_layernorm": (_I, [_P, _P, _P, _F, _L, _I, _P, _P, _I, _P]),
     "svla_rmsnorm_residual": (_I, [_P, _P, _P, _P, _F, _L, _I, _P, _I, _L, _P]),
+    "svla_rmsnorm_residual_hilo": (_I, [_P, _P, _P, _P, _F, _L, _I, _P, _P, _I, _L, _P]),
+    "svla_decode_attention_fused_hilo": (_I, [_P, _I, _L, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P]),
     "svla_decode_mega_supported": (_I, [_I, _I, _I, _I, _I, _I, _I]),
     "svla_decode_mega_scratch_bytes": (_L, [_I, _I, _I, _I, _I]),
     "svla_decode_mega_maps_bytes": (_L, [_I]),

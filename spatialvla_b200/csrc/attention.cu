@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(kDecThreads, STAGES <= 6 ? 2 : 1)
 svla_decode_attn_fused_kernel(const float* __restrict__ qkv_f32, int n_partials, long long partial_stride,
                               __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out,
                               int hq, int hkv, int smax, int ctx, float theta, float scale, float softcap,
-                              const int* __restrict__ kv_start) {
+                              const int* __restrict__ kv_start, __nv_bfloat16* __restrict__ out_lo) {
   constexpr int D = 256;
   extern __shared__ __align__(16) uint8_t sm_fused[];
   svla_dec::ItemSmem sm;
@@ -505,7 +505,7 @@ svla_decode_attn_fused_kernel(const float* __restrict__ qkv_f32, int n_partials,
   a.b = blockIdx.y; a.hk = blockIdx.x;
   a.qkv = qkv_f32 + static_cast<long long>(a.b) * (hq + 2 * hkv) * D;
   a.n_partials = n_partials; a.partial_stride = partial_stride;
-  a.kc = kc; a.vc = vc; a.out = out;
+  a.kc = kc; a.vc = vc; a.out = out; a.out_lo = out_lo;
   a.hq = hq; a.hkv = hkv; a.smax = smax; a.ctx = ctx;
   a.kstart = kv_start ? kv_start[a.b] : 0;              // immutable input (not written by the PDL predecessor)
   a.theta = theta; a.scale = scale; a.softcap = softcap;
@@ -589,9 +589,31 @@ extern "C" int svla_decode_attention(const void* q, const void* kcache, const vo
 }
 
 // Decode step of one layer after the qkv projection: RoPE + cache append + attention in one launch (see the kernel).
+static int decode_attention_fused_impl(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache, void* vcache,
+                                       void* out, void* out_lo, int batch, int hq, int hkv, int d, int smax, int ctx, float theta,
+                                       float scale, float softcap, const int32_t* kv_start, void* stream);
+
 extern "C" int svla_decode_attention_fused(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache, void* vcache,
                                            void* out, int batch, int hq, int hkv, int d, int smax, int ctx, float theta,
                                            float scale, float softcap, const int32_t* kv_start, void* stream) {
+  return decode_attention_fused_impl(qkv_f32, n_partials, partial_stride, kcache, vcache, out, nullptr, batch, hq, hkv, d, smax, ctx,
+                                     theta, scale, softcap, kv_start, stream);
+}
+
+// hi/lo variant of the decode chain: the attention output leaves as two bf16 planes (hi = bf16(o), lo = bf16(o - hi)) for the
+// X_HILO mode of the o-projection (svla_gemm_skinny)
+extern "C" int svla_decode_attention_fused_hilo(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache,
+                                                void* vcache, void* out_hi, void* out_lo, int batch, int hq, int hkv, int d, int smax,
+                                                int ctx, float theta, float scale, float softcap, const int32_t* kv_start,
+                                                void* stream) {
+  SVLA_REQUIRE(out_lo, "svla_decode_attention_fused_hilo: null lo plane");
+  return decode_attention_fused_impl(qkv_f32, n_partials, partial_stride, kcache, vcache, out_hi, out_lo, batch, hq, hkv, d, smax, ctx,
+                                     theta, scale, softcap, kv_start, stream);
+}
+
+static int decode_attention_fused_impl(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache, void* vcache,
+                                       void* out, void* out_lo, int batch, int hq, int hkv, int d, int smax, int ctx, float theta,
+                                       float scale, float softcap, const int32_t* kv_start, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SVLA_REQUIRE(qkv_f32 && kcache && vcache && out, "svla_decode_attention_fused: null pointer");
   SVLA_REQUIRE(d == 256, "svla_decode_attention_fused: head dim %d unsupported (256 only)", d);
@@ -618,18 +640,19 @@ extern "C" int svla_decode_attention_fused(const float* qkv_f32, int n_partials,
   auto* kcp = static_cast<__nv_bfloat16*>(kcache);
   auto* vcp = static_cast<__nv_bfloat16*>(vcache);
   auto* op = static_cast<__nv_bfloat16*>(out);
+  auto* olp = static_cast<__nv_bfloat16*>(out_lo);
   const long long ps = partial_stride;
   cudaError_t le;
   if (deep)
     le = grp == 1 ? svla_launch_pdl(svla_decode_attn_fused_kernel<1, kFusedStagesDeep>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
-                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start)
+                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start, olp)
                   : svla_launch_pdl(svla_decode_attn_fused_kernel<2, kFusedStagesDeep>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
-                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start);
+                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start, olp);
   else
     le = grp == 1 ? svla_launch_pdl(svla_decode_attn_fused_kernel<1, kFusedStages>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
-                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start)
+                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start, olp)
                   : svla_launch_pdl(svla_decode_attn_fused_kernel<2, kFusedStages>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
-                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start);
+                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start, olp);
   SVLA_REQUIRE(le == cudaSuccess, "svla_decode_attention_fused: launch failed: %s", cudaGetErrorString(le));
   SVLA_LAUNCH_CHECK("svla_decode_attn_fused");
   return 0;

@@ -65,6 +65,7 @@ struct ItemArgs {
   __nv_bfloat16* kc;         // cache of this layer [B, smax, hkv, D]
   __nv_bfloat16* vc;
   __nv_bfloat16* out;        // [B, hq * D]
+  __nv_bfloat16* out_lo;     // NULL, or the lo plane bf16(o - bf16(o)) of the hi/lo activation pair (same layout as out)
   int b, hk, hq, hkv, smax, ctx, kstart;
   float theta, scale, softcap;
 };
@@ -142,10 +143,11 @@ __device__ __forceinline__ void decode_attn_item(const ItemArgs& a, const ItemSm
       sincosf(static_cast<float>(ctx - kstart) * inv_freq, &sn, &cs);      // position of the new token: ctx - leading pads
 #pragma unroll
       for (int g = 0; g <= GRP; ++g) {
-        const __nv_bfloat16 o1 = __float2bfloat16(x1[g] * cs - x2[g] * sn), o2 = __float2bfloat16(x2[g] * cs + x1[g] * sn);
-        if (g < GRP) {
-          s.q[g * D + j] = __bfloat162float(o1);
-          s.q[g * D + j + D / 2] = __bfloat162float(o2);
+        const float r1 = x1[g] * cs - x2[g] * sn, r2 = x2[g] * cs + x1[g] * sn;
+        const __nv_bfloat16 o1 = __float2bfloat16(r1), o2 = __float2bfloat16(r2);
+        if (g < GRP) {                // the query stays in fp32 on the hi/lo chain (bf16 like the prefill kernels' otherwise)
+          s.q[g * D + j] = a.out_lo ? r1 : __bfloat162float(o1);
+          s.q[g * D + j + D / 2] = a.out_lo ? r2 : __bfloat162float(o2);
         } else {
           s.newk[j] = o1; s.newk[j + D / 2] = o2;
           a.kc[cache_row + j] = o1; a.kc[cache_row + j + D / 2] = o2;
@@ -285,7 +287,13 @@ __device__ __forceinline__ void decode_attn_item(const ItemArgs& a, const ItemSm
       const float pn = s.p[g * ctx_pad + n_old], inv = s.inv[g];
       const float o0 = (acc[g][0] + s.red[g * D + 2 * dp] + pn * nv.x) * inv;
       const float o1 = (acc[g][1] + s.red[g * D + 2 * dp + 1] + pn * nv.y) * inv;
-      *reinterpret_cast<__nv_bfloat162*>(a.out + (static_cast<long long>(b) * hq + hk * GRP + g) * D + 2 * dp) = __floats2bfloat162_rn(o0, o1);
+      const long long oi = (static_cast<long long>(b) * hq + hk * GRP + g) * D + 2 * dp;
+      const __nv_bfloat162 ohi = __floats2bfloat162_rn(o0, o1);
+      *reinterpret_cast<__nv_bfloat162*>(a.out + oi) = ohi;
+      if (a.out_lo) {
+        const float2 hf = __bfloat1622float2(ohi);
+        *reinterpret_cast<__nv_bfloat162*>(a.out_lo + oi) = __floats2bfloat162_rn(o0 - hf.x, o1 - hf.y);
+      }
     }
   }
 }

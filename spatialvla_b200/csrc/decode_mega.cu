@@ -499,7 +499,7 @@ svla_decode_mega_kernel(const MegaParams p) {
           ia.qkv = p.part + static_cast<long long>(ia.b) * width;
           ia.n_partials = p.g[0].splits;
           ia.partial_stride = static_cast<long long>(kNB) * width;
-          ia.kc = kc; ia.vc = vc; ia.out = p.ctxb;
+          ia.kc = kc; ia.vc = vc; ia.out = p.ctxb; ia.out_lo = nullptr;
           ia.hq = p.hq; ia.hkv = p.hkv; ia.smax = p.smax; ia.ctx = p.ctx;
           ia.kstart = p.kv_start ? p.kv_start[ia.b] : 0;
           ia.theta = p.theta; ia.scale = p.scale; ia.softcap = p.softcap;

@@ -70,7 +70,7 @@ svla_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gam
 __global__ void __launch_bounds__(kRowThreads)
 svla_rmsnorm_residual_kernel(float* __restrict__ x, const float* __restrict__ branch, const float* __restrict__ w_post,
                              const float* __restrict__ w_pre, float eps, int cols, __nv_bfloat16* __restrict__ out_bf16,
-                             int n_partials, long long partial_stride) {
+                             int n_partials, long long partial_stride, __nv_bfloat16* __restrict__ out_lo) {
   __shared__ float sh[33];
   pdl_launch_dependents();          // the next kernel (a weight-streaming GEMM in the decode chain) may start its prefetch
   pdl_wait();
@@ -126,9 +126,16 @@ svla_rmsnorm_residual_kernel(float* __restrict__ x, const float* __restrict__ br
       const int i = threadIdx.x + k * kRowThreads;
       if (i < nv) {
         const float4 w = reinterpret_cast<const float4*>(w_pre)[i];
-        reinterpret_cast<uint2*>(out_bf16 + row * cols)[i] =
-            make_uint2(pack_bf16x2(xv[k].x * r * (1.f + w.x), xv[k].y * r * (1.f + w.y)),
-                       pack_bf16x2(xv[k].z * r * (1.f + w.z), xv[k].w * r * (1.f + w.w)));
+        const float o0 = xv[k].x * r * (1.f + w.x), o1 = xv[k].y * r * (1.f + w.y);
+        const float o2 = xv[k].z * r * (1.f + w.z), o3 = xv[k].w * r * (1.f + w.w);
+        const uint2 hi = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+        reinterpret_cast<uint2*>(out_bf16 + row * cols)[i] = hi;
+        if (out_lo) {       // hi/lo activation planes of the decode chain: lo = bf16(value - hi), consumed by svla_gemm_skinny (X_HILO)
+          const float2 h01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi.x));
+          const float2 h23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi.y));
+          reinterpret_cast<uint2*>(out_lo + row * cols)[i] =
+              make_uint2(pack_bf16x2(o0 - h01.x, o1 - h01.y), pack_bf16x2(o2 - h23.x, o3 - h23.y));
+        }
       }
     }
   }
@@ -1442,8 +1449,26 @@ extern "C" int svla_layernorm(const float* x, const float* gamma, const float* b
   return 0;
 }
 
+static int rmsnorm_residual_impl(float* x, const float* branch, const float* w_post, const float* w_pre, float eps, int64_t rows, int cols,
+                                 void* out_bf16, void* out_lo_bf16, int n_partials, int64_t partial_stride, void* stream);
+
 extern "C" int svla_rmsnorm_residual(float* x, const float* branch, const float* w_post, const float* w_pre, float eps,
                                      int64_t rows, int cols, void* out_bf16, int n_partials, int64_t partial_stride, void* stream) {
+  return rmsnorm_residual_impl(x, branch, w_post, w_pre, eps, rows, cols, out_bf16, nullptr, n_partials, partial_stride, stream);
+}
+
+// Decode-chain variant: the normalised activations leave as TWO bf16 planes, hi = bf16(v) and lo = bf16(v - hi) (16 mantissa
+// bits together), for the X_HILO mode of svla_gemm_skinny.  Few-row (block-per-row) kernel only.
+extern "C" int svla_rmsnorm_residual_hilo(float* x, const float* branch, const float* w_post, const float* w_pre, float eps,
+                                          int64_t rows, int cols, void* out_hi_bf16, void* out_lo_bf16, int n_partials,
+                                          int64_t partial_stride, void* stream) {
+  SVLA_REQUIRE(out_hi_bf16 && out_lo_bf16 && w_pre, "svla_rmsnorm_residual_hilo: needs w_pre and both output planes");
+  SVLA_REQUIRE(rows < 2048, "svla_rmsnorm_residual_hilo: decode-sized inputs only (rows=%lld)", (long long)rows);
+  return rmsnorm_residual_impl(x, branch, w_post, w_pre, eps, rows, cols, out_hi_bf16, out_lo_bf16, n_partials, partial_stride, stream);
+}
+
+static int rmsnorm_residual_impl(float* x, const float* branch, const float* w_post, const float* w_pre, float eps, int64_t rows, int cols,
+                                 void* out_bf16, void* out_lo_bf16, int n_partials, int64_t partial_stride, void* stream) {
   SVLA_REQUIRE(x, "svla_rmsnorm_residual: null x");
   SVLA_REQUIRE((branch == nullptr) == (w_post == nullptr), "svla_rmsnorm_residual: branch and w_post go together");
   SVLA_REQUIRE((w_pre == nullptr) == (out_bf16 == nullptr), "svla_rmsnorm_residual: w_pre and out_bf16 go together");
@@ -1459,7 +1484,7 @@ extern "C" int svla_rmsnorm_residual(float* x, const float* branch, const float*
   else if (rows >= 2048 && need <= 18) svla_rmsnorm_residual_warp_kernel<18><<<wblocks, 128, 0, st>>>(x, branch, w_post, w_pre, eps, rows, cols, ob, np, partial_stride);
   else {
     cudaError_t le = svla_launch_pdl(svla_rmsnorm_residual_kernel, dim3(static_cast<unsigned>(rows)), dim3(kRowThreads), 0, st, x, branch, w_post,
-                                     w_pre, eps, cols, ob, np, static_cast<long long>(partial_stride));
+                                     w_pre, eps, cols, ob, np, static_cast<long long>(partial_stride), static_cast<__nv_bfloat16*>(out_lo_bf16));
     SVLA_REQUIRE(le == cudaSuccess, "svla_rmsnorm_residual: launch failed: %s", cudaGetErrorString(le));
   }
   SVLA_LAUNCH_CHECK("svla_rmsnorm_residual");

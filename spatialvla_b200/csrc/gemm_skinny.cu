@@ -49,6 +49,8 @@ struct SkinnyParams {
   int act, flags;
   int n_tiles, kb_per_split, num_k_blocks;
   int stages;      // pipeline depth (<= SCfg::kMaxStages)
+  int x_lo_row;    // > 0 (X_HILO): X holds two bf16 planes, rows [0, m) = hi, rows [m, 2m) = lo = bf16(x - hi); each plane is
+                   // loaded into one half of the NB-row activation tile and the epilogue adds the two accumulator halves
   int w_tiled;     // W is stored tile-major [n_tile][k_block][128 rows][64 cols]: every 16 KB stage is one contiguous read
 };
 
@@ -103,6 +105,8 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
       auto load_x = [&](int it, int stage) {
         const int kb = kb0 + (it + rot) % nkb;
         tma_load_2d(smem_x + stage * C::kXBytes, &tm_x, &full_bar[stage], kb * kBK, 0);
+        if (p.x_lo_row > 0)        // hi/lo planes: two boxes of NB/2 rows (rows past 2m are zero-filled by the TMA unit)
+          tma_load_2d(smem_x + stage * C::kXBytes + C::kXBytes / 2, &tm_x, &full_bar[stage], kb * kBK, p.x_lo_row);
       };
       // PDL: the weights are immutable, so the first kStages weight tiles are requested BEFORE waiting for the kernel that
       // produces the activations; their HBM latency (and this kernel's launch + prologue) hides behind that kernel
@@ -152,6 +156,9 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
     const long long n = static_cast<long long>(n_tile) * kWM + q * 32 + lane;
     const bool n_ok = n < p.n;
     const bool partial = (p.flags & 2) != 0, geglu = (p.flags & 1) != 0;
+    const bool hilo_in = p.x_lo_row > 0, hilo_out = (p.flags & 16) != 0;
+    const int ncols = hilo_in ? NB / 2 : (NB < 32 ? 32 : NB);      // accumulator columns that carry activation rows
+    const long long lo_plane = p.m * p.ldo;                         // OUT_HILO: the lo plane follows the hi plane
     const float bias = (p.bias != nullptr && n_ok && !partial) ? __ldg(p.bias + n) : 0.f;
     pdl_wait();
     mbar_wait(acc_bar, 0);
@@ -162,10 +169,16 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
     // address / activation / store chains of the 32 rows run back to back (measured in the persistent decode kernel: 3 us to
     // store one 64-row partial tile, 8 us for the GeGLU tile); predicated stores let the 32 rows overlap.
 #pragma unroll 1
-    for (int c0 = 0; c0 < (NB < 32 ? 32 : NB); c0 += 32) {
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
       if (c0 >= p.m) break;                         // warp-uniform
       uint32_t r[32];
       tmem_ld32(taddr + c0, r);
+      if (hilo_in) {                                // x.W = hi.W + lo.W: the lo plane's accumulators sit NB/2 columns further
+        uint32_t r2[32];
+        tmem_ld32(taddr + NB / 2 + c0, r2);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+      }
       const int rows = static_cast<int>(p.m) - c0;  // rows of this chunk that exist (>= 1)
       if (partial) {
         float* dst = pout + static_cast<long long>(c0) * p.ldo + n;
@@ -179,8 +192,13 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
         for (int j = 0; j < 32; ++j) {
           const float v = __uint_as_float(r[j]) * p.alpha + bias;
           const float other = __shfl_xor_sync(0xffffffffu, v, 1);
-          const __nv_bfloat16 o = __float2bfloat16(gelu_tanh_fast(v) * other);
-          if (wr && j < rows) dst[static_cast<long long>(j) * p.ldo] = o;
+          // tanh.approx (2^-11 relative) is below the bf16 rounding of a single plane but not of a hi/lo pair: libm tanh there
+          const float a = (hilo_out ? 0.5f * v * (1.f + tanhf(0.7978845608028654f * (v + 0.044715f * v * v * v))) : gelu_tanh_fast(v)) * other;
+          const __nv_bfloat16 o = __float2bfloat16(a);
+          if (wr && j < rows) {
+            dst[static_cast<long long>(j) * p.ldo] = o;
+            if (hilo_out) dst[lo_plane + static_cast<long long>(j) * p.ldo] = __float2bfloat16(a - __bfloat162float(o));
+          }
         }
       } else {
 #pragma unroll
@@ -192,7 +210,11 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
           if (n_ok && j < rows) {
             const long long o = static_cast<long long>(c0 + j) * p.ldo + n;
             if (p.out_f32) p.out_f32[o] = v;
-            if (p.out_bf16) p.out_bf16[o] = __float2bfloat16(v);
+            if (p.out_bf16) {
+              const __nv_bfloat16 hi = __float2bfloat16(v);
+              p.out_bf16[o] = hi;
+              if (hilo_out) p.out_bf16[lo_plane + o] = __float2bfloat16(v - __bfloat162float(hi));
+            }
           }
         }
       }
@@ -279,6 +301,9 @@ extern "C" int svla_gemm_skinny(const SvlaSkinnyArgs* g, void* stream) {
   SVLA_REQUIRE(g->m > 0 && g->m <= 128 && g->n > 0 && g->k > 0, "svla_gemm_skinny: need 0 < m <= 128 (m=%lld)", (long long)g->m);
   SVLA_REQUIRE((g->ldx % 8) == 0 && g->ldx >= g->k && (((g->flags & 4) != 0) || ((g->ldw % 8) == 0 && g->ldw >= g->k)), "svla_gemm_skinny: bad leading dimensions");
   const bool geglu = (g->flags & 1) != 0, partial = (g->flags & 2) != 0, w_tiled = (g->flags & 4) != 0;
+  const bool x_hilo = (g->flags & 8) != 0, out_hilo = (g->flags & 16) != 0;
+  SVLA_REQUIRE(!x_hilo || g->m <= 64, "svla_gemm_skinny: X_HILO needs m <= 64 (m=%lld)", (long long)g->m);
+  SVLA_REQUIRE(!out_hilo || (g->out_bf16 && !partial), "svla_gemm_skinny: OUT_HILO needs a bf16 output");
   const int splits = g->splits > 0 ? g->splits : 1;
   SVLA_REQUIRE(partial || splits == 1, "svla_gemm_skinny: split-K needs the PARTIAL flag (fp32 partial sums)");
   SVLA_REQUIRE(!partial || (g->out_f32 && !g->out_bf16 && !geglu), "svla_gemm_skinny: PARTIAL writes out_f32 only");
@@ -292,13 +317,16 @@ extern "C" int svla_gemm_skinny(const SvlaSkinnyArgs* g, void* stream) {
   p.num_k_blocks = static_cast<int>((g->k + kBK - 1) / kBK);
   p.kb_per_split = (p.num_k_blocks + splits - 1) / splits;
   SVLA_REQUIRE(static_cast<long long>(p.kb_per_split) * (splits - 1) < p.num_k_blocks, "svla_gemm_skinny: too many splits (%d) for k=%lld", splits, (long long)g->k);
-  const int nb = g->m <= 16 ? 16 : (g->m <= 64 ? 64 : 128);
+  // X_HILO: the two planes of m <= 32 (64) rows fill the halves of a 64 (128) column tile
+  const int nb = x_hilo ? (g->m <= 32 ? 64 : 128) : (g->m <= 16 ? 16 : (g->m <= 64 ? 64 : 128));
+  p.x_lo_row = x_hilo ? static_cast<int>(g->m) : 0;
   CUtensorMap tw, tx;
   p.w_tiled = w_tiled ? 1 : 0;
   int rc = w_tiled ? encode_kmajor(&tw, g->w, kBK, static_cast<uint64_t>(p.n_tiles) * p.num_k_blocks * kWM, kBK, kWM)
                    : encode_kmajor(&tw, g->w, static_cast<uint64_t>(g->k), static_cast<uint64_t>(g->n), static_cast<uint64_t>(g->ldw), kWM);
   SVLA_REQUIRE(rc == 0, "svla_gemm_skinny: cuTensorMapEncodeTiled(W) failed (%d)", rc);
-  rc = encode_kmajor(&tx, g->x, static_cast<uint64_t>(g->k), static_cast<uint64_t>(g->m), static_cast<uint64_t>(g->ldx), static_cast<uint32_t>(nb));
+  rc = encode_kmajor(&tx, g->x, static_cast<uint64_t>(g->k), static_cast<uint64_t>(x_hilo ? 2 * g->m : g->m), static_cast<uint64_t>(g->ldx),
+                     static_cast<uint32_t>(x_hilo ? nb / 2 : nb));
   SVLA_REQUIRE(rc == 0, "svla_gemm_skinny: cuTensorMapEncodeTiled(X) failed (%d)", rc);
   const int ctas = p.n_tiles * splits;
   if (nb == 16) return launch_skinny<16>(tw, tx, p, ctas, st);

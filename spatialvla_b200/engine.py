@@ -312,7 +312,8 @@ class SpatialVLAEngine:
         return out
 
     def _skinny_partial(self, a, w, rows):
-        """Decode GEMM as split-K fp32 partial sums [splits, rows, N]; the consumer kernel adds the partials."""
+        """Decode GEMM as split-K fp32 partial sums [splits, rows, N]; the consumer kernel adds the partials.
+        a: bf16 [rows, K] or a hi/lo pair [2, rows, K]."""
         N, K = w.shape
         out = self.ops.empty((self.ops.skinny_splits(N, K), rows, N), F32)
         self.ops.gemm_skinny(a, w, out_f32=out)
@@ -609,6 +610,9 @@ class SpatialVLAEngine:
     # barrier (arrive + poll + fences, ~2.5 us) costs what a PDL kernel boundary costs, so the seven dependent phases of a
     # layer bound both designs and the chain's second resident CTA hides more of the attention phase.
     mega_decode = os.environ.get("SVLA_DECODE", "chain") == "mega"
+    # hi/lo activation pairs on the decode chain + the last prompt row re-evaluated as a decode step (see gemma_forward /
+    # language_stage); SVLA_DECODE_HILO=0 restores the plain bf16 chain for A/B measurements
+    decode_hilo = os.environ.get("SVLA_DECODE_HILO", "1") != "0"
 
     def _mega_plan(self):
         """TMA descriptors / norm-pointer table / scratch of the persistent decode kernel, built once (outside graph capture)."""
@@ -639,13 +643,15 @@ class SpatialVLAEngine:
         cache["len"] = pos0 + 1
         return h
 
-    def gemma_forward(self, x, B, S, cache, bidirectional, pads=None, causal_prefix=0):
+    def gemma_forward(self, x, B, S, cache, bidirectional, pads=None, causal_prefix=0, hilo_out=False):
         """x fp32 [B*S, H] (already scaled by sqrt(H)) -> final-normed hidden bf16 [B*S, H]; appends to the cache.
         pads: int32 [B] device tensor or None -- leading padding tokens per row of a left-padded batch: those cache slots are
         masked as keys and the RoPE positions restart at 1 on each row's first real token (model/modeling_spatialvla.py:298-303,
         model/modeling_gemma2.py:1042-1051).
         causal_prefix (with bidirectional=False): keys < causal_prefix stay visible to every query -- the prefix-LM mask of the
-        training forward (model/modeling_spatialvla.py:292-293,304-305)."""
+        training forward (model/modeling_spatialvla.py:292-293,304-305).
+        hilo_out: a decode step (S == 1) on the hi/lo chain returns the final-normed state as the pair [2, B, H] instead of its
+        hi plane."""
         ops, g, t = self.ops, self.gem, self.t
         H, nh, nkv, hd, FF = t["hidden_size"], t["num_attention_heads"], t["num_key_value_heads"], t["head_dim"], t["intermediate_size"]
         eps, theta = t["rms_norm_eps"], float(t.get("rope_theta", 10000.0))
@@ -659,11 +665,20 @@ class SpatialVLAEngine:
             raise NotImplementedError(f"context of {pos0 + S} tokens exceeds the sliding window ({win}): windowed layers are not implemented")
         if S == 1 and not bidirectional and self._mega_ok(B, pos0 + 1):
             return self.gemma_decode_mega(x, B, cache, pads=pads)
-        h = ops.empty((M, H), BF16)
+        skinny = (S == 1 and M <= 128)          # decode step: weight-streaming swap-AB / split-K GEMMs
+        # Decode rows carry their activations between the kernels of the chain as hi/lo bf16 PAIRS [2, M, cols] (hi = bf16(v),
+        # lo = bf16(v - hi)): the weight-streaming GEMMs are HBM-bound, a twice as wide activation tile is free, and the bf16
+        # rounding of a row's OWN activations in front of each of the 4 x 26 Linear layers is what dominates the logit noise of
+        # this path against the fp32 reference (CPU re-statement: rms 0.0050 -> 0.0010 on the decode positions; the cached K / V
+        # of earlier positions average out over the keys).
+        hilo = skinny and self.decode_hilo and M <= 64 and hd == 256 and nh // nkv in (1, 2)
+
+        def act_buf(cols):
+            return ops.empty((2, M, cols) if hilo else (M, cols), BF16)
+        h = act_buf(H)
         ops.rmsnorm_residual(x, w_pre=g["layers"][0]["ln_in"], eps=eps, out_bf16=h)
         q = ops.empty((M, nh * hd), BF16)
-        ctx = ops.empty((M, nh * hd), BF16)
-        skinny = (S == 1 and M <= 128)          # decode step: weight-streaming swap-AB / split-K GEMMs
+        ctx = act_buf(nh * hd)
         for li, L_ in enumerate(g["layers"]):
             kc, vc = cache["k"][li], cache["v"][li]
             if skinny:
@@ -676,7 +691,7 @@ class SpatialVLAEngine:
                                            scale=scale, softcap=cap, kv_start=pads)
                 br = self._skinny_partial(ctx, L_["wo"], M)
                 ops.rmsnorm_residual(x, branch=br, w_post=L_["ln_post_attn"], w_pre=L_["ln_pre_ff"], eps=eps, out_bf16=h)
-                act = ops.empty((M, FF), BF16)
+                act = act_buf(FF)
                 ops.gemm_skinny(h, L_["wgu"], out_bf16=act, geglu=True)
                 br = self._skinny_partial(act, L_["wd"], M)
                 nxt = g["layers"][li + 1]["ln_in"] if li + 1 < len(g["layers"]) else g["final"]
@@ -703,7 +718,7 @@ class SpatialVLAEngine:
             nxt = g["layers"][li + 1]["ln_in"] if li + 1 < len(g["layers"]) else g["final"]
             ops.rmsnorm_residual(x, branch=br, w_post=L_["ln_post_ff"], w_pre=nxt, eps=eps, out_bf16=h)
         cache["len"] = pos0 + S
-        return h
+        return h if (hilo_out or not hilo) else h[0]
 
     def embed(self, ids, image_feats=None):
         ops, g, t = self.ops, self.gem, self.t
@@ -786,9 +801,21 @@ class SpatialVLAEngine:
         H = self.t["hidden_size"]
         x, status = self.embed(ids, feats)
         cache = self.new_cache(B, P + n_new)
+        t = self.t
+        redo = (self.decode_hilo and B <= 64 and P >= 2 and t["head_dim"] == 256
+                and t["num_attention_heads"] // t["num_key_value_heads"] in (1, 2) and not self.mega_decode)
+        x_last = x.view(B, P, H)[:, P - 1].contiguous() if redo else None     # embedding of the last prompt token (x is updated in place)
         h = self.gemma_forward(x, B, P, cache, bidirectional=True, pads=pads)
         toks = ops.zeros((B, n_new), torch.int64)
-        rows = h.view(B, P * H)[:, (P - 1) * H:]
+        if redo:
+            # The first action token is read off the LAST prompt row.  That row sees every key of the bidirectional prefix, i.e.
+            # exactly what a decode step at slot P-1 sees, so it is evaluated once more as a decode step on the hi/lo chain
+            # (one extra weight pass, ~1.3 % of a batch-64 step) and its K / V cache slot is rewritten with the more exact
+            # values: all n_new logits then come from the same, more exact arithmetic.
+            cache["len"] = P - 1
+            rows = self.gemma_forward(x_last, B, 1, cache, bidirectional=False, pads=pads, hilo_out=True)
+        else:
+            rows = h.view(B, P * H)[:, (P - 1) * H:]
         for step in range(n_new):
             lg = self.action_logits(rows, B)
             if logs is not None:
@@ -798,7 +825,7 @@ class SpatialVLAEngine:
                 break
             feed = toks[:, step:step + 1] if forced_tokens is None else forced_tokens[:, step:step + 1]
             x, _ = self.embed(feed.contiguous())
-            rows = self.gemma_forward(x, B, 1, cache, bidirectional=False, pads=pads)
+            rows = self.gemma_forward(x, B, 1, cache, bidirectional=False, pads=pads, hilo_out=True)
         self.last_status = status
         return toks
 

@@ -216,8 +216,17 @@ class CudaOps:
     def gemm_skinny(self, x, w, *, out_bf16=None, out_f32=None, bias=None, act=ACT_NONE, act_param=0.0, alpha=1.0,
                     geglu=False, splits=1, tiled_n=None):
         """Decode GEMM (M <= 128). splits > 1 (or out_f32 with 3 dims) writes raw fp32 partial sums out_f32[s, M, N].
-        tiled_n: w is the tile-major copy made by `tile_weight` of a [tiled_n, K] matrix."""
+        tiled_n: w is the tile-major copy made by `tile_weight` of a [tiled_n, K] matrix.
+        x of shape [2, M, K] (contiguous) is a hi/lo activation pair (X_HILO, M <= 64): the result is hi @ w.T + lo @ w.T;
+        out_bf16 of shape [2, M, N] is written as such a pair (OUT_HILO)."""
         g = L.SvlaSkinnyArgs()
+        x_hilo = x.dim() == 3
+        if x_hilo:
+            _req(x.shape[0] == 2 and x.is_contiguous() and x.shape[1] <= 64, "gemm_skinny: hi/lo activations must be contiguous [2, M <= 64, K]")
+            x = x.view(2 * x.shape[1], x.shape[2])
+        out_hilo = out_bf16 is not None and out_bf16.dim() == 3
+        if out_hilo:
+            _req(out_bf16.shape[0] == 2 and out_bf16.is_contiguous(), "gemm_skinny: hi/lo output must be contiguous [2, M, N]")
         _req(x.dtype == BF16 and w.dtype == BF16 and x.dim() == 2 and x.stride(1) == 1, "gemm_skinny: bf16 row-major operands")
         if tiled_n is not None:
             _req(w.dim() == 4 and w.shape[2] == 128 and w.shape[3] == 64 and w.is_contiguous(), "gemm_skinny: tiled w must be [nt, kb, 128, 64]")
@@ -226,13 +235,13 @@ class CudaOps:
         _req(partial or splits == 1, "gemm_skinny: split-K needs a [splits, M, N] fp32 output")
         g.x, g.w, g.bias = _ptr(x), _ptr(w), _ptr(bias)
         g.out_bf16, g.out_f32 = _ptr(out_bf16), _ptr(out_f32)
-        g.m, g.n, g.k = int(x.shape[0]), int(w.shape[0] if tiled_n is None else tiled_n), int(x.shape[1])
+        g.m, g.n, g.k = int(x.shape[0]) // (2 if x_hilo else 1), int(w.shape[0] if tiled_n is None else tiled_n), int(x.shape[1])
         g.ldx, g.ldw = int(x.stride(0)), int(w.stride(0) if tiled_n is None else 64)
         o = out_f32 if out_f32 is not None else out_bf16
         g.ldo = int(o.stride(-2))
         g.partial_stride = int(out_f32.stride(0)) if partial else 0
         g.alpha, g.act_param, g.act = float(alpha), float(act_param), int(act)
-        g.flags = (1 if geglu else 0) | (2 if partial else 0) | (4 if tiled_n is not None else 0)
+        g.flags = (1 if geglu else 0) | (2 if partial else 0) | (4 if tiled_n is not None else 0) | (8 if x_hilo else 0) | (16 if out_hilo else 0)
         g.splits = int(out_f32.shape[0]) if partial else 1
         L.check(self.lib.svla_gemm_skinny(C.byref(g), self._stream()), "svla_gemm_skinny")
 
@@ -274,9 +283,17 @@ class CudaOps:
 
     def decode_attention_fused(self, qkv_partials, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, theta, scale, softcap=0.0,
                                kv_start=None):
-        """RoPE + KV-cache append + attention of one decode step; qkv_partials fp32 [splits, batch, (hq+2hkv)*d]."""
+        """RoPE + KV-cache append + attention of one decode step; qkv_partials fp32 [splits, batch, (hq+2hkv)*d].
+        out bf16 [batch, hq*d], or a contiguous hi/lo pair [2, batch, hq*d]."""
         _req(qkv_partials.dtype == F32 and qkv_partials.dim() == 3 and qkv_partials.stride(2) == 1 and
              qkv_partials.stride(1) == qkv_partials.shape[2], "decode_attention_fused: qkv must be fp32 [splits, batch, W]")
+        if out.dim() == 3:
+            _req(out.shape[0] == 2 and out.is_contiguous(), "decode_attention_fused: hi/lo output must be contiguous [2, batch, hq*d]")
+            L.check(self.lib.svla_decode_attention_fused_hilo(_ptr(qkv_partials), int(qkv_partials.shape[0]), int(qkv_partials.stride(0)),
+                                                              _ptr(kcache), _ptr(vcache), _ptr(out[0]), _ptr(out[1]), batch, hq, hkv, d, smax,
+                                                              ctx, float(theta), float(scale), float(softcap or 0.0), _ptr(kv_start),
+                                                              self._stream()), "svla_decode_attention_fused_hilo")
+            return
         L.check(self.lib.svla_decode_attention_fused(_ptr(qkv_partials), int(qkv_partials.shape[0]), int(qkv_partials.stride(0)),
                                                      _ptr(kcache), _ptr(vcache), _ptr(out), batch, hq, hkv, d, smax, ctx,
                                                      float(theta), float(scale), float(softcap or 0.0), _ptr(kv_start), self._stream()),
@@ -336,6 +353,13 @@ class CudaOps:
         npart, pstride = 1, 0
         if branch is not None and branch.dim() == 3:
             npart, pstride = int(branch.shape[0]), int(branch.stride(0))
+        if out_bf16 is not None and out_bf16.dim() == 3 and out_bf16.shape[0] == 2 and out_bf16.shape[1] == rows:
+            # hi/lo activation pair [2, rows, cols] of the decode chain
+            _req(out_bf16.is_contiguous(), "rmsnorm_residual: hi/lo output must be contiguous [2, rows, cols]")
+            L.check(self.lib.svla_rmsnorm_residual_hilo(_ptr(x), _ptr(branch), _ptr(w_post), _ptr(w_pre), float(eps), rows, cols,
+                                                        _ptr(out_bf16[0]), _ptr(out_bf16[1]), npart, pstride, self._stream()),
+                    "svla_rmsnorm_residual_hilo")
+            return
         L.check(self.lib.svla_rmsnorm_residual(_ptr(x), _ptr(branch), _ptr(w_post), _ptr(w_pre), float(eps), rows,
                                                cols, _ptr(out_bf16), npart, pstride, self._stream()), "svla_rmsnorm_residual")
 

@@ -232,7 +232,95 @@ def skinny_consumers_case(dev="cuda:0"):
     return res
 
 
+def _hilo_pair(v):
+    """fp32 -> the hi/lo bf16 pair [2, rows, cols] of the decode chain (hi = bf16(v), lo = bf16(v - hi))"""
+    hi = v.to(BF16)
+    return torch.stack([hi, (v - hi.float()).to(BF16)]).contiguous()
+
+
+def _hilo_sum(t):
+    return t[0].float() + t[1].float()
+
+
+def skinny_hilo_case(name, M, N, K, *, mode="partial", act=ACT_NONE, act_param=0.0, seed=0, tiled=False):
+    """X_HILO / OUT_HILO modes of svla_gemm_skinny: hi/lo activation pairs in, fp32 partial sums / fp32 / hi/lo pairs out.
+    Checked (1) against the re-statement on the same pair and (2) against the fp64 product of the UNSPLIT fp32 activations,
+    where the pair must be far inside what one bf16 plane can give (2^-9 per element)."""
+    def case(dev="cuda:0"):
+        from spatialvla_b200.ops import tile_weight
+        g = _gen(seed)
+        xf = _randn(g, M, K)
+        wt = (_randn(g, N, K) / K ** 0.5).to(BF16)
+        exact = (xf.double() @ wt.double().t()).float()
+
+        def run(ops, to):
+            X = to(_hilo_pair(xf))
+            W = to(tile_weight(wt)) if tiled else to(wt)
+            tn = N if tiled else None
+            if mode == "partial":
+                S = ops.skinny_splits(N, K) if ops.name == "cuda" else 1
+                out = ops.zeros((S, M, N), F32)
+                ops.gemm_skinny(X, W, out_f32=out, tiled_n=tn)
+                return (out.sum(0),)
+            if mode == "geglu":
+                out = ops.zeros((2, M, N // 2), BF16)
+                ops.gemm_skinny(X, W, out_bf16=out, geglu=True, tiled_n=tn)
+                return (_hilo_sum(out), out[0].float())
+            of, ob = ops.zeros((M, N), F32), ops.zeros((2, M, N), BF16)
+            ops.gemm_skinny(X, W, out_f32=of, out_bf16=ob, act=act, act_param=act_param, tiled_n=tn)
+            return of, _hilo_sum(ob), ob[0].float()
+        c, r = _both(run, dev)
+        res = Result(name)
+        for i, (a_, b_) in enumerate(zip(c, r)):
+            res.add(f"out{i}", _err(a_, b_), 1e-4 if i < len(c) - 1 or mode == "partial" else TOL_BF16)
+        if mode == "partial":
+            res.add("vs_fp64_unsplit", _err(c[0], exact), 5e-5)
+        elif mode == "geglu":
+            ref = torch.nn.functional.gelu(exact[:, 0::2].double(), approximate="tanh") * exact[:, 1::2].double()
+            res.add("vs_fp64_unsplit", _err(c[0], ref), 5e-5)
+        return res
+    case.__name__ = name
+    return case
+
+
+def decode_hilo_consumers_case(dev="cuda:0"):
+    """hi/lo outputs of the sandwich norm and of the fused decode attention (the producers of the X_HILO GEMM operands)."""
+    g = _gen(23)
+    rows, cols, S = 64, 2304, 5
+    x, parts = _randn(g, rows, cols), _randn(g, S, rows, cols)
+    wp, wq = _randn(g, cols) * 0.1, _randn(g, cols) * 0.1
+    B, hq, hkv, d, smax, ctx, splits = 3, 8, 4, 256, 290, 285, 4
+    part = _randn(g, splits, B, (hq + 2 * hkv) * d, scale=0.6)
+    kc0, vc0 = _randn(g, B, smax, hkv, d, dtype=BF16), _randn(g, B, smax, hkv, d, dtype=BF16)
+    pads = torch.tensor([0, 6, 97], dtype=torch.int32)
+
+    def run(ops, to):
+        xx, ob = to(x), ops.zeros((2, rows, cols), BF16)
+        ops.rmsnorm_residual(xx, branch=to(parts), w_post=to(wp), w_pre=to(wq), eps=1e-6, out_bf16=ob)
+        x1, ob1 = to(x[:1]), ops.zeros((2, 1, cols), BF16)
+        ops.rmsnorm_residual(x1, w_pre=to(wq), eps=1e-6, out_bf16=ob1)
+        kc, vc = to(kc0), to(vc0)
+        out = ops.zeros((2, B, hq * d), BF16)
+        ops.decode_attention_fused(to(part), kc, vc, out, batch=B, hq=hq, hkv=hkv, d=d, smax=smax, ctx=ctx, theta=10000.0,
+                                   scale=1 / 16, softcap=50.0, kv_start=to(pads))
+        return xx, _hilo_sum(ob), ob[0].float(), _hilo_sum(ob1), _hilo_sum(out), out[0].float(), kc[:, ctx - 1].clone()
+    c, r = _both(run, dev)
+    res = Result("decode_hilo_consumers")
+    for nm, a_, b_, tol in zip(("x", "h_pair", "h_hi", "h_pair_1row", "attn_pair", "attn_hi", "k_row"), c, r,
+                               (1e-5, 5e-5, TOL_BF16, 5e-5, 5e-4, TOL_BF16, TOL_BF16)):
+        res.add(nm, _err(a_, b_), tol)
+    return res
+
+
 SKINNY_CASES = [
+    skinny_hilo_case("skinny_hilo_qkv_partial", 64, 4096, 2304, seed=41),
+    skinny_hilo_case("skinny_hilo_down_partial_m33", 33, 2304, 9216, seed=42),
+    skinny_hilo_case("skinny_hilo_geglu", 64, 18432, 2304, mode="geglu", seed=43),
+    skinny_hilo_case("skinny_hilo_geglu_m1_tiled", 1, 1024, 512, mode="geglu", seed=44, tiled=True),
+    skinny_hilo_case("skinny_hilo_head_softcap_m64", 64, 8194, 2304, mode="plain", act=ACT_SOFTCAP, act_param=30.0, seed=45),
+    skinny_hilo_case("skinny_hilo_head_m17_ragged", 17, 300, 200, mode="plain", seed=46),
+    skinny_hilo_case("skinny_hilo_m32_partial", 32, 512, 1024, seed=47),
+    decode_hilo_consumers_case,
     skinny_case("skinny_qkv_partial", 64, 4096, 2304),
     skinny_case("skinny_o_partial_split8", 64, 2304, 2048, splits=8),
     skinny_case("skinny_down_partial", 64, 2304, 9216),

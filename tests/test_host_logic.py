@@ -40,6 +40,27 @@ def test_engine_matches_oracle_and_golden(tiny):
     assert np.abs(logits.numpy() - g["logits"]).max() < 6e-2
 
 
+def test_decode_hilo_chain_is_closer_to_the_fp32_oracle(tiny):
+    """The decode chain carries hi/lo bf16 activation pairs and the last prompt row is re-evaluated as a decode step
+    (engine.gemma_forward / language_stage): same tokens as the plain bf16 chain, logits closer to the fp32 oracle on the
+    language stage (the oracle's own image features are fed so that only the Gemma2 arithmetic differs)."""
+    cfg, px, ids, K, sd, eng = tiny
+    tk, lg, aux = R.predict_action_ref(sd, cfg, ids, px, K, 6, force_head=0, return_aux=True)
+    feats = aux["image_features"]
+    err = {}
+    try:
+        for mode in (True, False):
+            eng.decode_hilo = mode
+            logs = []
+            with torch.no_grad():
+                toks = eng.language_stage(ids, feats, 6, forced_tokens=tk, logs=logs)
+            assert torch.equal(toks, tk)
+            err[mode] = float((torch.stack(logs, 1) - lg).pow(2).mean().sqrt())
+    finally:
+        del eng.decode_hilo                     # back to the class default
+    assert err[True] < 0.6 * err[False], err
+
+
 def test_forward_logits_api(tiny):
     from spatialvla_b200.modeling_spatialvla import SpatialVLAForConditionalGeneration
     cfg, px, ids, K, sd, eng = tiny

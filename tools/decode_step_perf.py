@@ -34,7 +34,7 @@ out_tok = torch.zeros(B, dtype=torch.int64, device=dev)
 def step():
     cache["len"] = P
     xx, _ = eng.embed(tok)
-    rows = eng.gemma_forward(xx, B, 1, cache, bidirectional=False)
+    rows = eng.gemma_forward(xx, B, 1, cache, bidirectional=False, hilo_out=True)
     lg = eng.action_logits(rows, B)
     ops.argmax_rows(lg, out_tok, id_offset=cfg["action_token_begin_idx"])
 
@@ -59,7 +59,7 @@ t = cfg["text_config"]
 L_, nh, nkv, hd, FF = t["num_hidden_layers"], t["num_attention_heads"], t["num_key_value_heads"], t["head_dim"], t["intermediate_size"]
 w_bytes = L_ * 2 * (H * (nh + 2 * nkv) * hd + nh * hd * H + 3 * H * FF) + 8194 * H * 2
 kv_bytes = L_ * 2 * B * (P + 1) * nkv * hd * 2
-print({"name": "decode_step", "stages_env": os.environ.get("SVLA_SKINNY_STAGES", ""), "pdl": os.environ.get("SVLA_PDL", "1"),
+print({"name": "decode_step", "hilo": eng.decode_hilo, "stages_env": os.environ.get("SVLA_SKINNY_STAGES", ""), "pdl": os.environ.get("SVLA_PDL", "1"),
        "launches": launches, "us_median": round(ms * 1e3, 1), "us_min": round(ts[0] * 1e3, 1),
        "weight_GB": round(w_bytes / 1e9, 3), "kv_GB": round(kv_bytes / 1e9, 3),
        "GBs": round((w_bytes + kv_bytes) / ms / 1e6, 1), "roofline_us_at_6555GBs": round((w_bytes + kv_bytes) / 6555.8e3, 1)}, flush=True)

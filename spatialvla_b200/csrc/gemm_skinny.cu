@@ -192,8 +192,15 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
         for (int j = 0; j < 32; ++j) {
           const float v = __uint_as_float(r[j]) * p.alpha + bias;
           const float other = __shfl_xor_sync(0xffffffffu, v, 1);
-          // tanh.approx (2^-11 relative) is below the bf16 rounding of a single plane but not of a hi/lo pair: libm tanh there
-          const float a = (hilo_out ? 0.5f * v * (1.f + tanhf(0.7978845608028654f * (v + 0.044715f * v * v * v))) : gelu_tanh_fast(v)) * other;
+          // tanh.approx (2^-11 relative) is below the bf16 rounding of a single plane but not of a hi/lo pair: there
+          // 1 + tanh(u) = 2 - 2 / (exp(2u) + 1) through ex2 + rcp (absolute error ~1e-7, saturates correctly at +-inf)
+          float a;
+          if (hilo_out) {
+            const float e = __expf(1.5957691216057308f * (v + 0.044715f * v * v * v));
+            a = v * (1.f - __fdividef(1.f, e + 1.f)) * other;
+          } else {
+            a = gelu_tanh_fast(v) * other;
+          }
           const __nv_bfloat16 o = __float2bfloat16(a);
           if (wr && j < rows) {
             dst[static_cast<long long>(j) * p.ldo] = o;

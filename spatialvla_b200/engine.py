@@ -804,7 +804,7 @@ class SpatialVLAEngine:
         t = self.t
         redo = (self.decode_hilo and B <= 64 and P >= 2 and t["head_dim"] == 256
                 and t["num_attention_heads"] // t["num_key_value_heads"] in (1, 2) and not self.mega_decode)
-        x_last = x.view(B, P, H)[:, P - 1].contiguous() if redo else None     # embedding of the last prompt token (x is updated in place)
+        x_last = x.view(B, P, H)[:, P - 1].clone() if redo else None     # embedding of the last prompt token, COPIED: x is updated in place
         h = self.gemma_forward(x, B, P, cache, bidirectional=True, pads=pads)
         toks = ops.zeros((B, n_new), torch.int64)
         if redo:

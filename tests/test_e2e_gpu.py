@@ -165,6 +165,7 @@ def test_persistent_decode_kernel_matches_chain(tiny_gpu, cuda_device):
     """The single-launch persistent decode kernel (svla_decode_mega_step: TMA weight ring + tcgen05 swap-AB GEMMs + in-kernel grid
     barriers, opt-in SVLA_DECODE=mega) against the 7-kernels-per-layer chain of the default path (both are checked against the
     fp32 oracle elsewhere): the two run the same arithmetic in the same order, so tokens AND logits must be bit-identical.
+    The persistent kernel implements the PLAIN bf16 chain, so the chain side runs with the hi/lo activation pairs switched off.
     Batches 1 / 2 / 4, left-padded rows, eager launches and CUDA-graph capture + replay of the cooperative launch."""
     cfg, px, ids, K, sd, eng = tiny_gpu
     n_new = 6
@@ -182,6 +183,7 @@ def test_persistent_decode_kernel_matches_chain(tiny_gpu, cuda_device):
         args = (idb.to(cuda_device), pxb.to(cuda_device), K.to(cuda_device), n_new)
         eng.force_head = 0
         try:
+            eng.decode_hilo = False
             eng.mega_decode = True
             t_mega, l_mega = eng.generate_actions(*args, return_logits=True, pads=pads)
             t_graph = eng.generate_actions(*args, pads=pads)                   # CUDA-graph capture + replay of the persistent kernel
@@ -189,7 +191,8 @@ def test_persistent_decode_kernel_matches_chain(tiny_gpu, cuda_device):
             eng.mega_decode = False
             t_chain, l_chain = eng.generate_actions(*args, return_logits=True, pads=pads)
         finally:
-            eng.mega_decode = type(eng).mega_decode       # back to the configured default
+            eng.mega_decode = type(eng).mega_decode       # back to the configured defaults
+            eng.decode_hilo = type(eng).decode_hilo
             eng.force_head = None
             if hasattr(eng, "_graphs"):
                 eng._graphs.clear()
@@ -303,25 +306,24 @@ def test_full_size_4b_parity_teacher_forced(cuda_device):
 
 def test_full_size_parity_832_positions(cuda_device):
     """north_star's gate at the size it is stated for: SpatialVLA-4B-224, batch 64, 64 x 13 = 832 teacher-forced positions (SURVEY.md
-    §8d) against the fp32 oracle's offline golden (oracle/gen_golden_full.py -> tests/golden/full_4b_b64.npz).
-    MEASURED (profiles/parity_r2_*.txt): element-wise logits |d| <= 2e-2 + 2e-2 |ref| on 100 % of the sampled logits (rms 0.005), RAW
-    action-slice argmax agreement 98.9-99.2 % (9 / 7 of 832 in two code versions with identical logit rms: the flipped near-ties move
-    with the rounding order) -- BELOW north_star's 99.5 % (<= 4 of 832).  Every mismatch is an oracle near-tie
-    (top-1/top-2 margin <= 0.014 against a median of 0.156, i.e. inside 3 sigma of the bf16 logit noise, which comes from the 26 Gemma2
-    layers: feeding the oracle's fp32 image features changes the noise from 0.0050 to 0.0047, tools/parity_sources.py); the oracle's
-    OWN bf16 run flips 2.9 % of its positions.  The assertions below state exactly that and nothing softer: all logits inside the
-    tolerance, no mismatch outside the noise band, agreement well above the bf16 floor; the 99.5 % figure is reported, not claimed."""
+    §8d) against the fp32 oracle's offline golden (oracle/gen_golden_full.py -> tests/golden/full_4b_b64.npz), through the product's
+    own prefill + decode path (generate_actions with forced tokens).
+    MEASURED (profiles/parity_r2_v3.txt): RAW action-slice argmax agreement 99.76 % (2 of 832; gate >= 99.5 %), element-wise logits
+    |d| <= 2e-2 + 2e-2 |ref| on 100 % of the sampled logits, rms 0.0017, max 0.0083.  Before the decode chain carried hi/lo bf16
+    activation pairs (engine.gemma_forward) the same report read 98.9-99.2 % at rms 0.0050 (profiles/parity_r2_v1/v2.txt): the bf16
+    rounding of a decode row's own activations in front of the 4 x 26 Linear layers was the noise, not the tensor-core arithmetic.
+    The remaining mismatches are oracle near-ties (margin < 0.003 against a median of 0.156); the oracle's OWN bf16 run flips 2.9 %."""
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     from parity_report import full_size_parity
     res = full_size_parity(cuda_device)
     assert res["positions"] == 832
+    assert res["agreement"] >= 0.995, res                                     # north_star: >= 99.5 % of positions (<= 4 of 832)
     assert res["logit_cover"] >= 0.9999, res                                  # logits: rtol 2e-2 (+ atol 2e-2) everywhere
-    assert res["logit_rms"] < 8e-3 and res["logit_max_abs"] < 4e-2, res
+    assert res["logit_rms"] < 3e-3 and res["logit_max_abs"] < 2e-2, res
     noise_band = 4.0 * (2 ** 0.5) * res["logit_rms"]                          # 4 sigma of the difference of two noisy logits
     assert all(m <= noise_band for m in res["mismatch_margins"]), (noise_band, res["mismatch_margins"])
-    assert res["agreement"] >= 0.985, res                                     # measured 0.9892 - 0.9916; north_star's 0.995 is NOT met (see docstring)
-    assert res["agreement"] >= res["calibration"]["agreement"] + 0.01          # clearly above what the reference arithmetic in bf16 reaches
+    assert res["agreement"] >= res["calibration"]["agreement"] + 0.02          # clearly above what the reference arithmetic in bf16 reaches
     assert res["router_head"] == res["router_head_oracle"]
 
 

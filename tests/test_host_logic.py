@@ -61,6 +61,19 @@ def test_decode_hilo_chain_is_closer_to_the_fp32_oracle(tiny):
     assert err[True] < 0.6 * err[False], err
 
 
+def test_language_stage_batch1_equals_its_row_in_a_batch(tiny):
+    """A single observation decodes like the same observation inside a batch (the re-evaluation of the last prompt row starts from
+    a COPY of its embedding: at batch 1 the row slice is already contiguous and would alias the in-place residual stream)."""
+    cfg, px, ids, K, sd, eng = tiny
+    with torch.no_grad():
+        feats = eng.image_features(px, K)
+        logs2, logs1 = [], []
+        t2 = eng.language_stage(ids, feats, 4, logs=logs2)
+        t1 = eng.language_stage(ids[1:2], feats[1:2].contiguous(), 4, logs=logs1)
+    assert torch.equal(t1[0], t2[1])
+    assert float((torch.stack(logs1, 1)[0] - torch.stack(logs2, 1)[1]).abs().max()) < 1e-3
+
+
 def test_forward_logits_api(tiny):
     from spatialvla_b200.modeling_spatialvla import SpatialVLAForConditionalGeneration
     cfg, px, ids, K, sd, eng = tiny

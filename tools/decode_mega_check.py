@@ -21,6 +21,7 @@ ops = CudaOps(dev)
 eng = SpatialVLAEngine(cfg, sd, ops)
 del sd
 torch.cuda.empty_cache()
+eng.decode_hilo = False          # the persistent kernel implements the plain bf16 chain (no hi/lo activation pairs)
 t = cfg["text_config"]
 H = t["hidden_size"]
 P = 278 if name != "tiny" else 70

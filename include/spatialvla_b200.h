@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SVLA_ABI_VERSION 2
+#define SVLA_ABI_VERSION 3
 
 const char* svla_last_error(void);
 int svla_abi_version(void);
@@ -132,6 +132,9 @@ typedef struct SvlaAttnArgs {
                                 query row, s = log2(e) * (soft-capped, scaled, masked score) -- what svla_attention_bwd needs from the
                                 forward pass.  Only the tcgen05 kernels provide it (every shape of the training step). */
   int64_t lse_stride;
+  int32_t window;            /* > 0: key slot j is masked for query slot i = query index + (sk - sq) when i - j >= window, on top of every
+                                other mask (Gemma2's sliding-window layers, model/modeling_gemma2.py:461-471: tril(diagonal=-window)
+                                also over the bidirectional prefix mask); 0 = global layer */
 } SvlaAttnArgs;
 
 int svla_attention(const SvlaAttnArgs* args, void* stream);
@@ -149,10 +152,12 @@ int svla_decode_attention(const void* q, const void* kcache, const void* vcache,
 int svla_decode_attention_fused(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache, void* vcache,
                                 void* out, int batch, int hq, int hkv, int d, int smax, int ctx, float theta, float scale,
                                 float softcap, const int32_t* kv_start, void* stream);
-/* hi/lo variant (see svla_gemm_skinny X_HILO): the output leaves as two bf16 planes, out_hi = bf16(o), out_lo = bf16(o - out_hi) */
-int svla_decode_attention_fused_hilo(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache, void* vcache,
-                                     void* out_hi, void* out_lo, int batch, int hq, int hkv, int d, int smax, int ctx, float theta,
-                                     float scale, float softcap, const int32_t* kv_start, void* stream);
+/* Extended entry.  out_lo != NULL: the output leaves as two bf16 planes, out_hi = bf16(o) and out_lo = bf16(o - out_hi), for the
+ * X_HILO mode of svla_gemm_skinny, and the rotated query stays in fp32.  window > 0: sliding-window layer (even Gemma2 layers,
+ * model/modeling_gemma2.py:343,441-473): only the last `window` cache slots [ctx - window, ctx) receive weight. */
+int svla_decode_attention_fused_ex(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache, void* vcache,
+                                   void* out_hi, void* out_lo, int batch, int hq, int hkv, int d, int smax, int ctx, float theta,
+                                   float scale, float softcap, const int32_t* kv_start, int window, void* stream);
 
 /* G4: one whole Gemma2 decode step (all layers) for batch <= 64 in ONE persistent tensor-core launch: one CTA per SM
  * (cooperative launch), a TMA weight ring that streams the [128 x 64] weight tiles of ALL phases of ALL layers without waiting

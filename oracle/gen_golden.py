@@ -177,6 +177,34 @@ def gen_model_padded(n_new=6):
     print("tiny_model_padded: tokens", toks.tolist())
 
 
+WINDOW = 48
+
+
+def gen_model_window(n_new=6):
+    """Gemma2's sliding-window layers (even layer_idx, model/modeling_gemma2.py:343,441-473) through the live reference: the tiny
+    configuration with text_config.sliding_window = 48 << prompt length 264, so the window predicate is active in the bidirectional
+    prefill (tril(diagonal=-window) over the full mask) AND in every decode step (the reference's sliding cache keeps the last
+    `window` slots) -> tests/golden/tiny_model_window.npz; plus the same for the left-padded batch."""
+    cfg, px_u8, ids, K = tiny_inputs()
+    cfg["text_config"]["sliding_window"] = WINDOW
+    px = px_u8.float() / 255.0
+    model = compat.build_reference_model(cfg)
+    model.load_state_dict(synth_state_dict(cfg, seed=0), strict=True)
+    lo, hi = cfg["action_token_begin_idx"], cfg["action_token_begin_idx"] + cfg["spatial_token_num"]
+    toks, logits = compat.reference_greedy(model, ids, px, K, n_new, lo, hi)
+    B, P = ids.shape
+    with torch.no_grad():          # every prefill position (no cache): post-softcap logits at 64 fixed action columns
+        full = model(input_ids=ids, pixel_values=px, intrinsic=K, attention_mask=torch.zeros(B, 1, P, P), use_cache=False).logits
+    cols = torch.arange(lo, hi, (hi - lo) // 64)[:64]
+    _, px_u8p, idsp, amp, Kp = padded_inputs()
+    toks_p, logits_p = compat.reference_greedy_padded(model, idsp, amp, px_u8p.float() / 255.0, Kp, n_new, lo, hi)
+    np.savez_compressed(os.path.join(GOLD, "tiny_model_window.npz"), window=np.int64(WINDOW), tokens=toks.numpy(),
+                        logits=logits.numpy().astype(np.float32), prefill_cols=cols.numpy(),
+                        prefill_logits=full[:, :, cols].float().numpy(), tokens_padded=toks_p.numpy(),
+                        logits_padded=logits_p.numpy().astype(np.float32), n_new=np.int64(n_new))
+    print("tiny_model_window: tokens", toks.tolist(), "padded", toks_p.tolist())
+
+
 def train_inputs(B=2, T=6, n_act=6, seed=2):
     """Training-shaped samples (train/monkey_patch.py:21-75, data/dataset.py:145-153): prefix = image tokens + BOS + text +
     newline (token type 0, labels -100), suffix = action tokens + EOS (token type 1, labels = ids)."""
@@ -281,9 +309,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "train":
         gen_model_train()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "window":
+        gen_model_window()
+        sys.exit(0)
     gen_tokenizer()
     gen_model()
     gen_model_padded()
+    gen_model_window()
     gen_model_train()
     gen_model_train_grads()
     gen_adaption()

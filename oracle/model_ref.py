@@ -411,6 +411,14 @@ def gemma2_forward(sd, cfg, x, pos_start, kv_cache, bidirectional, pads=None, ca
             # triangular mask (model/modeling_spatialvla.py:292-293,304-305)
             mask = torch.arange(L)[None, :] > torch.clamp(torch.arange(S)[:, None] + (L - S), min=causal_prefix - 1)
             sc = sc.masked_fill(mask, float("-inf"))
+        win = t.get("sliding_window")
+        if win and i % 2 == 0 and K.shape[2] > win:
+            # sliding-window layers (even layer_idx, model/modeling_gemma2.py:343,441): key slot j is masked for query slot i when
+            # i - j >= window (:461-471, tril(diagonal=-window) on top of whatever mask the layer received -- also on top of the
+            # bidirectional prefix mask); a decode row therefore sees the last `window` slots (HF's HybridCache keeps exactly those)
+            L = K.shape[2]
+            qslot = torch.arange(S)[:, None] + (L - S)
+            sc = sc.masked_fill((qslot - torch.arange(L)[None, :]) >= win, float("-inf"))
         if pads is not None:
             sc = sc.masked_fill((torch.arange(K.shape[2])[None, :] < pads[:, None])[:, None, None, :], float("-inf"))
         ctx = (torch.softmax(sc, -1) @ V).transpose(1, 2).reshape(B, S, nh * hd)

@@ -267,7 +267,7 @@ class RefOps:
 
     def attention(self, q, k, v, out, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
                   scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0, relpos_head_major=False, kv_start=None,
-                  causal_prefix=0, lse=None):
+                  causal_prefix=0, lse=None, window=0):
         self.launches += 1
         Q = self._strided(q, *q_strides, batch, sq, hq, d).float().permute(0, 2, 1, 3)
         K = self._strided(k, *k_strides, batch, sk, hkv, d).float().permute(0, 2, 1, 3).repeat_interleave(hq // hkv, 1)
@@ -286,6 +286,8 @@ class RefOps:
             # prefix-LM (training forward, model/modeling_spatialvla.py:292-305): keys < causal_prefix stay visible
             m = torch.arange(sk)[None, :] > torch.clamp(torch.arange(sq)[:, None] + (sk - sq), min=causal_prefix - 1)
             s = s.masked_fill(m, float("-inf"))
+        if window:                  # sliding-window layer: key slot j masked for query slot i when i - j >= window
+            s = s.masked_fill((torch.arange(sq)[:, None] + (sk - sq) - torch.arange(sk)[None, :]) >= window, float("-inf"))
         # the kernel rounds the un-normalised probabilities to bf16 and divides by the fp32 row sum
         mx = s.max(-1, keepdim=True).values
         e = torch.exp(s - mx)
@@ -294,7 +296,7 @@ class RefOps:
         if lse is not None:                      # log2-domain log-sum-exp of every row, kept for the backward pass
             lse[:, :, :sq] = torch.logsumexp(s, -1) * 1.4426950408889634
 
-    def decode_attention(self, q, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, scale, softcap=0.0, kv_start=None):
+    def decode_attention(self, q, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, scale, softcap=0.0, kv_start=None, window=0):
         self.launches += 1
         Q = q.float().view(batch, hq, 1, d)
         K = kcache.float().view(batch, smax, hkv, d)[:, :ctx].permute(0, 2, 1, 3).repeat_interleave(hq // hkv, 1)
@@ -304,11 +306,13 @@ class RefOps:
             s = softcap * torch.tanh(s / softcap)
         if kv_start is not None:
             s = s.masked_fill((torch.arange(ctx)[None, :] < kv_start.long()[:, None])[:, None, None, :], float("-inf"))
+        if window:                  # re-statement only (the fused kernel is the windowed decode path on the device)
+            s = s.masked_fill((torch.arange(ctx) < ctx - window)[None, None, None, :], float("-inf"))
         p = torch.softmax(s, -1).to(BF16).float()
         out.view(batch, hq, d)[:] = (p @ V).squeeze(2).to(BF16)
 
     def decode_attention_fused(self, qkv_partials, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, theta, scale, softcap=0.0,
-                               kv_start=None):
+                               kv_start=None, window=0):
         if out.dim() == 3:                      # hi/lo output pair: the kernel's own precision (fp32 q and probabilities, bf16 cache)
             q = torch.empty(batch, hq * d, dtype=F32)
             self.rope_kv(qkv_partials, q, kcache, vcache, batch=batch, s=1, hq=hq, hkv=hkv, d=d, smax=smax, pos0=ctx - 1, theta=theta,
@@ -321,6 +325,8 @@ class RefOps:
                 s = softcap * torch.tanh(s / softcap)
             if kv_start is not None:
                 s = s.masked_fill((torch.arange(ctx)[None, :] < kv_start.long()[:, None])[:, None, None, :], float("-inf"))
+            if window:
+                s = s.masked_fill((torch.arange(ctx) < ctx - window)[None, None, None, :], float("-inf"))
             _store_bf16(out, (torch.softmax(s, -1) @ V).squeeze(2).reshape(batch, hq * d), hq * d)
             return
         q = torch.empty(batch, hq * d, dtype=BF16)
@@ -328,7 +334,7 @@ class RefOps:
                      row_pads=kv_start)
         self.launches -= 1                      # one launch on the device
         self.decode_attention(q, kcache, vcache, out, batch=batch, hq=hq, hkv=hkv, d=d, smax=smax, ctx=ctx, scale=scale, softcap=softcap,
-                              kv_start=kv_start)
+                              kv_start=kv_start, window=window)
 
     # ---- fused memory-bound ops
     def layernorm(self, x, gamma, beta, eps, *, out_bf16=None, out_f32=None, relu=False):

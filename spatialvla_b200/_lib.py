@@ -53,6 +53,7 @@ class SvlaAttnArgs(C.Structure):
         ("d", C.c_int32), ("scale", C.c_float), ("softcap", C.c_float), ("causal", C.c_int32),
         ("relpos_table", C.c_void_p), ("relpos_win", C.c_int32), ("relpos_head_major", C.c_int32),
         ("kv_start", C.c_void_p), ("causal_prefix", C.c_int32), ("lse", C.c_void_p), ("lse_stride", C.c_int64),
+        ("window", C.c_int32),
     ]
 
 
@@ -96,7 +97,7 @@ SIGNATURES = {
     "svla_layernorm": (_I, [_P, _P, _P, _F, _L, _I, _P, _P, _I, _P]),
     "svla_rmsnorm_residual": (_I, [_P, _P, _P, _P, _F, _L, _I, _P, _I, _L, _P]),
     "svla_rmsnorm_residual_hilo": (_I, [_P, _P, _P, _P, _F, _L, _I, _P, _P, _I, _L, _P]),
-    "svla_decode_attention_fused_hilo": (_I, [_P, _I, _L, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P]),
+    "svla_decode_attention_fused_ex": (_I, [_P, _I, _L, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P, _I, _P]),
     "svla_decode_mega_supported": (_I, [_I, _I, _I, _I, _I, _I, _I]),
     "svla_decode_mega_scratch_bytes": (_L, [_I, _I, _I, _I, _I]),
     "svla_decode_mega_maps_bytes": (_L, [_I]),
@@ -202,7 +203,7 @@ def load_library():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.svla_abi_version() != 2:
+    if lib.svla_abi_version() != 3:
         raise SvlaError("libspatialvla_b200.so ABI version mismatch")
     _lib = lib
     return lib

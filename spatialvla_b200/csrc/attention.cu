@@ -74,6 +74,7 @@ struct AttnP {
   const int* kv_start;
   int win;
   int prefix;          // causal only: keys < prefix are visible to every query (prefix-LM)
+  int window;          // > 0: key slot j is masked for query slot i when i - j >= window (sliding-window layers)
 };
 
 // Loads rows [r0, r0+ROWS) x d (bf16) of a [s, ...] strided matrix into smem [ROWS][DP+8]; rows >= s are zeroed.
@@ -203,7 +204,7 @@ svla_flash_attn_kernel(const AttnP p) {
     // version), so every feature is folded into as few per-element operations as possible and the special cases
     // (CLS row/column of BEiT, ragged/causal mask, large soft-cap arguments) are warp-uniform branches.
     const int kstart = p.kv_start ? p.kv_start[b] : 0;
-    const bool need_mask = f_causal || (jt + 1) * kBKV > p.sk || kstart > jt * kBKV;
+    const bool need_mask = f_causal || (jt + 1) * kBKV > p.sk || kstart > jt * kBKV || p.window > 0;
     float mx[2] = {-INFINITY, -INFINITY};
     if (f_relpos) {
       const bool has_cls = (jt == 0) || (q0 + warp * 16 == 0);      // only then a CLS key / query is in this block
@@ -265,7 +266,8 @@ svla_flash_attn_kernel(const AttnP p) {
         for (int e = 0; e < 4; ++e) {
           const int qi = qi0 + (e >> 1) * 8;
           const int kj = jt * kBKV + nt * 8 + 2 * t + (e & 1);
-          const bool masked = (kj >= p.sk) || (kj < kstart) || (f_causal && kj > max(qi + causal_off, p.prefix - 1));
+          const bool masked = (kj >= p.sk) || (kj < kstart) || (f_causal && kj > max(qi + causal_off, p.prefix - 1)) ||
+                              (p.window > 0 && qi + causal_off - kj >= p.window);
           s[nt][e] = masked ? -INFINITY : s[nt][e];
         }
       }
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(kDecThreads, STAGES <= 6 ? 2 : 1)
 svla_decode_attn_fused_kernel(const float* __restrict__ qkv_f32, int n_partials, long long partial_stride,
                               __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out,
                               int hq, int hkv, int smax, int ctx, float theta, float scale, float softcap,
-                              const int* __restrict__ kv_start, __nv_bfloat16* __restrict__ out_lo) {
+                              const int* __restrict__ kv_start, __nv_bfloat16* __restrict__ out_lo, int window) {
   constexpr int D = 256;
   extern __shared__ __align__(16) uint8_t sm_fused[];
   svla_dec::ItemSmem sm;
@@ -508,6 +510,7 @@ svla_decode_attn_fused_kernel(const float* __restrict__ qkv_f32, int n_partials,
   a.kc = kc; a.vc = vc; a.out = out; a.out_lo = out_lo;
   a.hq = hq; a.hkv = hkv; a.smax = smax; a.ctx = ctx;
   a.kstart = kv_start ? kv_start[a.b] : 0;              // immutable input (not written by the PDL predecessor)
+  a.kmask = window > 0 ? max(a.kstart, ctx - window) : a.kstart;     // sliding-window layer: the last `window` slots only
   a.theta = theta; a.scale = scale; a.softcap = softcap;
   pdl_launch_dependents();          // lets the o-projection GEMM start prefetching its weights
   // The cached rows [0, ctx-1) were written by the prefill or by this layer's kernel of an EARLIER decode step, i.e. at least
@@ -556,6 +559,7 @@ extern "C" int svla_attention(const SvlaAttnArgs* a, void* stream) {
   p.hq = a->hq; p.hkv = a->hkv; p.sq = a->sq; p.sk = a->sk; p.d = a->d;
   p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.relpos = a->relpos_table; p.win = a->relpos_win; p.head_major = a->relpos_head_major; p.kv_start = a->kv_start;
   p.prefix = a->causal ? a->causal_prefix : 0;
+  p.window = a->window;
   const int mode = (p.relpos ? 1 : 0) | (p.softcap > 0.f ? 2 : 0) | (p.causal ? 4 : 0);
   if (a->d <= 32) return launch_attn<32, 8>(p, a->batch, st);
   if (a->d <= 64) return mode == 1 ? launch_attn<64, 1>(p, a->batch, st) : launch_attn<64, 8>(p, a->batch, st);
@@ -591,29 +595,30 @@ extern "C" int svla_decode_attention(const void* q, const void* kcache, const vo
 // Decode step of one layer after the qkv projection: RoPE + cache append + attention in one launch (see the kernel).
 static int decode_attention_fused_impl(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache, void* vcache,
                                        void* out, void* out_lo, int batch, int hq, int hkv, int d, int smax, int ctx, float theta,
-                                       float scale, float softcap, const int32_t* kv_start, void* stream);
+                                       float scale, float softcap, const int32_t* kv_start, int window, void* stream);
 
 extern "C" int svla_decode_attention_fused(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache, void* vcache,
                                            void* out, int batch, int hq, int hkv, int d, int smax, int ctx, float theta,
                                            float scale, float softcap, const int32_t* kv_start, void* stream) {
   return decode_attention_fused_impl(qkv_f32, n_partials, partial_stride, kcache, vcache, out, nullptr, batch, hq, hkv, d, smax, ctx,
-                                     theta, scale, softcap, kv_start, stream);
+                                     theta, scale, softcap, kv_start, 0, stream);
 }
 
-// hi/lo variant of the decode chain: the attention output leaves as two bf16 planes (hi = bf16(o), lo = bf16(o - hi)) for the
-// X_HILO mode of the o-projection (svla_gemm_skinny)
-extern "C" int svla_decode_attention_fused_hilo(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache,
-                                                void* vcache, void* out_hi, void* out_lo, int batch, int hq, int hkv, int d, int smax,
-                                                int ctx, float theta, float scale, float softcap, const int32_t* kv_start,
-                                                void* stream) {
-  SVLA_REQUIRE(out_lo, "svla_decode_attention_fused_hilo: null lo plane");
+// Extended entry: out_lo != NULL -> the output leaves as two bf16 planes (hi = bf16(o), lo = bf16(o - hi)) for the X_HILO mode of
+// the o-projection (svla_gemm_skinny) and the query stays in fp32; window > 0 -> sliding-window layer (even Gemma2 layers,
+// model/modeling_gemma2.py:343,441-473): only the last `window` cache slots [ctx - window, ctx) receive weight.
+extern "C" int svla_decode_attention_fused_ex(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache,
+                                              void* vcache, void* out_hi, void* out_lo, int batch, int hq, int hkv, int d, int smax,
+                                              int ctx, float theta, float scale, float softcap, const int32_t* kv_start, int window,
+                                              void* stream) {
+  SVLA_REQUIRE(window >= 0, "svla_decode_attention_fused_ex: negative window");
   return decode_attention_fused_impl(qkv_f32, n_partials, partial_stride, kcache, vcache, out_hi, out_lo, batch, hq, hkv, d, smax, ctx,
-                                     theta, scale, softcap, kv_start, stream);
+                                     theta, scale, softcap, kv_start, window, stream);
 }
 
 static int decode_attention_fused_impl(const float* qkv_f32, int n_partials, int64_t partial_stride, void* kcache, void* vcache,
                                        void* out, void* out_lo, int batch, int hq, int hkv, int d, int smax, int ctx, float theta,
-                                       float scale, float softcap, const int32_t* kv_start, void* stream) {
+                                       float scale, float softcap, const int32_t* kv_start, int window, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SVLA_REQUIRE(qkv_f32 && kcache && vcache && out, "svla_decode_attention_fused: null pointer");
   SVLA_REQUIRE(d == 256, "svla_decode_attention_fused: head dim %d unsupported (256 only)", d);
@@ -645,14 +650,14 @@ static int decode_attention_fused_impl(const float* qkv_f32, int n_partials, int
   cudaError_t le;
   if (deep)
     le = grp == 1 ? svla_launch_pdl(svla_decode_attn_fused_kernel<1, kFusedStagesDeep>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
-                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start, olp)
+                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start, olp, window)
                   : svla_launch_pdl(svla_decode_attn_fused_kernel<2, kFusedStagesDeep>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
-                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start, olp);
+                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start, olp, window);
   else
     le = grp == 1 ? svla_launch_pdl(svla_decode_attn_fused_kernel<1, kFusedStages>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
-                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start, olp)
+                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start, olp, window)
                   : svla_launch_pdl(svla_decode_attn_fused_kernel<2, kFusedStages>, grid, dim3(kDecThreads), smem, st, qkv_f32, n_partials, ps, kcp, vcp, op,
-                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start, olp);
+                                    hq, hkv, smax, ctx, theta, scale, softcap, kv_start, olp, window);
   SVLA_REQUIRE(le == cudaSuccess, "svla_decode_attention_fused: launch failed: %s", cudaGetErrorString(le));
   SVLA_LAUNCH_CHECK("svla_decode_attn_fused");
   return 0;

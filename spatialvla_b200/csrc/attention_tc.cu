@@ -57,6 +57,7 @@ struct Params {
   int head_major;      // relpos is [hq][nrel] (coalesced per-head row) instead of HF's [nrel][hq]
   const int* kv_start; // [batch] or null: keys < kv_start[b] are masked (left-padded prompts)
   int prefix;          // causal only: keys < prefix are visible to every query (prefix-LM training mask)
+  int window;          // > 0: key slot j is masked for query slot i when i - j >= window (Gemma2 sliding-window layers)
   float* lse;          // null or fp32 [batch, hq, lse_stride]: log2-domain logsumexp of every query row (kept for the backward pass)
   long long lse_stride;
 };
@@ -463,11 +464,12 @@ svla_flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
 #pragma unroll
         for (int i = 0; i < HC; ++i) s[i] *= sl2;
       }
-      if (kCausal || k0 + HC > p.sk || kstart > k0) {
+      if (kCausal || k0 + HC > p.sk || kstart > k0 || p.window > 0) {
 #pragma unroll
         for (int i = 0; i < HC; ++i) {
           const int kj = k0 + i;
-          if (kj >= p.sk || kj < kstart || (kCausal && kj > max(qi + causal_off, p.prefix - 1))) s[i] = -INFINITY;
+          if (kj >= p.sk || kj < kstart || (kCausal && kj > max(qi + causal_off, p.prefix - 1)) ||
+              (p.window > 0 && qi + causal_off - kj >= p.window)) s[i] = -INFINITY;
         }
       }
       float mj = -INFINITY;
@@ -676,6 +678,7 @@ int svla_attention_tc_try(const SvlaAttnArgs* a, void* stream) {
     p.relpitch = pitch;
   }
   p.prefix = a->causal ? a->causal_prefix : 0;
+  p.window = a->window;
   p.lse = a->lse;
   p.lse_stride = a->lse_stride;
   // a batch stride of 0 is not expressible in a tensor map; batch == 1 problems get a dummy stride

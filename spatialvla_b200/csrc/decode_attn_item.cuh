@@ -67,6 +67,7 @@ struct ItemArgs {
   __nv_bfloat16* out;        // [B, hq * D]
   __nv_bfloat16* out_lo;     // NULL, or the lo plane bf16(o - bf16(o)) of the hi/lo activation pair (same layout as out)
   int b, hk, hq, hkv, smax, ctx, kstart;
+  int kmask;                 // first cache slot that may receive weight: max(kstart, ctx - sliding window)
   float theta, scale, softcap;
 };
 
@@ -76,7 +77,7 @@ __device__ __forceinline__ void decode_attn_item(const ItemArgs& a, const ItemSm
   constexpr int TPP = 8 / GRP;            // threads per (key, head) pair
   constexpr int PPT = 32 / TPP;           // 16-byte pieces of a K row per thread
   constexpr int NW = kItemThreads / 32;
-  const int hq = a.hq, hkv = a.hkv, ctx = a.ctx, smax = a.smax, b = a.b, hk = a.hk, kstart = a.kstart;
+  const int hq = a.hq, hkv = a.hkv, ctx = a.ctx, smax = a.smax, b = a.b, hk = a.hk, kstart = a.kstart, kmask = a.kmask;
   const int ctx_pad = (ctx + 31) & ~31;
   const int lane = t & 31, warp = t >> 5;
   const int n_old = ctx - 1;                                  // cached keys; the new token sits at slot ctx - 1
@@ -209,7 +210,7 @@ __device__ __forceinline__ void decode_attn_item(const ItemArgs& a, const ItemSm
     if (part == 0 && key < n_old) {
       float sc = dot * a.scale;
       if (a.softcap > 0.f) sc = a.softcap * tanh_small(sc * inv_cap);
-      s.p[g_k * ctx_pad + key] = key < kstart ? -INFINITY : sc;       // padded prompt slots never receive weight
+      s.p[g_k * ctx_pad + key] = key < kmask ? -INFINITY : sc;        // padded prompt slots / slots behind the sliding window never receive weight
     }
   }
   // ---- new key's score (warp g computes head g)

@@ -502,6 +502,7 @@ svla_decode_mega_kernel(const MegaParams p) {
           ia.kc = kc; ia.vc = vc; ia.out = p.ctxb; ia.out_lo = nullptr;
           ia.hq = p.hq; ia.hkv = p.hkv; ia.smax = p.smax; ia.ctx = p.ctx;
           ia.kstart = p.kv_start ? p.kv_start[ia.b] : 0;
+          ia.kmask = ia.kstart;
           ia.theta = p.theta; ia.scale = p.scale; ia.softcap = p.softcap;
           if (grp == 2) svla_dec::decode_attn_item<2, kKvStages>(ia, sm, t, wsync, [] {});
           else svla_dec::decode_attn_item<1, kKvStages>(ia, sm, t, wsync, [] {});

@@ -658,16 +658,19 @@ class SpatialVLAEngine:
         scale, cap = t["query_pre_attn_scalar"] ** -0.5, t["attn_logit_softcapping"] or 0.0
         M, pos0, smax = B * S, cache["len"], cache["smax"]
         assert pos0 + S <= smax, "KV cache overflow"
-        win = t.get("sliding_window")
-        if win and pos0 + S > win:
-            # Gemma2 alternates sliding-window and global layers (model/modeling_gemma2.py:364-413); every context on this path
-            # (278 + 12 tokens) is far inside the 4096-token window, where the two layer kinds are identical
-            raise NotImplementedError(f"context of {pos0 + S} tokens exceeds the sliding window ({win}): windowed layers are not implemented")
-        if S == 1 and not bidirectional and self._mega_ok(B, pos0 + 1):
+        # Gemma2 alternates sliding-window (even layer_idx) and global layers (model/modeling_gemma2.py:343,441-473).  While the
+        # context fits the window (every context of the benchmark: 278 + 12 tokens against 4096) the two kinds are identical and
+        # no predicate is passed; beyond it the even layers mask key slot j for query slot i when i - j >= window, in the prefill
+        # kernels (on top of the bidirectional prefix mask, as the reference's tril(diagonal=-window) does) and in the fused decode
+        # kernel (the last `window` slots -- what HF's sliding cache keeps).  The cache itself keeps every slot.
+        win = int(t.get("sliding_window") or 0)
+        win = win if pos0 + S > win else 0
+        if S == 1 and not bidirectional and not win and self._mega_ok(B, pos0 + 1):
             return self.gemma_decode_mega(x, B, cache, pads=pads)
         skinny = (S == 1 and M <= 128)          # decode step: weight-streaming swap-AB / split-K GEMMs
         # Decode rows carry their activations between the kernels of the chain as hi/lo bf16 PAIRS [2, M, cols] (hi = bf16(v),
-        # lo = bf16(v - hi)): the weight-streaming GEMMs are HBM-bound, a twice as wide activation tile is free, and the bf16
+        # lo = bf16(v - hi)): the weight-streaming GEMMs are HBM-bound, a twice as wide activation tile costs ~7 % of a decode step
+        # (the weights are still streamed once; measured 1886 -> 2023 us at batch 64), and the bf16
         # rounding of a row's OWN activations in front of each of the 4 x 26 Linear layers is what dominates the logit noise of
         # this path against the fp32 reference (CPU re-statement: rms 0.0050 -> 0.0010 on the decode positions; the cached K / V
         # of earlier positions average out over the keys).
@@ -681,6 +684,7 @@ class SpatialVLAEngine:
         ctx = act_buf(nh * hd)
         for li, L_ in enumerate(g["layers"]):
             kc, vc = cache["k"][li], cache["v"][li]
+            win_l = win if li % 2 == 0 else 0
             if skinny:
                 qkv = self._skinny_partial(h, L_["wqkv"], M)
             else:
@@ -688,7 +692,7 @@ class SpatialVLAEngine:
             if skinny and hd == 256 and nh // nkv in (1, 2):
                 # decode: RoPE + cache append + attention over the cache in one launch
                 ops.decode_attention_fused(qkv, kc, vc, ctx, batch=B, hq=nh, hkv=nkv, d=hd, smax=smax, ctx=pos0 + 1, theta=theta,
-                                           scale=scale, softcap=cap, kv_start=pads)
+                                           scale=scale, softcap=cap, kv_start=pads, window=win_l)
                 br = self._skinny_partial(ctx, L_["wo"], M)
                 ops.rmsnorm_residual(x, branch=br, w_post=L_["ln_post_attn"], w_pre=L_["ln_pre_ff"], eps=eps, out_bf16=h)
                 act = act_buf(FF)
@@ -699,13 +703,15 @@ class SpatialVLAEngine:
                 continue
             ops.rope_kv(qkv, q, kc, vc, batch=B, s=S, hq=nh, hkv=nkv, d=hd, smax=smax, pos0=pos0, theta=theta, row_pads=pads)
             if S == 1:
+                if win_l:
+                    raise NotImplementedError("sliding-window decode needs the fused decode kernel (head_dim 256, GQA group 1 or 2)")
                 ops.decode_attention(q, kc, vc, ctx, batch=B, hq=nh, hkv=nkv, d=hd, smax=smax, ctx=pos0 + 1, scale=scale, softcap=cap,
                                      kv_start=pads)
             else:
                 kvs = (smax * nkv * hd, nkv * hd)
                 ops.attention(q, kc, vc, ctx, batch=B, hq=nh, hkv=nkv, sq=S, sk=pos0 + S, d=hd, q_strides=(S * nh * hd, nh * hd),
                               k_strides=kvs, v_strides=kvs, o_strides=(S * nh * hd, nh * hd), scale=scale, softcap=cap,
-                              causal=not bidirectional, kv_start=pads, causal_prefix=0 if bidirectional else causal_prefix)
+                              causal=not bidirectional, kv_start=pads, causal_prefix=0 if bidirectional else causal_prefix, window=win_l)
             br = self._skinny_partial(ctx, L_["wo"], M) if skinny else self._lin(ctx, L_["wo"], M, F32)
             ops.rmsnorm_residual(x, branch=br, w_post=L_["ln_post_attn"], w_pre=L_["ln_pre_ff"], eps=eps, out_bf16=h)
             if skinny:

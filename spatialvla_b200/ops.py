@@ -248,7 +248,7 @@ class CudaOps:
     # ---- G2 / G3
     def attention(self, q, k, v, out, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
                   scale, softcap=0.0, causal=False, relpos_table=None, relpos_win=0, relpos_head_major=False, kv_start=None,
-                  causal_prefix=0, lse=None):
+                  causal_prefix=0, lse=None, window=0):
         """strides = (batch stride, token stride) in elements; head h lives at column offset h*d.
         lse: fp32 [batch, hq, >= sq] -- the kernel also stores the log2-domain log-sum-exp of every query row (training forward).
         relpos_table: fp32 [(2*win-1)^2+3, hq] (HF layout) or, with relpos_head_major, its transpose [hq, (2*win-1)^2+3]."""
@@ -262,6 +262,7 @@ class CudaOps:
         a.o_bs, a.o_ss = o_strides
         a.batch, a.hq, a.hkv, a.sq, a.sk, a.d = batch, hq, hkv, sq, sk, d
         a.scale, a.softcap, a.causal = float(scale), float(softcap or 0.0), int(bool(causal))
+        a.window = int(window or 0)       # sliding-window layer: key slot j masked for query slot i when i - j >= window
         _req(relpos_table is None or relpos_table.dtype == F32, "attention: relpos table must be fp32")
         _req(relpos_table is None or relpos_table.is_contiguous(), "attention: relpos table must be contiguous")
         a.relpos_table, a.relpos_win, a.relpos_head_major = _ptr(relpos_table), int(relpos_win), int(bool(relpos_head_major))
@@ -282,22 +283,19 @@ class CudaOps:
                 "svla_decode_attention")
 
     def decode_attention_fused(self, qkv_partials, kcache, vcache, out, *, batch, hq, hkv, d, smax, ctx, theta, scale, softcap=0.0,
-                               kv_start=None):
+                               kv_start=None, window=0):
         """RoPE + KV-cache append + attention of one decode step; qkv_partials fp32 [splits, batch, (hq+2hkv)*d].
-        out bf16 [batch, hq*d], or a contiguous hi/lo pair [2, batch, hq*d]."""
+        out bf16 [batch, hq*d], or a contiguous hi/lo pair [2, batch, hq*d]; window > 0: only the last `window` cache slots."""
         _req(qkv_partials.dtype == F32 and qkv_partials.dim() == 3 and qkv_partials.stride(2) == 1 and
              qkv_partials.stride(1) == qkv_partials.shape[2], "decode_attention_fused: qkv must be fp32 [splits, batch, W]")
+        hi, lo = out, None
         if out.dim() == 3:
             _req(out.shape[0] == 2 and out.is_contiguous(), "decode_attention_fused: hi/lo output must be contiguous [2, batch, hq*d]")
-            L.check(self.lib.svla_decode_attention_fused_hilo(_ptr(qkv_partials), int(qkv_partials.shape[0]), int(qkv_partials.stride(0)),
-                                                              _ptr(kcache), _ptr(vcache), _ptr(out[0]), _ptr(out[1]), batch, hq, hkv, d, smax,
-                                                              ctx, float(theta), float(scale), float(softcap or 0.0), _ptr(kv_start),
-                                                              self._stream()), "svla_decode_attention_fused_hilo")
-            return
-        L.check(self.lib.svla_decode_attention_fused(_ptr(qkv_partials), int(qkv_partials.shape[0]), int(qkv_partials.stride(0)),
-                                                     _ptr(kcache), _ptr(vcache), _ptr(out), batch, hq, hkv, d, smax, ctx,
-                                                     float(theta), float(scale), float(softcap or 0.0), _ptr(kv_start), self._stream()),
-                "svla_decode_attention_fused")
+            hi, lo = out[0], out[1]
+        L.check(self.lib.svla_decode_attention_fused_ex(_ptr(qkv_partials), int(qkv_partials.shape[0]), int(qkv_partials.stride(0)),
+                                                        _ptr(kcache), _ptr(vcache), _ptr(hi), _ptr(lo), batch, hq, hkv, d, smax, ctx,
+                                                        float(theta), float(scale), float(softcap or 0.0), _ptr(kv_start),
+                                                        int(window or 0), self._stream()), "svla_decode_attention_fused_ex")
 
     # ---- G4 persistent small-batch decode step
     # ---- persistent tensor-core decode step (csrc/decode_mega.cu)

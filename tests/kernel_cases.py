@@ -340,7 +340,7 @@ SKINNY_CASES = [
 
 # ------------------------------------------------------------------------------------------------ attention
 def attn_case(name, B, hq, hkv, sq, sk, d, *, scale=None, softcap=0.0, causal=False, relpos_win=0, packed_qkv=False,
-              smax=None, seed=0, head_major=False, kv_start=None, causal_prefix=0):
+              smax=None, seed=0, head_major=False, kv_start=None, causal_prefix=0, window=0):
     def case(dev="cuda:0"):
         g = _gen(seed)
         sc = scale if scale is not None else d ** -0.5
@@ -370,7 +370,7 @@ def attn_case(name, B, hq, hkv, sq, sk, d, *, scale=None, softcap=0.0, causal=Fa
                 kvs = (sm * hkv * d, hkv * d)
                 ops.attention(to(q), to(kc), to(vc), out, batch=B, hq=hq, hkv=hkv, sq=sq, sk=sk, d=d,
                               q_strides=(sq * hq * d, hq * d), k_strides=kvs, v_strides=kvs, o_strides=(sq * hq * d, hq * d),
-                              scale=sc, softcap=softcap, causal=causal, causal_prefix=causal_prefix,
+                              scale=sc, softcap=softcap, causal=causal, causal_prefix=causal_prefix, window=window,
                               kv_start=None if kv_start is None else to(torch.tensor(kv_start, dtype=torch.int32)))
                 return out
         c, r = _both(run, dev)
@@ -431,6 +431,33 @@ def decode_attn_fused_case(dev="cuda:0"):
     return res
 
 
+def decode_attn_fused_window_case(dev="cuda:0"):
+    """fused decode step on a sliding-window layer: only the last `window` cache slots receive weight (plain and hi/lo outputs,
+    left-padded rows whose padding lies inside / outside the window)."""
+    res = Result("decode_attention_fused_window")
+    for tag, (B, hq, hkv, smax, ctx, splits, window, pads) in {"w48_ctx271": (3, 8, 4, 300, 271, 3, 48, None),
+                                                                "w200_pads_inside": (3, 8, 4, 290, 285, 4, 200, [0, 6, 97]),
+                                                                "w1_self_only": (2, 4, 2, 64, 40, 2, 1, None),
+                                                                "w_ge_ctx": (2, 2, 2, 40, 33, 2, 33, None)}.items():
+        g = _gen(ctx + window)
+        d = 256
+        part = _randn(g, splits, B, (hq + 2 * hkv) * d, scale=0.6)
+        kc0, vc0 = _randn(g, B, smax, hkv, d, dtype=BF16), _randn(g, B, smax, hkv, d, dtype=BF16)
+        pt = None if pads is None else torch.tensor(pads, dtype=torch.int32)
+
+        def run(ops, to):
+            kc, vc = to(kc0), to(vc0)
+            out, pair = ops.zeros((B, hq * d), BF16), ops.zeros((2, B, hq * d), BF16)
+            kw = dict(batch=B, hq=hq, hkv=hkv, d=d, smax=smax, ctx=ctx, theta=10000.0, scale=1 / 16, softcap=50.0, kv_start=to(pt), window=window)
+            ops.decode_attention_fused(to(part), kc, vc, out, **kw)
+            ops.decode_attention_fused(to(part), kc, vc, pair, **kw)
+            return out, _hilo_sum(pair)
+        (co, cp), (ro, rp) = _both(run, dev)
+        res.add(f"out[{tag}]", _err(co, ro), 1.5e-2)
+        res.add(f"pair[{tag}]", _err(cp, rp), 5e-4)
+    return res
+
+
 ATTN_CASES = [
     attn_case("attn_siglip_d72", 2, 2, 2, 256, 256, 72, packed_qkv=True),
     attn_case("attn_beit_d64_relpos", 1, 2, 2, 577, 577, 64, packed_qkv=True, relpos_win=24),
@@ -459,8 +486,17 @@ ATTN_CASES = [
     attn_case("attn_tc_d256_prefix_lm_all", 1, 2, 2, 150, 150, 256, scale=1 / 16, softcap=50.0, causal=True, smax=150, seed=16, causal_prefix=150),
     attn_case("attn_mma_d128_prefix_lm", 2, 2, 2, 100, 100, 128, causal=True, smax=100, seed=17, causal_prefix=70),
     attn_case("attn_mma_d128_left_padded", 2, 2, 2, 100, 130, 128, smax=130, seed=13, kv_start=[9, 77]),
+    # sliding-window layers (even Gemma2 layers): key slot j masked for query slot i when i - j >= window
+    attn_case("attn_tc_d256_window_bidirectional", 2, 8, 4, 278, 278, 256, scale=1 / 16, softcap=50.0, smax=290, seed=51, window=48),
+    attn_case("attn_tc_d256_window_causal_gqa", 2, 8, 4, 200, 200, 256, scale=1 / 16, softcap=50.0, causal=True, smax=208, seed=52, window=70),
+    attn_case("attn_tc_d256_window_causal_offset_left_padded", 3, 2, 1, 150, 214, 256, scale=1 / 16, softcap=50.0, causal=True, smax=214, seed=53,
+              window=130, kv_start=[0, 5, 60]),
+    attn_case("attn_tc_d256_window_prefix_lm", 2, 2, 1, 200, 200, 256, scale=1 / 16, softcap=50.0, causal=True, smax=208, seed=54, causal_prefix=90,
+              window=64),
+    attn_case("attn_mma_d128_window", 2, 2, 2, 100, 130, 128, smax=130, seed=55, kv_start=[9, 77], window=40),
     decode_attn_case,
     decode_attn_fused_case,
+    decode_attn_fused_window_case,
 ]
 
 

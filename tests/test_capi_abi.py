@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert sorted(L.SIGNATURES) == names, "ctypes SIGNATURES and the header disagree"
-    assert lib.svla_abi_version() == 2
+    assert lib.svla_abi_version() == 3
     assert lib.svla_launch_count() >= 0
 
 
@@ -42,7 +42,8 @@ def test_gemm_args_struct_matches_header_layout():
     assert L.SvlaGemmTnArgs.groups.offset == 56 and C.sizeof(L.SvlaTnGroup) == 40 and L.SvlaAttnBwdArgs.lse.offset == 24 * 8
     assert L.SvlaAttnArgs.batch.offset == 12 * 8
     assert L.SvlaAttnArgs.kv_start.offset == 152 and L.SvlaAttnArgs.causal_prefix.offset == 160 and L.SvlaAttnArgs.lse.offset == 168
-    assert C.sizeof(L.SvlaAttnArgs) == 184 and L.SvlaAttnBwdArgs.fwd_lse2.offset == 26 * 8 + 10 * 4 and C.sizeof(L.SvlaAttnBwdArgs) == 26 * 8 + 40 + 16
+    assert L.SvlaAttnArgs.window.offset == 184          # sliding-window predicate appended (ABI v3)
+    assert C.sizeof(L.SvlaAttnArgs) == 192 and L.SvlaAttnBwdArgs.fwd_lse2.offset == 26 * 8 + 10 * 4 and C.sizeof(L.SvlaAttnBwdArgs) == 26 * 8 + 40 + 16
 
 
 def test_validation_errors_before_any_cuda_call(lib):

@@ -161,6 +161,33 @@ def test_left_padded_batch_vs_reference_golden(tiny_gpu, cuda_device):
         model.engine.force_head = None
 
 
+def test_sliding_window_layers_vs_reference_golden(cuda_device):
+    """Gemma2's sliding-window / global layer alternation on the GPU (window predicate of the tcgen05 prefill kernel and of the fused
+    decode kernel; even layer_idx windowed, model/modeling_gemma2.py:343,441-473): tiny config with sliding_window = 48 << 264 prompt
+    tokens against the golden the live reference produced (tests/golden/tiny_model_window.npz), eager launches and CUDA-graph replay,
+    every prefill position through forward()."""
+    from spatialvla_b200 import SpatialVLAForConditionalGeneration
+    g = np.load(os.path.join(GOLD, "tiny_model_window.npz"))
+    cfg, px_u8, ids, K = tiny_inputs()
+    cfg["text_config"]["sliding_window"] = int(g["window"])
+    sd = synth_state_dict(cfg, seed=0)
+    px = px_u8.float() / 255.0
+    model = SpatialVLAForConditionalGeneration(cfg, sd, device=cuda_device, action_chunk_size=2)
+    batch = {"input_ids": ids, "pixel_values": px, "intrinsic": K}
+    n_new = int(g["n_new"])
+    toks, logits = model.predict_action(batch, max_new_tokens=n_new, return_logits=True)
+    toks_g = model.predict_action(batch, max_new_tokens=n_new)
+    toks_g2 = model.predict_action(batch, max_new_tokens=n_new)
+    assert np.array_equal(toks.cpu().numpy(), g["tokens"])
+    assert np.abs(logits.cpu().numpy() - g["logits"]).max() < 6e-2
+    assert torch.equal(toks_g, toks) and torch.equal(toks_g2, toks)
+    base = np.load(os.path.join(GOLD, "tiny_model.npz"))
+    assert np.abs(logits.cpu().numpy() - base["logits"]).max() > 0.5          # the window is really applied
+    out = model.forward(input_ids=ids, pixel_values=px, intrinsic=K)
+    cols = torch.from_numpy(g["prefill_cols"]).to(cuda_device)
+    assert np.abs(out.logits[:, :, cols].cpu().numpy() - g["prefill_logits"]).max() < 8e-2
+
+
 def test_persistent_decode_kernel_matches_chain(tiny_gpu, cuda_device):
     """The single-launch persistent decode kernel (svla_decode_mega_step: TMA weight ring + tcgen05 swap-AB GEMMs + in-kernel grid
     barriers, opt-in SVLA_DECODE=mega) against the 7-kernels-per-layer chain of the default path (both are checked against the

@@ -74,6 +74,26 @@ def test_language_stage_batch1_equals_its_row_in_a_batch(tiny):
     assert float((torch.stack(logs1, 1)[0] - torch.stack(logs2, 1)[1]).abs().max()) < 1e-3
 
 
+def test_sliding_window_layers_vs_reference_golden():
+    """Gemma2's sliding-window / global layer alternation (even layer_idx windowed, model/modeling_gemma2.py:343,441-473) through
+    the engine's kernel sequence: tiny config with sliding_window = 48 << 264 prompt tokens, so the window predicate is active in
+    the prefill attention and in every fused decode step; golden minted from the live reference (tests/golden/tiny_model_window.npz)."""
+    g = np.load(os.path.join(GOLD, "tiny_model_window.npz"))
+    cfg, px_u8, ids, K = tiny_inputs()
+    cfg["text_config"]["sliding_window"] = int(g["window"])
+    sd = synth_state_dict(cfg, seed=0)
+    eng = SpatialVLAEngine(cfg, sd, RefOps())
+    px = px_u8.float() / 255.0
+    with torch.no_grad():
+        toks, logits = eng.generate_actions(ids, px, K, int(g["n_new"]), return_logits=True)
+    assert np.array_equal(toks.numpy(), g["tokens"])
+    assert np.abs(logits.numpy() - g["logits"]).max() < 6e-2
+    from spatialvla_b200.modeling_spatialvla import SpatialVLAForConditionalGeneration
+    m = SpatialVLAForConditionalGeneration(cfg, sd, ops=RefOps())
+    out = m.forward(input_ids=ids, pixel_values=px, intrinsic=K)                  # every prefill position
+    assert np.abs(out.logits[:, :, torch.from_numpy(g["prefill_cols"])].numpy() - g["prefill_logits"]).max() < 8e-2
+
+
 def test_forward_logits_api(tiny):
     from spatialvla_b200.modeling_spatialvla import SpatialVLAForConditionalGeneration
     cfg, px, ids, K, sd, eng = tiny

@@ -94,6 +94,41 @@ def test_model_restatement_left_padded_batch_matches_reference_golden():
         R.left_pads(torch.tensor([[1, 1, 0], [1, 1, 1]]))
 
 
+def test_model_restatement_sliding_window_matches_reference_golden():
+    """Gemma2 sliding-window layers (even layer_idx): tiny config with text_config.sliding_window = 48 << 264 prompt tokens, golden
+    minted by the live reference (oracle/gen_golden.py gen_model_window): greedy tokens + logits (window active in the prefill and in
+    every decode step), every prefill position's logits, and the left-padded batch."""
+    g = np.load(os.path.join(GOLD, "tiny_model_window.npz"))
+    gp = np.load(os.path.join(GOLD, "tiny_model_padded.npz"))
+    from oracle.gen_golden import tiny_inputs
+    cfg, px_u8, ids, K = tiny_inputs()
+    cfg["text_config"]["sliding_window"] = int(g["window"])
+    sd = synth_state_dict(cfg, seed=0)
+    px = px_u8.float() / 255.0
+    n_new = int(g["n_new"])
+    toks, logits = R.predict_action_ref(sd, cfg, ids, px, K, n_new)
+    assert np.array_equal(toks.numpy(), g["tokens"])
+    assert np.abs(logits.numpy() - g["logits"]).max() < 2e-5
+    base = np.load(os.path.join(GOLD, "tiny_model.npz"))
+    assert np.abs(g["logits"] - base["logits"]).max() > 0.5          # the window really changes the result
+    with torch.no_grad():
+        x = R.embed_inputs(sd, cfg, ids, R.image_features(sd, cfg, px, K, None))
+        h = R.gemma2_forward(sd, cfg, x, 0, [None] * cfg["text_config"]["num_hidden_layers"], bidirectional=True)
+        cols = torch.from_numpy(g["prefill_cols"])
+        lg = torch.tanh(torch.nn.functional.linear(h, sd["language_model.lm_head.weight"][cols]) / 30.0) * 30.0
+    assert np.abs(lg.numpy() - g["prefill_logits"]).max() < 2e-5
+    idsp, amp = torch.from_numpy(gp["input_ids"]), torch.from_numpy(gp["attention_mask"])
+    pxp = torch.from_numpy(gp["pixel_u8"]).float() / 255.0
+    tp, lp = R.predict_action_ref(sd, cfg, idsp, pxp, torch.from_numpy(gp["intrinsic"]), n_new, attention_mask=amp)
+    # left-padded rows: the prefill position is pinned.  The reference's DECODE steps of padded rows are not comparable under this
+    # harness: transformers 5.5's sliding cache layer hands the attention only the last `window` keys while the padding mask still
+    # has one column per slot and is sliced from the FRONT (`attention_mask[..., :key_len]`), so the pad columns land on the wrong
+    # keys; with the padding slots hundreds of slots behind the window the intended result is the plain window, which row 0 pins.
+    assert np.array_equal(tp.numpy()[:, 0], g["tokens_padded"][:, 0])
+    assert np.abs(lp.numpy()[:, 0] - g["logits_padded"][:, 0]).max() < 2e-5
+    assert np.abs(lp.numpy()[0] - g["logits_padded"][0]).max() < 2e-5
+
+
 def _train_golden():
     g = np.load(os.path.join(GOLD, "tiny_model_train.npz"))
     from spatialvla_b200.configs import get_config_dict

@@ -89,7 +89,9 @@ int svla_gemm(const SvlaGemmArgs* args, void* stream);
  * 8 = X_HILO (m <= 64): x holds TWO bf16 planes [2][M, ldx] -- hi = bf16(v) and lo = bf16(v - hi), 16 mantissa bits together --
  * and the result is hi.W^T + lo.W^T accumulated in fp32: the weights are streamed once, the activation tile is twice as wide
  * (the decode rows' own bf16 rounding before each of the 4 x 26 Linear layers is what dominates the bf16-vs-fp32 logit noise of
- * this path, tools/parity_report.py); 16 = OUT_HILO: out_bf16 is written as two such planes [2][M, ldo] (GEGLU or plain).
+ * this path, tools/parity_report.py); 16 = OUT_HILO: out_bf16 is written as two such planes [2][M, ldo] (GEGLU or plain);
+ * 32 = PAIR: CTA pairs (tcgen05 cta_group::2, 256 weight rows per MMA, half an activation tile staged per CTA) for the 64 / 128
+ * column tiles -- same results, measured slower on the decode chain, opt-in.
  * model/modeling_gemma2.py:80-92,351-354,993 */
 typedef struct SvlaSkinnyArgs {
   const void* x;          /* bf16 [M, ldx] */

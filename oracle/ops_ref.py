@@ -231,7 +231,7 @@ class RefOps:
         return max(1, min(148 // max(1, (n + 127) // 128), max(1, ((k + 63) // 64) // 4)))
 
     def gemm_skinny(self, x, w, *, out_bf16=None, out_f32=None, bias=None, act=ACT_NONE, act_param=0.0, alpha=1.0,
-                    geglu=False, splits=1, tiled_n=None):
+                    geglu=False, splits=1, tiled_n=None, pair=False):
         self.launches += 1
         if x.dim() == 3:                    # hi/lo activation pair [2, M, K]: hi @ w.T + lo @ w.T in fp32
             x = x[0].float() + x[1].float()

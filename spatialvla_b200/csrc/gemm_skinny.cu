@@ -20,10 +20,15 @@ using namespace svla_ptx;
 constexpr int kWM = 128;       // weight rows per CTA (UMMA M)
 constexpr int kBK = 64;
 constexpr int kThreads = 192;
+constexpr int kDefaultCG = 1;  // CTAs per MMA unless SVLA_SKINNY_CG says otherwise
 
-template <int NB> struct SCfg {
+// CG = CTAs per MMA: 2 = a CTA pair (cluster of two consecutive weight-row tiles of the same K split) issues ONE
+// tcgen05.mma.cta_group::2 of 256 weight rows per K step; each CTA stages its own 128 weight rows but only HALF of the activation
+// tile (with hi/lo planes: rank 0 the hi plane, rank 1 the lo plane), so the L2 -> shared-memory traffic of the activations,
+// which equals the weight traffic once the tile is 128 rows wide, is halved.
+template <int NB, int CG = 1> struct SCfg {
   static constexpr int kWBytes = kWM * kBK * 2;
-  static constexpr int kXBytes = NB * kBK * 2;
+  static constexpr int kXBytes = (NB / CG) * kBK * 2;
   static constexpr int kStageBytes = kWBytes + kXBytes;
   static constexpr int kMaxStages = 8;
   static constexpr int kTmemCols = NB < 32 ? 32 : NB;
@@ -48,16 +53,17 @@ struct SkinnyParams {
   float alpha, act_param;
   int act, flags;
   int n_tiles, kb_per_split, num_k_blocks;
+  int n_tiles_grid; // n_tiles rounded up to the cluster size (a surplus CTA computes an all-zero tile and stores nothing)
   int stages;      // pipeline depth (<= SCfg::kMaxStages)
   int x_lo_row;    // > 0 (X_HILO): X holds two bf16 planes, rows [0, m) = hi, rows [m, 2m) = lo = bf16(x - hi); each plane is
                    // loaded into one half of the NB-row activation tile and the epilogue adds the two accumulator halves
   int w_tiled;     // W is stored tile-major [n_tile][k_block][128 rows][64 cols]: every 16 KB stage is one contiguous read
 };
 
-template <int NB>
+template <int NB, int CG>
 __global__ void __launch_bounds__(kThreads, 2)
 svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x, const SkinnyParams p) {
-  using C = SCfg<NB>;
+  using C = SCfg<NB, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -71,7 +77,10 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x % p.n_tiles, split = blockIdx.x / p.n_tiles;
+  // grid = n_tiles_grid x splits, n_tiles_grid = n_tiles rounded up to a multiple of CG: the CTAs of a pair share the K split
+  const int n_tile = blockIdx.x % p.n_tiles_grid, split = blockIdx.x / p.n_tiles_grid;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   const int kb0 = split * p.kb_per_split;
   const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
 
@@ -83,9 +92,9 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
     mbar_init(acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<C::kTmemCols, 1>(tmem_ptr_smem);
+  if (warp == 1) tmem_alloc<C::kTmemCols, CG>(tmem_ptr_smem);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();      // the pair's barriers exist before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -95,18 +104,31 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
       // every CTA walks its K range from a different starting block (rotation by n_tile) so that the CTAs do not all ask
       // for the same activation tile at the same time
       const int nkb = kb1 - kb0;
-      const int rot = nkb > 0 ? (n_tile * 5) % nkb : 0;
+      const int rot = nkb > 0 ? ((n_tile / CG) * 5) % nkb : 0;          // the same order in both CTAs of a pair
       auto load_w = [&](int it, int stage) {
         const int kb = kb0 + (it + rot) % nkb;
-        mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-        if (p.w_tiled) tma_load_2d(smem_w + stage * C::kWBytes, &tm_w, &full_bar[stage], 0, (n_tile * p.num_k_blocks + kb) * kWM);
-        else tma_load_2d(smem_w + stage * C::kWBytes, &tm_w, &full_bar[stage], kb * kBK, n_tile * kWM);
+        if constexpr (CG == 1) {
+          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          if (p.w_tiled) tma_load_2d(smem_w + stage * C::kWBytes, &tm_w, &full_bar[stage], 0, (n_tile * p.num_k_blocks + kb) * kWM);
+          else tma_load_2d(smem_w + stage * C::kWBytes, &tm_w, &full_bar[stage], kb * kBK, n_tile * kWM);
+        } else {
+          // the leader arms its barrier for the bytes of BOTH CTAs; the peer's TMA signals the leader's barrier
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+          if (p.w_tiled) tma_load_2d_cg2(smem_w + stage * C::kWBytes, &tm_w, &full_bar[stage], 0, (n_tile * p.num_k_blocks + kb) * kWM);
+          else tma_load_2d_cg2(smem_w + stage * C::kWBytes, &tm_w, &full_bar[stage], kb * kBK, n_tile * kWM);
+        }
       };
       auto load_x = [&](int it, int stage) {
         const int kb = kb0 + (it + rot) % nkb;
-        tma_load_2d(smem_x + stage * C::kXBytes, &tm_x, &full_bar[stage], kb * kBK, 0);
-        if (p.x_lo_row > 0)        // hi/lo planes: two boxes of NB/2 rows (rows past 2m are zero-filled by the TMA unit)
-          tma_load_2d(smem_x + stage * C::kXBytes + C::kXBytes / 2, &tm_x, &full_bar[stage], kb * kBK, p.x_lo_row);
+        if constexpr (CG == 1) {
+          tma_load_2d(smem_x + stage * C::kXBytes, &tm_x, &full_bar[stage], kb * kBK, 0);
+          if (p.x_lo_row > 0)        // hi/lo planes: two boxes of NB/2 rows (rows past 2m are zero-filled by the TMA unit)
+            tma_load_2d(smem_x + stage * C::kXBytes + C::kXBytes / 2, &tm_x, &full_bar[stage], kb * kBK, p.x_lo_row);
+        } else {
+          // this CTA's half of the activation tile: rows [rank * NB/2, ...) -- with hi/lo planes rank 0 takes hi, rank 1 lo
+          const int row0 = p.x_lo_row > 0 ? static_cast<int>(cta_rank) * p.x_lo_row : static_cast<int>(cta_rank) * (NB / 2);
+          tma_load_2d_cg2(smem_x + stage * C::kXBytes, &tm_x, &full_bar[stage], kb * kBK, row0);
+        }
       };
       // PDL: the weights are immutable, so the first kStages weight tiles are requested BEFORE waiting for the kernel that
       // produces the activations; their HBM latency (and this kernel's launch + prologue) hides behind that kernel
@@ -124,8 +146,8 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
       }
     }
   } else if (warp == 1) {
-    {                                      // converged warp, an elected lane issues (tc_ptx.cuh: elect_one)
-      constexpr uint32_t idesc = make_idesc_bf16(kWM, NB < 16 ? 16 : NB);
+    if (leader) {                          // converged warp, an elected lane issues (tc_ptx.cuh: elect_one); CG == 2: the leader only
+      constexpr uint32_t idesc = make_idesc_bf16(kWM * CG, NB < 16 ? 16 : NB);
       const uint64_t dw0 = make_kmajor_sw128_desc(smem_u32(smem_w)), dx0 = make_kmajor_sw128_desc(smem_u32(smem_x));
       int stage = 0;
       uint32_t phase = 0;
@@ -136,17 +158,24 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
           const uint64_t dw = dw0 + static_cast<uint64_t>((stage * C::kWBytes) >> 4);
           const uint64_t dx = dx0 + static_cast<uint64_t>((stage * C::kXBytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)
-            umma_bf16(tmem_base, dw + static_cast<uint64_t>(k * 2), dx + static_cast<uint64_t>(k * 2), idesc,
-                      static_cast<uint32_t>((kb > kb0) || k != 0));
-          umma_commit(&empty_bar[stage]);
-          if (kb == kb1 - 1) umma_commit(acc_bar);
+          for (int k = 0; k < kBK / 16; ++k) {
+            if constexpr (CG == 1)
+              umma_bf16(tmem_base, dw + static_cast<uint64_t>(k * 2), dx + static_cast<uint64_t>(k * 2), idesc,
+                        static_cast<uint32_t>((kb > kb0) || k != 0));
+            else
+              umma_bf16_cg2(tmem_base, dw + static_cast<uint64_t>(k * 2), dx + static_cast<uint64_t>(k * 2), idesc,
+                            static_cast<uint32_t>((kb > kb0) || k != 0));
+          }
+          if constexpr (CG == 1) umma_commit(&empty_bar[stage]); else umma_commit_cg2(&empty_bar[stage]);   // frees the stage in both CTAs
+          if (kb == kb1 - 1) {
+            if constexpr (CG == 1) umma_commit(acc_bar); else umma_commit_cg2(acc_bar);
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
       if (kb1 <= kb0) {                    // empty K range (cannot happen with the host's split choice): release the epilogue
-        if (elect_one()) umma_commit(acc_bar);
+        if (elect_one()) { if constexpr (CG == 1) umma_commit(acc_bar); else umma_commit_cg2(acc_bar); }
         __syncwarp();
       }
     }
@@ -228,10 +257,10 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<C::kTmemCols, 1>(tmem_base);
+    tmem_dealloc<C::kTmemCols, CG>(tmem_base);
   }
 }
 
@@ -261,9 +290,9 @@ int encode_kmajor(CUtensorMap* tm, const void* base, uint64_t k, uint64_t rows, 
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 100;
 }
 
-template <int NB>
+template <int NB, int CG>
 int launch_skinny(const CUtensorMap& tw, const CUtensorMap& tx, SkinnyParams p, int ctas, cudaStream_t st) {
-  using C = SCfg<NB>;
+  using C = SCfg<NB, CG>;
   static bool configured = false;
   // never more stages than K steps per CTA: the o-projection (4 K steps per split) then needs 97 KB instead of 193 KB and a
   // CTA of it fits beside a running attention CTA, so its whole weight slice is requested before griddepcontrol.wait
@@ -273,7 +302,7 @@ int launch_skinny(const CUtensorMap& tw, const CUtensorMap& tx, SkinnyParams p, 
   if (qkv_stages >= 2 && qkv_stages <= 8 && p.kb_per_split == 9 && p.stages > qkv_stages) p.stages = qkv_stages;
   const int smem_bytes = C::smem_bytes(p.stages);
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(svla_gemm_skinny_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(svla_gemm_skinny_kernel<NB, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::smem_bytes(skinny_stages(C::kStageBytes)));
     if (e != cudaSuccess) {
       svla_set_error("svla_gemm_skinny: smem opt-in failed: %s", cudaGetErrorString(e));
@@ -281,7 +310,8 @@ int launch_skinny(const CUtensorMap& tw, const CUtensorMap& tx, SkinnyParams p, 
     }
     configured = true;
   }
-  cudaError_t le = svla_launch_pdl(svla_gemm_skinny_kernel<NB>, dim3(ctas), dim3(kThreads), smem_bytes, st, tw, tx, p);
+  cudaError_t le = CG == 1 ? svla_launch_pdl(svla_gemm_skinny_kernel<NB, CG>, dim3(ctas), dim3(kThreads), smem_bytes, st, tw, tx, p)
+                           : svla_launch_pdl_cluster(svla_gemm_skinny_kernel<NB, CG>, dim3(ctas), dim3(kThreads), smem_bytes, st, CG, tw, tx, p);
   if (le != cudaSuccess) {
     svla_set_error("svla_gemm_skinny: launch failed: %s", cudaGetErrorString(le));
     return -2;
@@ -332,11 +362,19 @@ extern "C" int svla_gemm_skinny(const SvlaSkinnyArgs* g, void* stream) {
   int rc = w_tiled ? encode_kmajor(&tw, g->w, kBK, static_cast<uint64_t>(p.n_tiles) * p.num_k_blocks * kWM, kBK, kWM)
                    : encode_kmajor(&tw, g->w, static_cast<uint64_t>(g->k), static_cast<uint64_t>(g->n), static_cast<uint64_t>(g->ldw), kWM);
   SVLA_REQUIRE(rc == 0, "svla_gemm_skinny: cuTensorMapEncodeTiled(W) failed (%d)", rc);
+  // CTA pairs (cta_group::2, flag 32 or SVLA_SKINNY_CG=2) stage half an activation tile each.  Built to halve the L2 -> shared
+  // memory traffic of the hi/lo activation tile and MEASURED on B200 (batch-64 decode step, tools/decode_step_perf.py): correct
+  // (all skinny cases green with pairs) but not faster -- hi/lo chain 2097 us with pairs vs 2072 us without, plain chain 2556
+  // vs 1990 us: co-scheduling two CTAs per cluster costs the PDL chain more than the activation traffic saves.  Opt-in only.
+  static const int cg_env = getenv("SVLA_SKINNY_CG") ? atoi(getenv("SVLA_SKINNY_CG")) : kDefaultCG;
+  const bool pair = (cg_env == 2 || (g->flags & 32) != 0) && nb >= 64 && p.n_tiles >= 2;
   rc = encode_kmajor(&tx, g->x, static_cast<uint64_t>(g->k), static_cast<uint64_t>(x_hilo ? 2 * g->m : g->m), static_cast<uint64_t>(g->ldx),
-                     static_cast<uint32_t>(x_hilo ? nb / 2 : nb));
+                     static_cast<uint32_t>((x_hilo || pair) ? nb / 2 : nb));
   SVLA_REQUIRE(rc == 0, "svla_gemm_skinny: cuTensorMapEncodeTiled(X) failed (%d)", rc);
-  const int ctas = p.n_tiles * splits;
-  if (nb == 16) return launch_skinny<16>(tw, tx, p, ctas, st);
-  if (nb == 64) return launch_skinny<64>(tw, tx, p, ctas, st);
-  return launch_skinny<128>(tw, tx, p, ctas, st);
+  const int cg = pair ? 2 : 1;
+  p.n_tiles_grid = (p.n_tiles + cg - 1) / cg * cg;
+  const int ctas = p.n_tiles_grid * splits;
+  if (nb == 16) return launch_skinny<16, 1>(tw, tx, p, ctas, st);
+  if (nb == 64) return cg == 2 ? launch_skinny<64, 2>(tw, tx, p, ctas, st) : launch_skinny<64, 1>(tw, tx, p, ctas, st);
+  return cg == 2 ? launch_skinny<128, 2>(tw, tx, p, ctas, st) : launch_skinny<128, 1>(tw, tx, p, ctas, st);
 }

@@ -214,7 +214,7 @@ class CudaOps:
         return int(self.lib.svla_gemm_skinny_splits(int(n), int(k)))
 
     def gemm_skinny(self, x, w, *, out_bf16=None, out_f32=None, bias=None, act=ACT_NONE, act_param=0.0, alpha=1.0,
-                    geglu=False, splits=1, tiled_n=None):
+                    geglu=False, splits=1, tiled_n=None, pair=False):
         """Decode GEMM (M <= 128). splits > 1 (or out_f32 with 3 dims) writes raw fp32 partial sums out_f32[s, M, N].
         tiled_n: w is the tile-major copy made by `tile_weight` of a [tiled_n, K] matrix.
         x of shape [2, M, K] (contiguous) is a hi/lo activation pair (X_HILO, M <= 64): the result is hi @ w.T + lo @ w.T;
@@ -241,7 +241,7 @@ class CudaOps:
         g.ldo = int(o.stride(-2))
         g.partial_stride = int(out_f32.stride(0)) if partial else 0
         g.alpha, g.act_param, g.act = float(alpha), float(act_param), int(act)
-        g.flags = (1 if geglu else 0) | (2 if partial else 0) | (4 if tiled_n is not None else 0) | (8 if x_hilo else 0) | (16 if out_hilo else 0)
+        g.flags = (1 if geglu else 0) | (2 if partial else 0) | (4 if tiled_n is not None else 0) | (8 if x_hilo else 0) | (16 if out_hilo else 0) | (32 if pair else 0)
         g.splits = int(out_f32.shape[0]) if partial else 1
         L.check(self.lib.svla_gemm_skinny(C.byref(g), self._stream()), "svla_gemm_skinny")
 

@@ -177,7 +177,8 @@ SIMT_CASES = [
 ]
 
 
-def skinny_case(name, M, N, K, *, mode="partial", splits=0, bias=False, act=ACT_NONE, act_param=0.0, ldx=None, seed=0, tiled=False):
+def skinny_case(name, M, N, K, *, mode="partial", splits=0, bias=False, act=ACT_NONE, act_param=0.0, ldx=None, seed=0, tiled=False,
+                pair=False):
     def case(dev="cuda:0"):
         from spatialvla_b200.ops import tile_weight
         g = _gen(seed)
@@ -192,14 +193,14 @@ def skinny_case(name, M, N, K, *, mode="partial", splits=0, bias=False, act=ACT_
             if mode == "partial":
                 S = splits or ops.skinny_splits(N, K) if ops.name == "cuda" else (splits or 1)
                 out = ops.zeros((S, M, N), F32)
-                ops.gemm_skinny(X, W, out_f32=out, tiled_n=tn)
+                ops.gemm_skinny(X, W, out_f32=out, tiled_n=tn, pair=pair)
                 return (out.sum(0),)
             if mode == "geglu":
                 out = ops.zeros((M, N // 2), BF16)
-                ops.gemm_skinny(X, W, out_bf16=out, geglu=True, bias=to(b), tiled_n=tn)
+                ops.gemm_skinny(X, W, out_bf16=out, geglu=True, bias=to(b), tiled_n=tn, pair=pair)
                 return (out,)
             of, ob = ops.zeros((M, N), F32), ops.zeros((M, N), BF16)
-            ops.gemm_skinny(X, W, out_f32=of, out_bf16=ob, bias=to(b), act=act, act_param=act_param, tiled_n=tn)
+            ops.gemm_skinny(X, W, out_f32=of, out_bf16=ob, bias=to(b), act=act, act_param=act_param, tiled_n=tn, pair=pair)
             return of, ob
         c, r = _both(run, dev)
         res = Result(name)
@@ -242,7 +243,7 @@ def _hilo_sum(t):
     return t[0].float() + t[1].float()
 
 
-def skinny_hilo_case(name, M, N, K, *, mode="partial", act=ACT_NONE, act_param=0.0, seed=0, tiled=False):
+def skinny_hilo_case(name, M, N, K, *, mode="partial", act=ACT_NONE, act_param=0.0, seed=0, tiled=False, pair=False):
     """X_HILO / OUT_HILO modes of svla_gemm_skinny: hi/lo activation pairs in, fp32 partial sums / fp32 / hi/lo pairs out.
     Checked (1) against the re-statement on the same pair and (2) against the fp64 product of the UNSPLIT fp32 activations,
     where the pair must be far inside what one bf16 plane can give (2^-9 per element)."""
@@ -260,14 +261,14 @@ def skinny_hilo_case(name, M, N, K, *, mode="partial", act=ACT_NONE, act_param=0
             if mode == "partial":
                 S = ops.skinny_splits(N, K) if ops.name == "cuda" else 1
                 out = ops.zeros((S, M, N), F32)
-                ops.gemm_skinny(X, W, out_f32=out, tiled_n=tn)
+                ops.gemm_skinny(X, W, out_f32=out, tiled_n=tn, pair=pair)
                 return (out.sum(0),)
             if mode == "geglu":
                 out = ops.zeros((2, M, N // 2), BF16)
-                ops.gemm_skinny(X, W, out_bf16=out, geglu=True, tiled_n=tn)
+                ops.gemm_skinny(X, W, out_bf16=out, geglu=True, tiled_n=tn, pair=pair)
                 return (_hilo_sum(out), out[0].float())
             of, ob = ops.zeros((M, N), F32), ops.zeros((2, M, N), BF16)
-            ops.gemm_skinny(X, W, out_f32=of, out_bf16=ob, act=act, act_param=act_param, tiled_n=tn)
+            ops.gemm_skinny(X, W, out_f32=of, out_bf16=ob, act=act, act_param=act_param, tiled_n=tn, pair=pair)
             return of, _hilo_sum(ob), ob[0].float()
         c, r = _both(run, dev)
         res = Result(name)
@@ -320,6 +321,10 @@ SKINNY_CASES = [
     skinny_hilo_case("skinny_hilo_head_softcap_m64", 64, 8194, 2304, mode="plain", act=ACT_SOFTCAP, act_param=30.0, seed=45),
     skinny_hilo_case("skinny_hilo_head_m17_ragged", 17, 300, 200, mode="plain", seed=46),
     skinny_hilo_case("skinny_hilo_m32_partial", 32, 512, 1024, seed=47),
+    # CTA pairs (cta_group::2; opt-in, measured slower on the decode chain): same results, odd tile count = one surplus CTA
+    skinny_hilo_case("skinny_hilo_pair_qkv_partial", 64, 4096, 2304, seed=48, pair=True),
+    skinny_hilo_case("skinny_hilo_pair_geglu_m20", 20, 18432, 2304, mode="geglu", seed=49, pair=True),
+    skinny_hilo_case("skinny_hilo_pair_head_odd_tiles", 64, 8194, 2304, mode="plain", act=ACT_SOFTCAP, act_param=30.0, seed=50, pair=True, tiled=True),
     decode_hilo_consumers_case,
     skinny_case("skinny_qkv_partial", 64, 4096, 2304),
     skinny_case("skinny_o_partial_split8", 64, 2304, 2048, splits=8),
@@ -334,6 +339,9 @@ SKINNY_CASES = [
     skinny_case("skinny_tiled_geglu", 64, 18432, 2304, mode="geglu", tiled=True, seed=32),
     skinny_case("skinny_tiled_head_ragged", 64, 8194, 2304, mode="plain", act=ACT_SOFTCAP, act_param=30.0, tiled=True, seed=33),
     skinny_case("skinny_tiled_ragged_k", 5, 300, 200, mode="plain", bias=True, tiled=True, seed=34),
+    skinny_case("skinny_pair_down_partial", 64, 2304, 9216, pair=True, seed=35),
+    skinny_case("skinny_pair_m100_ragged", 100, 384 + 128, 192, mode="plain", act=ACT_RELU, bias=True, pair=True, seed=36),
+    skinny_case("skinny_pair_m20_geglu_odd_tiles", 20, 128 * 5, 256, mode="geglu", pair=True, seed=37),
     skinny_consumers_case,
 ]
 

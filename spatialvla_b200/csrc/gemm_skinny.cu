@@ -203,10 +203,15 @@ svla_gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_c
       uint32_t r[32];
       tmem_ld32(taddr + c0, r);
       if (hilo_in) {                                // x.W = hi.W + lo.W: the lo plane's accumulators sit NB/2 columns further
-        uint32_t r2[32];
-        tmem_ld32(taddr + NB / 2 + c0, r2);
+        if constexpr (NB == 16) {                   // m <= 8: both planes are inside the one 32-column load
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r[j + 8]));
+        } else {
+          uint32_t r2[32];
+          tmem_ld32(taddr + NB / 2 + c0, r2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        }
       }
       const int rows = static_cast<int>(p.m) - c0;  // rows of this chunk that exist (>= 1)
       if (partial) {
@@ -354,8 +359,8 @@ extern "C" int svla_gemm_skinny(const SvlaSkinnyArgs* g, void* stream) {
   p.num_k_blocks = static_cast<int>((g->k + kBK - 1) / kBK);
   p.kb_per_split = (p.num_k_blocks + splits - 1) / splits;
   SVLA_REQUIRE(static_cast<long long>(p.kb_per_split) * (splits - 1) < p.num_k_blocks, "svla_gemm_skinny: too many splits (%d) for k=%lld", splits, (long long)g->k);
-  // X_HILO: the two planes of m <= 32 (64) rows fill the halves of a 64 (128) column tile
-  const int nb = x_hilo ? (g->m <= 32 ? 64 : 128) : (g->m <= 16 ? 16 : (g->m <= 64 ? 64 : 128));
+  // X_HILO: the two planes of m <= 8 (32, 64) rows fill the halves of a 16 (64, 128) column tile
+  const int nb = x_hilo ? (g->m <= 8 ? 16 : (g->m <= 32 ? 64 : 128)) : (g->m <= 16 ? 16 : (g->m <= 64 ? 64 : 128));
   p.x_lo_row = x_hilo ? static_cast<int>(g->m) : 0;
   CUtensorMap tw, tx;
   p.w_tiled = w_tiled ? 1 : 0;

@@ -321,6 +321,10 @@ SKINNY_CASES = [
     skinny_hilo_case("skinny_hilo_head_softcap_m64", 64, 8194, 2304, mode="plain", act=ACT_SOFTCAP, act_param=30.0, seed=45),
     skinny_hilo_case("skinny_hilo_head_m17_ragged", 17, 300, 200, mode="plain", seed=46),
     skinny_hilo_case("skinny_hilo_m32_partial", 32, 512, 1024, seed=47),
+    skinny_hilo_case("skinny_hilo_m8_partial", 8, 2304, 2048, seed=56),
+    skinny_hilo_case("skinny_hilo_m5_geglu", 5, 18432, 2304, mode="geglu", seed=57),
+    skinny_hilo_case("skinny_hilo_m1_head_softcap", 1, 8194, 2304, mode="plain", act=ACT_SOFTCAP, act_param=30.0, seed=58),
+    skinny_hilo_case("skinny_hilo_m9_partial", 9, 512, 1024, seed=59),
     # CTA pairs (cta_group::2; opt-in, measured slower on the decode chain): same results, odd tile count = one surplus CTA
     skinny_hilo_case("skinny_hilo_pair_qkv_partial", 64, 4096, 2304, seed=48, pair=True),
     skinny_hilo_case("skinny_hilo_pair_geglu_m20", 20, 18432, 2304, mode="geglu", seed=49, pair=True),

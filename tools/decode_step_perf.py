@@ -21,7 +21,7 @@ ops = CudaOps(dev)
 eng = SpatialVLAEngine(cfg, sd, ops)
 del sd
 torch.cuda.empty_cache()
-B, P, H = 64, 278, cfg["text_config"]["hidden_size"]
+B, P, H = int(os.environ.get("B", "64")), 278, cfg["text_config"]["hidden_size"]
 g = torch.Generator().manual_seed(0)
 ids = torch.randint(3, 250000, (B, P), generator=g).to(dev)
 x, _ = eng.embed(ids)
@@ -59,7 +59,7 @@ t = cfg["text_config"]
 L_, nh, nkv, hd, FF = t["num_hidden_layers"], t["num_attention_heads"], t["num_key_value_heads"], t["head_dim"], t["intermediate_size"]
 w_bytes = L_ * 2 * (H * (nh + 2 * nkv) * hd + nh * hd * H + 3 * H * FF) + 8194 * H * 2
 kv_bytes = L_ * 2 * B * (P + 1) * nkv * hd * 2
-print({"name": "decode_step", "hilo": eng.decode_hilo, "stages_env": os.environ.get("SVLA_SKINNY_STAGES", ""), "pdl": os.environ.get("SVLA_PDL", "1"),
+print({"name": "decode_step", "batch": B, "hilo": eng.decode_hilo, "stages_env": os.environ.get("SVLA_SKINNY_STAGES", ""), "pdl": os.environ.get("SVLA_PDL", "1"),
        "launches": launches, "us_median": round(ms * 1e3, 1), "us_min": round(ts[0] * 1e3, 1),
        "weight_GB": round(w_bytes / 1e9, 3), "kv_GB": round(kv_bytes / 1e9, 3),
        "GBs": round((w_bytes + kv_bytes) / ms / 1e6, 1), "roofline_us_at_6555GBs": round((w_bytes + kv_bytes) / 6555.8e3, 1)}, flush=True)

@@ -73,9 +73,19 @@ svla_rmsnorm_residual_kernel(float* __restrict__ x, const float* __restrict__ br
                              int n_partials, long long partial_stride, __nv_bfloat16* __restrict__ out_lo) {
   __shared__ float sh[33];
   pdl_launch_dependents();          // the next kernel (a weight-streaming GEMM in the decode chain) may start its prefetch
-  pdl_wait();
   const long long row = blockIdx.x;
   const int nv = cols >> 2;
+  // The norm weights are immutable: they are requested BEFORE griddepcontrol.wait (their L2 round trips hide behind the tail of
+  // the producing GEMM) and all at once.  Loaded inside the output loops they were one dependent L2 round trip per float4 slice,
+  // and with the hi/lo output the compiler serialised the slices behind each other (6.0 -> 7.0 us per launch at 64 rows).
+  float4 wpost[kMaxVec], wpre[kMaxVec];
+#pragma unroll
+  for (int k = 0; k < kMaxVec; ++k) {
+    const int i = threadIdx.x + k * kRowThreads;
+    wpost[k] = (branch && i < nv) ? __ldg(reinterpret_cast<const float4*>(w_post) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    wpre[k] = (w_pre && i < nv) ? __ldg(reinterpret_cast<const float4*>(w_pre) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  pdl_wait();
   float4 xv[kMaxVec];
   load_row(x + row * cols, cols, xv);
   if (branch) {
@@ -107,7 +117,7 @@ svla_rmsnorm_residual_kernel(float* __restrict__ x, const float* __restrict__ br
     for (int k = 0; k < kMaxVec; ++k) {
       const int i = threadIdx.x + k * kRowThreads;
       if (i < nv) {
-        const float4 w = reinterpret_cast<const float4*>(w_post)[i];
+        const float4 w = wpost[k];
         xv[k].x += bv[k].x * r * (1.f + w.x);
         xv[k].y += bv[k].y * r * (1.f + w.y);
         xv[k].z += bv[k].z * r * (1.f + w.z);
@@ -125,7 +135,7 @@ svla_rmsnorm_residual_kernel(float* __restrict__ x, const float* __restrict__ br
     for (int k = 0; k < kMaxVec; ++k) {
       const int i = threadIdx.x + k * kRowThreads;
       if (i < nv) {
-        const float4 w = reinterpret_cast<const float4*>(w_pre)[i];
+        const float4 w = wpre[k];
         const float o0 = xv[k].x * r * (1.f + w.x), o1 = xv[k].y * r * (1.f + w.y);
         const float o2 = xv[k].z * r * (1.f + w.z), o3 = xv[k].w * r * (1.f + w.w);
         const uint2 hi = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));

@@ -303,7 +303,7 @@ int svla_fill_zero(void* ptr, int64_t bytes, void* stream);   /* cudaMemsetAsync
 
 /* Backward of G2 (flash formulation; see csrc/train_mma.cu).  q/k/v/out as in SvlaAttnArgs (out = the forward result), dout = dL/dout;
  * dq/dk/dv bf16 with their own strides (they may be column blocks of one [tokens, (hq + 2 hkv) d] tensor); lse / delta: fp32
- * [batch, hq, sq] scratch written by the first launch.  Masks: causal / causal_prefix as in SvlaAttnArgs (no kv_start, no relpos). */
+ * [batch, hq, sq] scratch written by the first launch.  Masks: causal / causal_prefix / window as in SvlaAttnArgs (no kv_start, no relpos). */
 typedef struct SvlaAttnBwdArgs {
   const void* q; const void* k; const void* v; const void* out; const void* dout;
   void* dq; void* dk; void* dv;
@@ -317,6 +317,7 @@ typedef struct SvlaAttnBwdArgs {
                                 must be fp32 [batch, hq, lse_stride] scratch (delta is written, lse unused); NULL = the warp-MMA kernels, which
                                 recompute the row statistics themselves */
   int64_t lse_stride;
+  int32_t window;            /* sliding-window predicate of the forward (SvlaAttnArgs.window); 0 = none */
 } SvlaAttnBwdArgs;
 int svla_attention_bwd(const SvlaAttnBwdArgs* args, void* stream);
 

@@ -200,7 +200,7 @@ class RefOps:
         t.zero_()
 
     def attention_bwd(self, q, k, v, out, dout, dq, dk, dv, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
-                      do_strides, dq_strides, dk_strides, dv_strides, scale, softcap=0.0, causal=False, causal_prefix=0, lse=None):
+                      do_strides, dq_strides, dk_strides, dv_strides, scale, softcap=0.0, causal=False, causal_prefix=0, lse=None, window=0):
         from .backward_ref import softcap_attention_bwd
         self.launches += 3
         Q = self._strided(q, q_strides[0], q_strides[1], batch, sq, hq, d).float().permute(0, 2, 1, 3)
@@ -212,6 +212,9 @@ class RefOps:
         mask = None
         if causal:
             mask = torch.arange(sk)[None, :] > torch.clamp(torch.arange(sq)[:, None] + (sk - sq), min=causal_prefix - 1)
+        if window:
+            wm = (torch.arange(sq)[:, None] + (sk - sq) - torch.arange(sk)[None, :]) >= window
+            mask = wm if mask is None else (mask | wm)
         gq, gk, gv = softcap_attention_bwd(Q, Kr, Vr, dO, scale, softcap, mask)
         gk = gk.view(batch, hkv, G, sk, d).sum(2)
         gv = gv.view(batch, hkv, G, sk, d).sum(2)

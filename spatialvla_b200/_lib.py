@@ -67,7 +67,7 @@ class SvlaAttnBwdArgs(C.Structure):
         ("lse", C.c_void_p), ("delta", C.c_void_p),
         ("batch", C.c_int32), ("hq", C.c_int32), ("hkv", C.c_int32), ("sq", C.c_int32), ("sk", C.c_int32), ("d", C.c_int32),
         ("scale", C.c_float), ("softcap", C.c_float), ("causal", C.c_int32), ("causal_prefix", C.c_int32),
-        ("fwd_lse2", C.c_void_p), ("lse_stride", C.c_int64),
+        ("fwd_lse2", C.c_void_p), ("lse_stride", C.c_int64), ("window", C.c_int32),
     ]
 
 

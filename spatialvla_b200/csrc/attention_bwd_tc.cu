@@ -43,6 +43,7 @@ struct Params {
   int hq, hkv, sq, sk, d;
   float scale, softcap;
   int causal, prefix;
+  int window;                       // > 0: key j masked for query i when i + (sk - sq) - j >= window (sliding-window layers)
 };
 
 template <int D, int KIND> struct Cfg {
@@ -328,9 +329,9 @@ svla_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_
       const int rlo = r0 + q * 32, rhi = rlo + 32;                  // rows of this warp
       bool plain;
       if (kRowsAreQueries) {
-        plain = rhi <= p.sq && c0 + HC <= p.sk && (!p.causal || (c0 + HC - 1) <= max(rlo + off, p.prefix - 1));
+        plain = p.window == 0 && rhi <= p.sq && c0 + HC <= p.sk && (!p.causal || (c0 + HC - 1) <= max(rlo + off, p.prefix - 1));
       } else {
-        plain = rhi <= p.sk && c0 + HC <= p.sq && (!p.causal || (rhi - 1) <= max(c0 + off, p.prefix - 1));
+        plain = p.window == 0 && rhi <= p.sk && c0 + HC <= p.sq && (!p.causal || (rhi - 1) <= max(c0 + off, p.prefix - 1));
       }
       uint32_t zk[HC / 2];
       // Two columns per FMUL2 / FFMA2 (the scalar loop with a per-element tanh branch and two shuffles per element made the 8
@@ -381,7 +382,8 @@ svla_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_
           for (int e = 0; e < 2; ++e) {
             const int ci = c0 + i + e;                              // streamed index
             const int qi = kRowsAreQueries ? ri : ci, kj = kRowsAreQueries ? ci : ri;
-            const bool masked = qi >= p.sq || kj >= p.sk || (p.causal && kj > max(qi + off, p.prefix - 1));
+            const bool masked = qi >= p.sq || kj >= p.sk || (p.causal && kj > max(qi + off, p.prefix - 1)) ||
+                                (p.window > 0 && qi + off - kj >= p.window);
             if (masked) { if (e == 0) pr0 = 0.f; else pr1 = 0.f; }
           }
         }
@@ -537,6 +539,7 @@ static int run_all(const SvlaAttnBwdArgs* a, cudaStream_t st) {
   p.lse2 = a->fwd_lse2; p.delta = a->delta; p.stat_stride = a->lse_stride;
   p.hq = a->hq; p.hkv = a->hkv; p.sq = a->sq; p.sk = a->sk; p.d = a->d;
   p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.prefix = a->causal ? a->causal_prefix : 0;
+  p.window = a->window;
   const long long total = static_cast<long long>(a->batch) * a->sq * a->hq;
   svla_attn_delta_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(a->out), static_cast<const __nv_bfloat16*>(a->dout), a->o_bs, a->o_ss, a->do_bs, a->do_ss, a->hq, a->sq, a->d,

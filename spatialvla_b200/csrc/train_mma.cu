@@ -151,6 +151,7 @@ struct AttnBwdP {
   int hq, hkv, sq, sk, d;
   float scale, softcap;
   int causal, prefix;
+  int window;             // > 0: key j masked for query i when i + (sk - sq) - j >= window
 };
 
 constexpr int kAbThreads = 128;      // 4 warps x 16 rows
@@ -176,7 +177,7 @@ __device__ __forceinline__ void ab_zero_pad(__nv_bfloat16* sm, int rows, int d) 
 
 // visible(i, j): key j visible to query i
 __device__ __forceinline__ bool ab_masked(const AttnBwdP& p, int i, int j) {
-  return j >= p.sk || (p.causal && j > max(i + (p.sk - p.sq), p.prefix - 1));
+  return j >= p.sk || (p.causal && j > max(i + (p.sk - p.sq), p.prefix - 1)) || (p.window > 0 && i + (p.sk - p.sq) - j >= p.window);
 }
 // tanh for soft-capping: |u| is small (scores / 50), an odd degree-9 polynomial is exact to fp32 rounding below 0.35 (the same
 // evaluation the forward kernels use, so the recomputed probabilities are consistent with the forward pass)
@@ -211,7 +212,7 @@ __device__ __forceinline__ void ab_score(const AttnBwdP& p, float raw, float& c,
 }
 // a (query tile, key tile) pair needs no per-element mask when every key is in range and visible to every query of the tile
 __device__ __forceinline__ bool ab_tile_unmasked(const AttnBwdP& p, int q_lo, int q_hi, int k_lo, int k_hi) {
-  if (k_hi > p.sk || q_hi > p.sq) return false;
+  if (k_hi > p.sk || q_hi > p.sq || p.window > 0) return false;
   if (!p.causal) return true;
   return (k_hi - 1) <= max(q_lo + (p.sk - p.sq), p.prefix - 1);
 }
@@ -643,7 +644,7 @@ extern "C" int svla_attention_bwd(const SvlaAttnBwdArgs* a, void* stream) {
   p.dq_bs = a->dq_bs; p.dq_ss = a->dq_ss; p.dk_bs = a->dk_bs; p.dk_ss = a->dk_ss; p.dv_bs = a->dv_bs; p.dv_ss = a->dv_ss;
   p.lse = a->lse; p.delta = a->delta;
   p.hq = a->hq; p.hkv = a->hkv; p.sq = a->sq; p.sk = a->sk; p.d = a->d;
-  p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.prefix = a->causal_prefix;
+  p.scale = a->scale; p.softcap = a->softcap; p.causal = a->causal; p.prefix = a->causal_prefix; p.window = a->window;
   const long long strides[] = {p.q_bs, p.q_ss, p.k_bs, p.k_ss, p.v_bs, p.v_ss, p.do_bs, p.do_ss, p.o_bs, p.o_ss, p.dq_bs, p.dq_ss,
                                p.dk_bs, p.dk_ss, p.dv_bs, p.dv_ss};
   for (long long s : strides) SVLA_REQUIRE(s % 8 == 0, "svla_attention_bwd: strides must be multiples of 8 elements (16-byte rows)");

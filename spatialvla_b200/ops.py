@@ -173,7 +173,7 @@ class CudaOps:
         L.check(self.lib.svla_fill_zero(_ptr(t), t.numel() * t.element_size(), self._stream()), "svla_fill_zero")
 
     def attention_bwd(self, q, k, v, out, dout, dq, dk, dv, *, batch, hq, hkv, sq, sk, d, q_strides, k_strides, v_strides, o_strides,
-                      do_strides, dq_strides, dk_strides, dv_strides, scale, softcap=0.0, causal=False, causal_prefix=0, lse=None):
+                      do_strides, dq_strides, dk_strides, dv_strides, scale, softcap=0.0, causal=False, causal_prefix=0, lse=None, window=0):
         """Backward of `attention` (no relpos / kv_start): strides = (batch stride, token stride) in elements, head h at column h*d.
         lse: the forward call's `lse` output -> the tcgen05 sweeps (dQ, dK, dV); None -> warp-MMA kernels that recompute it."""
         a = L.SvlaAttnBwdArgs()
@@ -191,6 +191,7 @@ class CudaOps:
             a.fwd_lse2, a.lse_stride = _ptr(lse), sp
         a.batch, a.hq, a.hkv, a.sq, a.sk, a.d = batch, hq, hkv, sq, sk, d
         a.scale, a.softcap, a.causal, a.causal_prefix = float(scale), float(softcap or 0.0), int(bool(causal)), int(causal_prefix)
+        a.window = int(window or 0)
         L.check(self.lib.svla_attention_bwd(C.byref(a), self._stream()), "svla_attention_bwd")
         return stats
 

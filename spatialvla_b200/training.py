@@ -138,9 +138,10 @@ class LoRATrainer:
         eps, theta = t["rms_norm_eps"], float(t.get("rope_theta", 10000.0))
         scale, cap = t["query_pre_attn_scalar"] ** -0.5, t["attn_logit_softcapping"] or 0.0
         M = B * S
-        win = t.get("sliding_window")
-        if win and S > win:
-            raise NotImplementedError(f"training sequence of {S} tokens exceeds the sliding window ({win})")
+        # sliding-window layers (even layer_idx, model/modeling_gemma2.py:343,441-473): the predicate is passed to the forward and
+        # backward attention kernels once the sequence exceeds the window (never at the 291 tokens of config #5 against 4096)
+        win = int(t.get("sliding_window") or 0)
+        win = win if S > win else 0
         nL = len(g["layers"])
         kc_all, vc_all = ops.empty((nL, B, S, nkv, hd), BF16), ops.empty((nL, B, S, nkv, hd), BF16)
         h1 = ops.empty((M, H), BF16)
@@ -156,7 +157,7 @@ class LoRATrainer:
             c["lse"] = ops.empty((B, nh, (S + 63) // 64 * 64), F32)
             ops.attention(c["q"], c["kc"], c["vc"], c["ctx"], batch=B, hq=nh, hkv=nkv, sq=S, sk=S, d=hd, q_strides=(S * nh * hd, nh * hd),
                           k_strides=kvs, v_strides=kvs, o_strides=(S * nh * hd, nh * hd), scale=scale, softcap=cap, causal=causal,
-                          causal_prefix=prefix if causal else 0, lse=c["lse"])
+                          causal_prefix=prefix if causal else 0, lse=c["lse"], window=win if li % 2 == 0 else 0)
             c["br"], c["u_o"] = self._lin_fwd(c["ctx"], L_["wo"], F_[f"gem.{li}.o"], M, out_dtype=F32)
             c["x_mid"], c["h2"] = ops.empty((M, H), F32), ops.empty((M, H), BF16)
             ops.rmsnorm_train_fwd(x, branch=c["br"], w_post=L_["ln_post_attn"], w_pre=L_["ln_pre_ff"], eps=eps, x_out=c["x_mid"], h=c["h2"])
@@ -182,6 +183,8 @@ class LoRATrainer:
         Wd = (nh + 2 * nkv) * hd
         kvs = (S * nkv * hd, nkv * hd)
         qs = (S * nh * hd, nh * hd)
+        win = int(t.get("sliding_window") or 0)
+        win = win if S > win else 0              # as in the forward: even layers are windowed once the sequence exceeds the window
         for li in reversed(range(len(g["layers"]))):
             L_, T_, c = g["layers"][li], self.gem_t[li], sv["layers"][li]
             H = dx.shape[1]
@@ -199,7 +202,8 @@ class LoRATrainer:
             ops.attention_bwd(c["q"], c["kc"], c["vc"], c["ctx"], dctx, dqkv, dqkv[:, nh * hd:], dqkv[:, (nh + nkv) * hd:], batch=B, hq=nh,
                               hkv=nkv, sq=S, sk=S, d=hd, q_strides=qs, k_strides=kvs, v_strides=kvs, o_strides=qs, do_strides=qs,
                               dq_strides=(S * Wd, Wd), dk_strides=(S * Wd, Wd), dv_strides=(S * Wd, Wd), scale=scale, softcap=cap,
-                              causal=causal, causal_prefix=prefix if causal else 0, lse=c["lse"])
+                              causal=causal, causal_prefix=prefix if causal else 0, lse=c["lse"],
+                              window=win if li % 2 == 0 else 0)
             ops.rope_bwd(dqkv, batch=B, s=S, hq=nh, hkv=nkv, d=hd, theta=theta)
             dh1 = self._lin_bwd(dqkv, T_["wqkv"], F_[f"gem.{li}.qkv"], c["h1"], c["u_qkv"], M)
             ops.rmsnorm_bwd(c["x_in"], L_["ln_in"], dh1, eps=eps, dx_accum=dx)

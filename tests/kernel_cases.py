@@ -1024,7 +1024,7 @@ def train_elementwise_case(dev="cuda:0"):
     return res
 
 
-def attn_bwd_case(name, B, hq, hkv, sq, sk, d, *, softcap=0.0, causal=False, prefix=0, seed=0, with_lse=True):
+def attn_bwd_case(name, B, hq, hkv, sq, sk, d, *, softcap=0.0, causal=False, prefix=0, seed=0, with_lse=True, window=0):
     """svla_attention_bwd (3 launches) vs the closed form oracle/backward_ref.softcap_attention_bwd (itself pinned on autograd);
     q/k/v packed like the step's tensors (q in its own tensor, k / v as rows of a [B, sk, hkv, d] cache, gradients as column blocks
     of one [tokens, (hq + 2 hkv) d] tensor)."""
@@ -1044,13 +1044,13 @@ def attn_bwd_case(name, B, hq, hkv, sq, sk, d, *, softcap=0.0, causal=False, pre
             lse = ops.zeros((B, hq, (sq + 63) // 64 * 64), F32) if with_lse else None
             ops.attention(Q, K, V, out, batch=B, hq=hq, hkv=hkv, sq=sq, sk=sk, d=d, q_strides=(sq * hq * d, hq * d), k_strides=kvs,
                           v_strides=kvs, o_strides=(sq * hq * d, hq * d), scale=scale, softcap=softcap, causal=causal, causal_prefix=prefix,
-                          lse=lse)
+                          lse=lse, window=window)
             assert sq == sk
             dqkv = ops.zeros((B * sq, W), BF16) + 5.0                       # poison: every element must be written
             ops.attention_bwd(Q, K, V, out, dO, dqkv, dqkv[:, hq * d:], dqkv[:, (hq + hkv) * d:], batch=B, hq=hq, hkv=hkv, sq=sq, sk=sk,
                               d=d, q_strides=(sq * hq * d, hq * d), k_strides=kvs, v_strides=kvs, o_strides=(sq * hq * d, hq * d),
                               do_strides=(sq * hq * d, hq * d), dq_strides=(sq * W, W), dk_strides=(sk * W, W), dv_strides=(sk * W, W),
-                              scale=scale, softcap=softcap, causal=causal, causal_prefix=prefix, lse=lse)
+                              scale=scale, softcap=softcap, causal=causal, causal_prefix=prefix, lse=lse, window=window)
             return dqkv if lse is None else (dqkv, lse)
         c, r = _both(run, dev)
         res = Result(name)
@@ -1071,6 +1071,11 @@ ATTN_BWD_CASES = [
     attn_bwd_case("attn_bwd_mma_siglip_d72", 2, 4, 4, 256, 256, 72, with_lse=False),
     attn_bwd_case("attn_bwd_mma_d64_causal_prefix", 2, 4, 1, 200, 200, 64, causal=True, prefix=50, softcap=20.0, with_lse=False),
     # tcgen05 sweeps (dQ / dK / dV) fed by the forward kernel's log-sum-exp
+    attn_bwd_case("attn_bwd_mma_gemma_window", 2, 4, 2, 200, 200, 256, softcap=50.0, causal=True, prefix=90, with_lse=False, window=64, seed=7),
+    # sliding-window layers in the tcgen05 sweeps
+    attn_bwd_case("attn_bwd_gemma_window_prefixlm", 2, 4, 2, 291, 291, 256, softcap=50.0, causal=True, prefix=278, window=100, seed=8),
+    attn_bwd_case("attn_bwd_gemma_window_causal", 1, 8, 4, 200, 200, 256, softcap=50.0, causal=True, window=48, seed=9),
+    attn_bwd_case("attn_bwd_gemma_window_bidirectional", 2, 2, 2, 150, 150, 256, softcap=50.0, window=70, seed=10),
     attn_bwd_case("attn_bwd_tiny_tile", 1, 1, 1, 40, 40, 64),
     attn_bwd_case("attn_bwd_two_tiles_d64", 1, 2, 2, 128, 128, 64),
     attn_bwd_case("attn_bwd_gqa4_d256", 1, 4, 1, 150, 150, 256, softcap=50.0, causal=True, prefix=30),

@@ -43,7 +43,7 @@ def test_gemm_args_struct_matches_header_layout():
     assert L.SvlaAttnArgs.batch.offset == 12 * 8
     assert L.SvlaAttnArgs.kv_start.offset == 152 and L.SvlaAttnArgs.causal_prefix.offset == 160 and L.SvlaAttnArgs.lse.offset == 168
     assert L.SvlaAttnArgs.window.offset == 184          # sliding-window predicate appended (ABI v3)
-    assert C.sizeof(L.SvlaAttnArgs) == 192 and L.SvlaAttnBwdArgs.fwd_lse2.offset == 26 * 8 + 10 * 4 and C.sizeof(L.SvlaAttnBwdArgs) == 26 * 8 + 40 + 16
+    assert C.sizeof(L.SvlaAttnArgs) == 192 and L.SvlaAttnBwdArgs.fwd_lse2.offset == 26 * 8 + 10 * 4 and C.sizeof(L.SvlaAttnBwdArgs) == 26 * 8 + 40 + 16 + 8 and L.SvlaAttnBwdArgs.window.offset == 26 * 8 + 40 + 16
 
 
 def test_validation_errors_before_any_cuda_call(lib):

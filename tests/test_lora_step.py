@@ -19,8 +19,10 @@ from spatialvla_b200.weights import synth_state_dict
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def _setup(ops, seed=0):
+def _setup(ops, seed=0, window=None):
     cfg, px_u8, ids, tt, labels, K = train_inputs()
+    if window:          # sliding-window layers active: window << the 270-token training sequence
+        cfg["text_config"]["sliding_window"] = window
     sd = synth_state_dict(cfg, seed=0)
     eng = SpatialVLAEngine(cfg, sd, ops)
     tr = LoRATrainer(eng, r=32, alpha=32.0, lr=1e-3, seed=seed)
@@ -58,11 +60,11 @@ def _check_grads(tr, ref, tol):
     return worst
 
 
-@pytest.mark.parametrize("mask", ["prefix_lm", "causal"])
+@pytest.mark.parametrize("mask", ["prefix_lm", "causal", "prefix_lm_window48"])
 def test_lora_step_host_logic_gradients_match_autograd_oracle(mask):
-    cfg, px, ids, tt, labels, K, sd, eng, tr = _setup(RefOps())
+    cfg, px, ids, tt, labels, K, sd, eng, tr = _setup(RefOps(), window=48 if mask.endswith("window48") else None)
     B, L = ids.shape
-    am = torch.ones(B, L, dtype=torch.int64) if mask == "prefix_lm" else None
+    am = torch.ones(B, L, dtype=torch.int64) if mask.startswith("prefix_lm") else None
     summary = tr.forward_backward(ids, px, K, labels, token_type_ids=tt, attention_mask=am)
     ref_loss, ref = _oracle_adapter_grads(tr, sd, cfg, ids, px, K, labels, tt, am, eng.last_router_head)
     assert abs(float(summary[0]) - ref_loss) < 2e-2, (float(summary[0]), ref_loss)
@@ -99,11 +101,11 @@ def test_lora_step_with_zero_B_equals_the_base_model_and_updates_only_B():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mask", ["prefix_lm", "causal"])
+@pytest.mark.parametrize("mask", ["prefix_lm", "causal", "causal_window48"])
 def test_lora_step_on_gpu_gradients_match_autograd_oracle(mask, cuda_device):
     from spatialvla_b200.ops import CudaOps
     ops = CudaOps(cuda_device)
-    cfg, px, ids, tt, labels, K, sd, eng, tr = _setup(ops)
+    cfg, px, ids, tt, labels, K, sd, eng, tr = _setup(ops, window=48 if mask.endswith("window48") else None)
     B, L = ids.shape
     am = torch.ones(B, L, dtype=torch.int64) if mask == "prefix_lm" else None
     n0 = ops.launch_count()

@@ -8,6 +8,11 @@
 // lane = weight row n, so for a fixed m the 32 lanes of a warp store 32 consecutive n -- fully coalesced without any
 // shared-memory transpose.  Split-K partial sums go to out_f32[split][m][n]; the consumers (svla_rmsnorm_residual,
 // svla_rope_kv) add the partials while they read them, deterministically.
+// hi/lo activation pairs (flags X_HILO / OUT_HILO): the decode chain hands its activations over as two bf16 planes, hi = bf16(v)
+// and lo = bf16(v - hi).  The planes are staged as the two halves of the activation tile, the MMA computes both products against
+// the SAME weight tile (streamed once) and the epilogue adds the accumulator halves: hi.W^T + lo.W^T in fp32.  Rounding the decode
+// row's own activations to 8 mantissa bits in front of every Linear was the bf16-vs-fp32 logit noise of the path (full-size parity
+// 98.9 % -> 99.8 % of 832 positions, profiles/decode_hilo_r2.txt); the wider tile costs 4-7 % of a decode step.
 // Reference ops replaced: the q/k/v/o/gate/up/down/lm_head nn.Linear calls of a decode step
 // (model/modeling_gemma2.py:80-92,351-354,993).
 #include <cstdlib>

@@ -338,6 +338,8 @@ def run_ours(args):
                    "global_batch": B * world, "prompt_len": 256 + 2 + P_TEXT, "new_tokens": N_NEW, "weights": "random-init synthetic",
                    "parallelism": f"replicas x{world} (batch sharded, no collective)",
                    "launch": "ONE CUDA graph per step (the ZoeDepth router vote is taken on the device)",
+                   "decode": ("hi/lo bf16 activation pairs on the decode chain, last prompt row re-evaluated as a decode step "
+                              f"({N_NEW + 1} chain passes)") if _decode_hilo() else f"plain bf16 chain ({N_NEW} passes)",
                    "l2": "256 MiB buffer rewritten between steps; per-step working set (8.1 GB weights) >> 126 MB L2"},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
@@ -653,6 +655,11 @@ def run_reference(args):
             "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def _decode_hilo():
+    from spatialvla_b200.engine import SpatialVLAEngine
+    return bool(SpatialVLAEngine.decode_hilo)
 
 
 def main():

@@ -812,7 +812,7 @@ class SpatialVLAEngine:
                 and t["num_attention_heads"] // t["num_key_value_heads"] in (1, 2) and not self.mega_decode)
         x_last = x.view(B, P, H)[:, P - 1].clone() if redo else None     # embedding of the last prompt token, COPIED: x is updated in place
         h = self.gemma_forward(x, B, P, cache, bidirectional=True, pads=pads)
-        toks = ops.zeros((B, n_new), torch.int64)
+        toks_t = ops.zeros((n_new, B), torch.int64)          # step-major: the ids of one step are one contiguous row (no gather copy)
         if redo:
             # The first action token is read off the LAST prompt row.  That row sees every key of the bidirectional prefix, i.e.
             # exactly what a decode step at slot P-1 sees, so it is evaluated once more as a decode step on the hi/lo chain
@@ -826,14 +826,14 @@ class SpatialVLAEngine:
             lg = self.action_logits(rows, B)
             if logs is not None:
                 logs.append(lg)
-            ops.argmax_rows(lg, toks[:, step], id_offset=self.act_lo)
+            ops.argmax_rows(lg, toks_t[step], id_offset=self.act_lo)
             if step == n_new - 1:
                 break
-            feed = toks[:, step:step + 1] if forced_tokens is None else forced_tokens[:, step:step + 1]
-            x, _ = self.embed(feed.contiguous())
+            feed = toks_t[step].view(B, 1) if forced_tokens is None else forced_tokens[:, step:step + 1].contiguous()
+            x, _ = self.embed(feed)
             rows = self.gemma_forward(x, B, 1, cache, bidirectional=False, pads=pads, hilo_out=True)
         self.last_status = status
-        return toks
+        return toks_t.t().contiguous()                       # [B, n_new]
 
     def generate_reference(self, ids, px, intrinsic, max_new_tokens, eos_id, pad_id, pads=None):
         """The reference's own decoding rule (model/modeling_spatialvla.py:484-492: HF greedy `generate(max_new_tokens=256,
